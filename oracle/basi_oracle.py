@@ -1,0 +1,413 @@
+"""CPU oracle for the BAIS PSPNet hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module is a from-the-source restatement (numpy + PyTorch-CPU) of what the
+reference computes on its hot path.  It is the *checker*: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``instance-segment-basi_b200/``
+(the product) imports it.
+
+PARITY UNPINNED.  The reference's arithmetic lives in TensorFlow 1.x, which is
+third-party, un-vendored and un-pinned (no requirements file; TF1 is implied by
+``tf.contrib.slim`` / ``tf.placeholder``), it cannot be imported in this
+container, and the reference ships no test, golden vector or fixture for this
+path.  The oracle therefore follows the reference's
+own call sites plus the published TF1 op semantics, and is pinned only by
+hand-computed known-answer cases and fp64 finite-difference checks
+(tests/test_oracle.py).
+
+What each function restates (paths relative to /root/reference):
+
+* ``mask_gaussian``          back/2AddClass/BAISData.py:189-202 (sigma=30),
+                             back/5COCO/BAISData.py:405-417 (sigma=20)
+* ``pack_input``             back/2AddClass/BAISData.py:79-80
+* ``encode_labels_border``   back/4BorderClass/BAISData.py:143-165
+* ``conv2d`` / ``atrous``    back/2AddClass/BAISPSPNet.py:118-146 (tf.nn.conv2d /
+                             tf.pad + tf.nn.atrous_conv2d, NHWC, HWIO weights)
+* ``batch_norm``             back/2AddClass/BAISPSPNet.py:204-236 (training=True always)
+* ``max_pool_3x3_s2_same``   back/2AddClass/BAISPSPNet.py:152-155, used at :269
+* ``avg_pool``               back/2AddClass/BAISPSPNet.py:157-160
+* ``resize_bilinear_ac``     back/2AddClass/BAISPSPNet.py:242-244 (align_corners=True)
+* ``resize_bilinear_legacy`` back/4BorderClass/BAISRunnerGUI.py:30 (TF1 default)
+* ``pspnet_forward``         back/2AddClass/BAISPSPNet.py:260-734 and the head
+                             variants 4BorderClass/BAISPSPNet.py:716-737,
+                             5COCO/BAISPSPNet.py:716-737
+* ``losses`` / ``train_step``back/{1NoClass,2AddClass,4BorderClass,5COCO}/BAISRunnerTrain.py
+                             build_net (loss, poly LR, plain SGD)
+* ``predict_*``              back/2AddClass/BAISRunnerTrain.py:88-89,
+                             back/4BorderClass/BAISRunnerOne.py:40-45,
+                             back/4BorderClass/BAISRunnerGUI.py:29-34,84
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+
+# --------------------------------------------------------------------------
+# A1 / A2 / A3: host-side data path
+# --------------------------------------------------------------------------
+
+
+def mask_gaussian(image_size, where, sigma=30):
+    """Gaussian click map, float64 math rounded once to float32."""
+    x = np.arange(0, image_size[1], 1, float)
+    y = np.arange(0, image_size[0], 1, float)[:, np.newaxis]
+    x0, y0 = where[1], where[0]
+    return np.exp(-4 * np.log(2) * ((x - x0) ** 2 + (y - y0) ** 2) / sigma ** 2).astype(np.float32)
+
+
+def pack_input(image_u8, where, sigma=30):
+    """uint8 HxWx3 image + click -> float32 HxWx4 (image/255 in float32, click map)."""
+    img = np.asarray(image_u8, dtype=np.float32)
+    img /= 255
+    m = mask_gaussian(img.shape[:2], where, sigma)
+    return np.concatenate((img, np.expand_dims(m, 2)), 2)
+
+
+def encode_labels_border(ann_u8, num):
+    """4-class label map of the 4BorderClass snapshot (has_255=True branch).
+
+    ann_u8: uint8 instance-id map (0 background, 255 border, k instance k).
+    Result: 0 other instance, 1 the attended instance, 2 border, 3 background --
+    including the uint8 wrap-around of (0 - 1) // 84 == 3.
+    """
+    ann = np.asarray(ann_u8, dtype=np.uint8)
+    ann = np.where(ann == 255, 171, ann).astype(np.uint8)
+    one = np.where(ann == num, 85, ann).astype(np.uint8)
+    return ((one - np.uint8(1)) // np.uint8(84)).astype(np.uint8)
+
+
+def encode_labels_binary(ann_u8, num):
+    return np.where(np.asarray(ann_u8) == num, 1, 0)
+
+
+# --------------------------------------------------------------------------
+# TF1 op semantics on NCHW torch tensors
+# --------------------------------------------------------------------------
+
+
+def tf_same_pad(n_in, k, s, d=1):
+    keff = (k - 1) * d + 1
+    n_out = -(-n_in // s)
+    total = max((n_out - 1) * s + keff - n_in, 0)
+    return total // 2, total - total // 2
+
+
+def conv2d(x, w_hwio, stride=1, padding="VALID", dilation=1, bias=None):
+    """tf.nn.conv2d / atrous_conv2d.  x: NCHW, w: [kh,kw,Cin,Cout]."""
+    w = w_hwio.permute(3, 2, 0, 1)
+    kh, kw = w_hwio.shape[0], w_hwio.shape[1]
+    if padding == "SAME":
+        pt, pb = tf_same_pad(x.shape[2], kh, stride, dilation)
+        pl, pr = tf_same_pad(x.shape[3], kw, stride, dilation)
+        x = F.pad(x, (pl, pr, pt, pb))
+    elif isinstance(padding, int):
+        x = F.pad(x, (padding,) * 4)
+    return F.conv2d(x, w, bias, stride=stride, dilation=dilation)
+
+
+def batch_norm(x, gamma, beta, relu=False, eps=BN_EPS):
+    """tf.layers.batch_normalization(training=True): batch mean, biased variance."""
+    mean = x.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((x - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    y = (x - mean) * torch.rsqrt(var + eps) * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    return F.relu(y) if relu else y
+
+
+def max_pool_3x3_s2_same(x):
+    pt, pb = tf_same_pad(x.shape[2], 3, 2)
+    pl, pr = tf_same_pad(x.shape[3], 3, 2)
+    x = F.pad(x, (pl, pr, pt, pb), value=float("-inf"))
+    return F.max_pool2d(x, 3, 2)
+
+
+def avg_pool(x, k):
+    return F.avg_pool2d(x, k, k)
+
+
+def resize_bilinear_ac(x, size):
+    return F.interpolate(x, size=tuple(size), mode="bilinear", align_corners=True)
+
+
+def resize_bilinear_legacy(x, size):
+    """TF1 resize_bilinear(align_corners=False): src = dst * in/out, no half-pixel offset."""
+    n, c, h, w = x.shape
+    oh, ow = size
+
+    def axis(n_in, n_out):
+        src = torch.arange(n_out, dtype=x.dtype) * (n_in / n_out)
+        lo = src.floor().long().clamp(max=n_in - 1)
+        hi = (lo + 1).clamp(max=n_in - 1)
+        return lo, hi, src - lo.to(x.dtype)
+
+    y0, y1, fy = axis(h, oh)
+    x0, x1, fx = axis(w, ow)
+    top = x[:, :, y0][:, :, :, x0] * (1 - fx) + x[:, :, y0][:, :, :, x1] * fx
+    bot = x[:, :, y1][:, :, :, x0] * (1 - fx) + x[:, :, y1][:, :, :, x1] * fx
+    return top * (1 - fy).view(1, 1, -1, 1) + bot * fy.view(1, 1, -1, 1)
+
+
+def resize_nearest(x, size):
+    n, c, h, w = x.shape
+    oh, ow = size
+    yi = torch.clamp((torch.arange(oh) * (h / oh)).floor().long(), max=h - 1)
+    xi = torch.clamp((torch.arange(ow) * (w / ow)).floor().long(), max=w - 1)
+    return x[:, :, yi][:, :, :, xi]
+
+
+def weighted_cross_entropy_with_logits(targets, logits, pos_weight):
+    z, x, q = targets, logits, pos_weight
+    return (1 - z) * x + (1 + (q - 1) * z) * (torch.log1p(torch.exp(-x.abs())) + F.relu(-x))
+
+
+# --------------------------------------------------------------------------
+# Variants, parameter inventory, init
+# --------------------------------------------------------------------------
+
+VARIANTS = {
+    # name: (segment head layer, class fc layer, has class head, seg loss kind)
+    "1NoClass": ("conv6_n", None, False, "bce"),
+    "2AddClass": ("conv6_n", "class_attention_fc", True, "bce"),
+    "3ThreeClass": ("conv6_n_3", "class_attention_fc", True, "softmax"),
+    "4BorderClass": ("conv6_n_4", "class_attention_fc", True, "softmax"),
+    "5COCO": ("conv6_n_3_coco", "class_attention_fc_coco", True, "softmax"),
+}
+
+STAGES = ((2, 3, 1, 1, 1), (3, 4, 2, 2, 1), (4, 23, 4, 1, 2), (5, 3, 8, 1, 4))  # (stage, blocks, mid/F, stride, dilation)
+PSP_LEVELS = (1, 2, 3, 6)
+
+
+def param_specs(variant="2AddClass", num_classes=21, num_segment=1, filter_number=32):
+    """Ordered {tf variable name: shape} for the PSPNet lineage (HWIO conv weights)."""
+    seg_name, fc_name, has_class, _ = VARIANTS[variant]
+    Fn = filter_number
+    specs = OrderedDict()
+
+    def conv(name, k, cin, cout, biased=False):
+        specs[name + "/weights"] = (k, k, cin, cout)
+        if biased:
+            specs[name + "/biases"] = (cout,)
+
+    def bn(name, c):
+        specs["%s/%s/gamma" % (name, name)] = (c,)
+        specs["%s/%s/beta" % (name, name)] = (c,)
+
+    conv("conv1_1_3x3_s2_n", 3, 4, Fn); bn("conv1_1_3x3_s2_bn", Fn)
+    conv("conv1_2_3x3", 3, Fn, Fn); bn("conv1_2_3x3_bn", Fn)
+    conv("conv1_3_3x3", 3, Fn, 2 * Fn); bn("conv1_3_3x3_bn", 2 * Fn)
+    cin = 2 * Fn
+    for stage, blocks, mult, _, _ in STAGES:
+        mid, out = mult * Fn, 4 * mult * Fn
+        for b in range(1, blocks + 1):
+            p = "conv%d_%d" % (stage, b)
+            if b == 1:
+                conv(p + "_1x1_proj", 1, cin, out); bn(p + "_1x1_proj_bn", out)
+            conv(p + "_1x1_reduce", 1, cin, mid); bn(p + "_1x1_reduce_bn", mid)
+            conv(p + "_3x3", 3, mid, mid); bn(p + "_3x3_bn", mid)
+            conv(p + "_1x1_increase", 1, mid, out); bn(p + "_1x1_increase_bn", out)
+            cin = out
+    psp = cin // 4
+    for lvl in PSP_LEVELS:
+        conv("conv5_3_pool%d_conv" % lvl, 1, cin, psp); bn("conv5_3_pool%d_conv_bn" % lvl, psp)
+    conv("conv5_4", 3, 2 * cin, psp); bn("conv5_4_bn", psp)
+    conv(seg_name, 1, psp, num_segment, biased=True)
+    if has_class:
+        conv("class_attention_conv", 5, cin, 16 * Fn, biased=True)
+        specs[fc_name + "/weights"] = (16 * Fn, num_classes)
+        specs[fc_name + "/biases"] = (num_classes,)
+    return specs
+
+
+def init_params(specs, seed=0, dtype=np.float32, trained_like=False):
+    """glorot_uniform for weights and biases (tf.get_variable default), gamma=1, beta=0.
+
+    trained_like=True perturbs gamma/beta so that parity tests do not run on the
+    degenerate gamma=1/beta=0 point (SURVEY section 7 'hard parts').
+    """
+    rng = np.random.RandomState(seed)
+    out = OrderedDict()
+    for name, shape in specs.items():
+        if name.endswith("/gamma"):
+            v = np.ones(shape) if not trained_like else rng.uniform(0.5, 1.5, shape)
+        elif name.endswith("/beta"):
+            v = np.zeros(shape) if not trained_like else rng.uniform(-0.3, 0.3, shape)
+        else:
+            if len(shape) == 4:
+                fan_in, fan_out = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
+            elif len(shape) == 2:
+                fan_in, fan_out = shape
+            else:
+                fan_in = fan_out = shape[0]
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            v = rng.uniform(-lim, lim, shape)
+        out[name] = np.ascontiguousarray(v, dtype=dtype)
+    return out
+
+
+# --------------------------------------------------------------------------
+# A4..A11: network forward
+# --------------------------------------------------------------------------
+
+
+def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_pool_size=40,
+                   attention_channel=None, keep=()):
+    """Forward pass.  params: {tf name: torch tensor}; data: [B,S,S,4] torch tensor (NHWC).
+
+    Returns dict with NHWC tensors: the segment logits under the variant's head
+    name, class logits (if any) and any layer named in ``keep``.
+    """
+    seg_name, fc_name, has_class, _ = VARIANTS[variant]
+    if attention_channel is None:
+        attention_channel = {"3ThreeClass": 1, "4BorderClass": 1, "5COCO": 2}.get(variant, 0)
+    L = {}
+
+    def W(n):
+        return params[n + "/weights"]
+
+    def BN(x, n, relu):
+        return batch_norm(x, params["%s/%s/gamma" % (n, n)], params["%s/%s/beta" % (n, n)], relu)
+
+    x = data_nhwc.permute(0, 3, 1, 2)
+    x = F.relu(BN(conv2d(x, W("conv1_1_3x3_s2_n"), 2, "SAME"), "conv1_1_3x3_s2_bn", False))
+    x = BN(conv2d(x, W("conv1_2_3x3"), 1, "SAME"), "conv1_2_3x3_bn", True)
+    x = BN(conv2d(x, W("conv1_3_3x3"), 1, "SAME"), "conv1_3_3x3_bn", True)
+    L["conv1_3_3x3_bn"] = x
+    x = max_pool_3x3_s2_same(x)
+    L["pool1_3x3_s2"] = x
+    for stage, blocks, _, stride, dil in STAGES:
+        for b in range(1, blocks + 1):
+            p = "conv%d_%d" % (stage, b)
+            s = stride if b == 1 else 1
+            if b == 1:
+                sc = BN(conv2d(x, W(p + "_1x1_proj"), s), p + "_1x1_proj_bn", False)
+            else:
+                sc = x
+            y = BN(conv2d(x, W(p + "_1x1_reduce"), s), p + "_1x1_reduce_bn", True)
+            y = BN(conv2d(y, W(p + "_3x3"), 1, dil, dil), p + "_3x3_bn", True)   # tf.pad(d) + (atrous) VALID
+            y = BN(conv2d(y, W(p + "_1x1_increase"), 1), p + "_1x1_increase_bn", False)
+            pre = sc + y
+            x = F.relu(pre)
+            L[p] = pre
+            L[p + "/relu"] = x
+    c53 = x
+    P = last_pool_size
+    size = c53.shape[2:4]
+    branches = {}
+    for lvl in PSP_LEVELS:
+        k = P // lvl
+        n = "conv5_3_pool%d" % lvl
+        y = avg_pool(c53, k)
+        y = BN(conv2d(y, W(n + "_conv"), 1), n + "_conv_bn", True)
+        branches[lvl] = resize_bilinear_ac(y, size)
+        L[n + "_interp"] = branches[lvl]
+    cat = torch.cat([c53, branches[6], branches[3], branches[2], branches[1]], dim=1)
+    y = BN(conv2d(cat, W("conv5_4"), 1, "SAME"), "conv5_4_bn", True)
+    L["conv5_4_bn"] = y
+    seg = conv2d(y, W(seg_name), 1, bias=params[seg_name + "/biases"])
+    L[seg_name] = seg
+    if has_class:
+        gate = seg if num_segment == 1 else seg[:, attention_channel:attention_channel + 1]
+        m = F.relu(L["conv5_3"]) * gate
+        L["class_attention_multiply"] = m
+        m = avg_pool(m, P // 5)
+        m = F.relu(conv2d(m, W("class_attention_conv"), 5, bias=params["class_attention_conv/biases"]))
+        assert m.shape[2] == 1 and m.shape[3] == 1, "class head expects a 1x1 map after the 5x5/s5 conv"
+        m = m[:, :, 0, 0]
+        L[fc_name] = m @ params[fc_name + "/weights"] + params[fc_name + "/biases"]
+    out = {seg_name: L[seg_name].permute(0, 2, 3, 1)}
+    if has_class:
+        out[fc_name] = L[fc_name]
+    for k_ in keep:
+        v = L[k_]
+        out[k_] = v.permute(0, 2, 3, 1) if v.dim() == 4 else v
+    return out
+
+
+# --------------------------------------------------------------------------
+# A15..A18: losses, SGD, predictions
+# --------------------------------------------------------------------------
+
+
+def losses(seg_logits_nhwc, cls_logits, label_seg, label_cls, variant="2AddClass", pos_weight=3.0,
+           class_weight=0.2):
+    """(loss, loss_segment, loss_classes) exactly as build_net composes them."""
+    _, _, has_class, kind = VARIANTS[variant]
+    nseg = seg_logits_nhwc.shape[-1]
+    if kind == "bce":
+        pred = seg_logits_nhwc.reshape(-1)
+        lab = label_seg.reshape(-1).to(pred.dtype)
+        loss_seg = weighted_cross_entropy_with_logits(lab, pred, pos_weight).mean()
+    else:
+        pred = seg_logits_nhwc.reshape(-1, nseg)
+        loss_seg = F.cross_entropy(pred, label_seg.reshape(-1).long(), reduction="mean")
+    if has_class:
+        loss_cls = F.cross_entropy(cls_logits, label_cls.long(), reduction="mean")
+        return loss_seg + class_weight * loss_cls, loss_seg, loss_cls
+    return loss_seg, loss_seg, torch.zeros((), dtype=loss_seg.dtype)
+
+
+def poly_lr(base_lr, step, num_steps, power=0.9):
+    """float32 arithmetic like the TF graph (step fed as float32)."""
+    s = np.float32(step) / np.float32(num_steps)
+    return np.float32(base_lr) * np.power(np.float32(1) - s, np.float32(power))
+
+
+def to_torch(params, dtype=torch.float32, requires_grad=False):
+    out = OrderedDict()
+    for k, v in params.items():
+        t = torch.tensor(np.asarray(v), dtype=dtype)
+        t.requires_grad_(requires_grad)
+        out[k] = t
+    return out
+
+
+def train_step(params_np, data_nhwc, label_seg, label_cls, variant="2AddClass", num_segment=1,
+               last_pool_size=40, pos_weight=3.0, class_weight=0.2, lr=5e-3, dtype=torch.float32,
+               attention_channel=None, keep=()):
+    """One forward/backward/SGD step.  Returns dict(loss.., logits.., grads, new_params)."""
+    seg_name, fc_name, has_class, _ = VARIANTS[variant]
+    p = to_torch(params_np, dtype, requires_grad=True)
+    x = torch.as_tensor(np.asarray(data_nhwc)).to(dtype)
+    out = pspnet_forward(p, x, variant, num_segment, last_pool_size, attention_channel, keep)
+    lab = torch.as_tensor(np.asarray(label_seg))
+    cls = torch.as_tensor(np.asarray(label_cls)) if has_class else None
+    loss, lseg, lcls = losses(out[seg_name], out.get(fc_name), lab, cls, variant, pos_weight, class_weight)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    g = OrderedDict()
+    new = OrderedDict()
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(p[n]) if gr is None else gr
+        g[n] = gr.detach().numpy()
+        new[n] = (p[n].detach() - torch.tensor(lr, dtype=dtype) * gr).numpy()
+    res = {"loss": float(loss.detach()), "loss_segment": float(lseg.detach()), "loss_classes": float(lcls.detach()),
+           "seg_logits": out[seg_name].detach().numpy(), "grads": g, "new_params": new}
+    if has_class:
+        res["cls_logits"] = out[fc_name].detach().numpy()
+    for k_ in keep:
+        res[k_] = out[k_].detach().numpy()
+    return res
+
+
+def predict_train(seg_logits, cls_logits=None):
+    """Training-time predictions: binary head thresholds the *logits* at 0.5; multi-class argmax."""
+    if seg_logits.shape[-1] == 1:
+        pred = (seg_logits > 0.5).astype(np.int32)
+    else:
+        pred = np.argmax(seg_logits, axis=-1).astype(np.int32)[..., None]
+    cls = None if cls_logits is None else np.argmax(cls_logits, axis=-1).astype(np.int32)
+    return pred, cls
+
+
+def predict_click(seg_logits_nhwc, input_size=None):
+    """Runner / RunnerGUI mask: argmax(sigmoid(logits)) (optionally after the legacy upsample)."""
+    x = torch.as_tensor(np.asarray(seg_logits_nhwc), dtype=torch.float32).permute(0, 3, 1, 2)
+    if input_size is not None:
+        x = resize_bilinear_legacy(x, input_size)
+    s = torch.sigmoid(x)
+    return torch.argmax(s, dim=1).numpy().astype(np.int64)
