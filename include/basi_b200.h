@@ -1,0 +1,184 @@
+/*
+ * basi_b200.h -- C ABI of the B200-native BAIS PSPNet hot path.
+ *
+ * The reference (alisure-ml/Instance-Segment-BASI) has no FFI: the boundary its
+ * hot path sits behind is tf.Session.run(fetches, feed_dict)
+ *   train     back/2AddClass/BAISRunnerTrain.py:158-168
+ *   inference back/4BorderClass/BAISRunnerOne.py:53-55, BAISRunnerGUI.py:75-76
+ * and every TF op reached from there (call sites in back/2AddClass/BAISPSPNet.py:118-253).
+ * Each entry point below replaces one of those TF call sites (cited per function) so
+ * that a ctypes stub inside the reference's Network / Train / Runner classes can call
+ * it.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - every data pointer is a DEVICE pointer owned by the caller; nothing is allocated
+ *    or freed inside except through basi_tc_conv_create / _destroy.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host
+ *    synchronisation happens inside (safe under CUDA-graph capture).
+ *  - return value: 0 on success, a negative BASI_E_* code otherwise;
+ *    basi_last_error() gives the text for the calling thread.
+ *  - activations are NHWC; `ld` is the element distance between two consecutive pixels
+ *    (== c for a dense tensor, larger for a channel slice of the PSP concat buffer).
+ *  - convolution weights are HWIO float32 ([kh][kw][Cin][Cout]), the TF variable layout.
+ */
+#ifndef BASI_B200_H_
+#define BASI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BASI_OK 0
+#define BASI_E_INVALID (-1)  /* bad argument / unsupported shape */
+#define BASI_E_CUDA (-2)     /* CUDA runtime error, see basi_last_error() */
+#define BASI_E_NOGPU (-3)    /* no usable sm_100 device */
+
+#define BASI_F32 0
+#define BASI_BF16 1
+
+typedef struct basi_tensor {
+  void* ptr;     /* device pointer to element (0,0,0,0) */
+  int32_t n, h, w, c;
+  int32_t ld;    /* elements between consecutive pixels (>= c) */
+  int32_t dtype; /* BASI_F32 | BASI_BF16 */
+} basi_tensor;
+
+/* tf.nn.conv2d / tf.pad + tf.nn.atrous_conv2d geometry (BAISPSPNet.py:118-146).
+ * TF 'SAME' is expressed by the caller as explicit pad_t / pad_l (the "before" pads);
+ * bottom/right padding is implied by the output size. */
+typedef struct basi_conv_desc {
+  int32_t kh, kw;
+  int32_t stride;
+  int32_t dil;
+  int32_t pad_t, pad_l;
+  int32_t relu; /* fuse ReLU into the fprop epilogue (class_attention_conv) */
+} basi_conv_desc;
+
+const char* basi_last_error(void);
+int basi_version(void);
+/* number of SMs of the current device (148 on B200), negative on error */
+int basi_sm_count(void);
+int basi_memset(void* ptr, int value, int64_t bytes, void* stream);
+
+/* ---- A1/A2: Data._mask_gaussian + np.concatenate (back/2AddClass/BAISData.py:189-202, :79-80) ----
+ * img: uint8 [B,H,W,3] (img_is_f32 = 0) or float32 [B,H,W,3] already /255 (img_is_f32 = 1).
+ * clicks: int32 [B][2] = (y0, x0).  lut: float32 table indexed by d2 = (x-x0)^2 + (y-y0)^2,
+ * built on the host in float64 and rounded once (bit-exact with the numpy expression).
+ * out: float32 [B,H,W,4]. */
+int basi_clickmap_pack(const void* img, int img_is_f32, const int32_t* clicks, const float* lut,
+                       int64_t lut_len, float* out, int B, int H, int W, void* stream);
+
+/* ---- A4/A5: Network.conv / Network.atrous_conv (BAISPSPNet.py:122-146) ----
+ * Generic CUDA-core implicit-GEMM path (fp32 accumulate); x/y may be f32 or bf16. */
+int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* w, const float* bias,
+                    const basi_tensor* y, void* stream);
+/* adjoint w.r.t. the input (what tf.gradients derives for train_op, BAISRunnerTrain.py:117).
+ * accumulate != 0: dx += result. */
+int basi_conv_dgrad(const basi_conv_desc* d, const basi_tensor* dy, const float* w, const basi_tensor* dx,
+                    int accumulate, void* stream);
+/* adjoint w.r.t. the HWIO weights; ADDS into dw (and dbias when non-NULL). */
+int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* dy, float* dw,
+                    float* dbias, void* stream);
+
+/* ---- A6/A7: Network.batch_normalization (+relu, +add) (BAISPSPNet.py:204-236, :148-150, :171-173) ----
+ * sums: double [2*C] (sum x, sum x^2), ADDED into (caller zeroes). */
+int basi_bn_stats(const basi_tensor* x, double* sums, void* stream);
+/* bnp: float [4*C] = [mean | istd | gamma*istd | beta] (batch mean, biased variance, eps inside sqrt). */
+int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, double count, float eps,
+                     float* bnp, int C, void* stream);
+/* out = act((x-mean)*scale+beta [+ res | + (res-res_mean)*res_scale+res_beta]); res / res_bnp may be NULL. */
+int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp,
+                  int relu, const basi_tensor* out, void* stream);
+/* dsums (double [2*C]) += (sum dy, sum dy*xhat), dy = dout * (out > 0) when out != NULL. */
+int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
+                       double* dsums, void* stream);
+/* dgamma += sum dy*xhat, dbeta += sum dy; coef: float [2*C] = dsums / count. */
+int basi_bn_bwd_finalize(const double* dsums, double count, float* dgamma, float* dbeta, float* coef, int C,
+                         void* stream);
+/* dx = gamma*istd*(dy - coef0 - xhat*coef1); dres (optional) (+)= dy. */
+int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
+                      const float* coef, const basi_tensor* dx, const basi_tensor* dres, int dres_accumulate,
+                      void* stream);
+
+/* ---- A8: Network.max_pool 3x3 s2 SAME (:152-155, :269), Network.avg_pool k=s VALID (:157-160) ---- */
+int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream);
+int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,
+                        void* stream);
+int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* stream);
+int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int accumulate, void* stream);
+
+/* ---- A9: Network.resize_bilinear, align_corners=True (:242-244) ---- */
+int basi_bilinear_ac_fwd(const basi_tensor* x, const basi_tensor* y, void* stream);
+int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream);
+
+/* ---- A11: Network.multiply (relu(conv5_3) * logits[..., att]) (:246-249; 4BorderClass :246-252) ----
+ * logits: float32 [n,h,w,nseg].  out = relu(feat) * logits[...,att]. */
+int basi_gate_mul_fwd(const basi_tensor* feat, const float* logits, int nseg, int att, const basi_tensor* out,
+                      void* stream);
+/* dfeat (+)= dout*gate*(feat>0);  dlogits[...,att] += sum_c dout*relu(feat). */
+int basi_gate_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const float* logits, int nseg, int att,
+                      const basi_tensor* dfeat, int dfeat_accumulate, float* dlogits, void* stream);
+
+/* ---- A11: class_attention_conv (5x5 s5 on a 5x5 map) and Network.fc (:175-189) as skinny GEMMs ----
+ * y[m][n] = act(sum_k a[m][k] w[k][n] + bias[n]), m <= 64. a may be f32/bf16 (dtype_a), y float32. */
+int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,
+                    int M, int K, int N, int relu, void* stream);
+/* da[m][k] (+)= sum_n dy[m][n] w[k][n]   (da dtype_a) */
+int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, int64_t lda, int M, int K, int N,
+                      int accumulate, void* stream);
+/* dw[k][n] += sum_m a[m][k] dy[m][n]; dbias[n] += sum_m dy[m][n] */
+int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, float* dw, float* dbias, int M,
+                      int K, int N, void* stream);
+/* dy *= (y > 0)  (ReLU adjoint for the skinny path), n elements float32 */
+int basi_relu_bwd_f32(float* dy, const float* y, int64_t n, void* stream);
+
+/* ---- A15: tf.reduce_mean(weighted_cross_entropy_with_logits) (2AddClass/BAISRunnerTrain.py:104-105) ----
+ * loss_acc[0] += scale * sum(loss_i) (double);  dlogits = grad_scale * dloss_i/dx. */
+int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight, double scale,
+                      float grad_scale, int64_t n, double* loss_acc, float* dlogits, void* stream);
+/* ---- A15/A16: tf.reduce_mean(sparse_softmax_cross_entropy_with_logits) (4BorderClass :111-116) ---- */
+int basi_softmax_ce_fwd_bwd(const float* logits, const int32_t* labels, int64_t rows, int C, double scale,
+                            float grad_scale, double* loss_acc, float* dlogits, void* stream);
+
+/* ---- A17: GradientDescentOptimizer (2AddClass/BAISRunnerTrain.py:115-117): w -= lr*g ----
+ * lr is read from device memory so a captured graph can be replayed with a new rate.
+ * w_bf16 (optional) receives the bf16 copy of the updated weights. */
+int basi_sgd_step(float* w, const float* g, const float* lr_dev, int64_t n, void* w_bf16, void* stream);
+
+/* ---- A18: predictions ---- */
+/* out = logits > thr (2AddClass/BAISRunnerTrain.py:88) */
+int basi_threshold(const float* logits, float thr, int32_t* out, int64_t n, void* stream);
+/* first-max argmax over the last axis (BAISRunnerOne.py:41-45) */
+int basi_argmax(const float* logits, int64_t rows, int C, int32_t* out, void* stream);
+/* TF1 resize_bilinear(align_corners=False) to SxS then argmax(sigmoid) (BAISRunnerGUI.py:29-31) */
+int basi_upsample_legacy_argmax(const float* logits, int B, int P_h, int P_w, int C, int S_h, int S_w,
+                                int32_t* out, void* stream);
+/* dst[i] = (bf16) src[i] / (f32) src[i] helpers */
+int basi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int basi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+
+/* ---- tcgen05 / TMEM / TMA implicit-GEMM convolutions (bf16 in, fp32 accumulate) ----
+ * One plan per (layer, pass); owns the TMA descriptors for fixed device pointers.
+ * kind: 0 fprop (y = conv(x,w)), 1 dgrad (dx = conv^T(dy,w)), 2 wgrad (dw += x^T dy).
+ * Weights are bf16 copies produced by basi_tc_pack_weights. */
+#define BASI_TC_FPROP 0
+#define BASI_TC_DGRAD 1
+#define BASI_TC_WGRAD 2
+typedef struct basi_tc_conv basi_tc_conv;
+/* returns 1 if the tcgen05 path supports this geometry / channel counts, else 0 */
+int basi_tc_conv_supported(int kind, const basi_conv_desc* d, const basi_tensor* in, const basi_tensor* out);
+/* w_hwio f32 [taps][Cin][Cout] -> bf16 [taps][Cin][Cout] and bf16 [taps][Cout][Cin] */
+int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int taps, int cin, int cout,
+                         void* stream);
+int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
+                        const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out);
+int basi_tc_conv_run(basi_tc_conv* plan, void* stream);
+void basi_tc_conv_destroy(basi_tc_conv* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASI_B200_H_ */

@@ -1,0 +1,124 @@
+"""ctypes binding of libbasi_b200.so (the C ABI declared in include/basi_b200.h).
+
+There is no CPU fallback: every call goes to the CUDA library, and a missing
+library or a failing call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbasi_b200.so")
+
+F32, BF16 = 0, 1
+TC_FPROP, TC_DGRAD, TC_WGRAD = 0, 1, 2
+
+
+class BasiError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("ld", C.c_int32), ("dtype", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("dil", C.c_int32),
+                ("pad_t", C.c_int32), ("pad_l", C.c_int32), ("relu", C.c_int32)]
+
+
+_P = C.c_void_p
+_TP = C.POINTER(Tensor)
+_DP = C.POINTER(ConvDesc)
+_i, _i64, _f, _d = C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> argtypes.  Every symbol include/basi_b200.h declares is listed here; tests check the two agree.
+SIGNATURES = {
+    "basi_memset": [_P, _i, _i64, _P],
+    "basi_clickmap_pack": [_P, _i, _P, _P, _i64, _P, _i, _i, _i, _P],
+    "basi_conv_fprop": [_DP, _TP, _P, _P, _TP, _P],
+    "basi_conv_dgrad": [_DP, _TP, _P, _TP, _i, _P],
+    "basi_conv_wgrad": [_DP, _TP, _TP, _P, _P, _P],
+    "basi_bn_stats": [_TP, _P, _P],
+    "basi_bn_finalize": [_P, _P, _P, _d, _f, _P, _i, _P],
+    "basi_bn_apply": [_TP, _P, _TP, _P, _i, _TP, _P],
+    "basi_bn_bwd_reduce": [_TP, _TP, _TP, _P, _P, _P],
+    "basi_bn_bwd_finalize": [_P, _d, _P, _P, _P, _i, _P],
+    "basi_bn_bwd_apply": [_TP, _TP, _TP, _P, _P, _TP, _TP, _i, _P],
+    "basi_maxpool3s2_fwd": [_TP, _TP, _P, _P],
+    "basi_maxpool3s2_bwd": [_TP, _P, _TP, _i, _P],
+    "basi_avgpool_fwd": [_TP, _i, _TP, _P],
+    "basi_avgpool_bwd": [_TP, _i, _TP, _i, _P],
+    "basi_bilinear_ac_fwd": [_TP, _TP, _P],
+    "basi_bilinear_ac_bwd": [_TP, _TP, _i, _P],
+    "basi_gate_mul_fwd": [_TP, _P, _i, _i, _TP, _P],
+    "basi_gate_mul_bwd": [_TP, _TP, _P, _i, _i, _TP, _i, _P, _P],
+    "basi_skinny_fwd": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _i, _P],
+    "basi_skinny_dgrad": [_P, _P, _P, _i, _i64, _i, _i, _i, _i, _P],
+    "basi_skinny_wgrad": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _P],
+    "basi_relu_bwd_f32": [_P, _P, _i64, _P],
+    "basi_wbce_fwd_bwd": [_P, _P, _f, _d, _f, _i64, _P, _P, _P],
+    "basi_softmax_ce_fwd_bwd": [_P, _P, _i64, _i, _d, _f, _P, _P, _P],
+    "basi_sgd_step": [_P, _P, _P, _i64, _P, _P],
+    "basi_threshold": [_P, _f, _P, _i64, _P],
+    "basi_argmax": [_P, _i64, _i, _P, _P],
+    "basi_upsample_legacy_argmax": [_P, _i, _i, _i, _i, _i, _i, _P, _P],
+    "basi_cast_f32_to_bf16": [_P, _P, _i64, _P],
+    "basi_cast_bf16_to_f32": [_P, _P, _i64, _P],
+    "basi_tc_conv_supported": [_i, _DP, _TP, _TP],
+    "basi_tc_pack_weights": [_P, _P, _P, _i, _i, _i, _P],
+    "basi_tc_conv_create": [_i, _DP, _TP, _TP, _P, _P, _i, C.POINTER(_P)],
+    "basi_tc_conv_run": [_P, _P],
+}
+_NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
+            "basi_tc_conv_destroy": ([_P], None)}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raises BasiError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BasiError("libbasi_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or instance-segment-basi_b200/csrc/build.sh)")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i
+    for name, (args, res) in _NOCHECK.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(SIGNATURES) + list(_NOCHECK)
+
+
+LAUNCHES = 0  # number of C-ABI compute calls issued (each enqueues >= 1 of our kernels)
+
+
+def call(name, *args):
+    global LAUNCHES
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    LAUNCHES += 1
+    if rc != 0:
+        raise BasiError("%s failed (%d): %s" % (name, rc, lib.basi_last_error().decode()))
+    return rc
+
+
+def last_error():
+    return load().basi_last_error().decode()
+
+
+def sm_count():
+    return load().basi_sm_count()

@@ -1,0 +1,707 @@
+"""Lowers a ``Network`` graph (BAISPSPNet.py) to a static plan of C-ABI kernel calls and runs it.
+
+This is the analogue of the reference's ``tf.Session``: the graph the fluent builder recorded is
+compiled once into two flat call lists (forward, backward) over preallocated NHWC device buffers,
+with the fusions the B200 design wants:
+
+  * zero_padding + conv / atrous_conv            -> one implicit-GEMM conv with explicit pads
+  * conv -> batch_normalization[+relu]           -> conv, bn_stats, bn_finalize, bn_apply(+ReLU)
+  * add(shortcut, increase_bn) -> relu           -> one bn_apply with fused residual (and second BN) + ReLU
+  * concat                                       -> producers write straight into channel slices
+  * class_attention_conv (5x5/s5 on 5x5) and fc  -> skinny GEMMs
+  * loss forward + gradient                      -> one kernel each
+
+PyTorch is used for device memory, streams, CUDA graphs and NCCL only; every arithmetic op is one of
+our kernels reached through ``_lib.call``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Tensor
+
+_ALIGN = 64  # parameter offsets aligned to 64 floats (256 B)
+
+
+def _same_pad_before(n_in, k, s, d):
+    keff = (k - 1) * d + 1
+    n_out = -(-n_in // s)
+    total = max((n_out - 1) * s + keff - n_in, 0)
+    return total // 2
+
+
+class Act(object):
+    """A device activation (NHWC torch tensor or channel-slice view) plus its C descriptor."""
+
+    def __init__(self, t):
+        assert t.dim() == 4 and t.stride(3) == 1
+        n, h, w, c = t.shape
+        ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+        if w > 1 and h > 1:
+            assert t.stride(1) == w * ld
+        if h * w > 1 and n > 1:
+            assert t.stride(0) == h * w * ld
+        self.t = t
+        self.dtype = _lib.F32 if t.dtype == torch.float32 else _lib.BF16
+        self.desc = Tensor(t.data_ptr(), n, h, w, c, ld, self.dtype)
+        self.ref = C.byref(self.desc)
+        self.grad = None
+        self.gw = False   # plan-time flag: has a backward op already written .grad ?
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+
+class _BNRec(object):
+    __slots__ = ("x", "gamma", "beta", "sums", "dsums", "bnp", "coef", "count", "C")
+
+
+class Engine(object):
+    def __init__(self, net, batch_size, precision="bf16", training=True, loss=None, device=None, use_tc=True,
+                 dry_run=False):
+        """net: a built Network; loss: dict(kind='bce'|'softmax', pos_weight, class_weight, seg, cls).
+
+        dry_run=True only builds the plan (buffers on the host, nothing can be executed): used by the
+        CPU-side tests of the lowering."""
+        self.dry_run = bool(dry_run)
+        if self.dry_run:
+            device, use_tc = "cpu", False
+        elif not torch.cuda.is_available():
+            raise _lib.BasiError("basi_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        _lib.load()
+        self.net = net
+        self.B = int(batch_size)
+        self.precision = precision
+        self.adt = torch.float32 if precision == "f32" else torch.bfloat16
+        self.training = training
+        self.loss_cfg = loss
+        if device is None:
+            device = "cuda:%d" % torch.cuda.current_device()
+        self.device = torch.device(device)
+        self.use_tc = bool(use_tc) and precision != "f32"
+        self.fwd, self.bwd = [], []
+        self._keep = []          # ctypes objects that must outlive the plan
+        self._ops = []
+        self._tc_plans = []
+        self._tc_weights = []
+        self._zero_grads = []    # gradient buffers that are pre-zeroed every step (concat buffers)
+        self._acts = {}          # node index -> Act (or tuple for deferred bn)
+        self._graph = None
+        self.tc_layers = 0
+        self._build_params()
+        self._lower()
+        if training:
+            self._emit_backward()
+
+    # ------------------------------------------------------------------ parameters
+    def _build_params(self):
+        off = 0
+        self.param_index = OrderedDict()
+        for name, shape in self.net.variables.items():
+            n = int(np.prod(shape))
+            self.param_index[name] = (off, shape)
+            off += -(-n // _ALIGN) * _ALIGN
+        self.n_flat = off
+        self.n_params = sum(int(np.prod(s)) for _, s in self.param_index.values())
+        dev = self.device
+        self.params_flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads_flat = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def _pptr(self, name):
+        return self.params_flat.data_ptr() + 4 * self.param_index[name][0]
+
+    def _gptr(self, name):
+        return self.grads_flat.data_ptr() + 4 * self.param_index[name][0]
+
+    def param_view(self, name, grads=False):
+        off, shape = self.param_index[name]
+        flat = self.grads_flat if grads else self.params_flat
+        return flat[off:off + int(np.prod(shape))].view(*shape)
+
+    def set_params(self, params):
+        """params: {tf variable name: ndarray} (conv weights HWIO)."""
+        for name, (off, shape) in self.param_index.items():
+            if name not in params:
+                raise KeyError("missing variable %s" % name)
+            v = np.ascontiguousarray(params[name], dtype=np.float32)
+            if tuple(v.shape) != tuple(shape):
+                raise ValueError("variable %s: shape %s != %s" % (name, v.shape, shape))
+            self.param_view(name).copy_(torch.from_numpy(v))
+        self._refresh_weight_copies()
+
+    def get_params(self):
+        return OrderedDict((n, self.param_view(n).cpu().numpy().copy()) for n in self.param_index)
+
+    def get_grads(self):
+        return OrderedDict((n, self.param_view(n, True).cpu().numpy().copy()) for n in self.param_index)
+
+    def init_params(self, seed=0):
+        """glorot_uniform for weights and biases (tf.get_variable default, BAISPSPNet.py:111-113), gamma=1, beta=0."""
+        rng = np.random.RandomState(seed)
+        p = {}
+        for name, (off, shape) in self.param_index.items():
+            if name.endswith("/gamma"):
+                v = np.ones(shape)
+            elif name.endswith("/beta"):
+                v = np.zeros(shape)
+            else:
+                if len(shape) == 4:
+                    fi, fo = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
+                elif len(shape) == 2:
+                    fi, fo = shape
+                else:
+                    fi = fo = shape[0]
+                lim = np.sqrt(6.0 / (fi + fo))
+                v = rng.uniform(-lim, lim, shape)
+            p[name] = v.astype(np.float32)
+        self.set_params(p)
+
+    # ------------------------------------------------------------------ allocation helpers
+    def _alloc(self, shape, dtype=None):
+        return torch.zeros(*shape, dtype=dtype or self.adt, device=self.device)
+
+    def _new_act(self, h, w, c, dtype=None):
+        return Act(self._alloc((self.B, h, w, c), dtype))
+
+    def _grad_of(self, act):
+        if act.grad is None:
+            act.grad = Act(torch.zeros_like(act.t))
+        return act.grad
+
+    def _call(self, lst, name, *args):
+        fn = getattr(_lib.load(), name)
+        lst.append((name, fn, args))
+
+    # ------------------------------------------------------------------ lowering
+    def _lower(self):
+        net = self.net
+        B = self.B
+        nodes = net.nodes
+        cons = {n.index: [] for n in nodes}
+        for n in nodes:
+            for i in n.inputs:
+                cons[i.index].append(n)
+        self._cons = cons
+        # BN statistic scratch: [fwd sums | bwd sums] as doubles, zeroed once per step
+        tot_c = sum(n.shape[-1] for n in nodes if n.op == "batch_normalization")
+        self.bn_scratch = torch.zeros(4 * tot_c + 8, dtype=torch.float64, device=self.device)
+        self._bn_off = 0
+        # concat: producers write into slices
+        self._slice_of = {}
+        for n in nodes:
+            if n.op == "concat":
+                h, w, ctot = n.shape
+                buf = self._new_act(h, w, ctot)
+                self._acts[n.index] = buf
+                o = 0
+                for i in n.inputs:
+                    c = i.shape[2]
+                    self._slice_of[i.index] = (buf, o, c)
+                    o += c
+        self.input = None
+        self.seg_logits = None
+        self.cls_logits = None
+        for n in nodes:
+            getattr(self, "_lower_" + n.op)(n)
+        self._lower_loss()
+
+    def _out_act(self, node, dtype=None):
+        """Output buffer for a node: a concat slice when the node feeds a concat, else a fresh tensor."""
+        if node.index in self._slice_of:
+            buf, o, c = self._slice_of[node.index]
+            a = Act(buf.t[..., o:o + c])
+            if self.training:
+                if buf.grad is None:
+                    self._zero_grads.append(self._grad_of(buf))
+                a.grad = Act(buf.grad.t[..., o:o + c])
+                a.gw = True            # concat grads are pre-zeroed -> every writer accumulates
+                buf.gw = True
+            return a
+        h, w, c = node.shape
+        return self._new_act(h, w, c, dtype)
+
+    def _lower_data(self, n):
+        h, w, c = n.shape
+        self.input = Act(self._alloc((self.B, h, w, c), torch.float32))
+        self._acts[n.index] = self.input
+
+    def _lower_zero_padding(self, n):
+        self._acts[n.index] = ("pad", self._acts[n.inputs[0].index], n.attrs["pad"])
+
+    def _lower_conv(self, n):
+        a = n.attrs
+        src = self._acts[n.inputs[0].index]
+        pad = 0
+        if isinstance(src, tuple) and src[0] == "pad":
+            _, src, pad = src
+        x = src
+        k, s, d = a["k_h"], a["stride"], a["dilation"]
+        if a["padding"] == "SAME":
+            pt, pl = _same_pad_before(x.shape[1], k, s, d), _same_pad_before(x.shape[2], a["k_w"], s, d)
+        else:
+            pt = pl = pad
+        oh, ow, co = n.shape
+        followers = self._cons[n.index]
+        has_bn = any(f.op == "batch_normalization" for f in followers)
+        wname, bname = a["weights"], a["biases"]
+        # class_attention_conv pattern: 5x5/s5 over a dense 5x5 map -> skinny GEMM
+        if (k == 5 and s == 5 and x.shape[1] == 5 and x.shape[2] == 5 and pt == 0 and oh == 1 and ow == 1
+                and x.desc.ld == x.shape[3] and self.B <= 64):
+            y = Act(self._alloc((self.B, 1, 1, co), torch.float32))
+            self._acts[n.index] = y
+            self._ops.append(("skinny", dict(x=x, y=y, w=wname, b=bname, relu=bool(a["relu"]),
+                                             K=25 * x.shape[3], N=co)))
+            self._emit_skinny_fwd(self._ops[-1][1])
+            return
+        f32_out = (not has_bn)
+        y = self._out_act(n, torch.float32 if f32_out else None)
+        desc = ConvDesc(k, a["k_w"], s, d, pt, pl, 1 if (a["relu"] and not has_bn) else 0)
+        self._keep.append(desc)
+        op = dict(x=x, y=y, w=wname, b=bname, desc=desc, relu=bool(a["relu"] and not has_bn), name=n.name, tc=None)
+        self._acts[n.index] = y
+        self._ops.append(("conv", op))
+        self._emit_conv_fwd(op)
+
+    def _lower_batch_normalization(self, n):
+        x = self._acts[n.inputs[0].index]
+        rec = _BNRec()
+        rec.x, rec.gamma, rec.beta, rec.C = x, n.attrs["gamma"], n.attrs["beta"], n.shape[-1]
+        rec.count = float(x.shape[0] * x.shape[1] * x.shape[2])
+        Cc = rec.C
+        base = self.bn_scratch.data_ptr()
+        rec.sums = base + 8 * self._bn_off
+        rec.dsums = base + 8 * (self._bn_off + 2 * Cc)
+        self._bn_off += 4 * Cc
+        rec.bnp = self._alloc((4 * Cc,), torch.float32)
+        rec.coef = self._alloc((2 * Cc,), torch.float32)
+        followers = self._cons[n.index]
+        if followers and all(f.op == "add" for f in followers):
+            self._acts[n.index] = ("bn_deferred", rec)     # applied inside the junction
+            self._emit_bn_stats(rec)
+            return
+        relu = bool(n.attrs["relu"])
+        if len(followers) == 1 and followers[0].op == "relu":
+            relu = True                                      # bn(relu=False) -> relu (conv1_1)
+            out = self._out_act(followers[0])
+            self._acts[followers[0].index] = out
+        else:
+            out = self._out_act(n)
+        if not (len(followers) == 1 and followers[0].op == "relu"):
+            self._acts[n.index] = out
+        else:
+            self._acts[n.index] = ("fused_into_relu", out)
+        self._emit_bn_stats(rec)
+        op = dict(main=rec, res=None, res_bn=None, relu=relu, out=out)
+        self._ops.append(("bnact", op))
+        self._emit_bnact_fwd(op)
+
+    def _lower_relu(self, n):
+        src = n.inputs[0]
+        if src.op == "batch_normalization":
+            assert n.index in self._acts, "relu after bn must have been fused"
+            return
+        if src.op != "add":
+            raise NotImplementedError("relu after %s" % src.op)
+        ins = [self._acts[i.index] for i in src.inputs]
+        assert len(ins) == 2
+        deferred = [i for i in ins if isinstance(i, tuple) and i[0] == "bn_deferred"]
+        plain = [i for i in ins if isinstance(i, Act)]
+        if len(deferred) == 2:
+            # (proj_bn, increase_bn): main = the later one
+            res_bn, main = deferred[0][1], deferred[1][1]
+            res = res_bn.x
+        elif len(deferred) == 1 and len(plain) == 1:
+            main, res, res_bn = deferred[0][1], plain[0], None
+        else:
+            raise NotImplementedError("add of %s" % (ins,))
+        out = self._out_act(n)
+        self._acts[n.index] = out
+        self._acts[src.index] = ("pre_relu_of", out)
+        op = dict(main=main, res=res, res_bn=res_bn, relu=True, out=out)
+        self._ops.append(("bnact", op))
+        self._emit_bnact_fwd(op)
+
+    def _lower_add(self, n):
+        pass  # materialised by the following relu (junction)
+
+    def _lower_concat(self, n):
+        pass  # producers already wrote into the slices
+
+    def _lower_max_pool(self, n):
+        x = self._acts[n.inputs[0].index]
+        y = self._out_act(n)
+        amax = torch.zeros(self.B * n.shape[0] * n.shape[1] * n.shape[2], dtype=torch.uint8, device=self.device)
+        op = dict(x=x, y=y, amax=amax)
+        self._acts[n.index] = y
+        self._ops.append(("maxpool", op))
+        self._call(self.fwd, "basi_maxpool3s2_fwd", x.ref, y.ref, amax.data_ptr())
+
+    def _lower_avg_pool(self, n):
+        x = self._acts[n.inputs[0].index]
+        y = self._out_act(n)
+        op = dict(x=x, y=y, k=n.attrs["k"])
+        self._acts[n.index] = y
+        self._ops.append(("avgpool", op))
+        self._call(self.fwd, "basi_avgpool_fwd", x.ref, op["k"], y.ref)
+
+    def _lower_resize_bilinear(self, n):
+        x = self._acts[n.inputs[0].index]
+        y = self._out_act(n)
+        op = dict(x=x, y=y)
+        self._acts[n.index] = y
+        self._ops.append(("bilinear", op))
+        self._call(self.fwd, "basi_bilinear_ac_fwd", x.ref, y.ref)
+
+    def _lower_multiply(self, n):
+        feat = self._acts[n.inputs[0].index]
+        if isinstance(feat, tuple) and feat[0] == "pre_relu_of":
+            feat = feat[1]      # relu(pre) == the junction output
+        logits = self._acts[n.inputs[1].index]
+        assert logits.t.dtype == torch.float32
+        y = self._out_act(n)
+        nseg = logits.shape[3]
+        att = n.attrs["segment_place"] if nseg > 1 else 0
+        op = dict(feat=feat, logits=logits, y=y, nseg=nseg, att=att)
+        self._acts[n.index] = y
+        self._ops.append(("gate", op))
+        self._call(self.fwd, "basi_gate_mul_fwd", feat.ref, logits.t.data_ptr(), nseg, att, y.ref)
+
+    def _lower_squeeze(self, n):
+        self._acts[n.index] = self._acts[n.inputs[0].index]
+
+    def _lower_fc(self, n):
+        x = self._acts[n.inputs[0].index]
+        assert x.t.dtype == torch.float32 and x.shape[1] == 1 and x.shape[2] == 1
+        co = n.shape[0]
+        y = Act(self._alloc((self.B, 1, 1, co), torch.float32))
+        self._acts[n.index] = y
+        op = dict(x=x, y=y, w=n.attrs["weights"], b=n.attrs["biases"], relu=bool(n.attrs["relu"]),
+                  K=x.shape[3], N=co)
+        self._ops.append(("skinny", op))
+        self._emit_skinny_fwd(op)
+
+    # ---- forward emitters
+    def _emit_conv_fwd(self, op):
+        x, y = op["x"], op["y"]
+        bptr = self._pptr(op["b"]) if op["b"] else None
+        if self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]:
+            if _lib.load().basi_tc_conv_supported(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
+                self._emit_tc(op, _lib.TC_FPROP, self.fwd)
+                return
+        self._call(self.fwd, "basi_conv_fprop", C.byref(op["desc"]), x.ref, self._pptr(op["w"]), bptr, y.ref)
+
+    def _emit_bn_stats(self, rec):
+        self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums)
+        self._call(self.fwd, "basi_bn_finalize", rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
+                   C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.C)
+
+    def _emit_bnact_fwd(self, op):
+        main, res, res_bn = op["main"], op["res"], op["res_bn"]
+        self._call(self.fwd, "basi_bn_apply", main.x.ref, main.bnp.data_ptr(), res.ref if res is not None else None,
+                   res_bn.bnp.data_ptr() if res_bn is not None else None, 1 if op["relu"] else 0, op["out"].ref)
+
+    def _emit_skinny_fwd(self, op):
+        x, y = op["x"], op["y"]
+        lda = x.t.stride(0) if x.shape[0] > 1 else op["K"]
+        op["lda"] = lda
+        self._call(self.fwd, "basi_skinny_fwd", x.t.data_ptr(), x.dtype, C.c_int64(lda), self._pptr(op["w"]),
+                   self._pptr(op["b"]) if op["b"] else None, y.t.data_ptr(), self.B, op["K"], op["N"],
+                   1 if op["relu"] else 0)
+
+    # ---- loss
+    def _lower_loss(self):
+        cfg = self.loss_cfg
+        segname = (cfg or {}).get("seg")
+        if segname is None:
+            for name in ("conv6_n", "conv6_n_3", "conv6_n_4", "conv6_n_3_coco"):
+                if name in self.net.layers:
+                    segname = name
+        self.seg_name = segname
+        self.seg_logits = self._acts[self.net.layers[segname].index]
+        clsname = (cfg or {}).get("cls")
+        if clsname is None:
+            for name in ("class_attention_fc", "class_attention_fc_coco"):
+                if name in self.net.layers:
+                    clsname = name
+        self.cls_name = clsname
+        self.cls_logits = self._acts[self.net.layers[clsname].index] if clsname else None
+        B, P_h, P_w, nseg = self.seg_logits.shape
+        dev = self.device
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.pred_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.int32, device=dev)
+        self.pred_cls = torch.zeros((B,), dtype=torch.int32, device=dev) if self.cls_logits is not None else None
+        self.post = []
+        lp = self.seg_logits.t.data_ptr()
+        if nseg == 1:
+            self._call(self.post, "basi_threshold", lp, C.c_float(0.5), self.pred_seg.data_ptr(),
+                       C.c_int64(B * P_h * P_w))
+        else:
+            self._call(self.post, "basi_argmax", lp, C.c_int64(B * P_h * P_w), nseg, self.pred_seg.data_ptr())
+        if self.cls_logits is not None:
+            self._call(self.post, "basi_argmax", self.cls_logits.t.data_ptr(), C.c_int64(B),
+                       self.cls_logits.shape[3], self.pred_cls.data_ptr())
+        if not self.training:
+            return
+        assert cfg is not None, "training needs a loss configuration"
+        kind = cfg.get("kind", "bce" if nseg == 1 else "softmax")
+        N = B * P_h * P_w
+        self.lossl = []
+        g = self._grad_of(self.seg_logits)
+        self.seg_logits.gw = True
+        if kind == "bce":
+            assert nseg == 1
+            self.label_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.float32, device=dev)
+            self._call(self.lossl, "basi_wbce_fwd_bwd", lp, self.label_seg.data_ptr(),
+                       C.c_float(cfg.get("pos_weight", 3.0)), C.c_double(1.0 / N), C.c_float(1.0 / N),
+                       C.c_int64(N), self.loss_acc.data_ptr(), g.t.data_ptr())
+        else:
+            self.label_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.int32, device=dev)
+            self._call(self.lossl, "basi_softmax_ce_fwd_bwd", lp, self.label_seg.data_ptr(), C.c_int64(N), nseg,
+                       C.c_double(1.0 / N), C.c_float(1.0 / N), self.loss_acc.data_ptr(), g.t.data_ptr())
+        self.class_weight = float(cfg.get("class_weight", 0.2))
+        if self.cls_logits is not None:
+            self.label_cls = torch.zeros((B,), dtype=torch.int32, device=dev)
+            gc = self._grad_of(self.cls_logits)
+            self.cls_logits.gw = True
+            ncls = self.cls_logits.shape[3]
+            self._call(self.lossl, "basi_softmax_ce_fwd_bwd", self.cls_logits.t.data_ptr(),
+                       self.label_cls.data_ptr(), C.c_int64(B), ncls, C.c_double(1.0 / B),
+                       C.c_float(self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
+        else:
+            self.label_cls = None
+
+    # ------------------------------------------------------------------ backward emission
+    def _acc_flag(self, act):
+        """plan-time: returns 1 if act.grad already holds a contribution, and marks it written."""
+        self._grad_of(act)
+        f = 1 if act.gw else 0
+        act.gw = True
+        return f
+
+    def _emit_backward(self):
+        # which activations need a gradient: everything except the data input
+        for kind, op in reversed(self._ops):
+            getattr(self, "_bwd_" + kind)(op)
+
+    def _bwd_conv(self, op):
+        x, y = op["x"], op["y"]
+        dy = y.grad
+        assert dy is not None and y.gw, "conv %s: no gradient reaches its output" % op["name"]
+        if op["relu"]:
+            assert y.dtype == _lib.F32
+            n = int(np.prod(y.shape))
+            self._call(self.bwd, "basi_relu_bwd_f32", dy.t.data_ptr(), y.t.data_ptr(), C.c_int64(n))
+        dptr = C.byref(op["desc"])
+        need_dx = x is not self.input
+        tc_ok = self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]
+        lib = _lib.load()
+        if tc_ok and lib.basi_tc_conv_supported(_lib.TC_WGRAD, dptr, x.ref, y.ref) == 1:
+            self._emit_tc(op, _lib.TC_WGRAD, self.bwd)
+        else:
+            self._call(self.bwd, "basi_conv_wgrad", dptr, x.ref, dy.ref, self._gptr(op["w"]),
+                       self._gptr(op["b"]) if op["b"] else None)
+        if need_dx:
+            acc = self._acc_flag(x)
+            if tc_ok and lib.basi_tc_conv_supported(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1:
+                self._emit_tc(op, _lib.TC_DGRAD, self.bwd, acc)
+            else:
+                self._call(self.bwd, "basi_conv_dgrad", dptr, dy.ref, self._pptr(op["w"]), x.grad.ref, acc)
+
+    def _bwd_bnact(self, op):
+        out = op["out"]
+        dout = out.grad
+        assert dout is not None and out.gw
+        mask = out.ref if op["relu"] else None
+        recs = [(op["main"], True)]
+        if op["res_bn"] is not None:
+            recs.append((op["res_bn"], False))
+        for rec, is_main in recs:
+            x = rec.x
+            dx = self._grad_of(x)
+            x.gw = True
+            dres, dacc = None, 0
+            if is_main and op["res"] is not None and op["res_bn"] is None:
+                dacc = self._acc_flag(op["res"])
+                dres = op["res"].grad.ref
+            self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), rec.dsums)
+            self._call(self.bwd, "basi_bn_bwd_finalize", rec.dsums, C.c_double(rec.count), self._gptr(rec.gamma),
+                       self._gptr(rec.beta), rec.coef.data_ptr(), rec.C)
+            self._call(self.bwd, "basi_bn_bwd_apply", dout.ref, mask, x.ref, rec.bnp.data_ptr(),
+                       rec.coef.data_ptr(), dx.ref, dres, dacc)
+
+    def _bwd_maxpool(self, op):
+        x, y = op["x"], op["y"]
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_maxpool3s2_bwd", y.grad.ref, op["amax"].data_ptr(), x.grad.ref, acc)
+
+    def _bwd_avgpool(self, op):
+        x, y = op["x"], op["y"]
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_avgpool_bwd", y.grad.ref, op["k"], x.grad.ref, acc)
+
+    def _bwd_bilinear(self, op):
+        x, y = op["x"], op["y"]
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_bilinear_ac_bwd", y.grad.ref, x.grad.ref, acc)
+
+    def _bwd_gate(self, op):
+        feat, logits, y = op["feat"], op["logits"], op["y"]
+        acc = self._acc_flag(feat)
+        assert logits.gw, "segment-loss gradient must be written before the gate adjoint adds to it"
+        self._call(self.bwd, "basi_gate_mul_bwd", y.grad.ref, feat.ref, logits.t.data_ptr(), op["nseg"], op["att"],
+                   feat.grad.ref, acc, logits.grad.t.data_ptr())
+
+    def _bwd_skinny(self, op):
+        x, y = op["x"], op["y"]
+        dy = y.grad
+        assert dy is not None and y.gw
+        if op["relu"]:
+            self._call(self.bwd, "basi_relu_bwd_f32", dy.t.data_ptr(), y.t.data_ptr(), C.c_int64(self.B * op["N"]))
+        self._call(self.bwd, "basi_skinny_wgrad", x.t.data_ptr(), x.dtype, C.c_int64(op["lda"]), dy.t.data_ptr(),
+                   self._gptr(op["w"]), self._gptr(op["b"]) if op["b"] else None, self.B, op["K"], op["N"])
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_skinny_dgrad", dy.t.data_ptr(), self._pptr(op["w"]), x.grad.t.data_ptr(), x.dtype,
+                   C.c_int64(op["lda"]), self.B, op["K"], op["N"], acc)
+
+    # ------------------------------------------------------------------ tcgen05 plans
+    def _emit_tc(self, op, kind, lst, acc=0):
+        lib = _lib.load()
+        off, shape = self.param_index[op["w"]]
+        taps, cin, cout = shape[0] * shape[1], shape[2], shape[3]
+        if "w_io" not in op:
+            op["w_io"] = torch.zeros(taps * cin * cout, dtype=torch.bfloat16, device=self.device)
+            op["w_oi"] = torch.zeros(taps * cin * cout, dtype=torch.bfloat16, device=self.device)
+            self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout))
+        x, y = op["x"], op["y"]
+        handle = C.c_void_p()
+        if kind == _lib.TC_FPROP:
+            _lib.call("basi_tc_conv_create", kind, C.byref(op["desc"]), x.ref, y.ref, op["w_oi"].data_ptr(), None, 0,
+                      C.byref(handle))
+        elif kind == _lib.TC_DGRAD:
+            _lib.call("basi_tc_conv_create", kind, C.byref(op["desc"]), y.grad.ref, x.grad.ref,
+                      op["w_io"].data_ptr(), None, acc, C.byref(handle))
+        else:
+            _lib.call("basi_tc_conv_create", kind, C.byref(op["desc"]), x.ref, y.grad.ref, None,
+                      self._gptr(op["w"]), 1, C.byref(handle))
+        self._tc_plans.append(handle)
+        self.tc_layers += 1
+        lst.append(("basi_tc_conv_run", lib.basi_tc_conv_run, (handle,)))
+
+    def _refresh_weight_copies(self, stream=None):
+        if not self._tc_weights:
+            return
+        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        for wptr, w_io, w_oi, taps, cin, cout in self._tc_weights:
+            _lib.call("basi_tc_pack_weights", wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, st)
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h in self._tc_plans:
+                lib.basi_tc_conv_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, lst, st):
+        if self.dry_run:
+            raise _lib.BasiError("dry_run engine cannot execute")
+        for name, fn, args in lst:
+            rc = fn(*args, st)
+            if rc != 0:
+                raise _lib.BasiError("%s failed (%d): %s" % (name, rc, _lib.last_error()))
+        _lib.LAUNCHES += len(lst)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _zero_step_state(self, st):
+        _lib.call("basi_memset", self.bn_scratch.data_ptr(), 0, C.c_int64(self.bn_scratch.numel() * 8), st)
+        _lib.call("basi_memset", self.loss_acc.data_ptr(), 0, C.c_int64(32), st)
+        if self.training:
+            _lib.call("basi_memset", self.grads_flat.data_ptr(), 0, C.c_int64(self.n_flat * 4), st)
+            for g in self._zero_grads:
+                _lib.call("basi_memset", g.t.data_ptr(), 0, C.c_int64(g.t.numel() * g.t.element_size()), st)
+
+    def forward_device(self):
+        """Forward only, inputs already in self.input (device)."""
+        st = self._stream()
+        self._zero_step_state(st)
+        self._run(self.fwd, st)
+        self._run(self.post, st)
+
+    def step_device(self, sync_grads=None):
+        """One training step on inputs already resident in the static device buffers."""
+        st = self._stream()
+        self._zero_step_state(st)
+        self._run(self.fwd, st)
+        self._run(self.lossl, st)
+        self._run(self.post, st)
+        self._run(self.bwd, st)
+        if sync_grads is not None:
+            sync_grads(self.grads_flat)
+        _lib.call("basi_sgd_step", self.params_flat.data_ptr(), self.grads_flat.data_ptr(), self.lr_dev.data_ptr(),
+                  C.c_int64(self.n_flat), None, st)
+        self._refresh_weight_copies(st)
+
+    def launches_per_step(self):
+        n = len(self.fwd) + len(self.post)
+        if self.training:
+            n += len(self.lossl) + len(self.bwd) + 1 + len(self._tc_weights)
+        return n
+
+    # ---- CUDA graph capture of the whole step
+    def capture(self, train=True):
+        torch.cuda.synchronize(self.device)
+        lr_saved = self.lr_dev.clone()
+        self.lr_dev.zero_()      # the warm-up steps below must not move the weights
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step_device() if train else self.forward_device()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self.step_device() if train else self.forward_device()
+        self.lr_dev.copy_(lr_saved)
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
+        _lib.LAUNCHES += self.launches_per_step()
+
+    # ---- host-facing helpers
+    def feed(self, data=None, label_seg=None, label_cls=None, lr=None):
+        """Copies host arrays (numpy or pinned torch tensors) into the static device buffers."""
+        if data is not None:
+            self.input.t.copy_(_as_tensor(data, torch.float32).view(self.input.t.shape), non_blocking=True)
+        if label_seg is not None:
+            self.label_seg.copy_(_as_tensor(label_seg, self.label_seg.dtype).view(self.label_seg.shape),
+                                 non_blocking=True)
+        if label_cls is not None and self.label_cls is not None:
+            self.label_cls.copy_(_as_tensor(label_cls, torch.int32).view(self.label_cls.shape), non_blocking=True)
+        if lr is not None:
+            self.lr_dev.fill_(float(lr))
+
+    def losses(self):
+        acc = self.loss_acc.cpu().numpy()
+        seg, cls = float(acc[0]), float(acc[1])
+        total = seg + (self.class_weight * cls if self.cls_logits is not None else 0.0)
+        return total, seg, cls
+
+
+def _as_tensor(x, dtype):
+    if isinstance(x, torch.Tensor):
+        return x if x.dtype == dtype else x.to(dtype)
+    a = np.asarray(x)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)

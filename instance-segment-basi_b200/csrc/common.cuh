@@ -1,0 +1,129 @@
+// Shared helpers for the basi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "basi_b200.h"
+
+namespace basi {
+
+void set_error(const char* fmt, ...);
+
+#define BASI_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      basi::set_error(__VA_ARGS__);    \
+      return BASI_E_INVALID;           \
+    }                                  \
+  } while (0)
+
+#define BASI_CHECK_LAUNCH(name)                                              \
+  do {                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      basi::set_error("%s: %s", name, cudaGetErrorString(e__));              \
+      return BASI_E_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+int sm_count();
+
+typedef __nv_bfloat16 bf16;
+
+// ---- 128-bit vector access: 4 x f32 or 8 x bf16 -------------------------------------------
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    Vec r;
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ __forceinline__ static Vec zero() {
+    Vec r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = 0.f;
+    return r;
+  }
+};
+template <>
+struct Vec<bf16> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ static Vec load(const bf16* p) {
+    Vec r;
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void store(bf16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ static Vec zero() {
+    Vec r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    return r;
+  }
+};
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float x);
+template <>
+__device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline bool vec_ok(const basi_tensor* t) {
+  int vn = t->dtype == BASI_F32 ? 4 : 8;
+  int es = t->dtype == BASI_F32 ? 4 : 2;
+  (void)es;
+  return (t->c % vn == 0) && (t->ld % vn == 0) && ((reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0);
+}
+inline int64_t pixels(const basi_tensor* t) { return (int64_t)t->n * t->h * t->w; }
+inline bool same_shape(const basi_tensor* a, const basi_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+
+inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace basi

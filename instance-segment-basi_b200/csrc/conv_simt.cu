@@ -1,0 +1,668 @@
+// CUDA-core implicit-GEMM convolutions (fp32 accumulate) for every geometry on the BAIS PSPNet
+// path: fprop, dgrad (adjoint w.r.t. input) and wgrad (adjoint w.r.t. HWIO weights), plus the
+// skinny GEMMs of the attention-class head.  This is the exact-fp32 path (parity mode) and the
+// fallback for layers the tcgen05 path does not take (Cin=4 stem, strided 1x1, tiny heads).
+#include "common.cuh"
+
+namespace basi {
+
+struct GemmConv {
+  // gather-source tensor S and destination tensor D of the implicit GEMM
+  const void* S;
+  void* D;
+  const float* W;     // HWIO
+  const float* bias;  // fprop only
+  int N, SH, SW, SC, lds;
+  int DH, DW, DC, ldd;
+  int Cin, Cout;  // of the convolution (weights)
+  int kh, kw, stride, dil, pad_t, pad_l;
+  int relu, accumulate;
+  int M, K;       // GEMM sizes: M = N*DH*DW, K = taps*SC
+  int fastA;      // SC % 16 == 0 and aligned -> vector loads within one tap
+  int fastB;
+  int fastD;      // vector stores in the epilogue
+};
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1 };
+
+constexpr int BM = 128, BN = 64, BK = 16, BNP = BN + 4;
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&o)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&o)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&o)[8]) {
+  Vec<bf16> v = Vec<bf16>::load(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = v.v[i];
+}
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&o)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void load4<bf16>(const bf16* p, float (&o)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xffff0000u);
+  o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+// source coordinate of (dest coordinate d, tap offset r) along one axis; returns false if invalid
+template <int MODE>
+__device__ __forceinline__ bool src_coord(int d, int r, int stride, int dil, int pad, int S, int& s) {
+  if (MODE == MODE_FPROP) {
+    s = d * stride + r * dil - pad;
+    return s >= 0 && s < S;
+  } else {
+    int t = d + pad - r * dil;
+    if (t < 0) return false;
+    if (stride == 1) {
+      s = t;
+    } else {
+      if (t % stride) return false;
+      s = t / stride;
+    }
+    return s < S;
+  }
+}
+
+template <int MODE, typename TS, typename TD>
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const GemmConv g) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BNP];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const TS* __restrict__ S = (const TS*)g.S;
+  const float* __restrict__ W = g.W;
+
+  // A-load role: one destination pixel per thread, 8 consecutive k
+  const int am = tid & (BM - 1), akh = (tid >> 7) * 8;
+  const int gm = m0 + am;
+  int pn = 0, pdh = 0, pdw = 0;
+  const bool mvalid = gm < g.M;
+  if (mvalid) {
+    pdw = gm % g.DW;
+    int t = gm / g.DW;
+    pdh = t % g.DH;
+    pn = t / g.DH;
+  }
+  // B-load role
+  const int bk = MODE == MODE_FPROP ? (tid >> 4) : (tid & 3) * 4;
+  const int bn = MODE == MODE_FPROP ? (tid & 15) * 4 : (tid >> 2);
+
+  float ra[8], rb[4];
+  auto load_tile = [&](int k0) {
+    // ---- A ----
+    if (g.fastA) {
+      const int tap = k0 / g.SC, c0 = k0 - tap * g.SC + akh;
+      const int r = tap / g.kw, s = tap - r * g.kw;
+      int sh, sw;
+      bool ok = mvalid && src_coord<MODE>(pdh, r, g.stride, g.dil, g.pad_t, g.SH, sh) &&
+                src_coord<MODE>(pdw, s, g.stride, g.dil, g.pad_l, g.SW, sw);
+      if (ok) {
+        load8<TS>(S + (((int64_t)pn * g.SH + sh) * g.SW + sw) * g.lds + c0, ra);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ra[j] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + akh + j;
+        float v = 0.f;
+        if (mvalid && k < g.K) {
+          const int tap = k / g.SC, c = k - tap * g.SC;
+          const int r = tap / g.kw, s = tap - r * g.kw;
+          int sh, sw;
+          if (src_coord<MODE>(pdh, r, g.stride, g.dil, g.pad_t, g.SH, sh) &&
+              src_coord<MODE>(pdw, s, g.stride, g.dil, g.pad_l, g.SW, sw))
+            v = to_f32(S[(((int64_t)pn * g.SH + sh) * g.SW + sw) * g.lds + c]);
+        }
+        ra[j] = v;
+      }
+    }
+    // ---- B ----
+    if (MODE == MODE_FPROP) {
+      const int k = k0 + bk, n = n0 + bn;
+      if (g.fastB && k < g.K && n + 3 < g.DC) {
+        float4 t = *reinterpret_cast<const float4*>(W + (int64_t)k * g.Cout + n);
+        rb[0] = t.x; rb[1] = t.y; rb[2] = t.z; rb[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = (k < g.K && n + j < g.DC) ? W[(int64_t)k * g.Cout + n + j] : 0.f;
+      }
+    } else {
+      // B[k=(tap,co)][n=ci] = W[(tap*Cin + ci)*Cout + co]; 4 consecutive co for one ci
+      const int k = k0 + bk, n = n0 + bn;
+      if (g.fastB && n < g.DC && k + 3 < g.K) {
+        const int tap = k / g.SC, co = k - tap * g.SC;
+        float4 t = *reinterpret_cast<const float4*>(W + ((int64_t)tap * g.Cin + n) * g.Cout + co);
+        rb[0] = t.x; rb[1] = t.y; rb[2] = t.z; rb[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k + j;
+          float v = 0.f;
+          if (n < g.DC && kk < g.K) {
+            const int tap = kk / g.SC, co = kk - tap * g.SC;
+            v = W[((int64_t)tap * g.Cin + n) * g.Cout + co];
+          }
+          rb[j] = v;
+        }
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[buf][akh + j][am] = ra[j];
+    if (MODE == MODE_FPROP) {
+      *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[buf][bk + j][bn] = rb[j];
+    }
+  };
+
+  const int tm = tid >> 4, tn = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ktiles = (g.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ktiles) load_tile((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < ktiles) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  TD* __restrict__ D = (TD*)g.D;
+  const int nc = n0 + tn * 4;
+  float bvals[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (nc + j < g.DC) bvals[j] = g.bias[nc + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm * 8 + i;
+    if (m >= g.M) continue;
+    TD* dst = D + (int64_t)m * g.ldd + nc;
+    if (g.fastD && nc + 3 < g.DC) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bvals[j];
+      if (g.accumulate) {
+        float o[4];
+        load4<TD>(dst, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += o[j];
+      }
+      if (g.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      store4<TD>(dst, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (nc + j >= g.DC) continue;
+        float v = acc[i][j] + bvals[j];
+        if (g.accumulate) v += to_f32(dst[j]);
+        if (g.relu) v = fmaxf(v, 0.f);
+        dst[j] = from_f32<TD>(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[kk=(tap,ci)][co] += sum_m A[m][kk] * dY[m][co], split over m across blockIdx.z
+// ------------------------------------------------------------------------------------------
+struct WgradConv {
+  const void* X;
+  const void* G;
+  float* dW;
+  int N, IH, IW, Cin, ldx;
+  int OH, OW, Cout, ldg;
+  int kh, kw, stride, dil, pad_t, pad_l;
+  int M, K;
+  int m_per_split;
+  int fastA, fastG;
+};
+
+constexpr int WK = 64, WN = 64, WP = 16, WS = 68;
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradConv g) {
+  __shared__ __align__(16) float As[2][WP][WS];
+  __shared__ __align__(16) float Gs[2][WP][WS];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * WK, n0 = blockIdx.y * WN;
+  const int mbeg = blockIdx.z * g.m_per_split;
+  const int mend = min(g.M, mbeg + g.m_per_split);
+  const TX* __restrict__ X = (const TX*)g.X;
+  const TG* __restrict__ G = (const TG*)g.G;
+
+  const int lp = tid >> 4, lq = (tid & 15) * 4;
+  // fixed tap / channel of this thread's 4 A columns (fast path)
+  const int kk = k0 + lq;
+  int tr = 0, ts = 0, tci = 0;
+  if (kk < g.K) {
+    int tap = kk / g.Cin;
+    tci = kk - tap * g.Cin;
+    tr = tap / g.kw;
+    ts = tap - tr * g.kw;
+  }
+  float ra[4], rg[4];
+  auto load_chunk = [&](int mb) {
+    const int m = mb + lp;
+    const bool mv = m < mend;
+    int ow = 0, oh = 0, n = 0;
+    if (mv) {
+      ow = m % g.OW;
+      int t = m / g.OW;
+      oh = t % g.OH;
+      n = t / g.OH;
+    }
+    if (g.fastA) {
+      const int ih = oh * g.stride + tr * g.dil - g.pad_t, iw = ow * g.stride + ts * g.dil - g.pad_l;
+      if (mv && kk < g.K && ih >= 0 && ih < g.IH && iw >= 0 && iw < g.IW) {
+        load4<TX>(X + (((int64_t)n * g.IH + ih) * g.IW + iw) * g.ldx + tci, ra);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[j] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        const int k = kk + j;
+        if (mv && k < g.K) {
+          const int tap = k / g.Cin, ci = k - tap * g.Cin;
+          const int r = tap / g.kw, s = tap - r * g.kw;
+          const int ih = oh * g.stride + r * g.dil - g.pad_t, iw = ow * g.stride + s * g.dil - g.pad_l;
+          if (ih >= 0 && ih < g.IH && iw >= 0 && iw < g.IW)
+            v = to_f32(X[(((int64_t)n * g.IH + ih) * g.IW + iw) * g.ldx + ci]);
+        }
+        ra[j] = v;
+      }
+    }
+    const int nn = n0 + lq;
+    if (g.fastG && mv && nn + 3 < g.Cout) {
+      load4<TG>(G + (int64_t)m * g.ldg + nn, rg);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rg[j] = (mv && nn + j < g.Cout) ? to_f32(G[(int64_t)m * g.ldg + nn + j]) : 0.f;
+    }
+  };
+  auto store_chunk = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lp][lq]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    *reinterpret_cast<float4*>(&Gs[buf][lp][lq]) = make_float4(rg[0], rg[1], rg[2], rg[3]);
+  };
+
+  const int tk = tid >> 4, tn = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int chunks = (mend - mbeg + WP - 1) / WP;
+  if (chunks > 0) {
+    load_chunk(mbeg);
+    store_chunk(0);
+    __syncthreads();
+    for (int c = 0; c < chunks; ++c) {
+      const int buf = c & 1;
+      if (c + 1 < chunks) load_chunk(mbeg + (c + 1) * WP);
+#pragma unroll
+      for (int p = 0; p < WP; ++p) {
+        float4 a = *reinterpret_cast<const float4*>(&As[buf][p][tk * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Gs[buf][p][tn * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (c + 1 < chunks) {
+        store_chunk(buf ^ 1);
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + tk * 4 + i;
+    if (k >= g.K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn * 4 + j;
+      if (n < g.Cout) atomicAdd(g.dW + (int64_t)k * g.Cout + n, acc[i][j]);
+    }
+  }
+}
+
+// column sums: out[n] += sum_m G[m][n]
+template <typename TG>
+__global__ void colsum_kernel(const TG* __restrict__ G, int64_t M, int C, int ld, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (n < C)
+    for (int64_t m = (int64_t)blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8)
+      a += to_f32(G[m * ld + n]);
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < C) {
+    for (int y = 1; y < 8; ++y) a += sm[y][threadIdx.x];
+    atomicAdd(out + n, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Skinny GEMMs (M <= 64 rows): attention-class head
+// ------------------------------------------------------------------------------------------
+constexpr int SK_KT = 64;  // k-slab per block (fwd / wgrad)
+
+template <typename TA>
+__global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ a, int64_t lda,
+                                                         const float* __restrict__ w, float* __restrict__ y, int M,
+                                                         int K, int N) {
+  __shared__ float sa[64][SK_KT + 1];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * SK_KT;
+  const int kt = min(SK_KT, K - k0);
+  for (int i = threadIdx.x; i < M * SK_KT; i += 128) {
+    int m = i / SK_KT, k = i - m * SK_KT;
+    sa[m][k] = k < kt ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+  }
+  __syncthreads();
+  if (n >= N) return;
+  for (int mb = 0; mb < M; mb += 16) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int k = 0; k < kt; ++k) {
+      const float wv = __ldg(w + (int64_t)(k0 + k) * N + n);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(sa[min(mb + i, 63)][k], wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (mb + i < M) atomicAdd(y + (int64_t)(mb + i) * N + n, acc[i]);
+  }
+}
+
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int M, int N, int relu) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float v = y[i] + (bias ? bias[i % N] : 0.f);
+  y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+// da[m][k] (+)= sum_n dy[m][n] * w[k][n]; one warp per k row
+template <typename TA>
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                           TA* __restrict__ da, int64_t lda, int M, int K, int N,
+                                                           int acc_flag) {
+  extern __shared__ float sdy[];  // [M][N]
+  for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = blockIdx.x * 8 + wid; k < K; k += gridDim.x * 8) {
+    const float* wr = w + (int64_t)k * N;
+    for (int mb = 0; mb < M; mb += 16) {
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      for (int n = lane; n < N; n += 32) {
+        const float wv = __ldg(wr + n);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (mb + i < M) acc[i] = fmaf(sdy[(mb + i) * N + n], wv, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = warp_sum(acc[i]);
+        if (lane == 0 && mb + i < M) {
+          TA* dst = da + (int64_t)(mb + i) * lda + k;
+          if (acc_flag) v += to_f32(*dst);
+          *dst = from_f32<TA>(v);
+        }
+      }
+    }
+  }
+}
+
+// dw[k][n] += sum_m a[m][k] * dy[m][n]
+template <typename TA>
+__global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict__ a, int64_t lda,
+                                                           const float* __restrict__ dy, float* __restrict__ dw,
+                                                           float* __restrict__ dbias, int M, int K, int N) {
+  __shared__ float sa[64][SK_KT + 1];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * SK_KT;
+  const int kt = min(SK_KT, K - k0);
+  for (int i = threadIdx.x; i < M * SK_KT; i += 128) {
+    int m = i / SK_KT, k = i - m * SK_KT;
+    sa[m][k] = k < kt ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+  }
+  __syncthreads();
+  if (n >= N) return;
+  float g[64];
+  float bs = 0.f;
+#pragma unroll
+  for (int m = 0; m < 64; ++m) {
+    g[m] = m < M ? dy[(int64_t)m * N + n] : 0.f;
+    bs += g[m];
+  }
+  if (dbias && blockIdx.y == 0) dbias[n] += bs;
+  for (int k = 0; k < kt; ++k) {
+    float acc = 0.f;
+#pragma unroll
+    for (int m = 0; m < 64; ++m) acc = fmaf(sa[m][k], g[m], acc);
+    dw[(int64_t)(k0 + k) * N + n] += acc;
+  }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace basi
+
+using namespace basi;
+
+static int check_conv(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y, const char* who) {
+  BASI_CHECK_ARG(d && x && y && x->ptr && y->ptr, "%s: null argument", who);
+  BASI_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->dil > 0 && d->pad_t >= 0 && d->pad_l >= 0,
+                 "%s: bad geometry", who);
+  BASI_CHECK_ARG(x->n == y->n, "%s: batch mismatch", who);
+  // output extent must be reachable: (OH-1)*stride + (kh-1)*dil - pad_t <= IH-1 + pad_bottom (pad_bottom >= 0 implied)
+  BASI_CHECK_ARG((y->h - 1) * d->stride - d->pad_t < x->h && (y->w - 1) * d->stride - d->pad_l < x->w,
+                 "%s: output larger than the padded input allows", who);
+  return BASI_OK;
+}
+
+template <int MODE>
+static int launch_gemm_conv(const GemmConv& g, int ts, int td, cudaStream_t st) {
+  dim3 grid((g.M + BM - 1) / BM, (g.DC + BN - 1) / BN);
+  if (ts == BASI_F32 && td == BASI_F32) conv_gemm_kernel<MODE, float, float><<<grid, 256, 0, st>>>(g);
+  else if (ts == BASI_BF16 && td == BASI_BF16) conv_gemm_kernel<MODE, bf16, bf16><<<grid, 256, 0, st>>>(g);
+  else if (ts == BASI_BF16 && td == BASI_F32) conv_gemm_kernel<MODE, bf16, float><<<grid, 256, 0, st>>>(g);
+  else conv_gemm_kernel<MODE, float, bf16><<<grid, 256, 0, st>>>(g);
+  return BASI_OK;
+}
+
+extern "C" {
+
+int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* w, const float* bias,
+                    const basi_tensor* y, void* stream) {
+  int rc = check_conv(d, x, y, "conv_fprop");
+  if (rc) return rc;
+  BASI_CHECK_ARG(w, "conv_fprop: null weights");
+  GemmConv g{};
+  g.S = x->ptr; g.D = y->ptr; g.W = w; g.bias = bias;
+  g.N = x->n; g.SH = x->h; g.SW = x->w; g.SC = x->c; g.lds = x->ld;
+  g.DH = y->h; g.DW = y->w; g.DC = y->c; g.ldd = y->ld;
+  g.Cin = x->c; g.Cout = y->c;
+  g.kh = d->kh; g.kw = d->kw; g.stride = d->stride; g.dil = d->dil; g.pad_t = d->pad_t; g.pad_l = d->pad_l;
+  g.relu = d->relu; g.accumulate = 0;
+  g.M = (int)pixels(y); g.K = d->kh * d->kw * x->c;
+  g.fastA = (x->c % 16 == 0) && (x->ld % 8 == 0) && aligned16(x->ptr);
+  g.fastB = (y->c % 4 == 0) && aligned16(w);
+  g.fastD = (y->c % 4 == 0) && (y->ld % 4 == 0) && aligned16(y->ptr);
+  launch_gemm_conv<MODE_FPROP>(g, x->dtype, y->dtype, (cudaStream_t)stream);
+  BASI_CHECK_LAUNCH("conv_fprop");
+  return BASI_OK;
+}
+
+int basi_conv_dgrad(const basi_conv_desc* d, const basi_tensor* dy, const float* w, const basi_tensor* dx,
+                    int accumulate, void* stream) {
+  int rc = check_conv(d, dx, dy, "conv_dgrad");
+  if (rc) return rc;
+  BASI_CHECK_ARG(w, "conv_dgrad: null weights");
+  GemmConv g{};
+  g.S = dy->ptr; g.D = dx->ptr; g.W = w; g.bias = nullptr;
+  g.N = dx->n; g.SH = dy->h; g.SW = dy->w; g.SC = dy->c; g.lds = dy->ld;
+  g.DH = dx->h; g.DW = dx->w; g.DC = dx->c; g.ldd = dx->ld;
+  g.Cin = dx->c; g.Cout = dy->c;
+  g.kh = d->kh; g.kw = d->kw; g.stride = d->stride; g.dil = d->dil; g.pad_t = d->pad_t; g.pad_l = d->pad_l;
+  g.relu = 0; g.accumulate = accumulate;
+  g.M = (int)pixels(dx); g.K = d->kh * d->kw * dy->c;
+  g.fastA = (dy->c % 16 == 0) && (dy->ld % 8 == 0) && aligned16(dy->ptr);
+  g.fastB = (dy->c % 16 == 0) && aligned16(w);
+  g.fastD = (dx->c % 4 == 0) && (dx->ld % 4 == 0) && aligned16(dx->ptr);
+  launch_gemm_conv<MODE_DGRAD>(g, dy->dtype, dx->dtype, (cudaStream_t)stream);
+  BASI_CHECK_LAUNCH("conv_dgrad");
+  return BASI_OK;
+}
+
+int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* dy, float* dw, float* dbias,
+                    void* stream) {
+  int rc = check_conv(d, x, dy, "conv_wgrad");
+  if (rc) return rc;
+  BASI_CHECK_ARG(dw, "conv_wgrad: null dw");
+  WgradConv g{};
+  g.X = x->ptr; g.G = dy->ptr; g.dW = dw;
+  g.N = x->n; g.IH = x->h; g.IW = x->w; g.Cin = x->c; g.ldx = x->ld;
+  g.OH = dy->h; g.OW = dy->w; g.Cout = dy->c; g.ldg = dy->ld;
+  g.kh = d->kh; g.kw = d->kw; g.stride = d->stride; g.dil = d->dil; g.pad_t = d->pad_t; g.pad_l = d->pad_l;
+  g.M = (int)pixels(dy); g.K = d->kh * d->kw * x->c;
+  g.fastA = (x->c % 4 == 0) && (x->ld % 4 == 0) && aligned16(x->ptr);
+  g.fastG = (dy->c % 4 == 0) && (dy->ld % 4 == 0) && aligned16(dy->ptr);
+  int tiles = ((g.K + WK - 1) / WK) * ((g.Cout + WN - 1) / WN);
+  int want = (basi::sm_count() * 4 + tiles - 1) / tiles;
+  int maxsplit = (g.M + 255) / 256;  // >= 256 pixels per split
+  int splits = want < maxsplit ? want : maxsplit;
+  if (splits < 1) splits = 1;
+  g.m_per_split = ((g.M + splits - 1) / splits + WP - 1) / WP * WP;
+  splits = (g.M + g.m_per_split - 1) / g.m_per_split;
+  dim3 grid((g.K + WK - 1) / WK, (g.Cout + WN - 1) / WN, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->dtype == BASI_F32 && dy->dtype == BASI_F32) conv_wgrad_kernel<float, float><<<grid, 256, 0, st>>>(g);
+  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_BF16) conv_wgrad_kernel<bf16, bf16><<<grid, 256, 0, st>>>(g);
+  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_F32) conv_wgrad_kernel<bf16, float><<<grid, 256, 0, st>>>(g);
+  else conv_wgrad_kernel<float, bf16><<<grid, 256, 0, st>>>(g);
+  BASI_CHECK_LAUNCH("conv_wgrad");
+  if (dbias) {
+    int64_t M = g.M;
+    int gy = (int)((M + 255) / 256);
+    if (gy > 256) gy = 256;
+    dim3 cg((g.Cout + 31) / 32, gy), cb(32, 8);
+    if (dy->dtype == BASI_F32) colsum_kernel<float><<<cg, cb, 0, st>>>((const float*)dy->ptr, M, g.Cout, g.ldg, dbias);
+    else colsum_kernel<bf16><<<cg, cb, 0, st>>>((const bf16*)dy->ptr, M, g.Cout, g.ldg, dbias);
+    BASI_CHECK_LAUNCH("conv_wgrad(dbias)");
+  }
+  return BASI_OK;
+}
+
+int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y, int M, int K,
+                    int N, int relu, void* stream) {
+  BASI_CHECK_ARG(a && w && y && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_fwd: bad argument (M must be <= 64)");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
+  dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
+  if (dtype_a == BASI_F32) skinny_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)a, lda, w, y, M, K, N);
+  else skinny_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)a, lda, w, y, M, K, N);
+  BASI_CHECK_LAUNCH("skinny_fwd");
+  bias_act_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(y, bias, M, N, relu);
+  BASI_CHECK_LAUNCH("skinny_fwd(bias)");
+  return BASI_OK;
+}
+
+int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, int64_t lda, int M, int K, int N,
+                      int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && w && da && M > 0 && M <= 64 && K > 0 && N > 0 && (size_t)M * N * 4 <= 96 * 1024,
+                 "skinny_dgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = sizeof(float) * (size_t)M * N;
+  int blocks = (K + 7) / 8;
+  int cap = basi::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype_a == BASI_F32) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(skinny_dgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    skinny_dgrad_kernel<float><<<blocks, 256, smem, st>>>(dy, w, (float*)da, lda, M, K, N, accumulate);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(skinny_dgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    skinny_dgrad_kernel<bf16><<<blocks, 256, smem, st>>>(dy, w, (bf16*)da, lda, M, K, N, accumulate);
+  }
+  BASI_CHECK_LAUNCH("skinny_dgrad");
+  return BASI_OK;
+}
+
+int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, float* dw, float* dbias, int M, int K,
+                      int N, void* stream) {
+  BASI_CHECK_ARG(a && dy && dw && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_wgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
+  if (dtype_a == BASI_F32) skinny_wgrad_kernel<float><<<grid, 128, 0, st>>>((const float*)a, lda, dy, dw, dbias, M, K, N);
+  else skinny_wgrad_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  BASI_CHECK_LAUNCH("skinny_wgrad");
+  return BASI_OK;
+}
+
+}  // extern "C"

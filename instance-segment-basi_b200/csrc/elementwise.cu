@@ -1,0 +1,1086 @@
+// HBM-bound kernels of the BAIS PSPNet hot path: batch-norm (batch statistics) forward /
+// backward with fused ReLU and residual add, pooling, align-corners bilinear and its adjoint,
+// attention gating, click-map rasterisation, fused losses, SGD and prediction helpers.
+// All tensors NHWC; 128-bit vector access over channels (4 x f32 / 8 x bf16).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace basi {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  cached = n;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-channel reductions over rows: thread (tx, ty) owns channel group tx (+ blockIdx.y*bdx) and
+// strides over rows with ty.  fp32 partials are flushed to double every 16 rows; block-level
+// reduction in shared memory (double), one double atomicAdd per channel per block.
+// ------------------------------------------------------------------------------------------
+template <int VN>
+__device__ __forceinline__ void block_reduce_to_global(double (&a)[VN], double (&b)[VN], double* ga, double* gb,
+                                                        int c0, bool valid) {
+  extern __shared__ double sred[];  // [blockDim.y][blockDim.x][2*VN]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double* mine = sred + ((size_t)ty * blockDim.x + tx) * (2 * VN);
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    mine[i] = a[i];
+    mine[VN + i] = b[i];
+  }
+  __syncthreads();
+  if (ty == 0 && valid) {
+    for (int y = 1; y < blockDim.y; ++y) {
+      const double* o = sred + ((size_t)y * blockDim.x + tx) * (2 * VN);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        a[i] += o[i];
+        b[i] += o[VN + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      atomicAdd(ga + c0 + i, a[i]);
+      atomicAdd(gb + c0 + i, b[i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, int64_t R, int C, int ld, double* __restrict__ sums) {
+  constexpr int VN = Vec<T>::N;
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool valid = cg * VN < C;
+  const int c0 = cg * VN;
+  double s[VN], q[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.0;
+  if (valid) {
+    const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
+    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    while (r < R) {
+      float fs[VN], fq[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
+#pragma unroll 4
+      for (int it = 0; it < 16 && r < R; ++it, r += rstep) {
+        Vec<T> v = Vec<T>::load(x + r * ld + c0);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          fs[i] += v.v[i];
+          fq[i] = fmaf(v.v[i], v.v[i], fq[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        s[i] += (double)fs[i];
+        q[i] += (double)fq[i];
+      }
+    }
+  }
+  block_reduce_to_global<VN>(s, q, sums, sums + C, c0, valid);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, double count, float eps, float* __restrict__ bnp,
+                                   int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  double istd = 1.0 / sqrt(var + (double)eps);
+  bnp[c] = (float)mean;
+  bnp[C + c] = (float)istd;
+  bnp[2 * C + c] = (float)((double)gamma[c] * istd);
+  bnp[3 * C + c] = beta[c];
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ bnp,
+                                const T* __restrict__ res, int ldr, const float* __restrict__ rbnp, int relu,
+                                T* __restrict__ out, int ldo, int64_t R, int C) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  const int64_t total = R * cgs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cgs;
+    const int c0 = (int)(i - r * cgs) * VN;
+    Vec<T> v = Vec<T>::load(x + r * ldx + c0);
+    Vec<T> rv;
+    if (res) rv = Vec<T>::load(res + r * ldr + c0);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const int c = c0 + j;
+      float o = fmaf(v.v[j] - __ldg(bnp + c), __ldg(bnp + 2 * C + c), __ldg(bnp + 3 * C + c));
+      if (res) {
+        float rr = rv.v[j];
+        if (rbnp) rr = fmaf(rr - __ldg(rbnp + c), __ldg(rbnp + 2 * C + c), __ldg(rbnp + 3 * C + c));
+        o += rr;
+      }
+      if (relu) o = fmaxf(o, 0.f);
+      v.v[j] = o;
+    }
+    v.store(out + r * ldo + c0);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo,
+                                     const T* __restrict__ x, int ldx, const float* __restrict__ bnp, int64_t R,
+                                     int C, double* __restrict__ dsums) {
+  constexpr int VN = Vec<T>::N;
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool valid = cg * VN < C;
+  const int c0 = cg * VN;
+  double s[VN], q[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.0;
+  if (valid) {
+    float mean[VN], istd[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      mean[i] = bnp[c0 + i];
+      istd[i] = bnp[C + c0 + i];
+    }
+    const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
+    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    while (r < R) {
+      float fs[VN], fq[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
+#pragma unroll 2
+      for (int it = 0; it < 16 && r < R; ++it, r += rstep) {
+        Vec<T> d = Vec<T>::load(dout + r * ldd + c0);
+        Vec<T> xv = Vec<T>::load(x + r * ldx + c0);
+        if (out) {
+          Vec<T> o = Vec<T>::load(out + r * ldo + c0);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          fs[i] += d.v[i];
+          fq[i] = fmaf(d.v[i], (xv.v[i] - mean[i]) * istd[i], fq[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        s[i] += (double)fs[i];
+        q[i] += (double)fq[i];
+      }
+    }
+  }
+  block_reduce_to_global<VN>(s, q, dsums, dsums + C, c0, valid);
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ dsums, double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = dsums[c], s2 = dsums[C + c];
+  dbeta[c] += (float)s1;
+  dgamma[c] += (float)s2;
+  coef[c] = (float)(s1 / count);
+  coef[C + c] = (float)(s2 / count);
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo,
+                                    const T* __restrict__ x, int ldx, const float* __restrict__ bnp,
+                                    const float* __restrict__ coef, T* __restrict__ dx, int lddx, T* __restrict__ dres,
+                                    int lddr, int dres_acc, int64_t R, int C) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  const int64_t total = R * cgs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cgs;
+    const int c0 = (int)(i - r * cgs) * VN;
+    Vec<T> d = Vec<T>::load(dout + r * ldd + c0);
+    Vec<T> xv = Vec<T>::load(x + r * ldx + c0);
+    if (out) {
+      Vec<T> o = Vec<T>::load(out + r * ldo + c0);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) d.v[j] = o.v[j] > 0.f ? d.v[j] : 0.f;
+    }
+    if (dres) {
+      Vec<T> dr = d;
+      if (dres_acc) {
+        Vec<T> old = Vec<T>::load(dres + r * lddr + c0);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) dr.v[j] += old.v[j];
+      }
+      dr.store(dres + r * lddr + c0);
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const int c = c0 + j;
+      float xh = (xv.v[j] - __ldg(bnp + c)) * __ldg(bnp + C + c);
+      d.v[j] = __ldg(bnp + 2 * C + c) * (d.v[j] - __ldg(coef + c) - xh * __ldg(coef + C + c));
+    }
+    d.store(dx + r * lddx + c0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pooling
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, T* __restrict__ y,
+                                      int ldy, int OH, int OW, int pad_t, int pad_l, uint8_t* __restrict__ amax,
+                                      int64_t total) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    int ow = (int)(p % OW);
+    int64_t t = p / OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    float best[VN];
+    uint8_t bi[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - pad_t + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - pad_l + s;
+        if (iw < 0 || iw >= W) continue;
+        Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + ih) * W + iw) * ldx + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (v.v[j] > best[j]) {
+            best[j] = v.v[j];
+            bi[j] = (uint8_t)(r * 3 + s);
+          }
+      }
+    }
+    Vec<T> o;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o.v[j] = best[j];
+    o.store(y + p * ldy + cg * VN);
+    uint8_t* a = amax + p * C + cg * VN;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) a[j] = bi[j];
+  }
+}
+
+template <typename T>
+__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, const uint8_t* __restrict__ amax,
+                                      T* __restrict__ dx, int ldx, int H, int W, int C, int pad_t, int pad_l, int acc,
+                                      int64_t total) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    int iw = (int)(p % W);
+    int64_t t = p / W;
+    int ih = (int)(t % H);
+    int n = (int)(t / H);
+    Vec<T> g = Vec<T>::zero();
+    if (acc) g = Vec<T>::load(dx + p * ldx + cg * VN);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int th = ih + pad_t - r;
+      if (th < 0 || (th & 1)) continue;
+      int oh = th >> 1;
+      if (oh >= OH) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int tw = iw + pad_l - s;
+        if (tw < 0 || (tw & 1)) continue;
+        int ow = tw >> 1;
+        if (ow >= OW) continue;
+        int64_t op = ((int64_t)n * OH + oh) * OW + ow;
+        Vec<T> d = Vec<T>::load(dy + op * ldy + cg * VN);
+        const uint8_t* a = amax + op * C + cg * VN;
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (a[j] == (uint8_t)(r * 3 + s)) g.v[j] += d.v[j];
+      }
+    }
+    g.store(dx + p * ldx + cg * VN);
+  }
+}
+
+// one block per output pixel; threads (tx over channel groups, ty over window pixels)
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, int k, T* __restrict__ y,
+                                   int ldy, int OH, int OW) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float sacc[];  // [blockDim.y][blockDim.x*VN]
+  const int ow = blockIdx.x % OW;
+  const int oh = (blockIdx.x / OW) % OH;
+  const int n = blockIdx.x / (OW * OH);
+  const int cgs = C / VN;
+  const float inv = 1.0f / (float)(k * k);
+  for (int cgb = 0; cgb < cgs; cgb += blockDim.x) {
+    const int cg = cgb + threadIdx.x;
+    float a[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) a[j] = 0.f;
+    if (cg < cgs) {
+      for (int p = threadIdx.y; p < k * k; p += blockDim.y) {
+        int ih = oh * k + p / k, iw = ow * k + p % k;
+        Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + ih) * W + iw) * ldx + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) a[j] += v.v[j];
+      }
+    }
+    float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) mine[j] = a[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && cg < cgs) {
+      for (int yy = 1; yy < blockDim.y; ++yy) {
+        const float* o = sacc + ((size_t)yy * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) a[j] += o[j];
+      }
+      Vec<T> r;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) r.v[j] = a[j] * inv;
+      r.store(y + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, int k, T* __restrict__ dx,
+                                   int ldx, int H, int W, int C, int acc, int64_t total) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  const float inv = 1.0f / (float)(k * k);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    int iw = (int)(p % W);
+    int64_t t = p / W;
+    int ih = (int)(t % H);
+    int n = (int)(t / H);
+    int oh = ih / k, ow = iw / k;
+    Vec<T> g = Vec<T>::zero();
+    if (acc) g = Vec<T>::load(dx + p * ldx + cg * VN);
+    if (oh < OH && ow < OW) {
+      Vec<T> d = Vec<T>::load(dy + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) g.v[j] += d.v[j] * inv;
+    } else if (acc) {
+      continue;
+    }
+    g.store(dx + p * ldx + cg * VN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bilinear, align_corners=True
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ac_coord(int o, float scale, int in_size, int& lo, int& hi, float& f) {
+  float src = (float)o * scale;
+  lo = (int)floorf(src);
+  if (lo > in_size - 1) lo = in_size - 1;
+  hi = min(lo + 1, in_size - 1);
+  f = src - (float)lo;
+}
+
+template <typename T>
+__global__ void bilinear_ac_fwd_kernel(const T* __restrict__ x, int ldx, int IH, int IW, int C, T* __restrict__ y,
+                                       int ldy, int OH, int OW, float sh, float sw, int64_t total) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    int ow = (int)(p % OW);
+    int64_t t = p / OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    int y0, y1, x0, x1;
+    float fy, fx;
+    ac_coord(oh, sh, IH, y0, y1, fy);
+    ac_coord(ow, sw, IW, x0, x1, fx);
+    const T* base = x + (int64_t)n * IH * IW * ldx + cg * VN;
+    Vec<T> tl = Vec<T>::load(base + ((int64_t)y0 * IW + x0) * ldx);
+    Vec<T> tr = Vec<T>::load(base + ((int64_t)y0 * IW + x1) * ldx);
+    Vec<T> bl = Vec<T>::load(base + ((int64_t)y1 * IW + x0) * ldx);
+    Vec<T> br = Vec<T>::load(base + ((int64_t)y1 * IW + x1) * ldx);
+    Vec<T> o;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      float top = tl.v[j] + (tr.v[j] - tl.v[j]) * fx;
+      float bot = bl.v[j] + (br.v[j] - bl.v[j]) * fx;
+      o.v[j] = top + (bot - top) * fy;
+    }
+    o.store(y + p * ldy + cg * VN);
+  }
+}
+
+// adjoint: one block per input (small) pixel, gather over the output pixels that touch it
+template <typename T>
+__global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, T* __restrict__ dx, int ldx,
+                                       int IH, int IW, int C, float sh, float sw, int acc) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float sacc[];
+  const int sx = blockIdx.x % IW;
+  const int sy = (blockIdx.x / IW) % IH;
+  const int n = blockIdx.x / (IW * IH);
+  const int cgs = C / VN;
+  for (int cgb = 0; cgb < cgs; cgb += blockDim.x) {
+    const int cg = cgb + threadIdx.x;
+    float a[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) a[j] = 0.f;
+    if (cg < cgs) {
+      for (int p = threadIdx.y; p < OH * OW; p += blockDim.y) {
+        int oh = p / OW, ow = p % OW;
+        int y0, y1, x0, x1;
+        float fy, fx;
+        ac_coord(oh, sh, IH, y0, y1, fy);
+        ac_coord(ow, sw, IW, x0, x1, fx);
+        float wy = (y0 == sy ? 1.f - fy : 0.f) + (y1 == sy ? fy : 0.f);
+        float wx = (x0 == sx ? 1.f - fx : 0.f) + (x1 == sx ? fx : 0.f);
+        float wgt = wy * wx;
+        if (wgt == 0.f) continue;
+        Vec<T> d = Vec<T>::load(dy + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) a[j] = fmaf(d.v[j], wgt, a[j]);
+      }
+    }
+    float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) mine[j] = a[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && cg < cgs) {
+      for (int yy = 1; yy < blockDim.y; ++yy) {
+        const float* o = sacc + ((size_t)yy * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) a[j] += o[j];
+      }
+      T* dst = dx + (((int64_t)n * IH + sy) * IW + sx) * ldx + cg * VN;
+      Vec<T> r;
+      if (acc) {
+        r = Vec<T>::load(dst);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) r.v[j] += a[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) r.v[j] = a[j];
+      }
+      r.store(dst);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention gating
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gate_mul_fwd_kernel(const T* __restrict__ feat, int ldf, const float* __restrict__ logits, int nseg,
+                                    int att, T* __restrict__ out, int ldo, int64_t R, int C) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  const int64_t total = R * cgs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cgs;
+    const int c0 = (int)(i - r * cgs) * VN;
+    const float g = __ldg(logits + r * nseg + att);
+    Vec<T> v = Vec<T>::load(feat + r * ldf + c0);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) v.v[j] = fmaxf(v.v[j], 0.f) * g;
+    v.store(out + r * ldo + c0);
+  }
+}
+
+// one warp per pixel
+template <typename T>
+__global__ void gate_mul_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ feat, int ldf,
+                                    const float* __restrict__ logits, int nseg, int att, T* __restrict__ dfeat,
+                                    int lddf, int acc, float* __restrict__ dlogits, int64_t R, int C) {
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const float g = __ldg(logits + r * nseg + att);
+    float s = 0.f;
+    for (int cg = lane; cg < cgs; cg += 32) {
+      Vec<T> d = Vec<T>::load(dout + r * ldd + cg * VN);
+      Vec<T> f = Vec<T>::load(feat + r * ldf + cg * VN);
+      Vec<T> o;
+      if (acc) o = Vec<T>::load(dfeat + r * lddf + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        float fr = fmaxf(f.v[j], 0.f);
+        s = fmaf(d.v[j], fr, s);
+        float gf = f.v[j] > 0.f ? d.v[j] * g : 0.f;
+        o.v[j] = acc ? o.v[j] + gf : gf;
+      }
+      o.store(dfeat + r * lddf + cg * VN);
+    }
+    s = warp_sum(s);
+    if (lane == 0) dlogits[r * nseg + att] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Click map + NHWC4 packing.  No fast-math: the table holds float32 subnormals.
+// ------------------------------------------------------------------------------------------
+__global__ void clickmap_pack_kernel(const uint8_t* __restrict__ img_u8, const float* __restrict__ img_f32,
+                                     const int32_t* __restrict__ clicks, const float* __restrict__ lut,
+                                     int64_t lut_len, float4* __restrict__ out, int B, int H, int W) {
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int64_t t = i / W;
+    int y = (int)(t % H);
+    int b = (int)(t / H);
+    int64_t dy = y - clicks[2 * b], dx = x - clicks[2 * b + 1];
+    int64_t d2 = dx * dx + dy * dy;
+    float m = d2 < lut_len ? __ldg(lut + d2) : 0.f;
+    float4 o;
+    if (img_u8) {
+      const uint8_t* p = img_u8 + i * 3;
+      o.x = (float)p[0] / 255.0f;
+      o.y = (float)p[1] / 255.0f;
+      o.z = (float)p[2] / 255.0f;
+    } else {
+      const float* p = img_f32 + i * 3;
+      o.x = p[0];
+      o.y = p[1];
+      o.z = p[2];
+    }
+    o.w = m;
+    out[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Losses (fused forward + gradient), SGD, predictions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum_atomic(double v, double* dst) {
+  __shared__ double wsum[32];
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (int)((blockDim.x + 31) >> 5) ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(dst, v);
+  }
+}
+
+__global__ void wbce_kernel(const float* __restrict__ logits, const float* __restrict__ labels, float q, double scale,
+                            float gscale, int64_t n, double* __restrict__ loss_acc, float* __restrict__ dlogits) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x = logits[i], z = labels[i];
+    float w = 1.f + (q - 1.f) * z;
+    float e = expf(-fabsf(x));
+    float sp = log1pf(e) + fmaxf(-x, 0.f);  // softplus(-x)
+    acc += (double)((1.f - z) * x + w * sp);
+    // sigmoid(-x), stable on both sides
+    float sneg = x >= 0.f ? e / (1.f + e) : 1.f / (1.f + e);
+    if (dlogits) dlogits[i] = gscale * ((1.f - z) - w * sneg);
+  }
+  block_sum_atomic(acc * scale, loss_acc);
+}
+
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int64_t rows,
+                                  int C, double scale, float gscale, double* __restrict__ loss_acc,
+                                  float* __restrict__ dlogits) {
+  double acc = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = logits + r * C;
+    float mx = x[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
+    int lab = labels[r];
+    float lse = logf(se) + mx;
+    acc += (double)(lse - x[lab]);
+    if (dlogits) {
+      float inv = 1.f / se;
+      for (int c = 0; c < C; ++c) {
+        float p = expf(x[c] - mx) * inv;
+        dlogits[r * C + c] = gscale * (p - (c == lab ? 1.f : 0.f));
+      }
+    }
+  }
+  block_sum_atomic(acc * scale, loss_acc);
+}
+
+__global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ lr_dev,
+                           int64_t n, bf16* __restrict__ wb) {
+  const float lr = __ldg(lr_dev);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(w)[i];
+    float4 b = reinterpret_cast<const float4*>(g)[i];
+    a.x -= lr * b.x;
+    a.y -= lr * b.y;
+    a.z -= lr * b.z;
+    a.w -= lr * b.w;
+    reinterpret_cast<float4*>(w)[i] = a;
+    if (wb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+      reinterpret_cast<uint2*>(wb)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float a = w[i] - lr * g[i];
+      w[i] = a;
+      if (wb) wb[i] = __float2bfloat16_rn(a);
+    }
+  }
+}
+
+__global__ void threshold_kernel(const float* __restrict__ x, float thr, int32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] > thr ? 1 : 0;
+}
+
+__global__ void argmax_kernel(const float* __restrict__ x, int64_t rows, int C, int32_t* __restrict__ out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = x + r * C;
+    float b = p[0];
+    int bi = 0;
+    for (int c = 1; c < C; ++c)
+      if (p[c] > b) {
+        b = p[c];
+        bi = c;
+      }
+    out[r] = bi;
+  }
+}
+
+// TF1 legacy resize (src = dst*in/out) + argmax(sigmoid(.)) == argmax of the interpolated logits only if sigmoid is
+// monotone per channel -- it is, but the reference takes sigmoid first in float32, so do the same to keep ties equal.
+__global__ void upsample_legacy_argmax_kernel(const float* __restrict__ x, int B, int PH, int PW, int C, int SH, int SW,
+                                              float sh, float sw, int32_t* __restrict__ out) {
+  const int64_t total = (int64_t)B * SH * SW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ox = (int)(i % SW);
+    int64_t t = i / SW;
+    int oy = (int)(t % SH);
+    int b = (int)(t / SH);
+    float sy = (float)oy * sh, sx = (float)ox * sw;
+    int y0 = min((int)floorf(sy), PH - 1), x0 = min((int)floorf(sx), PW - 1);
+    int y1 = min(y0 + 1, PH - 1), x1 = min(x0 + 1, PW - 1);
+    float fy = sy - (float)y0, fx = sx - (float)x0;
+    const float* base = x + (int64_t)b * PH * PW * C;
+    float best = -1.f;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+      float tl = base[((int64_t)y0 * PW + x0) * C + c], tr = base[((int64_t)y0 * PW + x1) * C + c];
+      float bl = base[((int64_t)y1 * PW + x0) * C + c], br = base[((int64_t)y1 * PW + x1) * C + c];
+      float top = tl + (tr - tl) * fx, bot = bl + (br - bl) * fx;
+      float v = top + (bot - top) * fy;
+      float s = 1.f / (1.f + expf(-v));
+      if (s > best) {
+        best = s;
+        bi = c;
+      }
+    }
+    out[i] = bi;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+__global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+
+// channel-reduction launch geometry shared by bn_stats / bn_bwd_reduce
+struct RedGeom {
+  dim3 grid, block;
+  size_t smem;
+};
+static RedGeom red_geom(int64_t R, int C, int VN) {
+  int cgs = C / VN;
+  int bx = cgs < 256 ? cgs : 256;
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  int gy = (cgs + bx - 1) / bx;
+  int64_t want = (R + (int64_t)by * 16 - 1) / ((int64_t)by * 16);  // >= 16 rows per thread
+  int64_t cap = (int64_t)sm_count() * 4 / gy;
+  if (cap < 1) cap = 1;
+  int gx = (int)(want < cap ? want : cap);
+  if (gx < 1) gx = 1;
+  RedGeom g;
+  g.grid = dim3(gx, gy);
+  g.block = dim3(bx, by);
+  g.smem = (size_t)bx * by * 2 * VN * sizeof(double);
+  return g;
+}
+
+}  // namespace basi
+
+using namespace basi;
+
+#define DISPATCH_T(dtype, ...)             \
+  if ((dtype) == BASI_F32) {               \
+    typedef float T;                       \
+    __VA_ARGS__                            \
+  } else {                                 \
+    typedef bf16 T;                        \
+    __VA_ARGS__                            \
+  }
+
+extern "C" {
+
+const char* basi_last_error(void) { return g_err; }
+int basi_version(void) { return 100; }
+int basi_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    set_error("basi_sm_count: %s", cudaGetErrorString(cudaGetLastError()));
+    return BASI_E_NOGPU;
+  }
+  return n;
+}
+int basi_memset(void* ptr, int value, int64_t bytes, void* stream) {
+  cudaError_t e = cudaMemsetAsync(ptr, value, (size_t)bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("basi_memset: %s", cudaGetErrorString(e));
+    return BASI_E_CUDA;
+  }
+  return BASI_OK;
+}
+
+int basi_clickmap_pack(const void* img, int img_is_f32, const int32_t* clicks, const float* lut, int64_t lut_len,
+                       float* out, int B, int H, int W, void* stream) {
+  BASI_CHECK_ARG(img && clicks && lut && out && B > 0 && H > 0 && W > 0, "clickmap_pack: bad argument");
+  int64_t total = (int64_t)B * H * W;
+  clickmap_pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      img_is_f32 ? nullptr : (const uint8_t*)img, img_is_f32 ? (const float*)img : nullptr, clicks, lut, lut_len,
+      (float4*)out, B, H, W);
+  BASI_CHECK_LAUNCH("clickmap_pack");
+  return BASI_OK;
+}
+
+int basi_bn_stats(const basi_tensor* x, double* sums, void* stream) {
+  BASI_CHECK_ARG(x && sums && vec_ok(x), "bn_stats: tensor must have c,ld multiple of the vector width");
+  int64_t R = pixels(x);
+  DISPATCH_T(x->dtype, {
+    RedGeom g = red_geom(R, x->c, Vec<T>::N);
+    bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>((const T*)x->ptr, R, x->c, x->ld, sums);
+  })
+  BASI_CHECK_LAUNCH("bn_stats");
+  return BASI_OK;
+}
+
+int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, double count, float eps, float* bnp,
+                     int C, void* stream) {
+  BASI_CHECK_ARG(sums && gamma && beta && bnp && C > 0 && count > 0, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, count, eps, bnp, C);
+  BASI_CHECK_LAUNCH("bn_finalize");
+  return BASI_OK;
+}
+
+int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp, int relu,
+                  const basi_tensor* out, void* stream) {
+  BASI_CHECK_ARG(x && bnp && out && vec_ok(x) && vec_ok(out) && same_shape(x, out) && x->dtype == out->dtype,
+                 "bn_apply: bad x/out");
+  BASI_CHECK_ARG(!res || (vec_ok(res) && same_shape(x, res) && res->dtype == x->dtype), "bn_apply: bad residual");
+  int64_t R = pixels(x);
+  DISPATCH_T(x->dtype, {
+    int64_t total = R * (x->c / Vec<T>::N);
+    bn_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x->ptr, x->ld, bnp, res ? (const T*)res->ptr : nullptr, res ? res->ld : 0, res ? res_bnp : nullptr,
+        relu, (T*)out->ptr, out->ld, R, x->c);
+  })
+  BASI_CHECK_LAUNCH("bn_apply");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
+                       double* dsums, void* stream) {
+  BASI_CHECK_ARG(dout && x && bnp && dsums && vec_ok(dout) && vec_ok(x) && same_shape(dout, x) &&
+                     dout->dtype == x->dtype,
+                 "bn_bwd_reduce: bad dout/x");
+  BASI_CHECK_ARG(!out || (vec_ok(out) && same_shape(out, x) && out->dtype == x->dtype), "bn_bwd_reduce: bad out");
+  int64_t R = pixels(x);
+  DISPATCH_T(x->dtype, {
+    RedGeom g = red_geom(R, x->c, Vec<T>::N);
+    bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
+        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
+        bnp, R, x->c, dsums);
+  })
+  BASI_CHECK_LAUNCH("bn_bwd_reduce");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_finalize(const double* dsums, double count, float* dgamma, float* dbeta, float* coef, int C,
+                         void* stream) {
+  BASI_CHECK_ARG(dsums && dgamma && dbeta && coef && C > 0, "bn_bwd_finalize: bad argument");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dsums, count, dgamma, dbeta, coef, C);
+  BASI_CHECK_LAUNCH("bn_bwd_finalize");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
+                      const float* coef, const basi_tensor* dx, const basi_tensor* dres, int dres_accumulate,
+                      void* stream) {
+  BASI_CHECK_ARG(dout && x && dx && bnp && coef && vec_ok(dout) && vec_ok(x) && vec_ok(dx) && same_shape(dout, x) &&
+                     same_shape(dx, x) && dout->dtype == x->dtype && dx->dtype == x->dtype,
+                 "bn_bwd_apply: bad dout/x/dx");
+  BASI_CHECK_ARG(!out || (vec_ok(out) && same_shape(out, x) && out->dtype == x->dtype), "bn_bwd_apply: bad out");
+  BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_apply: bad dres");
+  int64_t R = pixels(x);
+  DISPATCH_T(x->dtype, {
+    int64_t total = R * (x->c / Vec<T>::N);
+    bn_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
+        bnp, coef, (T*)dx->ptr, dx->ld, dres ? (T*)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, R, x->c);
+  })
+  BASI_CHECK_LAUNCH("bn_bwd_apply");
+  return BASI_OK;
+}
+
+static void same_pad_3s2(int in, int out, int* before) {
+  int total = (out - 1) * 2 + 3 - in;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream) {
+  BASI_CHECK_ARG(x && y && argmax && vec_ok(x) && vec_ok(y) && x->dtype == y->dtype && x->c == y->c && x->n == y->n,
+                 "maxpool fwd: bad tensors");
+  BASI_CHECK_ARG(y->h == (x->h + 1) / 2 && y->w == (x->w + 1) / 2, "maxpool fwd: output must be ceil(in/2)");
+  int pt, pl;
+  same_pad_3s2(x->h, y->h, &pt);
+  same_pad_3s2(x->w, y->w, &pl);
+  DISPATCH_T(x->dtype, {
+    int64_t total = pixels(y) * (y->c / Vec<T>::N);
+    maxpool3s2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, pt, pl, argmax, total);
+  })
+  BASI_CHECK_LAUNCH("maxpool3s2_fwd");
+  return BASI_OK;
+}
+
+int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,
+                        void* stream) {
+  BASI_CHECK_ARG(dy && dx && argmax && vec_ok(dy) && vec_ok(dx) && dx->dtype == dy->dtype && dx->c == dy->c &&
+                     dx->n == dy->n && dy->h == (dx->h + 1) / 2 && dy->w == (dx->w + 1) / 2,
+                 "maxpool bwd: bad tensors");
+  int pt, pl;
+  same_pad_3s2(dx->h, dy->h, &pt);
+  same_pad_3s2(dx->w, dy->w, &pl);
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
+    maxpool3s2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy->ptr, dy->ld, dy->h, dy->w, argmax, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, pt, pl, accumulate,
+        total);
+  })
+  BASI_CHECK_LAUNCH("maxpool3s2_bwd");
+  return BASI_OK;
+}
+
+static void pool_block(int cgs, int VN, dim3* block, size_t* smem) {
+  int bx = cgs < 256 ? cgs : 256;
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  *block = dim3(bx, by);
+  *smem = (size_t)bx * by * VN * sizeof(float);
+}
+
+int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* stream) {
+  BASI_CHECK_ARG(x && y && k > 0 && vec_ok(x) && vec_ok(y) && x->dtype == y->dtype && x->c == y->c && x->n == y->n &&
+                     y->h == x->h / k && y->w == x->w / k && y->h > 0 && y->w > 0,
+                 "avgpool fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    dim3 block;
+    size_t smem;
+    pool_block(x->c / Vec<T>::N, Vec<T>::N, &block, &smem);
+    avgpool_fwd_kernel<T><<<(unsigned)pixels(y), block, smem, (cudaStream_t)stream>>>(
+        (const T*)x->ptr, x->ld, x->h, x->w, x->c, k, (T*)y->ptr, y->ld, y->h, y->w);
+  })
+  BASI_CHECK_LAUNCH("avgpool_fwd");
+  return BASI_OK;
+}
+
+int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && dx && k > 0 && vec_ok(dy) && vec_ok(dx) && dx->dtype == dy->dtype && dx->c == dy->c &&
+                     dx->n == dy->n && dy->h == dx->h / k && dy->w == dx->w / k,
+                 "avgpool bwd: bad tensors");
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
+    avgpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy->ptr, dy->ld, dy->h, dy->w, k, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
+  })
+  BASI_CHECK_LAUNCH("avgpool_bwd");
+  return BASI_OK;
+}
+
+static float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+int basi_bilinear_ac_fwd(const basi_tensor* x, const basi_tensor* y, void* stream) {
+  BASI_CHECK_ARG(x && y && vec_ok(x) && vec_ok(y) && x->dtype == y->dtype && x->c == y->c && x->n == y->n,
+                 "bilinear fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    int64_t total = pixels(y) * (y->c / Vec<T>::N);
+    bilinear_ac_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, ac_scale(x->h, y->h),
+        ac_scale(x->w, y->w), total);
+  })
+  BASI_CHECK_LAUNCH("bilinear_ac_fwd");
+  return BASI_OK;
+}
+
+int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && dx && vec_ok(dy) && vec_ok(dx) && dx->dtype == dy->dtype && dx->c == dy->c && dx->n == dy->n,
+                 "bilinear bwd: bad tensors");
+  DISPATCH_T(dx->dtype, {
+    dim3 block;
+    size_t smem;
+    pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem);
+    bilinear_ac_bwd_kernel<T><<<(unsigned)pixels(dx), block, smem, (cudaStream_t)stream>>>(
+        (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, ac_scale(dx->h, dy->h),
+        ac_scale(dx->w, dy->w), accumulate);
+  })
+  BASI_CHECK_LAUNCH("bilinear_ac_bwd");
+  return BASI_OK;
+}
+
+int basi_gate_mul_fwd(const basi_tensor* feat, const float* logits, int nseg, int att, const basi_tensor* out,
+                      void* stream) {
+  BASI_CHECK_ARG(feat && logits && out && vec_ok(feat) && vec_ok(out) && same_shape(feat, out) &&
+                     feat->dtype == out->dtype && att >= 0 && att < nseg,
+                 "gate_mul fwd: bad argument");
+  int64_t R = pixels(feat);
+  DISPATCH_T(feat->dtype, {
+    int64_t total = R * (feat->c / Vec<T>::N);
+    gate_mul_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)out->ptr, out->ld, R, feat->c);
+  })
+  BASI_CHECK_LAUNCH("gate_mul_fwd");
+  return BASI_OK;
+}
+
+int basi_gate_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const float* logits, int nseg, int att,
+                      const basi_tensor* dfeat, int dfeat_accumulate, float* dlogits, void* stream) {
+  BASI_CHECK_ARG(dout && feat && logits && dfeat && dlogits && vec_ok(dout) && vec_ok(feat) && vec_ok(dfeat) &&
+                     same_shape(dout, feat) && same_shape(dfeat, feat) && dout->dtype == feat->dtype &&
+                     dfeat->dtype == feat->dtype && att >= 0 && att < nseg,
+                 "gate_mul bwd: bad argument");
+  int64_t R = pixels(feat);
+  DISPATCH_T(feat->dtype, {
+    gate_mul_bwd_kernel<T><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)dfeat->ptr, dfeat->ld,
+        dfeat_accumulate, dlogits, R, feat->c);
+  })
+  BASI_CHECK_LAUNCH("gate_mul_bwd");
+  return BASI_OK;
+}
+
+int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight, double scale, float grad_scale,
+                      int64_t n, double* loss_acc, float* dlogits, void* stream) {
+  BASI_CHECK_ARG(logits && labels && loss_acc && n > 0, "wbce: bad argument");
+  wbce_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(logits, labels, pos_weight, scale, grad_scale, n,
+                                                                    loss_acc, dlogits);
+  BASI_CHECK_LAUNCH("wbce_fwd_bwd");
+  return BASI_OK;
+}
+
+int basi_softmax_ce_fwd_bwd(const float* logits, const int32_t* labels, int64_t rows, int C, double scale,
+                            float grad_scale, double* loss_acc, float* dlogits, void* stream) {
+  BASI_CHECK_ARG(logits && labels && loss_acc && rows > 0 && C > 0, "softmax_ce: bad argument");
+  softmax_ce_kernel<<<grid_for(rows, 128, 4), 128, 0, (cudaStream_t)stream>>>(logits, labels, rows, C, scale,
+                                                                             grad_scale, loss_acc, dlogits);
+  BASI_CHECK_LAUNCH("softmax_ce_fwd_bwd");
+  return BASI_OK;
+}
+
+int basi_sgd_step(float* w, const float* g, const float* lr_dev, int64_t n, void* w_bf16, void* stream) {
+  BASI_CHECK_ARG(w && g && lr_dev && n > 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)g & 15) == 0 &&
+                     ((uintptr_t)w_bf16 & 7) == 0,
+                 "sgd_step: bad argument / alignment");
+  sgd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(w, g, lr_dev, n, (bf16*)w_bf16);
+  BASI_CHECK_LAUNCH("sgd_step");
+  return BASI_OK;
+}
+
+int basi_threshold(const float* logits, float thr, int32_t* out, int64_t n, void* stream) {
+  BASI_CHECK_ARG(logits && out && n > 0, "threshold: bad argument");
+  threshold_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(logits, thr, out, n);
+  BASI_CHECK_LAUNCH("threshold");
+  return BASI_OK;
+}
+
+int basi_argmax(const float* logits, int64_t rows, int C, int32_t* out, void* stream) {
+  BASI_CHECK_ARG(logits && out && rows > 0 && C > 0, "argmax: bad argument");
+  argmax_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, rows, C, out);
+  BASI_CHECK_LAUNCH("argmax");
+  return BASI_OK;
+}
+
+int basi_upsample_legacy_argmax(const float* logits, int B, int P_h, int P_w, int C, int S_h, int S_w, int32_t* out,
+                                void* stream) {
+  BASI_CHECK_ARG(logits && out && B > 0 && P_h > 0 && P_w > 0 && C > 0 && S_h > 0 && S_w > 0,
+                 "upsample_legacy_argmax: bad argument");
+  int64_t total = (int64_t)B * S_h * S_w;
+  upsample_legacy_argmax_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, B, P_h, P_w, C, S_h, S_w, (float)P_h / (float)S_h, (float)P_w / (float)S_w, out);
+  BASI_CHECK_LAUNCH("upsample_legacy_argmax");
+  return BASI_OK;
+}
+
+int basi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  BASI_CHECK_ARG(src && dst && n > 0, "cast: bad argument");
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  BASI_CHECK_LAUNCH("cast_f32_to_bf16");
+  return BASI_OK;
+}
+int basi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  BASI_CHECK_ARG(src && dst && n > 0, "cast: bad argument");
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  BASI_CHECK_LAUNCH("cast_bf16_to_f32");
+  return BASI_OK;
+}
+int basi_relu_bwd_f32(float* dy, const float* y, int64_t n, void* stream) {
+  BASI_CHECK_ARG(dy && y && n > 0, "relu_bwd: bad argument");
+  relu_bwd_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, n);
+  BASI_CHECK_LAUNCH("relu_bwd_f32");
+  return BASI_OK;
+}
+
+}  // extern "C"
