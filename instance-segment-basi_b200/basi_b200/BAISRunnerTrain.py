@@ -1,0 +1,141 @@
+"""Training runner with the reference's ``Train`` call surface.
+
+back/2AddClass/BAISRunnerTrain.py:13-188 (segment + attention-class, pos_weight BCE, 0.1/0.2 class term),
+back/1NoClass (segment only), back/4BorderClass and back/5COCO (softmax segment heads): same constructor
+kwargs and ``train(save_pred_freq, begin_step)``; ``variant`` picks the snapshot.  One ``sess.run`` of the
+reference == one ``Engine`` step here (forward, fused losses, backward, SGD on the B200).
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from .BAISData import Data, SyntheticData
+from .BAISPSPNet import PSPNet, Placeholder, VARIANTS
+from .BAISTools import Tools
+from .engine import Engine
+
+# per-snapshot training constants (file:line in the class docstring above)
+SNAPSHOT = {
+    "1NoClass": dict(num_segment=1, kind="bce", pos_weight=3.0, class_weight=0.0, lr=1e-2, num_steps=400001),
+    "2AddClass": dict(num_segment=1, kind="bce", pos_weight=3.0, class_weight=0.2, lr=5e-3, num_steps=500001),
+    "3ThreeClass": dict(num_segment=3, kind="softmax", pos_weight=1.0, class_weight=0.1, lr=5e-3, num_steps=500001),
+    "4BorderClass": dict(num_segment=4, kind="softmax", pos_weight=1.0, class_weight=0.1, lr=5e-3, num_steps=500001),
+    "5COCO": dict(num_segment=3, kind="softmax", pos_weight=1.0, class_weight=0.2, lr=5e-3, num_steps=1000001),
+}
+
+
+def poly_learning_rate(base_lr, step, num_steps, power=0.9):
+    """lr = base * (1 - step/num_steps)^0.9 in float32, step fed as float32 (BAISRunnerTrain.py:115-116)."""
+    s = np.float32(step) / np.float32(num_steps)
+    return float(np.float32(base_lr) * np.power(np.float32(1) - s, np.float32(power)))
+
+
+class Train(object):
+
+    def __init__(self, batch_size, last_pool_size, input_size, log_dir, data_root_path=None, train_list=None,
+                 data_path=None, annotation_path=None, class_path=None, model_name="model.ckpt", is_test=False,
+                 variant="2AddClass", num_classes=21, precision="bf16", filter_number=32, pos_weight=None,
+                 class_weight=None, learning_rate=None, num_steps=None, seed=0, device=None, dp=None,
+                 use_cuda_graph=True, use_tc=True):
+        snap = SNAPSHOT[variant]
+        self.log_dir = Tools.new_dir(log_dir)
+        self.model_name = model_name
+        self.checkpoint_path = os.path.join(self.log_dir, self.model_name)
+        self.input_size = input_size
+        self.batch_size = batch_size
+        self.num_classes = num_classes
+        self.num_segment = snap["num_segment"]
+        self.ratio = 8
+        self.last_pool_size = last_pool_size
+        self.filter_number = filter_number
+        self.learning_rate = snap["lr"] if learning_rate is None else learning_rate
+        self.num_steps = snap["num_steps"] if num_steps is None else num_steps
+        self.variant = variant
+        self.print_step = 1 if is_test else 25
+        self.dp = dp
+        self.use_cuda_graph = use_cuda_graph
+        self.synthetic = data_root_path is None
+        if self.synthetic:
+            self.data_reader = SyntheticData(batch_size, tuple(input_size), self.ratio, num_classes,
+                                             self.num_segment, sigma=20 if variant == "5COCO" else 30,
+                                             seed=seed + (dp.rank if dp else 0))
+        else:
+            self.data_reader = Data(data_root_path=data_root_path, data_list=train_list, data_path=data_path,
+                                    annotation_path=annotation_path, class_path=class_path,
+                                    batch_size=batch_size, image_size=input_size, is_test=is_test)
+        self.loss_cfg = dict(kind=snap["kind"],
+                             pos_weight=snap["pos_weight"] if pos_weight is None else pos_weight,
+                             class_weight=snap["class_weight"] if class_weight is None else class_weight)
+        self.net, self.engine = self.build_net(precision, device, use_tc)
+        self.engine.init_params(seed)
+
+    def build_net(self, precision="bf16", device=None, use_tc=True):
+        image_placeholder = Placeholder((None, self.input_size[0], self.input_size[1], 4))
+        net = PSPNet({'data': image_placeholder}, is_training=True, num_classes=self.num_classes,
+                     num_segment=self.num_segment, last_pool_size=self.last_pool_size,
+                     filter_number=self.filter_number, variant=self.variant)
+        engine = Engine(net, self.batch_size, precision, True, self.loss_cfg, device, use_tc)
+        if self.synthetic:
+            engine.enable_click_input(self.data_reader.sigma)
+        self.raw_output_segment = net.layers[VARIANTS[self.variant]["seg"]]
+        fc = VARIANTS[self.variant]["fc"]
+        self.raw_output_classes = net.layers[fc] if fc else None
+        return net, engine
+
+    def run_step(self, step, batch=None, fetch=True):
+        """One reference ``sess.run([... train_op ...], feed_dict)``; returns the fetched values."""
+        eng = self.engine
+        lr = poly_learning_rate(self.learning_rate, step, self.num_steps)
+        if self.synthetic:
+            images, clicks, label_seg, label_cls = batch if batch is not None else self.data_reader.next_batch()
+            eng.feed_clicks(images, clicks)
+            eng.feed(None, label_seg, label_cls, lr)
+        else:
+            data, ann, cls, _, _ = batch if batch is not None else self.data_reader.next_batch_train()
+            label_cls, label_seg = cls, np.asarray(ann)
+            eng.feed(np.asarray(data, dtype=np.float32), label_seg, np.asarray(cls, dtype=np.int32), lr)
+        if self.dp is not None:
+            eng.step_device(sync_grads=self.dp.all_reduce_mean)
+        elif self.use_cuda_graph:
+            if eng._graph is None:
+                eng.capture(train=True)
+            eng.replay()
+        else:
+            eng.step_device()
+        if not fetch:
+            return None
+        loss, loss_seg, loss_cls = eng.losses()
+        raw = eng.seg_logits.t.cpu().numpy()
+        pred_seg = eng.pred_seg.cpu().numpy()
+        out = dict(loss=loss, loss_segment=loss_seg, loss_classes=loss_cls, learning_rate=lr,
+                   raw_output_segment=raw, pred_segment=pred_seg)
+        lab = np.asarray(label_seg).reshape(pred_seg.shape)
+        if self.num_segment == 1:
+            out["accuracy_0"] = float(np.mean(raw.reshape(-1) > 0.5))
+            out["accuracy_1"] = float(np.mean(lab.reshape(-1) > 0.5))
+        else:
+            out["accuracy_segment"] = float(np.mean(pred_seg == lab))
+        if eng.cls_logits is not None:
+            out["raw_output_classes"] = eng.cls_logits.t.cpu().numpy().reshape(self.batch_size, -1)
+            out["pred_classes"] = eng.pred_cls.cpu().numpy()
+            out["accuracy_classes"] = float(np.mean(out["pred_classes"] == np.asarray(label_cls)))
+        return out
+
+    def train(self, save_pred_freq, begin_step=0, max_steps=None):
+        Tools.restore_if_y(self.engine, self.log_dir)
+        end = self.num_steps if max_steps is None else min(self.num_steps, begin_step + max_steps)
+        r = None
+        for step in range(begin_step, end):
+            start_time = time.time()
+            r = self.run_step(step)
+            if step % save_pred_freq == 0:
+                Tools.save(self.engine, self.checkpoint_path, step)
+                Tools.print_info('The checkpoint has been created.')
+            duration = time.time() - start_time
+            if step % self.print_step == 0:
+                Tools.print_info('step {:d} loss={:.3f} seg={:.3f} class={:.3f} lr={:.6f} ({:.3f} s/step)'.format(
+                    step, r["loss"], r["loss_segment"], r["loss_classes"], r["learning_rate"], duration))
+        return r

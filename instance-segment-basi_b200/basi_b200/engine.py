@@ -85,7 +85,7 @@ class Engine(object):
             device = "cuda:%d" % torch.cuda.current_device()
         self.device = torch.device(device)
         self.use_tc = bool(use_tc) and precision != "f32"
-        self.fwd, self.bwd = [], []
+        self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
         self._tc_plans = []
@@ -620,6 +620,8 @@ class Engine(object):
         _lib.LAUNCHES += len(lst)
 
     def _stream(self):
+        if self.dry_run:
+            raise _lib.BasiError("dry_run engine cannot execute")
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _zero_step_state(self, st):
@@ -630,10 +632,27 @@ class Engine(object):
             for g in self._zero_grads:
                 _lib.call("basi_memset", g.t.data_ptr(), 0, C.c_int64(g.t.numel() * g.t.element_size()), st)
 
+    def enable_click_input(self, sigma=30):
+        """Device-side batch assembly (A1/A2): uint8 images + clicks -> float32 NHWC4 via basi_clickmap_pack."""
+        from .BAISData import click_lut
+        B, H, W, _ = self.input.shape
+        lut = click_lut((H, W), sigma)
+        self.lut_dev = torch.from_numpy(lut).to(self.device)
+        self.img_u8 = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device)
+        self.clicks_dev = torch.zeros((B, 2), dtype=torch.int32, device=self.device)
+        self.pre = []
+        self._call(self.pre, "basi_clickmap_pack", self.img_u8.data_ptr(), 0, self.clicks_dev.data_ptr(),
+                   self.lut_dev.data_ptr(), C.c_int64(lut.size), self.input.t.data_ptr(), B, H, W)
+
+    def feed_clicks(self, images_u8, clicks):
+        self.img_u8.copy_(_as_tensor(images_u8, torch.uint8).view(self.img_u8.shape), non_blocking=True)
+        self.clicks_dev.copy_(_as_tensor(clicks, torch.int32).view(self.clicks_dev.shape), non_blocking=True)
+
     def forward_device(self):
         """Forward only, inputs already in self.input (device)."""
         st = self._stream()
         self._zero_step_state(st)
+        self._run(self.pre, st)
         self._run(self.fwd, st)
         self._run(self.post, st)
 
@@ -641,6 +660,7 @@ class Engine(object):
         """One training step on inputs already resident in the static device buffers."""
         st = self._stream()
         self._zero_step_state(st)
+        self._run(self.pre, st)
         self._run(self.fwd, st)
         self._run(self.lossl, st)
         self._run(self.post, st)
@@ -652,7 +672,7 @@ class Engine(object):
         self._refresh_weight_copies(st)
 
     def launches_per_step(self):
-        n = len(self.fwd) + len(self.post)
+        n = len(self.pre) + len(self.fwd) + len(self.post)
         if self.training:
             n += len(self.lossl) + len(self.bwd) + 1 + len(self._tc_weights)
         return n

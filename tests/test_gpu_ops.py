@@ -1,0 +1,431 @@
+"""GPU parity of each C-ABI kernel against the oracle (same seeded inputs).  Run with -m gpu on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import basi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 2e-5     # relative to the tensor max-norm (fp32 kernels, different summation order)
+BF16_TOL = 1.5e-2  # bf16 storage of inputs/outputs, fp32 accumulate
+
+
+def _u(rng, *shape):
+    return rng.uniform(-1, 1, shape).astype(np.float32)
+
+
+def nchw(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).permute(0, 3, 1, 2)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+# ------------------------------------------------------------------ click map (bit exact)
+@pytest.mark.parametrize("B,H,W,sigma", [(3, 320, 320, 30), (2, 64, 48, 20), (1, 8, 8, 30)])
+def test_clickmap_pack_bit_exact(B, H, W, sigma):
+    from gpu_util import call, dev, host
+    from basi_b200.BAISData import click_lut
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    clicks = np.stack([rng.randint(0, H, B), rng.randint(0, W, B)], 1).astype(np.int32)
+    clicks[0] = [H - 1, 0]
+    lut = click_lut((H, W), sigma)
+    out = torch.zeros((B, H, W, 4), dtype=torch.float32, device="cuda:0")
+    call("basi_clickmap_pack", dev(img).data_ptr(), 0, dev(clicks).data_ptr(), dev(lut).data_ptr(),
+         C.c_int64(lut.size), out.data_ptr(), B, H, W)
+    got = host(out)
+    for b in range(B):
+        ref = O.pack_input(img[b], clicks[b], sigma)
+        assert np.array_equal(got[b].view(np.uint32), ref.view(np.uint32))
+    # float-image entry (reference feeds /255 float images)
+    imgf = (img.astype(np.float32) / 255)
+    call("basi_clickmap_pack", dev(imgf).data_ptr(), 1, dev(clicks).data_ptr(), dev(lut).data_ptr(),
+         C.c_int64(lut.size), out.data_ptr(), B, H, W)
+    assert np.array_equal(host(out).view(np.uint32), got.view(np.uint32))
+
+
+# ------------------------------------------------------------------ convolutions
+CONVS = [
+    # k, stride, dil, padding, Cin, Cout, H, W, B, bias, relu
+    (3, 2, 1, "SAME", 4, 32, 32, 32, 2, False, False),     # conv1_1 (asymmetric SAME pad)
+    (3, 2, 1, "SAME", 4, 8, 15, 17, 1, False, False),      # odd input -> symmetric SAME pad
+    (3, 1, 1, "SAME", 32, 64, 16, 16, 2, False, False),    # conv1_3
+    (1, 1, 1, "VALID", 64, 32, 16, 16, 2, False, False),   # reduce
+    (3, 1, 1, 1, 32, 32, 16, 16, 2, False, False),         # zero_padding(1) + 3x3 VALID
+    (1, 2, 1, "VALID", 128, 256, 16, 16, 2, False, False), # conv3_1 proj / reduce, stride 2
+    (3, 1, 2, 2, 128, 128, 16, 16, 2, False, False),       # conv4 dilated
+    (3, 1, 4, 4, 64, 64, 12, 12, 1, False, False),         # conv5 dilated
+    (1, 1, 1, "VALID", 256, 1, 8, 8, 2, True, False),      # conv6_n head
+    (1, 1, 1, "VALID", 64, 4, 8, 8, 2, True, False),       # conv6_n_4 head
+    (5, 5, 1, "VALID", 16, 32, 8, 8, 2, True, True),       # class_attention_conv on a non-5x5 map
+    (3, 1, 1, "SAME", 8, 12, 9, 7, 3, False, False),       # ragged channels -> scalar paths
+    (1, 1, 1, "VALID", 16, 16, 1, 1, 2, False, False),     # PSP pool1 branch, 1x1 map
+]
+
+
+def _conv_case(case, dtype):
+    from gpu_util import act, bf16_round, call, dev, empty_act, host
+    from basi_b200._lib import ConvDesc
+    k, s, d, padding, cin, cout, H, W, B, bias, relu = case
+    rng = np.random.RandomState(hash(case) % 1000)
+    x = _u(rng, B, H, W, cin)
+    w = _u(rng, k, k, cin, cout) / np.sqrt(k * k * cin)
+    b = _u(rng, cout) if bias else None
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    if dtype == "bf16":
+        x = bf16_round(x)
+    xt = nchw(x).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True) if bias else None
+    y_ref = O.conv2d(xt, wt, s, padding, d, bt)
+    if relu:
+        y_ref = torch.relu(y_ref)
+    oh, ow = y_ref.shape[2], y_ref.shape[3]
+    if padding == "SAME":
+        pt, pl = O.tf_same_pad(H, k, s, d)[0], O.tf_same_pad(W, k, s, d)[0]
+    elif padding == "VALID":
+        pt = pl = 0
+    else:
+        pt = pl = padding
+    desc = ConvDesc(k, k, s, d, pt, pl, 1 if relu else 0)
+    out_dt = torch.float32 if bias else tdt
+    xa, ya = act(x, tdt), empty_act((B, oh, ow, cout), out_dt, fill=7.0)
+    wd = dev(w)
+    bd = dev(b) if bias else None
+    call("basi_conv_fprop", C.byref(desc), xa.ref, wd.data_ptr(), bd.data_ptr() if bias else None, ya.ref)
+    y = host(ya)
+    # backward
+    dy = _u(rng, B, oh, ow, cout)
+    if out_dt == torch.bfloat16:
+        dy = bf16_round(dy)
+    (y_ref * nchw(dy).double()).sum().backward()
+    dya = act(dy, out_dt)
+    if relu:
+        call("basi_relu_bwd_f32", dya.t.data_ptr(), ya.t.data_ptr(), C.c_int64(dya.t.numel()))
+    dxa = empty_act((B, H, W, cin), tdt, fill=3.0)
+    call("basi_conv_dgrad", C.byref(desc), dya.ref, wd.data_ptr(), dxa.ref, 0)
+    dx0 = host(dxa)
+    call("basi_conv_dgrad", C.byref(desc), dya.ref, wd.data_ptr(), dxa.ref, 1)
+    dx1 = host(dxa)
+    dw = torch.zeros(k, k, cin, cout, device="cuda:0")
+    db = torch.zeros(cout, device="cuda:0") if bias else None
+    call("basi_conv_wgrad", C.byref(desc), xa.ref, dya.ref, dw.data_ptr(), db.data_ptr() if bias else None)
+    return dict(y=y, y_ref=nhwc(y_ref.detach()), dx=dx0, dx2=dx1, dx_ref=nhwc(xt.grad), dw=host(dw),
+                dw_ref=wt.grad.numpy(), db=host(db) if bias else None, db_ref=bt.grad.numpy() if bias else None)
+
+
+@pytest.mark.parametrize("case", CONVS, ids=lambda c: "k%ds%dd%d_%s_%dto%d_%dx%d" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]))
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_conv_fprop_dgrad_wgrad(case, dtype):
+    from gpu_util import rel_err
+    r = _conv_case(case, dtype)
+    tol = F32_TOL if dtype == "f32" else BF16_TOL
+    assert rel_err(r["y"], r["y_ref"]) < tol
+    assert rel_err(r["dx"], r["dx_ref"]) < tol
+    assert rel_err(r["dx2"], 2 * r["dx_ref"]) < 2 * tol        # accumulate=1 adds onto the first result
+    assert rel_err(r["dw"], r["dw_ref"]) < (F32_TOL * 5 if dtype == "f32" else tol)
+    if r["db"] is not None:
+        assert rel_err(r["db"], r["db_ref"]) < 1e-4
+
+
+# ------------------------------------------------------------------ batch norm (+relu, +residual) forward/backward
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("mode", ["plain", "relu", "res", "res_bn"])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32), (1, 1, 1, 16), (3, 5, 7, 8), (2, 8, 8, 2048)])
+def test_batch_norm_forward_backward(dtype, mode, shape):
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    B, H, W, Cc = shape
+    rng = np.random.RandomState(1)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    x = rnd(_u(rng, *shape) * 2 + 0.5)
+    x2 = rnd(_u(rng, *shape))
+    gamma, beta = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    gamma2, beta2 = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    dout = rnd(_u(rng, *shape))
+    relu = mode != "plain"
+    # oracle (float64)
+    xt, x2t = nchw(x).double().requires_grad_(True), nchw(x2).double().requires_grad_(True)
+    g1, b1 = torch.from_numpy(gamma).double().requires_grad_(True), torch.from_numpy(beta).double().requires_grad_(True)
+    g2, b2 = torch.from_numpy(gamma2).double().requires_grad_(True), torch.from_numpy(beta2).double().requires_grad_(True)
+    y = O.batch_norm(xt, g1, b1)
+    if mode == "res":
+        y = y + x2t
+    if mode == "res_bn":
+        y = y + O.batch_norm(x2t, g2, b2)
+    if relu:
+        y = torch.relu(y)
+    # device forward
+    R = float(B * H * W)
+    xa, x2a, outa = act(x, tdt), act(x2, tdt), empty_act(shape, tdt)
+    sums = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda:0")
+    bnp, bnp2 = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(4 * Cc, device="cuda:0")
+    gd, bd, g2d, b2d = dev(gamma), dev(beta), dev(gamma2), dev(beta2)
+    call("basi_bn_stats", xa.ref, sums.data_ptr())
+    call("basi_bn_finalize", sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), Cc)
+    res_ref, res_bnp = None, None
+    if mode in ("res", "res_bn"):
+        res_ref = x2a.ref
+    if mode == "res_bn":
+        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc)
+        call("basi_bn_finalize", sums.data_ptr() + 8 * 2 * Cc, g2d.data_ptr(), b2d.data_ptr(), C.c_double(R),
+             C.c_float(1e-5), bnp2.data_ptr(), Cc)
+        res_bnp = bnp2.data_ptr()
+    call("basi_bn_apply", xa.ref, bnp.data_ptr(), res_ref, res_bnp, 1 if relu else 0, outa.ref)
+    tol = 1e-5 if dtype == "f32" else 1e-2
+    if B * H * W > 1:
+        assert rel_err(host(outa), nhwc(y.detach())) < tol
+    else:
+        assert np.allclose(host(outa), nhwc(y.detach()), atol=1e-2 if dtype == "bf16" else 1e-6)
+    # backward against autograd, with the device's own (possibly bf16-rounded) output as the ReLU mask
+    if B * H * W == 1:
+        return
+    (y * nchw(dout).double()).sum().backward()
+    da = act(dout, tdt)
+    dsums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda:0")
+    coef = torch.zeros(2 * Cc, device="cuda:0")
+    dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
+    dxa = empty_act(shape, tdt, fill=5.0)
+    dresa = empty_act(shape, tdt, fill=1.0)
+    mask = outa.ref if relu else None
+    call("basi_bn_bwd_reduce", da.ref, mask, xa.ref, bnp.data_ptr(), dsums.data_ptr())
+    call("basi_bn_bwd_finalize", dsums.data_ptr(), C.c_double(R), dgamma.data_ptr(), dbeta.data_ptr(),
+         coef.data_ptr(), Cc)
+    call("basi_bn_bwd_apply", da.ref, mask, xa.ref, bnp.data_ptr(), coef.data_ptr(), dxa.ref,
+         dresa.ref if mode == "res" else None, 1)
+    btol = 2e-4 if dtype == "f32" else 3e-2
+    assert rel_err(host(dxa), nhwc(xt.grad)) < btol
+    assert rel_err(host(dgamma), g1.grad.numpy()) < btol
+    assert rel_err(host(dbeta), b1.grad.numpy()) < btol
+    if mode == "res":
+        assert rel_err(host(dresa) - 1.0, nhwc(x2t.grad)) < btol
+    if mode == "res_bn":
+        dsums.zero_()
+        dx2a = empty_act(shape, tdt)
+        dg2, db2 = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
+        call("basi_bn_bwd_reduce", da.ref, mask, x2a.ref, bnp2.data_ptr(), dsums.data_ptr())
+        call("basi_bn_bwd_finalize", dsums.data_ptr(), C.c_double(R), dg2.data_ptr(), db2.data_ptr(),
+             coef.data_ptr(), Cc)
+        call("basi_bn_bwd_apply", da.ref, mask, x2a.ref, bnp2.data_ptr(), coef.data_ptr(), dx2a.ref, None, 0)
+        assert rel_err(host(dx2a), nhwc(x2t.grad)) < btol
+        assert rel_err(host(dg2), g2.grad.numpy()) < btol
+
+
+# ------------------------------------------------------------------ pooling / bilinear / gate
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32), (1, 15, 17, 8), (2, 160, 160, 64)])
+def test_maxpool_3x3_s2_same(dtype, shape):
+    from gpu_util import act, bf16_round, call, empty_act, host, rel_err
+    B, H, W, Cc = shape
+    rng = np.random.RandomState(2)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    x = _u(rng, *shape)
+    if dtype == "bf16":
+        x = bf16_round(x)
+    xt = nchw(x).double().requires_grad_(True)
+    y = O.max_pool_3x3_s2_same(xt)
+    oh, ow = y.shape[2], y.shape[3]
+    xa, ya = act(x, tdt), empty_act((B, oh, ow, Cc), tdt)
+    amax = torch.zeros(B * oh * ow * Cc, dtype=torch.uint8, device="cuda:0")
+    call("basi_maxpool3s2_fwd", xa.ref, ya.ref, amax.data_ptr())
+    assert np.array_equal(host(ya), nhwc(y.detach()).astype(np.float32))
+    dy = _u(rng, B, oh, ow, Cc)
+    if dtype == "bf16":
+        dy = bf16_round(dy)
+    (y * nchw(dy).double()).sum().backward()
+    dxa = empty_act(shape, tdt, fill=9.0)
+    call("basi_maxpool3s2_bwd", act(dy, tdt).ref, amax.data_ptr(), dxa.ref, 0)
+    assert rel_err(host(dxa), nhwc(xt.grad)) < (1e-6 if dtype == "f32" else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("H,k,Cc", [(40, 40, 64), (40, 20, 64), (40, 13, 64), (40, 6, 64), (40, 8, 1024), (8, 1, 16)])
+def test_avgpool(dtype, H, k, Cc):
+    from gpu_util import act, bf16_round, call, empty_act, host, rel_err
+    B = 2
+    rng = np.random.RandomState(3)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    x = _u(rng, B, H, H, Cc)
+    if dtype == "bf16":
+        x = bf16_round(x)
+    xt = nchw(x).double().requires_grad_(True)
+    y = O.avg_pool(xt, k)
+    o = y.shape[2]
+    xa, ya = act(x, tdt), empty_act((B, o, o, Cc), tdt)
+    call("basi_avgpool_fwd", xa.ref, k, ya.ref)
+    assert rel_err(host(ya), nhwc(y.detach())) < (1e-5 if dtype == "f32" else 1e-2)
+    dy = _u(rng, B, o, o, Cc)
+    if dtype == "bf16":
+        dy = bf16_round(dy)
+    (y * nchw(dy).double()).sum().backward()
+    dxa = empty_act((B, H, H, Cc), tdt, fill=2.0)
+    call("basi_avgpool_bwd", act(dy, tdt).ref, k, dxa.ref, 0)
+    assert rel_err(host(dxa), nhwc(xt.grad)) < (1e-5 if dtype == "f32" else 1e-2)
+    call("basi_avgpool_bwd", act(dy, tdt).ref, k, dxa.ref, 1)
+    assert rel_err(host(dxa), 2 * nhwc(xt.grad)) < (1e-5 if dtype == "f32" else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("o,P", [(1, 8), (2, 8), (3, 40), (6, 40), (4, 8)])
+def test_bilinear_align_corners(dtype, o, P):
+    from gpu_util import act, bf16_round, call, empty_act, host, rel_err
+    B, Cc = 2, 32
+    rng = np.random.RandomState(4)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    x = _u(rng, B, o, o, Cc)
+    if dtype == "bf16":
+        x = bf16_round(x)
+    xt = nchw(x).double().requires_grad_(True)
+    y = O.resize_bilinear_ac(xt, (P, P))
+    # write into a channel slice of a wider buffer, like the PSP concat
+    wide = torch.zeros((B, P, P, 3 * Cc), dtype=tdt, device="cuda:0")
+    from basi_b200.engine import Act
+    ya = Act(wide[..., Cc:2 * Cc])
+    call("basi_bilinear_ac_fwd", act(x, tdt).ref, ya.ref)
+    got = host(wide)
+    assert rel_err(got[..., Cc:2 * Cc], nhwc(y.detach())) < (1e-5 if dtype == "f32" else 1e-2)
+    assert np.all(got[..., :Cc] == 0) and np.all(got[..., 2 * Cc:] == 0)
+    dy = _u(rng, B, P, P, 3 * Cc)
+    if dtype == "bf16":
+        dy = bf16_round(dy)
+    (y * nchw(dy[..., Cc:2 * Cc]).double()).sum().backward()
+    dwide = act(dy, tdt)
+    dxa = empty_act((B, o, o, Cc), tdt, fill=4.0)
+    call("basi_bilinear_ac_bwd", Act(dwide.t[..., Cc:2 * Cc]).ref, dxa.ref, 0)
+    assert rel_err(host(dxa), nhwc(xt.grad)) < (2e-5 if dtype == "f32" else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("nseg,att", [(1, 0), (4, 1), (3, 2)])
+def test_gate_multiply(dtype, nseg, att):
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    B, P, Cc = 2, 8, 64
+    rng = np.random.RandomState(5)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    feat, logits, dout = rnd(_u(rng, B, P, P, Cc)), _u(rng, B, P, P, nseg) * 3, rnd(_u(rng, B, P, P, Cc))
+    ft = torch.from_numpy(feat).double().requires_grad_(True)
+    lt = torch.from_numpy(logits).double().requires_grad_(True)
+    y = torch.relu(ft) * lt[..., att:att + 1]
+    (y * torch.from_numpy(dout).double()).sum().backward()
+    fa, ya, ld = act(feat, tdt), empty_act((B, P, P, Cc), tdt), dev(logits)
+    call("basi_gate_mul_fwd", fa.ref, ld.data_ptr(), nseg, att, ya.ref)
+    assert rel_err(host(ya), y.detach().numpy()) < (1e-6 if dtype == "f32" else 1e-2)
+    dfa = empty_act((B, P, P, Cc), tdt, fill=1.0)
+    dl = torch.full((B, P, P, nseg), 0.5, device="cuda:0")
+    call("basi_gate_mul_bwd", act(dout, tdt).ref, fa.ref, ld.data_ptr(), nseg, att, dfa.ref, 1, dl.data_ptr())
+    assert rel_err(host(dfa) - 1.0, ft.grad.numpy()) < (1e-5 if dtype == "f32" else 2e-2)
+    assert rel_err(host(dl) - 0.5, lt.grad.numpy()) < 1e-4
+
+
+# ------------------------------------------------------------------ losses / SGD / predictions / skinny GEMMs
+@pytest.mark.parametrize("n", [1, 777, 25600])
+def test_weighted_bce_fused(n):
+    from gpu_util import call, dev, host, rel_err
+    rng = np.random.RandomState(6)
+    x = (_u(rng, n) * 12).astype(np.float32)
+    z = (rng.rand(n) > 0.7).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    loss = O.weighted_cross_entropy_with_logits(torch.from_numpy(z).double(), xt, 3.0).mean()
+    loss.backward()
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    dl = torch.zeros(n, device="cuda:0")
+    call("basi_wbce_fwd_bwd", dev(x).data_ptr(), dev(z).data_ptr(), C.c_float(3.0), C.c_double(1.0 / n),
+         C.c_float(1.0 / n), C.c_int64(n), acc.data_ptr(), dl.data_ptr())
+    assert abs(host(acc)[0] - loss.item()) < 1e-6 * max(1.0, abs(loss.item()))
+    assert rel_err(host(dl), xt.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,Cc", [(16, 21), (2, 91), (3200, 4), (128, 3)])
+def test_softmax_ce_fused(rows, Cc):
+    from gpu_util import call, dev, host, rel_err
+    rng = np.random.RandomState(7)
+    x = (_u(rng, rows, Cc) * 6).astype(np.float32)
+    lab = rng.randint(0, Cc, rows).astype(np.int32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(xt, torch.from_numpy(lab).long())
+    (0.2 * loss).backward()
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    dl = torch.zeros(rows, Cc, device="cuda:0")
+    call("basi_softmax_ce_fwd_bwd", dev(x).data_ptr(), dev(lab).data_ptr(), C.c_int64(rows), Cc,
+         C.c_double(1.0 / rows), C.c_float(0.2 / rows), acc.data_ptr(), dl.data_ptr())
+    assert abs(host(acc)[0] - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+    assert rel_err(host(dl), xt.grad.numpy()) < 1e-5
+
+
+def test_sgd_bit_exact_and_bf16_copy():
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(8)
+    n = 100003
+    w, g = _u(rng, n), _u(rng, n)
+    wd, gd, lr = dev(w), dev(g), dev(np.array([5e-3], dtype=np.float32))
+    wb = torch.zeros(n, dtype=torch.bfloat16, device="cuda:0")
+    call("basi_sgd_step", wd.data_ptr(), gd.data_ptr(), lr.data_ptr(), C.c_int64(n), wb.data_ptr())
+    ref = w - np.float32(5e-3) * g
+    got = host(wd)
+    # fused multiply-add vs separate rounding: allow 1 ulp
+    assert np.max(np.abs(got - ref)) <= np.max(np.abs(np.spacing(ref)))
+    assert np.array_equal(host(wb), torch.from_numpy(got).to(torch.bfloat16).float().numpy())
+
+
+def test_predictions_bit_exact():
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(9)
+    B, P, Cc, S = 2, 8, 4, 64
+    logits = (_u(rng, B, P, P, Cc) * 4).astype(np.float32)
+    logits[0, 0, 0] = [1.0, 1.0, 0.5, 1.0]                      # tie -> first index wins
+    ld = dev(logits)
+    out = torch.zeros(B * P * P, dtype=torch.int32, device="cuda:0")
+    call("basi_argmax", ld.data_ptr(), C.c_int64(B * P * P), Cc, out.data_ptr())
+    assert np.array_equal(host(out).reshape(B, P, P), np.argmax(logits, -1))
+    one = (_u(rng, 1000) * 2).astype(np.float32)
+    one[:3] = [0.5, 0.50000006, 0.49999997]
+    th = torch.zeros(1000, dtype=torch.int32, device="cuda:0")
+    call("basi_threshold", dev(one).data_ptr(), C.c_float(0.5), th.data_ptr(), C.c_int64(1000))
+    assert np.array_equal(host(th), (one > 0.5).astype(np.int32))
+    up = torch.zeros(B * S * S, dtype=torch.int32, device="cuda:0")
+    call("basi_upsample_legacy_argmax", ld.data_ptr(), B, P, P, Cc, S, S, up.data_ptr())
+    ref = O.predict_click(logits, (S, S))
+    agree = np.mean(host(up).reshape(B, S, S) == ref)
+    assert agree >= 0.999, agree                                 # float32 lerp order may flip exact ties only
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("M,K,N,relu", [(16, 25600, 512, True), (2, 512, 21, False), (1, 1600, 64, True), (4, 512, 91, False)])
+def test_skinny_gemms(dtype, M, K, N, relu):
+    from gpu_util import bf16_round, call, dev, host, rel_err
+    rng = np.random.RandomState(10)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    code = 0 if dtype == "f32" else 1
+    a = _u(rng, M, K)
+    if dtype == "bf16":
+        a = bf16_round(a)
+    w, b, dy = _u(rng, K, N) / np.sqrt(K), _u(rng, N), _u(rng, M, N)
+    at = torch.from_numpy(a).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True)
+    y = at @ wt + bt
+    if relu:
+        y = torch.relu(y)
+    (y * torch.from_numpy(dy).double()).sum().backward()
+    ad, wd, bd = dev(a, tdt), dev(w), dev(b)
+    yd = torch.full((M, N), 3.0, device="cuda:0")
+    call("basi_skinny_fwd", ad.data_ptr(), code, C.c_int64(K), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), M, K, N,
+         1 if relu else 0)
+    assert rel_err(host(yd), y.detach().numpy()) < 2e-5
+    dyd = dev(dy)
+    if relu:
+        call("basi_relu_bwd_f32", dyd.data_ptr(), yd.data_ptr(), C.c_int64(M * N))
+    dw, db = torch.zeros(K, N, device="cuda:0"), torch.zeros(N, device="cuda:0")
+    call("basi_skinny_wgrad", ad.data_ptr(), code, C.c_int64(K), dyd.data_ptr(), dw.data_ptr(), db.data_ptr(), M, K, N)
+    assert rel_err(host(dw), wt.grad.numpy()) < 2e-5
+    assert rel_err(host(db), bt.grad.numpy()) < 2e-5
+    da = torch.zeros(M, K, dtype=tdt, device="cuda:0")
+    call("basi_skinny_dgrad", dyd.data_ptr(), wd.data_ptr(), da.data_ptr(), code, C.c_int64(K), M, K, N, 0)
+    assert rel_err(host(da), at.grad.numpy()) < (2e-5 if dtype == "f32" else 1e-2)

@@ -1,0 +1,100 @@
+"""CPU: the graph builder mirrors the reference topology and the engine lowers it to the expected plan."""
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from basi_b200.BAISPSPNet import PSPNet, Placeholder, VARIANTS
+from basi_b200.engine import Engine
+from oracle import basi_oracle as O
+
+
+def build(variant="2AddClass", nseg=1, S=320, F=32, classes=21):
+    return PSPNet({'data': Placeholder((None, S, S, 4))}, num_classes=classes, num_segment=nseg, is_training=True,
+                  last_pool_size=S // 8, filter_number=F, variant=variant)
+
+
+@pytest.mark.parametrize("variant,nseg,classes", [("1NoClass", 1, 21), ("2AddClass", 1, 21), ("4BorderClass", 4, 21),
+                                                  ("5COCO", 3, 91)])
+def test_variables_match_oracle_inventory(variant, nseg, classes):
+    net = build(variant, nseg, classes=classes)
+    spec = O.param_specs(variant, classes, nseg, 32)
+    assert dict(net.variables) == {k: tuple(v) for k, v in spec.items()}
+
+
+def test_layer_shapes_at_320():
+    net = build()
+    L = net.layers
+    assert L['conv1_3_3x3_bn'].shape == (160, 160, 64)
+    assert L['pool1_3x3_s2'].shape == (80, 80, 64)
+    assert L['conv2_3/relu'].shape == (80, 80, 128)
+    assert L['conv3_4/relu'].shape == (40, 40, 256)
+    assert L['conv4_23/relu'].shape == (40, 40, 512)
+    assert L['conv5_3/relu'].shape == (40, 40, 1024)
+    assert [L['conv5_3_pool%d' % l].shape[0] for l in (1, 2, 3, 6)] == [1, 2, 3, 6]
+    assert L['conv5_3_concat'].shape == (40, 40, 2048)
+    assert L['conv6_n'].shape == (40, 40, 1)
+    assert L['class_attention_pool'].shape == (5, 5, 1024)
+    assert L['class_attention_fc'].shape == (21,)
+    assert L['conv6_n'].get_shape()[1:3] == [40, 40]
+
+
+def test_counts_match_survey():
+    net = build()
+    ops = Counter(n.op for n in net.nodes)
+    assert ops["conv"] + ops["fc"] == 114 and ops["batch_normalization"] == 111 and ops["add"] == 33
+
+
+def test_lowered_plan_structure():
+    e = Engine(build(), 2, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
+    f, b = Counter(n for n, _, _ in e.fwd), Counter(n for n, _, _ in e.bwd)
+    assert e.n_params == 29571606
+    assert f["basi_conv_fprop"] == 112 and f["basi_skinny_fwd"] == 2
+    assert f["basi_bn_stats"] == 111 and f["basi_bn_apply"] == 107          # 4 proj BNs folded into junctions
+    assert b["basi_conv_wgrad"] == 112 and b["basi_conv_dgrad"] == 111      # conv1_1 needs no dgrad
+    assert b["basi_bn_bwd_apply"] == 111
+    # the first backward call is the class-head adjoint, the last one the stem's wgrad
+    assert e.bwd[-1][0] == "basi_conv_wgrad"
+
+
+def test_segment_only_plan_has_no_class_head():
+    e = Engine(build("1NoClass"), 2, "f32", True, dict(kind="bce", pos_weight=3.0), dry_run=True)
+    assert e.cls_logits is None and e.n_params == 16453121
+    assert not any(n.startswith("basi_skinny") or n.startswith("basi_gate") for n, _, _ in e.fwd + e.bwd)
+
+
+def test_unknown_variant_and_dry_run_cannot_execute():
+    with pytest.raises(ValueError):
+        build("nope")
+    e = Engine(build(S=64, F=8), 1, "f32", False, None, dry_run=True)
+    from basi_b200 import BasiError
+    with pytest.raises(BasiError):
+        e.forward_device()
+
+
+def test_click_lut_matches_reference_expression_bitwise():
+    from basi_b200.BAISData import Data, click_lut
+    lut = click_lut((320, 320), 30)
+    assert lut.size == 2 * 319 * 319 + 1
+    for where in ([137, 201], [0, 0], [319, 319], [160, 5]):
+        ref = O.mask_gaussian((320, 320), where, 30)
+        yy, xx = np.mgrid[0:320, 0:320]
+        d2 = (xx - where[1]) ** 2 + (yy - where[0]) ** 2
+        assert np.array_equal(lut[d2].view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(Data._mask_gaussian((320, 320), where).view(np.uint32), ref.view(np.uint32))
+    lut20 = click_lut((64, 48), 20)
+    ref = O.mask_gaussian((64, 48), [10, 40], 20)
+    yy, xx = np.mgrid[0:64, 0:48]
+    assert np.array_equal(lut20[(xx - 40) ** 2 + (yy - 10) ** 2].view(np.uint32), ref.view(np.uint32))
+
+
+def test_synthetic_batches_are_reference_shaped():
+    from basi_b200.BAISData import SyntheticData
+    s = SyntheticData(3, (64, 64), 8, 21, 4, seed=1)
+    img, clicks, lab, cls = s.next_batch()
+    assert img.shape == (3, 64, 64, 3) and img.dtype == np.uint8
+    assert lab.shape == (3, 8, 8, 1) and set(np.unique(lab)) <= {0, 1, 2, 3}
+    for b in range(3):
+        assert lab[b, clicks[b, 0] // 8, clicks[b, 1] // 8, 0] == 1       # the click lies on the instance
+    data, ann, c, raw, mask = SyntheticData(2, (64, 64), 8, 21, 1, seed=1).next_batch_train()
+    assert data[0].shape == (64, 64, 4) and data[0].dtype == np.float32 and ann[0].shape == (8, 8, 1)
