@@ -227,13 +227,21 @@ def init_params(specs, seed=0, dtype=np.float32, trained_like=False):
     """glorot_uniform for weights and biases (tf.get_variable default), gamma=1, beta=0.
 
     trained_like=True perturbs gamma/beta so that parity tests do not run on the
-    degenerate gamma=1/beta=0 point (SURVEY section 7 'hard parts').
+    degenerate gamma=1/beta=0 point (SURVEY section 7 'hard parts'), and keeps the residual
+    branches small (increase_bn gamma in [0.05, 0.25]) the way trained residual nets are: a
+    random-init 100-layer batch-stat-BN net is chaotic (float32 vs float64 runs of this very
+    oracle differ by 1e-3 on the logits), which would make any parity tolerance meaningless.
     """
     rng = np.random.RandomState(seed)
     out = OrderedDict()
     for name, shape in specs.items():
         if name.endswith("/gamma"):
-            v = np.ones(shape) if not trained_like else rng.uniform(0.5, 1.5, shape)
+            if not trained_like:
+                v = np.ones(shape)
+            elif name.endswith("increase_bn/gamma"):
+                v = rng.uniform(0.05, 0.25, shape)
+            else:
+                v = rng.uniform(0.5, 1.5, shape)
         elif name.endswith("/beta"):
             v = np.zeros(shape) if not trained_like else rng.uniform(-0.3, 0.3, shape)
         else:

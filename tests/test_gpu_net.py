@@ -63,17 +63,26 @@ def test_train_step_fp32_matches_oracle(case):
     # device-side click map is bit exact
     assert np.array_equal(eng.input.t.cpu().numpy().view(np.uint32), data.view(np.uint32))
     ref = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, lr, torch.float64)
+    # the same oracle in float32 gives the noise floor any float32 implementation has against float64
+    r32 = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, lr, torch.float32)
     loss, lseg, lcls = eng.losses()
     assert abs(lseg - ref["loss_segment"]) < F32_TOL * max(1, abs(ref["loss_segment"]))
     if eng.cls_logits is not None:
         assert abs(lcls - ref["loss_classes"]) < F32_TOL * max(1, abs(ref["loss_classes"]))
-        assert _rel(eng.cls_logits.t.cpu().numpy().reshape(B, -1), ref["cls_logits"]) < F32_TOL
+        e = _rel(eng.cls_logits.t.cpu().numpy().reshape(B, -1), ref["cls_logits"])
+        assert e < F32_TOL + 3 * _rel(r32["cls_logits"], ref["cls_logits"]), e
     assert abs(loss - ref["loss"]) < F32_TOL * max(1, abs(ref["loss"]))
     logits = eng.seg_logits.t.cpu().numpy()
     assert _rel(logits, ref["seg_logits"]) < F32_TOL
     grads = eng.get_grads()
-    worst = max((_rel(grads[n], ref["grads"][n]), n) for n in grads if np.max(np.abs(ref["grads"][n])) > 1e-12)
-    assert worst[0] < 5 * F32_TOL, worst
+    bad = []
+    for n in grads:
+        if np.max(np.abs(ref["grads"][n])) <= 1e-12:
+            continue
+        e, floor = _rel(grads[n], ref["grads"][n]), _rel(r32["grads"][n], ref["grads"][n])
+        if e > F32_TOL + 3 * floor:
+            bad.append((n, e, floor))
+    assert not bad, bad[:5]
     new = eng.get_params()
     worst = max((_rel(new[n], ref["new_params"][n]), n) for n in new)
     assert worst[0] < F32_TOL, worst

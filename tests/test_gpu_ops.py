@@ -36,15 +36,16 @@ def test_clickmap_pack_bit_exact(B, H, W, sigma):
     clicks[0] = [H - 1, 0]
     lut = click_lut((H, W), sigma)
     out = torch.zeros((B, H, W, 4), dtype=torch.float32, device="cuda:0")
-    call("basi_clickmap_pack", dev(img).data_ptr(), 0, dev(clicks).data_ptr(), dev(lut).data_ptr(),
+    imgd, clickd, lutd = dev(img), dev(clicks), dev(lut)
+    call("basi_clickmap_pack", imgd.data_ptr(), 0, clickd.data_ptr(), lutd.data_ptr(),
          C.c_int64(lut.size), out.data_ptr(), B, H, W)
     got = host(out)
     for b in range(B):
         ref = O.pack_input(img[b], clicks[b], sigma)
         assert np.array_equal(got[b].view(np.uint32), ref.view(np.uint32))
     # float-image entry (reference feeds /255 float images)
-    imgf = (img.astype(np.float32) / 255)
-    call("basi_clickmap_pack", dev(imgf).data_ptr(), 1, dev(clicks).data_ptr(), dev(lut).data_ptr(),
+    imgfd = dev(img.astype(np.float32) / 255)
+    call("basi_clickmap_pack", imgfd.data_ptr(), 1, clickd.data_ptr(), lutd.data_ptr(),
          C.c_int64(lut.size), out.data_ptr(), B, H, W)
     assert np.array_equal(host(out).view(np.uint32), got.view(np.uint32))
 
@@ -74,7 +75,7 @@ def _conv_case(case, dtype):
     k, s, d, padding, cin, cout, H, W, B, bias, relu = case
     rng = np.random.RandomState(hash(case) % 1000)
     x = _u(rng, B, H, W, cin)
-    w = _u(rng, k, k, cin, cout) / np.sqrt(k * k * cin)
+    w = (_u(rng, k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
     b = _u(rng, cout) if bias else None
     tdt = torch.float32 if dtype == "f32" else torch.bfloat16
     if dtype == "bf16":
@@ -240,7 +241,8 @@ def test_maxpool_3x3_s2_same(dtype, shape):
         dy = bf16_round(dy)
     (y * nchw(dy).double()).sum().backward()
     dxa = empty_act(shape, tdt, fill=9.0)
-    call("basi_maxpool3s2_bwd", act(dy, tdt).ref, amax.data_ptr(), dxa.ref, 0)
+    dya = act(dy, tdt)
+    call("basi_maxpool3s2_bwd", dya.ref, amax.data_ptr(), dxa.ref, 0)
     assert rel_err(host(dxa), nhwc(xt.grad)) < (1e-6 if dtype == "f32" else 1e-2)
 
 
@@ -265,9 +267,10 @@ def test_avgpool(dtype, H, k, Cc):
         dy = bf16_round(dy)
     (y * nchw(dy).double()).sum().backward()
     dxa = empty_act((B, H, H, Cc), tdt, fill=2.0)
-    call("basi_avgpool_bwd", act(dy, tdt).ref, k, dxa.ref, 0)
+    dya = act(dy, tdt)
+    call("basi_avgpool_bwd", dya.ref, k, dxa.ref, 0)
     assert rel_err(host(dxa), nhwc(xt.grad)) < (1e-5 if dtype == "f32" else 1e-2)
-    call("basi_avgpool_bwd", act(dy, tdt).ref, k, dxa.ref, 1)
+    call("basi_avgpool_bwd", dya.ref, k, dxa.ref, 1)
     assert rel_err(host(dxa), 2 * nhwc(xt.grad)) < (1e-5 if dtype == "f32" else 2e-2)
 
 
@@ -287,7 +290,8 @@ def test_bilinear_align_corners(dtype, o, P):
     wide = torch.zeros((B, P, P, 3 * Cc), dtype=tdt, device="cuda:0")
     from basi_b200.engine import Act
     ya = Act(wide[..., Cc:2 * Cc])
-    call("basi_bilinear_ac_fwd", act(x, tdt).ref, ya.ref)
+    xa = act(x, tdt)
+    call("basi_bilinear_ac_fwd", xa.ref, ya.ref)
     got = host(wide)
     assert rel_err(got[..., Cc:2 * Cc], nhwc(y.detach())) < (1e-5 if dtype == "f32" else 1e-2)
     assert np.all(got[..., :Cc] == 0) and np.all(got[..., 2 * Cc:] == 0)
@@ -297,7 +301,8 @@ def test_bilinear_align_corners(dtype, o, P):
     (y * nchw(dy[..., Cc:2 * Cc]).double()).sum().backward()
     dwide = act(dy, tdt)
     dxa = empty_act((B, o, o, Cc), tdt, fill=4.0)
-    call("basi_bilinear_ac_bwd", Act(dwide.t[..., Cc:2 * Cc]).ref, dxa.ref, 0)
+    dslice = Act(dwide.t[..., Cc:2 * Cc])
+    call("basi_bilinear_ac_bwd", dslice.ref, dxa.ref, 0)
     assert rel_err(host(dxa), nhwc(xt.grad)) < (2e-5 if dtype == "f32" else 1e-2)
 
 
@@ -319,7 +324,8 @@ def test_gate_multiply(dtype, nseg, att):
     assert rel_err(host(ya), y.detach().numpy()) < (1e-6 if dtype == "f32" else 1e-2)
     dfa = empty_act((B, P, P, Cc), tdt, fill=1.0)
     dl = torch.full((B, P, P, nseg), 0.5, device="cuda:0")
-    call("basi_gate_mul_bwd", act(dout, tdt).ref, fa.ref, ld.data_ptr(), nseg, att, dfa.ref, 1, dl.data_ptr())
+    douta = act(dout, tdt)
+    call("basi_gate_mul_bwd", douta.ref, fa.ref, ld.data_ptr(), nseg, att, dfa.ref, 1, dl.data_ptr())
     assert rel_err(host(dfa) - 1.0, ft.grad.numpy()) < (1e-5 if dtype == "f32" else 2e-2)
     assert rel_err(host(dl) - 0.5, lt.grad.numpy()) < 1e-4
 
@@ -336,7 +342,8 @@ def test_weighted_bce_fused(n):
     loss.backward()
     acc = torch.zeros(2, dtype=torch.float64, device="cuda:0")
     dl = torch.zeros(n, device="cuda:0")
-    call("basi_wbce_fwd_bwd", dev(x).data_ptr(), dev(z).data_ptr(), C.c_float(3.0), C.c_double(1.0 / n),
+    xd, zd = dev(x), dev(z)
+    call("basi_wbce_fwd_bwd", xd.data_ptr(), zd.data_ptr(), C.c_float(3.0), C.c_double(1.0 / n),
          C.c_float(1.0 / n), C.c_int64(n), acc.data_ptr(), dl.data_ptr())
     assert abs(host(acc)[0] - loss.item()) < 1e-6 * max(1.0, abs(loss.item()))
     assert rel_err(host(dl), xt.grad.numpy()) < 1e-5
@@ -353,7 +360,8 @@ def test_softmax_ce_fused(rows, Cc):
     (0.2 * loss).backward()
     acc = torch.zeros(2, dtype=torch.float64, device="cuda:0")
     dl = torch.zeros(rows, Cc, device="cuda:0")
-    call("basi_softmax_ce_fwd_bwd", dev(x).data_ptr(), dev(lab).data_ptr(), C.c_int64(rows), Cc,
+    xd, labd = dev(x), dev(lab)
+    call("basi_softmax_ce_fwd_bwd", xd.data_ptr(), labd.data_ptr(), C.c_int64(rows), Cc,
          C.c_double(1.0 / rows), C.c_float(0.2 / rows), acc.data_ptr(), dl.data_ptr())
     assert abs(host(acc)[0] - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
     assert rel_err(host(dl), xt.grad.numpy()) < 1e-5
@@ -387,7 +395,8 @@ def test_predictions_bit_exact():
     one = (_u(rng, 1000) * 2).astype(np.float32)
     one[:3] = [0.5, 0.50000006, 0.49999997]
     th = torch.zeros(1000, dtype=torch.int32, device="cuda:0")
-    call("basi_threshold", dev(one).data_ptr(), C.c_float(0.5), th.data_ptr(), C.c_int64(1000))
+    oned = dev(one)
+    call("basi_threshold", oned.data_ptr(), C.c_float(0.5), th.data_ptr(), C.c_int64(1000))
     assert np.array_equal(host(th), (one > 0.5).astype(np.int32))
     up = torch.zeros(B * S * S, dtype=torch.int32, device="cuda:0")
     call("basi_upsample_legacy_argmax", ld.data_ptr(), B, P, P, Cc, S, S, up.data_ptr())
@@ -406,7 +415,7 @@ def test_skinny_gemms(dtype, M, K, N, relu):
     a = _u(rng, M, K)
     if dtype == "bf16":
         a = bf16_round(a)
-    w, b, dy = _u(rng, K, N) / np.sqrt(K), _u(rng, N), _u(rng, M, N)
+    w, b, dy = (_u(rng, K, N) / np.sqrt(K)).astype(np.float32), _u(rng, N), _u(rng, M, N)
     at = torch.from_numpy(a).double().requires_grad_(True)
     wt = torch.from_numpy(w).double().requires_grad_(True)
     bt = torch.from_numpy(b).double().requires_grad_(True)
