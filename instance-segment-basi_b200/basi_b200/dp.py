@@ -1,0 +1,112 @@
+"""Data parallelism for the training step: one process per GPU, NCCL gradient all-reduce over NVLink.
+
+The reference is single-GPU (os.environ["CUDA_VISIBLE_DEVICES"], back/2AddClass/BAISRunnerTrain.py);
+the path shards by samples: every rank holds a full replica and its own batch slice,
+batch-norm statistics stay per replica (== the reference at batch B/N), and the only exchange is one
+averaged all-reduce of the flat gradient buffer per step.  The buffer is cut into buckets in reverse
+parameter order; each bucket's all-reduce is issued on a side stream as soon as the last backward call
+that writes into it has been enqueued, so the transfer overlaps the remaining backward kernels.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel(object):
+
+    def __init__(self, bucket_bytes=25 << 20, backend=None, device=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        self.backend = backend
+        if backend == "nccl":
+            torch.cuda.set_device(self.local_rank)
+            self.device = torch.device("cuda:%d" % self.local_rank)
+        else:
+            self.device = torch.device(device or "cpu")
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = self.device
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
+        self.bucket_bytes = int(bucket_bytes)
+        self.comm_stream = torch.cuda.Stream(self.device) if backend == "nccl" else None
+        self._plan = None
+
+    # ---- simple (non-overlapped) form: callable on the flat gradient buffer
+    def __call__(self, flat):
+        return self.all_reduce_mean(flat)
+
+    def all_reduce_mean(self, flat):
+        if self.world == 1:
+            return flat
+        if self.backend == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(self.world)
+        return flat
+
+    def broadcast(self, flat, src=0):
+        if self.world > 1:
+            dist.broadcast(flat, src)
+        return flat
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+
+    # ---- bucket plan: which backward call completes which slice of the flat gradient buffer
+    @staticmethod
+    def plan_buckets(param_index, bwd_calls, n_flat, bucket_elems):
+        """Returns [(call_index, start, end)]: after bwd_calls[call_index] has been enqueued, flat[start:end]
+        is final.  Buckets are cut from the end of the buffer (the head's parameters finish first)."""
+        last_writer = {}
+        for i, call in enumerate(bwd_calls):
+            for name in call[3].get("writes", ()):
+                last_writer[name] = i
+        names = list(param_index.keys())
+        offs = [param_index[n][0] for n in names] + [n_flat]
+        buckets = []
+        end = n_flat
+        ready = -1
+        for j in range(len(names) - 1, -1, -1):
+            ready = max(ready, last_writer.get(names[j], -1))
+            start = offs[j]
+            if end - start >= bucket_elems or j == 0:
+                buckets.append((ready, start, end))
+                end, ready = start, -1
+        # a bucket must not be launched before an earlier-cut bucket (keeps every rank's collective order equal)
+        out, hi = [], -1
+        for ready, start, end in buckets:
+            hi = max(hi, ready)
+            out.append((hi, start, end))
+        return out
+
+    def run_backward(self, engine, st):
+        """Runs engine.bwd on the current stream, launching bucket all-reduces on the side stream."""
+        if self._plan is None:
+            self._plan = self.plan_buckets(engine.param_index, engine.bwd, engine.n_flat,
+                                           max(1, self.bucket_bytes // 4))
+        calls = engine.bwd
+        cur = torch.cuda.current_stream(self.device)
+        pos = 0
+        for ready, start, end in self._plan:
+            if ready + 1 > pos:
+                engine._run(calls[pos:ready + 1], st)
+                pos = ready + 1
+            if self.world > 1:
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(engine.grads_flat[start:end], op=dist.ReduceOp.AVG)
+        if pos < len(calls):
+            engine._run(calls[pos:], st)
+        if self.world > 1:
+            cur.wait_stream(self.comm_stream)

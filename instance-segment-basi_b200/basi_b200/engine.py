@@ -175,9 +175,10 @@ class Engine(object):
             act.grad = Act(torch.zeros_like(act.t))
         return act.grad
 
-    def _call(self, lst, name, *args):
+    def _call(self, lst, name, *args, **meta):
+        """Appends one C-ABI call; meta: flops / bytes (algorithmic, for the roofline) and writes=[param names]."""
         fn = getattr(_lib.load(), name)
-        lst.append((name, fn, args))
+        lst.append((name, fn, args, meta))
 
     # ------------------------------------------------------------------ lowering
     def _lower(self):
@@ -387,6 +388,11 @@ class Engine(object):
         self._ops.append(("skinny", op))
         self._emit_skinny_fwd(op)
 
+    @staticmethod
+    def _conv_flops(op):
+        y, d, x = op["y"], op["desc"], op["x"]
+        return 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * d.kh * d.kw * x.shape[3]
+
     # ---- forward emitters
     def _emit_conv_fwd(self, op):
         x, y = op["x"], op["y"]
@@ -395,17 +401,23 @@ class Engine(object):
             if _lib.load().basi_tc_conv_supported(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
                 self._emit_tc(op, _lib.TC_FPROP, self.fwd)
                 return
-        self._call(self.fwd, "basi_conv_fprop", C.byref(op["desc"]), x.ref, self._pptr(op["w"]), bptr, y.ref)
+        self._call(self.fwd, "basi_conv_fprop", C.byref(op["desc"]), x.ref, self._pptr(op["w"]), bptr, y.ref,
+                   flops=self._conv_flops(op))
+
+    @staticmethod
+    def _nbytes(act):
+        return float(np.prod(act.shape)) * act.t.element_size()
 
     def _emit_bn_stats(self, rec):
-        self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums)
+        self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums, bytes=self._nbytes(rec.x))
         self._call(self.fwd, "basi_bn_finalize", rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
                    C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.C)
 
     def _emit_bnact_fwd(self, op):
         main, res, res_bn = op["main"], op["res"], op["res_bn"]
         self._call(self.fwd, "basi_bn_apply", main.x.ref, main.bnp.data_ptr(), res.ref if res is not None else None,
-                   res_bn.bnp.data_ptr() if res_bn is not None else None, 1 if op["relu"] else 0, op["out"].ref)
+                   res_bn.bnp.data_ptr() if res_bn is not None else None, 1 if op["relu"] else 0, op["out"].ref,
+                   bytes=self._nbytes(main.x) * (2 + (1 if res is not None else 0)))
 
     def _emit_skinny_fwd(self, op):
         x, y = op["x"], op["y"]
@@ -506,13 +518,15 @@ class Engine(object):
             self._emit_tc(op, _lib.TC_WGRAD, self.bwd)
         else:
             self._call(self.bwd, "basi_conv_wgrad", dptr, x.ref, dy.ref, self._gptr(op["w"]),
-                       self._gptr(op["b"]) if op["b"] else None)
+                       self._gptr(op["b"]) if op["b"] else None, flops=self._conv_flops(op),
+                       writes=[op["w"]] + ([op["b"]] if op["b"] else []))
         if need_dx:
             acc = self._acc_flag(x)
             if tc_ok and lib.basi_tc_conv_supported(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1:
                 self._emit_tc(op, _lib.TC_DGRAD, self.bwd, acc)
             else:
-                self._call(self.bwd, "basi_conv_dgrad", dptr, dy.ref, self._pptr(op["w"]), x.grad.ref, acc)
+                self._call(self.bwd, "basi_conv_dgrad", dptr, dy.ref, self._pptr(op["w"]), x.grad.ref, acc,
+                           flops=self._conv_flops(op))
 
     def _bwd_bnact(self, op):
         out = op["out"]
@@ -530,11 +544,14 @@ class Engine(object):
             if is_main and op["res"] is not None and op["res_bn"] is None:
                 dacc = self._acc_flag(op["res"])
                 dres = op["res"].grad.ref
-            self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), rec.dsums)
+            nb = self._nbytes(x)
+            self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), rec.dsums,
+                       bytes=nb * (3 if mask is not None else 2))
             self._call(self.bwd, "basi_bn_bwd_finalize", rec.dsums, C.c_double(rec.count), self._gptr(rec.gamma),
-                       self._gptr(rec.beta), rec.coef.data_ptr(), rec.C)
+                       self._gptr(rec.beta), rec.coef.data_ptr(), rec.C, writes=[rec.gamma, rec.beta])
             self._call(self.bwd, "basi_bn_bwd_apply", dout.ref, mask, x.ref, rec.bnp.data_ptr(),
-                       rec.coef.data_ptr(), dx.ref, dres, dacc)
+                       rec.coef.data_ptr(), dx.ref, dres, dacc,
+                       bytes=nb * ((4 if mask is not None else 3) + (0 if dres is None else (2 if dacc else 1))))
 
     def _bwd_maxpool(self, op):
         x, y = op["x"], op["y"]
@@ -565,7 +582,8 @@ class Engine(object):
         if op["relu"]:
             self._call(self.bwd, "basi_relu_bwd_f32", dy.t.data_ptr(), y.t.data_ptr(), C.c_int64(self.B * op["N"]))
         self._call(self.bwd, "basi_skinny_wgrad", x.t.data_ptr(), x.dtype, C.c_int64(op["lda"]), dy.t.data_ptr(),
-                   self._gptr(op["w"]), self._gptr(op["b"]) if op["b"] else None, self.B, op["K"], op["N"])
+                   self._gptr(op["w"]), self._gptr(op["b"]) if op["b"] else None, self.B, op["K"], op["N"],
+                   writes=[op["w"]] + ([op["b"]] if op["b"] else []))
         acc = self._acc_flag(x)
         self._call(self.bwd, "basi_skinny_dgrad", dy.t.data_ptr(), self._pptr(op["w"]), x.grad.t.data_ptr(), x.dtype,
                    C.c_int64(op["lda"]), self.B, op["K"], op["N"], acc)
@@ -592,7 +610,10 @@ class Engine(object):
                       self._gptr(op["w"]), 1, C.byref(handle))
         self._tc_plans.append(handle)
         self.tc_layers += 1
-        lst.append(("basi_tc_conv_run", lib.basi_tc_conv_run, (handle,)))
+        meta = dict(flops=self._conv_flops(op))
+        if kind == _lib.TC_WGRAD:
+            meta["writes"] = [op["w"]]
+        lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))
 
     def _refresh_weight_copies(self, stream=None):
         if not self._tc_weights:
@@ -613,7 +634,7 @@ class Engine(object):
     def _run(self, lst, st):
         if self.dry_run:
             raise _lib.BasiError("dry_run engine cannot execute")
-        for name, fn, args in lst:
+        for name, fn, args, _ in lst:
             rc = fn(*args, st)
             if rc != 0:
                 raise _lib.BasiError("%s failed (%d): %s" % (name, rc, _lib.last_error()))
@@ -664,9 +685,12 @@ class Engine(object):
         self._run(self.fwd, st)
         self._run(self.lossl, st)
         self._run(self.post, st)
-        self._run(self.bwd, st)
-        if sync_grads is not None:
-            sync_grads(self.grads_flat)
+        if sync_grads is not None and hasattr(sync_grads, "run_backward"):
+            sync_grads.run_backward(self, st)          # bucketed all-reduce overlapped with the backward calls
+        else:
+            self._run(self.bwd, st)
+            if sync_grads is not None:
+                sync_grads(self.grads_flat)
         _lib.call("basi_sgd_step", self.params_flat.data_ptr(), self.grads_flat.data_ptr(), self.lr_dev.data_ptr(),
                   C.c_int64(self.n_flat), None, st)
         self._refresh_weight_copies(st)

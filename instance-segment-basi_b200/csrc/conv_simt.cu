@@ -196,6 +196,12 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const GemmConv g) {
   for (int kt = 0; kt < ktiles; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < ktiles) load_tile((kt + 1) * BK);
+    // two-level summation: a fresh partial per k-tile keeps the fp32 error growth at sqrt(K/16)
+    float part[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
@@ -206,8 +212,12 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const GemmConv g) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     if (kt + 1 < ktiles) {
       store_tile(buf ^ 1);
       __syncthreads();
@@ -356,6 +366,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradConv g) {
     for (int c = 0; c < chunks; ++c) {
       const int buf = c & 1;
       if (c + 1 < chunks) load_chunk(mbeg + (c + 1) * WP);
+      float part[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
       for (int p = 0; p < WP; ++p) {
         float4 a = *reinterpret_cast<const float4*>(&As[buf][p][tk * 4]);
@@ -365,8 +380,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradConv g) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
       if (c + 1 < chunks) {
         store_chunk(buf ^ 1);
         __syncthreads();

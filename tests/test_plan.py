@@ -47,7 +47,7 @@ def test_counts_match_survey():
 
 def test_lowered_plan_structure():
     e = Engine(build(), 2, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
-    f, b = Counter(n for n, _, _ in e.fwd), Counter(n for n, _, _ in e.bwd)
+    f, b = Counter(n for n, _, _, _ in e.fwd), Counter(n for n, _, _, _ in e.bwd)
     assert e.n_params == 29571606
     assert f["basi_conv_fprop"] == 112 and f["basi_skinny_fwd"] == 2
     assert f["basi_bn_stats"] == 111 and f["basi_bn_apply"] == 107          # 4 proj BNs folded into junctions
@@ -60,7 +60,7 @@ def test_lowered_plan_structure():
 def test_segment_only_plan_has_no_class_head():
     e = Engine(build("1NoClass"), 2, "f32", True, dict(kind="bce", pos_weight=3.0), dry_run=True)
     assert e.cls_logits is None and e.n_params == 16453121
-    assert not any(n.startswith("basi_skinny") or n.startswith("basi_gate") for n, _, _ in e.fwd + e.bwd)
+    assert not any(n.startswith("basi_skinny") or n.startswith("basi_gate") for n, _, _, _ in e.fwd + e.bwd)
 
 
 def test_unknown_variant_and_dry_run_cannot_execute():
