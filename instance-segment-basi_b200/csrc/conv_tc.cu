@@ -1,16 +1,721 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution path (placeholder until the kernels land).
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (bf16 operands, fp32 accumulate in TMEM).
+//
+//   fprop / dgrad :  D[128 pixels][BN ch] = sum_{tap, 64-ch chunk} A_tap[128 px][64] * B_tap[BN][64]^T
+//       A_tap is a 4-D TMA box (64 ch, TW, TH, TN) of the NHWC activation shifted by the filter tap;
+//       out-of-image coordinates are zero-filled by TMA, which *is* the convolution padding.
+//       B_tap is a 3-D TMA box of the bf16 weights laid out [tap][N][K] (K contiguous).
+//       Both land in shared memory in the canonical K-major SWIZZLE_128B layout that tcgen05.mma reads.
+//   wgrad        :  dW_tap[128 ci][BN co] += sum_{pixel tiles} X_tap[px][ci]^T * dY[px][co]
+//       the same boxes, consumed as MN-major operands (pixels are the GEMM K dimension), split over
+//       pixel tiles across CTAs, fp32 red.global.add epilogue into the HWIO gradient.
+//
+// Persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).  Two TMEM accumulators
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace basi {
+namespace tc {
+
+constexpr int BM = 128;            // pixels per tile (UMMA M)
+constexpr int KC = 64;             // channels per k-chunk: 64 bf16 = 128 B = one swizzle row
+constexpr int A_BYTES = BM * 128;  // 16 KB
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+      printf("basi tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
+//   K-major : LBO unused (1), SBO = 1024 B (8 rows of 128 B)
+//   MN-major: LBO = distance between 64-element MN blocks, SBO = 1024 B (8 k-rows of 128 B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct ConvParams {
+  // tiling of the destination pixels: tile = TN images x TH rows x TW cols = 128 pixels
+  int TW, TH, TN;
+  int tiles_w, tiles_h, tiles_n;   // number of tiles per axis
+  int m_tiles, n_tiles;
+  int N, H, W;                     // destination tensor extents
+  int ldd;                         // destination pixel stride (elements)
+  int Cdst;                        // destination channels
+  int taps, kw;
+  int k_chunks;                    // source channels / 64
+  // source coordinate of tap (r,s) for destination pixel p: p*1 + off0 + r*step (fprop: off0=-pad, step=dil;
+  // dgrad: off0=+pad, step=-dil)
+  int off_h, off_w, step;
+  int accumulate;
+  int stages;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// fprop / dgrad
+// ------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               bf16* __restrict__ dst, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int STAGE = SmemLayout<BN>::STAGE;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
+  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
+  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int ksteps = p.taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const int sh = h0 + p.off_h + r * p.step, sw = w0 + p.off_w + s * p.step;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, STAGE);
+            tma_load_4d(sa, &mapA, fb, kc * KC, sw, sh, n0);
+            tma_load_3d(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+          const uint64_t adesc = make_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_desc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          }
+          umma_commit(empty0 + 8 * stage);   // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull0 + 8 * acc);       // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global (bf16) =====================
+    const int q = warp - 4;                  // TMEM lane quarter
+    const int row = q * 32 + lane;           // pixel row inside the tile
+    const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.TW + wl, h = th * p.TH + hl, n = tn * p.TN + nl;
+      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+      bf16* out = dst + (((int64_t)n * p.H + h) * p.W + w) * p.ldd + nt * BN;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        if (valid) {
+          uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+            if (p.accumulate) {
+              uint4 old = o4[v];
+              const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[2 * j] += __uint_as_float(ow[j] << 16);
+                f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
+              }
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            o4[v] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// wgrad: one work item = (tap, ci tile of 128, co tile of BN, pixel-tile range); fp32 atomics into dW (HWIO)
+// ------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int TW, TH, TN;
+  int tiles_w, tiles_h, tiles_n, m_tiles;
+  int taps, kw;
+  int ci_tiles, co_tiles;   // Cin/128, Cout/BN
+  int splits, tiles_per_split;
+  int off_h, off_w, step;   // x coordinate = p + off + r*step (fprop mapping)
+  int Cin, Cout;
+  int stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG,
+                float* __restrict__ dw, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int XB = 2 * A_BYTES;            // 128 ci = two 64-channel boxes of [128 px][128 B]
+  constexpr int GB = (BN / 64) * A_BYTES;    // BN co = BN/64 boxes
+  constexpr int STAGE = XB + GB;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages, tfull = empty0 + 8 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item of this CTA
+  int wi = blockIdx.x;
+  const int split = wi % p.splits; wi /= p.splits;
+  const int cot = wi % p.co_tiles; wi /= p.co_tiles;
+  const int cit = wi % p.ci_tiles; wi /= p.ci_tiles;
+  const int tap = wi;
+  const int r = tap / p.kw, s = tap - r * p.kw;
+  const int mt_beg = split * p.tiles_per_split;
+  const int mt_end = min(p.m_tiles, mt_beg + p.tiles_per_split);
+  const int nsteps = mt_end - mt_beg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = mt_beg; mt < mt_end; ++mt) {
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+        const uint32_t fb = full0 + 8 * stage;
+        mbar_expect_tx(fb, STAGE);
+        tma_load_4d(sa, &mapX, fb, cit * 128, w0 + p.off_w + s * p.step, h0 + p.off_h + r * p.step, n0);
+        tma_load_4d(sa + A_BYTES, &mapX, fb, cit * 128 + 64, w0 + p.off_w + s * p.step, h0 + p.off_h + r * p.step, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sa + XB + j * A_BYTES, &mapG, fb, cot * BN + j * 64, w0, h0, n0);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = 0; st < nsteps; ++st) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+        // MN-major: LBO = 16 KB between 64-channel blocks, SBO = 1 KB between groups of 8 pixel rows
+        const uint64_t adesc = make_desc(sa, A_BYTES, 1024);
+        const uint64_t bdesc = make_desc(sa + XB, A_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < BM / 16; ++k) {
+          // 16 pixels (K) further = 16 rows of 128 B = 2 KB -> +128 in 16-B units
+          umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (st | k) != 0);
+        }
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int ci = cit * 128 + q * 32 + lane;
+    if (nsteps > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      float* out = dw + ((int64_t)tap * p.Cin + ci) * p.Cout + cot * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + c * 32, rr);
+        if (ci < p.Cin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(out + c * 32 + j, __uint_as_float(rr[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// w f32 [taps][cin][cout] -> bf16 [taps][cin][cout] and bf16 [taps][cout][cin]
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ w_io, bf16* __restrict__ w_oi,
+                                    int taps, int cin, int cout) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const float* src = w + (size_t)tap * cin * cout;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int ci = ci0 + i, co = co0 + threadIdx.x;
+    float v = (ci < cin && co < cout) ? src[(size_t)ci * cout + co] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (ci < cin && co < cout) w_io[(size_t)tap * cin * cout + (size_t)ci * cout + co] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (ci < cin && co < cout)
+      w_oi[(size_t)tap * cin * cout + (size_t)co * cin + ci] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// NHWC activation: dims (C, W, H, N), box (64, TW, TH, TN)
+static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, int TN) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc: cuTensorMapEncodeTiled not available");
+    return BASI_E_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->ld * 2 * t->w, (cuuint64_t)t->ld * 2 * t->w * t->h};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc: cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
+    return BASI_E_CUDA;
+  }
+  return BASI_OK;
+}
+// weights [taps][Ndim][Kdim] bf16, box (64, BN, 1)
+static int make_w_map(CUtensorMap* m, const void* w, int taps, int ndim, int kdim, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc: cuTensorMapEncodeTiled not available");
+    return BASI_E_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ndim, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)kdim * 2, (cuuint64_t)kdim * 2 * ndim};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    return BASI_E_CUDA;
+  }
+  return BASI_OK;
+}
+
+static void pick_tile(int N, int H, int W, int* TW, int* TH, int* TN) {
+  long best = -1;
+  for (int tw = 1; tw <= 128; tw *= 2)
+    for (int th = 1; tw * th <= 128; th *= 2) {
+      int tn = 128 / (tw * th);
+      if (tw > 256 || th > 256 || tn > 256) continue;
+      long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((N + tn - 1) / tn);
+      // fewer tiles first (less padding waste); then prefer wide rows (longer contiguous runs)
+      long score = tiles * 1024 - tw;
+      if (best < 0 || score < best) {
+        best = score;
+        *TW = tw; *TH = th; *TN = tn;
+      }
+    }
+}
+
+}  // namespace tc
+}  // namespace basi
+
+using namespace basi;
+using namespace basi::tc;
+
+struct basi_tc_conv {
+  int kind;
+  int bn;
+  CUtensorMap mapA, mapB;
+  ConvParams cp;
+  WgradParams wp;
+  bf16* dst;
+  float* dw;
+  int grid;
+  size_t smem;
+};
+
+static bool tc_geometry_ok(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  if (!d || !x || !y) return false;
+  if (x->dtype != BASI_BF16 || y->dtype != BASI_BF16) return false;
+  if (d->stride != 1 || d->kh != d->kw || d->relu) return false;
+  if (x->n != y->n) return false;
+  // 'same-size' convolutions only: output extent == input extent, symmetric padding
+  const int span = (d->kh - 1) * d->dil;
+  if (y->h != x->h || y->w != x->w || 2 * d->pad_t != span || 2 * d->pad_l != span) return false;
+  if (x->ld % 8 || y->ld % 8) return false;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
+  const int cin = x->c, cout = y->c;
+  if (kind == BASI_TC_FPROP) return cin % 64 == 0 && cout % 32 == 0;
+  if (kind == BASI_TC_DGRAD) return cout % 64 == 0 && cin % 32 == 0;
+  if (kind == BASI_TC_WGRAD) return cin % 128 == 0 && cout % 64 == 0;
+  return false;
+}
+
+template <int BN>
+static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->dst, pl->cp);
+  return BASI_OK;
+}
+template <int BN>
+static int launch_wgrad(basi_tc_conv* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  wgrad_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->dw, pl->wp);
+  return BASI_OK;
+}
+
 extern "C" {
-int basi_tc_conv_supported(int, const basi_conv_desc*, const basi_tensor*, const basi_tensor*) { return 0; }
-int basi_tc_pack_weights(const float*, void*, void*, int, int, int, void*) {
-  basi::set_error("tc path not built");
-  return BASI_E_INVALID;
+
+int basi_tc_conv_supported(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  return tc_geometry_ok(kind, d, x, y) ? 1 : 0;
 }
-int basi_tc_conv_create(int, const basi_conv_desc*, const basi_tensor*, const basi_tensor*, const void*, float*, int,
-                        basi_tc_conv**) {
-  basi::set_error("tc path not built");
-  return BASI_E_INVALID;
+
+int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int taps, int cin, int cout, void* stream) {
+  BASI_CHECK_ARG(w && w_io_bf16 && w_oi_bf16 && taps > 0 && cin > 0 && cout > 0, "tc_pack_weights: bad argument");
+  dim3 grid((cout + 31) / 32, (cin + 31) / 32, taps), block(32, 8);
+  pack_weights_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (bf16*)w_io_bf16, (bf16*)w_oi_bf16, taps, cin, cout);
+  BASI_CHECK_LAUNCH("tc_pack_weights");
+  return BASI_OK;
 }
-int basi_tc_conv_run(basi_tc_conv*, void*) { return BASI_E_INVALID; }
-void basi_tc_conv_destroy(basi_tc_conv*) {}
+
+/* kind FPROP: a = x, b = y (written), w_bf16 = [tap][Cout][Cin]
+ * kind DGRAD: a = dy, b = dx (written / accumulated), w_bf16 = [tap][Cin][Cout]
+ * kind WGRAD: a = x, b = dy, dw = HWIO float32 gradient (added into) */
+int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
+                        const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out) {
+  BASI_CHECK_ARG(d && a && b && out, "tc_conv_create: null argument");
+  const basi_tensor* x = (kind == BASI_TC_DGRAD) ? b : a;   // forward input geometry
+  const basi_tensor* y = (kind == BASI_TC_DGRAD) ? a : b;   // forward output geometry
+  BASI_CHECK_ARG(tc_geometry_ok(kind, d, x, y), "tc_conv_create: geometry not supported by the tcgen05 path");
+  basi_tc_conv* pl = new basi_tc_conv();
+  memset(pl, 0, sizeof(*pl));
+  pl->kind = kind;
+  int TW, TH, TN;
+  pick_tile(x->n, x->h, x->w, &TW, &TH, &TN);
+  const int tiles_w = (x->w + TW - 1) / TW, tiles_h = (x->h + TH - 1) / TH, tiles_n = (x->n + TN - 1) / TN;
+  const int m_tiles = tiles_w * tiles_h * tiles_n;
+  const int sms = basi::sm_count();
+  int rc = BASI_OK;
+  if (kind == BASI_TC_FPROP || kind == BASI_TC_DGRAD) {
+    BASI_CHECK_ARG(w_bf16, "tc_conv_create: null weights");
+    const basi_tensor* src = a;
+    const basi_tensor* dstt = b;
+    const int ndim = dstt->c, kdim = src->c;
+    int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
+    pl->bn = bn;
+    rc = make_act_map(&pl->mapA, src, TW, TH, TN);
+    if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, bn);
+    if (rc != BASI_OK) {
+      delete pl;
+      return rc;
+    }
+    ConvParams& cp = pl->cp;
+    cp.TW = TW; cp.TH = TH; cp.TN = TN;
+    cp.tiles_w = tiles_w; cp.tiles_h = tiles_h; cp.tiles_n = tiles_n;
+    cp.m_tiles = m_tiles; cp.n_tiles = ndim / bn;
+    cp.N = dstt->n; cp.H = dstt->h; cp.W = dstt->w; cp.ldd = dstt->ld; cp.Cdst = dstt->c;
+    cp.taps = d->kh * d->kw; cp.kw = d->kw; cp.k_chunks = kdim / 64;
+    if (kind == BASI_TC_FPROP) {
+      cp.off_h = -d->pad_t; cp.off_w = -d->pad_l; cp.step = d->dil;
+    } else {
+      cp.off_h = d->pad_t; cp.off_w = d->pad_l; cp.step = -d->dil;
+    }
+    cp.accumulate = accumulate;
+    const int stage_bytes = A_BYTES + bn * 128;
+    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    if (stages > 8) stages = 8;
+    cp.stages = stages;
+    pl->smem = (size_t)stages * stage_bytes + 1024 + 256;
+    pl->dst = (bf16*)dstt->ptr;
+    const int total = cp.m_tiles * cp.n_tiles;
+    pl->grid = total < sms ? total : sms;
+  } else {
+    BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
+    const int cin = a->c, cout = b->c;
+    int bn = cout % 128 == 0 ? 128 : 64;
+    pl->bn = bn;
+    rc = make_act_map(&pl->mapA, a, TW, TH, TN);
+    if (rc == BASI_OK) rc = make_act_map(&pl->mapB, b, TW, TH, TN);
+    if (rc != BASI_OK) {
+      delete pl;
+      return rc;
+    }
+    WgradParams& wp = pl->wp;
+    wp.TW = TW; wp.TH = TH; wp.TN = TN;
+    wp.tiles_w = tiles_w; wp.tiles_h = tiles_h; wp.tiles_n = tiles_n; wp.m_tiles = m_tiles;
+    wp.taps = d->kh * d->kw; wp.kw = d->kw;
+    wp.ci_tiles = cin / 128; wp.co_tiles = cout / bn;
+    wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
+    wp.Cin = cin; wp.Cout = cout;
+    const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
+    int splits = (2 * sms + out_tiles - 1) / out_tiles;
+    if (splits > m_tiles) splits = m_tiles;
+    if (splits < 1) splits = 1;
+    wp.tiles_per_split = (m_tiles + splits - 1) / splits;
+    wp.splits = (m_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
+    const int stage_bytes = 2 * A_BYTES + (bn / 64) * A_BYTES;
+    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    if (stages > 6) stages = 6;
+    wp.stages = stages;
+    pl->smem = (size_t)stages * stage_bytes + 1024 + 256;
+    pl->dw = dw;
+    pl->grid = out_tiles * wp.splits;
+  }
+  *out = pl;
+  return BASI_OK;
 }
+
+int basi_tc_conv_run(basi_tc_conv* pl, void* stream) {
+  BASI_CHECK_ARG(pl, "tc_conv_run: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->kind == BASI_TC_WGRAD) {
+    if (pl->bn == 128) launch_wgrad<128>(pl, st);
+    else launch_wgrad<64>(pl, st);
+  } else {
+    if (pl->bn == 128) launch_conv<128>(pl, st);
+    else if (pl->bn == 64) launch_conv<64>(pl, st);
+    else launch_conv<32>(pl, st);
+  }
+  BASI_CHECK_LAUNCH("tc_conv_run");
+  return BASI_OK;
+}
+
+void basi_tc_conv_destroy(basi_tc_conv* pl) { delete pl; }
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""GPU parity of the tcgen05/TMEM/TMA implicit-GEMM convolutions (fprop, dgrad, wgrad) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import basi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# k, dil, Cin, Cout, H, W, B
+TC_CASES = [
+    (1, 1, 64, 128, 16, 16, 2),
+    (1, 1, 64, 32, 80, 80, 1),      # conv2 reduce, N tile 32
+    (3, 1, 64, 64, 40, 40, 2),      # conv3 3x3 (tile 8x8x2)
+    (3, 2, 128, 128, 40, 40, 3),    # conv4 dilated, odd batch -> image-axis overhang
+    (3, 4, 256, 256, 24, 24, 1),    # conv5 dilated, B=1
+    (1, 1, 512, 128, 40, 40, 2),
+    (1, 1, 128, 512, 40, 40, 2),
+    (3, 1, 256, 64, 20, 12, 2),     # ragged map -> partial tiles
+]
+
+
+def _tc_case(case, sliced=False):
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    from basi_b200.engine import Act
+    from gpu_util import bf16_round, call, dev, host
+    k, d, cin, cout, H, W, B = case
+    rng = np.random.RandomState(sum(case))
+    x = bf16_round(rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32))
+    w = bf16_round((rng.uniform(-1, 1, (k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32))
+    dy = bf16_round(rng.uniform(-1, 1, (B, H, W, cout)).astype(np.float32))
+    pad = d * (k - 1) // 2
+    desc = ConvDesc(k, k, 1, d, pad, pad, 0)
+    bt = torch.bfloat16
+    if sliced:   # operands are channel slices of wider buffers (the PSP concat case)
+        xw = torch.zeros((B, H, W, cin + 128), dtype=bt, device="cuda:0")
+        xw[..., 64:64 + cin] = torch.from_numpy(x).to("cuda:0").to(bt)
+        xa = Act(xw[..., 64:64 + cin])
+        yw = torch.full((B, H, W, cout + 64), 3.0, dtype=bt, device="cuda:0")
+        ya = Act(yw[..., 32:32 + cout])
+    else:
+        xa = Act(torch.from_numpy(x).to("cuda:0").to(bt).contiguous())
+        ya = Act(torch.full((B, H, W, cout), 3.0, dtype=bt, device="cuda:0"))
+    wd = dev(w)
+    w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    call("basi_tc_pack_weights", wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout)
+    lib = _lib.load()
+    res = {}
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    yref = O.conv2d(xt, wt, 1, pad, d)
+    (yref * torch.from_numpy(dy).permute(0, 3, 1, 2).double()).sum().backward()
+    res["y_ref"] = yref.detach().permute(0, 2, 3, 1).numpy()
+    res["dx_ref"] = xt.grad.permute(0, 2, 3, 1).numpy()
+    res["dw_ref"] = wt.grad.numpy()
+    handles = []
+    if lib.basi_tc_conv_supported(0, C.byref(desc), xa.ref, ya.ref) == 1:
+        h = C.c_void_p()
+        _lib.call("basi_tc_conv_create", 0, C.byref(desc), xa.ref, ya.ref, w_oi.data_ptr(), None, 0, C.byref(h))
+        call("basi_tc_conv_run", h)
+        res["y"] = host(ya)
+        if sliced:
+            full = host(yw)
+            assert np.all(full[..., :32] == 3.0) and np.all(full[..., 32 + cout:] == 3.0)
+        handles.append(h)
+    dya = Act(torch.from_numpy(dy).to("cuda:0").to(bt).contiguous())
+    dxa = Act(torch.full((B, H, W, cin), 1.0, dtype=bt, device="cuda:0"))
+    if lib.basi_tc_conv_supported(1, C.byref(desc), xa.ref, ya.ref) == 1:
+        h = C.c_void_p()
+        _lib.call("basi_tc_conv_create", 1, C.byref(desc), dya.ref, dxa.ref, w_io.data_ptr(), None, 0, C.byref(h))
+        call("basi_tc_conv_run", h)
+        res["dx"] = host(dxa)
+        h2 = C.c_void_p()
+        _lib.call("basi_tc_conv_create", 1, C.byref(desc), dya.ref, dxa.ref, w_io.data_ptr(), None, 1, C.byref(h2))
+        call("basi_tc_conv_run", h2)
+        res["dx_acc"] = host(dxa)
+        handles += [h, h2]
+    if lib.basi_tc_conv_supported(2, C.byref(desc), xa.ref, ya.ref) == 1:
+        dw = torch.zeros((k, k, cin, cout), dtype=torch.float32, device="cuda:0")
+        h = C.c_void_p()
+        _lib.call("basi_tc_conv_create", 2, C.byref(desc), xa.ref, dya.ref, None, dw.data_ptr(), 1, C.byref(h))
+        call("basi_tc_conv_run", h)
+        res["dw"] = host(dw)
+        handles.append(h)
+    torch.cuda.synchronize()
+    for h in handles:
+        lib.basi_tc_conv_destroy(h)
+    return res
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_conv_matches_oracle(case):
+    from gpu_util import rel_err
+    r = _tc_case(case)
+    assert "y" in r and "dx" in r, "tcgen05 path refused a supported geometry"
+    assert rel_err(r["y"], r["y_ref"]) < 1e-2             # bf16 output rounding only (fp32 accumulate)
+    assert rel_err(r["dx"], r["dx_ref"]) < 1e-2
+    assert rel_err(r["dx_acc"], 2 * r["dx_ref"]) < 2e-2
+    if case[2] % 128 == 0:
+        assert "dw" in r
+        assert rel_err(r["dw"], r["dw_ref"]) < 1e-4      # fp32 accumulate + fp32 atomics, bf16-exact inputs
+
+
+def test_tc_conv_on_channel_slices():
+    from gpu_util import rel_err
+    r = _tc_case((3, 1, 128, 64, 16, 16, 2), sliced=True)
+    assert rel_err(r["y"], r["y_ref"]) < 1e-2
+    assert rel_err(r["dw"], r["dw_ref"]) < 1e-4
+
+
+def test_tc_refuses_unsupported_geometries():
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    from basi_b200.engine import Act
+    lib = _lib.load()
+    bt = torch.bfloat16
+    x = Act(torch.zeros((1, 16, 16, 64), dtype=bt, device="cuda:0"))
+    y = Act(torch.zeros((1, 8, 8, 64), dtype=bt, device="cuda:0"))
+    assert lib.basi_tc_conv_supported(0, C.byref(ConvDesc(1, 1, 2, 1, 0, 0, 0)), x.ref, y.ref) == 0     # stride 2
+    x4 = Act(torch.zeros((1, 16, 16, 32), dtype=bt, device="cuda:0"))
+    y4 = Act(torch.zeros((1, 16, 16, 64), dtype=bt, device="cuda:0"))
+    assert lib.basi_tc_conv_supported(0, C.byref(ConvDesc(3, 3, 1, 1, 1, 1, 0)), x4.ref, y4.ref) == 0   # Cin 32
+    h = C.c_void_p()
+    rc = lib.basi_tc_conv_create(0, C.byref(ConvDesc(3, 3, 1, 1, 1, 1, 0)), x4.ref, y4.ref, None, None, 0, C.byref(h))
+    assert rc == -1 and b"not supported" in lib.basi_last_error()
