@@ -84,24 +84,29 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
                     float* dbias, void* stream);
 
 /* ---- A6/A7: Network.batch_normalization (+relu, +add) (BAISPSPNet.py:204-236, :148-150, :171-173) ----
- * sums: double [2*C] (sum x, sum x^2), ADDED into (caller zeroes). */
-int basi_bn_stats(const basi_tensor* x, double* sums, void* stream);
-/* bnp: float [4*C] = [mean | istd | gamma*istd | beta] (batch mean, biased variance, eps inside sqrt). */
+ * sums: double [2*C] (sum x, sum x^2), ADDED into (caller zeroes); counter: one zeroed uint32 per launch.
+ * When gamma != NULL the last block to finish also writes bnp (fused finalize):
+ * bnp: float [4*C] = [mean | istd | gamma*istd | beta] (batch mean, biased variance, eps inside the sqrt). */
+int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const float* beta, double count, float eps,
+                  float* bnp, uint32_t* counter, void* stream);
 int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, double count, float eps,
                      float* bnp, int C, void* stream);
 /* out = act((x-mean)*scale+beta [+ res | + (res-res_mean)*res_scale+res_beta]); res / res_bnp may be NULL. */
 int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp,
                   int relu, const basi_tensor* out, void* stream);
-/* dsums (double [2*C]) += (sum dy, sum dy*xhat), dy = dout * (out > 0) when out != NULL. */
+/* dsums (double [2*C]) += (sum dy, sum dy*xhat).  dy = dout * (out > 0) when out != NULL; else, when
+ * relu_from_x, dy = dout * ((x-mean)*scale+beta > 0) (plain BN+ReLU: the mask is recomputed, out is not read).
+ * When coef != NULL the last block also does the finalize: dgamma += sum dy*xhat, dbeta += sum dy,
+ * coef (float [2*C]) = dsums / count. */
 int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
-                       double* dsums, void* stream);
-/* dgamma += sum dy*xhat, dbeta += sum dy; coef: float [2*C] = dsums / count. */
+                       int relu_from_x, double* dsums, double count, float* dgamma, float* dbeta, float* coef,
+                       uint32_t* counter, void* stream);
 int basi_bn_bwd_finalize(const double* dsums, double count, float* dgamma, float* dbeta, float* coef, int C,
                          void* stream);
 /* dx = gamma*istd*(dy - coef0 - xhat*coef1); dres (optional) (+)= dy. */
 int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
-                      const float* coef, const basi_tensor* dx, const basi_tensor* dres, int dres_accumulate,
-                      void* stream);
+                      const float* coef, int relu_from_x, const basi_tensor* dx, const basi_tensor* dres,
+                      int dres_accumulate, void* stream);
 
 /* ---- A8: Network.max_pool 3x3 s2 SAME (:152-155, :269), Network.avg_pool k=s VALID (:157-160) ---- */
 int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream);

@@ -59,7 +59,7 @@ class Act(object):
 
 
 class _BNRec(object):
-    __slots__ = ("x", "gamma", "beta", "sums", "dsums", "bnp", "coef", "count", "C")
+    __slots__ = ("x", "gamma", "beta", "sums", "dsums", "bnp", "coef", "count", "C", "cnt_f", "cnt_b")
 
 
 class Engine(object):
@@ -192,8 +192,11 @@ class Engine(object):
         self._cons = cons
         # BN statistic scratch: [fwd sums | bwd sums] as doubles, zeroed once per step
         tot_c = sum(n.shape[-1] for n in nodes if n.op == "batch_normalization")
+        n_bn = sum(1 for n in nodes if n.op == "batch_normalization")
         self.bn_scratch = torch.zeros(4 * tot_c + 8, dtype=torch.float64, device=self.device)
+        self.bn_counters = torch.zeros(2 * n_bn + 2, dtype=torch.int32, device=self.device)   # last-block tickets
         self._bn_off = 0
+        self._bn_idx = 0
         # concat: producers write into slices
         self._slice_of = {}
         for n in nodes:
@@ -280,6 +283,9 @@ class Engine(object):
         rec.sums = base + 8 * self._bn_off
         rec.dsums = base + 8 * (self._bn_off + 2 * Cc)
         self._bn_off += 4 * Cc
+        rec.cnt_f = self.bn_counters.data_ptr() + 8 * self._bn_idx
+        rec.cnt_b = rec.cnt_f + 4
+        self._bn_idx += 1
         rec.bnp = self._alloc((4 * Cc,), torch.float32)
         rec.coef = self._alloc((2 * Cc,), torch.float32)
         followers = self._cons[n.index]
@@ -409,9 +415,8 @@ class Engine(object):
         return float(np.prod(act.shape)) * act.t.element_size()
 
     def _emit_bn_stats(self, rec):
-        self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums, bytes=self._nbytes(rec.x))
-        self._call(self.fwd, "basi_bn_finalize", rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
-                   C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.C)
+        self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
+                   C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.cnt_f, bytes=self._nbytes(rec.x))
 
     def _emit_bnact_fwd(self, op):
         main, res, res_bn = op["main"], op["res"], op["res_bn"]
@@ -532,7 +537,10 @@ class Engine(object):
         out = op["out"]
         dout = out.grad
         assert dout is not None and out.gw
-        mask = out.ref if op["relu"] else None
+        junction = op["res"] is not None
+        # plain BN+ReLU: the mask is recomputed from x (saves reading `out`); junctions need the stored output
+        mask = out.ref if (op["relu"] and junction) else None
+        from_x = 1 if (op["relu"] and not junction) else 0
         recs = [(op["main"], True)]
         if op["res_bn"] is not None:
             recs.append((op["res_bn"], False))
@@ -541,17 +549,17 @@ class Engine(object):
             dx = self._grad_of(x)
             x.gw = True
             dres, dacc = None, 0
-            if is_main and op["res"] is not None and op["res_bn"] is None:
+            if is_main and junction and op["res_bn"] is None:
                 dacc = self._acc_flag(op["res"])
                 dres = op["res"].grad.ref
             nb = self._nbytes(x)
-            self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), rec.dsums,
-                       bytes=nb * (3 if mask is not None else 2))
-            self._call(self.bwd, "basi_bn_bwd_finalize", rec.dsums, C.c_double(rec.count), self._gptr(rec.gamma),
-                       self._gptr(rec.beta), rec.coef.data_ptr(), rec.C, writes=[rec.gamma, rec.beta])
+            nin = 3 if mask is not None else 2
+            self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), from_x, rec.dsums,
+                       C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
+                       rec.cnt_b, bytes=nb * nin, writes=[rec.gamma, rec.beta])
             self._call(self.bwd, "basi_bn_bwd_apply", dout.ref, mask, x.ref, rec.bnp.data_ptr(),
-                       rec.coef.data_ptr(), dx.ref, dres, dacc,
-                       bytes=nb * ((4 if mask is not None else 3) + (0 if dres is None else (2 if dacc else 1))))
+                       rec.coef.data_ptr(), from_x, dx.ref, dres, dacc,
+                       bytes=nb * (nin + 1 + (0 if dres is None else (2 if dacc else 1))))
 
     def _bwd_maxpool(self, op):
         x, y = op["x"], op["y"]
@@ -647,6 +655,7 @@ class Engine(object):
 
     def _zero_step_state(self, st):
         _lib.call("basi_memset", self.bn_scratch.data_ptr(), 0, C.c_int64(self.bn_scratch.numel() * 8), st)
+        _lib.call("basi_memset", self.bn_counters.data_ptr(), 0, C.c_int64(self.bn_counters.numel() * 4), st)
         _lib.call("basi_memset", self.loss_acc.data_ptr(), 0, C.c_int64(32), st)
         if self.training:
             _lib.call("basi_memset", self.grads_flat.data_ptr(), 0, C.c_int64(self.n_flat * 4), st)

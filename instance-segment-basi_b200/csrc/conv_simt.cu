@@ -434,9 +434,9 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
   const int kt = min(SK_KT, K - k0);
-  for (int i = threadIdx.x; i < M * SK_KT; i += 128) {
+  for (int i = threadIdx.x; i < 64 * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
     int m = i / SK_KT, k = i - m * SK_KT;
-    sa[m][k] = k < kt ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+    sa[m][k] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
   }
   __syncthreads();
   if (n >= N) return;
@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict_
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
   const int kt = min(SK_KT, K - k0);
-  for (int i = threadIdx.x; i < M * SK_KT; i += 128) {
+  for (int i = threadIdx.x; i < 64 * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
     int m = i / SK_KT, k = i - m * SK_KT;
-    sa[m][k] = k < kt ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+    sa[m][k] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
   }
   __syncthreads();
   if (n >= N) return;

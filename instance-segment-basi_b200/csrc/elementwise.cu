@@ -29,216 +29,6 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-channel reductions over rows: thread (tx, ty) owns channel group tx (+ blockIdx.y*bdx) and
-// strides over rows with ty.  fp32 partials are flushed to double every 16 rows; block-level
-// reduction in shared memory (double), one double atomicAdd per channel per block.
-// ------------------------------------------------------------------------------------------
-template <int VN>
-__device__ __forceinline__ void block_reduce_to_global(double (&a)[VN], double (&b)[VN], double* ga, double* gb,
-                                                        int c0, bool valid) {
-  extern __shared__ double sred[];  // [blockDim.y][blockDim.x][2*VN]
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  double* mine = sred + ((size_t)ty * blockDim.x + tx) * (2 * VN);
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    mine[i] = a[i];
-    mine[VN + i] = b[i];
-  }
-  __syncthreads();
-  if (ty == 0 && valid) {
-    for (int y = 1; y < blockDim.y; ++y) {
-      const double* o = sred + ((size_t)y * blockDim.x + tx) * (2 * VN);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        a[i] += o[i];
-        b[i] += o[VN + i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      atomicAdd(ga + c0 + i, a[i]);
-      atomicAdd(gb + c0 + i, b[i]);
-    }
-  }
-}
-
-template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ x, int64_t R, int C, int ld, double* __restrict__ sums) {
-  constexpr int VN = Vec<T>::N;
-  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
-  const bool valid = cg * VN < C;
-  const int c0 = cg * VN;
-  double s[VN], q[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.0;
-  if (valid) {
-    const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
-    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-    while (r < R) {
-      float fs[VN], fq[VN];
-#pragma unroll
-      for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
-#pragma unroll 4
-      for (int it = 0; it < 16 && r < R; ++it, r += rstep) {
-        Vec<T> v = Vec<T>::load(x + r * ld + c0);
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          fs[i] += v.v[i];
-          fq[i] = fmaf(v.v[i], v.v[i], fq[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        s[i] += (double)fs[i];
-        q[i] += (double)fq[i];
-      }
-    }
-  }
-  block_reduce_to_global<VN>(s, q, sums, sums + C, c0, valid);
-}
-
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, double count, float eps, float* __restrict__ bnp,
-                                   int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double mean = sums[c] / count;
-  double var = sums[C + c] / count - mean * mean;
-  if (var < 0) var = 0;
-  double istd = 1.0 / sqrt(var + (double)eps);
-  bnp[c] = (float)mean;
-  bnp[C + c] = (float)istd;
-  bnp[2 * C + c] = (float)((double)gamma[c] * istd);
-  bnp[3 * C + c] = beta[c];
-}
-
-template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ bnp,
-                                const T* __restrict__ res, int ldr, const float* __restrict__ rbnp, int relu,
-                                T* __restrict__ out, int ldo, int64_t R, int C) {
-  constexpr int VN = Vec<T>::N;
-  const int cgs = C / VN;
-  const int64_t total = R * cgs;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / cgs;
-    const int c0 = (int)(i - r * cgs) * VN;
-    Vec<T> v = Vec<T>::load(x + r * ldx + c0);
-    Vec<T> rv;
-    if (res) rv = Vec<T>::load(res + r * ldr + c0);
-#pragma unroll
-    for (int j = 0; j < VN; ++j) {
-      const int c = c0 + j;
-      float o = fmaf(v.v[j] - __ldg(bnp + c), __ldg(bnp + 2 * C + c), __ldg(bnp + 3 * C + c));
-      if (res) {
-        float rr = rv.v[j];
-        if (rbnp) rr = fmaf(rr - __ldg(rbnp + c), __ldg(rbnp + 2 * C + c), __ldg(rbnp + 3 * C + c));
-        o += rr;
-      }
-      if (relu) o = fmaxf(o, 0.f);
-      v.v[j] = o;
-    }
-    v.store(out + r * ldo + c0);
-  }
-}
-
-template <typename T>
-__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo,
-                                     const T* __restrict__ x, int ldx, const float* __restrict__ bnp, int64_t R,
-                                     int C, double* __restrict__ dsums) {
-  constexpr int VN = Vec<T>::N;
-  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
-  const bool valid = cg * VN < C;
-  const int c0 = cg * VN;
-  double s[VN], q[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.0;
-  if (valid) {
-    float mean[VN], istd[VN];
-#pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      mean[i] = bnp[c0 + i];
-      istd[i] = bnp[C + c0 + i];
-    }
-    const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
-    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-    while (r < R) {
-      float fs[VN], fq[VN];
-#pragma unroll
-      for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
-#pragma unroll 2
-      for (int it = 0; it < 16 && r < R; ++it, r += rstep) {
-        Vec<T> d = Vec<T>::load(dout + r * ldd + c0);
-        Vec<T> xv = Vec<T>::load(x + r * ldx + c0);
-        if (out) {
-          Vec<T> o = Vec<T>::load(out + r * ldo + c0);
-#pragma unroll
-          for (int i = 0; i < VN; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          fs[i] += d.v[i];
-          fq[i] = fmaf(d.v[i], (xv.v[i] - mean[i]) * istd[i], fq[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        s[i] += (double)fs[i];
-        q[i] += (double)fq[i];
-      }
-    }
-  }
-  block_reduce_to_global<VN>(s, q, dsums, dsums + C, c0, valid);
-}
-
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ dsums, double count, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = dsums[c], s2 = dsums[C + c];
-  dbeta[c] += (float)s1;
-  dgamma[c] += (float)s2;
-  coef[c] = (float)(s1 / count);
-  coef[C + c] = (float)(s2 / count);
-}
-
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo,
-                                    const T* __restrict__ x, int ldx, const float* __restrict__ bnp,
-                                    const float* __restrict__ coef, T* __restrict__ dx, int lddx, T* __restrict__ dres,
-                                    int lddr, int dres_acc, int64_t R, int C) {
-  constexpr int VN = Vec<T>::N;
-  const int cgs = C / VN;
-  const int64_t total = R * cgs;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / cgs;
-    const int c0 = (int)(i - r * cgs) * VN;
-    Vec<T> d = Vec<T>::load(dout + r * ldd + c0);
-    Vec<T> xv = Vec<T>::load(x + r * ldx + c0);
-    if (out) {
-      Vec<T> o = Vec<T>::load(out + r * ldo + c0);
-#pragma unroll
-      for (int j = 0; j < VN; ++j) d.v[j] = o.v[j] > 0.f ? d.v[j] : 0.f;
-    }
-    if (dres) {
-      Vec<T> dr = d;
-      if (dres_acc) {
-        Vec<T> old = Vec<T>::load(dres + r * lddr + c0);
-#pragma unroll
-        for (int j = 0; j < VN; ++j) dr.v[j] += old.v[j];
-      }
-      dr.store(dres + r * lddr + c0);
-    }
-#pragma unroll
-    for (int j = 0; j < VN; ++j) {
-      const int c = c0 + j;
-      float xh = (xv.v[j] - __ldg(bnp + c)) * __ldg(bnp + C + c);
-      d.v[j] = __ldg(bnp + 2 * C + c) * (d.v[j] - __ldg(coef + c) - xh * __ldg(coef + C + c));
-    }
-    d.store(dx + r * lddx + c0);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Pooling
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -727,29 +517,6 @@ __global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restr
     if (!(y[i] > 0.f)) dy[i] = 0.f;
 }
 
-// channel-reduction launch geometry shared by bn_stats / bn_bwd_reduce
-struct RedGeom {
-  dim3 grid, block;
-  size_t smem;
-};
-static RedGeom red_geom(int64_t R, int C, int VN) {
-  int cgs = C / VN;
-  int bx = cgs < 256 ? cgs : 256;
-  int by = 256 / bx;
-  if (by < 1) by = 1;
-  int gy = (cgs + bx - 1) / bx;
-  int64_t want = (R + (int64_t)by * 16 - 1) / ((int64_t)by * 16);  // >= 16 rows per thread
-  int64_t cap = (int64_t)sm_count() * 4 / gy;
-  if (cap < 1) cap = 1;
-  int gx = (int)(want < cap ? want : cap);
-  if (gx < 1) gx = 1;
-  RedGeom g;
-  g.grid = dim3(gx, gy);
-  g.block = dim3(bx, by);
-  g.smem = (size_t)bx * by * 2 * VN * sizeof(double);
-  return g;
-}
-
 }  // namespace basi
 
 using namespace basi;
@@ -793,85 +560,6 @@ int basi_clickmap_pack(const void* img, int img_is_f32, const int32_t* clicks, c
       img_is_f32 ? nullptr : (const uint8_t*)img, img_is_f32 ? (const float*)img : nullptr, clicks, lut, lut_len,
       (float4*)out, B, H, W);
   BASI_CHECK_LAUNCH("clickmap_pack");
-  return BASI_OK;
-}
-
-int basi_bn_stats(const basi_tensor* x, double* sums, void* stream) {
-  BASI_CHECK_ARG(x && sums && vec_ok(x), "bn_stats: tensor must have c,ld multiple of the vector width");
-  int64_t R = pixels(x);
-  DISPATCH_T(x->dtype, {
-    RedGeom g = red_geom(R, x->c, Vec<T>::N);
-    bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>((const T*)x->ptr, R, x->c, x->ld, sums);
-  })
-  BASI_CHECK_LAUNCH("bn_stats");
-  return BASI_OK;
-}
-
-int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, double count, float eps, float* bnp,
-                     int C, void* stream) {
-  BASI_CHECK_ARG(sums && gamma && beta && bnp && C > 0 && count > 0, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, count, eps, bnp, C);
-  BASI_CHECK_LAUNCH("bn_finalize");
-  return BASI_OK;
-}
-
-int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp, int relu,
-                  const basi_tensor* out, void* stream) {
-  BASI_CHECK_ARG(x && bnp && out && vec_ok(x) && vec_ok(out) && same_shape(x, out) && x->dtype == out->dtype,
-                 "bn_apply: bad x/out");
-  BASI_CHECK_ARG(!res || (vec_ok(res) && same_shape(x, res) && res->dtype == x->dtype), "bn_apply: bad residual");
-  int64_t R = pixels(x);
-  DISPATCH_T(x->dtype, {
-    int64_t total = R * (x->c / Vec<T>::N);
-    bn_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)x->ptr, x->ld, bnp, res ? (const T*)res->ptr : nullptr, res ? res->ld : 0, res ? res_bnp : nullptr,
-        relu, (T*)out->ptr, out->ld, R, x->c);
-  })
-  BASI_CHECK_LAUNCH("bn_apply");
-  return BASI_OK;
-}
-
-int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
-                       double* dsums, void* stream) {
-  BASI_CHECK_ARG(dout && x && bnp && dsums && vec_ok(dout) && vec_ok(x) && same_shape(dout, x) &&
-                     dout->dtype == x->dtype,
-                 "bn_bwd_reduce: bad dout/x");
-  BASI_CHECK_ARG(!out || (vec_ok(out) && same_shape(out, x) && out->dtype == x->dtype), "bn_bwd_reduce: bad out");
-  int64_t R = pixels(x);
-  DISPATCH_T(x->dtype, {
-    RedGeom g = red_geom(R, x->c, Vec<T>::N);
-    bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
-        bnp, R, x->c, dsums);
-  })
-  BASI_CHECK_LAUNCH("bn_bwd_reduce");
-  return BASI_OK;
-}
-
-int basi_bn_bwd_finalize(const double* dsums, double count, float* dgamma, float* dbeta, float* coef, int C,
-                         void* stream) {
-  BASI_CHECK_ARG(dsums && dgamma && dbeta && coef && C > 0, "bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dsums, count, dgamma, dbeta, coef, C);
-  BASI_CHECK_LAUNCH("bn_bwd_finalize");
-  return BASI_OK;
-}
-
-int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x, const float* bnp,
-                      const float* coef, const basi_tensor* dx, const basi_tensor* dres, int dres_accumulate,
-                      void* stream) {
-  BASI_CHECK_ARG(dout && x && dx && bnp && coef && vec_ok(dout) && vec_ok(x) && vec_ok(dx) && same_shape(dout, x) &&
-                     same_shape(dx, x) && dout->dtype == x->dtype && dx->dtype == x->dtype,
-                 "bn_bwd_apply: bad dout/x/dx");
-  BASI_CHECK_ARG(!out || (vec_ok(out) && same_shape(out, x) && out->dtype == x->dtype), "bn_bwd_apply: bad out");
-  BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_apply: bad dres");
-  int64_t R = pixels(x);
-  DISPATCH_T(x->dtype, {
-    int64_t total = R * (x->c / Vec<T>::N);
-    bn_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
-        bnp, coef, (T*)dx->ptr, dx->ld, dres ? (T*)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, R, x->c);
-  })
-  BASI_CHECK_LAUNCH("bn_bwd_apply");
   return BASI_OK;
 }
 

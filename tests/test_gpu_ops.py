@@ -167,14 +167,15 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     sums = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda:0")
     bnp, bnp2 = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(4 * Cc, device="cuda:0")
     gd, bd, g2d, b2d = dev(gamma), dev(beta), dev(gamma2), dev(beta2)
-    call("basi_bn_stats", xa.ref, sums.data_ptr())
-    call("basi_bn_finalize", sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
-         bnp.data_ptr(), Cc)
+    cnt = torch.zeros(8, dtype=torch.int32, device="cuda:0")
+    call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), cnt.data_ptr())
     res_ref, res_bnp = None, None
     if mode in ("res", "res_bn"):
         res_ref = x2a.ref
     if mode == "res_bn":
-        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc)
+        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc, None, None, C.c_double(R), C.c_float(1e-5), None,
+             cnt.data_ptr() + 4)                           # unfused form: separate finalize launch
         call("basi_bn_finalize", sums.data_ptr() + 8 * 2 * Cc, g2d.data_ptr(), b2d.data_ptr(), C.c_double(R),
              C.c_float(1e-5), bnp2.data_ptr(), Cc)
         res_bnp = bnp2.data_ptr()
@@ -194,11 +195,12 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
     dxa = empty_act(shape, tdt, fill=5.0)
     dresa = empty_act(shape, tdt, fill=1.0)
-    mask = outa.ref if relu else None
-    call("basi_bn_bwd_reduce", da.ref, mask, xa.ref, bnp.data_ptr(), dsums.data_ptr())
-    call("basi_bn_bwd_finalize", dsums.data_ptr(), C.c_double(R), dgamma.data_ptr(), dbeta.data_ptr(),
-         coef.data_ptr(), Cc)
-    call("basi_bn_bwd_apply", da.ref, mask, xa.ref, bnp.data_ptr(), coef.data_ptr(), dxa.ref,
+    # plain BN+ReLU recomputes the mask from x; the junction forms read the stored output
+    mask = outa.ref if (relu and mode != "relu") else None
+    from_x = 1 if mode == "relu" else 0
+    call("basi_bn_bwd_reduce", da.ref, mask, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(), C.c_double(R),
+         dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 8)
+    call("basi_bn_bwd_apply", da.ref, mask, xa.ref, bnp.data_ptr(), coef.data_ptr(), from_x, dxa.ref,
          dresa.ref if mode == "res" else None, 1)
     btol = 2e-4 if dtype == "f32" else 3e-2
     assert rel_err(host(dxa), nhwc(xt.grad)) < btol
@@ -210,10 +212,11 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
         dsums.zero_()
         dx2a = empty_act(shape, tdt)
         dg2, db2 = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
-        call("basi_bn_bwd_reduce", da.ref, mask, x2a.ref, bnp2.data_ptr(), dsums.data_ptr())
+        call("basi_bn_bwd_reduce", da.ref, mask, x2a.ref, bnp2.data_ptr(), 0, dsums.data_ptr(), C.c_double(R), None,
+             None, None, cnt.data_ptr() + 12)              # unfused form
         call("basi_bn_bwd_finalize", dsums.data_ptr(), C.c_double(R), dg2.data_ptr(), db2.data_ptr(),
              coef.data_ptr(), Cc)
-        call("basi_bn_bwd_apply", da.ref, mask, x2a.ref, bnp2.data_ptr(), coef.data_ptr(), dx2a.ref, None, 0)
+        call("basi_bn_bwd_apply", da.ref, mask, x2a.ref, bnp2.data_ptr(), coef.data_ptr(), 0, dx2a.ref, None, 0)
         assert rel_err(host(dx2a), nhwc(x2t.grad)) < btol
         assert rel_err(host(dg2), g2.grad.numpy()) < btol
 

@@ -51,6 +51,7 @@ def test_lowered_plan_structure():
     assert e.n_params == 29571606
     assert f["basi_conv_fprop"] == 112 and f["basi_skinny_fwd"] == 2
     assert f["basi_bn_stats"] == 111 and f["basi_bn_apply"] == 107          # 4 proj BNs folded into junctions
+    assert f["basi_bn_finalize"] == 0 and b["basi_bn_bwd_finalize"] == 0    # finalize fused into the reductions
     assert b["basi_conv_wgrad"] == 112 and b["basi_conv_dgrad"] == 111      # conv1_1 needs no dgrad
     assert b["basi_bn_bwd_apply"] == 111
     # the first backward call is the class-head adjoint, the last one the stem's wgrad
