@@ -295,9 +295,16 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
                 sc = BN(conv2d(x, W(p + "_1x1_proj"), s), p + "_1x1_proj_bn", False)
             else:
                 sc = x
-            y = BN(conv2d(x, W(p + "_1x1_reduce"), s), p + "_1x1_reduce_bn", True)
-            y = BN(conv2d(y, W(p + "_3x3"), 1, dil, dil), p + "_3x3_bn", True)   # tf.pad(d) + (atrous) VALID
-            y = BN(conv2d(y, W(p + "_1x1_increase"), 1), p + "_1x1_increase_bn", False)
+            def step(t, conv_name, relu, *conv_args):
+                c = conv2d(t, W(conv_name), *conv_args)
+                L[conv_name] = c
+                o = BN(c, conv_name + "_bn", relu)
+                L[conv_name + "_bn"] = o
+                return o
+
+            y = step(x, p + "_1x1_reduce", True, s)
+            y = step(y, p + "_3x3", True, 1, dil, dil)                            # tf.pad(d) + (atrous) VALID
+            y = step(y, p + "_1x1_increase", False, 1)
             pre = sc + y
             x = F.relu(pre)
             L[p] = pre
@@ -333,6 +340,7 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
     for k_ in keep:
         v = L[k_]
         out[k_] = v.permute(0, 2, 3, 1) if v.dim() == 4 else v
+    out["__nchw__"] = {k_: L[k_] for k_ in keep}     # graph tensors (for activation gradients)
     return out
 
 
@@ -376,8 +384,10 @@ def to_torch(params, dtype=torch.float32, requires_grad=False):
 
 def train_step(params_np, data_nhwc, label_seg, label_cls, variant="2AddClass", num_segment=1,
                last_pool_size=40, pos_weight=3.0, class_weight=0.2, lr=5e-3, dtype=torch.float32,
-               attention_channel=None, keep=()):
-    """One forward/backward/SGD step.  Returns dict(loss.., logits.., grads, new_params)."""
+               attention_channel=None, keep=(), keep_grads=False):
+    """One forward/backward/SGD step.  Returns dict(loss.., logits.., grads, new_params).
+
+    keep: layer names whose activations are returned (NHWC); keep_grads additionally returns d loss / d layer."""
     seg_name, fc_name, has_class, _ = VARIANTS[variant]
     p = to_torch(params_np, dtype, requires_grad=True)
     x = torch.as_tensor(np.asarray(data_nhwc)).to(dtype)
@@ -386,7 +396,9 @@ def train_step(params_np, data_nhwc, label_seg, label_cls, variant="2AddClass", 
     cls = torch.as_tensor(np.asarray(label_cls)) if has_class else None
     loss, lseg, lcls = losses(out[seg_name], out.get(fc_name), lab, cls, variant, pos_weight, class_weight)
     names = list(p.keys())
-    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    kept = [out["__nchw__"][k_] for k_ in keep] if keep_grads else []
+    grads = torch.autograd.grad(loss, [p[n] for n in names] + kept, allow_unused=True)
+    act_grads, grads = grads[len(names):], grads[:len(names)]
     g = OrderedDict()
     new = OrderedDict()
     for n, gr in zip(names, grads):
@@ -397,8 +409,11 @@ def train_step(params_np, data_nhwc, label_seg, label_cls, variant="2AddClass", 
            "seg_logits": out[seg_name].detach().numpy(), "grads": g, "new_params": new}
     if has_class:
         res["cls_logits"] = out[fc_name].detach().numpy()
-    for k_ in keep:
+    for i, k_ in enumerate(keep):
         res[k_] = out[k_].detach().numpy()
+        if keep_grads:
+            g_ = act_grads[i]
+            res["d:" + k_] = None if g_ is None else (g_.permute(0, 2, 3, 1) if g_.dim() == 4 else g_).detach().numpy()
     return res
 
 

@@ -1,26 +1,35 @@
-"""Ad-hoc GPU diagnostics (not a test)."""
+"""Ad-hoc GPU diagnostics (not a test): locate the wrong elements of d(conv5_3_1x1_increase) on the B=1 case."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import conftest  # noqa
 import numpy as np, torch
 from oracle import basi_oracle as O
-from test_gpu_net import _setup, _engine, _rel, CASES
+from test_gpu_net import _setup, _engine, _rel
 
-for case in (CASES[4], ("1NoClass", 1, 320, 8, 1, 21, 3.0, 0.0), ("2AddClass", 1, 320, 8, 2, 21, 5.0, 0.1)):
-    variant, nseg, S, F, B, classes, pw, cw = case
-    params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
-    eng = _engine(variant, nseg, S, F, B, classes, "f32", dict(kind="bce", pos_weight=pw, class_weight=cw))
-    eng.set_params(params); eng.feed(data, lab, cls, 5e-3); eng.step_device(); torch.cuda.synchronize()
-    ref = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float64)
-    r32 = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float32)
-    g = eng.get_grads()
-    rows = []
-    for n in g:
-        if np.max(np.abs(ref["grads"][n])) <= 1e-12: continue
-        rows.append((_rel(g[n], ref["grads"][n]), _rel(r32["grads"][n], ref["grads"][n]), float(np.max(np.abs(ref["grads"][n]))), n))
-    rows.sort(reverse=True)
-    print(case, "logits", _rel(eng.seg_logits.t.cpu().numpy(), ref["seg_logits"]), "floor", _rel(r32["seg_logits"], ref["seg_logits"]))
-    for r in rows[:12]:
-        print("   err %.2e floor %.2e |g|max %.2e %s" % r)
-    bad = [r for r in rows if r[0] > 1e-4 + 10 * r[1]]
-    print("   failing:", len(bad), "of", len(rows))
+case = ("1NoClass", 1, 320, 8, 1, 21, 3.0, 0.0)
+variant, nseg, S, F, B, classes, pw, cw = case
+params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
+eng = _engine(variant, nseg, S, F, B, classes, "f32", dict(kind="bce", pos_weight=pw, class_weight=cw))
+eng.set_params(params); eng.feed(data, lab, cls, 5e-3); eng.step_device(); torch.cuda.synchronize()
+keep = ("conv5_3_1x1_increase", "conv5_3/relu", "conv5_2/relu")
+ref = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float64, keep=keep, keep_grads=True)
+A = lambda k: eng._acts[eng.net.layers[k].index]
+x = A("conv5_3_1x1_increase"); out = A("conv5_3/relu")
+dx = x.grad.t.cpu().numpy()[0]; rdx = ref["d:conv5_3_1x1_increase"][0]
+err = np.abs(dx - rdx)
+print("dx err max", err.max(), "at", np.unravel_index(err.argmax(), err.shape), "ref |max|", np.abs(rdx).max())
+print("per-row(h) max err", np.round(err.max(axis=(1, 2)) / np.abs(rdx).max(), 4))
+print("per-col(w) max err", np.round(err.max(axis=(0, 2)) / np.abs(rdx).max(), 4))
+ce = err.max(axis=(0, 1)) / np.abs(rdx).max()
+print("channels with err>1e-3:", np.where(ce > 1e-3)[0][:40], "count", (ce > 1e-3).sum(), "of", ce.size)
+# recompute dx in numpy (float64) from the engine's own tensors
+o = out.t.cpu().numpy()[0].astype(np.float64); do = out.grad.t.cpu().numpy()[0].astype(np.float64)
+xv = x.t.cpu().numpy()[0].astype(np.float64)
+g = params["conv5_3_1x1_increase_bn/conv5_3_1x1_increase_bn/gamma"].astype(np.float64)
+dy = do * (o > 0)
+mean = xv.mean(axis=(0, 1)); var = xv.var(axis=(0, 1)); istd = 1 / np.sqrt(var + 1e-5)
+xh = (xv - mean) * istd
+mine = g * istd * (dy - dy.mean(axis=(0, 1)) - xh * (dy * xh).mean(axis=(0, 1)))
+print("engine dx vs numpy-from-engine-tensors", _rel(dx, mine), " | numpy-from-engine vs oracle", _rel(mine, rdx))
+print("mask agreement engine-out vs oracle-out:", np.mean((o > 0) == (ref["conv5_3/relu"][0] > 0)), "n diff", np.sum((o > 0) != (ref["conv5_3/relu"][0] > 0)))
+print("dout agreement", _rel(do, ref["d:conv5_3/relu"][0]))

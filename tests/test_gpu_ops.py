@@ -441,3 +441,46 @@ def test_skinny_gemms(dtype, M, K, N, relu):
     da = torch.zeros(M, K, dtype=tdt, device="cuda:0")
     call("basi_skinny_dgrad", dyd.data_ptr(), wd.data_ptr(), da.data_ptr(), code, C.c_int64(K), M, K, N, 0)
     assert rel_err(host(da), at.grad.numpy()) < (2e-5 if dtype == "f32" else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_batch_norm_junction_backward_on_concat_slices(dtype):
+    """out / dout of the conv5_3 junction are channel slices of the PSP concat buffer (ld != c)."""
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    from basi_b200.engine import Act
+    B, H, W, Cc = 1, 40, 40, 256
+    shape = (B, H, W, Cc)
+    rng = np.random.RandomState(11)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    x, res, dout = rnd(_u(rng, *shape) * 2), rnd(_u(rng, *shape)), rnd(_u(rng, *shape))
+    gamma, beta = rng.uniform(0.05, 0.25, Cc).astype(np.float32), _u(rng, Cc)
+    xt, rt = nchw(x).double().requires_grad_(True), nchw(res).double().requires_grad_(True)
+    g1, b1 = torch.from_numpy(gamma).double().requires_grad_(True), torch.from_numpy(beta).double().requires_grad_(True)
+    y = torch.relu(O.batch_norm(xt, g1, b1) + rt)
+    (y * nchw(dout).double()).sum().backward()
+    R = float(B * H * W)
+    xa, ra = act(x, tdt), act(res, tdt)
+    wide = torch.zeros((B, H, W, 2 * Cc), dtype=tdt, device="cuda:0")
+    dwide = torch.zeros((B, H, W, 2 * Cc), dtype=tdt, device="cuda:0")
+    dwide[..., :Cc] = torch.from_numpy(dout).to("cuda:0").to(tdt)
+    outa, da = Act(wide[..., :Cc]), Act(dwide[..., :Cc])
+    sums = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda:0")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda:0")
+    bnp, coef = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(2 * Cc, device="cuda:0")
+    gd, bd = dev(gamma), dev(beta)
+    call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), cnt.data_ptr())
+    call("basi_bn_apply", xa.ref, bnp.data_ptr(), ra.ref, None, 1, outa.ref)
+    tol = 1e-5 if dtype == "f32" else 1e-2
+    assert rel_err(host(wide)[..., :Cc], nhwc(y.detach())) < tol
+    dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
+    dxa, dra = empty_act(shape, tdt, fill=5.0), empty_act(shape, tdt, fill=7.0)
+    call("basi_bn_bwd_reduce", da.ref, outa.ref, xa.ref, bnp.data_ptr(), 0, sums.data_ptr() + 16 * Cc, C.c_double(R),
+         dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 4)
+    call("basi_bn_bwd_apply", da.ref, outa.ref, xa.ref, bnp.data_ptr(), coef.data_ptr(), 0, dxa.ref, dra.ref, 0)
+    btol = 2e-4 if dtype == "f32" else 3e-2
+    assert rel_err(host(dbeta), b1.grad.numpy()) < btol
+    assert rel_err(host(dgamma), g1.grad.numpy()) < btol
+    assert rel_err(host(dra), nhwc(rt.grad)) < btol
+    assert rel_err(host(dxa), nhwc(xt.grad)) < btol
