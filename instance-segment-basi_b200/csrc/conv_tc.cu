@@ -312,13 +312,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------------
-// wgrad: one work item = (tap, ci tile of 128, co tile of BN, pixel-tile range); fp32 atomics into dW (HWIO)
+// wgrad: D[co 128][ci BN] = sum_px dY[px][co]^T * X_tap[px][ci]   (both operands MN-major: pixels are K)
+// one work item = (tap, co tile of 128, ci tile of BN, pixel-tile range); the accumulator row is an output
+// channel, so for a fixed ci the 32 lanes of a warp add to 32 consecutive floats of the HWIO gradient
+// (coalesced red.global.add).  Channel counts that are not multiples of the tile are zero-filled by TMA.
 // ------------------------------------------------------------------------------------------------------
 struct WgradParams {
   int TW, TH, TN;
   int tiles_w, tiles_h, tiles_n, m_tiles;
   int taps, kw;
-  int ci_tiles, co_tiles;   // Cin/128, Cout/BN
+  int ci_tiles, co_tiles;   // ceil(Cin/BN), ceil(Cout/128)
   int splits, tiles_per_split;
   int off_h, off_w, step;   // x coordinate = p + off + r*step (fprop mapping)
   int Cin, Cout;
@@ -330,9 +333,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG,
                 float* __restrict__ dw, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int XB = 2 * A_BYTES;            // 128 ci = two 64-channel boxes of [128 px][128 B]
-  constexpr int GB = (BN / 64) * A_BYTES;    // BN co = BN/64 boxes
-  constexpr int STAGE = XB + GB;
+  constexpr int GB = 2 * A_BYTES;            // 128 co = two 64-channel boxes of [128 px][128 B]
+  constexpr int XB = (BN / 64) * A_BYTES;    // BN ci = BN/64 boxes
+  constexpr int STAGE = GB + XB;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
@@ -366,8 +369,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   // work item of this CTA
   int wi = blockIdx.x;
   const int split = wi % p.splits; wi /= p.splits;
-  const int cot = wi % p.co_tiles; wi /= p.co_tiles;
   const int cit = wi % p.ci_tiles; wi /= p.ci_tiles;
+  const int cot = wi % p.co_tiles; wi /= p.co_tiles;
   const int tap = wi;
   const int r = tap / p.kw, s = tap - r * p.kw;
   const int mt_beg = split * p.tiles_per_split;
@@ -385,11 +388,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, STAGE);
-        tma_load_4d(sa, &mapX, fb, cit * 128, w0 + p.off_w + s * p.step, h0 + p.off_h + r * p.step, n0);
-        tma_load_4d(sa + A_BYTES, &mapX, fb, cit * 128 + 64, w0 + p.off_w + s * p.step, h0 + p.off_h + r * p.step, n0);
+        tma_load_4d(sa, &mapG, fb, cot * 128, w0, h0, n0);
+        tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
+        const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(sa + XB + j * A_BYTES, &mapG, fb, cot * BN + j * 64, w0, h0, n0);
+        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, cit * BN + j * 64, xw, xh, n0);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -407,7 +410,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
         // MN-major: LBO = 16 KB between 64-channel blocks, SBO = 1 KB between groups of 8 pixel rows
         const uint64_t adesc = make_desc(sa, A_BYTES, 1024);
-        const uint64_t bdesc = make_desc(sa + XB, A_BYTES, 1024);
+        const uint64_t bdesc = make_desc(sa + GB, A_BYTES, 1024);
 #pragma unroll
         for (int k = 0; k < BM / 16; ++k) {
           // 16 pixels (K) further = 16 rows of 128 B = 2 KB -> +128 in 16-B units
@@ -423,19 +426,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int q = warp - 4;
-    const int ci = cit * 128 + q * 32 + lane;
+    const int co = cot * 128 + q * 32 + lane;
     if (nsteps > 0) {
       mbar_wait(tfull, 0);
       tc_fence_after();
-      float* out = dw + ((int64_t)tap * p.Cin + ci) * p.Cout + cot * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool covalid = co < p.Cout;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t rr[32];
         tmem_ld32(taddr + c * 32, rr);
-        if (ci < p.Cin) {
+        const int ci0 = cit * BN + c * 32;
+        if (covalid && ci0 < p.Cin) {
+          float* out = dw + ((int64_t)tap * p.Cin + ci0) * p.Cout + co;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(out + c * 32 + j, __uint_as_float(rr[j]));
+          for (int j = 0; j < 32; ++j)
+            if (ci0 + j < p.Cin) atomicAdd(out + (int64_t)j * p.Cout, __uint_as_float(rr[j]));
         }
       }
     }
@@ -573,9 +579,11 @@ static bool tc_geometry_ok(int kind, const basi_conv_desc* d, const basi_tensor*
   if (x->ld % 8 || y->ld % 8) return false;
   if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
   const int cin = x->c, cout = y->c;
-  if (kind == BASI_TC_FPROP) return cin % 64 == 0 && cout % 32 == 0;
-  if (kind == BASI_TC_DGRAD) return cout % 64 == 0 && cin % 32 == 0;
-  if (kind == BASI_TC_WGRAD) return cin % 128 == 0 && cout % 64 == 0;
+  // K (the reduced channel axis) only has to keep the TMA strides 16-byte aligned: a 64-channel box over a
+  // narrower tensor is zero-filled.  N (the produced channel axis) is tiled by 32/64/128.
+  if (kind == BASI_TC_FPROP) return cin % 8 == 0 && cin >= 16 && cout % 32 == 0;
+  if (kind == BASI_TC_DGRAD) return cout % 8 == 0 && cout >= 16 && cin % 32 == 0;
+  if (kind == BASI_TC_WGRAD) return cin % 8 == 0 && cin >= 16 && cout % 8 == 0 && cout >= 16;
   return false;
 }
 
@@ -650,7 +658,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     cp.tiles_w = tiles_w; cp.tiles_h = tiles_h; cp.tiles_n = tiles_n;
     cp.m_tiles = m_tiles; cp.n_tiles = ndim / bn;
     cp.N = dstt->n; cp.H = dstt->h; cp.W = dstt->w; cp.ldd = dstt->ld; cp.Cdst = dstt->c;
-    cp.taps = d->kh * d->kw; cp.kw = d->kw; cp.k_chunks = kdim / 64;
+    cp.taps = d->kh * d->kw; cp.kw = d->kw; cp.k_chunks = (kdim + 63) / 64;
     if (kind == BASI_TC_FPROP) {
       cp.off_h = -d->pad_t; cp.off_w = -d->pad_l; cp.step = d->dil;
     } else {
@@ -668,7 +676,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
     const int cin = a->c, cout = b->c;
-    int bn = cout % 128 == 0 ? 128 : 64;
+    int bn = cin > 64 ? 128 : 64;            // ci tile (UMMA N); co is the UMMA M = 128
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, a, TW, TH, TN);
     if (rc == BASI_OK) rc = make_act_map(&pl->mapB, b, TW, TH, TN);
@@ -680,7 +688,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     wp.TW = TW; wp.TH = TH; wp.TN = TN;
     wp.tiles_w = tiles_w; wp.tiles_h = tiles_h; wp.tiles_n = tiles_n; wp.m_tiles = m_tiles;
     wp.taps = d->kh * d->kw; wp.kw = d->kw;
-    wp.ci_tiles = cin / 128; wp.co_tiles = cout / bn;
+    wp.ci_tiles = (cin + bn - 1) / bn; wp.co_tiles = (cout + 127) / 128;
     wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
     wp.Cin = cin; wp.Cout = cout;
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
