@@ -180,6 +180,11 @@ int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int t
                          void* stream);
 int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
                         const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out);
+/* fprop plans only: also accumulate the batch-norm statistics of the produced tensor in the epilogue (same
+ * contract as basi_bn_stats: sums += (sum y, sum y^2) in double, counter = one zeroed uint32 per launch, and the
+ * last CTA writes bnp when it is non-NULL), which removes the separate statistics pass over the conv output. */
+int basi_tc_conv_set_bn_stats(basi_tc_conv* plan, double* sums, const float* gamma, const float* beta, double count,
+                              float eps, float* bnp, uint32_t* counter);
 int basi_tc_conv_run(basi_tc_conv* plan, void* stream);
 void basi_tc_conv_destroy(basi_tc_conv* plan);
 

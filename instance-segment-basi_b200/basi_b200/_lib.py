@@ -70,6 +70,7 @@ SIGNATURES = {
     "basi_tc_conv_supported": [_i, _DP, _TP, _TP],
     "basi_tc_pack_weights": [_P, _P, _P, _i, _i, _i, _P],
     "basi_tc_conv_create": [_i, _DP, _TP, _TP, _P, _P, _i, C.POINTER(_P)],
+    "basi_tc_conv_set_bn_stats": [_P, _P, _P, _P, _d, _f, _P, _P],
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),

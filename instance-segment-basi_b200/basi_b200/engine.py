@@ -64,7 +64,7 @@ class _BNRec(object):
 
 class Engine(object):
     def __init__(self, net, batch_size, precision="bf16", training=True, loss=None, device=None, use_tc=True,
-                 dry_run=False):
+                 dry_run=False, fuse_bn_stats=True):
         """net: a built Network; loss: dict(kind='bce'|'softmax', pos_weight, class_weight, seg, cls).
 
         dry_run=True only builds the plan (buffers on the host, nothing can be executed): used by the
@@ -89,6 +89,9 @@ class Engine(object):
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
         self._tc_plans = []
+        self._tc_producer = {}
+        self.fuse_bn_stats = fuse_bn_stats
+        self.fused_stats = 0
         self._tc_weights = []
         self._zero_grads = []    # gradient buffers that are pre-zeroed every step (concat buffers)
         self._acts = {}          # node index -> Act (or tuple for deferred bn)
@@ -405,7 +408,8 @@ class Engine(object):
         bptr = self._pptr(op["b"]) if op["b"] else None
         if self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]:
             if _lib.load().basi_tc_conv_supported(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
-                self._emit_tc(op, _lib.TC_FPROP, self.fwd)
+                op["tc_fprop"] = self._emit_tc(op, _lib.TC_FPROP, self.fwd)
+                self._tc_producer[id(y)] = op
                 return
         self._call(self.fwd, "basi_conv_fprop", C.byref(op["desc"]), x.ref, self._pptr(op["w"]), bptr, y.ref,
                    flops=self._conv_flops(op))
@@ -415,6 +419,13 @@ class Engine(object):
         return float(np.prod(act.shape)) * act.t.element_size()
 
     def _emit_bn_stats(self, rec):
+        prod = self._tc_producer.get(id(rec.x))
+        if prod is not None and self.fuse_bn_stats:
+            # statistics come out of the tcgen05 conv epilogue: no separate pass over the conv output
+            _lib.call("basi_tc_conv_set_bn_stats", prod["tc_fprop"], rec.sums, self._pptr(rec.gamma),
+                      self._pptr(rec.beta), C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.cnt_f)
+            self.fused_stats += 1
+            return
         self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
                    C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.cnt_f, bytes=self._nbytes(rec.x))
 
@@ -618,10 +629,12 @@ class Engine(object):
                       self._gptr(op["w"]), 1, C.byref(handle))
         self._tc_plans.append(handle)
         self.tc_layers += 1
+        self._last_tc = handle
         meta = dict(flops=self._conv_flops(op))
         if kind == _lib.TC_WGRAD:
             meta["writes"] = [op["w"]]
         lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))
+        return handle
 
     def _refresh_weight_copies(self, stream=None):
         if not self._tc_weights:

@@ -361,7 +361,7 @@ int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const 
   BASI_CHECK_ARG(!gamma || (beta && bnp && count > 0), "bn_stats: fused finalize needs gamma, beta, bnp, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, 4 * UNR, 6, 2 * Vec<T>::N * sizeof(double));
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 8, 2 * Vec<T>::N * sizeof(double));
     bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>((const T*)x->ptr, R, x->c, x->ld, sums, gamma,
                                                                           beta, count, eps, bnp, counter);
   })
@@ -413,7 +413,7 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
   BASI_CHECK_ARG(!coef || (dgamma && dbeta && count > 0), "bn_bwd_reduce: fused finalize needs dgamma, dbeta, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, 4 * UNR, 6, 2 * Vec<T>::N * sizeof(double));
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 8, 2 * Vec<T>::N * sizeof(double));
     bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, relu_from_x, R, x->c, dsums, count, dgamma, dbeta, coef, counter);

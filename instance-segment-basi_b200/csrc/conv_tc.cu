@@ -136,7 +136,30 @@ struct ConvParams {
   int off_h, off_w, step;
   int accumulate;
   int stages;
+  // optional fused batch-norm statistics of the produced tensor (fprop): per-channel sum / sum of squares of the
+  // bf16-rounded outputs, double atomics per tile, last CTA finalizes bnp = [mean | istd | gamma*istd | beta]
+  double* bn_sums;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_bnp;
+  unsigned int* bn_counter;
+  double bn_count;
+  float bn_eps;
 };
+
+// transpose-reduce across the 32 lanes of a warp: on return v[0] of lane l is the sum over all lanes of their v[l]
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
 
 template <int BN>
 struct SmemLayout {
@@ -160,6 +183,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [4 warps][2*BN]
+  __shared__ bool s_is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -268,46 +293,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const bool do_stats = p.bn_sums != nullptr;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+        if (p.accumulate && valid) {
+          const uint4* o4 = reinterpret_cast<const uint4*>(out + c * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 old = o4[v];
+            const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[v * 8 + 2 * j] += __uint_as_float(ow[j] << 16);
+              f[v * 8 + 2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
         if (valid) {
           uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            float f[8];
+          for (int v = 0; v < 4; ++v) o4[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        }
+        if (do_stats) {
+          // statistics of the values as stored (bf16-rounded); rows outside the tensor are exact zeros
+          float sq[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
-            if (p.accumulate) {
-              uint4 old = o4[v];
-              const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[2 * j] += __uint_as_float(ow[j] << 16);
-                f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
-              }
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            o4[v] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(pk[j] << 16), b = __uint_as_float(pk[j] & 0xffff0000u);
+            f[2 * j] = a;
+            f[2 * j + 1] = b;
+            sq[2 * j] = a * a;
+            sq[2 * j + 1] = b * b;
           }
+          warp_column_sums(f, lane);
+          warp_column_sums(sq, lane);
+          stat_s[q * (2 * BN) + c * 32 + lane] = f[0];
+          stat_s[q * (2 * BN) + BN + c * 32 + lane] = sq[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        for (int col = q * 32 + lane; col < BN; col += 128) {
+          const float s1 = stat_s[col] + stat_s[2 * BN + col] + stat_s[4 * BN + col] + stat_s[6 * BN + col];
+          const float s2 = stat_s[BN + col] + stat_s[3 * BN + col] + stat_s[5 * BN + col] + stat_s[7 * BN + col];
+          atomicAdd(p.bn_sums + nt * BN + col, (double)s1);
+          atomicAdd(p.bn_sums + p.Cdst + nt * BN + col, (double)s2);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
+    if (p.bn_sums != nullptr) __threadfence();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+  if (p.bn_sums != nullptr && p.bn_bnp != nullptr) {
+    // last CTA to finish turns the sums into the per-channel parameters (fused finalize)
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(p.bn_counter, 1u);
+      s_is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_is_last) {
+      __threadfence();
+      const int C = p.Cdst;
+      for (int c = threadIdx.x; c < C; c += NTHREADS) {
+        const double mean = __ldcg(p.bn_sums + c) / p.bn_count;
+        double var = __ldcg(p.bn_sums + C + c) / p.bn_count - mean * mean;
+        if (var < 0) var = 0;
+        const double istd = 1.0 / sqrt(var + (double)p.bn_eps);
+        p.bn_bnp[c] = (float)mean;
+        p.bn_bnp[C + c] = (float)istd;
+        p.bn_bnp[2 * C + c] = (float)((double)p.bn_gamma[c] * istd);
+        p.bn_bnp[3 * C + c] = p.bn_beta[c];
+      }
+    }
   }
 }
 
@@ -666,10 +743,10 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     }
     cp.accumulate = accumulate;
     const int stage_bytes = A_BYTES + bn * 128;
-    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    int stages = (int)((227 * 1024 - 2048 - 8 * bn * (int)sizeof(float)) / stage_bytes);
     if (stages > 8) stages = 8;
     cp.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + 1024 + 256;
+    pl->smem = (size_t)stages * stage_bytes + 1024 + 256 + 8 * bn * sizeof(float);
     pl->dst = (bf16*)dstt->ptr;
     const int total = cp.m_tiles * cp.n_tiles;
     pl->grid = total < sms ? total : sms;
@@ -706,6 +783,20 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     pl->grid = out_tiles * wp.splits;
   }
   *out = pl;
+  return BASI_OK;
+}
+
+int basi_tc_conv_set_bn_stats(basi_tc_conv* pl, double* sums, const float* gamma, const float* beta, double count,
+                              float eps, float* bnp, uint32_t* counter) {
+  BASI_CHECK_ARG(pl && pl->kind == BASI_TC_FPROP, "tc_conv_set_bn_stats: needs an fprop plan");
+  BASI_CHECK_ARG(sums && counter && (!bnp || (gamma && beta && count > 0)), "tc_conv_set_bn_stats: bad argument");
+  pl->cp.bn_sums = sums;
+  pl->cp.bn_gamma = gamma;
+  pl->cp.bn_beta = beta;
+  pl->cp.bn_bnp = bnp;
+  pl->cp.bn_counter = counter;
+  pl->cp.bn_count = count;
+  pl->cp.bn_eps = eps;
   return BASI_OK;
 }
 

@@ -134,3 +134,48 @@ def test_tc_refuses_unsupported_geometries():
     h = C.c_void_p()
     rc = lib.basi_tc_conv_create(0, C.byref(ConvDesc(3, 3, 1, 1, 1, 1, 0)), x4.ref, y4.ref, None, None, 0, C.byref(h))
     assert rc == -1 and b"not supported" in lib.basi_last_error()
+
+
+@pytest.mark.parametrize("case", [(3, 2, 128, 128, 40, 40, 3), (1, 1, 128, 512, 40, 40, 2), (1, 1, 64, 32, 80, 80, 1)],
+                         ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_fprop_fused_bn_statistics(case):
+    """The fprop epilogue accumulates per-channel sum / sum-of-squares of the stored (bf16) output and the last CTA
+    finalizes [mean | istd | gamma*istd | beta]: must equal statistics computed from the stored tensor."""
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    from basi_b200.engine import Act
+    from gpu_util import bf16_round, call, dev, host, rel_err
+    k, d, cin, cout, H, W, B = case
+    rng = np.random.RandomState(3)
+    x = bf16_round(rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32) + 0.3)
+    w = bf16_round((rng.uniform(-1, 1, (k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32))
+    gamma, beta = rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.uniform(-1, 1, cout).astype(np.float32)
+    pad = d * (k - 1) // 2
+    desc = ConvDesc(k, k, 1, d, pad, pad, 0)
+    bt = torch.bfloat16
+    xa = Act(torch.from_numpy(x).to("cuda:0").to(bt).contiguous())
+    ya = Act(torch.zeros((B, H, W, cout), dtype=bt, device="cuda:0"))
+    wd, gd, bd = dev(w), dev(gamma), dev(beta)
+    w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    call("basi_tc_pack_weights", wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda:0")
+    bnp = torch.zeros(4 * cout, device="cuda:0")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create", 0, C.byref(desc), xa.ref, ya.ref, w_oi.data_ptr(), None, 0, C.byref(h))
+    R = float(B * H * W)
+    _lib.call("basi_tc_conv_set_bn_stats", h, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R),
+              C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
+    call("basi_tc_conv_run", h)
+    y = host(ya).astype(np.float64).reshape(-1, cout)
+    got, s = host(bnp), host(sums)
+    _lib.load().basi_tc_conv_destroy(h)
+    assert rel_err(s[:cout], y.sum(0)) < 1e-5 and rel_err(s[cout:], (y * y).sum(0)) < 1e-5
+    mean, var = y.mean(0), y.var(0)
+    istd = 1 / np.sqrt(var + 1e-5)
+    assert rel_err(got[:cout], mean) < 1e-5
+    assert rel_err(got[cout:2 * cout], istd) < 1e-4
+    assert rel_err(got[2 * cout:3 * cout], gamma * istd) < 1e-4
+    assert np.array_equal(got[3 * cout:], beta)
+    assert int(host(cnt)[0]) > 0
