@@ -184,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
   float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [4 warps][2*BN]
-  __shared__ bool s_is_last;
+  volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -368,10 +368,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // last CTA to finish turns the sums into the per-channel parameters (fused finalize)
     if (threadIdx.x == 0) {
       const unsigned int t = atomicAdd(p.bn_counter, 1u);
-      s_is_last = (t == gridDim.x - 1);
+      *s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_is_last) {
+    if (*s_is_last) {
       __threadfence();
       const int C = p.Cdst;
       for (int c = threadIdx.x; c < C; c += NTHREADS) {
