@@ -39,6 +39,11 @@ extern "C" {
 #define BASI_F32 0
 #define BASI_BF16 1
 
+/* Per-channel batch-norm accumulators are replicated: sums / dsums are double [BASI_BN_REPLICAS][2*C]; blocks add
+ * into replica (block % BASI_BN_REPLICAS) and the finalize step sums the replicas (shorter same-address atomic
+ * chains at L2). */
+#define BASI_BN_REPLICAS 8
+
 typedef struct basi_tensor {
   void* ptr;     /* device pointer to element (0,0,0,0) */
   int32_t n, h, w, c;
@@ -84,7 +89,8 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
                     float* dbias, void* stream);
 
 /* ---- A6/A7: Network.batch_normalization (+relu, +add) (BAISPSPNet.py:204-236, :148-150, :171-173) ----
- * sums: double [2*C] (sum x, sum x^2), ADDED into (caller zeroes); counter: one zeroed uint32 per launch.
+ * sums: double [BASI_BN_REPLICAS][2*C] (sum x, sum x^2), ADDED into (caller zeroes); counter: one zeroed uint32
+ * per launch.
  * When gamma != NULL the last block to finish also writes bnp (fused finalize):
  * bnp: float [4*C] = [mean | istd | gamma*istd | beta] (batch mean, biased variance, eps inside the sqrt). */
 int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const float* beta, double count, float eps,
@@ -94,7 +100,7 @@ int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, 
 /* out = act((x-mean)*scale+beta [+ res | + (res-res_mean)*res_scale+res_beta]); res / res_bnp may be NULL. */
 int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp,
                   int relu, const basi_tensor* out, void* stream);
-/* dsums (double [2*C]) += (sum dy, sum dy*xhat).  dy = dout * (out > 0) when out != NULL; else, when
+/* dsums (double [BASI_BN_REPLICAS][2*C]) += (sum dy, sum dy*xhat).  dy = dout * (out > 0) when out != NULL; else, when
  * relu_from_x, dy = dout * ((x-mean)*scale+beta > 0) (plain BN+ReLU: the mask is recomputed, out is not read).
  * When coef != NULL the last block also does the finalize: dgamma += sum dy*xhat, dbeta += sum dy,
  * coef (float [2*C]) = dsums / count. */

@@ -26,6 +26,7 @@ from . import _lib
 from ._lib import ConvDesc, Tensor
 
 _ALIGN = 64  # parameter offsets aligned to 64 floats (256 B)
+BN_REPLICAS = 8  # == BASI_BN_REPLICAS in include/basi_b200.h
 
 
 def _same_pad_before(n_in, k, s, d):
@@ -196,7 +197,7 @@ class Engine(object):
         # BN statistic scratch: [fwd sums | bwd sums] as doubles, zeroed once per step
         tot_c = sum(n.shape[-1] for n in nodes if n.op == "batch_normalization")
         n_bn = sum(1 for n in nodes if n.op == "batch_normalization")
-        self.bn_scratch = torch.zeros(4 * tot_c + 8, dtype=torch.float64, device=self.device)
+        self.bn_scratch = torch.zeros(4 * tot_c * BN_REPLICAS + 8, dtype=torch.float64, device=self.device)
         self.bn_counters = torch.zeros(2 * n_bn + 2, dtype=torch.int32, device=self.device)   # last-block tickets
         self._bn_off = 0
         self._bn_idx = 0
@@ -284,8 +285,8 @@ class Engine(object):
         Cc = rec.C
         base = self.bn_scratch.data_ptr()
         rec.sums = base + 8 * self._bn_off
-        rec.dsums = base + 8 * (self._bn_off + 2 * Cc)
-        self._bn_off += 4 * Cc
+        rec.dsums = base + 8 * (self._bn_off + 2 * Cc * BN_REPLICAS)
+        self._bn_off += 4 * Cc * BN_REPLICAS
         rec.cnt_f = self.bn_counters.data_ptr() + 8 * self._bn_idx
         rec.cnt_b = rec.cnt_f + 4
         self._bn_idx += 1

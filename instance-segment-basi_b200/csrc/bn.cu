@@ -12,6 +12,7 @@
 namespace basi {
 
 constexpr int UNR = 4;
+constexpr int NREP = BASI_BN_REPLICAS;   // replicated accumulators: same-address atomic chains are NREP x shorter
 
 struct RowGeom {
   dim3 grid, block;
@@ -80,8 +81,14 @@ __device__ __forceinline__ bool reduce_and_ticket(double (&a)[VN], double (&b)[V
 
 __device__ __forceinline__ void finalize_channel(const double* sums, const float* gamma, const float* beta,
                                                  double count, float eps, float* bnp, int C, int c) {
-  double mean = __ldcg(sums + c) / count;
-  double var = __ldcg(sums + C + c) / count - mean * mean;
+  double s1 = 0, s2 = 0;
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    s1 += __ldcg(sums + (size_t)r * 2 * C + c);
+    s2 += __ldcg(sums + (size_t)r * 2 * C + C + c);
+  }
+  double mean = s1 / count;
+  double var = s2 / count - mean * mean;
   if (var < 0) var = 0;
   double istd = 1.0 / sqrt(var + (double)eps);
   bnp[c] = (float)mean;
@@ -122,7 +129,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
         }
     }
   }
-  const bool last = reduce_and_ticket<VN>(s, q, sums, sums + C, c0, valid, counter);
+  double* rep = sums + (size_t)(blockIdx.x % NREP) * 2 * C;
+  const bool last = reduce_and_ticket<VN>(s, q, rep, rep + C, c0, valid, counter);
   if (last && gamma) {
     for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y)
       finalize_channel(sums, gamma, beta, count, eps, bnp, C, c);
@@ -261,10 +269,16 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
       q[i] += (double)fq[i];
     }
   }
-  const bool last = reduce_and_ticket<VN>(s, q, dsums, dsums + C, c0, valid, counter);
+  double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
+  const bool last = reduce_and_ticket<VN>(s, q, rep, rep + C, c0, valid, counter);
   if (last && coef) {
     for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
-      const double s1 = __ldcg(dsums + c), s2 = __ldcg(dsums + C + c);
+      double s1 = 0, s2 = 0;
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        s1 += __ldcg(dsums + (size_t)r * 2 * C + c);
+        s2 += __ldcg(dsums + (size_t)r * 2 * C + C + c);
+      }
       dbeta[c] += (float)s1;
       dgamma[c] += (float)s2;
       coef[c] = (float)(s1 / count);
@@ -277,7 +291,11 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ dsums, double 
                                        float* __restrict__ dbeta, float* __restrict__ coef, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double s1 = dsums[c], s2 = dsums[C + c];
+  double s1 = 0, s2 = 0;
+  for (int r = 0; r < NREP; ++r) {
+    s1 += dsums[(size_t)r * 2 * C + c];
+    s2 += dsums[(size_t)r * 2 * C + C + c];
+  }
   dbeta[c] += (float)s1;
   dgamma[c] += (float)s2;
   coef[c] = (float)(s1 / count);
@@ -361,7 +379,7 @@ int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const 
   BASI_CHECK_ARG(!gamma || (beta && bnp && count > 0), "bn_stats: fused finalize needs gamma, beta, bnp, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 8, 2 * Vec<T>::N * sizeof(double));
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * UNR, 8, 2 * Vec<T>::N * sizeof(double));
     bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>((const T*)x->ptr, R, x->c, x->ld, sums, gamma,
                                                                           beta, count, eps, bnp, counter);
   })
@@ -413,7 +431,7 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
   BASI_CHECK_ARG(!coef || (dgamma && dbeta && count > 0), "bn_bwd_reduce: fused finalize needs dgamma, dbeta, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 8, 2 * Vec<T>::N * sizeof(double));
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * UNR, 8, 2 * Vec<T>::N * sizeof(double));
     bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, relu_from_x, R, x->c, dsums, count, dgamma, dbeta, coef, counter);

@@ -326,11 +326,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int v = 0; v < 4; ++v) o4[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
         }
         if (do_stats) {
-          // statistics of the values as stored (bf16-rounded); rows outside the tensor are exact zeros
+          // statistics of the values as stored (bf16-rounded).  Rows outside the tensor are masked: for k > 1 they
+          // hold phantom outputs of the padded convolution (their taps still reach valid pixels).
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(pk[j] << 16), b = __uint_as_float(pk[j] & 0xffff0000u);
+            const float a = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+            const float b = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
             f[2 * j] = a;
             f[2 * j + 1] = b;
             sq[2 * j] = a * a;
@@ -350,8 +352,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int col = q * 32 + lane; col < BN; col += 128) {
           const float s1 = stat_s[col] + stat_s[2 * BN + col] + stat_s[4 * BN + col] + stat_s[6 * BN + col];
           const float s2 = stat_s[BN + col] + stat_s[3 * BN + col] + stat_s[5 * BN + col] + stat_s[7 * BN + col];
-          atomicAdd(p.bn_sums + nt * BN + col, (double)s1);
-          atomicAdd(p.bn_sums + p.Cdst + nt * BN + col, (double)s2);
+          double* rep = p.bn_sums + (size_t)(mt % BASI_BN_REPLICAS) * 2 * p.Cdst;
+          atomicAdd(rep + nt * BN + col, (double)s1);
+          atomicAdd(rep + p.Cdst + nt * BN + col, (double)s2);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -375,8 +378,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __threadfence();
       const int C = p.Cdst;
       for (int c = threadIdx.x; c < C; c += NTHREADS) {
-        const double mean = __ldcg(p.bn_sums + c) / p.bn_count;
-        double var = __ldcg(p.bn_sums + C + c) / p.bn_count - mean * mean;
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int r = 0; r < BASI_BN_REPLICAS; ++r) {
+          s1 += __ldcg(p.bn_sums + (size_t)r * 2 * C + c);
+          s2 += __ldcg(p.bn_sums + (size_t)r * 2 * C + C + c);
+        }
+        const double mean = s1 / p.bn_count;
+        double var = s2 / p.bn_count - mean * mean;
         if (var < 0) var = 0;
         const double istd = 1.0 / sqrt(var + (double)p.bn_eps);
         p.bn_bnp[c] = (float)mean;

@@ -164,7 +164,7 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     # device forward
     R = float(B * H * W)
     xa, x2a, outa = act(x, tdt), act(x2, tdt), empty_act(shape, tdt)
-    sums = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda:0")
+    sums = torch.zeros(4 * Cc * 8, dtype=torch.float64, device="cuda:0")
     bnp, bnp2 = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(4 * Cc, device="cuda:0")
     gd, bd, g2d, b2d = dev(gamma), dev(beta), dev(gamma2), dev(beta2)
     cnt = torch.zeros(8, dtype=torch.int32, device="cuda:0")
@@ -174,9 +174,9 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     if mode in ("res", "res_bn"):
         res_ref = x2a.ref
     if mode == "res_bn":
-        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc, None, None, C.c_double(R), C.c_float(1e-5), None,
+        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc * 8, None, None, C.c_double(R), C.c_float(1e-5), None,
              cnt.data_ptr() + 4)                           # unfused form: separate finalize launch
-        call("basi_bn_finalize", sums.data_ptr() + 8 * 2 * Cc, g2d.data_ptr(), b2d.data_ptr(), C.c_double(R),
+        call("basi_bn_finalize", sums.data_ptr() + 8 * 2 * Cc * 8, g2d.data_ptr(), b2d.data_ptr(), C.c_double(R),
              C.c_float(1e-5), bnp2.data_ptr(), Cc)
         res_bnp = bnp2.data_ptr()
     call("basi_bn_apply", xa.ref, bnp.data_ptr(), res_ref, res_bnp, 1 if relu else 0, outa.ref)
@@ -190,7 +190,7 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
         return
     (y * nchw(dout).double()).sum().backward()
     da = act(dout, tdt)
-    dsums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda:0")
+    dsums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
     coef = torch.zeros(2 * Cc, device="cuda:0")
     dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
     dxa = empty_act(shape, tdt, fill=5.0)
@@ -465,7 +465,7 @@ def test_batch_norm_junction_backward_on_concat_slices(dtype):
     dwide = torch.zeros((B, H, W, 2 * Cc), dtype=tdt, device="cuda:0")
     dwide[..., :Cc] = torch.from_numpy(dout).to("cuda:0").to(tdt)
     outa, da = Act(wide[..., :Cc]), Act(dwide[..., :Cc])
-    sums = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda:0")
+    sums = torch.zeros(4 * Cc * 8, dtype=torch.float64, device="cuda:0")
     cnt = torch.zeros(4, dtype=torch.int32, device="cuda:0")
     bnp, coef = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(2 * Cc, device="cuda:0")
     gd, bd = dev(gamma), dev(beta)
@@ -476,7 +476,7 @@ def test_batch_norm_junction_backward_on_concat_slices(dtype):
     assert rel_err(host(wide)[..., :Cc], nhwc(y.detach())) < tol
     dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
     dxa, dra = empty_act(shape, tdt, fill=5.0), empty_act(shape, tdt, fill=7.0)
-    call("basi_bn_bwd_reduce", da.ref, outa.ref, xa.ref, bnp.data_ptr(), 0, sums.data_ptr() + 16 * Cc, C.c_double(R),
+    call("basi_bn_bwd_reduce", da.ref, outa.ref, xa.ref, bnp.data_ptr(), 0, sums.data_ptr() + 16 * Cc * 8, C.c_double(R),
          dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 4)
     call("basi_bn_bwd_apply", da.ref, outa.ref, xa.ref, bnp.data_ptr(), coef.data_ptr(), 0, dxa.ref, dra.ref, 0)
     btol = 2e-4 if dtype == "f32" else 3e-2

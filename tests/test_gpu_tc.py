@@ -159,7 +159,7 @@ def test_tc_fprop_fused_bn_statistics(case):
     w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
     w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
     call("basi_tc_pack_weights", wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout)
-    sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda:0")
+    sums = torch.zeros(2 * cout * 8, dtype=torch.float64, device="cuda:0")
     bnp = torch.zeros(4 * cout, device="cuda:0")
     cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
     h = C.c_void_p()
@@ -169,7 +169,7 @@ def test_tc_fprop_fused_bn_statistics(case):
               C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
     call("basi_tc_conv_run", h)
     y = host(ya).astype(np.float64).reshape(-1, cout)
-    got, s = host(bnp), host(sums)
+    got, s = host(bnp), host(sums).reshape(8, 2 * cout).sum(0)
     _lib.load().basi_tc_conv_destroy(h)
     assert rel_err(s[:cout], y.sum(0)) < 1e-5 and rel_err(s[cout:], (y * y).sum(0)) < 1e-5
     mean, var = y.mean(0), y.var(0)
