@@ -198,76 +198,100 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
   }
 }
 
+// 128-bit packed row fragment: elements are unpacked at the point of use so that the UNR rows in flight cost
+// 4 registers each (not 8 floats) -- these kernels live or die by occupancy (ncu: 210 regs -> 1 block/SM before).
+template <typename T>
+struct Pack;
+template <>
+struct Pack<float> {
+  static constexpr int N = 4;
+  float4 r;
+  __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = r; }
+  __device__ __forceinline__ float get(int i) const { return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w)); }
+  __device__ __forceinline__ void set2(int i2, float a, float b) {
+    if (i2 == 0) { r.x = a; r.y = b; } else { r.z = a; r.w = b; }
+  }
+};
+template <>
+struct Pack<bf16> {
+  static constexpr int N = 8;
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = r; }
+  __device__ __forceinline__ uint32_t word(int w) const { return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w)); }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = word(i >> 1);
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set2(int i2, float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t w = *reinterpret_cast<uint32_t*>(&h);
+    if (i2 == 0) r.x = w; else if (i2 == 1) r.y = w; else if (i2 == 2) r.z = w; else r.w = w;
+  }
+};
+
+constexpr int BUNR = 2;   // rows in flight per thread in the backward kernels (occupancy provides the rest)
+
 // ---- backward reduce: dsums += (sum dy, sum dy*xhat); dy = dout * mask.
 // mask: out > 0 when out != NULL; else, when relu_from_x, (x-mean)*scale+beta > 0 (plain BN+ReLU: no need to read out)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo, const T* __restrict__ x,
                      int ldx, const float* __restrict__ bnp, int relu_from_x, int64_t R, int C,
                      double* __restrict__ dsums, double count, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ coef, unsigned int* counter) {
-  constexpr int VN = Vec<T>::N;
+  constexpr int VN = Pack<T>::N;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   const bool valid = cg * VN < C;
   const int c0 = cg * VN;
-  double s[VN], q[VN];
+  float fs[VN], fq[VN];
 #pragma unroll
-  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.0;
+  for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
   if (valid) {
-    float mean[VN], istd[VN], scale[VN], beta[VN];
+    float mean[VN], thr[VN];   // thr: dy passes iff (x - mean) * sgn > thr  <=>  (x-mean)*scale+beta > 0
+    float sgn[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
       mean[i] = bnp[c0 + i];
-      istd[i] = bnp[C + c0 + i];
-      scale[i] = bnp[2 * C + c0 + i];
-      beta[i] = bnp[3 * C + c0 + i];
+      const float sc = bnp[2 * C + c0 + i], be = bnp[3 * C + c0 + i];
+      sgn[i] = sc;
+      thr[i] = be;
     }
     const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
-    float fs[VN], fq[VN];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * BUNR) {
+      Pack<T> d[BUNR], xv[BUNR], o[BUNR];
+      bool ok[BUNR];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
-    int flush = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * UNR) {
-      Vec<T> d[UNR], xv[UNR], o[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < BUNR; ++u) {
         const int64_t rr = r + u * rstep;
-        if (rr < R) {
-          d[u] = Vec<T>::load(dout + rr * ldd + c0);
-          xv[u] = Vec<T>::load(x + rr * ldx + c0);
-          if (out) o[u] = Vec<T>::load(out + rr * ldo + c0);
-        } else {
-          d[u] = Vec<T>::zero();
-          xv[u] = Vec<T>::zero();
-          o[u] = Vec<T>::zero();
+        ok[u] = rr < R;
+        if (ok[u]) {
+          d[u].load(dout + rr * ldd + c0);
+          xv[u].load(x + rr * ldx + c0);
+          if (out) o[u].load(out + rr * ldo + c0);
         }
       }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u)
+      for (int u = 0; u < BUNR; ++u) {
+        if (!ok[u]) continue;
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float xc = xv[u].v[i] - mean[i];
-          float dy = d[u].v[i];
-          if (out) dy = o[u].v[i] > 0.f ? dy : 0.f;
-          else if (relu_from_x) dy = fmaf(xc, scale[i], beta[i]) > 0.f ? dy : 0.f;
+          const float xc = xv[u].get(i) - mean[i];
+          float dy = d[u].get(i);
+          if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xc, sgn[i], thr[i]) > 0.f ? dy : 0.f;
           fs[i] += dy;
-          fq[i] = fmaf(dy, xc * istd[i], fq[i]);
-        }
-      if (++flush == 4) {   // fp32 partials over 16 rows, then double
-        flush = 0;
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          s[i] += (double)fs[i];
-          q[i] += (double)fq[i];
-          fs[i] = fq[i] = 0.f;
+          fq[i] = fmaf(dy, xc, fq[i]);      // istd is applied once at the end
         }
       }
     }
+  }
+  double s[VN], q[VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      s[i] += (double)fs[i];
-      q[i] += (double)fq[i];
-    }
+  for (int i = 0; i < VN; ++i) {
+    s[i] = (double)fs[i];
+    q[i] = valid ? (double)fq[i] * (double)bnp[C + c0 + i] : 0.0;
   }
   double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
   const bool last = reduce_and_ticket<VN>(s, q, rep, rep + C, c0, valid, counter);
@@ -302,55 +326,61 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ dsums, double 
   coef[C + c] = (float)(s2 / count);
 }
 
-// ---- backward apply: dx = scale*(dy - c1 - xhat*c2); dres (+)= dy
+// ---- backward apply: dx = scale*(dy - c1 - xhat*c2) = A*dy - B - (x-mean)*Cc ; dres (+)= dy
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo, const T* __restrict__ x,
                     int ldx, const float* __restrict__ bnp, const float* __restrict__ coef, int relu_from_x,
                     T* __restrict__ dx, int lddx, T* __restrict__ dres, int lddr, int dres_acc, int64_t R, int C) {
-  constexpr int VN = Vec<T>::N;
+  constexpr int VN = Pack<T>::N;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   if (cg * VN >= C) return;
   const int c0 = cg * VN;
-  float mean[VN], istd[VN], scale[VN], beta[VN], k1[VN], k2[VN];
+  float mean[VN], A[VN], Bc[VN], Cc[VN], beta[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
     mean[i] = bnp[c0 + i];
-    istd[i] = bnp[C + c0 + i];
-    scale[i] = bnp[2 * C + c0 + i];
+    const float istd = bnp[C + c0 + i];
+    A[i] = bnp[2 * C + c0 + i];
     beta[i] = bnp[3 * C + c0 + i];
-    k1[i] = coef[c0 + i];
-    k2[i] = coef[C + c0 + i];
+    Bc[i] = A[i] * coef[c0 + i];
+    Cc[i] = A[i] * istd * istd * coef[C + c0 + i];
   }
   const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
   // rows are visited from the end: the reduce pass that ran just before touched the tail last, so it is the part
   // of dout / x / out most likely still in L2
-  const int64_t first = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-  for (int64_t rb = first; rb < R; rb += rstep * UNR) {
-    Vec<T> d[UNR], xv[UNR], o[UNR], dr[UNR];
-    int64_t rows[UNR];
+  for (int64_t rb = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; rb < R; rb += rstep * BUNR) {
+    Pack<T> d[BUNR], xv[BUNR], o[BUNR], dr[BUNR];
+    int64_t rows[BUNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
+    for (int u = 0; u < BUNR; ++u) {
       const int64_t rr = rb + u * rstep;
       rows[u] = rr < R ? (R - 1 - rr) : -1;
       if (rows[u] >= 0) {
-        d[u] = Vec<T>::load(dout + rows[u] * ldd + c0);
-        xv[u] = Vec<T>::load(x + rows[u] * ldx + c0);
-        if (out) o[u] = Vec<T>::load(out + rows[u] * ldo + c0);
-        if (dres && dres_acc) dr[u] = Vec<T>::load(dres + rows[u] * lddr + c0);
+        d[u].load(dout + rows[u] * ldd + c0);
+        xv[u].load(x + rows[u] * ldx + c0);
+        if (out) o[u].load(out + rows[u] * ldo + c0);
+        if (dres && dres_acc) dr[u].load(dres + rows[u] * lddr + c0);
       }
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
+    for (int u = 0; u < BUNR; ++u) {
       if (rows[u] < 0) continue;
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float xc = xv[u].v[i] - mean[i];
-        float dy = d[u].v[i];
-        if (out) dy = o[u].v[i] > 0.f ? dy : 0.f;
-        else if (relu_from_x) dy = fmaf(xc, scale[i], beta[i]) > 0.f ? dy : 0.f;
-        if (dres) dr[u].v[i] = dres_acc ? dr[u].v[i] + dy : dy;
-        d[u].v[i] = scale[i] * (dy - k1[i] - xc * istd[i] * k2[i]);
+      for (int i2 = 0; i2 < VN / 2; ++i2) {
+        float res[2], drs[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * i2 + h;
+          const float xc = xv[u].get(i) - mean[i];
+          float dy = d[u].get(i);
+          if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+          drs[h] = (dres && dres_acc) ? dr[u].get(i) + dy : dy;
+          res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
+        }
+        d[u].set2(i2, res[0], res[1]);
+        if (dres) dr[u].set2(i2, drs[0], drs[1]);
       }
       if (dres) dr[u].store(dres + rows[u] * lddr + c0);
       d[u].store(dx + rows[u] * lddx + c0);
@@ -431,7 +461,7 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
   BASI_CHECK_ARG(!coef || (dgamma && dbeta && count > 0), "bn_bwd_reduce: fused finalize needs dgamma, dbeta, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * UNR, 8, 2 * Vec<T>::N * sizeof(double));
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, 4 * BUNR, 12, 2 * Vec<T>::N * sizeof(double));
     bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, relu_from_x, R, x->c, dsums, count, dgamma, dbeta, coef, counter);
@@ -458,7 +488,7 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
   BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_apply: bad dres");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
-    RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 16, 0);
+    RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * BUNR, 12, 0);
     bn_bwd_apply_kernel<T><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, coef, relu_from_x, (T*)dx->ptr, dx->ld, dres ? (T*)dres->ptr : nullptr, dres ? dres->ld : 0,
