@@ -344,7 +344,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
     A[i] = bnp[2 * C + c0 + i];
     beta[i] = bnp[3 * C + c0 + i];
     Bc[i] = A[i] * coef[c0 + i];
-    Cc[i] = A[i] * istd * istd * coef[C + c0 + i];
+    Cc[i] = A[i] * istd * coef[C + c0 + i];
   }
   const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
   // rows are visited from the end: the reduce pass that ran just before touched the tail last, so it is the part
