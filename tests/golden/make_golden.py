@@ -1,0 +1,50 @@
+"""Generates tests/golden/*.npz from the CPU oracle (float64), seeded.
+
+The reference cannot run in this environment (TensorFlow 1.x is not installable) and ships no golden vectors for
+this path, so these fixtures pin the ORACLE against regressions and give the CUDA path a
+committed target; they are not outputs of the reference itself.  Run from the repo root:
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "instance-segment-basi_b200"))
+
+from basi_b200.BAISData import SyntheticData  # noqa: E402  (host-side synthetic batches only)
+from oracle import basi_oracle as O  # noqa: E402
+
+CASES = {
+    # name: variant, nseg, S, F, B, classes, pos_weight, class_weight
+    "2AddClass_S64_F8": ("2AddClass", 1, 64, 8, 2, 21, 3.0, 0.2),
+    "4BorderClass_S64_F8": ("4BorderClass", 4, 64, 8, 2, 21, 1.0, 0.1),
+}
+GRAD_KEYS = ("conv1_1_3x3_s2_n/weights", "conv3_1_1x1_proj/weights", "conv4_7_3x3/weights", "conv5_3_pool6_conv/weights",
+             "conv5_4_bn/conv5_4_bn/gamma", "class_attention_conv/biases")
+
+
+def build(name):
+    variant, nseg, S, F, B, classes, pw, cw = CASES[name]
+    sd = SyntheticData(B, (S, S), 8, classes, nseg, seed=7)
+    img, clicks, lab, cls = sd.next_batch()
+    params = O.init_params(O.param_specs(variant, classes, nseg, F), 11, trained_like=True)
+    data = np.stack([O.pack_input(img[b], clicks[b]) for b in range(B)])
+    r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float64)
+    out = dict(images=img, clicks=clicks, label_seg=lab, label_cls=cls, click_map=data[..., 3],
+               loss=np.float64(r["loss"]), loss_segment=np.float64(r["loss_segment"]),
+               loss_classes=np.float64(r["loss_classes"]), seg_logits=r["seg_logits"].astype(np.float32),
+               cls_logits=r["cls_logits"].astype(np.float32))
+    for k in GRAD_KEYS:
+        out["grad:" + k] = r["grads"][k].astype(np.float32)
+    return out
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in CASES:
+        np.savez_compressed(os.path.join(here, "golden_%s.npz" % name), **build(name))
+        print("wrote", name)
