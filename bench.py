@@ -156,6 +156,7 @@ def run_ours(args):
     from basi_b200.dp import DataParallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
     dp = DataParallel() if world > 1 else None
     rank = dp.rank if dp else 0
     dev_index = dp.local_rank if dp else 0
@@ -163,7 +164,7 @@ def run_ours(args):
     device = "cuda:%d" % dev_index
     tr = Train(batch_size=BATCH, last_pool_size=P, input_size=[S, S], log_dir="/tmp/basi_bench_%d" % rank,
                variant=VARIANT, num_classes=CLASSES, precision=args.precision, filter_number=FILTERS, seed=0,
-               device=device, dp=dp, use_cuda_graph=(world == 1 and not args.no_graph), use_tc=not args.no_tc)
+               device=device, dp=dp, use_cuda_graph=not args.no_graph, use_tc=not args.no_tc)
     eng = tr.engine
     if dp:
         dp.broadcast(eng.params_flat)
@@ -184,10 +185,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def device_step():
-        if dp:
-            eng.step_device(sync_grads=dp)
-        elif tr.use_cuda_graph:
+        if tr.use_cuda_graph:
             eng.replay()
+        elif dp:
+            eng.step_device(sync_grads=dp)
         else:
             eng.step_device()
 
@@ -195,7 +196,14 @@ def run_ours(args):
     eng.feed_clicks(ring[0][0], ring[0][1])
     eng.feed(None, ring[0][2], None, 5e-3)
     if tr.use_cuda_graph:
-        eng.capture(train=True)
+        try:
+            eng.capture(train=True, sync_grads=dp)
+        except Exception as e:        # e.g. an NCCL build that cannot be captured: fall back to eager launches
+            if not dp:
+                raise
+            sys.stderr.write("CUDA-graph capture with NCCL failed (%s); running eagerly\n" % (e,))
+            tr.use_cuda_graph = False
+            torch.cuda.synchronize()
     for _ in range(max(3, args.warmup)):
         device_step()
     barrier()

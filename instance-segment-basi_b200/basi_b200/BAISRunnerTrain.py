@@ -97,12 +97,12 @@ class Train(object):
             data, ann, cls, _, _ = batch if batch is not None else self.data_reader.next_batch_train()
             label_cls, label_seg = cls, np.asarray(ann)
             eng.feed(np.asarray(data, dtype=np.float32), label_seg, np.asarray(cls, dtype=np.int32), lr)
-        if self.dp is not None:
-            eng.step_device(sync_grads=self.dp.all_reduce_mean)
-        elif self.use_cuda_graph:
+        if self.use_cuda_graph:
             if eng._graph is None:
-                eng.capture(train=True)
+                eng.capture(train=True, sync_grads=self.dp)
             eng.replay()
+        elif self.dp is not None:
+            eng.step_device(sync_grads=self.dp)
         else:
             eng.step_device()
         if not fetch:

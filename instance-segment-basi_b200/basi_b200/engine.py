@@ -725,7 +725,8 @@ class Engine(object):
         return n
 
     # ---- CUDA graph capture of the whole step
-    def capture(self, train=True):
+    def capture(self, train=True, sync_grads=None):
+        """Captures one whole step (incl. the bucketed NCCL all-reduces when sync_grads is given) into a CUDA graph."""
         torch.cuda.synchronize(self.device)
         lr_saved = self.lr_dev.clone()
         self.lr_dev.zero_()      # the warm-up steps below must not move the weights
@@ -733,12 +734,12 @@ class Engine(object):
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.step_device() if train else self.forward_device()
+                self.step_device(sync_grads) if train else self.forward_device()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
-            self.step_device() if train else self.forward_device()
+            self.step_device(sync_grads) if train else self.forward_device()
         self.lr_dev.copy_(lr_saved)
         self._graph = g
         return g
