@@ -156,7 +156,7 @@ def run_ours(args):
     from basi_b200.dp import DataParallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
+    os.environ.pop("NCCL_DEBUG", None)         # keep NCCL's version banner off stdout (one JSON line only)
     dp = DataParallel() if world > 1 else None
     rank = dp.rank if dp else 0
     dev_index = dp.local_rank if dp else 0
