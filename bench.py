@@ -125,11 +125,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def kernel_profile(eng, torch):
+def kernel_profile(eng, torch, detail_path=None):
     """One instrumented eager step: CUDA events around every C-ABI call, aggregated per kernel entry point."""
     st = torch.cuda.current_stream()
     eng._zero_step_state(st.cuda_stream)
     agg = {}
+    detail = []
     for lst in (eng.pre, eng.fwd, eng.lossl, eng.post, eng.bwd):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(lst) + 1)]
         evs[0].record(st)
@@ -145,6 +146,12 @@ def kernel_profile(eng, torch):
             d["n"] += 1
             d["flops"] += meta.get("flops", 0.0)
             d["bytes"] += meta.get("bytes", 0.0)
+            detail.append((name, meta.get("layer", ""), ms, meta.get("flops", 0.0), meta.get("bytes", 0.0)))
+    if detail_path:
+        with open(detail_path, "w") as f:
+            for name, layer, ms, fl, by in detail:
+                f.write("%s\t%s\t%.2f us\t%s\n" % (name, layer, ms * 1e3, ("%.0f TF/s" % (fl / ms / 1e9)) if fl else
+                                                     (("%.0f GB/s" % (by / ms / 1e6)) if by else "")))
     return agg
 
 
@@ -251,7 +258,7 @@ def run_ours(args):
     value = images / (ms_dev * 1e-3)
     e2e = images / (ms_e2e * 1e-3)
     # ---- roofline of the dominant kernel (per-launch CUDA-event times of one eager step)
-    agg = kernel_profile(eng, torch)
+    agg = kernel_profile(eng, torch, args.detail)
     total_ms = sum(d["ms"] for d in agg.values())
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     name, d = top
@@ -302,6 +309,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-tc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    ap.add_argument("--detail", default=None, help="write per-call CUDA-event timings of one eager step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

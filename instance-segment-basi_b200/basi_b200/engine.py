@@ -631,7 +631,7 @@ class Engine(object):
         self._tc_plans.append(handle)
         self.tc_layers += 1
         self._last_tc = handle
-        meta = dict(flops=self._conv_flops(op))
+        meta = dict(flops=self._conv_flops(op), layer=op["name"])
         if kind == _lib.TC_WGRAD:
             meta["writes"] = [op["w"]]
         lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))

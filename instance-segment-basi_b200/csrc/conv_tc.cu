@@ -74,6 +74,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+                   "l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -173,7 +185,7 @@ struct SmemLayout {
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               bf16* __restrict__ dst, const ConvParams p) {
+               const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int STAGE = SmemLayout<BN>::STAGE;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -184,12 +196,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
   float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [4 warps][2*BN]
+  // output staging for the TMA store: NBOX boxes of [128 px][64 ch] bf16, SWIZZLE_128B, 1024-B aligned
+  constexpr int NBOX = (BN + 63) / 64;
+  uint8_t* stage_out = smem + (size_t)p.stages * STAGE + 1024 + 8 * BN * sizeof(float);
+  stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_out) + 1023) & ~(uintptr_t)1023);
   volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -277,58 +294,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> global (bf16) =====================
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
     const int q = warp - 4;                  // TMEM lane quarter
     const int row = q * 32 + lane;           // pixel row inside the tile
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+    const bool issuer = (warp == 4 && lane == 0);
+    const uint32_t so = smem_u32(stage_out);
+    const bool do_stats = p.bn_sums != nullptr;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.TW + wl, h = th * p.TH + hl, n = tn * p.TN + nl;
-      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-      bf16* out = dst + (((int64_t)n * p.H + h) * p.W + w) * p.ldd + nt * BN;
+      const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+      const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
+      // the previous tile's TMA store must have finished reading the staging buffer
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      const bool do_stats = p.bn_sums != nullptr;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
-        if (p.accumulate && valid) {
-          const uint4* o4 = reinterpret_cast<const uint4*>(out + c * 32);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint4 old = o4[v];
-            const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[v * 8 + 2 * j] += __uint_as_float(ow[j] << 16);
-              f[v * 8 + 2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
-            }
-          }
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        if (valid) {
-          uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
+        // row `row` of box (c/2): 128-byte line, 16-byte chunks XOR-swizzled with (row & 7) like TMA SWIZZLE_128B
+        const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * 128;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) o4[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t chunk = (uint32_t)(((c & 1) * 4 + v) ^ (row & 7));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[4 * v]),
+                       "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                       : "memory");
         }
         if (do_stats) {
           // statistics of the values as stored (bf16-rounded).  Rows outside the tensor are masked: for k > 1 they
           // hold phantom outputs of the padded convolution (their taps still reach valid pixels).
-          float sq[32];
+          float f[32], sq[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float a = valid ? __uint_as_float(pk[j] << 16) : 0.f;
@@ -346,9 +355,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);          // TMEM accumulator is free again
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int j = 0; j < NBOX; ++j) {
+          if (p.accumulate) tma_reduce_add_4d(&mapD, so + j * A_BYTES, nt * BN + j * 64, w0, h0, n0);
+          else tma_store_4d(&mapD, so + j * A_BYTES, nt * BN + j * 64, w0, h0, n0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
         for (int col = q * 32 + lane; col < BN; col += 128) {
           const float s1 = stat_s[col] + stat_s[2 * BN + col] + stat_s[4 * BN + col] + stat_s[6 * BN + col];
           const float s2 = stat_s[BN + col] + stat_s[3 * BN + col] + stat_s[5 * BN + col] + stat_s[7 * BN + col];
@@ -356,9 +374,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           atomicAdd(rep + nt * BN + col, (double)s1);
           atomicAdd(rep + p.Cdst + nt * BN + col, (double)s2);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
     if (p.bn_sums != nullptr) __threadfence();
   }
   tc_fence_before();
@@ -645,7 +663,7 @@ using namespace basi::tc;
 struct basi_tc_conv {
   int kind;
   int bn;
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapD;
   ConvParams cp;
   WgradParams wp;
   bf16* dst;
@@ -680,7 +698,7 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->dst, pl->cp);
+  conv_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
   return BASI_OK;
 }
 template <int BN>
@@ -735,6 +753,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, bn);
+    if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN);
     if (rc != BASI_OK) {
       delete pl;
       return rc;
@@ -752,10 +771,12 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     }
     cp.accumulate = accumulate;
     const int stage_bytes = A_BYTES + bn * 128;
-    int stages = (int)((227 * 1024 - 2048 - 8 * bn * (int)sizeof(float)) / stage_bytes);
+    const int out_stage = ((bn + 63) / 64) * A_BYTES;
+    const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 8 * bn * (int)sizeof(float) + 1024 /*align*/ + out_stage;
+    int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     cp.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + 1024 + 256 + 8 * bn * sizeof(float);
+    pl->smem = (size_t)stages * stage_bytes + fixed;
     pl->dst = (bf16*)dstt->ptr;
     const int total = cp.m_tiles * cp.n_tiles;
     pl->grid = total < sms ? total : sms;
