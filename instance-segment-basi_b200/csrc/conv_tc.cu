@@ -326,10 +326,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
         // row `row` of box (c/2): 128-byte line, 16-byte chunks XOR-swizzled with (row & 7) like TMA SWIZZLE_128B
-        const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * 128;
+        // (BN == 32: one 32-channel box, 64-byte rows, no swizzle)
+        const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * (BN >= 64 ? 128 : 2 * BN);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          const uint32_t chunk = (uint32_t)(((c & 1) * 4 + v) ^ (row & 7));
+          const uint32_t chunk = BN >= 64 ? (uint32_t)(((c & 1) * 4 + v) ^ (row & 7)) : (uint32_t)v;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[4 * v]),
                        "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
                        : "memory");
@@ -599,7 +600,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC activation: dims (C, W, H, N), box (64, TW, TH, TN)
-static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, int TN) {
+static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, int TN, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc: cuTensorMapEncodeTiled not available");
@@ -607,10 +608,11 @@ static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, in
   }
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->ld * 2 * t->w, (cuuint64_t)t->ld * 2 * t->w * t->h};
-  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc: cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
     return BASI_E_CUDA;
@@ -753,7 +755,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, bn);
-    if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN);
+    if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
     if (rc != BASI_OK) {
       delete pl;
       return rc;
