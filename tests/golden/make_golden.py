@@ -34,12 +34,17 @@ def build(name):
     params = O.init_params(O.param_specs(variant, classes, nseg, F), 11, trained_like=True)
     data = np.stack([O.pack_input(img[b], clicks[b]) for b in range(B)])
     r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float64)
+    r32 = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float32)
     out = dict(images=img, clicks=clicks, label_seg=lab, label_cls=cls, click_map=data[..., 3],
                loss=np.float64(r["loss"]), loss_segment=np.float64(r["loss_segment"]),
                loss_classes=np.float64(r["loss_classes"]), seg_logits=r["seg_logits"].astype(np.float32),
                cls_logits=r["cls_logits"].astype(np.float32))
     for k in GRAD_KEYS:
         out["grad:" + k] = r["grads"][k].astype(np.float32)
+        # what the float32 run of the same oracle loses against float64 on this tensor (norm-wise): the noise floor
+        # any float32 implementation has on these tiny, ill-conditioned batch-stat-BN nets
+        a, b = r32["grads"][k].astype(np.float64).reshape(-1), r["grads"][k].astype(np.float64).reshape(-1)
+        out["floor:" + k] = np.float64(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
     return out
 
 
