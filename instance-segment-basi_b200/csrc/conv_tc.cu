@@ -22,7 +22,8 @@ namespace tc {
 constexpr int BM = 128;            // pixels per tile (UMMA M)
 constexpr int KC = 64;             // channels per k-chunk: 64 bf16 = 128 B = one swizzle row
 constexpr int A_BYTES = BM * 128;  // 16 KB
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;        // wgrad: 4 control warps + 4 epilogue warps
+constexpr int NTHREADS_CONV = 384;   // fprop/dgrad: 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -183,7 +184,7 @@ struct SmemLayout {
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -215,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 4);   // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * i, 8);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -295,7 +296,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
-    const int q = warp - 4;                  // TMEM lane quarter
+    const int q = warp & 3;                  // TMEM lane quarter (hardware: warp w may touch lanes 32*(w%4)..+31)
+    const int half = (warp - 4) >> 2;        // the two warps of a quarter split the 32-column chunks
     const int row = q * 32 + lane;           // pixel row inside the tile
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
     const bool issuer = (warp == 4 && lane == 0);
@@ -313,10 +315,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       // the previous tile's TMA store must have finished reading the staging buffer
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
+        if ((c & 1) != half && BN >= 64) continue;
+        if (BN < 64 && half != 0) continue;
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         uint32_t pk[16];
@@ -358,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);          // TMEM accumulator is free again
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (issuer) {
 #pragma unroll
         for (int j = 0; j < NBOX; ++j) {
@@ -368,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (do_stats) {
-        for (int col = q * 32 + lane; col < BN; col += 128) {
+        for (int col = (warp - 4) * 32 + lane; col < BN; col += 256) {
           const float s1 = stat_s[col] + stat_s[2 * BN + col] + stat_s[4 * BN + col] + stat_s[6 * BN + col];
           const float s2 = stat_s[BN + col] + stat_s[3 * BN + col] + stat_s[5 * BN + col] + stat_s[7 * BN + col];
           double* rep = p.bn_sums + (size_t)(mt % BASI_BN_REPLICAS) * 2 * p.Cdst;
@@ -396,7 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (*s_is_last) {
       __threadfence();
       const int C = p.Cdst;
-      for (int c = threadIdx.x; c < C; c += NTHREADS) {
+      for (int c = threadIdx.x; c < C; c += NTHREADS_CONV) {
         double s1 = 0, s2 = 0;
 #pragma unroll
         for (int r = 0; r < BASI_BN_REPLICAS; ++r) {
@@ -700,7 +704,7 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  conv_tc_kernel<BN><<<pl->grid, NTHREADS_CONV, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
   return BASI_OK;
 }
 template <int BN>
