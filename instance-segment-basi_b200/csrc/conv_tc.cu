@@ -149,6 +149,7 @@ struct ConvParams {
   int off_h, off_w, step;
   int accumulate;
   int stages;
+  int out_bufs;   // 1 or 2 output staging buffers (2: the TMA store of tile i overlaps the epilogue of tile i+1)
   // optional fused batch-norm statistics of the produced tensor (fprop): per-channel sum / sum of squares of the
   // bf16-rounded outputs, double atomics per tile, last CTA finalizes bnp = [mean | istd | gamma*istd | beta]
   double* bn_sums;
@@ -301,7 +302,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int row = q * 32 + lane;           // pixel row inside the tile
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
     const bool issuer = (warp == 4 && lane == 0);
-    const uint32_t so = smem_u32(stage_out);
+    const uint32_t so_base = smem_u32(stage_out);
     const bool do_stats = p.bn_sums != nullptr;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -313,8 +314,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      // the previous tile's TMA store must have finished reading the staging buffer
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // the TMA store that last used this staging buffer must have finished reading it
+      const uint32_t so = so_base + (p.out_bufs == 2 ? (uint32_t)(it & 1) * (NBOX * A_BYTES) : 0u);
+      if (issuer) {
+        if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll
@@ -777,7 +782,10 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     }
     cp.accumulate = accumulate;
     const int stage_bytes = A_BYTES + bn * 128;
-    const int out_stage = ((bn + 63) / 64) * A_BYTES;
+    // small-K layers are paced by the epilogue: give them two output staging buffers; large-K layers keep the
+    // shared memory for pipeline stages
+    cp.out_bufs = (cp.taps * cp.k_chunks <= 8) ? 2 : 1;
+    const int out_stage = cp.out_bufs * ((bn + 63) / 64) * A_BYTES;
     const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 8 * bn * (int)sizeof(float) + 1024 /*align*/ + out_stage;
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
