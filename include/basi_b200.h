@@ -184,6 +184,11 @@ int basi_tc_conv_supported(int kind, const basi_conv_desc* d, const basi_tensor*
 /* w_hwio f32 [taps][Cin][Cout] -> bf16 [taps][Cin][Cout] and bf16 [taps][Cout][Cin] */
 int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int taps, int cin, int cout,
                          void* stream);
+/* The same for many layers in ONE launch.  table_dev: device array of n_layers entries
+ *   struct { const float* w; void* w_io; void* w_oi; int32 taps, cin, cout, block_start, tiles_co, tiles_ci, pad; }
+ * (48 bytes each) with tiles_c* = ceil(c*/32), block_start = running sum of taps*tiles_ci*tiles_co, and
+ * total_blocks = that sum over all layers. */
+int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_blocks, void* stream);
 int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
                         const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out);
 /* fprop plans only: also accumulate the batch-norm statistics of the produced tensor in the epilogue (same

@@ -29,6 +29,12 @@ class ConvDesc(C.Structure):
                 ("pad_t", C.c_int32), ("pad_l", C.c_int32), ("relu", C.c_int32)]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("w_io", C.c_void_p), ("w_oi", C.c_void_p), ("taps", C.c_int32),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("block_start", C.c_int32), ("tiles_co", C.c_int32),
+                ("tiles_ci", C.c_int32), ("pad", C.c_int32)]
+
+
 _P = C.c_void_p
 _TP = C.POINTER(Tensor)
 _DP = C.POINTER(ConvDesc)
@@ -69,6 +75,7 @@ SIGNATURES = {
     "basi_cast_bf16_to_f32": [_P, _P, _i64, _P],
     "basi_tc_conv_supported": [_i, _DP, _TP, _TP],
     "basi_tc_pack_weights": [_P, _P, _P, _i, _i, _i, _P],
+    "basi_tc_pack_weights_multi": [_P, _i, _i, _P],
     "basi_tc_conv_create": [_i, _DP, _TP, _TP, _P, _P, _i, C.POINTER(_P)],
     "basi_tc_conv_set_bn_stats": [_P, _P, _P, _P, _d, _f, _P, _P],
     "basi_tc_conv_run": [_P, _P],

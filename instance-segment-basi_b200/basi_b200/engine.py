@@ -94,6 +94,7 @@ class Engine(object):
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
         self._tc_weights = []
+        self._pack_table = None
         self._zero_grads = []    # gradient buffers that are pre-zeroed every step (concat buffers)
         self._acts = {}          # node index -> Act (or tuple for deferred bn)
         self._graph = None
@@ -638,11 +639,22 @@ class Engine(object):
         return handle
 
     def _refresh_weight_copies(self, stream=None):
+        """bf16 copies (both layouts) of every tensor-core layer's weights: one launch for all layers."""
         if not self._tc_weights:
             return
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        for wptr, w_io, w_oi, taps, cin, cout in self._tc_weights:
-            _lib.call("basi_tc_pack_weights", wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, st)
+        if self._pack_table is None:
+            entries = (_lib.PackEntry * len(self._tc_weights))()
+            blocks = 0
+            for i, (wptr, w_io, w_oi, taps, cin, cout) in enumerate(self._tc_weights):
+                tco, tci = -(-cout // 32), -(-cin // 32)
+                entries[i] = _lib.PackEntry(wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, blocks, tco, tci, 0)
+                blocks += taps * tco * tci
+            raw = np.frombuffer(bytes(entries), dtype=np.uint8).copy()
+            self._pack_table = torch.from_numpy(raw).to(self.device)
+            self._pack_blocks = blocks
+        _lib.call("basi_tc_pack_weights_multi", self._pack_table.data_ptr(), len(self._tc_weights), self._pack_blocks,
+                  st)
 
     def __del__(self):
         try:
@@ -721,7 +733,7 @@ class Engine(object):
     def launches_per_step(self):
         n = len(self.pre) + len(self.fwd) + len(self.post)
         if self.training:
-            n += len(self.lossl) + len(self.bwd) + 1 + len(self._tc_weights)
+            n += len(self.lossl) + len(self.bwd) + 1 + (1 if self._tc_weights else 0)
         return n
 
     # ---- CUDA graph capture of the whole step

@@ -144,60 +144,6 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
   if (c < C) finalize_channel(sums, gamma, beta, count, eps, bnp, C, c);
 }
 
-// ---- apply: out = act((x-mean)*scale+beta [+ res | + (res-rmean)*rscale+rbeta])
-template <typename T, bool HAS_RES, bool RES_BN>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ bnp,
-                                                       const T* __restrict__ res, int ldr,
-                                                       const float* __restrict__ rbnp, int relu, T* __restrict__ out,
-                                                       int ldo, int64_t R, int C) {
-  constexpr int VN = Vec<T>::N;
-  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cg * VN >= C) return;
-  const int c0 = cg * VN;
-  float mean[VN], scale[VN], beta[VN];
-  float rmean[VN], rscale[VN], rbeta[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    mean[i] = bnp[c0 + i];
-    scale[i] = bnp[2 * C + c0 + i];
-    beta[i] = bnp[3 * C + c0 + i];
-    if (RES_BN) {
-      rmean[i] = rbnp[c0 + i];
-      rscale[i] = rbnp[2 * C + c0 + i];
-      rbeta[i] = rbnp[3 * C + c0 + i];
-    }
-  }
-  const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * UNR) {
-    Vec<T> v[UNR], rv[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int64_t rr = r + u * rstep;
-      if (rr < R) {
-        v[u] = Vec<T>::load(x + rr * ldx + c0);
-        if (HAS_RES) rv[u] = Vec<T>::load(res + rr * ldr + c0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int64_t rr = r + u * rstep;
-      if (rr >= R) break;
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        float o = fmaf(v[u].v[i] - mean[i], scale[i], beta[i]);
-        if (HAS_RES) {
-          float t = rv[u].v[i];
-          if (RES_BN) t = fmaf(t - rmean[i], rscale[i], rbeta[i]);
-          o += t;
-        }
-        if (relu) o = fmaxf(o, 0.f);
-        v[u].v[i] = o;
-      }
-      v[u].store(out + rr * ldo + c0);
-    }
-  }
-}
-
 // 128-bit packed row fragment: elements are unpacked at the point of use so that the UNR rows in flight cost
 // 4 registers each (not 8 floats) -- these kernels live or die by occupancy (ncu: 210 regs -> 1 block/SM before).
 template <typename T>
@@ -231,6 +177,60 @@ struct Pack<bf16> {
   }
 };
 
+// ---- apply: out = act((x-mean)*scale+beta [+ res | + (res-rmean)*rscale+rbeta])
+template <typename T, bool HAS_RES, bool RES_BN>
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(const T* __restrict__ x, int ldx,
+                                                          const float* __restrict__ bnp, const T* __restrict__ res,
+                                                          int ldr, const float* __restrict__ rbnp, int relu,
+                                                          T* __restrict__ out, int ldo, int64_t R, int C) {
+  constexpr int VN = Pack<T>::N;
+  constexpr int AUNR = 4;
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cg * VN >= C) return;
+  const int c0 = cg * VN;
+  // y = x*scale + shift  with shift = beta - mean*scale (+ the residual BN's shift)
+  float scale[VN], shift[VN], rscale[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    scale[i] = bnp[2 * C + c0 + i];
+    shift[i] = fmaf(-bnp[c0 + i], scale[i], bnp[3 * C + c0 + i]);
+    if (RES_BN) {
+      rscale[i] = rbnp[2 * C + c0 + i];
+      shift[i] += fmaf(-rbnp[c0 + i], rscale[i], rbnp[3 * C + c0 + i]);
+    }
+  }
+  const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * AUNR) {
+    Pack<T> v[AUNR], rv[AUNR];
+#pragma unroll
+    for (int u = 0; u < AUNR; ++u) {
+      const int64_t rr = r + u * rstep;
+      if (rr < R) {
+        v[u].load(x + rr * ldx + c0);
+        if (HAS_RES) rv[u].load(res + rr * ldr + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < AUNR; ++u) {
+      const int64_t rr = r + u * rstep;
+      if (rr >= R) break;
+#pragma unroll
+      for (int i2 = 0; i2 < VN / 2; ++i2) {
+        float o[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * i2 + h;
+          float t = fmaf(v[u].get(i), scale[i], shift[i]);
+          if (HAS_RES) t = RES_BN ? fmaf(rv[u].get(i), rscale[i], t) : t + rv[u].get(i);
+          o[h] = relu ? fmaxf(t, 0.f) : t;
+        }
+        v[u].set2(i2, o[0], o[1]);
+      }
+      v[u].store(out + rr * ldo + c0);
+    }
+  }
+}
+
 constexpr int BUNR = 2;   // rows in flight per thread in the backward kernels (occupancy provides the rest)
 
 // ---- backward reduce: dsums += (sum dy, sum dy*xhat); dy = dout * mask.
@@ -256,7 +256,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
       mean[i] = bnp[c0 + i];
       const float sc = bnp[2 * C + c0 + i], be = bnp[3 * C + c0 + i];
       sgn[i] = sc;
-      thr[i] = be;
+      thr[i] = fmaf(-mean[i], sc, be);   // same x*scale+shift expression as bn_apply -> identical ReLU mask
     }
     const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * BUNR) {
@@ -277,10 +277,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
         if (!ok[u]) continue;
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float xc = xv[u].get(i) - mean[i];
+          const float xr = xv[u].get(i);
+          const float xc = xr - mean[i];
           float dy = d[u].get(i);
           if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
-          else if (relu_from_x) dy = fmaf(xc, sgn[i], thr[i]) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xr, sgn[i], thr[i]) > 0.f ? dy : 0.f;
           fs[i] += dy;
           fq[i] = fmaf(dy, xc, fq[i]);      // istd is applied once at the end
         }
@@ -342,7 +343,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
     mean[i] = bnp[c0 + i];
     const float istd = bnp[C + c0 + i];
     A[i] = bnp[2 * C + c0 + i];
-    beta[i] = bnp[3 * C + c0 + i];
+    beta[i] = fmaf(-mean[i], A[i], bnp[3 * C + c0 + i]);   // shift of bn_apply's x*scale+shift (same ReLU mask)
     Bc[i] = A[i] * coef[c0 + i];
     Cc[i] = A[i] * istd * coef[C + c0 + i];
   }
@@ -372,10 +373,11 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int i = 2 * i2 + h;
-          const float xc = xv[u].get(i) - mean[i];
+          const float xr = xv[u].get(i);
+          const float xc = xr - mean[i];
           float dy = d[u].get(i);
           if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
-          else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xr, A[i], beta[i]) > 0.f ? dy : 0.f;
           drs[h] = (dres && dres_acc) ? dr[u].get(i) + dy : dy;
           res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
         }

@@ -13,6 +13,7 @@
 // warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).  Two TMEM accumulators
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -589,6 +590,47 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
   }
 }
 
+// all layers in one launch: blockIdx.x -> (layer, tap, ci tile, co tile) through a small table in device memory
+struct PackEntry {
+  const float* w;
+  bf16* w_io;
+  bf16* w_oi;
+  int taps, cin, cout;
+  int block_start;   // first block of this layer
+  int tiles_co, tiles_ci;
+  int pad;
+};
+__global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n_layers) {
+  __shared__ float tile[32][33];
+  __shared__ PackEntry e;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {   // last entry with block_start <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    e = table[lo];
+  }
+  __syncthreads();
+  int b = blockIdx.x - e.block_start;
+  const int cot = b % e.tiles_co; b /= e.tiles_co;
+  const int cit = b % e.tiles_ci; b /= e.tiles_ci;
+  const int tap = b;
+  const int ci0 = cit * 32, co0 = cot * 32;
+  const size_t base = (size_t)tap * e.cin * e.cout;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (ci < e.cin && co < e.cout) e.w_io[base + (size_t)ci * e.cout + co] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (ci < e.cin && co < e.cout) e.w_oi[base + (size_t)co * e.cin + ci] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -737,6 +779,15 @@ int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int t
   return BASI_OK;
 }
 
+int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_blocks, void* stream) {
+  BASI_CHECK_ARG(table_dev && n_layers > 0 && total_blocks > 0, "tc_pack_weights_multi: bad argument");
+  static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI (see include/basi_b200.h)");
+  pack_weights_multi_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>((const PackEntry*)table_dev,
+                                                                                   n_layers);
+  BASI_CHECK_LAUNCH("tc_pack_weights_multi");
+  return BASI_OK;
+}
+
 /* kind FPROP: a = x, b = y (written), w_bf16 = [tap][Cout][Cin]
  * kind DGRAD: a = dy, b = dx (written / accumulated), w_bf16 = [tap][Cin][Cout]
  * kind WGRAD: a = x, b = dy, dw = HWIO float32 gradient (added into) */
@@ -761,6 +812,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     const basi_tensor* dstt = b;
     const int ndim = dstt->c, kdim = src->c;
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
+    if (getenv("BASI_TC_BN256") && ndim % 256 == 0) bn = 256;   // experiment switch (measured: not faster)
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, bn);
@@ -851,7 +903,8 @@ int basi_tc_conv_run(basi_tc_conv* pl, void* stream) {
     if (pl->bn == 128) launch_wgrad<128>(pl, st);
     else launch_wgrad<64>(pl, st);
   } else {
-    if (pl->bn == 128) launch_conv<128>(pl, st);
+    if (pl->bn == 256) launch_conv<256>(pl, st);
+    else if (pl->bn == 128) launch_conv<128>(pl, st);
     else if (pl->bn == 64) launch_conv<64>(pl, st);
     else launch_conv<32>(pl, st);
   }

@@ -117,7 +117,7 @@ __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH,
   }
 }
 
-// one block per output pixel; threads (tx over channel groups, ty over window pixels)
+// one block per (output pixel, chunk of blockDim.x channel groups); ty strides over the window pixels
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, int k, T* __restrict__ y,
                                    int ldy, int OH, int OW) {
@@ -128,35 +128,37 @@ __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int ldx, int H, int 
   const int n = blockIdx.x / (OW * OH);
   const int cgs = C / VN;
   const float inv = 1.0f / (float)(k * k);
-  for (int cgb = 0; cgb < cgs; cgb += blockDim.x) {
-    const int cg = cgb + threadIdx.x;
-    float a[VN];
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  float a[VN];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) a[j] = 0.f;
-    if (cg < cgs) {
-      for (int p = threadIdx.y; p < k * k; p += blockDim.y) {
-        int ih = oh * k + p / k, iw = ow * k + p % k;
-        Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + ih) * W + iw) * ldx + cg * VN);
+  for (int j = 0; j < VN; ++j) a[j] = 0.f;
+  if (cg < cgs) {
+    const T* base = x + (((int64_t)n * H + oh * k) * W + ow * k) * ldx + cg * VN;
+    for (int p = threadIdx.y; p < k * k; p += blockDim.y) {
+      const int dy = p / k, dx = p - dy * k;
+      Vec<T> v = Vec<T>::load(base + ((int64_t)dy * W + dx) * ldx);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) a[j] += v.v[j];
-      }
+      for (int j = 0; j < VN; ++j) a[j] += v.v[j];
     }
-    float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
+  }
+  float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
 #pragma unroll
-    for (int j = 0; j < VN; ++j) mine[j] = a[j];
-    __syncthreads();
-    if (threadIdx.y == 0 && cg < cgs) {
-      for (int yy = 1; yy < blockDim.y; ++yy) {
-        const float* o = sacc + ((size_t)yy * blockDim.x + threadIdx.x) * VN;
+  for (int j = 0; j < VN; ++j) mine[j] = a[j];
+  __syncthreads();
+  // tree over ty
+  for (int s2 = blockDim.y >> 1; s2 >= 1; s2 >>= 1) {
+    if ((int)threadIdx.y < s2) {
+      const float* o = sacc + ((size_t)(threadIdx.y + s2) * blockDim.x + threadIdx.x) * VN;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) a[j] += o[j];
-      }
-      Vec<T> r;
-#pragma unroll
-      for (int j = 0; j < VN; ++j) r.v[j] = a[j] * inv;
-      r.store(y + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
+      for (int j = 0; j < VN; ++j) mine[j] += o[j];
     }
     __syncthreads();
+  }
+  if (threadIdx.y == 0 && cg < cgs) {
+    Vec<T> r;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) r.v[j] = mine[j] * inv;
+    r.store(y + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
   }
 }
 
@@ -230,7 +232,18 @@ __global__ void bilinear_ac_fwd_kernel(const T* __restrict__ x, int ldx, int IH,
   }
 }
 
-// adjoint: one block per input (small) pixel, gather over the output pixels that touch it
+// adjoint: one block per (input pixel, channel chunk); gathers only over the output window whose bilinear support
+// contains that input pixel
+__device__ __forceinline__ void ac_window(int s, float scale, int in_size, int out_size, int& lo, int& hi) {
+  if (scale <= 0.f || in_size <= 1) {
+    lo = 0;
+    hi = out_size - 1;
+    return;
+  }
+  lo = max(0, (int)floorf((float)(s - 1) / scale) - 1);
+  hi = min(out_size - 1, (int)ceilf((float)(s + 1) / scale) + 1);
+}
+
 template <typename T>
 __global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, T* __restrict__ dx, int ldx,
                                        int IH, int IW, int C, float sh, float sw, int acc) {
@@ -240,50 +253,54 @@ __global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH
   const int sy = (blockIdx.x / IW) % IH;
   const int n = blockIdx.x / (IW * IH);
   const int cgs = C / VN;
-  for (int cgb = 0; cgb < cgs; cgb += blockDim.x) {
-    const int cg = cgb + threadIdx.x;
-    float a[VN];
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  int oh0, oh1, ow0, ow1;
+  ac_window(sy, sh, IH, OH, oh0, oh1);
+  ac_window(sx, sw, IW, OW, ow0, ow1);
+  const int nh = oh1 - oh0 + 1, nw = ow1 - ow0 + 1;
+  float a[VN];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) a[j] = 0.f;
-    if (cg < cgs) {
-      for (int p = threadIdx.y; p < OH * OW; p += blockDim.y) {
-        int oh = p / OW, ow = p % OW;
-        int y0, y1, x0, x1;
-        float fy, fx;
-        ac_coord(oh, sh, IH, y0, y1, fy);
-        ac_coord(ow, sw, IW, x0, x1, fx);
-        float wy = (y0 == sy ? 1.f - fy : 0.f) + (y1 == sy ? fy : 0.f);
-        float wx = (x0 == sx ? 1.f - fx : 0.f) + (x1 == sx ? fx : 0.f);
-        float wgt = wy * wx;
-        if (wgt == 0.f) continue;
-        Vec<T> d = Vec<T>::load(dy + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
+  for (int j = 0; j < VN; ++j) a[j] = 0.f;
+  if (cg < cgs) {
+    for (int p = threadIdx.y; p < nh * nw; p += blockDim.y) {
+      const int oh = oh0 + p / nw, ow = ow0 + p % nw;
+      int y0, y1, x0, x1;
+      float fy, fx;
+      ac_coord(oh, sh, IH, y0, y1, fy);
+      ac_coord(ow, sw, IW, x0, x1, fx);
+      const float wy = (y0 == sy ? 1.f - fy : 0.f) + (y1 == sy ? fy : 0.f);
+      const float wx = (x0 == sx ? 1.f - fx : 0.f) + (x1 == sx ? fx : 0.f);
+      const float wgt = wy * wx;
+      if (wgt == 0.f) continue;
+      Vec<T> d = Vec<T>::load(dy + (((int64_t)n * OH + oh) * OW + ow) * ldy + cg * VN);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) a[j] = fmaf(d.v[j], wgt, a[j]);
-      }
+      for (int j = 0; j < VN; ++j) a[j] = fmaf(d.v[j], wgt, a[j]);
     }
-    float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
+  }
+  float* mine = sacc + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
 #pragma unroll
-    for (int j = 0; j < VN; ++j) mine[j] = a[j];
-    __syncthreads();
-    if (threadIdx.y == 0 && cg < cgs) {
-      for (int yy = 1; yy < blockDim.y; ++yy) {
-        const float* o = sacc + ((size_t)yy * blockDim.x + threadIdx.x) * VN;
+  for (int j = 0; j < VN; ++j) mine[j] = a[j];
+  __syncthreads();
+  for (int s2 = blockDim.y >> 1; s2 >= 1; s2 >>= 1) {
+    if ((int)threadIdx.y < s2) {
+      const float* o = sacc + ((size_t)(threadIdx.y + s2) * blockDim.x + threadIdx.x) * VN;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) a[j] += o[j];
-      }
-      T* dst = dx + (((int64_t)n * IH + sy) * IW + sx) * ldx + cg * VN;
-      Vec<T> r;
-      if (acc) {
-        r = Vec<T>::load(dst);
-#pragma unroll
-        for (int j = 0; j < VN; ++j) r.v[j] += a[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < VN; ++j) r.v[j] = a[j];
-      }
-      r.store(dst);
+      for (int j = 0; j < VN; ++j) mine[j] += o[j];
     }
     __syncthreads();
+  }
+  if (threadIdx.y == 0 && cg < cgs) {
+    T* dst = dx + (((int64_t)n * IH + sy) * IW + sx) * ldx + cg * VN;
+    Vec<T> r;
+    if (acc) {
+      r = Vec<T>::load(dst);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) r.v[j] += mine[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) r.v[j] = mine[j];
+    }
+    r.store(dst);
   }
 }
 
@@ -603,12 +620,14 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
   return BASI_OK;
 }
 
-static void pool_block(int cgs, int VN, dim3* block, size_t* smem) {
-  int bx = cgs < 256 ? cgs : 256;
+// (bx channel groups) x (by = 256/bx window threads, a power of two for the tree reduction); grid.y chunks
+static void pool_block(int cgs, int VN, dim3* block, size_t* smem, unsigned* chunks) {
+  int bx = 1;
+  while (bx * 2 <= 8 && bx * 2 <= cgs) bx *= 2;
   int by = 256 / bx;
-  if (by < 1) by = 1;
   *block = dim3(bx, by);
   *smem = (size_t)bx * by * VN * sizeof(float);
+  *chunks = (unsigned)((cgs + bx - 1) / bx);
 }
 
 int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* stream) {
@@ -618,8 +637,9 @@ int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* st
   DISPATCH_T(x->dtype, {
     dim3 block;
     size_t smem;
-    pool_block(x->c / Vec<T>::N, Vec<T>::N, &block, &smem);
-    avgpool_fwd_kernel<T><<<(unsigned)pixels(y), block, smem, (cudaStream_t)stream>>>(
+    unsigned chunks;
+    pool_block(x->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks);
+    avgpool_fwd_kernel<T><<<dim3((unsigned)pixels(y), chunks), block, smem, (cudaStream_t)stream>>>(
         (const T*)x->ptr, x->ld, x->h, x->w, x->c, k, (T*)y->ptr, y->ld, y->h, y->w);
   })
   BASI_CHECK_LAUNCH("avgpool_fwd");
@@ -660,8 +680,9 @@ int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accum
   DISPATCH_T(dx->dtype, {
     dim3 block;
     size_t smem;
-    pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem);
-    bilinear_ac_bwd_kernel<T><<<(unsigned)pixels(dx), block, smem, (cudaStream_t)stream>>>(
+    unsigned chunks;
+    pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks);
+    bilinear_ac_bwd_kernel<T><<<dim3((unsigned)pixels(dx), chunks), block, smem, (cudaStream_t)stream>>>(
         (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, ac_scale(dx->h, dy->h),
         ac_scale(dx->w, dy->w), accumulate);
   })
