@@ -185,8 +185,8 @@ int basi_tc_conv_supported(int kind, const basi_conv_desc* d, const basi_tensor*
 int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int taps, int cin, int cout,
                          void* stream);
 /* The same for many layers in ONE launch.  table_dev: device array of n_layers entries
- *   struct { const float* w; void* w_io; void* w_oi; int32 taps, cin, cout, block_start, tiles_co, tiles_ci, pad; }
- * (48 bytes each) with tiles_ci = ceil(cin / 32), tiles_co = ceil(cout / 32), block_start = running sum of
+ *   struct { const float* w; void* w_io; void* w_oi; int32 taps, cin, cout, block_start, tiles_co, tiles_ci, pad0, pad1; }
+ * (56 bytes each) with tiles_ci = ceil(cin / 32), tiles_co = ceil(cout / 32), block_start = running sum of
  * taps x tiles_ci x tiles_co, and
  * total_blocks = that sum over all layers. */
 int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_blocks, void* stream);

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
 class PackEntry(C.Structure):
     _fields_ = [("w", C.c_void_p), ("w_io", C.c_void_p), ("w_oi", C.c_void_p), ("taps", C.c_int32),
                 ("cin", C.c_int32), ("cout", C.c_int32), ("block_start", C.c_int32), ("tiles_co", C.c_int32),
-                ("tiles_ci", C.c_int32), ("pad", C.c_int32)]
+                ("tiles_ci", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32)]
 
 
 _P = C.c_void_p

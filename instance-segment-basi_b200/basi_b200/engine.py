@@ -648,7 +648,7 @@ class Engine(object):
             blocks = 0
             for i, (wptr, w_io, w_oi, taps, cin, cout) in enumerate(self._tc_weights):
                 tco, tci = -(-cout // 32), -(-cin // 32)
-                entries[i] = _lib.PackEntry(wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, blocks, tco, tci, 0)
+                entries[i] = _lib.PackEntry(wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, blocks, tco, tci, 0, 0)
                 blocks += taps * tco * tci
             raw = np.frombuffer(bytes(entries), dtype=np.uint8).copy()
             self._pack_table = torch.from_numpy(raw).to(self.device)

@@ -598,7 +598,7 @@ struct PackEntry {
   int taps, cin, cout;
   int block_start;   // first block of this layer
   int tiles_co, tiles_ci;
-  int pad;
+  int pad0, pad1;
 };
 __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n_layers) {
   __shared__ float tile[32][33];
@@ -781,7 +781,7 @@ int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int t
 
 int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_blocks, void* stream) {
   BASI_CHECK_ARG(table_dev && n_layers > 0 && total_blocks > 0, "tc_pack_weights_multi: bad argument");
-  static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI (see include/basi_b200.h)");
+  static_assert(sizeof(PackEntry) == 56, "PackEntry layout is part of the C ABI (see include/basi_b200.h)");
   pack_weights_multi_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>((const PackEntry*)table_dev,
                                                                                    n_layers);
   BASI_CHECK_LAUNCH("tc_pack_weights_multi");
