@@ -188,15 +188,18 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const T* __restrict__ 
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   if (cg * VN >= C) return;
   const int c0 = cg * VN;
-  // y = x*scale + shift  with shift = beta - mean*scale (+ the residual BN's shift)
-  float scale[VN], shift[VN], rscale[VN];
+  // y = (x - mean)*scale + beta: the centred form keeps the B=1 / tiny-variance case exact (istd up to 316 would
+  // amplify the rounding of x*scale - mean*scale)
+  float mean[VN], scale[VN], beta[VN], rmean[VN], rscale[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
+    mean[i] = bnp[c0 + i];
     scale[i] = bnp[2 * C + c0 + i];
-    shift[i] = fmaf(-bnp[c0 + i], scale[i], bnp[3 * C + c0 + i]);
+    beta[i] = bnp[3 * C + c0 + i];
     if (RES_BN) {
+      rmean[i] = rbnp[c0 + i];
       rscale[i] = rbnp[2 * C + c0 + i];
-      shift[i] += fmaf(-rbnp[c0 + i], rscale[i], rbnp[3 * C + c0 + i]);
+      beta[i] += rbnp[3 * C + c0 + i];
     }
   }
   const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const T* __restrict__ 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int i = 2 * i2 + h;
-          float t = fmaf(v[u].get(i), scale[i], shift[i]);
-          if (HAS_RES) t = RES_BN ? fmaf(rv[u].get(i), rscale[i], t) : t + rv[u].get(i);
+          float t = fmaf(v[u].get(i) - mean[i], scale[i], beta[i]);
+          if (HAS_RES) t = RES_BN ? fmaf(rv[u].get(i) - rmean[i], rscale[i], t) : t + rv[u].get(i);
           o[h] = relu ? fmaxf(t, 0.f) : t;
         }
         v[u].set2(i2, o[0], o[1]);
@@ -256,7 +259,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
       mean[i] = bnp[c0 + i];
       const float sc = bnp[2 * C + c0 + i], be = bnp[3 * C + c0 + i];
       sgn[i] = sc;
-      thr[i] = fmaf(-mean[i], sc, be);   // same x*scale+shift expression as bn_apply -> identical ReLU mask
+      thr[i] = be;                        // same (x-mean)*scale+beta expression as bn_apply -> identical ReLU mask
     }
     const int64_t rstep = (int64_t)gridDim.x * blockDim.y;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += rstep * BUNR) {
@@ -281,7 +284,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
           const float xc = xr - mean[i];
           float dy = d[u].get(i);
           if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
-          else if (relu_from_x) dy = fmaf(xr, sgn[i], thr[i]) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xc, sgn[i], thr[i]) > 0.f ? dy : 0.f;
           fs[i] += dy;
           fq[i] = fmaf(dy, xc, fq[i]);      // istd is applied once at the end
         }
@@ -343,7 +346,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
     mean[i] = bnp[c0 + i];
     const float istd = bnp[C + c0 + i];
     A[i] = bnp[2 * C + c0 + i];
-    beta[i] = fmaf(-mean[i], A[i], bnp[3 * C + c0 + i]);   // shift of bn_apply's x*scale+shift (same ReLU mask)
+    beta[i] = bnp[3 * C + c0 + i];
     Bc[i] = A[i] * coef[c0 + i];
     Cc[i] = A[i] * istd * coef[C + c0 + i];
   }
@@ -377,7 +380,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
           const float xc = xr - mean[i];
           float dy = d[u].get(i);
           if (out) dy = o[u].get(i) > 0.f ? dy : 0.f;
-          else if (relu_from_x) dy = fmaf(xr, A[i], beta[i]) > 0.f ? dy : 0.f;
+          else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
           drs[h] = (dres && dres_acc) ? dr[u].get(i) + dy : dy;
           res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
         }
