@@ -27,13 +27,27 @@ GRAD_KEYS = ("conv1_1_3x3_s2_n/weights", "conv3_1_1x1_proj/weights", "conv4_7_3x
              "conv5_4_bn/conv5_4_bn/gamma", "class_attention_conv/biases")
 
 
+SEEDS = {"2AddClass_S64_F8": (13, 113), "4BorderClass_S64_F8": (13, 113)}   # (data seed, parameter seed)
+RELU_MARGIN = 3e-6   # every ReLU input of the float64 run stays this far from zero (float32 resolves ~1e-6 here); seeds searched over 1..39
+
+
+def inputs(name):
+    variant, nseg, S, F, B, classes, pw, cw = CASES[name]
+    dseed, pseed = SEEDS[name]
+    sd = SyntheticData(B, (S, S), 8, classes, nseg, seed=dseed)
+    img, clicks, lab, cls = sd.next_batch()
+    params = O.init_params(O.param_specs(variant, classes, nseg, F), pseed, trained_like=True)
+    return img, clicks, lab, cls, params
+
+
 def build(name):
     variant, nseg, S, F, B, classes, pw, cw = CASES[name]
-    sd = SyntheticData(B, (S, S), 8, classes, nseg, seed=7)
-    img, clicks, lab, cls = sd.next_batch()
-    params = O.init_params(O.param_specs(variant, classes, nseg, F), 11, trained_like=True)
+    img, clicks, lab, cls, params = inputs(name)
     data = np.stack([O.pack_input(img[b], clicks[b]) for b in range(B)])
+    O.TRACE_RELU_MARGIN = []
     r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float64)
+    margin, O.TRACE_RELU_MARGIN = min(O.TRACE_RELU_MARGIN), None
+    assert margin > RELU_MARGIN, "ReLU tie (min |pre-activation| %.2e): pick other seeds for %s" % (margin, name)
     r32 = O.train_step(params, data, lab, cls, variant, nseg, S // 8, pw, cw, 5e-3, torch.float32)
     out = dict(images=img, clicks=clicks, label_seg=lab, label_cls=cls, click_map=data[..., 3],
                loss=np.float64(r["loss"]), loss_segment=np.float64(r["loss_segment"]),

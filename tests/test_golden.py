@@ -37,7 +37,7 @@ def test_cuda_path_reproduces_golden(name):
     from basi_b200.engine import Engine
     variant, nseg, S, F, B, classes, pw, cw = G.CASES[name]
     g = _load(name)
-    params = O.init_params(O.param_specs(variant, classes, nseg, F), 11, trained_like=True)
+    params = G.inputs(name)[4]
     net = PSPNet({'data': Placeholder((None, S, S, 4))}, num_classes=classes, num_segment=nseg, is_training=True,
                  last_pool_size=S // 8, filter_number=F, variant=variant)
     eng = Engine(net, B, "f32", True, dict(kind="bce" if nseg == 1 else "softmax", pos_weight=pw, class_weight=cw))
