@@ -107,6 +107,50 @@ def cpu_oracle_rate(batch, steps, warmup=1):
     return batch * len(times) / sum(times), cores, sum(times) / len(times)
 
 
+def click_latency(torch, precision, n=30):
+    """cfg 1: single-click inference (RunnerGUI semantics, 4BorderClass head, S=320, B=1): host image + click in,
+    thresholded full-resolution mask + class out.  p50 / p90 wall-clock latency in ms."""
+    import numpy as np
+    from basi_b200.BAISRunnerOne import RunnerGUI
+    gui = RunnerGUI(None, last_pool_size=P, variant="4BorderClass", num_classes=21, num_segment=4,
+                    filter_number=FILTERS, precision=precision)
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(S, S, 3), dtype=np.uint8)
+    for _ in range(3):
+        gui.click(img, [160, 160])
+    ts = []
+    for i in range(n):
+        where = [int(rng.randint(0, S)), int(rng.randint(0, S))]
+        t0 = time.perf_counter()
+        gui.click(img, where)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return {"p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "n": n,
+            "h2d_bytes": S * S * 3 + 8, "d2h_bytes": S * S * 4 + 4,
+            "workload": "cfg1: RunnerGUI single click, 320x320, batch 1, 4BorderClass head, CUDA-graph forward"}
+
+
+def cpu_click_latency(n=3):
+    import numpy as np
+    import torch
+    from oracle import basi_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.to_torch(O.init_params(O.param_specs("4BorderClass", 21, 4, FILTERS), 0), torch.float32)
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(S, S, 3), dtype=np.uint8)
+    ts = []
+    with torch.no_grad():
+        for i in range(n + 1):
+            t0 = time.perf_counter()
+            data = O.pack_input(img, [160, 160])[None]
+            out = O.pspnet_forward(params, torch.from_numpy(data), "4BorderClass", 4, P)
+            O.predict_click(out["conv6_n_4"].numpy(), (S, S))
+            if i:
+                ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -282,6 +326,14 @@ def run_ours(args):
         rate, cores, sec = cpu_oracle_rate(2, 2, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle fwd+bwd+SGD at S=320, batch 2 x 2 steps, float32 torch-CPU (%.1f s/step)" % sec}
+    use_graph, tc_layers = bool(tr.use_cuda_graph), eng.tc_layers
+    del tr, eng
+    torch.cuda.empty_cache()
+    click = None
+    if world == 1 and not args.no_click:
+        click = click_latency(torch, args.precision)
+        if not args.no_cpu:
+            click["cpu_oracle_p50_ms"] = cpu_click_latency()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
@@ -289,12 +341,13 @@ def run_ours(args):
                                    "VOC-shape 320x320, batch 16 per GPU, F=32, SGD",
                        "global_batch": world * BATCH, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (~3 GB of activations) exceeds the 126 MB L2",
-                       "cuda_graph": bool(tr.use_cuda_graph), "tc_layers": eng.tc_layers,
+                       "cuda_graph": use_graph, "tc_layers": tc_layers,
                        "model_tflops": value * FLOP_PER_IMAGE / 1e12},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "loss": last_loss[0] if last_loss else None},
             "gpu_launches": int(launches),
             "roofline": roof, "kernel_breakdown_ms_per_step": breakdown, "cpu_baseline": cpu,
+            "click_to_mask": click,
             "clocks": sampler.summary() if sampler else None}
     print(json.dumps(line), flush=True)
 
@@ -309,6 +362,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-tc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    ap.add_argument("--no-click", action="store_true", help="skip the click-to-mask latency leg (cfg 1)")
     ap.add_argument("--detail", default=None, help="write per-call CUDA-event timings of one eager step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
