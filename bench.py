@@ -185,6 +185,9 @@ def kernel_profile(eng, torch, detail_path=None):
         torch.cuda.synchronize()
         for i, (name, fn, a, meta) in enumerate(lst):
             ms = evs[i].elapsed_time(evs[i + 1])
+            # fprop (:0) and dgrad (:1) plans run the same kernel, conv_tc_kernel; wgrad (:2) is wgrad_tc_kernel
+            name = {"basi_tc_conv_run:0": "conv_tc_kernel(fprop+dgrad)", "basi_tc_conv_run:1": "conv_tc_kernel(fprop+dgrad)",
+                    "basi_tc_conv_run:2": "wgrad_tc_kernel"}.get(name, name)
             d = agg.setdefault(name, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
             d["ms"] += ms
             d["n"] += 1

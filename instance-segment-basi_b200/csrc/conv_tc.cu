@@ -865,7 +865,11 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
     wp.Cin = cin; wp.Cout = cout;
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
-    int splits = (2 * sms + out_tiles - 1) / out_tiles;
+    // split-K over pixel tiles: one wave of CTAs.  Every split adds |dW| fp32 atomics, so more splits than needed to
+    // fill the SMs only adds L2 atomic traffic (measured: 2 waves -> 22 us, atomics-bound, on the conv4 1x1 layers)
+    const char* env_w = getenv("BASI_TC_WGRAD_WAVES");
+    const int waves = env_w ? atoi(env_w) : 1;
+    int splits = (waves * sms + out_tiles - 1) / out_tiles;
     if (splits > m_tiles) splits = m_tiles;
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (m_tiles + splits - 1) / splits;
