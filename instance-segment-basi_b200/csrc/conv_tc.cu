@@ -865,10 +865,15 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
     wp.Cin = cin; wp.Cout = cout;
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
-    // split-K over pixel tiles: one wave of CTAs.  Every split adds |dW| fp32 atomics, so more splits than needed to
-    // fill the SMs only adds L2 atomic traffic (measured: 2 waves -> 22 us, atomics-bound, on the conv4 1x1 layers)
+    // split-K over pixel tiles.  Every split adds |dW| fp32 atomics, so tiny gradients (conv4 1x1: 65 K elements)
+    // want a single wave of CTAs (measured 22.6 -> 16.7 us); long pixel loops want two waves for balance.
     const char* env_w = getenv("BASI_TC_WGRAD_WAVES");
-    const int waves = env_w ? atoi(env_w) : 1;
+    int waves = 1;
+    {
+      const int s1 = (sms + out_tiles - 1) / out_tiles;
+      if (m_tiles / (s1 > 0 ? s1 : 1) > 10) waves = 2;
+    }
+    if (env_w) waves = atoi(env_w);
     int splits = (waves * sms + out_tiles - 1) / out_tiles;
     if (splits > m_tiles) splits = m_tiles;
     if (splits < 1) splits = 1;
