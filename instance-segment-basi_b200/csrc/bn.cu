@@ -8,6 +8,8 @@
 // block; the last block to finish (ticket counter) turns the sums into the per-channel parameters, so no
 // separate finalize launch is needed.
 #include "common.cuh"
+#include "ptx.cuh"
+#include <stdlib.h>
 
 namespace basi {
 
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const T* __restrict__ 
   }
 }
 
-constexpr int BUNR = 2;   // rows in flight per thread in the backward kernels (occupancy provides the rest)
+constexpr int BUNR = 2;   // rows in flight per thread in the register-staged backward kernels
 
 // ---- backward reduce: dsums += (sum dy, sum dy*xhat); dy = dout * mask.
 // mask: out > 0 when out != NULL; else, when relu_from_x, (x-mean)*scale+beta > 0 (plain BN+ReLU: no need to read out)
@@ -393,6 +395,343 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ o
   }
 }
 
+
+// ==========================================================================================================
+// Shared-memory-staged streaming (the B200 way to keep an HBM-bound kernel fed): one elected thread issues 1-D bulk
+// copies (cp.async.bulk, completion on an mbarrier) of whole row slabs of every input tensor into an NST-deep ring,
+// all threads consume 128-bit fragments from shared memory.  Bytes in flight per SM = the ring (about 100 KB per
+// block, 2 blocks/SM), independent of the register budget -- the register-staged kernels above topped out at
+// 1-2.6 TB/s with 125 registers and 2 rows in flight (ncu, profiles/).
+// ==========================================================================================================
+constexpr int SNT_MAX = 4;
+struct StreamArgs {
+  const char* src[SNT_MAX];
+  long long ldb[SNT_MAX];   // row pitch in bytes
+  int row_bytes;            // C * sizeof(T) == blockDim.x * 16
+  long long R;
+  int rows_per_stage;       // multiple of blockDim.y
+  int nst;
+  int reverse;              // visit slabs from the end (L2 reuse after a forward-order pass)
+};
+
+template <typename T, int NT, typename Body>
+__device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
+  extern __shared__ __align__(128) uint8_t stream_smem[];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int SR = a.rows_per_stage;
+  const int stage_bytes = SR * a.row_bytes;   // per tensor
+  const uint32_t bar0 = smem_u32(stream_smem + (size_t)a.nst * NT * stage_bytes);
+  if (tid == 0) {
+    for (int i = 0; i < a.nst; ++i) mbar_init(bar0 + 8 * i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long n_slabs = (a.R + SR - 1) / SR;
+  const long long nk = n_slabs > blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto slab_of = [&](long long k) {
+    const long long sidx = blockIdx.x + k * gridDim.x;
+    return a.reverse ? n_slabs - 1 - sidx : sidx;
+  };
+  auto issue = [&](long long k) {
+    const long long row0 = slab_of(k) * SR;
+    const int rows = (int)min((long long)SR, a.R - row0);
+    const int st = (int)(k % a.nst);
+    const uint32_t bar = bar0 + 8 * st;
+    mbar_expect_tx(bar, (uint32_t)(rows * a.row_bytes * NT));
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const uint32_t dst = smem_u32(stream_smem + (size_t)(st * NT + t) * stage_bytes);
+      const char* g = a.src[t] + row0 * a.ldb[t];
+      if (a.ldb[t] == a.row_bytes) {
+        bulk_load_1d(dst, g, (uint32_t)(rows * a.row_bytes), bar);
+      } else {
+        for (int r = 0; r < rows; ++r) bulk_load_1d(dst + r * a.row_bytes, g + r * a.ldb[t], (uint32_t)a.row_bytes, bar);
+      }
+    }
+  };
+  if (tid == 0)
+    for (long long k = 0; k < nk && k < a.nst - 1; ++k) issue(k);
+  for (long long k = 0; k < nk; ++k) {
+    const int st = (int)(k % a.nst);
+    if (tid == 0 && k + a.nst - 1 < nk) issue(k + a.nst - 1);   // refills the stage consumed in iteration k-1
+    mbar_wait(bar0 + 8 * st, (uint32_t)((k / a.nst) & 1));
+    const long long row0 = slab_of(k) * SR;
+    const int rows = (int)min((long long)SR, a.R - row0);
+    for (int rr = threadIdx.y; rr < rows; rr += blockDim.y) {
+      Pack<T> f[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        f[t].load(reinterpret_cast<const T*>(stream_smem + (size_t)(st * NT + t) * stage_bytes + (size_t)rr * a.row_bytes +
+                                             threadIdx.x * 16));
+      body(row0 + rr, f);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, bool HAS_RES, bool RES_BN>
+__global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp,
+                                                                 const float* __restrict__ rbnp, int relu,
+                                                                 T* __restrict__ out, int ldo, int C) {
+  constexpr int VN = Pack<T>::N;
+  const int c0 = threadIdx.x * VN;
+  float mean[VN], scale[VN], beta[VN], rmean[VN], rscale[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    mean[i] = bnp[c0 + i];
+    scale[i] = bnp[2 * C + c0 + i];
+    beta[i] = bnp[3 * C + c0 + i];
+    if (RES_BN) {
+      rmean[i] = rbnp[c0 + i];
+      rscale[i] = rbnp[2 * C + c0 + i];
+      beta[i] += rbnp[3 * C + c0 + i];
+    }
+  }
+  stream_rows<T, HAS_RES ? 2 : 1>(a, [&](long long row, Pack<T>(&f)[HAS_RES ? 2 : 1]) {
+    Pack<T> o;
+#pragma unroll
+    for (int i2 = 0; i2 < VN / 2; ++i2) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * i2 + h;
+        float t = fmaf(f[0].get(i) - mean[i], scale[i], beta[i]);
+        if (HAS_RES) t = RES_BN ? fmaf(f[HAS_RES ? 1 : 0].get(i) - rmean[i], rscale[i], t) : t + f[HAS_RES ? 1 : 0].get(i);
+        v[h] = relu ? fmaxf(t, 0.f) : t;
+      }
+      o.set2(i2, v[0], v[1]);
+    }
+    o.store(out + row * ldo + c0);
+  });
+}
+
+// inputs: 0 = dout, 1 = x, 2 = out (HAS_OUT)
+template <typename T, bool HAS_OUT>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, int relu_from_x, int C,
+                            double* __restrict__ dsums, double count, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta, float* __restrict__ coef, unsigned int* counter) {
+  constexpr int VN = Pack<T>::N;
+  constexpr int NT = HAS_OUT ? 3 : 2;
+  const int c0 = threadIdx.x * VN;
+  float fs[VN], fq[VN], mean[VN], sgn[VN], thr[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    fs[i] = fq[i] = 0.f;
+    mean[i] = bnp[c0 + i];
+    sgn[i] = bnp[2 * C + c0 + i];
+    thr[i] = bnp[3 * C + c0 + i];
+  }
+  stream_rows<T, NT>(a, [&](long long, Pack<T>(&f)[NT]) {
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      const float xc = f[1].get(i) - mean[i];
+      float dy = f[0].get(i);
+      if (HAS_OUT) dy = f[NT - 1].get(i) > 0.f ? dy : 0.f;
+      else if (relu_from_x) dy = fmaf(xc, sgn[i], thr[i]) > 0.f ? dy : 0.f;
+      fs[i] += dy;
+      fq[i] = fmaf(dy, xc, fq[i]);
+    }
+  });
+  // the ring is idle now (stream_rows ends with __syncthreads): reduce_and_ticket reuses the dynamic shared memory
+  double s[VN], q[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    s[i] = (double)fs[i];
+    q[i] = (double)fq[i] * (double)bnp[C + c0 + i];
+  }
+  double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
+  const bool last = reduce_and_ticket<VN>(s, q, rep, rep + C, c0, true, counter);
+  if (last && coef) {
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+      double s1 = 0, s2 = 0;
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        s1 += __ldcg(dsums + (size_t)r * 2 * C + c);
+        s2 += __ldcg(dsums + (size_t)r * 2 * C + C + c);
+      }
+      dbeta[c] += (float)s1;
+      dgamma[c] += (float)s2;
+      coef[c] = (float)(s1 / count);
+      coef[C + c] = (float)(s2 / count);
+    }
+  }
+}
+
+// inputs: 0 = dout, 1 = x, then out (HAS_OUT), then the old dres (DRES_ACC)
+template <typename T, bool HAS_OUT, bool DRES_ACC>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, const float* __restrict__ coef,
+                           int relu_from_x, int C, T* __restrict__ dx, int lddx, T* __restrict__ dres, int lddr) {
+  constexpr int VN = Pack<T>::N;
+  constexpr int NT = 2 + (HAS_OUT ? 1 : 0) + (DRES_ACC ? 1 : 0);
+  const int c0 = threadIdx.x * VN;
+  float mean[VN], A[VN], Bc[VN], Cc[VN], beta[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    mean[i] = bnp[c0 + i];
+    const float istd = bnp[C + c0 + i];
+    A[i] = bnp[2 * C + c0 + i];
+    beta[i] = bnp[3 * C + c0 + i];
+    Bc[i] = A[i] * coef[c0 + i];
+    Cc[i] = A[i] * istd * coef[C + c0 + i];
+  }
+  stream_rows<T, NT>(a, [&](long long row, Pack<T>(&f)[NT]) {
+    Pack<T> o, dr;
+#pragma unroll
+    for (int i2 = 0; i2 < VN / 2; ++i2) {
+      float res[2], drs[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * i2 + h;
+        const float xc = f[1].get(i) - mean[i];
+        float dy = f[0].get(i);
+        if (HAS_OUT) dy = f[HAS_OUT ? 2 : 0].get(i) > 0.f ? dy : 0.f;
+        else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+        drs[h] = DRES_ACC ? f[NT - 1].get(i) + dy : dy;
+        res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
+      }
+      o.set2(i2, res[0], res[1]);
+      dr.set2(i2, drs[0], drs[1]);
+    }
+    if (dres) dr.store(dres + row * lddr + c0);
+    o.store(dx + row * lddx + c0);
+  });
+}
+
+// ---- host side of the streamed kernels
+struct StreamGeom {
+  bool ok;
+  dim3 grid, block;
+  size_t smem;
+  int rows_per_stage, nst;
+};
+static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem) {
+  StreamGeom g{};
+  const int row_bytes = C * es;
+  const int bx = row_bytes / 16;
+  g.ok = false;
+  if (row_bytes % 16 || bx < 1 || bx > 256 || (bx & (bx - 1))) return g;   // one 16-byte fragment per thread per row
+  const int by = 256 / bx;
+  const int SR = 2 * by;                                                   // 8 KB per tensor per stage
+  const int64_t n_slabs = (R + SR - 1) / SR;
+  if (n_slabs < 64) return g;                                              // tiny tensors: the direct kernels
+  int nst = (int)((96 * 1024) / ((size_t)nt * SR * row_bytes));
+  if (nst > 8) nst = 8;
+  if (nst < 2) return g;
+  g.rows_per_stage = SR;
+  g.nst = nst;
+  g.block = dim3(bx, by);
+  const int64_t cap = 2 * (int64_t)sm_count();
+  g.grid = dim3((unsigned)(n_slabs < cap ? n_slabs : cap));
+  g.smem = (size_t)nst * nt * SR * row_bytes + 8 * nst + 16;
+  if (g.smem < min_smem) g.smem = min_smem;
+  g.ok = true;
+  return g;
+}
+static void fill_stream_args(StreamArgs* a, const StreamGeom& g, int64_t R, int C, int es, int reverse) {
+  a->row_bytes = C * es;
+  a->R = R;
+  a->rows_per_stage = g.rows_per_stage;
+  a->nst = g.nst;
+  a->reverse = reverse;
+}
+template <typename K>
+static void allow_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static bool stream_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("BASI_BN_DIRECT") ? 1 : 0;
+  return v == 1;
+}
+
+template <typename T>
+static bool launch_apply_stream(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* rbnp,
+                                int relu, const basi_tensor* out, cudaStream_t st) {
+  if (stream_disabled()) return false;
+  const int es = sizeof(T);
+  const int nt = res ? 2 : 1;
+  const int64_t R = pixels(x);
+  StreamGeom g = stream_geom(R, x->c, es, nt, 0);
+  if (!g.ok) return false;
+  StreamArgs a{};
+  fill_stream_args(&a, g, R, x->c, es, 0);
+  a.src[0] = (const char*)x->ptr; a.ldb[0] = (long long)x->ld * es;
+  if (res) { a.src[1] = (const char*)res->ptr; a.ldb[1] = (long long)res->ld * es; }
+  if (!res) {
+    allow_smem(bn_apply_stream_kernel<T, false, false>, g.smem);
+    bn_apply_stream_kernel<T, false, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+  } else if (!rbnp) {
+    allow_smem(bn_apply_stream_kernel<T, true, false>, g.smem);
+    bn_apply_stream_kernel<T, true, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+  } else {
+    allow_smem(bn_apply_stream_kernel<T, true, true>, g.smem);
+    bn_apply_stream_kernel<T, true, true><<<g.grid, g.block, g.smem, st>>>(a, bnp, rbnp, relu, (T*)out->ptr, out->ld, x->c);
+  }
+  return true;
+}
+
+template <typename T>
+static bool launch_bwd_reduce_stream(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x,
+                                     const float* bnp, int relu_from_x, double* dsums, double count, float* dgamma,
+                                     float* dbeta, float* coef, uint32_t* counter, cudaStream_t st) {
+  if (stream_disabled()) return false;
+  const int es = sizeof(T);
+  const int nt = out ? 3 : 2;
+  const int64_t R = pixels(x);
+  StreamGeom g = stream_geom(R, x->c, es, nt, (size_t)256 * 2 * Pack<T>::N * sizeof(double));
+  if (!g.ok) return false;
+  StreamArgs a{};
+  fill_stream_args(&a, g, R, x->c, es, 0);
+  a.src[0] = (const char*)dout->ptr; a.ldb[0] = (long long)dout->ld * es;
+  a.src[1] = (const char*)x->ptr; a.ldb[1] = (long long)x->ld * es;
+  if (out) { a.src[2] = (const char*)out->ptr; a.ldb[2] = (long long)out->ld * es; }
+  if (out) {
+    allow_smem(bn_bwd_reduce_stream_kernel<T, true>, g.smem);
+    bn_bwd_reduce_stream_kernel<T, true><<<g.grid, g.block, g.smem, st>>>(a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+  } else {
+    allow_smem(bn_bwd_reduce_stream_kernel<T, false>, g.smem);
+    bn_bwd_reduce_stream_kernel<T, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+  }
+  return true;
+}
+
+template <typename T>
+static bool launch_bwd_apply_stream(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x,
+                                    const float* bnp, const float* coef, int relu_from_x, const basi_tensor* dx,
+                                    const basi_tensor* dres, int dres_acc, cudaStream_t st) {
+  if (stream_disabled()) return false;
+  const int es = sizeof(T);
+  const bool acc = dres && dres_acc;
+  const int nt = 2 + (out ? 1 : 0) + (acc ? 1 : 0);
+  const int64_t R = pixels(x);
+  StreamGeom g = stream_geom(R, x->c, es, nt, 0);
+  if (!g.ok) return false;
+  StreamArgs a{};
+  fill_stream_args(&a, g, R, x->c, es, 1);
+  int k = 0;
+  a.src[k] = (const char*)dout->ptr; a.ldb[k++] = (long long)dout->ld * es;
+  a.src[k] = (const char*)x->ptr; a.ldb[k++] = (long long)x->ld * es;
+  if (out) { a.src[k] = (const char*)out->ptr; a.ldb[k++] = (long long)out->ld * es; }
+  if (acc) { a.src[k] = (const char*)dres->ptr; a.ldb[k++] = (long long)dres->ld * es; }
+  T* dxp = (T*)dx->ptr;
+  T* drp = dres ? (T*)dres->ptr : nullptr;
+  const int lddr = dres ? dres->ld : 0;
+#define BASI_LAUNCH_BWD_APPLY(HO, DA)                                                                               \
+  do {                                                                                                              \
+    allow_smem(bn_bwd_apply_stream_kernel<T, HO, DA>, g.smem);                                                      \
+    bn_bwd_apply_stream_kernel<T, HO, DA><<<g.grid, g.block, g.smem, st>>>(a, bnp, coef, relu_from_x, x->c, dxp,    \
+                                                                            dx->ld, drp, lddr);                     \
+  } while (0)
+  if (out && acc) BASI_LAUNCH_BWD_APPLY(true, true);
+  else if (out) BASI_LAUNCH_BWD_APPLY(true, false);
+  else if (acc) BASI_LAUNCH_BWD_APPLY(false, true);
+  else BASI_LAUNCH_BWD_APPLY(false, false);
+#undef BASI_LAUNCH_BWD_APPLY
+  return true;
+}
+
 }  // namespace basi
 
 using namespace basi;
@@ -439,6 +778,10 @@ int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res
   int64_t R = pixels(x);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_T(x->dtype, {
+    if (launch_apply_stream<T>(x, bnp, res, res_bnp, relu, out, st)) {
+      BASI_CHECK_LAUNCH("bn_apply(stream)");
+      return BASI_OK;
+    }
     RowGeom g = row_geom(R, x->c, Vec<T>::N, UNR, 16, 0);
     const T* rp = res ? (const T*)res->ptr : nullptr;
     const int ldr = res ? res->ld : 0;
@@ -466,6 +809,11 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
   BASI_CHECK_ARG(!coef || (dgamma && dbeta && count > 0), "bn_bwd_reduce: fused finalize needs dgamma, dbeta, count");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
+    if (launch_bwd_reduce_stream<T>(dout, out, x, bnp, relu_from_x, dsums, count, dgamma, dbeta, coef, counter,
+                                    (cudaStream_t)stream)) {
+      BASI_CHECK_LAUNCH("bn_bwd_reduce(stream)");
+      return BASI_OK;
+    }
     RowGeom g = row_geom(R, x->c, Vec<T>::N, 4 * BUNR, 12, 2 * Vec<T>::N * sizeof(double));
     bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
@@ -493,6 +841,11 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
   BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_apply: bad dres");
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
+    if (launch_bwd_apply_stream<T>(dout, out, x, bnp, coef, relu_from_x, dx, dres, dres_accumulate,
+                                   (cudaStream_t)stream)) {
+      BASI_CHECK_LAUNCH("bn_bwd_apply(stream)");
+      return BASI_OK;
+    }
     RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * BUNR, 12, 0);
     bn_bwd_apply_kernel<T><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,

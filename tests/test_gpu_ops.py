@@ -137,7 +137,7 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
 # ------------------------------------------------------------------ batch norm (+relu, +residual) forward/backward
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("mode", ["plain", "relu", "res", "res_bn"])
-@pytest.mark.parametrize("shape", [(2, 16, 16, 32), (1, 1, 1, 16), (3, 5, 7, 8), (2, 8, 8, 2048)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32), (1, 1, 1, 16), (3, 5, 7, 8), (2, 8, 8, 2048), (4, 40, 40, 128), (3, 37, 41, 512)])
 def test_batch_norm_forward_backward(dtype, mode, shape):
     from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
     B, H, W, Cc = shape
