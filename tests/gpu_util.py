@@ -48,3 +48,10 @@ def bf16_round(x_np):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def rel_l2(a, b):
+    """norm-wise relative error: one ReLU-mask tie (|pre-activation| below float32 resolution) may flip a single
+    element of a gradient by its full value; that must not fail a 2-million-element comparison"""
+    a, b = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
