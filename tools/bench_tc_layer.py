@@ -21,6 +21,8 @@ SHAPES = [  # name, k, dil, cin, cout, H, B
     ("conv1_3", 3, 1, 32, 64, 160, 16),
     ("conv2_3x3", 3, 1, 32, 32, 80, 16),
 ]
+if len(sys.argv) > 1:
+    SHAPES = [s_ for s_ in SHAPES if s_[0] in sys.argv[1:]]
 lib = _lib.load()
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
