@@ -41,6 +41,30 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// cluster-of-2 variants: the weight tile is loaded half by each CTA of the pair and multicast to both
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -150,10 +174,13 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
+  // CL == 2: the two CTAs of a cluster work on adjacent pixel tiles of the same channel tile in lock step; each
+  // loads its own activation box and HALF of the weight box, multicast to both (halves the weight-tile TMA requests
+  // per SM -- the main loop is bound by the TMA request rate, ~0.35 us per k-step, not by the tensor pipe).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int STAGE = SmemLayout<BN>::STAGE;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -179,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, CL);   // a stage is free when the MMA warps of every CTA writing into it are done
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
@@ -195,10 +222,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int cid = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ncl = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_groups = (p.m_tiles + CL - 1) / CL;
+  const int total_tiles = m_groups * p.n_tiles;   // loop space; pixel tile = group * CL + crank (may be a phantom)
   const int ksteps = p.taps * p.k_chunks;
 
   if (warp == 0) {
@@ -206,8 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      for (int t = cid; t < total_tiles; t += ncl) {
+        const int nt = t % p.n_tiles, mt = (t / p.n_tiles) * CL + crank;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -219,7 +251,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, STAGE);
             tma_load_4d(sa, &mapA, fb, kc * KC, sw, sh, n0);
-            tma_load_3d(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+            if (CL == 2)
+              tma_load_3d_mc(sa + A_BYTES + crank * (BN / 2) * 128, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap,
+                             (uint16_t)3);
+            else
+              tma_load_3d(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -235,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -252,7 +288,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
           }
-          umma_commit(empty0 + 8 * stage);   // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair: each has written half of the other's weight tile)
+          if (CL == 2) umma_commit_mc(empty0 + 8 * stage, (uint16_t)3);
+          else umma_commit(empty0 + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -271,10 +309,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t so_base = smem_u32(stage_out);
     const bool do_stats = p.bn_sums != nullptr;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = cid; t < total_tiles; t += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int nt = t % p.n_tiles, mt = (t / p.n_tiles) * CL + crank;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
       const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
@@ -357,6 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -681,6 +720,7 @@ using namespace basi::tc;
 struct basi_tc_conv {
   int kind;
   int bn;
+  int cluster;
   CUtensorMap mapA, mapB, mapD;
   ConvParams cp;
   WgradParams wp;
@@ -713,10 +753,27 @@ template <int BN>
 static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<pl->grid, NTHREADS_CONV, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  if (pl->cluster == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl->grid);
+    cfg.blockDim = dim3(NTHREADS_CONV);
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  } else {
+    conv_tc_kernel<BN, 1><<<pl->grid, NTHREADS_CONV, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  }
   return BASI_OK;
 }
 template <int BN>
@@ -779,8 +836,10 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
     if (getenv("BASI_TC_BN256") && ndim % 256 == 0) bn = 256;   // experiment switch (measured: not faster)
     pl->bn = bn;
+    // pairs of CTAs share the weight tile (cluster of 2) whenever there are at least two pixel tiles
+    pl->cluster = (m_tiles >= 2 && !getenv("BASI_TC_NO_CLUSTER")) ? 2 : 1;
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
-    if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, bn);
+    if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, pl->cluster == 2 ? bn / 2 : bn);
     if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
     if (rc != BASI_OK) {
       delete pl;
@@ -809,8 +868,15 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     cp.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
     pl->dst = (bf16*)dstt->ptr;
-    const int total = cp.m_tiles * cp.n_tiles;
-    pl->grid = total < sms ? total : sms;
+    if (pl->cluster == 2) {
+      const int total = ((cp.m_tiles + 1) / 2) * cp.n_tiles;     // pairs
+      const int pairs = total < sms / 2 ? total : sms / 2;
+      pl->grid = 2 * pairs;
+    } else {
+      const int total = cp.m_tiles * cp.n_tiles;
+      pl->grid = total < sms ? total : sms;
+    }
+    if (getenv("BASI_TC_DEBUG_EMPTY")) cp.m_tiles = 0;   // timing experiment: prologue + teardown only
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
     const int cin = a->c, cout = b->c;
