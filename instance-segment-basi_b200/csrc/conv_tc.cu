@@ -834,10 +834,19 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     const basi_tensor* dstt = b;
     const int ndim = dstt->c, kdim = src->c;
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
-    if (getenv("BASI_TC_BN256") && ndim % 256 == 0) bn = 256;   // experiment switch (measured: not faster)
+    // N = 256 tiles: the N = 128 main loop is bound by shared-memory operand reads (4 KB A + 4 KB B per 64-cycle
+    // MMA = 128 B/clk); N = 256 needs 96 B/clk.  Measured on conv5_4 dgrad: 975 -> 1404 TFLOP/s.  Per k-step a 256
+    // tile costs ~1.4x a 128 tile and there are half as many tiles: pick the cheaper wave count; small-K layers
+    // (overhead-bound) stay at 128.
+    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= 8 && !getenv("BASI_TC_NO_BN256")) {
+      const long t128 = ((long)m_tiles * (ndim / 128) + sms - 1) / sms * 10;
+      const long t256 = ((long)m_tiles * (ndim / 256) + sms - 1) / sms * 14;
+      if (t256 < t128) bn = 256;
+    }
     pl->bn = bn;
     // pairs of CTAs share the weight tile (cluster of 2) whenever there are at least two pixel tiles
-    pl->cluster = (m_tiles >= 2 && !getenv("BASI_TC_NO_CLUSTER")) ? 2 : 1;
+    // (measured: no gain -- the main loop is not bound by weight-tile TMA requests -- so it is opt-in)
+    pl->cluster = (m_tiles >= 2 && getenv("BASI_TC_CLUSTER")) ? 2 : 1;
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, pl->cluster == 2 ? bn / 2 : bn);
     if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
