@@ -133,6 +133,25 @@ int basi_gate_mul_fwd(const basi_tensor* feat, const float* logits, int nseg, in
 int basi_gate_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const float* logits, int nseg, int att,
                       const basi_tensor* dfeat, int dfeat_accumulate, float* dlogits, void* stream);
 
+/* ---- A12-A14: variant-B gating ops (click-gated features and the attention cascade) ----
+ * A12  tf.multiply(feature, mask) with the mask broadcast over channels: back/7OLD/BAISNet.py:535,
+ *      back/90AttentionSingle2/BAISNet.py:748,773-776; cascade gate back/8AttentionU/BAISNet.py:586-591.
+ *      mask: float32 [n,h,w,nch], channel ch is used.  dmask may be NULL (the click map needs no gradient). */
+int basi_mask_mul_fwd(const basi_tensor* feat, const float* mask, int nch, int ch, const basi_tensor* out,
+                      void* stream);
+int basi_mask_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const float* mask, int nch, int ch,
+                      const basi_tensor* dfeat, int dfeat_accumulate, float* dmask, void* stream);
+/* A13  softmax over C logits, channel `sel`, hard gate tf.where(p > thr, p, 0)
+ *      (back/90AttentionSingle2/BAISNet.py:743-746, thr = 0.9; thr < 0 gives the plain softmax channel of
+ *      back/8AttentionU/BAISNet.py:586).  gate: float32 [rows].  bwd: dlogits (+)= dgate * d gate / d logits. */
+int basi_softmax_gate_fwd(const float* logits, int64_t rows, int C, int sel, float thr, float* gate, void* stream);
+int basi_softmax_gate_bwd(const float* logits, const float* dgate, int64_t rows, int C, int sel, float thr,
+                          float* dlogits, int accumulate, void* stream);
+/* A14  tf.image.resize_nearest_neighbor (TF1 default): src = min(floor(dst * in / out), in - 1)
+ *      (back/90AttentionSingle2/BAISNet.py:750,752,773; labels in BAISRunnerTrain.py:92-93). */
+int basi_resize_nearest_fwd(const basi_tensor* x, const basi_tensor* y, void* stream);
+int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream);
+
 /* ---- A11: class_attention_conv (5x5 s5 on a 5x5 map) and Network.fc (:175-189) as skinny GEMMs ----
  * y[m][n] = act(sum_k a[m][k] w[k][n] + bias[n]), m <= 64. a may be f32/bf16 (dtype_a), y float32. */
 int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,

@@ -61,6 +61,12 @@ SIGNATURES = {
     "basi_bilinear_ac_bwd": [_TP, _TP, _i, _P],
     "basi_gate_mul_fwd": [_TP, _P, _i, _i, _TP, _P],
     "basi_gate_mul_bwd": [_TP, _TP, _P, _i, _i, _TP, _i, _P, _P],
+    "basi_mask_mul_fwd": [_TP, _P, _i, _i, _TP, _P],
+    "basi_mask_mul_bwd": [_TP, _TP, _P, _i, _i, _TP, _i, _P, _P],
+    "basi_softmax_gate_fwd": [_P, _i64, _i, _i, _f, _P, _P],
+    "basi_softmax_gate_bwd": [_P, _P, _i64, _i, _i, _f, _P, _i, _P],
+    "basi_resize_nearest_fwd": [_TP, _TP, _P],
+    "basi_resize_nearest_bwd": [_TP, _TP, _i, _P],
     "basi_skinny_fwd": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _i, _P],
     "basi_skinny_dgrad": [_P, _P, _P, _i, _i64, _i, _i, _i, _i, _P],
     "basi_skinny_wgrad": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _P],

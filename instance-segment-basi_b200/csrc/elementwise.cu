@@ -307,7 +307,7 @@ __global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH
 // ------------------------------------------------------------------------------------------
 // Attention gating
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool RELU>
 __global__ void gate_mul_fwd_kernel(const T* __restrict__ feat, int ldf, const float* __restrict__ logits, int nseg,
                                     int att, T* __restrict__ out, int ldo, int64_t R, int C) {
   constexpr int VN = Vec<T>::N;
@@ -319,13 +319,13 @@ __global__ void gate_mul_fwd_kernel(const T* __restrict__ feat, int ldf, const f
     const float g = __ldg(logits + r * nseg + att);
     Vec<T> v = Vec<T>::load(feat + r * ldf + c0);
 #pragma unroll
-    for (int j = 0; j < VN; ++j) v.v[j] = fmaxf(v.v[j], 0.f) * g;
+    for (int j = 0; j < VN; ++j) v.v[j] = (RELU ? fmaxf(v.v[j], 0.f) : v.v[j]) * g;
     v.store(out + r * ldo + c0);
   }
 }
 
 // one warp per pixel
-template <typename T>
+template <typename T, bool RELU>
 __global__ void gate_mul_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ feat, int ldf,
                                     const float* __restrict__ logits, int nseg, int att, T* __restrict__ dfeat,
                                     int lddf, int acc, float* __restrict__ dlogits, int64_t R, int C) {
@@ -344,15 +344,92 @@ __global__ void gate_mul_bwd_kernel(const T* __restrict__ dout, int ldd, const T
       if (acc) o = Vec<T>::load(dfeat + r * lddf + cg * VN);
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
-        float fr = fmaxf(f.v[j], 0.f);
+        float fr = RELU ? fmaxf(f.v[j], 0.f) : f.v[j];
         s = fmaf(d.v[j], fr, s);
-        float gf = f.v[j] > 0.f ? d.v[j] * g : 0.f;
+        float gf = (!RELU || f.v[j] > 0.f) ? d.v[j] * g : 0.f;
         o.v[j] = acc ? o.v[j] + gf : gf;
       }
       o.store(dfeat + r * lddf + cg * VN);
     }
     s = warp_sum(s);
-    if (lane == 0) dlogits[r * nseg + att] += s;
+    if (lane == 0 && dlogits) dlogits[r * nseg + att] += s;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Variant-B gating: softmax attention gate with a hard threshold, nearest-neighbour resize
+// ------------------------------------------------------------------------------------------
+// gate[r] = p > thr ? p : 0 with p = softmax(logits[r, :])[sel]        (90AttentionSingle2/BAISNet.py:743-746)
+__global__ void softmax_gate_fwd_kernel(const float* __restrict__ logits, int64_t rows, int C, int sel, float thr,
+                                        float* __restrict__ gate) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = logits + r * C;
+    float mx = x[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
+    const float p = expf(x[sel] - mx) / se;
+    gate[r] = p > thr ? p : 0.f;
+  }
+}
+// dlogits[r, j] += dgate[r] * p_sel * (delta(j, sel) - p_j) where the gate passed, 0 elsewhere (tf.where adjoint)
+__global__ void softmax_gate_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dgate, int64_t rows,
+                                        int C, int sel, float thr, float* __restrict__ dlogits, int accumulate) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = logits + r * C;
+    float mx = x[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
+    const float inv = 1.f / se;
+    const float ps = expf(x[sel] - mx) * inv;
+    const float g = ps > thr ? dgate[r] * ps : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float pj = expf(x[c] - mx) * inv;
+      const float v = g * ((c == sel ? 1.f : 0.f) - pj);
+      dlogits[r * C + c] = accumulate ? dlogits[r * C + c] + v : v;
+    }
+  }
+}
+
+__device__ __forceinline__ int nn_src(int o, float scale, int in_size) { return min((int)floorf((float)o * scale), in_size - 1); }
+
+// TF1 resize_nearest_neighbor (align_corners=False): src = min(floor(dst * in/out), in - 1)
+template <typename T>
+__global__ void resize_nearest_fwd_kernel(const T* __restrict__ x, int ldx, int IH, int IW, int C, T* __restrict__ y,
+                                          int ldy, int OH, int OW, float sh, float sw, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t p = i / C;
+    const int ow = (int)(p % OW);
+    int64_t t = p / OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    const int ih = nn_src(oh, sh, IH), iw = nn_src(ow, sw, IW);
+    y[p * ldy + c] = x[(((int64_t)n * IH + ih) * IW + iw) * ldx + c];
+  }
+}
+// adjoint in gather form: every input pixel sums the output pixels that map onto it
+template <typename T>
+__global__ void resize_nearest_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, T* __restrict__ dx, int ldx,
+                                          int IH, int IW, int C, float sh, float sw, int acc, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t p = i / C;
+    const int iw = (int)(p % IW);
+    int64_t t = p / IW;
+    const int ih = (int)(t % IH);
+    const int n = (int)(t / IH);
+    const int oh_lo = max(0, (int)floorf((float)ih / sh) - 1), oh_hi = min(OH - 1, (int)ceilf((float)(ih + 1) / sh) + 1);
+    const int ow_lo = max(0, (int)floorf((float)iw / sw) - 1), ow_hi = min(OW - 1, (int)ceilf((float)(iw + 1) / sw) + 1);
+    float a = acc ? to_f32(dx[p * ldx + c]) : 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      if (nn_src(oh, sh, IH) != ih) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow)
+        if (nn_src(ow, sw, IW) == iw) a += to_f32(dy[(((int64_t)n * OH + oh) * OW + ow) * ldy + c]);
+    }
+    dx[p * ldx + c] = from_f32<T>(a);
   }
 }
 
@@ -698,7 +775,7 @@ int basi_gate_mul_fwd(const basi_tensor* feat, const float* logits, int nseg, in
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
     int64_t total = R * (feat->c / Vec<T>::N);
-    gate_mul_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    gate_mul_fwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)out->ptr, out->ld, R, feat->c);
   })
   BASI_CHECK_LAUNCH("gate_mul_fwd");
@@ -713,11 +790,86 @@ int basi_gate_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const fl
                  "gate_mul bwd: bad argument");
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
-    gate_mul_bwd_kernel<T><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    gate_mul_bwd_kernel<T, true><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)dfeat->ptr, dfeat->ld,
         dfeat_accumulate, dlogits, R, feat->c);
   })
   BASI_CHECK_LAUNCH("gate_mul_bwd");
+  return BASI_OK;
+}
+
+/* ---- A12: click / attention map times features, broadcast over channels (no ReLU) ---- */
+int basi_mask_mul_fwd(const basi_tensor* feat, const float* mask, int nch, int ch, const basi_tensor* out,
+                      void* stream) {
+  BASI_CHECK_ARG(feat && mask && out && vec_ok(feat) && vec_ok(out) && same_shape(feat, out) &&
+                     feat->dtype == out->dtype && ch >= 0 && ch < nch,
+                 "mask_mul fwd: bad argument");
+  int64_t R = pixels(feat);
+  DISPATCH_T(feat->dtype, {
+    int64_t total = R * (feat->c / Vec<T>::N);
+    gate_mul_fwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)out->ptr, out->ld, R, feat->c);
+  })
+  BASI_CHECK_LAUNCH("mask_mul_fwd");
+  return BASI_OK;
+}
+
+int basi_mask_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const float* mask, int nch, int ch,
+                      const basi_tensor* dfeat, int dfeat_accumulate, float* dmask, void* stream) {
+  BASI_CHECK_ARG(dout && feat && mask && dfeat && vec_ok(dout) && vec_ok(feat) && vec_ok(dfeat) &&
+                     same_shape(dout, feat) && same_shape(dfeat, feat) && dout->dtype == feat->dtype &&
+                     dfeat->dtype == feat->dtype && ch >= 0 && ch < nch,
+                 "mask_mul bwd: bad argument");
+  int64_t R = pixels(feat);
+  DISPATCH_T(feat->dtype, {
+    gate_mul_bwd_kernel<T, false><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)dfeat->ptr, dfeat->ld,
+        dfeat_accumulate, dmask, R, feat->c);
+  })
+  BASI_CHECK_LAUNCH("mask_mul_bwd");
+  return BASI_OK;
+}
+
+int basi_softmax_gate_fwd(const float* logits, int64_t rows, int C, int sel, float thr, float* gate, void* stream) {
+  BASI_CHECK_ARG(logits && gate && rows > 0 && C > 0 && sel >= 0 && sel < C, "softmax_gate fwd: bad argument");
+  softmax_gate_fwd_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, rows, C, sel, thr, gate);
+  BASI_CHECK_LAUNCH("softmax_gate_fwd");
+  return BASI_OK;
+}
+
+int basi_softmax_gate_bwd(const float* logits, const float* dgate, int64_t rows, int C, int sel, float thr,
+                          float* dlogits, int accumulate, void* stream) {
+  BASI_CHECK_ARG(logits && dgate && dlogits && rows > 0 && C > 0 && sel >= 0 && sel < C,
+                 "softmax_gate bwd: bad argument");
+  softmax_gate_bwd_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, dgate, rows, C, sel, thr,
+                                                                               dlogits, accumulate);
+  BASI_CHECK_LAUNCH("softmax_gate_bwd");
+  return BASI_OK;
+}
+
+int basi_resize_nearest_fwd(const basi_tensor* x, const basi_tensor* y, void* stream) {
+  BASI_CHECK_ARG(x && y && x->ptr && y->ptr && x->dtype == y->dtype && x->c == y->c && x->n == y->n,
+                 "resize_nearest fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    int64_t total = pixels(y) * y->c;
+    resize_nearest_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, (float)x->h / (float)y->h,
+        (float)x->w / (float)y->w, total);
+  })
+  BASI_CHECK_LAUNCH("resize_nearest_fwd");
+  return BASI_OK;
+}
+
+int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && dx && dy->ptr && dx->ptr && dx->dtype == dy->dtype && dx->c == dy->c && dx->n == dy->n,
+                 "resize_nearest bwd: bad tensors");
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * dx->c;
+    resize_nearest_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, (float)dx->h / (float)dy->h,
+        (float)dx->w / (float)dy->w, accumulate, total);
+  })
+  BASI_CHECK_LAUNCH("resize_nearest_bwd");
   return BASI_OK;
 }
 

@@ -169,6 +169,19 @@ def resize_nearest(x, size):
     return x[:, :, yi][:, :, :, xi]
 
 
+def mask_multiply(feature_nchw, mask_n1hw):
+    """tf.multiply(feature, mask): the click / attention map broadcast over channels
+    (back/7OLD/BAISNet.py:535, back/90AttentionSingle2/BAISNet.py:748,773-776)."""
+    return feature_nchw * mask_n1hw
+
+
+def attention_gate(logits_nchw, sel=1, thr=0.9):
+    """softmax over channels -> channel `sel` -> tf.where(p > thr, p, 0)
+    (back/90AttentionSingle2/BAISNet.py:743-746; thr < 0: plain softmax channel, back/8AttentionU/BAISNet.py:586)."""
+    p = torch.softmax(logits_nchw, dim=1)[:, sel:sel + 1]
+    return torch.where(p > thr, p, torch.zeros_like(p))
+
+
 def weighted_cross_entropy_with_logits(targets, logits, pos_weight):
     z, x, q = targets, logits, pos_weight
     return (1 - z) * x + (1 + (q - 1) * z) * (torch.log1p(torch.exp(-x.abs())) + F.relu(-x))

@@ -484,3 +484,76 @@ def test_batch_norm_junction_backward_on_concat_slices(dtype):
     assert rel_err(host(dgamma), g1.grad.numpy()) < btol
     assert rel_err(host(dra), nhwc(rt.grad)) < btol
     assert rel_err(host(dxa), nhwc(xt.grad)) < btol
+
+
+# ------------------------------------------------------------------ variant-B gating ops
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_mask_multiply(dtype):
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    B, P, Cc = 2, 20, 64
+    rng = np.random.RandomState(21)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    feat, mask, dout = rnd(_u(rng, B, P, P, Cc)), rng.rand(B, P, P, 1).astype(np.float32), rnd(_u(rng, B, P, P, Cc))
+    ft = nchw(feat).double().requires_grad_(True)
+    mt = nchw(mask).double().requires_grad_(True)
+    y = O.mask_multiply(ft, mt)
+    (y * nchw(dout).double()).sum().backward()
+    fa, ya, md = act(feat, tdt), empty_act((B, P, P, Cc), tdt), dev(mask)
+    call("basi_mask_mul_fwd", fa.ref, md.data_ptr(), 1, 0, ya.ref)
+    assert rel_err(host(ya), nhwc(y.detach())) < (1e-6 if dtype == "f32" else 1e-2)
+    dfa = empty_act((B, P, P, Cc), tdt, fill=2.0)
+    dm = torch.zeros((B, P, P, 1), device="cuda:0")
+    douta = act(dout, tdt)
+    call("basi_mask_mul_bwd", douta.ref, fa.ref, md.data_ptr(), 1, 0, dfa.ref, 1, dm.data_ptr())
+    assert rel_err(host(dfa) - 2.0, nhwc(ft.grad)) < (1e-5 if dtype == "f32" else 2e-2)
+    assert rel_err(host(dm), nhwc(mt.grad)) < 1e-4
+    call("basi_mask_mul_bwd", douta.ref, fa.ref, md.data_ptr(), 1, 0, dfa.ref, 0, None)     # click map: no gradient
+    assert rel_err(host(dfa), nhwc(ft.grad)) < (1e-5 if dtype == "f32" else 2e-2)
+
+
+@pytest.mark.parametrize("Cc,sel,thr", [(2, 1, 0.9), (2, 1, 0.5), (4, 1, -1.0)])
+def test_softmax_attention_gate(Cc, sel, thr):
+    from gpu_util import call, dev, host, rel_err
+    rng = np.random.RandomState(22)
+    B, P = 2, 24
+    logits = (_u(rng, B, P, P, Cc) * 5).astype(np.float32)
+    dgate = _u(rng, B, P, P, 1)
+    lt = nchw(logits).double().requires_grad_(True)
+    g = O.attention_gate(lt, sel, thr)
+    (g * nchw(dgate).double()).sum().backward()
+    ld, dgd = dev(logits), dev(dgate)
+    gate = torch.zeros(B * P * P, device="cuda:0")
+    rows = B * P * P
+    call("basi_softmax_gate_fwd", ld.data_ptr(), C.c_int64(rows), Cc, sel, C.c_float(thr), gate.data_ptr())
+    ref = nhwc(g.detach()).reshape(-1)
+    got = host(gate)
+    assert np.array_equal(got > 0, ref > 0)                       # the hard gate selects the same pixels
+    assert rel_err(got, ref) < 1e-5
+    dl = torch.full((rows, Cc), 0.25, device="cuda:0")
+    call("basi_softmax_gate_bwd", ld.data_ptr(), dgd.data_ptr(), C.c_int64(rows), Cc, sel, C.c_float(thr),
+         dl.data_ptr(), 1)
+    assert rel_err(host(dl) - 0.25, nhwc(lt.grad).reshape(rows, Cc)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("ih,oh,Cc", [(40, 80, 1), (45, 90, 16), (40, 17, 8), (320, 40, 1), (7, 20, 3)])
+def test_resize_nearest_neighbor(dtype, ih, oh, Cc):
+    from gpu_util import act, bf16_round, call, empty_act, host, rel_err
+    B = 2
+    rng = np.random.RandomState(23)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    x = rnd(_u(rng, B, ih, ih + 1, Cc))
+    ow = oh + 3
+    ref = O.resize_nearest(nchw(x), (oh, ow))
+    xa, ya = act(x, tdt), empty_act((B, oh, ow, Cc), tdt)
+    call("basi_resize_nearest_fwd", xa.ref, ya.ref)
+    assert np.array_equal(host(ya), nhwc(ref))                    # pure gather: bit exact
+    # adjoint: <resize(x), dy> == <x, resize^T(dy)>
+    dy = rnd(_u(rng, B, oh, ow, Cc))
+    dya, dxa = act(dy, tdt), empty_act((B, ih, ih + 1, Cc), tdt, fill=0.5)
+    call("basi_resize_nearest_bwd", dya.ref, dxa.ref, 1)
+    xt = nchw(x).double().requires_grad_(True)
+    (O.resize_nearest(xt, (oh, ow)) * nchw(dy).double()).sum().backward()
+    assert rel_err(host(dxa) - 0.5, nhwc(xt.grad)) < (1e-6 if dtype == "f32" else 2e-2)
