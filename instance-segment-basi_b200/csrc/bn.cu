@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
                                                        double* __restrict__ sums, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, double count, float eps,
                                                        float* __restrict__ bnp, unsigned int* counter) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   const bool valid = cg * VN < C;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, double count, float eps, float* __restrict__ bnp,
                                    int C) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) finalize_channel(sums, gamma, beta, count, eps, bnp, C, c);
 }
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const T* __restrict__ 
                                                           const float* __restrict__ bnp, const T* __restrict__ res,
                                                           int ldr, const float* __restrict__ rbnp, int relu,
                                                           T* __restrict__ out, int ldo, int64_t R, int C) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   constexpr int AUNR = 4;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
@@ -246,6 +249,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
                      int ldx, const float* __restrict__ bnp, int relu_from_x, int64_t R, int C,
                      double* __restrict__ dsums, double count, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ coef, unsigned int* counter) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   const bool valid = cg * VN < C;
@@ -319,6 +323,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ 
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ dsums, double count, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0, s2 = 0;
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ out, int ldo, const T* __restrict__ x,
                     int ldx, const float* __restrict__ bnp, const float* __restrict__ coef, int relu_from_x,
                     T* __restrict__ dx, int lddx, T* __restrict__ dres, int lddr, int dres_acc, int64_t R, int C) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;
   if (cg * VN >= C) return;
@@ -473,6 +479,7 @@ template <typename T, bool HAS_RES, bool RES_BN>
 __global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp,
                                                                  const float* __restrict__ rbnp, int relu,
                                                                  T* __restrict__ out, int ldo, int C) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   const int c0 = threadIdx.x * VN;
   float mean[VN], scale[VN], beta[VN], rmean[VN], rscale[VN];
@@ -511,6 +518,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, int relu_from_x, int C,
                             double* __restrict__ dsums, double count, float* __restrict__ dgamma,
                             float* __restrict__ dbeta, float* __restrict__ coef, unsigned int* counter) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   constexpr int NT = HAS_OUT ? 3 : 2;
   const int c0 = threadIdx.x * VN;
@@ -563,6 +571,7 @@ template <typename T, bool HAS_OUT, bool DRES_ACC>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, const float* __restrict__ coef,
                            int relu_from_x, int C, T* __restrict__ dx, int lddx, T* __restrict__ dres, int lddr) {
+  pdl_prologue();
   constexpr int VN = Pack<T>::N;
   constexpr int NT = 2 + (HAS_OUT ? 1 : 0) + (DRES_ACC ? 1 : 0);
   const int c0 = threadIdx.x * VN;
@@ -661,13 +670,13 @@ static bool launch_apply_stream(const basi_tensor* x, const float* bnp, const ba
   if (res) { a.src[1] = (const char*)res->ptr; a.ldb[1] = (long long)res->ld * es; }
   if (!res) {
     allow_smem(bn_apply_stream_kernel<T, false, false>, g.smem);
-    bn_apply_stream_kernel<T, false, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, false, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
   } else if (!rbnp) {
     allow_smem(bn_apply_stream_kernel<T, true, false>, g.smem);
-    bn_apply_stream_kernel<T, true, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, true, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
   } else {
     allow_smem(bn_apply_stream_kernel<T, true, true>, g.smem);
-    bn_apply_stream_kernel<T, true, true><<<g.grid, g.block, g.smem, st>>>(a, bnp, rbnp, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, true, true>, g.grid, g.block, g.smem, st, a, bnp, rbnp, relu, (T*)out->ptr, out->ld, x->c);
   }
   return true;
 }
@@ -689,10 +698,10 @@ static bool launch_bwd_reduce_stream(const basi_tensor* dout, const basi_tensor*
   if (out) { a.src[2] = (const char*)out->ptr; a.ldb[2] = (long long)out->ld * es; }
   if (out) {
     allow_smem(bn_bwd_reduce_stream_kernel<T, true>, g.smem);
-    bn_bwd_reduce_stream_kernel<T, true><<<g.grid, g.block, g.smem, st>>>(a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+    basi::launch(bn_bwd_reduce_stream_kernel<T, true>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
   } else {
     allow_smem(bn_bwd_reduce_stream_kernel<T, false>, g.smem);
-    bn_bwd_reduce_stream_kernel<T, false><<<g.grid, g.block, g.smem, st>>>(a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+    basi::launch(bn_bwd_reduce_stream_kernel<T, false>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
   }
   return true;
 }
@@ -721,7 +730,7 @@ static bool launch_bwd_apply_stream(const basi_tensor* dout, const basi_tensor* 
 #define BASI_LAUNCH_BWD_APPLY(HO, DA)                                                                               \
   do {                                                                                                              \
     allow_smem(bn_bwd_apply_stream_kernel<T, HO, DA>, g.smem);                                                      \
-    bn_bwd_apply_stream_kernel<T, HO, DA><<<g.grid, g.block, g.smem, st>>>(a, bnp, coef, relu_from_x, x->c, dxp,    \
+    basi::launch(bn_bwd_apply_stream_kernel<T, HO, DA>, g.grid, g.block, g.smem, st, a, bnp, coef, relu_from_x, x->c, dxp,    \
                                                                             dx->ld, drp, lddr);                     \
   } while (0)
   if (out && acc) BASI_LAUNCH_BWD_APPLY(true, true);
@@ -754,7 +763,7 @@ int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const 
   int64_t R = pixels(x);
   DISPATCH_T(x->dtype, {
     RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * UNR, 8, 2 * Vec<T>::N * sizeof(double));
-    bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>((const T*)x->ptr, R, x->c, x->ld, sums, gamma,
+    basi::launch(bn_stats_kernel<T>, g.grid, g.block, g.smem, (cudaStream_t)stream, (const T*)x->ptr, R, x->c, x->ld, sums, gamma,
                                                                           beta, count, eps, bnp, counter);
   })
   BASI_CHECK_LAUNCH("bn_stats");
@@ -764,7 +773,7 @@ int basi_bn_stats(const basi_tensor* x, double* sums, const float* gamma, const 
 int basi_bn_finalize(const double* sums, const float* gamma, const float* beta, double count, float eps, float* bnp,
                      int C, void* stream) {
   BASI_CHECK_ARG(sums && gamma && beta && bnp && C > 0 && count > 0, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, count, eps, bnp, C);
+  basi::launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, sums, gamma, beta, count, eps, bnp, C);
   BASI_CHECK_LAUNCH("bn_finalize");
   return BASI_OK;
 }
@@ -786,13 +795,13 @@ int basi_bn_apply(const basi_tensor* x, const float* bnp, const basi_tensor* res
     const T* rp = res ? (const T*)res->ptr : nullptr;
     const int ldr = res ? res->ld : 0;
     if (!res)
-      bn_apply_kernel<T, false, false><<<g.grid, g.block, 0, st>>>((const T*)x->ptr, x->ld, bnp, rp, ldr, nullptr, relu,
+      basi::launch(bn_apply_kernel<T, false, false>, g.grid, g.block, 0, st, (const T*)x->ptr, x->ld, bnp, rp, ldr, nullptr, relu,
                                                                     (T*)out->ptr, out->ld, R, x->c);
     else if (!res_bnp)
-      bn_apply_kernel<T, true, false><<<g.grid, g.block, 0, st>>>((const T*)x->ptr, x->ld, bnp, rp, ldr, nullptr, relu,
+      basi::launch(bn_apply_kernel<T, true, false>, g.grid, g.block, 0, st, (const T*)x->ptr, x->ld, bnp, rp, ldr, nullptr, relu,
                                                                    (T*)out->ptr, out->ld, R, x->c);
     else
-      bn_apply_kernel<T, true, true><<<g.grid, g.block, 0, st>>>((const T*)x->ptr, x->ld, bnp, rp, ldr, res_bnp, relu,
+      basi::launch(bn_apply_kernel<T, true, true>, g.grid, g.block, 0, st, (const T*)x->ptr, x->ld, bnp, rp, ldr, res_bnp, relu,
                                                                   (T*)out->ptr, out->ld, R, x->c);
   })
   BASI_CHECK_LAUNCH("bn_apply");
@@ -815,8 +824,7 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
       return BASI_OK;
     }
     RowGeom g = row_geom(R, x->c, Vec<T>::N, 4 * BUNR, 12, 2 * Vec<T>::N * sizeof(double));
-    bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
+    basi::launch(bn_bwd_reduce_kernel<T>, g.grid, g.block, g.smem, (cudaStream_t)stream, (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, relu_from_x, R, x->c, dsums, count, dgamma, dbeta, coef, counter);
   })
   BASI_CHECK_LAUNCH("bn_bwd_reduce");
@@ -826,7 +834,7 @@ int basi_bn_bwd_reduce(const basi_tensor* dout, const basi_tensor* out, const ba
 int basi_bn_bwd_finalize(const double* dsums, double count, float* dgamma, float* dbeta, float* coef, int C,
                          void* stream) {
   BASI_CHECK_ARG(dsums && dgamma && dbeta && coef && C > 0, "bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dsums, count, dgamma, dbeta, coef, C);
+  basi::launch(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, dsums, count, dgamma, dbeta, coef, C);
   BASI_CHECK_LAUNCH("bn_bwd_finalize");
   return BASI_OK;
 }
@@ -847,8 +855,7 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
       return BASI_OK;
     }
     RowGeom g = row_geom(R, x->c, Vec<T>::N, 2 * BUNR, 12, 0);
-    bn_bwd_apply_kernel<T><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
+    basi::launch(bn_bwd_apply_kernel<T>, g.grid, g.block, 0, (cudaStream_t)stream, (const T*)dout->ptr, dout->ld, out ? (const T*)out->ptr : nullptr, out ? out->ld : 0, (const T*)x->ptr, x->ld,
         bnp, coef, relu_from_x, (T*)dx->ptr, dx->ld, dres ? (T*)dres->ptr : nullptr, dres ? dres->ld : 0,
         dres_accumulate, R, x->c);
   })

@@ -107,6 +107,49 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL): every kernel is launched with the stream-serialisation attribute and
+// starts with launch_dependents + wait.  The next kernel's CTAs become resident (and run their prologue) while the
+// tail of this one is still executing, and start the moment it has completed: the ~1000 dependent launches of a
+// training step no longer pay launch latency + drain between them.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();   // nothing produced by the predecessor is touched before this point
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                      Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = na ? attr : nullptr;
+  cfg.numAttrs = na;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_ex(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
+}
+
 inline bool vec_ok(const basi_tensor* t) {
   int vn = t->dtype == BASI_F32 ? 4 : 8;
   int es = t->dtype == BASI_F32 ? 4 : 2;

@@ -87,6 +87,7 @@ __device__ __forceinline__ bool src_coord(int d, int r, int stride, int dil, int
 
 template <int MODE, typename TS, typename TD>
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const GemmConv g) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BNP];
   const int tid = threadIdx.x;
@@ -285,6 +286,7 @@ constexpr int WK = 64, WN = 64, WP = 16, WS = 68;
 
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradConv g) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][WP][WS];
   __shared__ __align__(16) float Gs[2][WP][WS];
   const int tid = threadIdx.x;
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradConv g) {
 // column sums: out[n] += sum_m G[m][n]
 template <typename TG>
 __global__ void colsum_kernel(const TG* __restrict__ G, int64_t M, int C, int ld, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float sm[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -430,6 +433,7 @@ template <typename TA>
 __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ a, int64_t lda,
                                                          const float* __restrict__ w, float* __restrict__ y, int M,
                                                          int K, int N) {
+  pdl_prologue();
   __shared__ float sa[64][SK_KT + 1];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
 }
 
 __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int M, int N, int relu) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   float v = y[i] + (bias ? bias[i % N] : 0.f);
@@ -467,6 +472,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                            TA* __restrict__ da, int64_t lda, int M, int K, int N,
                                                            int acc_flag) {
+  pdl_prologue();
   extern __shared__ float sdy[];  // [M][N]
   for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
   __syncthreads();
@@ -501,6 +507,7 @@ template <typename TA>
 __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict__ a, int64_t lda,
                                                            const float* __restrict__ dy, float* __restrict__ dw,
                                                            float* __restrict__ dbias, int M, int K, int N) {
+  pdl_prologue();
   __shared__ float sa[64][SK_KT + 1];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
@@ -547,10 +554,10 @@ static int check_conv(const basi_conv_desc* d, const basi_tensor* x, const basi_
 template <int MODE>
 static int launch_gemm_conv(const GemmConv& g, int ts, int td, cudaStream_t st) {
   dim3 grid((g.M + BM - 1) / BM, (g.DC + BN - 1) / BN);
-  if (ts == BASI_F32 && td == BASI_F32) conv_gemm_kernel<MODE, float, float><<<grid, 256, 0, st>>>(g);
-  else if (ts == BASI_BF16 && td == BASI_BF16) conv_gemm_kernel<MODE, bf16, bf16><<<grid, 256, 0, st>>>(g);
-  else if (ts == BASI_BF16 && td == BASI_F32) conv_gemm_kernel<MODE, bf16, float><<<grid, 256, 0, st>>>(g);
-  else conv_gemm_kernel<MODE, float, bf16><<<grid, 256, 0, st>>>(g);
+  if (ts == BASI_F32 && td == BASI_F32) basi::launch(conv_gemm_kernel<MODE, float, float>, grid, 256, 0, st, g);
+  else if (ts == BASI_BF16 && td == BASI_BF16) basi::launch(conv_gemm_kernel<MODE, bf16, bf16>, grid, 256, 0, st, g);
+  else if (ts == BASI_BF16 && td == BASI_F32) basi::launch(conv_gemm_kernel<MODE, bf16, float>, grid, 256, 0, st, g);
+  else basi::launch(conv_gemm_kernel<MODE, float, bf16>, grid, 256, 0, st, g);
   return BASI_OK;
 }
 
@@ -620,18 +627,18 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   splits = (g.M + g.m_per_split - 1) / g.m_per_split;
   dim3 grid((g.K + WK - 1) / WK, (g.Cout + WN - 1) / WN, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  if (x->dtype == BASI_F32 && dy->dtype == BASI_F32) conv_wgrad_kernel<float, float><<<grid, 256, 0, st>>>(g);
-  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_BF16) conv_wgrad_kernel<bf16, bf16><<<grid, 256, 0, st>>>(g);
-  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_F32) conv_wgrad_kernel<bf16, float><<<grid, 256, 0, st>>>(g);
-  else conv_wgrad_kernel<float, bf16><<<grid, 256, 0, st>>>(g);
+  if (x->dtype == BASI_F32 && dy->dtype == BASI_F32) basi::launch(conv_wgrad_kernel<float, float>, grid, 256, 0, st, g);
+  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_BF16) basi::launch(conv_wgrad_kernel<bf16, bf16>, grid, 256, 0, st, g);
+  else if (x->dtype == BASI_BF16 && dy->dtype == BASI_F32) basi::launch(conv_wgrad_kernel<bf16, float>, grid, 256, 0, st, g);
+  else basi::launch(conv_wgrad_kernel<float, bf16>, grid, 256, 0, st, g);
   BASI_CHECK_LAUNCH("conv_wgrad");
   if (dbias) {
     int64_t M = g.M;
     int gy = (int)((M + 255) / 256);
     if (gy > 256) gy = 256;
     dim3 cg((g.Cout + 31) / 32, gy), cb(32, 8);
-    if (dy->dtype == BASI_F32) colsum_kernel<float><<<cg, cb, 0, st>>>((const float*)dy->ptr, M, g.Cout, g.ldg, dbias);
-    else colsum_kernel<bf16><<<cg, cb, 0, st>>>((const bf16*)dy->ptr, M, g.Cout, g.ldg, dbias);
+    if (dy->dtype == BASI_F32) basi::launch(colsum_kernel<float>, cg, cb, 0, st, (const float*)dy->ptr, M, g.Cout, g.ldg, dbias);
+    else basi::launch(colsum_kernel<bf16>, cg, cb, 0, st, (const bf16*)dy->ptr, M, g.Cout, g.ldg, dbias);
     BASI_CHECK_LAUNCH("conv_wgrad(dbias)");
   }
   return BASI_OK;
@@ -643,10 +650,10 @@ int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, con
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
   dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
-  if (dtype_a == BASI_F32) skinny_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)a, lda, w, y, M, K, N);
-  else skinny_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)a, lda, w, y, M, K, N);
+  if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)a, lda, w, y, M, K, N);
+  else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, w, y, M, K, N);
   BASI_CHECK_LAUNCH("skinny_fwd");
-  bias_act_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(y, bias, M, N, relu);
+  basi::launch(bias_act_kernel, (M * N + 255) / 256, 256, 0, st, y, bias, M, N, relu);
   BASI_CHECK_LAUNCH("skinny_fwd(bias)");
   return BASI_OK;
 }
@@ -663,11 +670,11 @@ int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, in
   if (dtype_a == BASI_F32) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(skinny_dgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    skinny_dgrad_kernel<float><<<blocks, 256, smem, st>>>(dy, w, (float*)da, lda, M, K, N, accumulate);
+    basi::launch(skinny_dgrad_kernel<float>, blocks, 256, smem, st, dy, w, (float*)da, lda, M, K, N, accumulate);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(skinny_dgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    skinny_dgrad_kernel<bf16><<<blocks, 256, smem, st>>>(dy, w, (bf16*)da, lda, M, K, N, accumulate);
+    basi::launch(skinny_dgrad_kernel<bf16>, blocks, 256, smem, st, dy, w, (bf16*)da, lda, M, K, N, accumulate);
   }
   BASI_CHECK_LAUNCH("skinny_dgrad");
   return BASI_OK;
@@ -678,8 +685,8 @@ int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, 
   BASI_CHECK_ARG(a && dy && dw && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_wgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
-  if (dtype_a == BASI_F32) skinny_wgrad_kernel<float><<<grid, 128, 0, st>>>((const float*)a, lda, dy, dw, dbias, M, K, N);
-  else skinny_wgrad_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
+  else basi::launch(skinny_wgrad_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
   BASI_CHECK_LAUNCH("skinny_wgrad");
   return BASI_OK;
 }

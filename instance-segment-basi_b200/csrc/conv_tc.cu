@@ -225,6 +225,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
   const int cid = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -484,6 +487,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // work item of this CTA
   int wi = blockIdx.x;
@@ -577,6 +582,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ w_io, bf16* __restrict__ w_oi,
                                     int taps, int cin, int cout) {
   __shared__ float tile[32][33];
+  pdl_prologue();
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
   const float* src = w + (size_t)tap * cin * cout;
@@ -607,6 +613,7 @@ struct PackEntry {
 __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n_layers) {
   __shared__ float tile[32][33];
   __shared__ PackEntry e;
+  pdl_prologue();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     int lo = 0, hi = n_layers - 1;
     while (lo < hi) {   // last entry with block_start <= blockIdx.x
@@ -757,23 +764,12 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     cudaFuncSetAttribute(conv_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  if (pl->cluster == 2) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pl->grid);
-    cfg.blockDim = dim3(NTHREADS_CONV);
-    cfg.dynamicSmemBytes = pl->smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, pl->mapA, pl->mapB, pl->mapD, pl->cp);
-  } else {
-    conv_tc_kernel<BN, 1><<<pl->grid, NTHREADS_CONV, pl->smem, st>>>(pl->mapA, pl->mapB, pl->mapD, pl->cp);
-  }
+  if (pl->cluster == 2)
+    basi::launch_ex(conv_tc_kernel<BN, 2>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, 2, pl->mapA, pl->mapB, pl->mapD,
+                    pl->cp);
+  else
+    basi::launch(conv_tc_kernel<BN, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA, pl->mapB, pl->mapD,
+                 pl->cp);
   return BASI_OK;
 }
 template <int BN>
@@ -783,7 +779,7 @@ static int launch_wgrad(basi_tc_conv* pl, cudaStream_t st) {
     cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  wgrad_tc_kernel<BN><<<pl->grid, NTHREADS, pl->smem, st>>>(pl->mapA, pl->mapB, pl->dw, pl->wp);
+  basi::launch(wgrad_tc_kernel<BN>, dim3(pl->grid), dim3(NTHREADS), pl->smem, st, pl->mapA, pl->mapB, pl->dw, pl->wp);
   return BASI_OK;
 }
 
@@ -796,7 +792,8 @@ int basi_tc_conv_supported(int kind, const basi_conv_desc* d, const basi_tensor*
 int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int taps, int cin, int cout, void* stream) {
   BASI_CHECK_ARG(w && w_io_bf16 && w_oi_bf16 && taps > 0 && cin > 0 && cout > 0, "tc_pack_weights: bad argument");
   dim3 grid((cout + 31) / 32, (cin + 31) / 32, taps), block(32, 8);
-  pack_weights_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (bf16*)w_io_bf16, (bf16*)w_oi_bf16, taps, cin, cout);
+  basi::launch(pack_weights_kernel, grid, block, 0, (cudaStream_t)stream, w, (bf16*)w_io_bf16, (bf16*)w_oi_bf16, taps, cin,
+               cout);
   BASI_CHECK_LAUNCH("tc_pack_weights");
   return BASI_OK;
 }
@@ -804,8 +801,8 @@ int basi_tc_pack_weights(const float* w, void* w_io_bf16, void* w_oi_bf16, int t
 int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_blocks, void* stream) {
   BASI_CHECK_ARG(table_dev && n_layers > 0 && total_blocks > 0, "tc_pack_weights_multi: bad argument");
   static_assert(sizeof(PackEntry) == 56, "PackEntry layout is part of the C ABI (see include/basi_b200.h)");
-  pack_weights_multi_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>((const PackEntry*)table_dev,
-                                                                                   n_layers);
+  basi::launch(pack_weights_multi_kernel, dim3(total_blocks), dim3(32, 8), 0, (cudaStream_t)stream,
+               (const PackEntry*)table_dev, n_layers);
   BASI_CHECK_LAUNCH("tc_pack_weights_multi");
   return BASI_OK;
 }

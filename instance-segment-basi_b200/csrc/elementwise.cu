@@ -3,6 +3,7 @@
 // attention gating, click-map rasterisation, fused losses, SGD and prediction helpers.
 // All tensors NHWC; 128-bit vector access over channels (4 x f32 / 8 x bf16).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BASI_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 int sm_count() {
   static int cached = 0;
@@ -35,6 +44,7 @@ template <typename T>
 __global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, T* __restrict__ y,
                                       int ldy, int OH, int OW, int pad_t, int pad_l, uint8_t* __restrict__ amax,
                                       int64_t total) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -82,6 +92,7 @@ template <typename T>
 __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, const uint8_t* __restrict__ amax,
                                       T* __restrict__ dx, int ldx, int H, int W, int C, int pad_t, int pad_l, int acc,
                                       int64_t total) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -121,6 +132,7 @@ __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH,
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, int k, T* __restrict__ y,
                                    int ldy, int OH, int OW) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   extern __shared__ float sacc[];  // [blockDim.y][blockDim.x*VN]
   const int ow = blockIdx.x % OW;
@@ -165,6 +177,7 @@ __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int ldx, int H, int 
 template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, int k, T* __restrict__ dx,
                                    int ldx, int H, int W, int C, int acc, int64_t total) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   const float inv = 1.0f / (float)(k * k);
@@ -203,6 +216,7 @@ __device__ __forceinline__ void ac_coord(int o, float scale, int in_size, int& l
 template <typename T>
 __global__ void bilinear_ac_fwd_kernel(const T* __restrict__ x, int ldx, int IH, int IW, int C, T* __restrict__ y,
                                        int ldy, int OH, int OW, float sh, float sw, int64_t total) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -247,6 +261,7 @@ __device__ __forceinline__ void ac_window(int s, float scale, int in_size, int o
 template <typename T>
 __global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, T* __restrict__ dx, int ldx,
                                        int IH, int IW, int C, float sh, float sw, int acc) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   extern __shared__ float sacc[];
   const int sx = blockIdx.x % IW;
@@ -310,6 +325,7 @@ __global__ void bilinear_ac_bwd_kernel(const T* __restrict__ dy, int ldy, int OH
 template <typename T, bool RELU>
 __global__ void gate_mul_fwd_kernel(const T* __restrict__ feat, int ldf, const float* __restrict__ logits, int nseg,
                                     int att, T* __restrict__ out, int ldo, int64_t R, int C) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   const int64_t total = R * cgs;
@@ -329,6 +345,7 @@ template <typename T, bool RELU>
 __global__ void gate_mul_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ feat, int ldf,
                                     const float* __restrict__ logits, int nseg, int att, T* __restrict__ dfeat,
                                     int lddf, int acc, float* __restrict__ dlogits, int64_t R, int C) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   const int lane = threadIdx.x & 31;
@@ -363,6 +380,7 @@ __global__ void gate_mul_bwd_kernel(const T* __restrict__ dout, int ldd, const T
 // gate[r] = p > thr ? p : 0 with p = softmax(logits[r, :])[sel]        (90AttentionSingle2/BAISNet.py:743-746)
 __global__ void softmax_gate_fwd_kernel(const float* __restrict__ logits, int64_t rows, int C, int sel, float thr,
                                         float* __restrict__ gate) {
+  pdl_prologue();
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const float* x = logits + r * C;
     float mx = x[0];
@@ -376,6 +394,7 @@ __global__ void softmax_gate_fwd_kernel(const float* __restrict__ logits, int64_
 // dlogits[r, j] += dgate[r] * p_sel * (delta(j, sel) - p_j) where the gate passed, 0 elsewhere (tf.where adjoint)
 __global__ void softmax_gate_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dgate, int64_t rows,
                                         int C, int sel, float thr, float* __restrict__ dlogits, int accumulate) {
+  pdl_prologue();
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const float* x = logits + r * C;
     float mx = x[0];
@@ -399,6 +418,7 @@ __device__ __forceinline__ int nn_src(int o, float scale, int in_size) { return 
 template <typename T>
 __global__ void resize_nearest_fwd_kernel(const T* __restrict__ x, int ldx, int IH, int IW, int C, T* __restrict__ y,
                                           int ldy, int OH, int OW, float sh, float sw, int64_t total) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     int64_t p = i / C;
@@ -414,6 +434,7 @@ __global__ void resize_nearest_fwd_kernel(const T* __restrict__ x, int ldx, int 
 template <typename T>
 __global__ void resize_nearest_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, T* __restrict__ dx, int ldx,
                                           int IH, int IW, int C, float sh, float sw, int acc, int64_t total) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     int64_t p = i / C;
@@ -439,6 +460,7 @@ __global__ void resize_nearest_bwd_kernel(const T* __restrict__ dy, int ldy, int
 __global__ void clickmap_pack_kernel(const uint8_t* __restrict__ img_u8, const float* __restrict__ img_f32,
                                      const int32_t* __restrict__ clicks, const float* __restrict__ lut,
                                      int64_t lut_len, float4* __restrict__ out, int B, int H, int W) {
+  pdl_prologue();
   const int64_t total = (int64_t)B * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int x = (int)(i % W);
@@ -483,6 +505,7 @@ __device__ __forceinline__ void block_sum_atomic(double v, double* dst) {
 
 __global__ void wbce_kernel(const float* __restrict__ logits, const float* __restrict__ labels, float q, double scale,
                             float gscale, int64_t n, double* __restrict__ loss_acc, float* __restrict__ dlogits) {
+  pdl_prologue();
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float x = logits[i], z = labels[i];
@@ -500,6 +523,7 @@ __global__ void wbce_kernel(const float* __restrict__ logits, const float* __res
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int64_t rows,
                                   int C, double scale, float gscale, double* __restrict__ loss_acc,
                                   float* __restrict__ dlogits) {
+  pdl_prologue();
   double acc = 0.0;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const float* x = logits + r * C;
@@ -523,6 +547,7 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_
 
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ lr_dev,
                            int64_t n, bf16* __restrict__ wb) {
+  pdl_prologue();
   const float lr = __ldg(lr_dev);
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -548,11 +573,13 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, c
 }
 
 __global__ void threshold_kernel(const float* __restrict__ x, float thr, int32_t* __restrict__ out, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = x[i] > thr ? 1 : 0;
 }
 
 __global__ void argmax_kernel(const float* __restrict__ x, int64_t rows, int C, int32_t* __restrict__ out) {
+  pdl_prologue();
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const float* p = x + r * C;
     float b = p[0];
@@ -570,6 +597,7 @@ __global__ void argmax_kernel(const float* __restrict__ x, int64_t rows, int C, 
 // monotone per channel -- it is, but the reference takes sigmoid first in float32, so do the same to keep ties equal.
 __global__ void upsample_legacy_argmax_kernel(const float* __restrict__ x, int B, int PH, int PW, int C, int SH, int SW,
                                               float sh, float sw, int32_t* __restrict__ out) {
+  pdl_prologue();
   const int64_t total = (int64_t)B * SH * SW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int ox = (int)(i % SW);
@@ -599,14 +627,17 @@ __global__ void upsample_legacy_argmax_kernel(const float* __restrict__ x, int B
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16_rn(s[i]);
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = __bfloat162float(s[i]);
 }
 __global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     if (!(y[i] > 0.f)) dy[i] = 0.f;
 }
@@ -650,8 +681,7 @@ int basi_clickmap_pack(const void* img, int img_is_f32, const int32_t* clicks, c
                        float* out, int B, int H, int W, void* stream) {
   BASI_CHECK_ARG(img && clicks && lut && out && B > 0 && H > 0 && W > 0, "clickmap_pack: bad argument");
   int64_t total = (int64_t)B * H * W;
-  clickmap_pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      img_is_f32 ? nullptr : (const uint8_t*)img, img_is_f32 ? (const float*)img : nullptr, clicks, lut, lut_len,
+  basi::launch(clickmap_pack_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, img_is_f32 ? nullptr : (const uint8_t*)img, img_is_f32 ? (const float*)img : nullptr, clicks, lut, lut_len,
       (float4*)out, B, H, W);
   BASI_CHECK_LAUNCH("clickmap_pack");
   return BASI_OK;
@@ -672,8 +702,7 @@ int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* arg
   same_pad_3s2(x->w, y->w, &pl);
   DISPATCH_T(x->dtype, {
     int64_t total = pixels(y) * (y->c / Vec<T>::N);
-    maxpool3s2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, pt, pl, argmax, total);
+    basi::launch(maxpool3s2_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, pt, pl, argmax, total);
   })
   BASI_CHECK_LAUNCH("maxpool3s2_fwd");
   return BASI_OK;
@@ -689,8 +718,7 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
   same_pad_3s2(dx->w, dy->w, &pl);
   DISPATCH_T(dx->dtype, {
     int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
-    maxpool3s2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dy->ptr, dy->ld, dy->h, dy->w, argmax, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, pt, pl, accumulate,
+    basi::launch(maxpool3s2_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, argmax, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, pt, pl, accumulate,
         total);
   })
   BASI_CHECK_LAUNCH("maxpool3s2_bwd");
@@ -716,8 +744,7 @@ int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* st
     size_t smem;
     unsigned chunks;
     pool_block(x->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks);
-    avgpool_fwd_kernel<T><<<dim3((unsigned)pixels(y), chunks), block, smem, (cudaStream_t)stream>>>(
-        (const T*)x->ptr, x->ld, x->h, x->w, x->c, k, (T*)y->ptr, y->ld, y->h, y->w);
+    basi::launch(avgpool_fwd_kernel<T>, dim3((unsigned)pixels(y), chunks), block, smem, (cudaStream_t)stream, (const T*)x->ptr, x->ld, x->h, x->w, x->c, k, (T*)y->ptr, y->ld, y->h, y->w);
   })
   BASI_CHECK_LAUNCH("avgpool_fwd");
   return BASI_OK;
@@ -729,8 +756,7 @@ int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int ac
                  "avgpool bwd: bad tensors");
   DISPATCH_T(dx->dtype, {
     int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
-    avgpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dy->ptr, dy->ld, dy->h, dy->w, k, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
+    basi::launch(avgpool_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, k, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
   })
   BASI_CHECK_LAUNCH("avgpool_bwd");
   return BASI_OK;
@@ -743,8 +769,7 @@ int basi_bilinear_ac_fwd(const basi_tensor* x, const basi_tensor* y, void* strea
                  "bilinear fwd: bad tensors");
   DISPATCH_T(x->dtype, {
     int64_t total = pixels(y) * (y->c / Vec<T>::N);
-    bilinear_ac_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, ac_scale(x->h, y->h),
+    basi::launch(bilinear_ac_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, ac_scale(x->h, y->h),
         ac_scale(x->w, y->w), total);
   })
   BASI_CHECK_LAUNCH("bilinear_ac_fwd");
@@ -759,8 +784,7 @@ int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accum
     size_t smem;
     unsigned chunks;
     pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks);
-    bilinear_ac_bwd_kernel<T><<<dim3((unsigned)pixels(dx), chunks), block, smem, (cudaStream_t)stream>>>(
-        (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, ac_scale(dx->h, dy->h),
+    basi::launch(bilinear_ac_bwd_kernel<T>, dim3((unsigned)pixels(dx), chunks), block, smem, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, ac_scale(dx->h, dy->h),
         ac_scale(dx->w, dy->w), accumulate);
   })
   BASI_CHECK_LAUNCH("bilinear_ac_bwd");
@@ -775,8 +799,7 @@ int basi_gate_mul_fwd(const basi_tensor* feat, const float* logits, int nseg, in
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
     int64_t total = R * (feat->c / Vec<T>::N);
-    gate_mul_fwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)out->ptr, out->ld, R, feat->c);
+    basi::launch(gate_mul_fwd_kernel<T, true>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)out->ptr, out->ld, R, feat->c);
   })
   BASI_CHECK_LAUNCH("gate_mul_fwd");
   return BASI_OK;
@@ -790,8 +813,7 @@ int basi_gate_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const fl
                  "gate_mul bwd: bad argument");
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
-    gate_mul_bwd_kernel<T, true><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)dfeat->ptr, dfeat->ld,
+    basi::launch(gate_mul_bwd_kernel<T, true>, grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream, (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, logits, nseg, att, (T*)dfeat->ptr, dfeat->ld,
         dfeat_accumulate, dlogits, R, feat->c);
   })
   BASI_CHECK_LAUNCH("gate_mul_bwd");
@@ -807,8 +829,7 @@ int basi_mask_mul_fwd(const basi_tensor* feat, const float* mask, int nch, int c
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
     int64_t total = R * (feat->c / Vec<T>::N);
-    gate_mul_fwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)out->ptr, out->ld, R, feat->c);
+    basi::launch(gate_mul_fwd_kernel<T, false>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)out->ptr, out->ld, R, feat->c);
   })
   BASI_CHECK_LAUNCH("mask_mul_fwd");
   return BASI_OK;
@@ -822,8 +843,7 @@ int basi_mask_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const fl
                  "mask_mul bwd: bad argument");
   int64_t R = pixels(feat);
   DISPATCH_T(feat->dtype, {
-    gate_mul_bwd_kernel<T, false><<<grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)dfeat->ptr, dfeat->ld,
+    basi::launch(gate_mul_bwd_kernel<T, false>, grid_for(R * 32, 256), 256, 0, (cudaStream_t)stream, (const T*)dout->ptr, dout->ld, (const T*)feat->ptr, feat->ld, mask, nch, ch, (T*)dfeat->ptr, dfeat->ld,
         dfeat_accumulate, dmask, R, feat->c);
   })
   BASI_CHECK_LAUNCH("mask_mul_bwd");
@@ -832,7 +852,7 @@ int basi_mask_mul_bwd(const basi_tensor* dout, const basi_tensor* feat, const fl
 
 int basi_softmax_gate_fwd(const float* logits, int64_t rows, int C, int sel, float thr, float* gate, void* stream) {
   BASI_CHECK_ARG(logits && gate && rows > 0 && C > 0 && sel >= 0 && sel < C, "softmax_gate fwd: bad argument");
-  softmax_gate_fwd_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, rows, C, sel, thr, gate);
+  basi::launch(softmax_gate_fwd_kernel, grid_for(rows, 128), 128, 0, (cudaStream_t)stream, logits, rows, C, sel, thr, gate);
   BASI_CHECK_LAUNCH("softmax_gate_fwd");
   return BASI_OK;
 }
@@ -841,7 +861,7 @@ int basi_softmax_gate_bwd(const float* logits, const float* dgate, int64_t rows,
                           float* dlogits, int accumulate, void* stream) {
   BASI_CHECK_ARG(logits && dgate && dlogits && rows > 0 && C > 0 && sel >= 0 && sel < C,
                  "softmax_gate bwd: bad argument");
-  softmax_gate_bwd_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, dgate, rows, C, sel, thr,
+  basi::launch(softmax_gate_bwd_kernel, grid_for(rows, 128), 128, 0, (cudaStream_t)stream, logits, dgate, rows, C, sel, thr,
                                                                                dlogits, accumulate);
   BASI_CHECK_LAUNCH("softmax_gate_bwd");
   return BASI_OK;
@@ -852,8 +872,7 @@ int basi_resize_nearest_fwd(const basi_tensor* x, const basi_tensor* y, void* st
                  "resize_nearest fwd: bad tensors");
   DISPATCH_T(x->dtype, {
     int64_t total = pixels(y) * y->c;
-    resize_nearest_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, (float)x->h / (float)y->h,
+    basi::launch(resize_nearest_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, (float)x->h / (float)y->h,
         (float)x->w / (float)y->w, total);
   })
   BASI_CHECK_LAUNCH("resize_nearest_fwd");
@@ -865,8 +884,7 @@ int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int ac
                  "resize_nearest bwd: bad tensors");
   DISPATCH_T(dx->dtype, {
     int64_t total = pixels(dx) * dx->c;
-    resize_nearest_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, (float)dx->h / (float)dy->h,
+    basi::launch(resize_nearest_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, (float)dx->h / (float)dy->h,
         (float)dx->w / (float)dy->w, accumulate, total);
   })
   BASI_CHECK_LAUNCH("resize_nearest_bwd");
@@ -876,7 +894,7 @@ int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int ac
 int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight, double scale, float grad_scale,
                       int64_t n, double* loss_acc, float* dlogits, void* stream) {
   BASI_CHECK_ARG(logits && labels && loss_acc && n > 0, "wbce: bad argument");
-  wbce_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(logits, labels, pos_weight, scale, grad_scale, n,
+  basi::launch(wbce_kernel, grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream, logits, labels, pos_weight, scale, grad_scale, n,
                                                                     loss_acc, dlogits);
   BASI_CHECK_LAUNCH("wbce_fwd_bwd");
   return BASI_OK;
@@ -885,7 +903,7 @@ int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight
 int basi_softmax_ce_fwd_bwd(const float* logits, const int32_t* labels, int64_t rows, int C, double scale,
                             float grad_scale, double* loss_acc, float* dlogits, void* stream) {
   BASI_CHECK_ARG(logits && labels && loss_acc && rows > 0 && C > 0, "softmax_ce: bad argument");
-  softmax_ce_kernel<<<grid_for(rows, 128, 4), 128, 0, (cudaStream_t)stream>>>(logits, labels, rows, C, scale,
+  basi::launch(softmax_ce_kernel, grid_for(rows, 128, 4), 128, 0, (cudaStream_t)stream, logits, labels, rows, C, scale,
                                                                              grad_scale, loss_acc, dlogits);
   BASI_CHECK_LAUNCH("softmax_ce_fwd_bwd");
   return BASI_OK;
@@ -895,21 +913,21 @@ int basi_sgd_step(float* w, const float* g, const float* lr_dev, int64_t n, void
   BASI_CHECK_ARG(w && g && lr_dev && n > 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)g & 15) == 0 &&
                      ((uintptr_t)w_bf16 & 7) == 0,
                  "sgd_step: bad argument / alignment");
-  sgd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(w, g, lr_dev, n, (bf16*)w_bf16);
+  basi::launch(sgd_kernel, grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, w, g, lr_dev, n, (bf16*)w_bf16);
   BASI_CHECK_LAUNCH("sgd_step");
   return BASI_OK;
 }
 
 int basi_threshold(const float* logits, float thr, int32_t* out, int64_t n, void* stream) {
   BASI_CHECK_ARG(logits && out && n > 0, "threshold: bad argument");
-  threshold_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(logits, thr, out, n);
+  basi::launch(threshold_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, logits, thr, out, n);
   BASI_CHECK_LAUNCH("threshold");
   return BASI_OK;
 }
 
 int basi_argmax(const float* logits, int64_t rows, int C, int32_t* out, void* stream) {
   BASI_CHECK_ARG(logits && out && rows > 0 && C > 0, "argmax: bad argument");
-  argmax_kernel<<<grid_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(logits, rows, C, out);
+  basi::launch(argmax_kernel, grid_for(rows, 128), 128, 0, (cudaStream_t)stream, logits, rows, C, out);
   BASI_CHECK_LAUNCH("argmax");
   return BASI_OK;
 }
@@ -919,27 +937,26 @@ int basi_upsample_legacy_argmax(const float* logits, int B, int P_h, int P_w, in
   BASI_CHECK_ARG(logits && out && B > 0 && P_h > 0 && P_w > 0 && C > 0 && S_h > 0 && S_w > 0,
                  "upsample_legacy_argmax: bad argument");
   int64_t total = (int64_t)B * S_h * S_w;
-  upsample_legacy_argmax_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      logits, B, P_h, P_w, C, S_h, S_w, (float)P_h / (float)S_h, (float)P_w / (float)S_w, out);
+  basi::launch(upsample_legacy_argmax_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, logits, B, P_h, P_w, C, S_h, S_w, (float)P_h / (float)S_h, (float)P_w / (float)S_w, out);
   BASI_CHECK_LAUNCH("upsample_legacy_argmax");
   return BASI_OK;
 }
 
 int basi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   BASI_CHECK_ARG(src && dst && n > 0, "cast: bad argument");
-  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  basi::launch(cast_f32_bf16_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   BASI_CHECK_LAUNCH("cast_f32_to_bf16");
   return BASI_OK;
 }
 int basi_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
   BASI_CHECK_ARG(src && dst && n > 0, "cast: bad argument");
-  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  basi::launch(cast_bf16_f32_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)src, dst, n);
   BASI_CHECK_LAUNCH("cast_bf16_to_f32");
   return BASI_OK;
 }
 int basi_relu_bwd_f32(float* dy, const float* y, int64_t n, void* stream) {
   BASI_CHECK_ARG(dy && y && n > 0, "relu_bwd: bad argument");
-  relu_bwd_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, n);
+  basi::launch(relu_bwd_f32_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, dy, y, n);
   BASI_CHECK_LAUNCH("relu_bwd_f32");
   return BASI_OK;
 }
