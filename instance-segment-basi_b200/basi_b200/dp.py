@@ -104,6 +104,7 @@ class DataParallel(object):
                 pos = ready + 1
             if self.world > 1:
                 self.comm_stream.wait_stream(cur)
+                engine.join_side(self.comm_stream)      # weight gradients run on the engine's side stream
                 with torch.cuda.stream(self.comm_stream):
                     dist.all_reduce(engine.grads_flat[start:end], op=dist.ReduceOp.AVG)
         if pos < len(calls):

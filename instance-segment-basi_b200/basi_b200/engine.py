@@ -65,7 +65,7 @@ class _BNRec(object):
 
 class Engine(object):
     def __init__(self, net, batch_size, precision="bf16", training=True, loss=None, device=None, use_tc=True,
-                 dry_run=False, fuse_bn_stats=True):
+                 dry_run=False, fuse_bn_stats=True, overlap_wgrad=True):
         """net: a built Network; loss: dict(kind='bce'|'softmax', pos_weight, class_weight, seg, cls).
 
         dry_run=True only builds the plan (buffers on the host, nothing can be executed): used by the
@@ -89,6 +89,9 @@ class Engine(object):
         self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
+        self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run
+        self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
+        self._side_dirty = False
         self._tc_plans = []
         self._tc_producer = {}
         self.fuse_bn_stats = fuse_bn_stats
@@ -537,7 +540,7 @@ class Engine(object):
         else:
             self._call(self.bwd, "basi_conv_wgrad", dptr, x.ref, dy.ref, self._gptr(op["w"]),
                        self._gptr(op["b"]) if op["b"] else None, flops=self._conv_flops(op),
-                       writes=[op["w"]] + ([op["b"]] if op["b"] else []))
+                       writes=[op["w"]] + ([op["b"]] if op["b"] else []), side=True)
         if need_dx:
             acc = self._acc_flag(x)
             if tc_ok and lib.basi_tc_conv_supported(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1:
@@ -635,6 +638,7 @@ class Engine(object):
         meta = dict(flops=self._conv_flops(op), layer=op["name"])
         if kind == _lib.TC_WGRAD:
             meta["writes"] = [op["w"]]
+            meta["side"] = True
         lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))
         return handle
 
@@ -666,13 +670,30 @@ class Engine(object):
 
     # ------------------------------------------------------------------ execution
     def _run(self, lst, st):
+        """Enqueues the calls on stream `st`.  Calls tagged side=True (weight gradients: nothing on the main chain
+        depends on them before the optimizer) go to a second stream behind an event, so they overlap the dgrad /
+        batch-norm chain; join_side() makes the main stream wait for them."""
         if self.dry_run:
             raise _lib.BasiError("dry_run engine cannot execute")
-        for name, fn, args, _ in lst:
-            rc = fn(*args, st)
+        side = self._side if self.overlap_wgrad else None
+        cur = torch.cuda.current_stream(self.device) if side is not None else None
+        for name, fn, args, meta in lst:
+            if side is not None and meta.get("side"):
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                rc = fn(*args, side.cuda_stream)
+                self._side_dirty = True
+            else:
+                rc = fn(*args, st)
             if rc != 0:
                 raise _lib.BasiError("%s failed (%d): %s" % (name, rc, _lib.last_error()))
         _lib.LAUNCHES += len(lst)
+
+    def join_side(self, waiter=None):
+        """Makes `waiter` (default: the current stream) wait for the side-stream work issued so far."""
+        if self._side is not None and self._side_dirty:
+            (waiter or torch.cuda.current_stream(self.device)).wait_stream(self._side)
 
     def _stream(self):
         if self.dry_run:
@@ -724,8 +745,11 @@ class Engine(object):
             sync_grads.run_backward(self, st)          # bucketed all-reduce overlapped with the backward calls
         else:
             self._run(self.bwd, st)
+            self.join_side()
             if sync_grads is not None:
                 sync_grads(self.grads_flat)
+        self.join_side()
+        self._side_dirty = False
         _lib.call("basi_sgd_step", self.params_flat.data_ptr(), self.grads_flat.data_ptr(), self.lr_dev.data_ptr(),
                   C.c_int64(self.n_flat), None, st)
         self._refresh_weight_copies(st)
