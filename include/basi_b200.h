@@ -88,6 +88,12 @@ int basi_conv_dgrad(const basi_conv_desc* d, const basi_tensor* dy, const float*
 int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* dy, float* dw,
                     float* dbias, void* stream);
 
+/* x[:, ::stride, ::stride, :] and its adjoint (dx (+)= dy scattered to the sampled pixels, zero elsewhere): the
+ * 1x1 stride-2 VALID convolutions conv3_1_1x1_proj / conv3_1_1x1_reduce (BAISPSPNet.py:310,314) are computed as the
+ * stride-1 1x1 convolution of the subsampled tensor. */
+int basi_subsample_fwd(const basi_tensor* x, int stride, const basi_tensor* y, void* stream);
+int basi_subsample_bwd(const basi_tensor* dy, int stride, const basi_tensor* dx, int accumulate, void* stream);
+
 /* ---- A6/A7: Network.batch_normalization (+relu, +add) (BAISPSPNet.py:204-236, :148-150, :171-173) ----
  * sums: double [BASI_BN_REPLICAS][2*C] (sum x, sum x^2), ADDED into (caller zeroes); counter: one zeroed uint32
  * per launch.

@@ -93,6 +93,7 @@ class Engine(object):
         self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
         self._side_dirty = False
         self._tc_plans = []
+        self._subsampled = {}
         self._tc_producer = {}
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
@@ -255,6 +256,19 @@ class Engine(object):
             _, src, pad = src
         x = src
         k, s, d = a["k_h"], a["stride"], a["dilation"]
+        if k == 1 and a["k_w"] == 1 and s > 1 and a["padding"] != "SAME" and pad == 0:
+            # strided 1x1 VALID conv == stride-1 1x1 conv of x[:, ::s, ::s, :]; the subsampled tensor is shared by all
+            # strided convs reading the same input (conv3_1 proj and reduce)
+            key = (id(x), s)
+            if key not in self._subsampled:
+                xs = self._new_act(-(-x.shape[1] // s), -(-x.shape[2] // s), x.shape[3],
+                                   torch.float32 if x.t.dtype == torch.float32 else None)
+                self._subsampled[key] = xs
+                sop = dict(x=x, y=xs, stride=s)
+                self._ops.append(("subsample", sop))
+                self._call(self.fwd, "basi_subsample_fwd", x.ref, s, xs.ref)
+            x = self._subsampled[key]
+            s = 1
         if a["padding"] == "SAME":
             pt, pl = _same_pad_before(x.shape[1], k, s, d), _same_pad_before(x.shape[2], a["k_w"], s, d)
         else:
@@ -576,6 +590,13 @@ class Engine(object):
             self._call(self.bwd, "basi_bn_bwd_apply", dout.ref, mask, x.ref, rec.bnp.data_ptr(),
                        rec.coef.data_ptr(), from_x, dx.ref, dres, dacc,
                        bytes=nb * (nin + 1 + (0 if dres is None else (2 if dacc else 1))))
+
+    def _bwd_subsample(self, op):
+        x, y = op["x"], op["y"]
+        if x is self.input:
+            return
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_subsample_bwd", y.grad.ref, op["stride"], x.grad.ref, acc)
 
     def _bwd_maxpool(self, op):
         x, y = op["x"], op["y"]

@@ -456,6 +456,57 @@ __global__ void resize_nearest_bwd_kernel(const T* __restrict__ dy, int ldy, int
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Spatial subsampling x[:, ::s, ::s, :] and its adjoint: a strided 1x1 VALID convolution (conv3_1_1x1_proj / _reduce,
+// BAISPSPNet.py:310,314) is the stride-1 1x1 convolution of the subsampled tensor, which the tcgen05 path takes.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void subsample_fwd_kernel(const T* __restrict__ x, int ldx, int IH, int IW, int C, int s, T* __restrict__ y,
+                                     int ldy, int OH, int OW, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    const int ow = (int)(p % OW);
+    int64_t t = p / OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    Vec<T> v = Vec<T>::load(x + (((int64_t)n * IH + oh * s) * IW + ow * s) * ldx + cg * VN);
+    v.store(y + p * ldy + cg * VN);
+  }
+}
+// dx[n,h,w,:] (+)= (h % s == 0 && w % s == 0) ? dy[n,h/s,w/s,:] : 0
+template <typename T>
+__global__ void subsample_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, int OW, int s, T* __restrict__ dx, int ldx,
+                                     int IH, int IW, int C, int acc, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    int64_t p = i / cgs;
+    const int iw = (int)(p % IW);
+    int64_t t = p / IW;
+    const int ih = (int)(t % IH);
+    const int n = (int)(t / IH);
+    const bool hit = (ih % s == 0) && (iw % s == 0) && (ih / s < OH) && (iw / s < OW);
+    if (!hit && acc) continue;
+    Vec<T> g = Vec<T>::zero();
+    if (hit) {
+      g = Vec<T>::load(dy + (((int64_t)n * OH + ih / s) * OW + iw / s) * ldy + cg * VN);
+      if (acc) {
+        Vec<T> o = Vec<T>::load(dx + p * ldx + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) g.v[j] += o.v[j];
+      }
+    }
+    g.store(dx + p * ldx + cg * VN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Click map + NHWC4 packing.  No fast-math: the table holds float32 subnormals.
 // ------------------------------------------------------------------------------------------
@@ -890,6 +941,32 @@ int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int ac
         (float)dx->w / (float)dy->w, accumulate, total);
   })
   BASI_CHECK_LAUNCH("resize_nearest_bwd");
+  return BASI_OK;
+}
+
+int basi_subsample_fwd(const basi_tensor* x, int stride, const basi_tensor* y, void* stream) {
+  BASI_CHECK_ARG(x && y && stride >= 1 && vec_ok(x) && vec_ok(y) && x->dtype == y->dtype && x->c == y->c &&
+                     x->n == y->n && y->h == (x->h + stride - 1) / stride && y->w == (x->w + stride - 1) / stride,
+                 "subsample fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    int64_t total = pixels(y) * (y->c / Vec<T>::N);
+    basi::launch(subsample_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld,
+                 x->h, x->w, x->c, stride, (T*)y->ptr, y->ld, y->h, y->w, total);
+  })
+  BASI_CHECK_LAUNCH("subsample_fwd");
+  return BASI_OK;
+}
+
+int basi_subsample_bwd(const basi_tensor* dy, int stride, const basi_tensor* dx, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && dx && stride >= 1 && vec_ok(dy) && vec_ok(dx) && dx->dtype == dy->dtype && dx->c == dy->c &&
+                     dx->n == dy->n && dy->h == (dx->h + stride - 1) / stride && dy->w == (dx->w + stride - 1) / stride,
+                 "subsample bwd: bad tensors");
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
+    basi::launch(subsample_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld,
+                 dy->h, dy->w, stride, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
+  })
+  BASI_CHECK_LAUNCH("subsample_bwd");
   return BASI_OK;
 }
 

@@ -557,3 +557,40 @@ def test_resize_nearest_neighbor(dtype, ih, oh, Cc):
     xt = nchw(x).double().requires_grad_(True)
     (O.resize_nearest(xt, (oh, ow)) * nchw(dy).double()).sum().backward()
     assert rel_err(host(dxa) - 0.5, nhwc(xt.grad)) < (1e-6 if dtype == "f32" else 2e-2)
+
+
+# ------------------------------------------------------------------ strided 1x1 conv = subsample + 1x1 conv (bit exact)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("shape,s", [((2, 80, 80, 128), 2), ((1, 7, 9, 8), 2), ((2, 10, 10, 16), 3), ((1, 4, 4, 8), 1)])
+def test_subsample_and_adjoint_bit_exact(dtype, shape, s):
+    from gpu_util import act, bf16_round, call, empty_act, host
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    rng = np.random.RandomState(5)
+    x = _u(rng, *shape)
+    if dtype == "bf16":
+        x = bf16_round(x)
+    B, H, W, Cc = shape
+    oh, ow = -(-H // s), -(-W // s)
+    xa = act(x, td)
+    ya = empty_act((B, oh, ow, Cc), td)
+    call("basi_subsample_fwd", xa.ref, s, ya.ref)
+    assert np.array_equal(host(ya), x[:, ::s, ::s, :])
+    dy = _u(rng, B, oh, ow, Cc)
+    if dtype == "bf16":
+        dy = bf16_round(dy)
+    dya = act(dy, td)
+    dxa = empty_act(shape, td, fill=7.0)        # stale contents must be overwritten when accumulate == 0
+    call("basi_subsample_bwd", dya.ref, s, dxa.ref, 0)
+    want = np.zeros(shape, np.float32)
+    want[:, ::s, ::s, :] = dy
+    assert np.array_equal(host(dxa), want)
+    base = _u(rng, *shape)
+    if dtype == "bf16":
+        base = bf16_round(base)
+    dxb = act(base, td)
+    call("basi_subsample_bwd", dya.ref, s, dxb.ref, 1)
+    want = base.copy()
+    want[:, ::s, ::s, :] += dy
+    if dtype == "bf16":
+        want = bf16_round(want)
+    assert np.array_equal(host(dxb), want)
