@@ -2,6 +2,8 @@
 // path: fprop, dgrad (adjoint w.r.t. input) and wgrad (adjoint w.r.t. HWIO weights), plus the
 // skinny GEMMs of the attention-class head.  This is the exact-fp32 path (parity mode) and the
 // fallback for layers the tcgen05 path does not take (Cin=4 stem, strided 1x1, tiny heads).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace basi {
@@ -534,6 +536,121 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Stem convolution conv1_1_3x3_s2 (BAISPSPNet.py:274): Cin = 4 (RGB + click map) is too narrow for the GEMM tiles
+// above (K = 36) and for a TMA box, but the whole filter bank fits in shared memory.  fprop: one thread per
+// (output pixel, 8 output channels); the 9 float4 input loads are shared by the 4..8 lanes of a pixel and the
+// weights are shared-memory broadcasts.  wgrad: lane = output channel, a warp walks pixels and keeps the 36 x NC
+// partial sums in registers; block-level reduction in shared memory, then one atomic per weight per block.
+// ------------------------------------------------------------------------------------------
+struct StemConv {
+  const float* X; const void* Y; const float* W; float* dW;
+  int N, IH, IW, OH, OW, ldy;
+  int stride, pad_t, pad_l, relu;
+  int64_t M;     // N*OH*OW
+};
+
+template <typename TD, int COUT>
+__global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
+  __shared__ __align__(16) float ws[36 * COUT];
+  for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) ws[i] = g.W[i];
+  __syncthreads();
+  constexpr int CG = COUT / 8;
+  const int64_t total = g.M * CG;
+  TD* Y = (TD*)g.Y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t p = i / CG;
+    const int ow = (int)(p % g.OW);
+    const int64_t t = p / g.OW;
+    const int oh = (int)(t % g.OH);
+    const int n = (int)(t / g.OH);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = ih0 + r;
+      const bool rok = (unsigned)ih < (unsigned)g.IH;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int iw = iw0 + q;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && (unsigned)iw < (unsigned)g.IW)
+          xv = __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)n * g.IH + ih) * g.IW + iw) * 4));
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float* wp = ws + ((r * 3 + q) * 4 + c) * COUT + cg * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(xs[c], w0.x, acc[0]); acc[1] = fmaf(xs[c], w0.y, acc[1]);
+          acc[2] = fmaf(xs[c], w0.z, acc[2]); acc[3] = fmaf(xs[c], w0.w, acc[3]);
+          acc[4] = fmaf(xs[c], w1.x, acc[4]); acc[5] = fmaf(xs[c], w1.y, acc[5]);
+          acc[6] = fmaf(xs[c], w1.z, acc[6]); acc[7] = fmaf(xs[c], w1.w, acc[7]);
+        }
+      }
+    }
+    if (g.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    TD* yp = Y + p * g.ldy + cg * 8;
+    const float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+    store4<TD>(yp, lo);
+    store4<TD>(yp + 4, hi);
+  }
+}
+
+template <typename TG, int COUT>
+__global__ void __launch_bounds__(256, 3) stem_wgrad_kernel(const StemConv g) {
+  constexpr int NC = COUT / 32;
+  __shared__ float red[36 * COUT];
+  for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const TG* G = (const TG*)g.Y;
+  float acc[36 * NC];
+#pragma unroll
+  for (int j = 0; j < 36 * NC; ++j) acc[j] = 0.f;
+  for (int64_t p = warp; p < g.M; p += nwarps) {
+    const int ow = (int)(p % g.OW);
+    const int64_t t = p / g.OW;
+    const int oh = (int)(t % g.OH);
+    const int n = (int)(t / g.OH);
+    float gv[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) gv[j] = to_f32(G[p * g.ldy + lane + 32 * j]);
+    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = ih0 + r;
+      const bool rok = (unsigned)ih < (unsigned)g.IH;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int iw = iw0 + q;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && (unsigned)iw < (unsigned)g.IW)
+          xv = __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)n * g.IH + ih) * g.IW + iw) * 4));
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < NC; ++j)
+            acc[((r * 3 + q) * 4 + c) * NC + j] = fmaf(xs[c], gv[j], acc[((r * 3 + q) * 4 + c) * NC + j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) atomicAdd(&red[k * COUT + lane + 32 * j], acc[k * NC + j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) atomicAdd(g.dW + i, red[i]);
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace basi
@@ -549,6 +666,21 @@ static int check_conv(const basi_conv_desc* d, const basi_tensor* x, const basi_
   BASI_CHECK_ARG((y->h - 1) * d->stride - d->pad_t < x->h && (y->w - 1) * d->stride - d->pad_l < x->w,
                  "%s: output larger than the padded input allows", who);
   return BASI_OK;
+}
+
+// conv1_1-shaped problem: fp32 NHWC4 input, 3x3, dilation 1, 32 or 64 output channels
+static bool stem_shape(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  return x->dtype == BASI_F32 && x->c == 4 && x->ld == 4 && aligned16(x->ptr) && d->kh == 3 && d->kw == 3 &&
+         d->dil == 1 && (y->c == 32 || y->c == 64) && y->ld % 4 == 0 && aligned16(y->ptr) &&
+         getenv("BASI_NO_STEM") == nullptr;
+}
+static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  StemConv s{};
+  s.X = (const float*)x->ptr; s.Y = y->ptr;
+  s.N = x->n; s.IH = x->h; s.IW = x->w; s.OH = y->h; s.OW = y->w; s.ldy = y->ld;
+  s.stride = d->stride; s.pad_t = d->pad_t; s.pad_l = d->pad_l;
+  s.M = pixels(y);
+  return s;
 }
 
 template <int MODE>
@@ -568,6 +700,22 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
   int rc = check_conv(d, x, y, "conv_fprop");
   if (rc) return rc;
   BASI_CHECK_ARG(w, "conv_fprop: null weights");
+  if (stem_shape(d, x, y) && !bias) {
+    StemConv s = stem_args(d, x, y);
+    s.W = w; s.relu = d->relu;
+    int64_t total = s.M * (y->c / 8);
+    int grid = grid_for(total, 256, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (y->dtype == BASI_BF16) {
+      if (y->c == 32) basi::launch(stem_fprop_kernel<bf16, 32>, grid, 256, 0, st, s);
+      else basi::launch(stem_fprop_kernel<bf16, 64>, grid, 256, 0, st, s);
+    } else {
+      if (y->c == 32) basi::launch(stem_fprop_kernel<float, 32>, grid, 256, 0, st, s);
+      else basi::launch(stem_fprop_kernel<float, 64>, grid, 256, 0, st, s);
+    }
+    BASI_CHECK_LAUNCH("conv_fprop(stem)");
+    return BASI_OK;
+  }
   GemmConv g{};
   g.S = x->ptr; g.D = y->ptr; g.W = w; g.bias = bias;
   g.N = x->n; g.SH = x->h; g.SW = x->w; g.SC = x->c; g.lds = x->ld;
@@ -610,6 +758,21 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   int rc = check_conv(d, x, dy, "conv_wgrad");
   if (rc) return rc;
   BASI_CHECK_ARG(dw, "conv_wgrad: null dw");
+  if (stem_shape(d, x, dy) && !dbias) {
+    StemConv s = stem_args(d, x, dy);
+    s.dW = dw;
+    int grid = basi::sm_count() * 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dy->dtype == BASI_BF16) {
+      if (dy->c == 32) basi::launch(stem_wgrad_kernel<bf16, 32>, grid, 256, 0, st, s);
+      else basi::launch(stem_wgrad_kernel<bf16, 64>, grid, 256, 0, st, s);
+    } else {
+      if (dy->c == 32) basi::launch(stem_wgrad_kernel<float, 32>, grid, 256, 0, st, s);
+      else basi::launch(stem_wgrad_kernel<float, 64>, grid, 256, 0, st, s);
+    }
+    BASI_CHECK_LAUNCH("conv_wgrad(stem)");
+    return BASI_OK;
+  }
   WgradConv g{};
   g.X = x->ptr; g.G = dy->ptr; g.dW = dw;
   g.N = x->n; g.IH = x->h; g.IW = x->w; g.Cin = x->c; g.ldx = x->ld;

@@ -594,3 +594,34 @@ def test_subsample_and_adjoint_bit_exact(dtype, shape, s):
     if dtype == "bf16":
         want = bf16_round(want)
     assert np.array_equal(host(dxb), want)
+
+
+# ------------------------------------------------------------------ conv1_1 stem kernels (fp32 NHWC4 input, Cout 32 / 64)
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("cout,H,W,s,B", [(32, 64, 64, 2, 2), (64, 33, 47, 2, 1), (32, 17, 9, 1, 3), (32, 320, 320, 2, 2)])
+def test_stem_conv_fprop_wgrad(out_dtype, cout, H, W, s, B):
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    from basi_b200._lib import ConvDesc
+    rng = np.random.RandomState(cout + H)
+    x = _u(rng, B, H, W, 4)
+    w = (_u(rng, 3, 3, 4, cout) / 6.0).astype(np.float32)
+    xt = nchw(x).double()
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    y_ref = O.conv2d(xt, wt, s, "SAME", 1, None)
+    oh, ow = y_ref.shape[2], y_ref.shape[3]
+    pt, pl = O.tf_same_pad(H, 3, s, 1)[0], O.tf_same_pad(W, 3, s, 1)[0]
+    desc = ConvDesc(3, 3, s, 1, pt, pl, 0)
+    tdt = torch.float32 if out_dtype == "f32" else torch.bfloat16
+    xa, ya = act(x), empty_act((B, oh, ow, cout), tdt, fill=7.0)
+    wd = dev(w)
+    call("basi_conv_fprop", C.byref(desc), xa.ref, wd.data_ptr(), None, ya.ref)
+    tol = F32_TOL if out_dtype == "f32" else BF16_TOL
+    assert rel_err(host(ya), nhwc(y_ref.detach())) < tol
+    dy = _u(rng, B, oh, ow, cout)
+    if out_dtype == "bf16":
+        dy = bf16_round(dy)
+    (y_ref * nchw(dy).double()).sum().backward()
+    dya = act(dy, tdt)
+    dw = torch.full((3, 3, 4, cout), 0.5, device="cuda:0")          # wgrad accumulates onto dw
+    call("basi_conv_wgrad", C.byref(desc), xa.ref, dya.ref, dw.data_ptr(), None)
+    assert rel_err(host(dw) - 0.5, wt.grad.numpy()) < 1e-4
