@@ -120,6 +120,15 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
                       const float* coef, int relu_from_x, const basi_tensor* dx, const basi_tensor* dres,
                       int dres_accumulate, void* stream);
 
+/* Resident backward: basi_bn_bwd_reduce + basi_bn_bwd_apply (no stored-output mask, no residual) in ONE cooperative
+ * launch that keeps dout and x in shared memory between the two phases (reads each once).  Needs dense rows
+ * (ld == c) and a tensor small enough that 2 * bytes(x) / #SMs fits in shared memory; query with
+ * basi_bn_bwd_fused_supported (1 = yes).  `barrier` is a zero-initialised grid-barrier word; `coef` may be NULL. */
+int basi_bn_bwd_fused_supported(const basi_tensor* x);
+int basi_bn_bwd_fused(const basi_tensor* dout, const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums,
+                      double count, float* dgamma, float* dbeta, float* coef, uint32_t* barrier,
+                      const basi_tensor* dx, void* stream);
+
 /* ---- A8: Network.max_pool 3x3 s2 SAME (:152-155, :269), Network.avg_pool k=s VALID (:157-160) ---- */
 int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream);
 int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,

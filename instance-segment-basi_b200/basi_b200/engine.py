@@ -65,7 +65,7 @@ class _BNRec(object):
 
 class Engine(object):
     def __init__(self, net, batch_size, precision="bf16", training=True, loss=None, device=None, use_tc=True,
-                 dry_run=False, fuse_bn_stats=True, overlap_wgrad=True):
+                 dry_run=False, fuse_bn_stats=True, overlap_wgrad=True, fuse_bn_bwd=True):
         """net: a built Network; loss: dict(kind='bce'|'softmax', pos_weight, class_weight, seg, cls).
 
         dry_run=True only builds the plan (buffers on the host, nothing can be executed): used by the
@@ -97,6 +97,8 @@ class Engine(object):
         self._tc_producer = {}
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
+        self.fuse_bn_bwd = bool(fuse_bn_bwd)
+        self.fused_bn_bwd = 0
         self._tc_weights = []
         self._pack_table = None
         self._zero_grads = []    # gradient buffers that are pre-zeroed every step (concat buffers)
@@ -584,6 +586,15 @@ class Engine(object):
                 dres = op["res"].grad.ref
             nb = self._nbytes(x)
             nin = 3 if mask is not None else 2
+            if (mask is None and dres is None and self.fuse_bn_bwd and not self.dry_run
+                    and _lib.load().basi_bn_bwd_fused_supported(x.ref) == 1
+                    and dout.desc.ld == dout.desc.c and dx.desc.ld == dx.desc.c):
+                # reduce + apply in one cooperative launch, dout and x resident in shared memory between the phases
+                self._call(self.bwd, "basi_bn_bwd_fused", dout.ref, x.ref, rec.bnp.data_ptr(), from_x, rec.dsums,
+                           C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
+                           rec.cnt_b, dx.ref, bytes=nb * 3, writes=[rec.gamma, rec.beta])
+                self.fused_bn_bwd += 1
+                continue
             self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), from_x, rec.dsums,
                        C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
                        rec.cnt_b, bytes=nb * nin, writes=[rec.gamma, rec.beta])

@@ -741,6 +741,234 @@ static bool launch_bwd_apply_stream(const basi_tensor* dout, const basi_tensor* 
   return true;
 }
 
+// ==========================================================================================================
+// Resident backward: reduce + apply in ONE cooperative launch.  The pixel rows are split evenly over one CTA per SM;
+// each CTA bulk-copies its slab of dout and x into shared memory ONCE (the 148 x ~200 KB of shared memory hold both
+// tensors of every plain BN+ReLU layer from conv2 on), reduces its slab, meets the other CTAs at a grid barrier,
+// then computes dx from the resident copies.  HBM traffic: read 2 tensors + write 1, instead of read 4 + write 1
+// for the reduce/apply pair, and one launch + one tail instead of two.
+// ==========================================================================================================
+struct ResidentArgs {
+  const char* dout;
+  const char* x;
+  char* dx;
+  long long R;
+  int row_bytes;       // C * sizeof(T) == blockDim.x * 16
+  int rows_per_cta;
+  int chunk_rows;      // rows per bulk copy (per tensor)
+  int n_chunks;
+};
+
+__device__ __forceinline__ void grid_barrier_thread0(unsigned int* ctr) {
+  __threadfence();
+  const unsigned int old = atomicAdd(ctr, 1u);
+  const unsigned int target = (old / gridDim.x + 1u) * gridDim.x;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (clock64() - t0 > 8000000000LL) {
+      printf("basi: grid barrier timed out (block %d, counter %u, target %u)\n", blockIdx.x, v, target);
+      __trap();
+    }
+  }
+  __threadfence();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int relu_from_x, int C,
+                       double* __restrict__ dsums, double count, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ coef, unsigned int* gbar) {
+  extern __shared__ __align__(128) uint8_t rs[];
+  constexpr int VN = Pack<T>::N;
+  const int tx = threadIdx.x, ty = threadIdx.y, by = blockDim.y;
+  const int tid = ty * blockDim.x + tx;
+  const size_t slab = (size_t)a.rows_per_cta * a.row_bytes;
+  uint8_t* s_dout = rs;
+  uint8_t* s_x = rs + slab;
+  float* red = reinterpret_cast<float*>(rs + 2 * slab);        // [by][C][2]
+  float* coef_s = red + (size_t)by * C * 2;                    // [2][C]
+  const uint32_t bar0 = smem_u32(coef_s + 2 * C);
+  const long long row0 = (long long)blockIdx.x * a.rows_per_cta;
+  long long left = a.R - row0;
+  const int rows = left <= 0 ? 0 : (left < a.rows_per_cta ? (int)left : a.rows_per_cta);
+  if (tid == 0) {
+    for (int k = 0; k < a.n_chunks; ++k) mbar_init(bar0 + 8 * k, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < a.n_chunks; ++k) {
+      const int r0 = k * a.chunk_rows;
+      const int n = min(a.chunk_rows, rows - r0);
+      if (n <= 0) break;
+      const uint32_t bytes = (uint32_t)n * a.row_bytes;
+      mbar_expect_tx(bar0 + 8 * k, 2 * bytes);
+      bulk_load_1d(smem_u32(s_dout + (size_t)r0 * a.row_bytes), a.dout + (row0 + r0) * a.row_bytes, bytes, bar0 + 8 * k);
+      bulk_load_1d(smem_u32(s_x + (size_t)r0 * a.row_bytes), a.x + (row0 + r0) * a.row_bytes, bytes, bar0 + 8 * k);
+    }
+  }
+  const int c0 = tx * VN;
+  float fs[VN], fq[VN], mean[VN], A[VN], beta[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    fs[i] = fq[i] = 0.f;
+    mean[i] = bnp[c0 + i];
+    A[i] = bnp[2 * C + c0 + i];
+    beta[i] = bnp[3 * C + c0 + i];
+  }
+  // ---- phase 1: per-channel sums of dy and dy * (x - mean) over the resident slab
+  for (int k = 0; k < a.n_chunks; ++k) {
+    const int r0 = k * a.chunk_rows;
+    const int n = min(a.chunk_rows, rows - r0);
+    if (n <= 0) break;
+    mbar_wait(bar0 + 8 * k, 0);
+    for (int rr = r0 + ty; rr < r0 + n; rr += by) {
+      Pack<T> d, xv;
+      d.load(reinterpret_cast<const T*>(s_dout + (size_t)rr * a.row_bytes + tx * 16));
+      xv.load(reinterpret_cast<const T*>(s_x + (size_t)rr * a.row_bytes + tx * 16));
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float xc = xv.get(i) - mean[i];
+        float dy = d.get(i);
+        if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+        fs[i] += dy;
+        fq[i] = fmaf(dy, xc, fq[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    red[((size_t)ty * C + c0 + i) * 2] = fs[i];
+    red[((size_t)ty * C + c0 + i) * 2 + 1] = fq[i];
+  }
+  __syncthreads();
+  double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
+  for (int c = tid; c < C; c += 256) {
+    double s1 = 0, s2 = 0;
+    for (int y = 0; y < by; ++y) {
+      s1 += (double)red[((size_t)y * C + c) * 2];
+      s2 += (double)red[((size_t)y * C + c) * 2 + 1];
+    }
+    atomicAdd(rep + c, s1);
+    atomicAdd(rep + C + c, s2 * (double)bnp[C + c]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) grid_barrier_thread0(gbar);
+  __syncthreads();
+  // ---- every CTA turns the (now final) sums into the two per-channel coefficients; CTA 0 publishes the gradients
+  for (int c = tid; c < C; c += 256) {
+    double s1 = 0, s2 = 0;
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      s1 += __ldcg(dsums + (size_t)r * 2 * C + c);
+      s2 += __ldcg(dsums + (size_t)r * 2 * C + C + c);
+    }
+    const float k1 = (float)(s1 / count), k2 = (float)(s2 / count);
+    coef_s[c] = k1;
+    coef_s[C + c] = k2;
+    if (blockIdx.x == 0) {
+      dbeta[c] += (float)s1;
+      dgamma[c] += (float)s2;
+      if (coef) {
+        coef[c] = k1;
+        coef[C + c] = k2;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: dx = scale * (dy - mean(dy)) - (x - mean) * scale * istd * mean(dy * xhat), from shared memory
+  float Bc[VN], Cc[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    Bc[i] = A[i] * coef_s[c0 + i];
+    Cc[i] = A[i] * bnp[C + c0 + i] * coef_s[C + c0 + i];
+  }
+  T* dxp = reinterpret_cast<T*>(a.dx + row0 * a.row_bytes);
+  for (int rr = ty; rr < rows; rr += by) {
+    Pack<T> d, xv, o;
+    d.load(reinterpret_cast<const T*>(s_dout + (size_t)rr * a.row_bytes + tx * 16));
+    xv.load(reinterpret_cast<const T*>(s_x + (size_t)rr * a.row_bytes + tx * 16));
+#pragma unroll
+    for (int i2 = 0; i2 < VN / 2; ++i2) {
+      float res[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * i2 + h;
+        const float xc = xv.get(i) - mean[i];
+        float dy = d.get(i);
+        if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+        res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
+      }
+      o.set2(i2, res[0], res[1]);
+    }
+    o.store(dxp + (size_t)rr * (a.row_bytes / sizeof(T)) + c0);
+  }
+}
+
+struct ResidentGeom {
+  bool ok;
+  int grid, bx, by, rows_per_cta, chunk_rows, n_chunks;
+  size_t smem;
+};
+static bool resident_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("BASI_BN_NO_RESIDENT") ? 1 : 0;
+  return v == 1;
+}
+static ResidentGeom resident_geom(int64_t R, int C, int es) {
+  ResidentGeom g{};
+  const int row_bytes = C * es;
+  const int bx = row_bytes / 16;
+  if (resident_disabled() || row_bytes % 16 || bx < 1 || bx > 256 || (bx & (bx - 1))) return g;
+  const int G = sm_count();
+  if (R < (int64_t)G * 8) return g;
+  const int64_t rpc = (R + G - 1) / G;
+  const int by = 256 / bx;
+  int chunk_rows = (16 * 1024) / row_bytes;
+  if (chunk_rows < 1) chunk_rows = 1;
+  const int64_t n_chunks = (rpc + chunk_rows - 1) / chunk_rows;
+  const size_t smem = 2 * (size_t)rpc * row_bytes + (size_t)by * C * 2 * sizeof(float) + 2 * (size_t)C * sizeof(float) +
+                      8 * (size_t)n_chunks + 128;
+  if (smem > 220 * 1024 || n_chunks > 64) return g;
+  g.ok = true;
+  g.grid = (int)((R + rpc - 1) / rpc);
+  g.bx = bx; g.by = by;
+  g.rows_per_cta = (int)rpc;
+  g.chunk_rows = chunk_rows;
+  g.n_chunks = (int)n_chunks;
+  g.smem = smem;
+  return g;
+}
+static bool dense_rows(const basi_tensor* t) { return t->ld == t->c; }
+
+template <typename T>
+static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, const basi_tensor* x, const float* bnp,
+                                int relu_from_x, double* dsums, double count, float* dgamma, float* dbeta, float* coef,
+                                uint32_t* gbar, const basi_tensor* dx, cudaStream_t st) {
+  ResidentArgs a{};
+  a.dout = (const char*)dout->ptr; a.x = (const char*)x->ptr; a.dx = (char*)dx->ptr;
+  a.R = pixels(x);
+  a.row_bytes = x->c * (int)sizeof(T);
+  a.rows_per_cta = g.rows_per_cta; a.chunk_rows = g.chunk_rows; a.n_chunks = g.n_chunks;
+  allow_smem(bn_bwd_resident_kernel<T>, g.smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g.grid);
+  cfg.blockDim = dim3(g.bx, g.by);
+  cfg.dynamicSmemBytes = g.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, bn_bwd_resident_kernel<T>, a, bnp, relu_from_x, (int)x->c, dsums, count, dgamma, dbeta, coef,
+                     (unsigned int*)gbar);
+}
+
 }  // namespace basi
 
 using namespace basi;
@@ -860,6 +1088,28 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
         dres_accumulate, R, x->c);
   })
   BASI_CHECK_LAUNCH("bn_bwd_apply");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_fused_supported(const basi_tensor* x) {
+  if (!x || !vec_ok(x) || !dense_rows(x)) return 0;
+  return resident_geom(pixels(x), x->c, x->dtype == BASI_F32 ? 4 : 2).ok ? 1 : 0;
+}
+
+int basi_bn_bwd_fused(const basi_tensor* dout, const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums,
+                      double count, float* dgamma, float* dbeta, float* coef, uint32_t* barrier,
+                      const basi_tensor* dx, void* stream) {
+  BASI_CHECK_ARG(dout && x && dx && bnp && dsums && dgamma && dbeta && barrier && count > 0 && vec_ok(dout) &&
+                     vec_ok(x) && vec_ok(dx) && same_shape(dout, x) && same_shape(dx, x) && dout->dtype == x->dtype &&
+                     dx->dtype == x->dtype && dense_rows(dout) && dense_rows(x) && dense_rows(dx),
+                 "bn_bwd_fused: bad dout/x/dx (dense rows required)");
+  ResidentGeom g = resident_geom(pixels(x), x->c, x->dtype == BASI_F32 ? 4 : 2);
+  BASI_CHECK_ARG(g.ok, "bn_bwd_fused: tensor does not fit the resident kernel (see basi_bn_bwd_fused_supported)");
+  DISPATCH_T(x->dtype, {
+    launch_bwd_resident<T>(g, dout, x, bnp, relu_from_x, dsums, count, dgamma, dbeta, coef, barrier, dx,
+                           (cudaStream_t)stream);
+  })
+  BASI_CHECK_LAUNCH("bn_bwd_fused");
   return BASI_OK;
 }
 

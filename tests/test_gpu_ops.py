@@ -625,3 +625,62 @@ def test_stem_conv_fprop_wgrad(out_dtype, cout, H, W, s, B):
     dw = torch.full((3, 3, 4, cout), 0.5, device="cuda:0")          # wgrad accumulates onto dw
     call("basi_conv_wgrad", C.byref(desc), xa.ref, dya.ref, dw.data_ptr(), None)
     assert rel_err(host(dw) - 0.5, wt.grad.numpy()) < 1e-4
+
+
+# ------------------------------------------------------------------ resident (cooperative) BN backward
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", [(16, 40, 40, 128), (16, 40, 40, 256), (4, 80, 80, 32), (3, 37, 41, 64), (2, 33, 35, 8)])
+def test_batch_norm_backward_resident(dtype, relu, shape):
+    """basi_bn_bwd_fused == basi_bn_bwd_reduce + basi_bn_bwd_apply, and both match autograd of the oracle BN."""
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err, rel_l2
+    from basi_b200 import _lib
+    B, H, W, Cc = shape
+    rng = np.random.RandomState(3)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    x = rnd(_u(rng, *shape) * 2 + 0.5)
+    dout = rnd(_u(rng, *shape))
+    gamma, beta = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    xt = nchw(x).double().requires_grad_(True)
+    g1, b1 = torch.from_numpy(gamma).double().requires_grad_(True), torch.from_numpy(beta).double().requires_grad_(True)
+    y = O.batch_norm(xt, g1, b1)
+    if relu:
+        y = torch.relu(y)
+    (y * nchw(dout).double()).sum().backward()
+    R = float(B * H * W)
+    xa, da = act(x, tdt), act(dout, tdt)
+    if _lib.load().basi_bn_bwd_fused_supported(xa.ref) != 1:
+        pytest.skip("tensor does not fit the resident kernel on this device")
+    sums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
+    bnp = torch.zeros(4 * Cc, device="cuda:0")
+    gd, bd = dev(gamma), dev(beta)
+    cnt = torch.zeros(8, dtype=torch.int32, device="cuda:0")
+    call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), cnt.data_ptr())
+    from_x = 1 if relu else 0
+    outs = []
+    for fused in (False, True, True):                      # twice fused: the barrier word is reused without a reset
+        dsums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
+        coef = torch.zeros(2 * Cc, device="cuda:0")
+        dgamma, dbeta = torch.full((Cc,), 0.25, device="cuda:0"), torch.full((Cc,), -0.5, device="cuda:0")
+        dxa = empty_act(shape, tdt, fill=5.0)
+        if fused:
+            call("basi_bn_bwd_fused", da.ref, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(), C.c_double(R),
+                 dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 16, dxa.ref)
+        else:
+            call("basi_bn_bwd_reduce", da.ref, None, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(), C.c_double(R),
+                 dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 8)
+            call("basi_bn_bwd_apply", da.ref, None, xa.ref, bnp.data_ptr(), coef.data_ptr(), from_x, dxa.ref, None, 0)
+        outs.append((host(dxa), host(dgamma) - 0.25, host(dbeta) + 0.5, host(coef)))
+    btol = 2e-4 if dtype == "f32" else 3e-2
+    for dx, dg, db, _ in outs:
+        assert rel_l2(dx, nhwc(xt.grad)) < btol
+        assert rel_err(dg, g1.grad.numpy()) < btol
+        assert rel_err(db, b1.grad.numpy()) < btol
+    # fused vs pair: same arithmetic up to the summation order of the per-channel sums
+    ptol = 1e-5 if dtype == "f32" else 1e-2
+    for k in (1, 2):
+        assert rel_err(outs[k][0], outs[0][0]) < ptol
+        assert rel_err(outs[k][1], outs[0][1]) < 1e-5 and rel_err(outs[k][2], outs[0][2]) < 1e-5
+        assert rel_err(outs[k][3], outs[0][3]) < 1e-5
