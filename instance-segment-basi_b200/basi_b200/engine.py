@@ -17,6 +17,7 @@ our kernels reached through ``_lib.call``.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -89,7 +90,7 @@ class Engine(object):
         self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
-        self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run
+        self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run and not os.environ.get("BASI_NO_OVERLAP")
         self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
         self._side_dirty = False
         self._tc_plans = []

@@ -964,7 +964,7 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("BASI_BN_RESIDENT_NOCOOP") ? 0 : 1;   // experiment only: without the attribute co-residency is not guaranteed
   cudaLaunchKernelEx(&cfg, bn_bwd_resident_kernel<T>, a, bnp, relu_from_x, (int)x->c, dsums, count, dgamma, dbeta, coef,
                      (unsigned int*)gbar);
 }

@@ -552,95 +552,129 @@ struct StemConv {
 
 template <typename TD, int COUT>
 __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
+  // thread = (4 consecutive output pixels of one row, 8 output channels): every weight fetched from shared memory
+  // feeds 4 FMAs, and neighbouring pixels share their input columns
   __shared__ __align__(16) float ws[36 * COUT];
   for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) ws[i] = g.W[i];
   __syncthreads();
-  constexpr int CG = COUT / 8;
-  const int64_t total = g.M * CG;
+  constexpr int CG = COUT / 8, PX = 4;
+  const int owg = (g.OW + PX - 1) / PX;
+  const int total = g.N * g.OH * owg * CG;
   TD* Y = (TD*)g.Y;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const int64_t p = i / CG;
-    const int ow = (int)(p % g.OW);
-    const int64_t t = p / g.OW;
-    const int oh = (int)(t % g.OH);
-    const int n = (int)(t / g.OH);
-    float acc[8];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    int t = i / CG;
+    const int ow0 = (t % owg) * PX;
+    t /= owg;
+    const int oh = t % g.OH;
+    const int n = t / g.OH;
+    float acc[PX][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+    for (int px = 0; px < PX; ++px)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[px][j] = 0.f;
+    const int ih0 = oh * g.stride - g.pad_t;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = ih0 + r;
       const bool rok = (unsigned)ih < (unsigned)g.IH;
+      const float* xrow = g.X + ((int64_t)n * g.IH + ih) * g.IW * 4;
+      float4 xv[PX][3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int iw = iw0 + q;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && (unsigned)iw < (unsigned)g.IW)
-          xv = __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)n * g.IH + ih) * g.IW + iw) * 4));
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int iw = (ow0 + px) * g.stride - g.pad_l + q;
+          xv[px][q] = (rok && (unsigned)iw < (unsigned)g.IW) ? __ldg(reinterpret_cast<const float4*>(xrow + iw * 4))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float* wp = ws + ((r * 3 + q) * 4 + c) * COUT + cg * 8;
           const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
-          acc[0] = fmaf(xs[c], w0.x, acc[0]); acc[1] = fmaf(xs[c], w0.y, acc[1]);
-          acc[2] = fmaf(xs[c], w0.z, acc[2]); acc[3] = fmaf(xs[c], w0.w, acc[3]);
-          acc[4] = fmaf(xs[c], w1.x, acc[4]); acc[5] = fmaf(xs[c], w1.y, acc[5]);
-          acc[6] = fmaf(xs[c], w1.z, acc[6]); acc[7] = fmaf(xs[c], w1.w, acc[7]);
-        }
-      }
-    }
-    if (g.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+          for (int px = 0; px < PX; ++px) {
+            const float xs = c == 0 ? xv[px][q].x : (c == 1 ? xv[px][q].y : (c == 2 ? xv[px][q].z : xv[px][q].w));
+            acc[px][0] = fmaf(xs, w0.x, acc[px][0]); acc[px][1] = fmaf(xs, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(xs, w0.z, acc[px][2]); acc[px][3] = fmaf(xs, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(xs, w1.x, acc[px][4]); acc[px][5] = fmaf(xs, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(xs, w1.z, acc[px][6]); acc[px][7] = fmaf(xs, w1.w, acc[px][7]);
+          }
+        }
     }
-    TD* yp = Y + p * g.ldy + cg * 8;
-    const float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
-    store4<TD>(yp, lo);
-    store4<TD>(yp + 4, hi);
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      if (ow0 + px >= g.OW) break;
+      if (g.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[px][j] = fmaxf(acc[px][j], 0.f);
+      }
+      TD* yp = Y + (((int64_t)n * g.OH + oh) * g.OW + ow0 + px) * g.ldy + cg * 8;
+      const float lo[4] = {acc[px][0], acc[px][1], acc[px][2], acc[px][3]};
+      const float hi[4] = {acc[px][4], acc[px][5], acc[px][6], acc[px][7]};
+      store4<TD>(yp, lo);
+      store4<TD>(yp + 4, hi);
+    }
   }
 }
 
 template <typename TG, int COUT>
-__global__ void __launch_bounds__(256, 3) stem_wgrad_kernel(const StemConv g) {
-  constexpr int NC = COUT / 32;
+__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const StemConv g) {
+  // lane = output channel; a warp takes 2 consecutive pixels per iteration (all their loads are issued before the
+  // FMAs) and keeps the 36 x NC partial sums in registers
+  constexpr int NC = COUT / 32, PX = 2;
   __shared__ float red[36 * COUT];
   for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const TG* G = (const TG*)g.Y;
+  const int M = (int)g.M;
   float acc[36 * NC];
 #pragma unroll
   for (int j = 0; j < 36 * NC; ++j) acc[j] = 0.f;
-  for (int64_t p = warp; p < g.M; p += nwarps) {
-    const int ow = (int)(p % g.OW);
-    const int64_t t = p / g.OW;
-    const int oh = (int)(t % g.OH);
-    const int n = (int)(t / g.OH);
-    float gv[NC];
+  for (int p0 = warp * PX; p0 < M; p0 += nwarps * PX) {
+    float gv[PX][NC];
+    int nn[PX], ih0[PX], iw0[PX];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) gv[j] = to_f32(G[p * g.ldy + lane + 32 * j]);
-    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+    for (int px = 0; px < PX; ++px) {
+      const int p = p0 + px;
+      const bool pok = p < M;
+      const int ow = p % g.OW;
+      const int t = p / g.OW;
+      const int oh = t % g.OH;
+      nn[px] = pok ? t / g.OH : -1;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) gv[px][j] = pok ? to_f32(G[(int64_t)p * g.ldy + lane + 32 * j]) : 0.f;
+      ih0[px] = oh * g.stride - g.pad_t;
+      iw0[px] = ow * g.stride - g.pad_l;
+    }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int ih = ih0 + r;
-      const bool rok = (unsigned)ih < (unsigned)g.IH;
+      float4 xv[PX][3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int iw = iw0 + q;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && (unsigned)iw < (unsigned)g.IW)
-          xv = __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)n * g.IH + ih) * g.IW + iw) * 4));
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      for (int px = 0; px < PX; ++px)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int q = 0; q < 3; ++q) {
+          const int ih = ih0[px] + r, iw = iw0[px] + q;
+          xv[px][q] = (nn[px] >= 0 && (unsigned)ih < (unsigned)g.IH && (unsigned)iw < (unsigned)g.IW)
+                          ? __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)nn[px] * g.IH + ih) * g.IW + iw) * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-          for (int j = 0; j < NC; ++j)
-            acc[((r * 3 + q) * 4 + c) * NC + j] = fmaf(xs[c], gv[j], acc[((r * 3 + q) * 4 + c) * NC + j]);
-      }
+      for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float xs[4] = {xv[px][q].x, xv[px][q].y, xv[px][q].z, xv[px][q].w};
+          const int k = r * 3 + q;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[(k * 4 + c) * NC + j] = fmaf(xs[c], gv[px][j], acc[(k * 4 + c) * NC + j]);
+        }
     }
   }
 #pragma unroll
@@ -703,7 +737,7 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
   if (stem_shape(d, x, y) && !bias) {
     StemConv s = stem_args(d, x, y);
     s.W = w; s.relu = d->relu;
-    int64_t total = s.M * (y->c / 8);
+    int64_t total = (int64_t)s.N * s.OH * ((s.OW + 3) / 4) * (y->c / 8);
     int grid = grid_for(total, 256, 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (y->dtype == BASI_BF16) {
@@ -761,7 +795,7 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   if (stem_shape(d, x, dy) && !dbias) {
     StemConv s = stem_args(d, x, dy);
     s.dW = dw;
-    int grid = basi::sm_count() * 3;
+    int grid = basi::sm_count() * 2;
     cudaStream_t st = (cudaStream_t)stream;
     if (dy->dtype == BASI_BF16) {
       if (dy->c == 32) basi::launch(stem_wgrad_kernel<bf16, 32>, grid, 256, 0, st, s);
