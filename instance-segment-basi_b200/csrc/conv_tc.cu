@@ -41,20 +41,48 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// cluster-of-2 variants: the weight tile is loaded half by each CTA of the pair and multicast to both
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                               int c2, uint16_t mask) {
+// CTA-pair (cta_group::2) variants: both CTAs of a cluster load into their own shared memory and signal the LEADER's
+// mbarrier (an address in the shared::cluster window); the leader issues one M = 256 MMA that reads both halves.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4, %5}], [%2], %6;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"(mask)
       : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -118,10 +146,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+// instruction descriptor: D=f32, A=B=bf16, M=128 (256 for a CTA pair)
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct ConvParams {
@@ -165,25 +193,33 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
   }
 }
 
-template <int BN>
+template <int BN, int MT = 1, int CL = 1>
 struct SmemLayout {
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int B_BYTES = BN * 128 / CL;   // a CTA pair holds half of the weight box in each CTA
+  static constexpr int STAGE = MT * A_BYTES + B_BYTES;
 };
 
 // ------------------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------------
-template <int BN, int CL>
+template <int BN, int CL, int MT>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
-  // CL == 2: the two CTAs of a cluster work on adjacent pixel tiles of the same channel tile in lock step; each
-  // loads its own activation box and HALF of the weight box, multicast to both (halves the weight-tile TMA requests
-  // per SM -- the main loop is bound by the TMA request rate, ~0.35 us per k-step, not by the tensor pipe).
+  // CL == 2: a CTA pair (tcgen05 cta_group::2).  The two CTAs own adjacent pixel tiles of the same channel tile;
+  // each loads its own activation box and HALF of the weight box into its own shared memory, the leader (rank 0)
+  // issues ONE M = 256 MMA per K slice that reads both CTAs' shared memory and writes both CTAs' TMEM.  The main
+  // loop is bound by shared-memory bandwidth (every operand byte is written once by TMA and read once by the MMA:
+  // 64 KB per 128x128x64 k-step at 128 B/clk = 0.27 us, measured 0.35 us); a pair moves 48 KB per CTA instead.
+  // MT == 2: one work item is TWO adjacent pixel tiles against the same weight tile: per k-step the CTA loads
+  // 2 x 16 KB of activations + one weight box and issues 2 x 4 MMAs into two TMEM accumulators.  The main loop is
+  // bound by L2 -> SM bytes (148 SMs x 32 KB per 0.37 us k-step = the ~12 TB/s L2 cap); sharing the weight box cuts
+  // the bytes per flop by 25 %.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int STAGE = SmemLayout<BN>::STAGE;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int STAGE = SmemLayout<BN, MT, CL>::STAGE;
+  static_assert(CL == 1 || MT == 1, "pairs take one pixel tile per CTA");
+  constexpr uint32_t TMEM_COLS = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
+  static_assert(2 * MT * BN <= 512, "TMEM has 512 columns");
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base slot
@@ -205,20 +241,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, CL);   // a stage is free when the MMA warps of every CTA writing into it are done
+      mbar_init(full0 + 8 * i, 1);    // pair: only the leader's is used (it expects the bytes of both CTAs)
+      mbar_init(empty0 + 8 * i, 1);   // pair: the leader's commit is multicast to both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 8);   // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * i, 8 * CL);   // one arrive per epilogue warp (pair: of both CTAs, on the leader's)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -232,8 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
   const int cid = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int ncl = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int m_groups = (p.m_tiles + CL - 1) / CL;
-  const int total_tiles = m_groups * p.n_tiles;   // loop space; pixel tile = group * CL + crank (may be a phantom)
+  const int m_groups = (p.m_tiles + CL * MT - 1) / (CL * MT);
+  // loop space; pixel tile = (group * CL + crank) * MT + sub (may be a phantom past the end)
+  const int total_tiles = m_groups * p.n_tiles;
   const int ksteps = p.taps * p.k_chunks;
 
   if (warp == 0) {
@@ -242,23 +286,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cid; t < total_tiles; t += ncl) {
-        const int nt = t % p.n_tiles, mt = (t / p.n_tiles) * CL + crank;
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        const int nt = t % p.n_tiles, mt0 = ((t / p.n_tiles) * CL + crank) * MT;
+        int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+          const int mt = mt0 + sub;
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+          w0[sub] = tw * p.TW; h0[sub] = th * p.TH; n0[sub] = tn * p.TN;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.kw, s = tap - r * p.kw;
-          const int sh = h0 + p.off_h + r * p.step, sw = w0 + p.off_w + s * p.step;
+          const int dh = p.off_h + r * p.step, dw = p.off_w + s * p.step;
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
-            const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, STAGE);
-            tma_load_4d(sa, &mapA, fb, kc * KC, sw, sh, n0);
-            if (CL == 2)
-              tma_load_3d_mc(sa + A_BYTES + crank * (BN / 2) * 128, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap,
-                             (uint16_t)3);
-            else
-              tma_load_3d(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+            if (CL == 2) {
+              // both CTAs' bytes are counted on the leader's barrier
+              const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+              if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE);
+              tma_load_4d_pair(sa, &mapA, fb, kc * KC, w0[0] + dw, h0[0] + dh, n0[0]);
+              tma_load_3d_pair(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap);
+            } else {
+              const uint32_t fb = full0 + 8 * stage;
+              mbar_expect_tx(fb, STAGE);
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub)
+                tma_load_4d(sa + sub * A_BYTES, &mapA, fb, kc * KC, w0[sub] + dw, h0[sub] + dh, n0[sub]);
+              tma_load_3d(sa + MT * A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -269,8 +324,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -279,27 +334,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
-          const uint64_t adesc = make_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_desc(sa + A_BYTES, 16, 1024);
+          const uint64_t bdesc = make_desc(sa + MT * A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint64_t adesc = make_desc(sa + sub * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+              if (CL == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+              else umma_f16(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            }
           }
-          // frees the smem slot (in both CTAs of a pair: each has written half of the other's weight tile)
-          if (CL == 2) umma_commit_mc(empty0 + 8 * stage, (uint16_t)3);
+          // frees the smem slot (pair: in both CTAs)
+          if (CL == 2) umma_commit_pair(empty0 + 8 * stage, (uint16_t)3);
           else umma_commit(empty0 + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tfull0 + 8 * acc);       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if (CL == 2) umma_commit_pair(tfull0 + 8 * acc, (uint16_t)3);
+        else umma_commit(tfull0 + 8 * acc);
       }
     }
   } else if (warp >= 4) {
@@ -311,24 +372,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool issuer = (warp == 4 && lane == 0);
     const uint32_t so_base = smem_u32(stage_out);
     const bool do_stats = p.bn_sums != nullptr;
-    int it = 0;
+    int it = 0, sidx = 0;
     for (int t = cid; t < total_tiles; t += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = t % p.n_tiles, mt = (t / p.n_tiles) * CL + crank;
+      const int nt = t % p.n_tiles;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub, ++sidx) {
+      const int mt = ((t / p.n_tiles) * CL + crank) * MT + sub;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
       const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      tc_fence_after();
       // the TMA store that last used this staging buffer must have finished reading it
-      const uint32_t so = so_base + (p.out_bufs == 2 ? (uint32_t)(it & 1) * (NBOX * A_BYTES) : 0u);
+      const uint32_t so = so_base + (p.out_bufs == 2 ? (uint32_t)(sidx & 1) * (NBOX * A_BYTES) : 0u);
       if (issuer) {
         if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + sub * BN;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         if ((c & 1) != half && BN >= 64) continue;
@@ -372,7 +436,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);          // TMEM accumulator is free again
+      if (lane == 0 && sub == MT - 1) {                                 // TMEM accumulator is free again
+        if (CL == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));
+        else mbar_arrive(tempty0 + 8 * acc);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (issuer) {
@@ -392,6 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           atomicAdd(rep + p.Cdst + nt * BN + col, (double)s2);
         }
       }
+      }   // sub
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
     if (p.bn_sums != nullptr) __threadfence();
@@ -401,7 +469,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (CL == 2) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CL == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   if (p.bn_sums != nullptr && p.bn_bnp != nullptr) {
     // last CTA to finish turns the sums into the per-channel parameters (fused finalize)
@@ -728,6 +799,7 @@ struct basi_tc_conv {
   int kind;
   int bn;
   int cluster;
+  int mt;        // pixel tiles per work item (1 or 2)
   CUtensorMap mapA, mapB, mapD;
   ConvParams cp;
   WgradParams wp;
@@ -760,15 +832,21 @@ template <int BN>
 static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (BN <= 128)
+      cudaFuncSetAttribute(conv_tc_kernel<(BN <= 128 ? BN : 128), 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024);
     attr_set = true;
   }
-  if (pl->cluster == 2)
-    basi::launch_ex(conv_tc_kernel<BN, 2>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, 2, pl->mapA, pl->mapB, pl->mapD,
-                    pl->cp);
+  if (pl->mt == 2 && BN <= 128)
+    basi::launch(conv_tc_kernel<(BN <= 128 ? BN : 128), 1, 2>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA,
+                 pl->mapB, pl->mapD, pl->cp);
+  else if (pl->cluster == 2)
+    basi::launch_ex(conv_tc_kernel<BN, 2, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, 2, pl->mapA, pl->mapB,
+                    pl->mapD, pl->cp);
   else
-    basi::launch(conv_tc_kernel<BN, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA, pl->mapB, pl->mapD,
+    basi::launch(conv_tc_kernel<BN, 1, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA, pl->mapB, pl->mapD,
                  pl->cp);
   return BASI_OK;
 }
@@ -841,9 +919,28 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       if (t256 < t128) bn = 256;
     }
     pl->bn = bn;
-    // pairs of CTAs share the weight tile (cluster of 2) whenever there are at least two pixel tiles
-    // (measured: no gain -- the main loop is not bound by weight-tile TMA requests -- so it is opt-in)
-    pl->cluster = (m_tiles >= 2 && getenv("BASI_TC_CLUSTER")) ? 2 : 1;
+    // CTA pairs (cta_group::2, M = 256): per CTA 25-50 % fewer shared-memory bytes per flop.  Measured (B=16, 40x40):
+    // conv5_4 fprop 250 -> 213 us, dgrad 170 -> 152 us (1593 TFLOP/s), conv5 3x3 41 -> 39 us; the short-K layers
+    // (conv1..conv4, <= 18 k-steps per tile) are paced by launch + epilogue and lose 10-60 % to the cluster launch
+    // and the lock-step of the two epilogues, so pairs are used for long main loops on 256-wide tiles only.
+    {
+      const int ksteps = d->kh * d->kw * ((kdim + 63) / 64);
+      const char* env_cl = getenv("BASI_TC_CLUSTER");
+      pl->cluster = (m_tiles >= 2 && bn == 256 && ksteps >= 32) ? 2 : 1;
+      if (env_cl) pl->cluster = (atoi(env_cl) >= 1 && m_tiles >= 2) ? 2 : 1;   // 1: force pairs, 0: never
+    }
+    // two pixel tiles per work item (shared weight box) when that still leaves every SM at least ~2/3 of a wave and
+    // the main loop is long enough to matter
+    pl->mt = 1;
+    {
+      const int ksteps = d->kh * d->kw * ((kdim + 63) / 64);
+      const long items2 = (long)((m_tiles + 1) / 2) * (ndim / bn);
+      const char* env_mt = getenv("BASI_TC_MT");
+      int min_k = 4;
+      if (bn <= 128 && pl->cluster == 1 && m_tiles >= 2 && items2 * 3 >= (long)sms * 2 && ksteps >= min_k) pl->mt = 2;
+      if (env_mt && atoi(env_mt) == 1) pl->mt = 1;
+      if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2) pl->mt = 2;   // tests
+    }
     rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, pl->cluster == 2 ? bn / 2 : bn);
     if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
@@ -863,18 +960,23 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       cp.off_h = d->pad_t; cp.off_w = d->pad_l; cp.step = -d->dil;
     }
     cp.accumulate = accumulate;
-    const int stage_bytes = A_BYTES + bn * 128;
+    const int stage_bytes = pl->mt * A_BYTES + bn * 128 / pl->cluster;
     // small-K layers are paced by the epilogue: give them two output staging buffers; large-K layers keep the
     // shared memory for pipeline stages
-    cp.out_bufs = (cp.taps * cp.k_chunks <= 8) ? 2 : 1;
+    cp.out_bufs = (cp.taps * cp.k_chunks <= 8 || pl->mt == 2) ? 2 : 1;
     const int out_stage = cp.out_bufs * ((bn + 63) / 64) * A_BYTES;
     const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 8 * bn * (int)sizeof(float) + 1024 /*align*/ + out_stage;
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
+    if (getenv("BASI_TC_STAGES") && atoi(getenv("BASI_TC_STAGES")) >= 2 && atoi(getenv("BASI_TC_STAGES")) < stages)
+      stages = atoi(getenv("BASI_TC_STAGES"));   // experiment: bytes in flight vs main-loop time
     cp.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
     pl->dst = (bf16*)dstt->ptr;
-    if (pl->cluster == 2) {
+    if (pl->mt == 2) {
+      const int total = ((cp.m_tiles + 1) / 2) * cp.n_tiles;     // double tiles
+      pl->grid = total < sms ? total : sms;
+    } else if (pl->cluster == 2) {
       const int total = ((cp.m_tiles + 1) / 2) * cp.n_tiles;     // pairs
       const int pairs = total < sms / 2 ? total : sms / 2;
       pl->grid = 2 * pairs;
