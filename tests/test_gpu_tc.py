@@ -23,6 +23,8 @@ TC_CASES = [
     (1, 1, 32, 128, 80, 80, 2),     # conv2 increase
     (3, 1, 32, 64, 48, 48, 1),      # conv1_3-like
     (3, 1, 64, 96, 16, 16, 2),      # Cout not a multiple of 64/128 -> partial co tile in wgrad
+    (3, 4, 256, 256, 40, 40, 6),    # conv5 3x3 at 75 pixel tiles: 256-wide tiles, 36 k-steps -> CTA pairs in auto mode,
+                                    # odd tile count (the last pair has a phantom second tile)
 ]
 
 
@@ -96,9 +98,21 @@ def _tc_case(case, sliced=False):
     return res
 
 
+# tile scheduling variants of the fprop/dgrad kernel, selected at plan creation through the environment
+TC_MODES = {
+    "auto": {},
+    "single": {"BASI_TC_MT": "1", "BASI_TC_CLUSTER": "0"},     # one 128-pixel tile per work item
+    "double": {"BASI_TC_MT": "2", "BASI_TC_CLUSTER": "0"},     # two pixel tiles share the weight box
+    "pairs": {"BASI_TC_CLUSTER": "1"},                          # cta_group::2: one M = 256 MMA per CTA pair
+}
+
+
+@pytest.mark.parametrize("mode", list(TC_MODES))
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
-def test_tc_conv_matches_oracle(case):
+def test_tc_conv_matches_oracle(case, mode, monkeypatch):
     from gpu_util import rel_err
+    for k_, v_ in TC_MODES[mode].items():
+        monkeypatch.setenv(k_, v_)
     r = _tc_case(case)
     k, d, cin, cout = case[:4]
     assert ("y" in r) == (cin % 8 == 0 and cout % 32 == 0), "fprop support does not match the documented rule"
@@ -136,15 +150,18 @@ def test_tc_refuses_unsupported_geometries():
     assert rc == -1 and b"not supported" in lib.basi_last_error()
 
 
+@pytest.mark.parametrize("mode", list(TC_MODES))
 @pytest.mark.parametrize("case", [(3, 2, 128, 128, 40, 40, 3), (1, 1, 128, 512, 40, 40, 2), (1, 1, 64, 32, 80, 80, 1)],
                          ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
-def test_tc_fprop_fused_bn_statistics(case):
+def test_tc_fprop_fused_bn_statistics(case, mode, monkeypatch):
     """The fprop epilogue accumulates per-channel sum / sum-of-squares of the stored (bf16) output and the last CTA
     finalizes [mean | istd | gamma*istd | beta]: must equal statistics computed from the stored tensor."""
     from basi_b200 import _lib
     from basi_b200._lib import ConvDesc
     from basi_b200.engine import Act
     from gpu_util import bf16_round, call, dev, host, rel_err
+    for k_, v_ in TC_MODES[mode].items():
+        monkeypatch.setenv(k_, v_)
     k, d, cin, cout, H, W, B = case
     rng = np.random.RandomState(3)
     x = bf16_round(rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32) + 0.3)
