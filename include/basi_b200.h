@@ -120,6 +120,19 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
                       const float* coef, int relu_from_x, const basi_tensor* dx, const basi_tensor* dres,
                       int dres_accumulate, void* stream);
 
+/* Packed ReLU mask for the residual junctions (relu(bn(x) + res), BAISPSPNet.py:171-173): basi_bn_apply_bits also
+ * writes one bit per output element (maskbits[row * c/8 + g] bit i <=> out[row][8*g + i] > 0) and the backward pair
+ * reads those bits instead of the stored output (1/16 of the bytes).  bf16, c % 128 == 0; query first. */
+int basi_bn_maskbits_supported(const basi_tensor* x);
+int basi_bn_apply_bits(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp, int relu,
+                       const basi_tensor* out, unsigned char* maskbits, void* stream);
+int basi_bn_bwd_reduce_bits(const basi_tensor* dout, const unsigned char* maskbits, const basi_tensor* x,
+                            const float* bnp, double* dsums, double count, float* dgamma, float* dbeta, float* coef,
+                            uint32_t* counter, void* stream);
+int basi_bn_bwd_apply_bits(const basi_tensor* dout, const unsigned char* maskbits, const basi_tensor* x,
+                           const float* bnp, const float* coef, const basi_tensor* dx, const basi_tensor* dres,
+                           int dres_accumulate, void* stream);
+
 /* Resident backward: basi_bn_bwd_reduce + basi_bn_bwd_apply (no stored-output mask, no residual) in ONE cooperative
  * launch that keeps dout and x in shared memory between the two phases (reads each once).  Needs dense rows
  * (ld == c) and a tensor small enough that 2 * bytes(x) / #SMs fits in shared memory; query with

@@ -47,6 +47,10 @@ SIGNATURES = {
     "basi_conv_fprop": [_DP, _TP, _P, _P, _TP, _P],
     "basi_conv_dgrad": [_DP, _TP, _P, _TP, _i, _P],
     "basi_conv_wgrad": [_DP, _TP, _TP, _P, _P, _P],
+    "basi_bn_maskbits_supported": [_TP],
+    "basi_bn_apply_bits": [_TP, _P, _TP, _P, _i, _TP, _P, _P],
+    "basi_bn_bwd_reduce_bits": [_TP, _P, _TP, _P, _P, _d, _P, _P, _P, _P, _P],
+    "basi_bn_bwd_apply_bits": [_TP, _P, _TP, _P, _P, _TP, _TP, _i, _P],
     "basi_bn_bwd_fused_supported": [_TP],
     "basi_bn_bwd_fused": [_TP, _TP, _P, _i, _P, _d, _P, _P, _P, _P, _TP, _P],
     "basi_subsample_fwd": [_TP, _i, _TP, _P],

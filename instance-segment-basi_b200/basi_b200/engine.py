@@ -99,6 +99,7 @@ class Engine(object):
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
+        self.mask_bits = not os.environ.get("BASI_NO_MASK_BITS")
         self.fused_bn_bwd = 0
         self._tc_weights = []
         self._pack_table = None
@@ -453,6 +454,16 @@ class Engine(object):
 
     def _emit_bnact_fwd(self, op):
         main, res, res_bn = op["main"], op["res"], op["res_bn"]
+        op["bits"] = None
+        if (res is not None and op["relu"] and self.training and self.mask_bits and not self.dry_run
+                and _lib.load().basi_bn_maskbits_supported(main.x.ref) == 1):
+            # residual junction: also emit the packed ReLU mask, the backward pair reads it instead of `out`
+            n_, h_, w_, c_ = main.x.shape
+            op["bits"] = torch.zeros(n_ * h_ * w_ * (c_ // 8), dtype=torch.uint8, device=self.device)
+            self._call(self.fwd, "basi_bn_apply_bits", main.x.ref, main.bnp.data_ptr(), res.ref,
+                       res_bn.bnp.data_ptr() if res_bn is not None else None, 1, op["out"].ref,
+                       op["bits"].data_ptr(), bytes=self._nbytes(main.x) * (3 + 1.0 / 16))
+            return
         self._call(self.fwd, "basi_bn_apply", main.x.ref, main.bnp.data_ptr(), res.ref if res is not None else None,
                    res_bn.bnp.data_ptr() if res_bn is not None else None, 1 if op["relu"] else 0, op["out"].ref,
                    bytes=self._nbytes(main.x) * (2 + (1 if res is not None else 0)))
@@ -595,6 +606,16 @@ class Engine(object):
                            C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
                            rec.cnt_b, dx.ref, bytes=nb * 3, writes=[rec.gamma, rec.beta])
                 self.fused_bn_bwd += 1
+                continue
+            if op.get("bits") is not None:
+                bits = op["bits"].data_ptr()
+                nr = 2 + 1.0 / 16
+                self._call(self.bwd, "basi_bn_bwd_reduce_bits", dout.ref, bits, x.ref, rec.bnp.data_ptr(), rec.dsums,
+                           C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
+                           rec.cnt_b, bytes=nb * nr, writes=[rec.gamma, rec.beta])
+                self._call(self.bwd, "basi_bn_bwd_apply_bits", dout.ref, bits, x.ref, rec.bnp.data_ptr(),
+                           rec.coef.data_ptr(), dx.ref, dres, dacc,
+                           bytes=nb * (nr + 1 + (0 if dres is None else (2 if dacc else 1))))
                 continue
             self._call(self.bwd, "basi_bn_bwd_reduce", dout.ref, mask, x.ref, rec.bnp.data_ptr(), from_x, rec.dsums,
                        C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),

@@ -418,15 +418,19 @@ struct StreamArgs {
   int rows_per_stage;       // multiple of blockDim.y
   int nst;
   int reverse;              // visit slabs from the end (L2 reuse after a forward-order pass)
+  const unsigned char* bits;   // optional packed ReLU mask, [R][row_bytes / 16] bytes (bit i of byte tx = channel 8*tx+i)
 };
 
-template <typename T, int NT, typename Body>
+template <typename T, int NT, bool BITS, typename Body>
 __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
   extern __shared__ __align__(128) uint8_t stream_smem[];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int SR = a.rows_per_stage;
   const int stage_bytes = SR * a.row_bytes;   // per tensor
   const uint32_t bar0 = smem_u32(stream_smem + (size_t)a.nst * NT * stage_bytes);
+  // mask bytes of a stage: one byte per 16-byte fragment, staged behind the barriers
+  const int bx = a.row_bytes / 16;
+  unsigned char* bits_s = stream_smem + (size_t)a.nst * NT * stage_bytes + (((size_t)8 * a.nst + 15) & ~(size_t)15);
   if (tid == 0) {
     for (int i = 0; i < a.nst; ++i) mbar_init(bar0 + 8 * i, 1);
     fence_mbar_init();
@@ -443,7 +447,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
     const int rows = (int)min((long long)SR, a.R - row0);
     const int st = (int)(k % a.nst);
     const uint32_t bar = bar0 + 8 * st;
-    mbar_expect_tx(bar, (uint32_t)(rows * a.row_bytes * NT));
+    mbar_expect_tx(bar, (uint32_t)(rows * a.row_bytes * NT + (BITS ? rows * bx : 0)));
+    if (BITS) bulk_load_1d(smem_u32(bits_s + (size_t)st * SR * bx), a.bits + row0 * bx, (uint32_t)(rows * bx), bar);
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const uint32_t dst = smem_u32(stream_smem + (size_t)(st * NT + t) * stage_bytes);
@@ -469,7 +474,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
       for (int t = 0; t < NT; ++t)
         f[t].load(reinterpret_cast<const T*>(stream_smem + (size_t)(st * NT + t) * stage_bytes + (size_t)rr * a.row_bytes +
                                              threadIdx.x * 16));
-      body(row0 + rr, f);
+      body(row0 + rr, f, BITS ? (unsigned)bits_s[(size_t)st * SR * bx + (size_t)rr * bx + threadIdx.x] : 0u);
     }
     __syncthreads();
   }
@@ -478,7 +483,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
 template <typename T, bool HAS_RES, bool RES_BN>
 __global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp,
                                                                  const float* __restrict__ rbnp, int relu,
-                                                                 T* __restrict__ out, int ldo, int C) {
+                                                                 T* __restrict__ out, int ldo, int C,
+                                                                 unsigned char* __restrict__ maskbits) {
   pdl_prologue();
   constexpr int VN = Pack<T>::N;
   const int c0 = threadIdx.x * VN;
@@ -494,8 +500,9 @@ __global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArg
       beta[i] += rbnp[3 * C + c0 + i];
     }
   }
-  stream_rows<T, HAS_RES ? 2 : 1>(a, [&](long long row, Pack<T>(&f)[HAS_RES ? 2 : 1]) {
+  stream_rows<T, HAS_RES ? 2 : 1, false>(a, [&](long long row, Pack<T>(&f)[HAS_RES ? 2 : 1], unsigned) {
     Pack<T> o;
+    unsigned mb = 0;
 #pragma unroll
     for (int i2 = 0; i2 < VN / 2; ++i2) {
       float v[2];
@@ -507,19 +514,31 @@ __global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArg
         v[h] = relu ? fmaxf(t, 0.f) : t;
       }
       o.set2(i2, v[0], v[1]);
+      // the mask is taken from the value AS STORED (bf16-rounded), like the backward kernels that read `out`
+      mb |= (o.get(2 * i2) > 0.f ? 1u : 0u) << (2 * i2);
+      mb |= (o.get(2 * i2 + 1) > 0.f ? 1u : 0u) << (2 * i2 + 1);
     }
     o.store(out + row * ldo + c0);
+    if (maskbits) {
+      // four neighbouring lanes (same row: blockDim.x is a multiple of 16) merge their bytes into one 32-bit store
+      const unsigned am = __activemask();
+      unsigned w = mb | (__shfl_down_sync(am, mb, 1) << 8);
+      w |= __shfl_down_sync(am, w, 2) << 16;
+      if ((threadIdx.x & 3) == 0)
+        *reinterpret_cast<unsigned*>(maskbits + row * (a.row_bytes / 16) + threadIdx.x) = w;
+    }
   });
 }
 
-// inputs: 0 = dout, 1 = x, 2 = out (HAS_OUT)
-template <typename T, bool HAS_OUT>
+// inputs: 0 = dout, 1 = x, 2 = out (MASK == 1); MASK == 2: packed mask bits instead of `out`
+template <typename T, int MASK>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, int relu_from_x, int C,
                             double* __restrict__ dsums, double count, float* __restrict__ dgamma,
                             float* __restrict__ dbeta, float* __restrict__ coef, unsigned int* counter) {
   pdl_prologue();
   constexpr int VN = Pack<T>::N;
+  constexpr bool HAS_OUT = MASK == 1;
   constexpr int NT = HAS_OUT ? 3 : 2;
   const int c0 = threadIdx.x * VN;
   float fs[VN], fq[VN], mean[VN], sgn[VN], thr[VN];
@@ -530,12 +549,13 @@ bn_bwd_reduce_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, i
     sgn[i] = bnp[2 * C + c0 + i];
     thr[i] = bnp[3 * C + c0 + i];
   }
-  stream_rows<T, NT>(a, [&](long long, Pack<T>(&f)[NT]) {
+  stream_rows<T, NT, MASK == 2>(a, [&](long long, Pack<T>(&f)[NT], unsigned mb) {
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
       const float xc = f[1].get(i) - mean[i];
       float dy = f[0].get(i);
       if (HAS_OUT) dy = f[NT - 1].get(i) > 0.f ? dy : 0.f;
+      else if (MASK == 2) dy = ((mb >> i) & 1u) ? dy : 0.f;
       else if (relu_from_x) dy = fmaf(xc, sgn[i], thr[i]) > 0.f ? dy : 0.f;
       fs[i] += dy;
       fq[i] = fmaf(dy, xc, fq[i]);
@@ -566,13 +586,14 @@ bn_bwd_reduce_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, i
   }
 }
 
-// inputs: 0 = dout, 1 = x, then out (HAS_OUT), then the old dres (DRES_ACC)
-template <typename T, bool HAS_OUT, bool DRES_ACC>
+// inputs: 0 = dout, 1 = x, then out (MASK == 1), then the old dres (DRES_ACC); MASK == 2: packed mask bits
+template <typename T, int MASK, bool DRES_ACC>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, const float* __restrict__ coef,
                            int relu_from_x, int C, T* __restrict__ dx, int lddx, T* __restrict__ dres, int lddr) {
   pdl_prologue();
   constexpr int VN = Pack<T>::N;
+  constexpr bool HAS_OUT = MASK == 1;
   constexpr int NT = 2 + (HAS_OUT ? 1 : 0) + (DRES_ACC ? 1 : 0);
   const int c0 = threadIdx.x * VN;
   float mean[VN], A[VN], Bc[VN], Cc[VN], beta[VN];
@@ -585,7 +606,7 @@ bn_bwd_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, co
     Bc[i] = A[i] * coef[c0 + i];
     Cc[i] = A[i] * istd * coef[C + c0 + i];
   }
-  stream_rows<T, NT>(a, [&](long long row, Pack<T>(&f)[NT]) {
+  stream_rows<T, NT, MASK == 2>(a, [&](long long row, Pack<T>(&f)[NT], unsigned mb) {
     Pack<T> o, dr;
 #pragma unroll
     for (int i2 = 0; i2 < VN / 2; ++i2) {
@@ -596,6 +617,7 @@ bn_bwd_apply_stream_kernel(const StreamArgs a, const float* __restrict__ bnp, co
         const float xc = f[1].get(i) - mean[i];
         float dy = f[0].get(i);
         if (HAS_OUT) dy = f[HAS_OUT ? 2 : 0].get(i) > 0.f ? dy : 0.f;
+        else if (MASK == 2) dy = ((mb >> i) & 1u) ? dy : 0.f;
         else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
         drs[h] = DRES_ACC ? f[NT - 1].get(i) + dy : dy;
         res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
@@ -615,17 +637,32 @@ struct StreamGeom {
   size_t smem;
   int rows_per_stage, nst;
 };
-static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem) {
+static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem, bool bits = false) {
   StreamGeom g{};
   const int row_bytes = C * es;
   const int bx = row_bytes / 16;
   g.ok = false;
   if (row_bytes % 16 || bx < 1 || bx > 256 || (bx & (bx - 1))) return g;   // one 16-byte fragment per thread per row
   const int by = 256 / bx;
-  const int SR = 2 * by;                                                   // 8 KB per tensor per stage
+  // Stage size: 16 KB per tensor (4 x 256 fragments).  The per-stage cost (mbarrier wake-up, issue of the next
+  // copies, block barrier) is what paces these kernels, not the bytes in flight: measured on the training step,
+  // 8 KB stages x 4-6 deep = 10.8 ms, 16 KB stages x 2-3 deep = 10.25 ms, 32 KB stages (ring too shallow) = 12.0 ms.
+  static int sr_env = -1;
+  if (sr_env < 0) {
+    const char* e = getenv("BASI_BN_STAGE_ROWS");
+    sr_env = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 0;
+  }
+  int sr_mult = sr_env ? sr_env : (12 / nt < 4 ? 12 / nt : 4);
+  if (sr_mult < 1) sr_mult = 1;
+  const int SR = sr_mult * by;
   const int64_t n_slabs = (R + SR - 1) / SR;
   if (n_slabs < 64) return g;                                              // tiny tensors: the direct kernels
-  int nst = (int)((96 * 1024) / ((size_t)nt * SR * row_bytes));
+  static int ring_kb = 0;
+  if (!ring_kb) {
+    const char* e = getenv("BASI_BN_RING_KB");
+    ring_kb = (e && atoi(e) >= 32 && atoi(e) <= 220) ? atoi(e) : 96;
+  }
+  int nst = (int)(((size_t)ring_kb * 1024) / ((size_t)nt * SR * row_bytes));
   if (nst > 8) nst = 8;
   if (nst < 2) return g;
   g.rows_per_stage = SR;
@@ -634,6 +671,10 @@ static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem)
   const int64_t cap = 2 * (int64_t)sm_count();
   g.grid = dim3((unsigned)(n_slabs < cap ? n_slabs : cap));
   g.smem = (size_t)nst * nt * SR * row_bytes + 8 * nst + 16;
+  if (bits) {
+    if (bx % 16) return g;                               // mask rows are bulk-copied: 16-byte granularity
+    g.smem += (size_t)nst * SR * bx + 16;
+  }
   if (g.smem < min_smem) g.smem = min_smem;
   g.ok = true;
   return g;
@@ -657,7 +698,7 @@ static bool stream_disabled() {
 
 template <typename T>
 static bool launch_apply_stream(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* rbnp,
-                                int relu, const basi_tensor* out, cudaStream_t st) {
+                                int relu, const basi_tensor* out, cudaStream_t st, unsigned char* maskbits = nullptr) {
   if (stream_disabled()) return false;
   const int es = sizeof(T);
   const int nt = res ? 2 : 1;
@@ -670,13 +711,13 @@ static bool launch_apply_stream(const basi_tensor* x, const float* bnp, const ba
   if (res) { a.src[1] = (const char*)res->ptr; a.ldb[1] = (long long)res->ld * es; }
   if (!res) {
     allow_smem(bn_apply_stream_kernel<T, false, false>, g.smem);
-    basi::launch(bn_apply_stream_kernel<T, false, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, false, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c, maskbits);
   } else if (!rbnp) {
     allow_smem(bn_apply_stream_kernel<T, true, false>, g.smem);
-    basi::launch(bn_apply_stream_kernel<T, true, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, true, false>, g.grid, g.block, g.smem, st, a, bnp, nullptr, relu, (T*)out->ptr, out->ld, x->c, maskbits);
   } else {
     allow_smem(bn_apply_stream_kernel<T, true, true>, g.smem);
-    basi::launch(bn_apply_stream_kernel<T, true, true>, g.grid, g.block, g.smem, st, a, bnp, rbnp, relu, (T*)out->ptr, out->ld, x->c);
+    basi::launch(bn_apply_stream_kernel<T, true, true>, g.grid, g.block, g.smem, st, a, bnp, rbnp, relu, (T*)out->ptr, out->ld, x->c, maskbits);
   }
   return true;
 }
@@ -684,24 +725,29 @@ static bool launch_apply_stream(const basi_tensor* x, const float* bnp, const ba
 template <typename T>
 static bool launch_bwd_reduce_stream(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x,
                                      const float* bnp, int relu_from_x, double* dsums, double count, float* dgamma,
-                                     float* dbeta, float* coef, uint32_t* counter, cudaStream_t st) {
+                                     float* dbeta, float* coef, uint32_t* counter, cudaStream_t st,
+                                     const unsigned char* bits = nullptr) {
   if (stream_disabled()) return false;
   const int es = sizeof(T);
   const int nt = out ? 3 : 2;
   const int64_t R = pixels(x);
-  StreamGeom g = stream_geom(R, x->c, es, nt, (size_t)256 * 2 * Pack<T>::N * sizeof(double));
+  StreamGeom g = stream_geom(R, x->c, es, nt, (size_t)256 * 2 * Pack<T>::N * sizeof(double), bits != nullptr);
   if (!g.ok) return false;
   StreamArgs a{};
   fill_stream_args(&a, g, R, x->c, es, 0);
+  a.bits = bits;
   a.src[0] = (const char*)dout->ptr; a.ldb[0] = (long long)dout->ld * es;
   a.src[1] = (const char*)x->ptr; a.ldb[1] = (long long)x->ld * es;
   if (out) { a.src[2] = (const char*)out->ptr; a.ldb[2] = (long long)out->ld * es; }
-  if (out) {
-    allow_smem(bn_bwd_reduce_stream_kernel<T, true>, g.smem);
-    basi::launch(bn_bwd_reduce_stream_kernel<T, true>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+  if (bits) {
+    allow_smem(bn_bwd_reduce_stream_kernel<T, 2>, g.smem);
+    basi::launch(bn_bwd_reduce_stream_kernel<T, 2>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+  } else if (out) {
+    allow_smem(bn_bwd_reduce_stream_kernel<T, 1>, g.smem);
+    basi::launch(bn_bwd_reduce_stream_kernel<T, 1>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
   } else {
-    allow_smem(bn_bwd_reduce_stream_kernel<T, false>, g.smem);
-    basi::launch(bn_bwd_reduce_stream_kernel<T, false>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
+    allow_smem(bn_bwd_reduce_stream_kernel<T, 0>, g.smem);
+    basi::launch(bn_bwd_reduce_stream_kernel<T, 0>, g.grid, g.block, g.smem, st, a, bnp, relu_from_x, x->c, dsums, count, dgamma, dbeta, coef, counter);
   }
   return true;
 }
@@ -709,16 +755,18 @@ static bool launch_bwd_reduce_stream(const basi_tensor* dout, const basi_tensor*
 template <typename T>
 static bool launch_bwd_apply_stream(const basi_tensor* dout, const basi_tensor* out, const basi_tensor* x,
                                     const float* bnp, const float* coef, int relu_from_x, const basi_tensor* dx,
-                                    const basi_tensor* dres, int dres_acc, cudaStream_t st) {
+                                    const basi_tensor* dres, int dres_acc, cudaStream_t st,
+                                    const unsigned char* bits = nullptr) {
   if (stream_disabled()) return false;
   const int es = sizeof(T);
   const bool acc = dres && dres_acc;
   const int nt = 2 + (out ? 1 : 0) + (acc ? 1 : 0);
   const int64_t R = pixels(x);
-  StreamGeom g = stream_geom(R, x->c, es, nt, 0);
+  StreamGeom g = stream_geom(R, x->c, es, nt, 0, bits != nullptr);
   if (!g.ok) return false;
   StreamArgs a{};
   fill_stream_args(&a, g, R, x->c, es, 1);
+  a.bits = bits;
   int k = 0;
   a.src[k] = (const char*)dout->ptr; a.ldb[k++] = (long long)dout->ld * es;
   a.src[k] = (const char*)x->ptr; a.ldb[k++] = (long long)x->ld * es;
@@ -733,10 +781,12 @@ static bool launch_bwd_apply_stream(const basi_tensor* dout, const basi_tensor* 
     basi::launch(bn_bwd_apply_stream_kernel<T, HO, DA>, g.grid, g.block, g.smem, st, a, bnp, coef, relu_from_x, x->c, dxp,    \
                                                                             dx->ld, drp, lddr);                     \
   } while (0)
-  if (out && acc) BASI_LAUNCH_BWD_APPLY(true, true);
-  else if (out) BASI_LAUNCH_BWD_APPLY(true, false);
-  else if (acc) BASI_LAUNCH_BWD_APPLY(false, true);
-  else BASI_LAUNCH_BWD_APPLY(false, false);
+  if (bits && acc) BASI_LAUNCH_BWD_APPLY(2, true);
+  else if (bits) BASI_LAUNCH_BWD_APPLY(2, false);
+  else if (out && acc) BASI_LAUNCH_BWD_APPLY(1, true);
+  else if (out) BASI_LAUNCH_BWD_APPLY(1, false);
+  else if (acc) BASI_LAUNCH_BWD_APPLY(0, true);
+  else BASI_LAUNCH_BWD_APPLY(0, false);
 #undef BASI_LAUNCH_BWD_APPLY
   return true;
 }
@@ -1088,6 +1138,58 @@ int basi_bn_bwd_apply(const basi_tensor* dout, const basi_tensor* out, const bas
         dres_accumulate, R, x->c);
   })
   BASI_CHECK_LAUNCH("bn_bwd_apply");
+  return BASI_OK;
+}
+
+/* ---- packed ReLU mask (one bit per element) for the residual junctions: the backward pair then reads 1/16 of the
+ * bytes of the stored output.  bf16 tensors with c % 128 == 0 that take the streamed kernels. */
+int basi_bn_maskbits_supported(const basi_tensor* x) {
+  if (!x || x->dtype != BASI_BF16 || !vec_ok(x) || x->c % 128 != 0 || stream_disabled()) return 0;
+  return stream_geom(pixels(x), x->c, 2, 4, 0, true).ok ? 1 : 0;
+}
+
+int basi_bn_apply_bits(const basi_tensor* x, const float* bnp, const basi_tensor* res, const float* res_bnp, int relu,
+                       const basi_tensor* out, unsigned char* maskbits, void* stream) {
+  BASI_CHECK_ARG(x && bnp && out && maskbits && vec_ok(x) && vec_ok(out) && same_shape(x, out) &&
+                     x->dtype == BASI_BF16 && out->dtype == BASI_BF16,
+                 "bn_apply_bits: bad x/out (bf16 only)");
+  BASI_CHECK_ARG(!res || (vec_ok(res) && same_shape(x, res) && res->dtype == x->dtype), "bn_apply_bits: bad residual");
+  BASI_CHECK_ARG(res || !res_bnp, "bn_apply_bits: res_bnp without res");
+  BASI_CHECK_ARG(basi_bn_maskbits_supported(x) == 1, "bn_apply_bits: tensor not supported (see basi_bn_maskbits_supported)");
+  bool ok = launch_apply_stream<bf16>(x, bnp, res, res_bnp, relu, out, (cudaStream_t)stream, maskbits);
+  BASI_CHECK_ARG(ok, "bn_apply_bits: streamed kernel unavailable");
+  BASI_CHECK_LAUNCH("bn_apply_bits");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_reduce_bits(const basi_tensor* dout, const unsigned char* maskbits, const basi_tensor* x,
+                            const float* bnp, double* dsums, double count, float* dgamma, float* dbeta, float* coef,
+                            uint32_t* counter, void* stream) {
+  BASI_CHECK_ARG(dout && x && maskbits && bnp && dsums && counter && vec_ok(dout) && vec_ok(x) && same_shape(dout, x) &&
+                     dout->dtype == BASI_BF16 && x->dtype == BASI_BF16,
+                 "bn_bwd_reduce_bits: bad dout/x (bf16 only)");
+  BASI_CHECK_ARG(!coef || (dgamma && dbeta && count > 0), "bn_bwd_reduce_bits: fused finalize needs dgamma, dbeta, count");
+  BASI_CHECK_ARG(basi_bn_maskbits_supported(x) == 1, "bn_bwd_reduce_bits: tensor not supported");
+  bool ok = launch_bwd_reduce_stream<bf16>(dout, nullptr, x, bnp, 0, dsums, count, dgamma, dbeta, coef, counter,
+                                           (cudaStream_t)stream, maskbits);
+  BASI_CHECK_ARG(ok, "bn_bwd_reduce_bits: streamed kernel unavailable");
+  BASI_CHECK_LAUNCH("bn_bwd_reduce_bits");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_apply_bits(const basi_tensor* dout, const unsigned char* maskbits, const basi_tensor* x,
+                           const float* bnp, const float* coef, const basi_tensor* dx, const basi_tensor* dres,
+                           int dres_accumulate, void* stream) {
+  BASI_CHECK_ARG(dout && x && dx && maskbits && bnp && coef && vec_ok(dout) && vec_ok(x) && vec_ok(dx) &&
+                     same_shape(dout, x) && same_shape(dx, x) && dout->dtype == BASI_BF16 && x->dtype == BASI_BF16 &&
+                     dx->dtype == BASI_BF16,
+                 "bn_bwd_apply_bits: bad dout/x/dx (bf16 only)");
+  BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_apply_bits: bad dres");
+  BASI_CHECK_ARG(basi_bn_maskbits_supported(x) == 1, "bn_bwd_apply_bits: tensor not supported");
+  bool ok = launch_bwd_apply_stream<bf16>(dout, nullptr, x, bnp, coef, 0, dx, dres, dres_accumulate,
+                                          (cudaStream_t)stream, maskbits);
+  BASI_CHECK_ARG(ok, "bn_bwd_apply_bits: streamed kernel unavailable");
+  BASI_CHECK_LAUNCH("bn_bwd_apply_bits");
   return BASI_OK;
 }
 

@@ -684,3 +684,61 @@ def test_batch_norm_backward_resident(dtype, relu, shape):
         assert rel_err(outs[k][0], outs[0][0]) < ptol
         assert rel_err(outs[k][1], outs[0][1]) < 1e-5 and rel_err(outs[k][2], outs[0][2]) < 1e-5
         assert rel_err(outs[k][3], outs[0][3]) < 1e-5
+
+
+# ------------------------------------------------------------------ packed ReLU mask of the residual junctions
+@pytest.mark.parametrize("mode", ["res", "res_bn"])
+@pytest.mark.parametrize("shape", [(4, 40, 40, 128), (3, 37, 41, 256), (16, 40, 40, 512)])
+def test_batch_norm_junction_mask_bits(mode, shape):
+    """basi_bn_apply_bits / _bwd_reduce_bits / _bwd_apply_bits == the pair that re-reads the stored output."""
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    from basi_b200 import _lib
+    B, H, W, Cc = shape
+    rng = np.random.RandomState(11)
+    tdt = torch.bfloat16
+    x, x2 = bf16_round(_u(rng, *shape) * 2 + 0.5), bf16_round(_u(rng, *shape))
+    dout, dres0 = bf16_round(_u(rng, *shape)), bf16_round(_u(rng, *shape))
+    gamma, beta = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    gamma2, beta2 = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    R = float(B * H * W)
+    xa, x2a, da = act(x, tdt), act(x2, tdt), act(dout, tdt)
+    assert _lib.load().basi_bn_maskbits_supported(xa.ref) == 1
+    gd, bd, g2d, b2d = dev(gamma), dev(beta), dev(gamma2), dev(beta2)
+    sums = torch.zeros(4 * Cc * 8, dtype=torch.float64, device="cuda:0")
+    bnp, bnp2 = torch.zeros(4 * Cc, device="cuda:0"), torch.zeros(4 * Cc, device="cuda:0")
+    cnt = torch.zeros(16, dtype=torch.int32, device="cuda:0")
+    call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), cnt.data_ptr())
+    res_bnp = None
+    if mode == "res_bn":
+        call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc * 8, g2d.data_ptr(), b2d.data_ptr(), C.c_double(R),
+             C.c_float(1e-5), bnp2.data_ptr(), cnt.data_ptr() + 4)
+        res_bnp = bnp2.data_ptr()
+    out_a, out_b = empty_act(shape, tdt), empty_act(shape, tdt)
+    bits = torch.zeros(B * H * W * Cc // 8, dtype=torch.uint8, device="cuda:0")
+    call("basi_bn_apply", xa.ref, bnp.data_ptr(), x2a.ref, res_bnp, 1, out_a.ref)
+    call("basi_bn_apply_bits", xa.ref, bnp.data_ptr(), x2a.ref, res_bnp, 1, out_b.ref, bits.data_ptr())
+    oa = host(out_a)
+    assert np.array_equal(oa, host(out_b))
+    want = np.packbits((oa > 0).reshape(-1, 8), axis=1, bitorder="little").reshape(-1)
+    assert np.array_equal(host(bits), want)
+    res = []
+    for use_bits in (False, True):
+        dsums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
+        coef = torch.zeros(2 * Cc, device="cuda:0")
+        dgamma, dbeta = torch.zeros(Cc, device="cuda:0"), torch.zeros(Cc, device="cuda:0")
+        dxa = empty_act(shape, tdt, fill=5.0)
+        dra = act(dres0, tdt)
+        if use_bits:
+            call("basi_bn_bwd_reduce_bits", da.ref, bits.data_ptr(), xa.ref, bnp.data_ptr(), dsums.data_ptr(),
+                 C.c_double(R), dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 8)
+            call("basi_bn_bwd_apply_bits", da.ref, bits.data_ptr(), xa.ref, bnp.data_ptr(), coef.data_ptr(), dxa.ref,
+                 dra.ref, 1)
+        else:
+            call("basi_bn_bwd_reduce", da.ref, out_a.ref, xa.ref, bnp.data_ptr(), 0, dsums.data_ptr(), C.c_double(R),
+                 dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 12)
+            call("basi_bn_bwd_apply", da.ref, out_a.ref, xa.ref, bnp.data_ptr(), coef.data_ptr(), 0, dxa.ref, dra.ref, 1)
+        res.append((host(dxa), host(dra), host(dgamma), host(dbeta)))
+    assert rel_err(res[1][0], res[0][0]) < 1e-2           # same arithmetic; only the atomics order differs
+    assert np.array_equal(res[1][1], res[0][1])           # dres += dout * mask: exact
+    assert rel_err(res[1][2], res[0][2]) < 1e-5 and rel_err(res[1][3], res[0][3]) < 1e-5
