@@ -319,6 +319,16 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"],
                 "launches_per_step": d["n"], "share_of_step": d["ms"] / total_ms}
+    # DRAM bytes per launch of that kernel group from the committed ncu capture of the same workload
+    # (profiles/traffic_r01.json, made by tools/make_traffic.py from the launch list of tools/profile_step.py)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            grp = json.load(f).get("groups", {}).get(name)
+        if grp:
+            roof["traffic"] = grp["dram_bytes_per_launch"]
+            roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/traffic_r01.json"
+    except (OSError, ValueError):
+        pass
     breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"],
                      "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None,
                      "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}

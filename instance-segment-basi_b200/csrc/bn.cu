@@ -468,13 +468,31 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
     mbar_wait(bar0 + 8 * st, (uint32_t)((k / a.nst) & 1));
     const long long row0 = slab_of(k) * SR;
     const int rows = (int)min((long long)SR, a.R - row0);
-    for (int rr = threadIdx.y; rr < rows; rr += blockDim.y) {
-      Pack<T> f[NT];
+    constexpr int M = NT >= 4 ? 3 : 4;   // rows per thread in a full stage of the default geometry (see stream_geom)
+    if (rows == SR && SR == M * (int)blockDim.y) {
+      // full stage: all shared-memory loads of the thread's M rows are issued before any arithmetic
+      Pack<T> f[M][NT];
+      unsigned mb[M];
 #pragma unroll
-      for (int t = 0; t < NT; ++t)
-        f[t].load(reinterpret_cast<const T*>(stream_smem + (size_t)(st * NT + t) * stage_bytes + (size_t)rr * a.row_bytes +
-                                             threadIdx.x * 16));
-      body(row0 + rr, f, BITS ? (unsigned)bits_s[(size_t)st * SR * bx + (size_t)rr * bx + threadIdx.x] : 0u);
+      for (int u = 0; u < M; ++u) {
+        const int rr = threadIdx.y + u * blockDim.y;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          f[u][t].load(reinterpret_cast<const T*>(stream_smem + (size_t)(st * NT + t) * stage_bytes +
+                                                  (size_t)rr * a.row_bytes + threadIdx.x * 16));
+        mb[u] = BITS ? (unsigned)bits_s[(size_t)st * SR * bx + (size_t)rr * bx + threadIdx.x] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < M; ++u) body(row0 + threadIdx.y + u * blockDim.y, f[u], mb[u]);
+    } else {
+      for (int rr = threadIdx.y; rr < rows; rr += blockDim.y) {
+        Pack<T> f[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          f[t].load(reinterpret_cast<const T*>(stream_smem + (size_t)(st * NT + t) * stage_bytes +
+                                               (size_t)rr * a.row_bytes + threadIdx.x * 16));
+        body(row0 + rr, f, BITS ? (unsigned)bits_s[(size_t)st * SR * bx + (size_t)rr * bx + threadIdx.x] : 0u);
+      }
     }
     __syncthreads();
   }
@@ -514,9 +532,10 @@ __global__ void __launch_bounds__(256, 2) bn_apply_stream_kernel(const StreamArg
         v[h] = relu ? fmaxf(t, 0.f) : t;
       }
       o.set2(i2, v[0], v[1]);
-      // the mask is taken from the value AS STORED (bf16-rounded), like the backward kernels that read `out`
-      mb |= (o.get(2 * i2) > 0.f ? 1u : 0u) << (2 * i2);
-      mb |= (o.get(2 * i2 + 1) > 0.f ? 1u : 0u) << (2 * i2 + 1);
+      // v >= 0 after the ReLU and bf16 keeps the fp32 exponent range, so (v > 0) == (stored bf16 value > 0) for every
+      // normal number: the same mask as the backward kernels that read `out`
+      if (v[0] > 0.f) mb |= 1u << (2 * i2);
+      if (v[1] > 0.f) mb |= 1u << (2 * i2 + 1);
     }
     o.store(out + row * ldo + c0);
     if (maskbits) {
