@@ -99,3 +99,24 @@ def test_synthetic_batches_are_reference_shaped():
         assert lab[b, clicks[b, 0] // 8, clicks[b, 1] // 8, 0] == 1       # the click lies on the instance
     data, ann, c, raw, mask = SyntheticData(2, (64, 64), 8, 21, 1, seed=1).next_batch_train()
     assert data[0].shape == (64, 64, 4) and data[0].dtype == np.float32 and ann[0].shape == (8, 8, 1)
+
+
+def test_psp_branches_are_tagged_and_their_pool_adjoints_deferred():
+    """The four pyramid branches run on their own streams: every call of a branch carries its tag, the shared-tensor
+    read-modify-write (avgpool adjoint) carries none and is emitted after the last branch call."""
+    eng = Engine(build("1NoClass", S=64, F=8), 2, precision="f32", dry_run=True,
+                 loss=dict(kind="bce", pos_weight=3.0))
+    for lst in (eng.fwd, eng.bwd):
+        tags = [m.get("branch") for _, _, _, m in lst]
+        assert set(t for t in tags if t is not None) == {0, 1, 2, 3}
+        idx = [i for i, t in enumerate(tags) if t is not None]
+        # one contiguous fork/join region per pass
+        assert all(tags[i] is not None for i in range(idx[0], idx[-1] + 1))
+    names = [n for n, _, _, _ in eng.bwd]
+    tags = [m.get("branch") for _, _, _, m in eng.bwd]
+    pools = [i for i, n in enumerate(names) if n == "basi_avgpool_bwd"]
+    last_branch = max(i for i, t in enumerate(tags) if t is not None)
+    assert len(pools) == 4 and all(tags[i] is None for i in pools) and min(pools) > last_branch
+    # ... and before the consumer of the tensor they add into (conv5_3's junction backward)
+    nxt = names[max(pools) + 1]
+    assert nxt.startswith("basi_bn_bwd"), nxt
