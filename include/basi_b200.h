@@ -149,6 +149,16 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
 int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* stream);
 int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int accumulate, void* stream);
 
+/* All pyramid pools of one tensor in ONE pass (BAISPSPNet.py:683-710: windows 40/20/13/6 of conv5_3 at 320^2): ks[p]
+ * is the window (= stride) of pool p, ys[p] its output ([n, h/k, w/k, c]).  `scratch` holds
+ * basi_avgpool_multi_scratch_floats() zero-initialised floats; the call leaves it zeroed again.  The adjoint adds
+ * (accumulate != 0) or writes every pool's contribution to dx in one read-modify-write pass.  At most 4 pools. */
+int64_t basi_avgpool_multi_scratch_floats(const basi_tensor* x, int n_pools, const int* ks);
+int basi_avgpool_multi_fwd(const basi_tensor* x, int n_pools, const int* ks, const basi_tensor* const* ys,
+                           float* scratch, void* stream);
+int basi_avgpool_multi_bwd(const basi_tensor* const* dys, int n_pools, const int* ks, const basi_tensor* dx,
+                           int accumulate, void* stream);
+
 /* ---- A9: Network.resize_bilinear, align_corners=True (:242-244) ---- */
 int basi_bilinear_ac_fwd(const basi_tensor* x, const basi_tensor* y, void* stream);
 int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "basi_bn_bwd_apply_bits": [_TP, _P, _TP, _P, _P, _TP, _TP, _i, _P],
     "basi_bn_bwd_fused_supported": [_TP],
     "basi_bn_bwd_fused": [_TP, _TP, _P, _i, _P, _d, _P, _P, _P, _P, _TP, _P],
+    "basi_avgpool_multi_fwd": [_TP, _i, _P, _P, _P, _P],
+    "basi_avgpool_multi_bwd": [_P, _i, _P, _TP, _i, _P],
     "basi_subsample_fwd": [_TP, _i, _TP, _P],
     "basi_subsample_bwd": [_TP, _i, _TP, _i, _P],
     "basi_bn_stats": [_TP, _P, _P, _P, _d, _f, _P, _P, _P],
@@ -95,7 +97,8 @@ SIGNATURES = {
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
-            "basi_tc_conv_destroy": ([_P], None)}
+            "basi_tc_conv_destroy": ([_P], None),
+            "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
 
 _lib = None
 

@@ -110,6 +110,7 @@ class Engine(object):
         self.fused_stats = 0
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.mask_bits = not os.environ.get("BASI_NO_MASK_BITS")
+        self.fuse_pools = not os.environ.get("BASI_NO_POOL_FUSION")
         self.fused_bn_bwd = 0
         self._tc_weights = []
         self._pack_table = None
@@ -397,12 +398,42 @@ class Engine(object):
         self._call(self.fwd, "basi_maxpool3s2_fwd", x.ref, y.ref, amax.data_ptr())
 
     def _lower_avg_pool(self, n):
+        if n.index in self._acts:
+            return                                   # already produced by the fused pass of its pyramid group
         x = self._acts[n.inputs[0].index]
+        # pyramid pooling: every avg_pool reading this tensor is computed in ONE pass, emitted at the first of them
+        sibs = [c for c in self._cons[n.inputs[0].index] if c.op == "avg_pool"]
+        if self.fuse_pools and 2 <= len(sibs) <= 4:
+            grp = dict(x=x, ops=[])
+            for sib in sibs:
+                op = dict(x=x, y=self._out_act(sib), k=sib.attrs["k"], group=grp)
+                self._acts[sib.index] = op["y"]
+                self._ops.append(("avgpool", op))
+                grp["ops"].append(op)
+            self._emit_pool_group_fwd(grp)
+            return
         y = self._out_act(n)
-        op = dict(x=x, y=y, k=n.attrs["k"])
+        op = dict(x=x, y=y, k=n.attrs["k"], group=None)
         self._acts[n.index] = y
         self._ops.append(("avgpool", op))
         self._call(self.fwd, "basi_avgpool_fwd", x.ref, op["k"], y.ref)
+
+    def _pool_group_args(self, grp, grads):
+        ops = grp["ops"]
+        ks = (C.c_int * len(ops))(*[o["k"] for o in ops])
+        ptrs = (C.POINTER(Tensor) * len(ops))(*[C.pointer((o["y"].grad if grads else o["y"]).desc) for o in ops])
+        self._keep.extend([ks, ptrs])
+        return len(ops), ks, ptrs
+
+    def _emit_pool_group_fwd(self, grp):
+        x = grp["x"]
+        cells = sum(o["y"].shape[1] * o["y"].shape[2] for o in grp["ops"])
+        grp["scratch"] = torch.zeros(self.B * cells * x.shape[3], dtype=torch.float32, device=self.device)
+        n, ks, ptrs = self._pool_group_args(grp, False)
+        br, self._cur_branch = self._cur_branch, None          # the shared pass runs before the branches fork
+        self._call(self.fwd, "basi_avgpool_multi_fwd", x.ref, n, ks, ptrs, grp["scratch"].data_ptr(),
+                   bytes=self._nbytes(x))
+        self._cur_branch = br
 
     def _lower_resize_bilinear(self, n):
         x = self._acts[n.inputs[0].index]
@@ -666,6 +697,20 @@ class Engine(object):
 
     def _bwd_avgpool(self, op):
         x, y = op["x"], op["y"]
+        grp = op.get("group")
+        if grp is not None:
+            # emitted once, when the LAST pool of the group is reached in backward order (all pooled gradients exist
+            # by then only after the other branches ran: the call is deferred behind the branch region)
+            grp["bwd_seen"] = grp.get("bwd_seen", 0) + 1
+            if grp["bwd_seen"] < len(grp["ops"]):
+                return
+            acc = self._acc_flag(x)
+            n, ks, ptrs = self._pool_group_args(grp, True)
+            br, self._cur_branch = self._cur_branch, None
+            lst = self._deferred_bwd if br is not None else self.bwd
+            self._call(lst, "basi_avgpool_multi_bwd", ptrs, n, ks, x.grad.ref, acc, bytes=self._nbytes(x) * 2)
+            self._cur_branch = br
+            return
         acc = self._acc_flag(x)
         if self._cur_branch is not None:
             # every pyramid branch adds into the SAME gradient tensor (read-modify-write): not on a branch stream, and

@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace basi {
@@ -201,6 +203,150 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int ldy, int OH, in
       continue;
     }
     g.store(dx + p * ldx + cg * VN);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Pyramid pooling (BAISPSPNet.py:683-710): the four average pools of conv5_3 read the SAME 52 MB tensor with windows
+// 40/20/13/6.  One pass: block = (image, band of rows, 64 channels); thread = (8-channel group, column) keeps the
+// running window sums of all pools in registers, flushes them to per-cell shared-memory accumulators when a row
+// window ends, the block adds its cells to an fp32 scratch; a tiny second kernel scales, converts and re-zeroes the
+// scratch.  The adjoint is one read-modify-write pass over dx instead of four.
+// ------------------------------------------------------------------------------------------
+constexpr int MP_MAX = 4;
+struct MultiPool {
+  int np, cells;
+  int k[MP_MAX], OH[MP_MAX], OW[MP_MAX], cell0[MP_MAX];
+  void* y[MP_MAX];   // pooled tensors (fwd: outputs, bwd: their gradients)
+  int ldy[MP_MAX];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_multi_acc_kernel(const T* __restrict__ x, int ldx, int H, int W, int C,
+                                                                const MultiPool mp, int RB, float* __restrict__ scratch) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  constexpr int CH = 64;                       // channels per block
+  extern __shared__ float cells_s[];           // [mp.cells][CH]
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < mp.cells * CH; i += blockDim.x * blockDim.y) cells_s[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.z, c0 = blockIdx.y * CH + threadIdx.x * VN;
+  const int h0 = blockIdx.x * RB, h1 = min(h0 + RB, H);
+  const bool cok = threadIdx.x * VN < CH && c0 < C;
+  if (cok) {
+    for (int w = threadIdx.y; w < W; w += blockDim.y) {
+      float acc[MP_MAX][VN];
+      int cur[MP_MAX];
+#pragma unroll
+      for (int p = 0; p < MP_MAX; ++p) {
+        cur[p] = p < mp.np ? h0 / mp.k[p] : 0;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
+      }
+      auto flush = [&](int p) {
+        const int ow = w / mp.k[p];
+        if (cur[p] < mp.OH[p] && ow < mp.OW[p]) {
+          float* d = cells_s + (size_t)(mp.cell0[p] + cur[p] * mp.OW[p] + ow) * CH + threadIdx.x * VN;
+#pragma unroll
+          for (int j = 0; j < VN; ++j) atomicAdd(d + j, acc[p][j]);
+        }
+      };
+      for (int h = h0; h < h1; ++h) {
+        const Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + h) * W + w) * ldx + c0);
+#pragma unroll
+        for (int p = 0; p < MP_MAX; ++p) {
+          if (p >= mp.np) continue;
+          const int oh = h / mp.k[p];
+          if (oh != cur[p]) {
+            flush(p);
+            cur[p] = oh;
+#pragma unroll
+            for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[p][j] += v.v[j];
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < MP_MAX; ++p)
+        if (p < mp.np) flush(p);
+    }
+  }
+  __syncthreads();
+  // the cells this band touched -> fp32 scratch [N][cells][C]
+  for (int p = 0; p < mp.np; ++p) {
+    const int oh_lo = h0 / mp.k[p], oh_hi = min((h1 - 1) / mp.k[p], mp.OH[p] - 1);
+    const int ncell = (oh_hi - oh_lo + 1) * mp.OW[p];
+    for (int i = tid; i < ncell * CH; i += blockDim.x * blockDim.y) {
+      const int cell = mp.cell0[p] + oh_lo * mp.OW[p] + i / CH, ch = i % CH;
+      if (blockIdx.y * CH + ch < C)
+        atomicAdd(scratch + ((size_t)n * mp.cells + cell) * C + blockIdx.y * CH + ch, cells_s[(size_t)cell * CH + ch]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void avgpool_multi_finalize_kernel(const MultiPool mp, int C, float* __restrict__ scratch, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t t = i / cgs;
+    const int cell = (int)(t % mp.cells), n = (int)(t / mp.cells);
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < MP_MAX; ++q)
+      if (q < mp.np && cell >= mp.cell0[q]) p = q;
+    const int local = cell - mp.cell0[p];
+    const float inv = 1.0f / (float)(mp.k[p] * mp.k[p]);
+    float* sp = scratch + ((size_t)n * mp.cells + cell) * C + cg * VN;
+    Vec<T> r;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      r.v[j] = sp[j] * inv;
+      sp[j] = 0.f;                                   // the scratch is clean again for the next step
+    }
+    r.store((T*)mp.y[p] + ((size_t)n * mp.OH[p] * mp.OW[p] + local) * mp.ldy[p] + cg * VN);
+  }
+}
+
+template <typename T>
+__global__ void avgpool_multi_bwd_kernel(const MultiPool mp, T* __restrict__ dx, int ldx, int H, int W, int C, int acc,
+                                         int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t px = i / cgs;
+    const int iw = (int)(px % W);
+    const int64_t t = px / W;
+    const int ih = (int)(t % H), n = (int)(t / H);
+    Vec<T> g = Vec<T>::zero();
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < MP_MAX; ++p) {
+      if (p >= mp.np) continue;
+      const int oh = ih / mp.k[p], ow = iw / mp.k[p];
+      if (oh < mp.OH[p] && ow < mp.OW[p]) {
+        const float inv = 1.0f / (float)(mp.k[p] * mp.k[p]);
+        const Vec<T> d =
+            Vec<T>::load((const T*)mp.y[p] + (((int64_t)n * mp.OH[p] + oh) * mp.OW[p] + ow) * mp.ldy[p] + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) g.v[j] += d.v[j] * inv;
+        any = true;
+      }
+    }
+    if (acc) {
+      if (!any) continue;
+      const Vec<T> o = Vec<T>::load(dx + px * ldx + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) g.v[j] += o.v[j];
+    }
+    g.store(dx + px * ldx + cg * VN);
   }
 }
 
@@ -812,6 +958,66 @@ int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int ac
     basi::launch(avgpool_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, k, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
   })
   BASI_CHECK_LAUNCH("avgpool_bwd");
+  return BASI_OK;
+}
+
+static int fill_multipool(MultiPool* mp, const basi_tensor* x, int n_pools, const int* ks, const basi_tensor* const* ys,
+                          const char* who) {
+  BASI_CHECK_ARG(x && ks && ys && n_pools >= 1 && n_pools <= MP_MAX && vec_ok(x), "%s: bad argument", who);
+  memset(mp, 0, sizeof(*mp));
+  mp->np = n_pools;
+  int cells = 0;
+  for (int p = 0; p < n_pools; ++p) {
+    const basi_tensor* y = ys[p];
+    BASI_CHECK_ARG(y && ks[p] > 0 && vec_ok(y) && y->dtype == x->dtype && y->c == x->c && y->n == x->n &&
+                       y->h == x->h / ks[p] && y->w == x->w / ks[p] && y->h > 0 && y->w > 0,
+                   "%s: pool %d does not match its input", who, p);
+    mp->k[p] = ks[p]; mp->OH[p] = y->h; mp->OW[p] = y->w; mp->cell0[p] = cells;
+    mp->y[p] = y->ptr; mp->ldy[p] = y->ld;
+    cells += y->h * y->w;
+  }
+  mp->cells = cells;
+  return BASI_OK;
+}
+
+int64_t basi_avgpool_multi_scratch_floats(const basi_tensor* x, int n_pools, const int* ks) {
+  if (!x || !ks || n_pools < 1 || n_pools > MP_MAX) return -1;
+  int64_t cells = 0;
+  for (int p = 0; p < n_pools; ++p) cells += (int64_t)(x->h / ks[p]) * (x->w / ks[p]);
+  return (int64_t)x->n * cells * x->c;
+}
+
+int basi_avgpool_multi_fwd(const basi_tensor* x, int n_pools, const int* ks, const basi_tensor* const* ys,
+                           float* scratch, void* stream) {
+  MultiPool mp;
+  int rc = fill_multipool(&mp, x, n_pools, ks, ys, "avgpool_multi fwd");
+  if (rc) return rc;
+  BASI_CHECK_ARG(scratch && mp.cells * 64 * sizeof(float) <= 48 * 1024, "avgpool_multi fwd: null scratch / too many cells");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int RB = 8;
+  DISPATCH_T(x->dtype, {
+    dim3 block(64 / Vec<T>::N, 256 / (64 / Vec<T>::N));
+    dim3 grid((x->h + RB - 1) / RB, (x->c + 63) / 64, x->n);
+    basi::launch(avgpool_multi_acc_kernel<T>, grid, block, (size_t)mp.cells * 64 * sizeof(float), st, (const T*)x->ptr,
+                 x->ld, x->h, x->w, x->c, mp, RB, scratch);
+    int64_t total = (int64_t)x->n * mp.cells * (x->c / Vec<T>::N);
+    basi::launch(avgpool_multi_finalize_kernel<T>, grid_for(total, 256), 256, 0, st, mp, x->c, scratch, total);
+  })
+  BASI_CHECK_LAUNCH("avgpool_multi_fwd");
+  return BASI_OK;
+}
+
+int basi_avgpool_multi_bwd(const basi_tensor* const* dys, int n_pools, const int* ks, const basi_tensor* dx,
+                           int accumulate, void* stream) {
+  MultiPool mp;
+  int rc = fill_multipool(&mp, dx, n_pools, ks, dys, "avgpool_multi bwd");
+  if (rc) return rc;
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
+    basi::launch(avgpool_multi_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mp, (T*)dx->ptr, dx->ld,
+                 dx->h, dx->w, dx->c, accumulate, total);
+  })
+  BASI_CHECK_LAUNCH("avgpool_multi_bwd");
   return BASI_OK;
 }
 

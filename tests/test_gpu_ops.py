@@ -742,3 +742,52 @@ def test_batch_norm_junction_mask_bits(mode, shape):
     assert rel_err(res[1][0], res[0][0]) < 1e-2           # same arithmetic; only the atomics order differs
     assert np.array_equal(res[1][1], res[0][1])           # dres += dout * mask: exact
     assert rel_err(res[1][2], res[0][2]) < 1e-5 and rel_err(res[1][3], res[0][3]) < 1e-5
+
+
+# ------------------------------------------------------------------ pyramid pooling in one pass
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("B,H,Cc,ks", [(2, 40, 128, (40, 20, 13, 6)), (3, 8, 64, (8, 4, 2, 1)), (1, 23, 16, (23, 11, 7)),
+                                       (16, 40, 1024, (40, 20, 13, 6))])
+def test_avgpool_multi_forward_backward(dtype, B, H, Cc, ks):
+    from gpu_util import act, bf16_round, call, empty_act, host, rel_err
+    from basi_b200 import _lib
+    from basi_b200._lib import Tensor
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    rng = np.random.RandomState(17)
+    x = _u(rng, B, H, H, Cc)
+    if dtype == "bf16":
+        x = bf16_round(x)
+    xa = act(x, td)
+    ys = [empty_act((B, H // k, H // k, Cc), td, fill=9.0) for k in ks]
+    karr = (C.c_int * len(ks))(*ks)
+    yptr = (C.POINTER(Tensor) * len(ks))(*[C.pointer(y.desc) for y in ys])
+    nfl = _lib.load().basi_avgpool_multi_scratch_floats(xa.ref, len(ks), karr)
+    assert nfl == B * sum((H // k) ** 2 for k in ks) * Cc
+    scratch = torch.zeros(nfl, dtype=torch.float32, device="cuda:0")
+    tol = 1e-5 if dtype == "f32" else 1e-2
+    for _ in range(2):                                      # twice: the scratch must come back zeroed
+        call("basi_avgpool_multi_fwd", xa.ref, len(ks), karr, yptr, scratch.data_ptr())
+        for k, y in zip(ks, ys):
+            want = nhwc(O.avg_pool(nchw(x).double(), k))
+            assert rel_err(host(y), want) < tol
+    assert float(scratch.abs().max()) == 0.0
+    # adjoint: every pool adds its share to dx in one pass
+    dys = [_u(rng, B, H // k, H // k, Cc) for k in ks]
+    if dtype == "bf16":
+        dys = [bf16_round(d) for d in dys]
+    dya = [act(d, td) for d in dys]
+    dptr = (C.POINTER(Tensor) * len(ks))(*[C.pointer(d.desc) for d in dya])
+    want = np.zeros((B, H, H, Cc), np.float64)
+    for k, d in zip(ks, dys):
+        o = H // k
+        up = np.repeat(np.repeat(d.astype(np.float64), k, axis=1), k, axis=2) / (k * k)
+        want[:, :o * k, :o * k, :] += up
+    dxa = empty_act((B, H, H, Cc), td, fill=3.0)
+    call("basi_avgpool_multi_bwd", dptr, len(ks), karr, dxa.ref, 0)
+    assert rel_err(host(dxa), want) < tol
+    base = _u(rng, B, H, H, Cc)
+    if dtype == "bf16":
+        base = bf16_round(base)
+    dxb = act(base, td)
+    call("basi_avgpool_multi_bwd", dptr, len(ks), karr, dxb.ref, 1)
+    assert rel_err(host(dxb), want + base) < 2 * tol

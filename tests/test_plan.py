@@ -114,9 +114,14 @@ def test_psp_branches_are_tagged_and_their_pool_adjoints_deferred():
         assert all(tags[i] is not None for i in range(idx[0], idx[-1] + 1))
     names = [n for n, _, _, _ in eng.bwd]
     tags = [m.get("branch") for _, _, _, m in eng.bwd]
-    pools = [i for i, n in enumerate(names) if n == "basi_avgpool_bwd"]
+    # the four pools are one fused pass (forward: before the fork; backward: one read-modify-write after the join)
+    pools = [i for i, n in enumerate(names) if n == "basi_avgpool_multi_bwd"]
     last_branch = max(i for i, t in enumerate(tags) if t is not None)
-    assert len(pools) == 4 and all(tags[i] is None for i in pools) and min(pools) > last_branch
-    # ... and before the consumer of the tensor they add into (conv5_3's junction backward)
-    nxt = names[max(pools) + 1]
-    assert nxt.startswith("basi_bn_bwd"), nxt
+    assert len(pools) == 1 and tags[pools[0]] is None and pools[0] == last_branch + 1
+    assert "basi_avgpool_bwd" not in names
+    # ... and before the consumer of the tensor it adds into (conv5_3's junction backward)
+    assert names[pools[0] + 1].startswith("basi_bn_bwd"), names[pools[0] + 1]
+    fnames = [n for n, _, _, _ in eng.fwd]
+    ftags = [m.get("branch") for _, _, _, m in eng.fwd]
+    fp = fnames.index("basi_avgpool_multi_fwd")
+    assert ftags[fp] is None and fp + 1 == min(i for i, t in enumerate(ftags) if t is not None)
