@@ -621,61 +621,66 @@ __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
 }
 
 template <typename TG, int COUT>
-__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const StemConv g) {
-  // lane = output channel; a warp takes 2 consecutive pixels per iteration (all their loads are issued before the
-  // FMAs) and keeps the 36 x NC partial sums in registers
-  constexpr int NC = COUT / 32, PX = 2;
+__global__ void __launch_bounds__(128) stem_wgrad_kernel(const StemConv g) {
+  // lane = output channel.  A warp takes 32 consecutive output pixels of one row per iteration: it stages their input
+  // patch (3 rows x (31*stride + 3) columns of float4) and their 32 x COUT gradients in shared memory with coalesced
+  // loads, then walks the pixels reading the taps as shared-memory broadcasts; the 36 x NC partial sums stay in
+  // registers for the whole kernel.
+  constexpr int NC = COUT / 32, XC = 66, WARPS = (sizeof(TG) * COUT > 128) ? 2 : 4;   // <= 48 KB static smem
+  __shared__ __align__(16) float4 sx[WARPS][3][XC];
+  __shared__ TG sdy[WARPS][32][COUT];
   __shared__ float red[36 * COUT];
   for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * WARPS + wib, nwarps = gridDim.x * WARPS;
   const TG* G = (const TG*)g.Y;
-  const int M = (int)g.M;
+  const int chunks_per_row = (g.OW + 31) / 32;
+  const int nchunks = g.N * g.OH * chunks_per_row;
+  const int ncols = 31 * g.stride + 3;
   float acc[36 * NC];
 #pragma unroll
   for (int j = 0; j < 36 * NC; ++j) acc[j] = 0.f;
-  for (int p0 = warp * PX; p0 < M; p0 += nwarps * PX) {
-    float gv[PX][NC];
-    int nn[PX], ih0[PX], iw0[PX];
-#pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      const int p = p0 + px;
-      const bool pok = p < M;
-      const int ow = p % g.OW;
-      const int t = p / g.OW;
-      const int oh = t % g.OH;
-      nn[px] = pok ? t / g.OH : -1;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) gv[px][j] = pok ? to_f32(G[(int64_t)p * g.ldy + lane + 32 * j]) : 0.f;
-      ih0[px] = oh * g.stride - g.pad_t;
-      iw0[px] = ow * g.stride - g.pad_l;
-    }
+  for (int ch = warp; ch < nchunks; ch += nwarps) {
+    const int ow0 = (ch % chunks_per_row) * 32;
+    const int t = ch / chunks_per_row;
+    const int oh = t % g.OH, n = t / g.OH;
+    const int npx = min(32, g.OW - ow0);
+    const int iw_base = ow0 * g.stride - g.pad_l;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      float4 xv[PX][3];
+      const int ih = oh * g.stride - g.pad_t + r;
+      const bool rok = (unsigned)ih < (unsigned)g.IH;
+      const float* xrow = g.X + ((int64_t)n * g.IH + ih) * g.IW * 4;
+      for (int c = lane; c < ncols; c += 32) {
+        const int iw = iw_base + c;
+        sx[wib][r][c] = (rok && (unsigned)iw < (unsigned)g.IW) ? __ldg(reinterpret_cast<const float4*>(xrow + iw * 4))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const int64_t p0 = ((int64_t)n * g.OH + oh) * g.OW + ow0;
+    for (int px = 0; px < npx; ++px)
 #pragma unroll
-      for (int px = 0; px < PX; ++px)
+      for (int j = 0; j < NC; ++j) sdy[wib][px][lane + 32 * j] = G[(p0 + px) * g.ldy + lane + 32 * j];
+    __syncwarp();
+    for (int px = 0; px < npx; ++px) {
+      float gv[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) gv[j] = to_f32(sdy[wib][px][lane + 32 * j]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          const int ih = ih0[px] + r, iw = iw0[px] + q;
-          xv[px][q] = (nn[px] >= 0 && (unsigned)ih < (unsigned)g.IH && (unsigned)iw < (unsigned)g.IW)
-                          ? __ldg(reinterpret_cast<const float4*>(g.X + (((int64_t)nn[px] * g.IH + ih) * g.IW + iw) * 4))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-      for (int px = 0; px < PX; ++px)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const float xs[4] = {xv[px][q].x, xv[px][q].y, xv[px][q].z, xv[px][q].w};
-          const int k = r * 3 + q;
+          const float4 xv = sx[wib][r][px * g.stride + q];
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int j = 0; j < NC; ++j) acc[(k * 4 + c) * NC + j] = fmaf(xs[c], gv[px][j], acc[(k * 4 + c) * NC + j]);
+            for (int j = 0; j < NC; ++j)
+              acc[((r * 3 + q) * 4 + c) * NC + j] = fmaf(xs[c], gv[j], acc[((r * 3 + q) * 4 + c) * NC + j]);
         }
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int k = 0; k < 36; ++k)
@@ -705,7 +710,7 @@ static int check_conv(const basi_conv_desc* d, const basi_tensor* x, const basi_
 // conv1_1-shaped problem: fp32 NHWC4 input, 3x3, dilation 1, 32 or 64 output channels
 static bool stem_shape(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
   return x->dtype == BASI_F32 && x->c == 4 && x->ld == 4 && aligned16(x->ptr) && d->kh == 3 && d->kw == 3 &&
-         d->dil == 1 && (y->c == 32 || y->c == 64) && y->ld % 4 == 0 && aligned16(y->ptr) &&
+         d->dil == 1 && d->stride <= 2 && (y->c == 32 || y->c == 64) && y->ld % 4 == 0 && aligned16(y->ptr) &&
          getenv("BASI_NO_STEM") == nullptr;
 }
 static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
@@ -795,14 +800,14 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   if (stem_shape(d, x, dy) && !dbias) {
     StemConv s = stem_args(d, x, dy);
     s.dW = dw;
-    int grid = basi::sm_count() * 2;
+    int grid = basi::sm_count() * 6;
     cudaStream_t st = (cudaStream_t)stream;
     if (dy->dtype == BASI_BF16) {
-      if (dy->c == 32) basi::launch(stem_wgrad_kernel<bf16, 32>, grid, 256, 0, st, s);
-      else basi::launch(stem_wgrad_kernel<bf16, 64>, grid, 256, 0, st, s);
+      if (dy->c == 32) basi::launch(stem_wgrad_kernel<bf16, 32>, grid, 128, 0, st, s);
+      else basi::launch(stem_wgrad_kernel<bf16, 64>, grid, 128, 0, st, s);
     } else {
-      if (dy->c == 32) basi::launch(stem_wgrad_kernel<float, 32>, grid, 256, 0, st, s);
-      else basi::launch(stem_wgrad_kernel<float, 64>, grid, 256, 0, st, s);
+      if (dy->c == 32) basi::launch(stem_wgrad_kernel<float, 32>, grid, 128, 0, st, s);
+      else basi::launch(stem_wgrad_kernel<float, 64>, grid * 2, 64, 0, st, s);     // 2 warps per block (shared memory)
     }
     BASI_CHECK_LAUNCH("conv_wgrad(stem)");
     return BASI_OK;

@@ -222,67 +222,76 @@ struct MultiPool {
   int ldy[MP_MAX];
 };
 
+constexpr int MP_CH = 128;   // channels per block of the accumulation pass
+constexpr int MP_RB = 8;     // rows per block
+
+// thread = (8-channel group, row of the band, half of the columns): walks along its row keeping the running window
+// sums of every pool in registers and flushes a pool's sum to the block's shared-memory cells when the column window
+// ends (at most 16 threads ever add to the same cell)
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_multi_acc_kernel(const T* __restrict__ x, int ldx, int H, int W, int C,
-                                                                const MultiPool mp, int RB, float* __restrict__ scratch) {
+                                                                const MultiPool mp, float* __restrict__ scratch) {
   pdl_prologue();
   constexpr int VN = Vec<T>::N;
-  constexpr int CH = 64;                       // channels per block
-  extern __shared__ float cells_s[];           // [mp.cells][CH]
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < mp.cells * CH; i += blockDim.x * blockDim.y) cells_s[i] = 0.f;
+  constexpr int CGS = MP_CH / VN;              // channel groups per block
+  constexpr int PARTS = 256 / (CGS * MP_RB);   // column ranges per row (bf16: 2, f32: 1)
+  extern __shared__ float cells_s[];           // [mp.cells][MP_CH]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < mp.cells * MP_CH; i += 256) cells_s[i] = 0.f;
   __syncthreads();
-  const int n = blockIdx.z, c0 = blockIdx.y * CH + threadIdx.x * VN;
-  const int h0 = blockIdx.x * RB, h1 = min(h0 + RB, H);
-  const bool cok = threadIdx.x * VN < CH && c0 < C;
-  if (cok) {
-    for (int w = threadIdx.y; w < W; w += blockDim.y) {
-      float acc[MP_MAX][VN];
-      int cur[MP_MAX];
+  const int cg = tid % CGS, row = (tid / CGS) % MP_RB, part = tid / (CGS * MP_RB);
+  const int n = blockIdx.z, c0 = blockIdx.y * MP_CH + cg * VN;
+  const int h0 = blockIdx.x * MP_RB, h = h0 + row;
+  const int wpp = (W + PARTS - 1) / PARTS, w0 = part * wpp, w1 = min(w0 + wpp, W);
+  if (h < H && c0 < C && part < PARTS) {
+    float acc[MP_MAX][VN];
+    int cur[MP_MAX];
+#pragma unroll
+    for (int p = 0; p < MP_MAX; ++p) {
+      cur[p] = p < mp.np ? w0 / mp.k[p] : 0;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
+    }
+    auto flush = [&](int p) {
+      const int oh = h / mp.k[p];
+      if (oh < mp.OH[p] && cur[p] < mp.OW[p]) {
+        float* d = cells_s + (size_t)(mp.cell0[p] + oh * mp.OW[p] + cur[p]) * MP_CH + cg * VN;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) atomicAdd(d + j, acc[p][j]);
+      }
+    };
+    const T* xr = x + (((int64_t)n * H + h) * W) * ldx + c0;
+#pragma unroll 4
+    for (int w = w0; w < w1; ++w) {
+      const Vec<T> v = Vec<T>::load(xr + (int64_t)w * ldx);
 #pragma unroll
       for (int p = 0; p < MP_MAX; ++p) {
-        cur[p] = p < mp.np ? h0 / mp.k[p] : 0;
-#pragma unroll
-        for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
-      }
-      auto flush = [&](int p) {
+        if (p >= mp.np) continue;
         const int ow = w / mp.k[p];
-        if (cur[p] < mp.OH[p] && ow < mp.OW[p]) {
-          float* d = cells_s + (size_t)(mp.cell0[p] + cur[p] * mp.OW[p] + ow) * CH + threadIdx.x * VN;
+        if (ow != cur[p]) {
+          flush(p);
+          cur[p] = ow;
 #pragma unroll
-          for (int j = 0; j < VN; ++j) atomicAdd(d + j, acc[p][j]);
+          for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
         }
-      };
-      for (int h = h0; h < h1; ++h) {
-        const Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + h) * W + w) * ldx + c0);
 #pragma unroll
-        for (int p = 0; p < MP_MAX; ++p) {
-          if (p >= mp.np) continue;
-          const int oh = h / mp.k[p];
-          if (oh != cur[p]) {
-            flush(p);
-            cur[p] = oh;
-#pragma unroll
-            for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < VN; ++j) acc[p][j] += v.v[j];
-        }
+        for (int j = 0; j < VN; ++j) acc[p][j] += v.v[j];
       }
-#pragma unroll
-      for (int p = 0; p < MP_MAX; ++p)
-        if (p < mp.np) flush(p);
     }
+#pragma unroll
+    for (int p = 0; p < MP_MAX; ++p)
+      if (p < mp.np) flush(p);
   }
   __syncthreads();
   // the cells this band touched -> fp32 scratch [N][cells][C]
+  const int h1 = min(h0 + MP_RB, H);
   for (int p = 0; p < mp.np; ++p) {
     const int oh_lo = h0 / mp.k[p], oh_hi = min((h1 - 1) / mp.k[p], mp.OH[p] - 1);
     const int ncell = (oh_hi - oh_lo + 1) * mp.OW[p];
-    for (int i = tid; i < ncell * CH; i += blockDim.x * blockDim.y) {
-      const int cell = mp.cell0[p] + oh_lo * mp.OW[p] + i / CH, ch = i % CH;
-      if (blockIdx.y * CH + ch < C)
-        atomicAdd(scratch + ((size_t)n * mp.cells + cell) * C + blockIdx.y * CH + ch, cells_s[(size_t)cell * CH + ch]);
+    for (int i = tid; i < ncell * MP_CH; i += 256) {
+      const int cell = mp.cell0[p] + oh_lo * mp.OW[p] + i / MP_CH, ch = i % MP_CH;
+      if (blockIdx.y * MP_CH + ch < C)
+        atomicAdd(scratch + ((size_t)n * mp.cells + cell) * C + blockIdx.y * MP_CH + ch, cells_s[(size_t)cell * MP_CH + ch]);
     }
   }
 }
@@ -992,14 +1001,13 @@ int basi_avgpool_multi_fwd(const basi_tensor* x, int n_pools, const int* ks, con
   MultiPool mp;
   int rc = fill_multipool(&mp, x, n_pools, ks, ys, "avgpool_multi fwd");
   if (rc) return rc;
-  BASI_CHECK_ARG(scratch && mp.cells * 64 * sizeof(float) <= 48 * 1024, "avgpool_multi fwd: null scratch / too many cells");
+  BASI_CHECK_ARG(scratch && mp.cells * MP_CH * sizeof(float) <= 48 * 1024,
+                 "avgpool_multi fwd: null scratch / too many cells");
   cudaStream_t st = (cudaStream_t)stream;
-  const int RB = 8;
   DISPATCH_T(x->dtype, {
-    dim3 block(64 / Vec<T>::N, 256 / (64 / Vec<T>::N));
-    dim3 grid((x->h + RB - 1) / RB, (x->c + 63) / 64, x->n);
-    basi::launch(avgpool_multi_acc_kernel<T>, grid, block, (size_t)mp.cells * 64 * sizeof(float), st, (const T*)x->ptr,
-                 x->ld, x->h, x->w, x->c, mp, RB, scratch);
+    dim3 grid((x->h + MP_RB - 1) / MP_RB, (x->c + MP_CH - 1) / MP_CH, x->n);
+    basi::launch(avgpool_multi_acc_kernel<T>, grid, dim3(256), (size_t)mp.cells * MP_CH * sizeof(float), st,
+                 (const T*)x->ptr, x->ld, x->h, x->w, x->c, mp, scratch);
     int64_t total = (int64_t)x->n * mp.cells * (x->c / Vec<T>::N);
     basi::launch(avgpool_multi_finalize_kernel<T>, grid_for(total, 256), 256, 0, st, mp, x->c, scratch, total);
   })
