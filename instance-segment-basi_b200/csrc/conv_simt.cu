@@ -690,6 +690,109 @@ __global__ void __launch_bounds__(128) stem_wgrad_kernel(const StemConv g) {
   for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) atomicAdd(g.dW + i, red[i]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Segment heads conv6_n* (BAISPSPNet.py:722-724): a 1x1 convolution to 1..4 fp32 logit channels is a per-pixel dot
+// product, not a GEMM tile.  fprop: warp per pixel; dgrad: thread per 128-bit fragment of dx; wgrad: thread owns a
+// channel group and walks pixels, block reduction, one atomic per weight per block (+ the bias gradient).
+// ------------------------------------------------------------------------------------------
+template <typename TX, int CO>
+__global__ void __launch_bounds__(256) head_fprop_kernel(const TX* __restrict__ x, int ldx, int C, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int ldy,
+                                                         int relu, int64_t M) {
+  constexpr int VN = Vec<TX>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int cgs = C / VN;
+  for (int64_t p = warp; p < M; p += nwarps) {
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    for (int cg = lane; cg < cgs; cg += 32) {
+      const Vec<TX> v = Vec<TX>::load(x + p * ldx + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[o] = fmaf(v.v[j], __ldg(w + (cg * VN + j) * CO + o), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        float r = acc[o] + (bias ? bias[o] : 0.f);
+        y[p * ldy + o] = relu ? fmaxf(r, 0.f) : r;
+      }
+    }
+  }
+}
+
+template <typename TD, int CO>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w,
+                                                         TD* __restrict__ dx, int ldx, int C, int acc, int64_t total) {
+  constexpr int VN = Vec<TD>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t p = i / cgs;
+    float g[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) g[o] = dy[p * ldy + o];
+    Vec<TD> r = acc ? Vec<TD>::load(dx + p * ldx + cg * VN) : Vec<TD>::zero();
+#pragma unroll
+    for (int j = 0; j < VN; ++j)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) r.v[j] = fmaf(g[o], __ldg(w + (cg * VN + j) * CO + o), r.v[j]);
+    r.store(dx + p * ldx + cg * VN);
+  }
+}
+
+template <typename TX, int CO>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const TX* __restrict__ x, int ldx, int C, const float* __restrict__ dy,
+                                                         int ldy, float* __restrict__ dw, float* __restrict__ dbias,
+                                                         int64_t M) {
+  constexpr int VN = Vec<TX>::N;
+  extern __shared__ float hred[];   // [blockDim.y][blockDim.x][VN*CO + CO]
+  const int cg = threadIdx.x;       // blockDim.x == C / VN
+  float acc[VN][CO], bsum[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    bsum[o] = 0.f;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j][o] = 0.f;
+  }
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < M; p += (int64_t)gridDim.x * blockDim.y) {
+    const Vec<TX> v = Vec<TX>::load(x + p * ldx + cg * VN);
+    float g[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      g[o] = dy[p * ldy + o];
+      bsum[o] += g[o];
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[j][o] = fmaf(v.v[j], g[o], acc[j][o]);
+  }
+  constexpr int PER = VN * CO + CO;
+  float* mine = hred + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * PER;
+#pragma unroll
+  for (int j = 0; j < VN; ++j)
+#pragma unroll
+    for (int o = 0; o < CO; ++o) mine[j * CO + o] = acc[j][o];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) mine[VN * CO + o] = bsum[o];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int k = 0; k < PER; ++k) {
+      float t = 0.f;
+      for (int yy = 0; yy < (int)blockDim.y; ++yy) t += hred[((size_t)yy * blockDim.x + threadIdx.x) * PER + k];
+      if (k < VN * CO) atomicAdd(dw + (cg * VN + k / CO) * CO + (k % CO), t);
+      else if (dbias && cg == 0) atomicAdd(dbias + (k - VN * CO), t);
+    }
+  }
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace basi
@@ -722,6 +825,21 @@ static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const b
   return s;
 }
 
+// conv6_n-shaped problem: 1x1, stride 1, no padding, <= 4 fp32 output channels
+static bool head_shape(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  const int vn = x->dtype == BASI_F32 ? 4 : 8;
+  return d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && y->c >= 1 && y->c <= 4 &&
+         y->dtype == BASI_F32 && x->h == y->h && x->w == y->w && basi::vec_ok(x) && x->c / vn <= 256 &&
+         getenv("BASI_NO_HEAD") == nullptr;
+}
+#define BASI_HEAD_CO(co, ...)                    \
+  switch (co) {                                  \
+    case 1: { constexpr int CO = 1; __VA_ARGS__ } break; \
+    case 2: { constexpr int CO = 2; __VA_ARGS__ } break; \
+    case 3: { constexpr int CO = 3; __VA_ARGS__ } break; \
+    default: { constexpr int CO = 4; __VA_ARGS__ } break; \
+  }
+
 template <int MODE>
 static int launch_gemm_conv(const GemmConv& g, int ts, int td, cudaStream_t st) {
   dim3 grid((g.M + BM - 1) / BM, (g.DC + BN - 1) / BN);
@@ -739,6 +857,21 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
   int rc = check_conv(d, x, y, "conv_fprop");
   if (rc) return rc;
   BASI_CHECK_ARG(w, "conv_fprop: null weights");
+  if (head_shape(d, x, y)) {
+    const int64_t M = pixels(y);
+    const int grid = basi::grid_for(M * 32, 256, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    BASI_HEAD_CO(y->c, {
+      if (x->dtype == BASI_BF16)
+        basi::launch(head_fprop_kernel<bf16, CO>, grid, 256, 0, st, (const bf16*)x->ptr, x->ld, x->c, w, bias, (float*)y->ptr,
+                     y->ld, d->relu, M);
+      else
+        basi::launch(head_fprop_kernel<float, CO>, grid, 256, 0, st, (const float*)x->ptr, x->ld, x->c, w, bias,
+                     (float*)y->ptr, y->ld, d->relu, M);
+    })
+    BASI_CHECK_LAUNCH("conv_fprop(head)");
+    return BASI_OK;
+  }
   if (stem_shape(d, x, y) && !bias) {
     StemConv s = stem_args(d, x, y);
     s.W = w; s.relu = d->relu;
@@ -776,6 +909,22 @@ int basi_conv_dgrad(const basi_conv_desc* d, const basi_tensor* dy, const float*
   int rc = check_conv(d, dx, dy, "conv_dgrad");
   if (rc) return rc;
   BASI_CHECK_ARG(w, "conv_dgrad: null weights");
+  if (head_shape(d, dx, dy)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BASI_HEAD_CO(dy->c, {
+      if (dx->dtype == BASI_BF16) {
+        const int64_t total = pixels(dx) * (dx->c / 8);
+        basi::launch(head_dgrad_kernel<bf16, CO>, basi::grid_for(total, 256), 256, 0, st, (const float*)dy->ptr, dy->ld, w,
+                     (bf16*)dx->ptr, dx->ld, dx->c, accumulate, total);
+      } else {
+        const int64_t total = pixels(dx) * (dx->c / 4);
+        basi::launch(head_dgrad_kernel<float, CO>, basi::grid_for(total, 256), 256, 0, st, (const float*)dy->ptr, dy->ld, w,
+                     (float*)dx->ptr, dx->ld, dx->c, accumulate, total);
+      }
+    })
+    BASI_CHECK_LAUNCH("conv_dgrad(head)");
+    return BASI_OK;
+  }
   GemmConv g{};
   g.S = dy->ptr; g.D = dx->ptr; g.W = w; g.bias = nullptr;
   g.N = dx->n; g.SH = dy->h; g.SW = dy->w; g.SC = dy->c; g.lds = dy->ld;
@@ -797,6 +946,28 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   int rc = check_conv(d, x, dy, "conv_wgrad");
   if (rc) return rc;
   BASI_CHECK_ARG(dw, "conv_wgrad: null dw");
+  if (head_shape(d, x, dy)) {
+    const int vn = x->dtype == BASI_F32 ? 4 : 8;
+    const int bx = x->c / vn;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    const int64_t M = pixels(dy);
+    int64_t want = (M + by * 8 - 1) / (by * 8);
+    const int64_t cap = (int64_t)basi::sm_count() * 4;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    BASI_HEAD_CO(dy->c, {
+      const size_t smem = (size_t)bx * by * (vn * CO + CO) * sizeof(float);
+      if (x->dtype == BASI_BF16)
+        basi::launch(head_wgrad_kernel<bf16, CO>, dim3(grid), dim3(bx, by), smem, st, (const bf16*)x->ptr, x->ld, x->c,
+                     (const float*)dy->ptr, dy->ld, dw, dbias, M);
+      else
+        basi::launch(head_wgrad_kernel<float, CO>, dim3(grid), dim3(bx, by), smem, st, (const float*)x->ptr, x->ld, x->c,
+                     (const float*)dy->ptr, dy->ld, dw, dbias, M);
+    })
+    BASI_CHECK_LAUNCH("conv_wgrad(head)");
+    return BASI_OK;
+  }
   if (stem_shape(d, x, dy) && !dbias) {
     StemConv s = stem_args(d, x, dy);
     s.dW = dw;

@@ -934,9 +934,11 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
 }
 
 // (bx channel groups) x (by = 256/bx window threads, a power of two for the tree reduction); grid.y chunks
-static void pool_block(int cgs, int VN, dim3* block, size_t* smem, unsigned* chunks) {
+static void pool_block(int cgs, int VN, dim3* block, size_t* smem, unsigned* chunks, int64_t out_pixels = 1 << 30) {
   int bx = 1;
   while (bx * 2 <= 8 && bx * 2 <= cgs) bx *= 2;
+  // few output pixels (the 1x1 .. 6x6 pyramid maps): narrower channel slices per block so the grid still fills the GPU
+  while (bx > 1 && out_pixels * ((cgs + bx - 1) / bx) < 4 * (int64_t)sm_count()) bx /= 2;
   int by = 256 / bx;
   *block = dim3(bx, by);
   *smem = (size_t)bx * by * VN * sizeof(float);
@@ -1050,7 +1052,7 @@ int basi_bilinear_ac_bwd(const basi_tensor* dy, const basi_tensor* dx, int accum
     dim3 block;
     size_t smem;
     unsigned chunks;
-    pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks);
+    pool_block(dx->c / Vec<T>::N, Vec<T>::N, &block, &smem, &chunks, pixels(dx));
     basi::launch(bilinear_ac_bwd_kernel<T>, dim3((unsigned)pixels(dx), chunks), block, smem, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, ac_scale(dx->h, dy->h),
         ac_scale(dx->w, dy->w), accumulate);
   })
