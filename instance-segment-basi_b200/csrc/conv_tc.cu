@@ -168,6 +168,7 @@ struct ConvParams {
   int accumulate;
   int stages;
   int out_bufs;   // 1 or 2 output staging buffers (2: the TMA store of tile i overlaps the epilogue of tile i+1)
+  int debug;      // timing experiments only: 1 = skip the statistics atomics, 2 = skip the column sums too
   // optional fused batch-norm statistics of the produced tensor (fprop): per-channel sum / sum of squares of the
   // bf16-rounded outputs, double atomics per tile, last CTA finalizes bnp = [mean | istd | gamma*istd | beta]
   double* bn_sums;
@@ -226,10 +227,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
-  float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [4 warps][2*BN]
+  float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [row groups][2*BN] = 1024 floats
   // output staging for the TMA store: NBOX boxes of [128 px][64 ch] bf16, SWIZZLE_128B, 1024-B aligned
   constexpr int NBOX = (BN + 63) / 64;
-  uint8_t* stage_out = smem + (size_t)p.stages * STAGE + 1024 + 8 * BN * sizeof(float);
+  uint8_t* stage_out = smem + (size_t)p.stages * STAGE + 1024 + 1024 * sizeof(float);
   stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_out) + 1023) & ~(uintptr_t)1023);
   volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,6 +374,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t so_base = smem_u32(stage_out);
     const bool do_stats = p.bn_sums != nullptr;
     int it = 0, sidx = 0;
+    int run_nt = -1;              // fused statistics: channel tile of the running sums below
+    float run1 = 0.f, run2 = 0.f;
     for (int t = cid; t < total_tiles; t += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -404,6 +407,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 16; ++j) {
           __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          // rows outside the tensor are never stored (TMA clips them) but the statistics below are summed from the
+          // staging tile: for k > 1 such rows hold phantom outputs of the padded convolution, so they are zeroed
+          if (do_stats && !valid) pk[j] = 0u;
         }
         // row `row` of box (c/2): 128-byte line, 16-byte chunks XOR-swizzled with (row & 7) like TMA SWIZZLE_128B
         // (BN == 32: one 32-channel box, 64-byte rows, no swizzle)
@@ -414,24 +420,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[4 * v]),
                        "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
                        : "memory");
-        }
-        if (do_stats) {
-          // statistics of the values as stored (bf16-rounded).  Rows outside the tensor are masked: for k > 1 they
-          // hold phantom outputs of the padded convolution (their taps still reach valid pixels).
-          float f[32], sq[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-            const float b = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
-            f[2 * j] = a;
-            f[2 * j + 1] = b;
-            sq[2 * j] = a * a;
-            sq[2 * j + 1] = b * b;
-          }
-          warp_column_sums(f, lane);
-          warp_column_sums(sq, lane);
-          stat_s[q * (2 * BN) + c * 32 + lane] = f[0];
-          stat_s[q * (2 * BN) + BN + c * 32 + lane] = sq[0];
         }
       }
       tc_fence_before();
@@ -450,16 +438,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (do_stats) {
-        for (int col = (warp - 4) * 32 + lane; col < BN; col += 256) {
-          const float s1 = stat_s[col] + stat_s[2 * BN + col] + stat_s[4 * BN + col] + stat_s[6 * BN + col];
-          const float s2 = stat_s[BN + col] + stat_s[3 * BN + col] + stat_s[5 * BN + col] + stat_s[7 * BN + col];
-          double* rep = p.bn_sums + (size_t)(mt % BASI_BN_REPLICAS) * 2 * p.Cdst;
-          atomicAdd(rep + nt * BN + col, (double)s1);
-          atomicAdd(rep + p.Cdst + nt * BN + col, (double)s2);
+      if (do_stats && p.debug != 2) {
+        // statistics of the values as stored (bf16): column sums straight from the staging tile.  Thread = (column
+        // pair, group of rows): one conflict-free 32-bit shared-memory load per row (a warp reads 32 consecutive
+        // words of one 128-byte line) -- the 4 x 31-shuffle transpose-reduce this replaces cost 6 of the 8 us the
+        // statistics added to a conv4 1x1-increase fprop.
+        constexpr int CP = BN / 2, RG = 256 / CP, RPG = BM / RG;
+        const int te = (int)threadIdx.x - 128, cp = te % CP, rg = te / CP;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const uint32_t colbase = BN >= 64 ? so + (uint32_t)(cp >> 5) * A_BYTES : so;
+#pragma unroll 8
+        for (int r = rg * RPG; r < (rg + 1) * RPG; ++r) {
+          const uint32_t addr = BN >= 64 ? colbase + (uint32_t)r * 128 + (uint32_t)((((cp & 31) >> 2) ^ (r & 7)) << 4) +
+                                               (uint32_t)(cp & 3) * 4
+                                         : colbase + (uint32_t)r * (2 * BN) + (uint32_t)cp * 4;
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          s0 += a; q0 = fmaf(a, a, q0);
+          s1 += b; q1 = fmaf(b, b, q1);
+        }
+        stat_s[rg * (2 * BN) + 2 * cp] = s0;
+        stat_s[rg * (2 * BN) + 2 * cp + 1] = s1;
+        stat_s[rg * (2 * BN) + BN + 2 * cp] = q0;
+        stat_s[rg * (2 * BN) + BN + 2 * cp + 1] = q1;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (te < BN) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < RG; ++g2) {
+            t1 += stat_s[g2 * (2 * BN) + te];
+            t2 += stat_s[g2 * (2 * BN) + BN + te];
+          }
+          // running sums of this CTA's tiles of one channel tile; flushed (2 double atomics per column) only when
+          // the channel tile changes and at the end
+          if (nt != run_nt) {
+            if (run_nt >= 0 && p.debug == 0) {
+              double* rep = p.bn_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * p.Cdst;
+              atomicAdd(rep + run_nt * BN + te, (double)run1);
+              atomicAdd(rep + p.Cdst + run_nt * BN + te, (double)run2);
+            }
+            run_nt = nt; run1 = 0.f; run2 = 0.f;
+          }
+          run1 += t1;
+          run2 += t2;
         }
       }
       }   // sub
+    }
+    if (do_stats && run_nt >= 0 && (int)threadIdx.x - 128 < BN && p.debug == 0) {
+      double* rep = p.bn_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * p.Cdst;
+      atomicAdd(rep + run_nt * BN + ((int)threadIdx.x - 128), (double)run1);
+      atomicAdd(rep + p.Cdst + run_nt * BN + ((int)threadIdx.x - 128), (double)run2);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
     if (p.bn_sums != nullptr) __threadfence();
@@ -913,7 +943,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // MMA = 128 B/clk); N = 256 needs 96 B/clk.  Measured on conv5_4 dgrad: 975 -> 1404 TFLOP/s.  Per k-step a 256
     // tile costs ~1.4x a 128 tile and there are half as many tiles: pick the cheaper wave count; small-K layers
     // (overhead-bound) stay at 128.
-    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= 8 && !getenv("BASI_TC_NO_BN256")) {
+    const int bn256_mink = getenv("BASI_TC_BN256_MINK") ? atoi(getenv("BASI_TC_BN256_MINK")) : 8;
+    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !getenv("BASI_TC_NO_BN256")) {
       const long t128 = ((long)m_tiles * (ndim / 128) + sms - 1) / sms * 10;
       const long t256 = ((long)m_tiles * (ndim / 256) + sms - 1) / sms * 14;
       if (t256 < t128) bn = 256;
@@ -965,7 +996,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // shared memory for pipeline stages
     cp.out_bufs = (cp.taps * cp.k_chunks <= 8 || pl->mt == 2) ? 2 : 1;
     const int out_stage = cp.out_bufs * ((bn + 63) / 64) * A_BYTES;
-    const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 8 * bn * (int)sizeof(float) + 1024 /*align*/ + out_stage;
+    const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 1024 * (int)sizeof(float) + 1024 /*align*/ + out_stage;
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (getenv("BASI_TC_STAGES") && atoi(getenv("BASI_TC_STAGES")) >= 2 && atoi(getenv("BASI_TC_STAGES")) < stages)
@@ -985,6 +1016,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       pl->grid = total < sms ? total : sms;
     }
     if (getenv("BASI_TC_DEBUG_EMPTY")) cp.m_tiles = 0;   // timing experiment: prologue + teardown only
+    cp.debug = getenv("BASI_TC_DEBUG_STATS") ? atoi(getenv("BASI_TC_DEBUG_STATS")) : 0;
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
     const int cin = a->c, cout = b->c;

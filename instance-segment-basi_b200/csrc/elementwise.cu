@@ -86,9 +86,11 @@ __global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, int ldx, int H, i
 #pragma unroll
     for (int j = 0; j < VN; ++j) o.v[j] = best[j];
     o.store(y + p * ldy + cg * VN);
-    uint8_t* a = amax + p * C + cg * VN;
+    uint32_t ab[2] = {0u, 0u};
 #pragma unroll
-    for (int j = 0; j < VN; ++j) a[j] = bi[j];
+    for (int j = 0; j < VN; ++j) ab[j >> 2] |= (uint32_t)bi[j] << (8 * (j & 3));
+    if (VN == 8) *reinterpret_cast<uint2*>(amax + p * C + cg * VN) = make_uint2(ab[0], ab[1]);
+    else *reinterpret_cast<uint32_t*>(amax + p * C + cg * VN) = ab[0];
   }
 }
 
@@ -122,10 +124,18 @@ __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH,
         if (ow >= OW) continue;
         int64_t op = ((int64_t)n * OH + oh) * OW + ow;
         Vec<T> d = Vec<T>::load(dy + op * ldy + cg * VN);
-        const uint8_t* a = amax + op * C + cg * VN;
+        // the VN argmax bytes of this fragment in one load (C % VN == 0 keeps them VN-byte aligned)
+        uint32_t ab[2];
+        if (VN == 8) {
+          const uint2 t2 = *reinterpret_cast<const uint2*>(amax + op * C + cg * VN);
+          ab[0] = t2.x; ab[1] = t2.y;
+        } else {
+          ab[0] = *reinterpret_cast<const uint32_t*>(amax + op * C + cg * VN);
+          ab[1] = 0;
+        }
 #pragma unroll
         for (int j = 0; j < VN; ++j)
-          if (a[j] == (uint8_t)(r * 3 + s)) g.v[j] += d.v[j];
+          if (((ab[j >> 2] >> (8 * (j & 3))) & 0xffu) == (uint32_t)(r * 3 + s)) g.v[j] += d.v[j];
       }
     }
     g.store(dx + p * ldx + cg * VN);
