@@ -255,17 +255,18 @@ __global__ void __launch_bounds__(256) avgpool_multi_acc_kernel(const T* __restr
   const int wpp = (W + PARTS - 1) / PARTS, w0 = part * wpp, w1 = min(w0 + wpp, W);
   if (h < H && c0 < C && part < PARTS) {
     float acc[MP_MAX][VN];
-    int cur[MP_MAX];
+    int cur[MP_MAX], nextb[MP_MAX], oh[MP_MAX];   // current column cell, its end column, this row's row cell
 #pragma unroll
     for (int p = 0; p < MP_MAX; ++p) {
       cur[p] = p < mp.np ? w0 / mp.k[p] : 0;
+      nextb[p] = p < mp.np ? (cur[p] + 1) * mp.k[p] : (1 << 30);
+      oh[p] = p < mp.np ? h / mp.k[p] : 0;
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
     }
     auto flush = [&](int p) {
-      const int oh = h / mp.k[p];
-      if (oh < mp.OH[p] && cur[p] < mp.OW[p]) {
-        float* d = cells_s + (size_t)(mp.cell0[p] + oh * mp.OW[p] + cur[p]) * MP_CH + cg * VN;
+      if (oh[p] < mp.OH[p] && cur[p] < mp.OW[p]) {
+        float* d = cells_s + (size_t)(mp.cell0[p] + oh[p] * mp.OW[p] + cur[p]) * MP_CH + cg * VN;
 #pragma unroll
         for (int j = 0; j < VN; ++j) atomicAdd(d + j, acc[p][j]);
       }
@@ -277,10 +278,10 @@ __global__ void __launch_bounds__(256) avgpool_multi_acc_kernel(const T* __restr
 #pragma unroll
       for (int p = 0; p < MP_MAX; ++p) {
         if (p >= mp.np) continue;
-        const int ow = w / mp.k[p];
-        if (ow != cur[p]) {
+        if (w == nextb[p]) {                       // the column window of pool p ends here (no division per element)
           flush(p);
-          cur[p] = ow;
+          ++cur[p];
+          nextb[p] += mp.k[p];
 #pragma unroll
           for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
         }
