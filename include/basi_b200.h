@@ -133,6 +133,16 @@ int basi_bn_bwd_apply_bits(const basi_tensor* dout, const unsigned char* maskbit
                            const float* bnp, const float* coef, const basi_tensor* dx, const basi_tensor* dres,
                            int dres_accumulate, void* stream);
 
+/* Cooperative streamed backward: basi_bn_bwd_reduce[_bits] + basi_bn_bwd_apply[_bits] in ONE cooperative launch (grid
+ * barrier between the two passes, second pass in reverse row order for L2 reuse).  For the tensors too large for
+ * basi_bn_bwd_fused: residual junctions (mask = `out` or `maskbits`, optional residual gradient `dres`) and the
+ * 160x160 layers.  `barrier` is a zero-initialised word.  Query with basi_bn_bwd_coop_supported (1 = yes). */
+int basi_bn_bwd_coop_supported(const basi_tensor* x, int has_out, int has_bits, int dres_accumulate);
+int basi_bn_bwd_coop(const basi_tensor* dout, const basi_tensor* out, const unsigned char* maskbits,
+                     const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums, double count,
+                     float* dgamma, float* dbeta, float* coef, uint32_t* barrier, const basi_tensor* dx,
+                     const basi_tensor* dres, int dres_accumulate, void* stream);
+
 /* Resident backward: basi_bn_bwd_reduce + basi_bn_bwd_apply (no stored-output mask, no residual) in ONE cooperative
  * launch that keeps dout and x in shared memory between the two phases (reads each once).  Needs dense rows
  * (ld == c) and a tensor small enough that 2 * bytes(x) / #SMs fits in shared memory; query with

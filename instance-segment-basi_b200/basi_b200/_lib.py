@@ -51,6 +51,8 @@ SIGNATURES = {
     "basi_bn_apply_bits": [_TP, _P, _TP, _P, _i, _TP, _P, _P],
     "basi_bn_bwd_reduce_bits": [_TP, _P, _TP, _P, _P, _d, _P, _P, _P, _P, _P],
     "basi_bn_bwd_apply_bits": [_TP, _P, _TP, _P, _P, _TP, _TP, _i, _P],
+    "basi_bn_bwd_coop_supported": [_TP, _i, _i, _i],
+    "basi_bn_bwd_coop": [_TP, _TP, _P, _TP, _P, _i, _P, _d, _P, _P, _P, _P, _TP, _TP, _i, _P],
     "basi_bn_bwd_fused_supported": [_TP],
     "basi_bn_bwd_fused": [_TP, _TP, _P, _i, _P, _d, _P, _P, _P, _P, _TP, _P],
     "basi_avgpool_multi_fwd": [_TP, _i, _P, _P, _P, _P],

@@ -111,6 +111,7 @@ class Engine(object):
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.mask_bits = not os.environ.get("BASI_NO_MASK_BITS")
         self.fuse_pools = not os.environ.get("BASI_NO_POOL_FUSION")
+        self.coop_bn_bwd = not os.environ.get("BASI_NO_COOP_BN")
         self.fused_bn_bwd = 0
         self._tc_weights = []
         self._pack_table = None
@@ -665,6 +666,19 @@ class Engine(object):
                            C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.coef.data_ptr(),
                            rec.cnt_b, dx.ref, bytes=nb * 3, writes=[rec.gamma, rec.beta])
                 self.fused_bn_bwd += 1
+                continue
+            bits_t = op.get("bits")
+            if (self.coop_bn_bwd and not self.dry_run
+                    and _lib.load().basi_bn_bwd_coop_supported(x.ref, 1 if (mask is not None and bits_t is None) else 0,
+                                                               1 if bits_t is not None else 0, dacc) == 1):
+                # reduce + dx pass in one cooperative launch (grid barrier in between)
+                nr = 2 + (1.0 / 16 if bits_t is not None else (1 if mask is not None else 0))
+                self._call(self.bwd, "basi_bn_bwd_coop", dout.ref, mask if bits_t is None else None,
+                           bits_t.data_ptr() if bits_t is not None else None, x.ref, rec.bnp.data_ptr(), from_x,
+                           rec.dsums, C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta),
+                           rec.coef.data_ptr(), rec.cnt_b, dx.ref, dres, dacc,
+                           bytes=nb * (2 * nr + 1 + (0 if dres is None else (2 if dacc else 1))),
+                           writes=[rec.gamma, rec.beta])
                 continue
             if op.get("bits") is not None:
                 bits = op["bits"].data_ptr()

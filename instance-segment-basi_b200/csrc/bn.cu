@@ -496,6 +496,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
     }
     __syncthreads();
   }
+  // the ring memory may be reused by the caller (block reductions, a second pass with another geometry)
+  if (tid == 0)
+    for (int i = 0; i < a.nst; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * i) : "memory");
+  __syncthreads();
 }
 
 template <typename T, bool HAS_RES, bool RES_BN>
@@ -978,6 +982,189 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
   }
 }
 
+// ==========================================================================================================
+// Cooperative streamed backward for the tensors that do not fit the resident kernel (residual junctions, the
+// 160x160 layers): the reduce pass and the dx pass of the pair above in ONE launch with a grid barrier in between.
+// The second pass visits the rows in reverse, so most of what it re-reads is still in the 126 MB L2; one launch and
+// one tail instead of two.
+// ==========================================================================================================
+template <typename T, int MASK, bool DRES_ACC>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_coop_kernel(const StreamArgs a1, const StreamArgs a2, const float* __restrict__ bnp, int relu_from_x, int C,
+                   double* __restrict__ dsums, double count, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ coef, unsigned int* gbar, T* __restrict__ dx, int lddx, T* __restrict__ dres,
+                   int lddr) {
+  extern __shared__ __align__(128) uint8_t coop_smem[];
+  constexpr int VN = Pack<T>::N;
+  constexpr bool HAS_OUT = MASK == 1;
+  constexpr int NT1 = HAS_OUT ? 3 : 2;
+  constexpr int NT2 = NT1 + (DRES_ACC ? 1 : 0);
+  const int c0 = threadIdx.x * VN;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  float mean[VN], A[VN], beta[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    mean[i] = bnp[c0 + i];
+    A[i] = bnp[2 * C + c0 + i];
+    beta[i] = bnp[3 * C + c0 + i];
+  }
+  // ---- pass 1: per-channel sums
+  {
+    float fs[VN], fq[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) fs[i] = fq[i] = 0.f;
+    stream_rows<T, NT1, MASK == 2>(a1, [&](long long, Pack<T>(&f)[NT1], unsigned mb) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float xc = f[1].get(i) - mean[i];
+        float dy = f[0].get(i);
+        if (HAS_OUT) dy = f[NT1 - 1].get(i) > 0.f ? dy : 0.f;
+        else if (MASK == 2) dy = ((mb >> i) & 1u) ? dy : 0.f;
+        else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+        fs[i] += dy;
+        fq[i] = fmaf(dy, xc, fq[i]);
+      }
+    });
+    // block reduction over threadIdx.y in the (idle) ring memory, one double atomic per channel and block
+    float* red = reinterpret_cast<float*>(coop_smem);      // [blockDim.y][C][2]
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      red[((size_t)threadIdx.y * C + c0 + i) * 2] = fs[i];
+      red[((size_t)threadIdx.y * C + c0 + i) * 2 + 1] = fq[i];
+    }
+    __syncthreads();
+    double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
+    for (int c = tid; c < C; c += 256) {
+      double s1 = 0, s2 = 0;
+      for (int y = 0; y < (int)blockDim.y; ++y) {
+        s1 += (double)red[((size_t)y * C + c) * 2];
+        s2 += (double)red[((size_t)y * C + c) * 2 + 1];
+      }
+      atomicAdd(rep + c, s1);
+      atomicAdd(rep + C + c, s2 * (double)bnp[C + c]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) grid_barrier_thread0(gbar);
+  __syncthreads();
+  // ---- final sums -> coefficients (every CTA), gradients of gamma / beta (CTA 0)
+  float* coef_s = reinterpret_cast<float*>(coop_smem);     // [2][C]
+  for (int c = tid; c < C; c += 256) {
+    double s1 = 0, s2 = 0;
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      s1 += __ldcg(dsums + (size_t)r * 2 * C + c);
+      s2 += __ldcg(dsums + (size_t)r * 2 * C + C + c);
+    }
+    const float k1 = (float)(s1 / count), k2 = (float)(s2 / count);
+    coef_s[c] = k1;
+    coef_s[C + c] = k2;
+    if (blockIdx.x == 0) {
+      dbeta[c] += (float)s1;
+      dgamma[c] += (float)s2;
+      if (coef) {
+        coef[c] = k1;
+        coef[C + c] = k2;
+      }
+    }
+  }
+  __syncthreads();
+  float Bc[VN], Cc[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    Bc[i] = A[i] * coef_s[c0 + i];
+    Cc[i] = A[i] * bnp[C + c0 + i] * coef_s[C + c0 + i];
+  }
+  __syncthreads();   // coef_s lives in the ring memory pass 2 is about to overwrite
+  // ---- pass 2: dx (and the residual-path gradient)
+  stream_rows<T, NT2, MASK == 2>(a2, [&](long long row, Pack<T>(&f)[NT2], unsigned mb) {
+    Pack<T> o, dr;
+#pragma unroll
+    for (int i2 = 0; i2 < VN / 2; ++i2) {
+      float res[2], drs[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * i2 + h;
+        const float xc = f[1].get(i) - mean[i];
+        float dy = f[0].get(i);
+        if (HAS_OUT) dy = f[HAS_OUT ? 2 : 0].get(i) > 0.f ? dy : 0.f;
+        else if (MASK == 2) dy = ((mb >> i) & 1u) ? dy : 0.f;
+        else if (relu_from_x) dy = fmaf(xc, A[i], beta[i]) > 0.f ? dy : 0.f;
+        drs[h] = DRES_ACC ? f[NT2 - 1].get(i) + dy : dy;
+        res[h] = fmaf(A[i], dy, -Bc[i]) - xc * Cc[i];
+      }
+      o.set2(i2, res[0], res[1]);
+      dr.set2(i2, drs[0], drs[1]);
+    }
+    if (dres) dr.store(dres + row * lddr + c0);
+    o.store(dx + row * lddx + c0);
+  });
+}
+
+static bool coop_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("BASI_BN_NO_COOP") ? 1 : 0;
+  return v == 1;
+}
+
+// returns false when the tensor does not take the cooperative streamed path
+template <typename T>
+static bool launch_bwd_coop(bool dry, const basi_tensor* dout, const basi_tensor* out, const unsigned char* bits,
+                            const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums, double count,
+                            float* dgamma, float* dbeta, float* coef, uint32_t* gbar, const basi_tensor* dx,
+                            const basi_tensor* dres, int dres_acc, cudaStream_t st) {
+  if (stream_disabled() || coop_disabled()) return false;
+  const int es = sizeof(T);
+  const bool acc = dres && dres_acc;
+  const int nt1 = out ? 3 : 2, nt2 = nt1 + (acc ? 1 : 0);
+  const int64_t R = pixels(x);
+  const size_t red_bytes = (size_t)(256 / (x->c * es / 16 > 0 ? x->c * es / 16 : 1)) * x->c * 2 * sizeof(float);
+  StreamGeom g1 = stream_geom(R, x->c, es, nt1, red_bytes, bits != nullptr);
+  StreamGeom g2 = stream_geom(R, x->c, es, nt2, 0, bits != nullptr);
+  if (!g1.ok || !g2.ok) return false;
+  const size_t smem = g1.smem > g2.smem ? g1.smem : g2.smem;
+  if (smem > 110 * 1024) return false;                     // two CTAs per SM must stay co-resident
+  if (dry) return true;
+  StreamArgs a1{}, a2{};
+  fill_stream_args(&a1, g1, R, x->c, es, 0);
+  fill_stream_args(&a2, g2, R, x->c, es, 1);
+  a1.bits = a2.bits = bits;
+  int k = 0;
+  a1.src[k] = a2.src[k] = (const char*)dout->ptr; a1.ldb[k] = a2.ldb[k] = (long long)dout->ld * es; ++k;
+  a1.src[k] = a2.src[k] = (const char*)x->ptr; a1.ldb[k] = a2.ldb[k] = (long long)x->ld * es; ++k;
+  if (out) { a1.src[k] = a2.src[k] = (const char*)out->ptr; a1.ldb[k] = a2.ldb[k] = (long long)out->ld * es; ++k; }
+  if (acc) { a2.src[k] = (const char*)dres->ptr; a2.ldb[k] = (long long)dres->ld * es; ++k; }
+  T* dxp = (T*)dx->ptr;
+  T* drp = dres ? (T*)dres->ptr : nullptr;
+  const int lddr = dres ? dres->ld : 0;
+  const int C = x->c;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * sm_count());
+  cfg.blockDim = g1.block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define BASI_LAUNCH_COOP(MK, DA)                                                                                      \
+  do {                                                                                                                \
+    allow_smem(bn_bwd_coop_kernel<T, MK, DA>, smem);                                                                  \
+    cudaLaunchKernelEx(&cfg, bn_bwd_coop_kernel<T, MK, DA>, a1, a2, bnp, relu_from_x, C, dsums, count, dgamma, dbeta, \
+                       coef, (unsigned int*)gbar, dxp, (int)dx->ld, drp, lddr);                                       \
+  } while (0)
+  if (bits && acc) BASI_LAUNCH_COOP(2, true);
+  else if (bits) BASI_LAUNCH_COOP(2, false);
+  else if (out && acc) BASI_LAUNCH_COOP(1, true);
+  else if (out) BASI_LAUNCH_COOP(1, false);
+  else if (acc) BASI_LAUNCH_COOP(0, true);
+  else BASI_LAUNCH_COOP(0, false);
+#undef BASI_LAUNCH_COOP
+  return true;
+}
+
 struct ResidentGeom {
   bool ok;
   int grid, bx, by, rows_per_cta, chunk_rows, n_chunks;
@@ -1209,6 +1396,41 @@ int basi_bn_bwd_apply_bits(const basi_tensor* dout, const unsigned char* maskbit
                                           (cudaStream_t)stream, maskbits);
   BASI_CHECK_ARG(ok, "bn_bwd_apply_bits: streamed kernel unavailable");
   BASI_CHECK_LAUNCH("bn_bwd_apply_bits");
+  return BASI_OK;
+}
+
+int basi_bn_bwd_coop_supported(const basi_tensor* x, int has_out, int has_bits, int dres_accumulate) {
+  if (!x || !vec_ok(x) || (has_out && has_bits)) return 0;
+  if (has_bits && basi_bn_maskbits_supported(x) != 1) return 0;
+  basi_tensor dres = *x;
+  const basi_tensor* outp = has_out ? x : nullptr;
+  const unsigned char* bitsp = has_bits ? (const unsigned char*)x->ptr : nullptr;
+  bool ok = false;
+  DISPATCH_T(x->dtype, {
+    ok = launch_bwd_coop<T>(true, x, outp, bitsp, x, nullptr, 0, nullptr, 1.0, nullptr, nullptr, nullptr, nullptr, x,
+                            dres_accumulate ? &dres : nullptr, dres_accumulate, nullptr);
+  })
+  return ok ? 1 : 0;
+}
+
+int basi_bn_bwd_coop(const basi_tensor* dout, const basi_tensor* out, const unsigned char* maskbits,
+                     const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums, double count,
+                     float* dgamma, float* dbeta, float* coef, uint32_t* barrier, const basi_tensor* dx,
+                     const basi_tensor* dres, int dres_accumulate, void* stream) {
+  BASI_CHECK_ARG(dout && x && dx && bnp && dsums && dgamma && dbeta && barrier && count > 0 && vec_ok(dout) &&
+                     vec_ok(x) && vec_ok(dx) && same_shape(dout, x) && same_shape(dx, x) && dout->dtype == x->dtype &&
+                     dx->dtype == x->dtype && !(out && maskbits),
+                 "bn_bwd_coop: bad dout/x/dx");
+  BASI_CHECK_ARG(!out || (vec_ok(out) && same_shape(out, x) && out->dtype == x->dtype), "bn_bwd_coop: bad out");
+  BASI_CHECK_ARG(!dres || (vec_ok(dres) && same_shape(dres, x) && dres->dtype == x->dtype), "bn_bwd_coop: bad dres");
+  BASI_CHECK_ARG(!maskbits || basi_bn_maskbits_supported(x) == 1, "bn_bwd_coop: mask bits not supported for this tensor");
+  bool ok = false;
+  DISPATCH_T(x->dtype, {
+    ok = launch_bwd_coop<T>(false, dout, out, maskbits, x, bnp, relu_from_x, dsums, count, dgamma, dbeta, coef, barrier,
+                            dx, dres, dres_accumulate, (cudaStream_t)stream);
+  })
+  BASI_CHECK_ARG(ok, "bn_bwd_coop: tensor does not take the cooperative path (see basi_bn_bwd_coop_supported)");
+  BASI_CHECK_LAUNCH("bn_bwd_coop");
   return BASI_OK;
 }
 

@@ -791,3 +791,75 @@ def test_avgpool_multi_forward_backward(dtype, B, H, Cc, ks):
     dxb = act(base, td)
     call("basi_avgpool_multi_bwd", dptr, len(ks), karr, dxb.ref, 1)
     assert rel_err(host(dxb), want + base) < 2 * tol
+
+
+# ------------------------------------------------------------------ cooperative streamed BN backward (one launch)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("mask_mode,dres_mode", [("bits", "acc"), ("bits", "none"), ("out", "write"), ("out", "acc"),
+                                                 ("from_x", "none"), ("none", "none")])
+@pytest.mark.parametrize("shape", [(16, 40, 40, 512), (3, 37, 41, 128)])
+def test_batch_norm_backward_coop(dtype, mask_mode, dres_mode, shape):
+    """basi_bn_bwd_coop == basi_bn_bwd_reduce[_bits] + basi_bn_bwd_apply[_bits] for every mask / residual mode."""
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err
+    from basi_b200 import _lib
+    if mask_mode == "bits" and dtype == "f32":
+        pytest.skip("mask bits are bf16 only")
+    B, H, W, Cc = shape
+    rng = np.random.RandomState(23)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a) if dtype == "f32" else bf16_round
+    x, x2 = rnd(_u(rng, *shape) * 2 + 0.5), rnd(_u(rng, *shape))
+    dout, dres0 = rnd(_u(rng, *shape)), rnd(_u(rng, *shape))
+    gamma, beta = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
+    R = float(B * H * W)
+    xa, x2a, da = act(x, tdt), act(x2, tdt), act(dout, tdt)
+    has_out, has_bits = int(mask_mode == "out"), int(mask_mode == "bits")
+    dacc = 1 if dres_mode == "acc" else 0
+    if _lib.load().basi_bn_bwd_coop_supported(xa.ref, has_out, has_bits, dacc) != 1:
+        pytest.skip("tensor does not take the cooperative path on this device")
+    gd, bd = dev(gamma), dev(beta)
+    sums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
+    bnp = torch.zeros(4 * Cc, device="cuda:0")
+    cnt = torch.zeros(24, dtype=torch.int32, device="cuda:0")
+    call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
+         bnp.data_ptr(), cnt.data_ptr())
+    outa = empty_act(shape, tdt)
+    bits = torch.zeros(max(1, B * H * W * Cc // 8), dtype=torch.uint8, device="cuda:0")
+    junction = mask_mode in ("bits", "out")
+    if mask_mode == "bits":
+        call("basi_bn_apply_bits", xa.ref, bnp.data_ptr(), x2a.ref, None, 1, outa.ref, bits.data_ptr())
+    elif junction:
+        call("basi_bn_apply", xa.ref, bnp.data_ptr(), x2a.ref, None, 1, outa.ref)
+    from_x = 1 if mask_mode == "from_x" else 0
+    res = []
+    for coop in (False, True, True):
+        dsums = torch.zeros(2 * Cc * 8, dtype=torch.float64, device="cuda:0")
+        coef = torch.zeros(2 * Cc, device="cuda:0")
+        dgamma, dbeta = torch.full((Cc,), 0.25, device="cuda:0"), torch.full((Cc,), -0.5, device="cuda:0")
+        dxa = empty_act(shape, tdt, fill=5.0)
+        dra = act(dres0, tdt) if dres_mode != "none" else None
+        dres_ref = dra.ref if dra is not None else None
+        out_ref = outa.ref if mask_mode == "out" else None
+        bits_ptr = bits.data_ptr() if mask_mode == "bits" else None
+        if coop:
+            call("basi_bn_bwd_coop", da.ref, out_ref, bits_ptr, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(),
+                 C.c_double(R), dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 16, dxa.ref,
+                 dres_ref, dacc)
+        elif mask_mode == "bits":
+            call("basi_bn_bwd_reduce_bits", da.ref, bits_ptr, xa.ref, bnp.data_ptr(), dsums.data_ptr(), C.c_double(R),
+                 dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 8)
+            call("basi_bn_bwd_apply_bits", da.ref, bits_ptr, xa.ref, bnp.data_ptr(), coef.data_ptr(), dxa.ref, dres_ref,
+                 dacc)
+        else:
+            call("basi_bn_bwd_reduce", da.ref, out_ref, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(), C.c_double(R),
+                 dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 12)
+            call("basi_bn_bwd_apply", da.ref, out_ref, xa.ref, bnp.data_ptr(), coef.data_ptr(), from_x, dxa.ref,
+                 dres_ref, dacc)
+        res.append((host(dxa), host(dra) if dra is not None else None, host(dgamma), host(dbeta), host(coef)))
+    ptol = 1e-5 if dtype == "f32" else 1e-2
+    for k in (1, 2):
+        assert rel_err(res[k][0], res[0][0]) < ptol
+        if res[0][1] is not None:
+            assert np.array_equal(res[k][1], res[0][1])
+        for j in (2, 3, 4):
+            assert rel_err(res[k][j], res[0][j]) < 1e-5
