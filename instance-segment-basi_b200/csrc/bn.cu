@@ -680,6 +680,13 @@ static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem,
   const int SR = sr_mult * by;
   const int64_t n_slabs = (R + SR - 1) / SR;
   if (n_slabs < 64) return g;                                              // tiny tensors: the direct kernels
+  {
+    // a small single-tensor pass (forward BN+ReLU of the conv2..conv5 bottleneck layers: ~22 KB per CTA) gains
+    // nothing from the ring; the register-staged kernel measured 0.07 ms/step faster there
+    static int min1 = -1;
+    if (min1 < 0) min1 = getenv("BASI_BN_STREAM_MIN1") ? atoi(getenv("BASI_BN_STREAM_MIN1")) : 1000;
+    if (nt == 1 && n_slabs < min1) return g;
+  }
   static int ring_kb = 0;
   if (!ring_kb) {
     const char* e = getenv("BASI_BN_RING_KB");
@@ -830,6 +837,8 @@ struct ResidentArgs {
   int rows_per_cta;
   int chunk_rows;      // rows per bulk copy (per tensor)
   int n_chunks;
+  int debug;           // BASI_BN_RESIDENT_DEBUG: CTA 0 records globaltimer stamps (start, sums done, barrier passed,
+                       // coefficients ready, end) into g_resident_dbg
 };
 
 __device__ __forceinline__ void grid_barrier_thread0(unsigned int* ctr) {
@@ -849,8 +858,15 @@ __device__ __forceinline__ void grid_barrier_thread0(unsigned int* ctr) {
   __threadfence();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 1)
+__device__ unsigned long long g_resident_dbg[8];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename T, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
 bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int relu_from_x, int C,
                        double* __restrict__ dsums, double count, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float* __restrict__ coef, unsigned int* gbar) {
@@ -858,6 +874,8 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
   constexpr int VN = Pack<T>::N;
   const int tx = threadIdx.x, ty = threadIdx.y, by = blockDim.y;
   const int tid = ty * blockDim.x + tx;
+  const bool dbg = a.debug && blockIdx.x == 0 && tid == 0;
+  if (dbg) g_resident_dbg[0] = gtimer();
   const size_t slab = (size_t)a.rows_per_cta * a.row_bytes;
   uint8_t* s_dout = rs;
   uint8_t* s_x = rs + slab;
@@ -912,6 +930,7 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
       }
     }
   }
+  if (dbg) g_resident_dbg[5] = gtimer();
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
     red[((size_t)ty * C + c0 + i) * 2] = fs[i];
@@ -919,7 +938,7 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
   }
   __syncthreads();
   double* rep = dsums + (size_t)(blockIdx.x % NREP) * 2 * C;
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += NTHR) {
     double s1 = 0, s2 = 0;
     for (int y = 0; y < by; ++y) {
       s1 += (double)red[((size_t)y * C + c) * 2];
@@ -928,12 +947,13 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
     atomicAdd(rep + c, s1);
     atomicAdd(rep + C + c, s2 * (double)bnp[C + c]);
   }
-  __threadfence();
-  __syncthreads();
+  __syncthreads();   // (thread 0's fence inside the barrier is cumulative over the atomics ordered before this sync)
+  if (dbg) g_resident_dbg[1] = gtimer();
   if (tid == 0) grid_barrier_thread0(gbar);
   __syncthreads();
+  if (dbg) g_resident_dbg[2] = gtimer();
   // ---- every CTA turns the (now final) sums into the two per-channel coefficients; CTA 0 publishes the gradients
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += NTHR) {
     double s1 = 0, s2 = 0;
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
@@ -960,6 +980,7 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
     Bc[i] = A[i] * coef_s[c0 + i];
     Cc[i] = A[i] * bnp[C + c0 + i] * coef_s[C + c0 + i];
   }
+  if (dbg) g_resident_dbg[3] = gtimer();
   T* dxp = reinterpret_cast<T*>(a.dx + row0 * a.row_bytes);
   for (int rr = ty; rr < rows; rr += by) {
     Pack<T> d, xv, o;
@@ -980,6 +1001,7 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
     }
     o.store(dxp + (size_t)rr * (a.row_bytes / sizeof(T)) + c0);
   }
+  if (dbg) g_resident_dbg[4] = gtimer();
 }
 
 // ==========================================================================================================
@@ -1167,6 +1189,7 @@ static bool launch_bwd_coop(bool dry, const basi_tensor* dout, const basi_tensor
 
 struct ResidentGeom {
   bool ok;
+  int threads;
   int grid, bx, by, rows_per_cta, chunk_rows, n_chunks;
   size_t smem;
 };
@@ -1183,13 +1206,28 @@ static ResidentGeom resident_geom(int64_t R, int C, int es) {
   const int G = sm_count();
   if (R < (int64_t)G * 8) return g;
   const int64_t rpc = (R + G - 1) / G;
-  const int by = 256 / bx;
+  // Threads per CTA (one CTA per SM).  Measured phases at C = 128, 256 threads, cold / L2-warm: rows 5.2 / 2.6 us,
+  // block reduction + atomics 2.2, grid barrier 1.6, coefficients 1.5 / 1.1, dx 1.6.  512 / 1024 threads make the
+  // block reduction longer (2.2 -> 6.3 us) without speeding the row pass up, so 256 it is.
+  static int thr_env = -1;
+  if (thr_env < 0) thr_env = getenv("BASI_BN_RESIDENT_THREADS") ? atoi(getenv("BASI_BN_RESIDENT_THREADS")) : 0;
+  int threads = (thr_env == 256 || thr_env == 512 || thr_env == 1024) ? thr_env : 256;
+  while (threads > 256 && threads / bx > rpc) threads /= 2;
+  if (threads < bx) threads = bx;
   int chunk_rows = (16 * 1024) / row_bytes;
   if (chunk_rows < 1) chunk_rows = 1;
   const int64_t n_chunks = (rpc + chunk_rows - 1) / chunk_rows;
-  const size_t smem = 2 * (size_t)rpc * row_bytes + (size_t)by * C * 2 * sizeof(float) + 2 * (size_t)C * sizeof(float) +
-                      8 * (size_t)n_chunks + 128;
-  if (smem > 220 * 1024 || n_chunks > 64) return g;
+  if (n_chunks > 64) return g;
+  size_t smem = 0;
+  int by = 1;
+  for (;; threads /= 2) {          // fewer threads -> smaller block-reduction scratch, until the slab fits
+    by = threads / bx;
+    smem = 2 * (size_t)rpc * row_bytes + (size_t)by * C * 2 * sizeof(float) + 2 * (size_t)C * sizeof(float) +
+           8 * (size_t)n_chunks + 128;
+    if (smem <= 220 * 1024) break;
+    if (threads <= 256 || threads / 2 < bx) return g;
+  }
+  g.threads = threads;
   g.ok = true;
   g.grid = (int)((R + rpc - 1) / rpc);
   g.bx = bx; g.by = by;
@@ -1210,7 +1248,7 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   a.R = pixels(x);
   a.row_bytes = x->c * (int)sizeof(T);
   a.rows_per_cta = g.rows_per_cta; a.chunk_rows = g.chunk_rows; a.n_chunks = g.n_chunks;
-  allow_smem(bn_bwd_resident_kernel<T>, g.smem);
+  a.debug = getenv("BASI_BN_RESIDENT_DEBUG") ? 1 : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g.grid);
   cfg.blockDim = dim3(g.bx, g.by);
@@ -1221,8 +1259,24 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("BASI_BN_RESIDENT_NOCOOP") ? 0 : 1;   // experiment only: without the attribute co-residency is not guaranteed
-  cudaLaunchKernelEx(&cfg, bn_bwd_resident_kernel<T>, a, bnp, relu_from_x, (int)x->c, dsums, count, dgamma, dbeta, coef,
-                     (unsigned int*)gbar);
+#define BASI_LAUNCH_RESIDENT(NT_)                                                                                  \
+  do {                                                                                                             \
+    allow_smem(bn_bwd_resident_kernel<T, NT_>, g.smem);                                                            \
+    cudaLaunchKernelEx(&cfg, bn_bwd_resident_kernel<T, NT_>, a, bnp, relu_from_x, (int)x->c, dsums, count, dgamma,  \
+                       dbeta, coef, (unsigned int*)gbar);                                                          \
+  } while (0)
+  if (g.threads == 1024) BASI_LAUNCH_RESIDENT(1024);
+  else if (g.threads == 512) BASI_LAUNCH_RESIDENT(512);
+  else BASI_LAUNCH_RESIDENT(256);
+#undef BASI_LAUNCH_RESIDENT
+  if (a.debug) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_resident_dbg, sizeof(h));
+    fprintf(stderr, "resident R=%lld C=%d: rows %.2f us | block reduce + atomics %.2f | barrier %.2f | coef %.2f | dx %.2f | total %.2f\n",
+            (long long)a.R, (int)x->c, (h[5] - h[0]) * 1e-3, (h[1] - h[5]) * 1e-3, (h[2] - h[1]) * 1e-3,
+            (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3, (h[4] - h[0]) * 1e-3);
+  }
 }
 
 }  // namespace basi
