@@ -107,10 +107,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// ---- programmatic dependent launch (PDL, BASI_PDL=1): every kernel can be launched with the stream-serialisation
-// attribute and starts with launch_dependents + wait, so the next kernel's CTAs become resident (and run their
-// prologue) while the tail of this one is still executing.  Inside the step's CUDA graph it measured no gain, so it
-// is off by default; griddepcontrol.* are no-ops for a kernel launched without the attribute.
+// ---- programmatic dependent launch (PDL, default on, BASI_PDL=0 disables): every kernel is launched with the
+// stream-serialisation attribute and starts with launch_dependents + wait, so the next kernel's CTAs become resident
+// (and run their prologue) while the tail of this one is still executing.  griddepcontrol.* are no-ops for a kernel
+// launched without the attribute (the cooperative BN kernels).  A kernel launched through basi::launch MUST call
+// pdl_prologue() (or pdl_wait()) before it touches anything a predecessor produced.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {

@@ -552,6 +552,7 @@ struct StemConv {
 
 template <typename TD, int COUT>
 __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
+  pdl_prologue();
   // thread = (4 consecutive output pixels of one row, 8 output channels): every weight fetched from shared memory
   // feeds 4 FMAs, and neighbouring pixels share their input columns
   __shared__ __align__(16) float ws[36 * COUT];
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
 
 template <typename TG, int COUT>
 __global__ void __launch_bounds__(128) stem_wgrad_kernel(const StemConv g) {
+  pdl_prologue();
   // lane = output channel.  A warp takes 32 consecutive output pixels of one row per iteration: it stages their input
   // patch (3 rows x (31*stride + 3) columns of float4) and their 32 x COUT gradients in shared memory with coalesced
   // loads, then walks the pixels reading the taps as shared-memory broadcasts; the 36 x NC partial sums stay in
@@ -699,6 +701,7 @@ template <typename TX, int CO>
 __global__ void __launch_bounds__(256) head_fprop_kernel(const TX* __restrict__ x, int ldx, int C, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ y, int ldy,
                                                          int relu, int64_t M) {
+  pdl_prologue();
   constexpr int VN = Vec<TX>::N;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -730,6 +733,7 @@ __global__ void __launch_bounds__(256) head_fprop_kernel(const TX* __restrict__ 
 template <typename TD, int CO>
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w,
                                                          TD* __restrict__ dx, int ldx, int C, int acc, int64_t total) {
+  pdl_prologue();
   constexpr int VN = Vec<TD>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -751,6 +755,7 @@ template <typename TX, int CO>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const TX* __restrict__ x, int ldx, int C, const float* __restrict__ dy,
                                                          int ldy, float* __restrict__ dw, float* __restrict__ dbias,
                                                          int64_t M) {
+  pdl_prologue();
   constexpr int VN = Vec<TX>::N;
   extern __shared__ float hred[];   // [blockDim.y][blockDim.x][VN*CO + CO]
   const int cg = threadIdx.x;       // blockDim.x == C / VN

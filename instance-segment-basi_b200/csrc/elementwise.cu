@@ -21,10 +21,13 @@ void set_error(const char* fmt, ...) {
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    // opt-in: measured 12.31 ms (on) vs 12.29 ms (off) per step inside the CUDA graph -- the graph already removes
-    // the launch gaps PDL would hide
+    // Programmatic dependent launch: on unless BASI_PDL=0.  Every kernel launched through basi::launch starts with
+    // griddepcontrol.launch_dependents + griddepcontrol.wait, so the next kernel's CTAs become resident during this
+    // kernel's tail wherever the SM still has room.  While every kernel used the whole shared memory this measured
+    // nothing (12.31 vs 12.29 ms); with the register-staged BN kernels and the other small-footprint kernels between
+    // the tcgen05 launches it is worth 0.37 ms of a 9.2 ms step.
     const char* e = getenv("BASI_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
