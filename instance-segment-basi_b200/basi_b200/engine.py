@@ -936,6 +936,7 @@ class Engine(object):
         torch.cuda.synchronize(self.device)
         lr_saved = self.lr_dev.clone()
         self.lr_dev.zero_()      # the warm-up steps below must not move the weights
+        # (a high-priority capture stream for the main chain measured slower: 9.07 vs 8.89 ms)
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):

@@ -234,6 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_out) + 1023) & ~(uintptr_t)1023);
   volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.debug == 10) return;   // timing experiment: launch cost only
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -251,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 2 && p.debug != 11) {
     if (CL == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                    "r"(TMEM_COLS)
@@ -497,7 +498,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (CL == 2) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
-  if (warp == 2) {
+  if (warp == 2 && p.debug != 11) {
     tc_fence_after();
     if (CL == 2)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -967,7 +968,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       const int ksteps = d->kh * d->kw * ((kdim + 63) / 64);
       const long items2 = (long)((m_tiles + 1) / 2) * (ndim / bn);
       const char* env_mt = getenv("BASI_TC_MT");
-      int min_k = 4;
+      int min_k = getenv("BASI_TC_MT_MINK") ? atoi(getenv("BASI_TC_MT_MINK")) : 4;
       if (bn <= 128 && pl->cluster == 1 && m_tiles >= 2 && items2 * 3 >= (long)sms * 2 && ksteps >= min_k) pl->mt = 2;
       if (env_mt && atoi(env_mt) == 1) pl->mt = 1;
       if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2) pl->mt = 2;   // tests
@@ -1046,6 +1047,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     }
     if (env_w) waves = atoi(env_w);
     int splits = (waves * sms + out_tiles - 1) / out_tiles;
+    if (getenv("BASI_TC_WGRAD_SPLITS")) splits = atoi(getenv("BASI_TC_WGRAD_SPLITS"));   // experiment
     if (splits > m_tiles) splits = m_tiles;
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (m_tiles + splits - 1) / splits;
