@@ -82,6 +82,13 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
                     const basi_tensor* y, void* stream);
 /* adjoint w.r.t. the input (what tf.gradients derives for train_op, BAISRunnerTrain.py:117).
  * accumulate != 0: dx += result. */
+/* conv1_1 (fp32 NHWC4 input, 3x3, 32 or 64 output channels) with the batch-norm statistics of its output fused into
+ * the kernel (same protocol as basi_tc_conv_set_bn_stats: sums = double[BASI_BN_REPLICAS][2][C], zeroed by the caller;
+ * the last block writes bnp = [mean | istd | gamma*istd | beta] when bnp != NULL). */
+int basi_stem_fprop_stats_supported(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y);
+int basi_stem_fprop_stats(const basi_conv_desc* d, const basi_tensor* x, const float* w, const basi_tensor* y,
+                          double* sums, const float* gamma, const float* beta, double count, float eps, float* bnp,
+                          uint32_t* counter, void* stream);
 int basi_conv_dgrad(const basi_conv_desc* d, const basi_tensor* dy, const float* w, const basi_tensor* dx,
                     int accumulate, void* stream);
 /* adjoint w.r.t. the HWIO weights; ADDS into dw (and dbias when non-NULL). */

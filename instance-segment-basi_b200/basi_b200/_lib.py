@@ -57,6 +57,8 @@ SIGNATURES = {
     "basi_bn_bwd_fused": [_TP, _TP, _P, _i, _P, _d, _P, _P, _P, _P, _TP, _P],
     "basi_avgpool_multi_fwd": [_TP, _i, _P, _P, _P, _P],
     "basi_avgpool_multi_bwd": [_P, _i, _P, _TP, _i, _P],
+    "basi_stem_fprop_stats_supported": [_DP, _TP, _TP],
+    "basi_stem_fprop_stats": [_DP, _TP, _P, _TP, _P, _P, _P, _d, _f, _P, _P, _P],
     "basi_subsample_fwd": [_TP, _i, _TP, _P],
     "basi_subsample_bwd": [_TP, _i, _TP, _i, _P],
     "basi_bn_stats": [_TP, _P, _P, _P, _d, _f, _P, _P, _P],

@@ -104,6 +104,7 @@ class Engine(object):
             self._bstreams = [torch.cuda.Stream(self.device) for _ in range(4)]
         self._side_dirty = False
         self._tc_plans = []
+        self._stem_producer = {}
         self._subsampled = {}
         self._tc_producer = {}
         self.fuse_bn_stats = fuse_bn_stats
@@ -486,6 +487,9 @@ class Engine(object):
                 op["tc_fprop"] = self._emit_tc(op, _lib.TC_FPROP, self.fwd)
                 self._tc_producer[id(y)] = op
                 return
+        if (not op["b"] and not self.dry_run and self.fuse_bn_stats
+                and _lib.load().basi_stem_fprop_stats_supported(C.byref(op["desc"]), x.ref, y.ref) == 1):
+            self._stem_producer[id(y)] = (len(self.fwd), op)       # _emit_bn_stats may upgrade this call
         self._call(self.fwd, "basi_conv_fprop", C.byref(op["desc"]), x.ref, self._pptr(op["w"]), bptr, y.ref,
                    flops=self._conv_flops(op))
 
@@ -499,6 +503,18 @@ class Engine(object):
             # statistics come out of the tcgen05 conv epilogue: no separate pass over the conv output
             _lib.call("basi_tc_conv_set_bn_stats", prod["tc_fprop"], rec.sums, self._pptr(rec.gamma),
                       self._pptr(rec.beta), C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.cnt_f)
+            self.fused_stats += 1
+            return
+        stem = self._stem_producer.get(id(rec.x))
+        if stem is not None:
+            # conv1_1: the stem kernel accumulates the statistics of its own output
+            pos, op = stem
+            name, _, args, meta = self.fwd[pos]
+            assert name == "basi_conv_fprop"
+            fn = _lib.load().basi_stem_fprop_stats
+            self.fwd[pos] = ("basi_stem_fprop_stats", fn,
+                             (args[0], args[1], args[2], args[4], rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),
+                              C.c_double(rec.count), C.c_float(1e-5), rec.bnp.data_ptr(), rec.cnt_f), meta)
             self.fused_stats += 1
             return
         self._call(self.fwd, "basi_bn_stats", rec.x.ref, rec.sums, self._pptr(rec.gamma), self._pptr(rec.beta),

@@ -548,6 +548,11 @@ struct StemConv {
   int N, IH, IW, OH, OW, ldy;
   int stride, pad_t, pad_l, relu;
   int64_t M;     // N*OH*OW
+  // optional fused batch-norm statistics of the produced tensor (same protocol as the tcgen05 fprop epilogue):
+  // per-channel sum / sum of squares of the values as stored, double atomics into BASI_BN_REPLICAS replicas, the
+  // last block finalizes bnp = [mean | istd | gamma*istd | beta]
+  double* bn_sums; const float* bn_gamma; const float* bn_beta; float* bn_bnp; unsigned int* bn_counter;
+  double bn_count; float bn_eps;
 };
 
 template <typename TD, int COUT>
@@ -559,6 +564,9 @@ __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
   for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) ws[i] = g.W[i];
   __syncthreads();
   constexpr int CG = COUT / 8, PX = 4;
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
   const int owg = (g.OW + PX - 1) / PX;
   const int total = g.N * g.OH * owg * CG;
   TD* Y = (TD*)g.Y;
@@ -617,6 +625,58 @@ __global__ void __launch_bounds__(256) stem_fprop_kernel(const StemConv g) {
       const float hi[4] = {acc[px][4], acc[px][5], acc[px][6], acc[px][7]};
       store4<TD>(yp, lo);
       store4<TD>(yp + 4, hi);
+      if (g.bn_sums) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = to_f32(from_f32<TD>(acc[px][j]));     // the value as stored
+          ssum[j] += v;
+          ssq[j] = fmaf(v, v, ssq[j]);
+        }
+      }
+    }
+  }
+  if (g.bn_sums) {
+    // every thread keeps the same channel group for the whole grid-stride loop (grid * block is a multiple of CG)
+    __shared__ float sred[256][16];
+    __shared__ unsigned int s_last;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sred[threadIdx.x][j] = ssum[j];
+      sred[threadIdx.x][8 + j] = ssq[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < COUT) {
+      const int c = threadIdx.x, cgc = c / 8, j = c % 8;
+      double s1 = 0, s2 = 0;
+      for (int t = cgc; t < 256; t += CG) {
+        s1 += (double)sred[t][j];
+        s2 += (double)sred[t][8 + j];
+      }
+      double* rep = g.bn_sums + (size_t)(blockIdx.x % BASI_BN_REPLICAS) * 2 * COUT;
+      atomicAdd(rep + c, s1);
+      atomicAdd(rep + COUT + c, s2);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(g.bn_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last && g.bn_bnp && threadIdx.x < COUT) {
+      __threadfence();
+      const int c = threadIdx.x;
+      double s1 = 0, s2 = 0;
+#pragma unroll
+      for (int r = 0; r < BASI_BN_REPLICAS; ++r) {
+        s1 += __ldcg(g.bn_sums + (size_t)r * 2 * COUT + c);
+        s2 += __ldcg(g.bn_sums + (size_t)r * 2 * COUT + COUT + c);
+      }
+      const double mean = s1 / g.bn_count;
+      double var = s2 / g.bn_count - mean * mean;
+      if (var < 0) var = 0;
+      const double istd = 1.0 / sqrt(var + (double)g.bn_eps);
+      g.bn_bnp[c] = (float)mean;
+      g.bn_bnp[COUT + c] = (float)istd;
+      g.bn_bnp[2 * COUT + c] = (float)((double)g.bn_gamma[c] * istd);
+      g.bn_bnp[3 * COUT + c] = g.bn_beta[c];
     }
   }
 }
@@ -830,6 +890,18 @@ static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const b
   return s;
 }
 
+static void launch_stem_fprop(const StemConv& s, const basi_tensor* y, cudaStream_t st) {
+  int64_t total = (int64_t)s.N * s.OH * ((s.OW + 3) / 4) * (y->c / 8);
+  int grid = grid_for(total, 256, 16);
+  if (y->dtype == BASI_BF16) {
+    if (y->c == 32) basi::launch(stem_fprop_kernel<bf16, 32>, grid, 256, 0, st, s);
+    else basi::launch(stem_fprop_kernel<bf16, 64>, grid, 256, 0, st, s);
+  } else {
+    if (y->c == 32) basi::launch(stem_fprop_kernel<float, 32>, grid, 256, 0, st, s);
+    else basi::launch(stem_fprop_kernel<float, 64>, grid, 256, 0, st, s);
+  }
+}
+
 // conv6_n-shaped problem: 1x1, stride 1, no padding, <= 4 fp32 output channels
 static bool head_shape(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
   const int vn = x->dtype == BASI_F32 ? 4 : 8;
@@ -880,16 +952,7 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
   if (stem_shape(d, x, y) && !bias) {
     StemConv s = stem_args(d, x, y);
     s.W = w; s.relu = d->relu;
-    int64_t total = (int64_t)s.N * s.OH * ((s.OW + 3) / 4) * (y->c / 8);
-    int grid = grid_for(total, 256, 16);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (y->dtype == BASI_BF16) {
-      if (y->c == 32) basi::launch(stem_fprop_kernel<bf16, 32>, grid, 256, 0, st, s);
-      else basi::launch(stem_fprop_kernel<bf16, 64>, grid, 256, 0, st, s);
-    } else {
-      if (y->c == 32) basi::launch(stem_fprop_kernel<float, 32>, grid, 256, 0, st, s);
-      else basi::launch(stem_fprop_kernel<float, 64>, grid, 256, 0, st, s);
-    }
+    launch_stem_fprop(s, y, (cudaStream_t)stream);
     BASI_CHECK_LAUNCH("conv_fprop(stem)");
     return BASI_OK;
   }
@@ -906,6 +969,26 @@ int basi_conv_fprop(const basi_conv_desc* d, const basi_tensor* x, const float* 
   g.fastD = (y->c % 4 == 0) && (y->ld % 4 == 0) && aligned16(y->ptr);
   launch_gemm_conv<MODE_FPROP>(g, x->dtype, y->dtype, (cudaStream_t)stream);
   BASI_CHECK_LAUNCH("conv_fprop");
+  return BASI_OK;
+}
+
+int basi_stem_fprop_stats_supported(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  return (d && x && y && check_conv(d, x, y, "stem_fprop_stats") == BASI_OK && stem_shape(d, x, y)) ? 1 : 0;
+}
+
+int basi_stem_fprop_stats(const basi_conv_desc* d, const basi_tensor* x, const float* w, const basi_tensor* y,
+                          double* sums, const float* gamma, const float* beta, double count, float eps, float* bnp,
+                          uint32_t* counter, void* stream) {
+  int rc = check_conv(d, x, y, "stem_fprop_stats");
+  if (rc) return rc;
+  BASI_CHECK_ARG(w && sums && counter && (!bnp || (gamma && beta && count > 0)), "stem_fprop_stats: bad argument");
+  BASI_CHECK_ARG(stem_shape(d, x, y), "stem_fprop_stats: not a stem-shaped convolution (fp32 NHWC4 input, 3x3, 32/64 out)");
+  StemConv s = stem_args(d, x, y);
+  s.W = w; s.relu = d->relu;
+  s.bn_sums = sums; s.bn_gamma = gamma; s.bn_beta = beta; s.bn_bnp = bnp; s.bn_counter = counter;
+  s.bn_count = count; s.bn_eps = eps;
+  launch_stem_fprop(s, y, (cudaStream_t)stream);
+  BASI_CHECK_LAUNCH("stem_fprop_stats");
   return BASI_OK;
 }
 

@@ -215,12 +215,16 @@ def test_click_inference_mask_matches_oracle():
 
 
 @pytest.mark.parametrize("prec", ["bf16", "f32"])
-def test_step_is_reproducible_at_benchmark_size(prec):
+def test_step_is_reproducible_at_benchmark_size(prec, monkeypatch):
     """Size-independent property at the full benchmark shape (S=320, B=16, F=32): the same step from the same
     parameters gives the same loss and (up to the order of the floating-point atomics: BN sums in double, weight
     gradients in fp32) the same gradient -- eagerly and as a replayed CUDA graph.  This is the race detector for the
     side-stream weight gradients, the programmatic dependent launches and the cooperative BN kernels."""
     variant, nseg, S, F, B, classes = "1NoClass", 1, 320, 32, 16, 21
+    if prec == "f32":
+        # the fused pyramid pooling accumulates with fp32 atomics: in fp32 storage that is forward order noise of one
+        # ulp which the deep batch-stat net amplifies; the four separate pools are order-free (bf16 rounds it away)
+        monkeypatch.setenv("BASI_NO_POOL_FUSION", "1")
     params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
     eng = _engine(variant, nseg, S, F, B, classes, prec, dict(kind="bce", pos_weight=3.0))
     eng.set_params(params)
@@ -243,9 +247,8 @@ def test_step_is_reproducible_at_benchmark_size(prec):
         one(eng.replay)
     loss0, g0 = runs[0]
     assert np.isfinite(loss0) and float(g0.norm()) > 0
-    # fp32 mode: the fused pyramid pooling accumulates with fp32 atomics, so even the forward carries order noise of
-    # one ulp, which the random-init net amplifies on its way back; bf16 storage rounds it away (measured 5e-7)
-    gtol = 1e-5 if prec == "bf16" else 1e-3
+    gtol = 1e-5 if prec == "bf16" else 1e-4
     for loss, g in runs[1:]:
-        assert abs(loss - loss0) <= 1e-6 * abs(loss0)
-        assert float((g - g0).norm() / g0.norm()) < gtol
+        assert abs(loss - loss0) <= 1e-6 * abs(loss0), (loss, loss0)
+        rel = float((g - g0).norm() / g0.norm())
+        assert rel < gtol, rel

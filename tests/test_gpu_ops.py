@@ -863,3 +863,39 @@ def test_batch_norm_backward_coop(dtype, mask_mode, dres_mode, shape):
             assert np.array_equal(res[k][1], res[0][1])
         for j in (2, 3, 4):
             assert rel_err(res[k][j], res[0][j]) < 1e-5
+
+
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("cout,H,W,B", [(32, 64, 64, 2), (64, 33, 47, 1), (32, 320, 320, 2)])
+def test_stem_conv_fused_bn_statistics(out_dtype, cout, H, W, B):
+    """basi_stem_fprop_stats: same output as basi_conv_fprop, and [mean | istd | gamma*istd | beta] equal to the
+    statistics of the tensor as stored."""
+    from gpu_util import act, call, dev, empty_act, host, rel_err
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    rng = np.random.RandomState(cout + W)
+    x = _u(rng, B, H, W, 4) + 0.2
+    w = (_u(rng, 3, 3, 4, cout) / 6.0).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 1.5, cout).astype(np.float32), _u(rng, cout)
+    oh, ow = (H + 1) // 2, (W + 1) // 2
+    pt, pl = O.tf_same_pad(H, 3, 2, 1)[0], O.tf_same_pad(W, 3, 2, 1)[0]
+    desc = ConvDesc(3, 3, 2, 1, pt, pl, 0)
+    tdt = torch.float32 if out_dtype == "f32" else torch.bfloat16
+    xa = act(x)
+    ya, yb = empty_act((B, oh, ow, cout), tdt, fill=7.0), empty_act((B, oh, ow, cout), tdt, fill=7.0)
+    assert _lib.load().basi_stem_fprop_stats_supported(C.byref(desc), xa.ref, ya.ref) == 1
+    wd, gd, bd = dev(w), dev(gamma), dev(beta)
+    sums = torch.zeros(2 * cout * 8, dtype=torch.float64, device="cuda:0")
+    bnp = torch.zeros(4 * cout, device="cuda:0")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    call("basi_conv_fprop", C.byref(desc), xa.ref, wd.data_ptr(), None, ya.ref)
+    call("basi_stem_fprop_stats", C.byref(desc), xa.ref, wd.data_ptr(), yb.ref, sums.data_ptr(), gd.data_ptr(),
+         bd.data_ptr(), C.c_double(B * oh * ow), C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
+    y = host(yb)
+    assert np.array_equal(host(ya), y)
+    flat = y.reshape(-1, cout).astype(np.float64)
+    mean, var = flat.mean(0), flat.var(0)
+    got = host(bnp).reshape(4, cout)
+    istd = 1.0 / np.sqrt(var + 1e-5)
+    assert rel_err(got[0], mean) < 1e-5 and rel_err(got[1], istd) < 1e-5
+    assert rel_err(got[2], gamma * istd) < 1e-5 and np.array_equal(got[3], beta)
