@@ -892,7 +892,8 @@ static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const b
 
 static void launch_stem_fprop(const StemConv& s, const basi_tensor* y, cudaStream_t st) {
   int64_t total = (int64_t)s.N * s.OH * ((s.OW + 3) / 4) * (y->c / 8);
-  int grid = grid_for(total, 256, 16);
+  // with fused statistics every block ends with 2 * Cout double atomics: fewer, longer blocks
+  int grid = grid_for(total, 256, s.bn_sums ? 3 : 16);
   if (y->dtype == BASI_BF16) {
     if (y->c == 32) basi::launch(stem_fprop_kernel<bf16, 32>, grid, 256, 0, st, s);
     else basi::launch(stem_fprop_kernel<bf16, 64>, grid, 256, 0, st, s);
