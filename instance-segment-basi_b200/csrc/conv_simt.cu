@@ -434,30 +434,40 @@ constexpr int SK_KT = 64;  // k-slab per block (fwd / wgrad)
 template <typename TA>
 __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ a, int64_t lda,
                                                          const float* __restrict__ w, float* __restrict__ y, int M,
-                                                         int K, int N) {
+                                                         int K, int N, int slabs_per_block) {
+  // block = (128 output columns, a run of k-slabs); the partial sums of the run stay in registers and are added to y
+  // once (with one slab per block the 52 MB class_attention_conv GEMV was bound by its 3.3 M atomics, not by HBM)
   pdl_prologue();
   __shared__ float sa[64][SK_KT + 1];
   const int n = blockIdx.x * 128 + threadIdx.x;
-  const int k0 = blockIdx.y * SK_KT;
-  const int kt = min(SK_KT, K - k0);
-  for (int i = threadIdx.x; i < 64 * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
-    int m = i / SK_KT, k = i - m * SK_KT;
-    sa[m][k] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
-  }
-  __syncthreads();
-  if (n >= N) return;
   for (int mb = 0; mb < M; mb += 16) {
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    for (int k = 0; k < kt; ++k) {
-      const float wv = __ldg(w + (int64_t)(k0 + k) * N + n);
+    for (int sl = 0; sl < slabs_per_block; ++sl) {
+      const int k0 = (blockIdx.y * slabs_per_block + sl) * SK_KT;
+      if (k0 >= K) break;
+      const int kt = min(SK_KT, K - k0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < 16 * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
+        const int m = i / SK_KT, k = i - m * SK_KT;
+        sa[m][k] = (mb + m < M && k < kt) ? to_f32(a[(int64_t)(mb + m) * lda + k0 + k]) : 0.f;
+      }
+      __syncthreads();
+      if (n < N) {
+#pragma unroll 4
+        for (int k = 0; k < kt; ++k) {
+          const float wv = __ldg(w + (int64_t)(k0 + k) * N + n);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(sa[min(mb + i, 63)][k], wv, acc[i]);
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(sa[i][k], wv, acc[i]);
+        }
+      }
     }
+    if (n < N) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (mb + i < M) atomicAdd(y + (int64_t)(mb + i) * N + n, acc[i]);
+      for (int i = 0; i < 16; ++i)
+        if (mb + i < M) atomicAdd(y + (int64_t)(mb + i) * N + n, acc[i]);
+    }
   }
 }
 
@@ -470,68 +480,89 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
 }
 
 // da[m][k] (+)= sum_n dy[m][n] * w[k][n]; one warp per k row
+// transpose-reduce across the 32 lanes of a warp: on return v[0] of lane l is the sum over all lanes of their v[l]
+__device__ __forceinline__ void warp_transpose_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
 template <typename TA>
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                            TA* __restrict__ da, int64_t lda, int M, int K, int N,
                                                            int acc_flag) {
+  // a warp takes TWO weight rows k per iteration against 16 batch rows: every dy value read from shared memory feeds
+  // two FMAs, and the 32 partial sums (2 k x 16 m) are reduced across the lanes with one 31-shuffle transpose-reduce
   pdl_prologue();
   extern __shared__ float sdy[];  // [M][N]
   for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int k = blockIdx.x * 8 + wid; k < K; k += gridDim.x * 8) {
-    const float* wr = w + (int64_t)k * N;
+  for (int k = (blockIdx.x * 8 + wid) * 2; k < K; k += gridDim.x * 16) {
+    const bool two = k + 1 < K;
+    const float* w0 = w + (int64_t)k * N;
+    const float* w1 = w + (int64_t)(two ? k + 1 : k) * N;
     for (int mb = 0; mb < M; mb += 16) {
-      float acc[16];
+      float acc[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       for (int n = lane; n < N; n += 32) {
-        const float wv = __ldg(wr + n);
+        const float wa = __ldg(w0 + n), wb = __ldg(w1 + n);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (mb + i < M) acc[i] = fmaf(sdy[(mb + i) * N + n], wv, acc[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = warp_sum(acc[i]);
-        if (lane == 0 && mb + i < M) {
-          TA* dst = da + (int64_t)(mb + i) * lda + k;
-          if (acc_flag) v += to_f32(*dst);
-          *dst = from_f32<TA>(v);
+        for (int i = 0; i < 16; ++i) {
+          const float g = mb + i < M ? sdy[(mb + i) * N + n] : 0.f;
+          acc[i] = fmaf(g, wa, acc[i]);
+          acc[16 + i] = fmaf(g, wb, acc[16 + i]);
         }
+      }
+      warp_transpose_sums(acc, lane);          // lane l now holds the total of entry l: (k + l / 16, mb + l % 16)
+      const int kk = k + (lane >> 4), m = mb + (lane & 15);
+      if (m < M && kk < K && (two || lane < 16)) {
+        TA* dst = da + (int64_t)m * lda + kk;
+        float v = acc[0];
+        if (acc_flag) v += to_f32(*dst);
+        *dst = from_f32<TA>(v);
       }
     }
   }
 }
 
 // dw[k][n] += sum_m a[m][k] * dy[m][n]
-template <typename TA>
+template <typename TA, int MB>
 __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict__ a, int64_t lda,
                                                            const float* __restrict__ dy, float* __restrict__ dw,
                                                            float* __restrict__ dbias, int M, int K, int N) {
   pdl_prologue();
-  __shared__ float sa[64][SK_KT + 1];
+  __shared__ float sa[MB][SK_KT + 1];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
   const int kt = min(SK_KT, K - k0);
-  for (int i = threadIdx.x; i < 64 * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
+  for (int i = threadIdx.x; i < MB * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
     int m = i / SK_KT, k = i - m * SK_KT;
     sa[m][k] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
   }
   __syncthreads();
   if (n >= N) return;
-  float g[64];
+  float g[MB];
   float bs = 0.f;
 #pragma unroll
-  for (int m = 0; m < 64; ++m) {
+  for (int m = 0; m < MB; ++m) {
     g[m] = m < M ? dy[(int64_t)m * N + n] : 0.f;
     bs += g[m];
   }
   if (dbias && blockIdx.y == 0) dbias[n] += bs;
+#pragma unroll 4
   for (int k = 0; k < kt; ++k) {
     float acc = 0.f;
 #pragma unroll
-    for (int m = 0; m < 64; ++m) acc = fmaf(sa[m][k], g[m], acc);
+    for (int m = 0; m < MB; ++m) acc = fmaf(sa[m][k], g[m], acc);
     dw[(int64_t)(k0 + k) * N + n] += acc;
   }
 }
@@ -1111,9 +1142,14 @@ int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, con
   BASI_CHECK_ARG(a && w && y && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_fwd: bad argument (M must be <= 64)");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
-  dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
-  if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)a, lda, w, y, M, K, N);
-  else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, w, y, M, K, N);
+  const int nslabs = (K + SK_KT - 1) / SK_KT, gx = (N + 127) / 128;
+  // about 4 blocks per SM in total; every block walks `spb` consecutive k-slabs
+  int gy = (4 * basi::sm_count() + gx - 1) / gx;
+  if (gy > nslabs) gy = nslabs;
+  const int spb = (nslabs + gy - 1) / gy;
+  dim3 grid(gx, (nslabs + spb - 1) / spb);
+  if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)a, lda, w, y, M, K, N, spb);
+  else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, w, y, M, K, N, spb);
   BASI_CHECK_LAUNCH("skinny_fwd");
   basi::launch(bias_act_kernel, (M * N + 255) / 256, 256, 0, st, y, bias, M, N, relu);
   BASI_CHECK_LAUNCH("skinny_fwd(bias)");
@@ -1126,7 +1162,7 @@ int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, in
                  "skinny_dgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = sizeof(float) * (size_t)M * N;
-  int blocks = (K + 7) / 8;
+  int blocks = (K + 15) / 16;
   int cap = basi::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (dtype_a == BASI_F32) {
@@ -1147,8 +1183,13 @@ int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, 
   BASI_CHECK_ARG(a && dy && dw && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_wgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
-  if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
-  else basi::launch(skinny_wgrad_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  if (M <= 16) {
+    if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 16>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
+    else basi::launch(skinny_wgrad_kernel<bf16, 16>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  } else {
+    if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 64>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
+    else basi::launch(skinny_wgrad_kernel<bf16, 64>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  }
   BASI_CHECK_LAUNCH("skinny_wgrad");
   return BASI_OK;
 }
