@@ -55,12 +55,14 @@ __global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, int ldx, int H, i
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cg = (int)(i % cgs);
-    int64_t p = i / cgs;
-    int ow = (int)(p % OW);
-    int64_t t = p / OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
+    // 32-bit index arithmetic (the host checks total < 2^31): 64-bit divisions cost tens of instructions each
+    const unsigned iu = (unsigned)i;
+    int cg = (int)(iu % (unsigned)cgs);
+    const unsigned p = iu / (unsigned)cgs;
+    int ow = (int)(p % (unsigned)OW);
+    const unsigned t = p / (unsigned)OW;
+    int oh = (int)(t % (unsigned)OH);
+    int n = (int)(t / (unsigned)OH);
     float best[VN];
     uint8_t bi[VN];
 #pragma unroll
@@ -105,12 +107,13 @@ __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, int ldy, int OH,
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cg = (int)(i % cgs);
-    int64_t p = i / cgs;
-    int iw = (int)(p % W);
-    int64_t t = p / W;
-    int ih = (int)(t % H);
-    int n = (int)(t / H);
+    const unsigned iu = (unsigned)i;      // 32-bit index arithmetic, see the forward kernel
+    int cg = (int)(iu % (unsigned)cgs);
+    const int64_t p = iu / (unsigned)cgs;
+    int iw = (int)((unsigned)p % (unsigned)W);
+    const unsigned t = (unsigned)p / (unsigned)W;
+    int ih = (int)(t % (unsigned)H);
+    int n = (int)(t / (unsigned)H);
     Vec<T> g = Vec<T>::zero();
     if (acc) g = Vec<T>::load(dx + p * ldx + cg * VN);
 #pragma unroll
@@ -336,40 +339,76 @@ __global__ void avgpool_multi_finalize_kernel(const MultiPool mp, int C, float* 
   }
 }
 
+// block = one pixel row (n, ih); thread = one 8-channel group, walks the columns: the row cell of every pool is
+// computed once per block and the column cell advances with a counter (no per-element integer division)
 template <typename T>
-__global__ void avgpool_multi_bwd_kernel(const MultiPool mp, T* __restrict__ dx, int ldx, int H, int W, int C, int acc,
-                                         int64_t total) {
+__global__ void __launch_bounds__(256) avgpool_multi_bwd_kernel(const MultiPool mp, T* __restrict__ dx, int ldx, int H,
+                                                                int W, int C, int acc) {
   pdl_prologue();
   constexpr int VN = Vec<T>::N;
   const int cgs = C / VN;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    const int64_t px = i / cgs;
-    const int iw = (int)(px % W);
-    const int64_t t = px / W;
-    const int ih = (int)(t % H), n = (int)(t / H);
-    Vec<T> g = Vec<T>::zero();
-    bool any = false;
+  const int n = blockIdx.x / H, ih = blockIdx.x % H;
+  const T* yrow[MP_MAX];
+  float inv[MP_MAX];
+  bool rowok[MP_MAX];
+#pragma unroll
+  for (int p = 0; p < MP_MAX; ++p) {
+    rowok[p] = false;
+    inv[p] = 0.f;
+    yrow[p] = nullptr;
+    if (p < mp.np) {
+      const int oh = ih / mp.k[p];
+      rowok[p] = oh < mp.OH[p];
+      inv[p] = 1.0f / (float)(mp.k[p] * mp.k[p]);
+      yrow[p] = (const T*)mp.y[p] + ((int64_t)n * mp.OH[p] + (rowok[p] ? oh : 0)) * mp.OW[p] * mp.ldy[p];
+    }
+  }
+  T* xrow = dx + ((int64_t)n * H + ih) * W * ldx;
+  for (int cg = threadIdx.x; cg < cgs; cg += blockDim.x) {
+    int ow[MP_MAX], nextb[MP_MAX];
+    Vec<T> cur[MP_MAX];           // the pooled gradient of the current column cell, already scaled
 #pragma unroll
     for (int p = 0; p < MP_MAX; ++p) {
-      if (p >= mp.np) continue;
-      const int oh = ih / mp.k[p], ow = iw / mp.k[p];
-      if (oh < mp.OH[p] && ow < mp.OW[p]) {
-        const float inv = 1.0f / (float)(mp.k[p] * mp.k[p]);
-        const Vec<T> d =
-            Vec<T>::load((const T*)mp.y[p] + (((int64_t)n * mp.OH[p] + oh) * mp.OW[p] + ow) * mp.ldy[p] + cg * VN);
+      ow[p] = 0;
+      nextb[p] = p < mp.np ? mp.k[p] : (1 << 30);
+      cur[p] = Vec<T>::zero();
+      if (p < mp.np && rowok[p]) {
+        cur[p] = Vec<T>::load(yrow[p] + cg * VN);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) g.v[j] += d.v[j] * inv;
-        any = true;
+        for (int j = 0; j < VN; ++j) cur[p].v[j] *= inv[p];
       }
     }
-    if (acc) {
-      if (!any) continue;
-      const Vec<T> o = Vec<T>::load(dx + px * ldx + cg * VN);
+    for (int iw = 0; iw < W; ++iw) {
+      bool any = false;
+      Vec<T> g = Vec<T>::zero();
 #pragma unroll
-      for (int j = 0; j < VN; ++j) g.v[j] += o.v[j];
+      for (int p = 0; p < MP_MAX; ++p) {
+        if (p >= mp.np) continue;
+        if (iw == nextb[p]) {
+          ++ow[p];
+          nextb[p] += mp.k[p];
+          cur[p] = Vec<T>::zero();
+          if (rowok[p] && ow[p] < mp.OW[p]) {
+            cur[p] = Vec<T>::load(yrow[p] + (int64_t)ow[p] * mp.ldy[p] + cg * VN);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) cur[p].v[j] *= inv[p];
+          }
+        }
+        if (rowok[p] && ow[p] < mp.OW[p]) {
+          any = true;
+#pragma unroll
+          for (int j = 0; j < VN; ++j) g.v[j] += cur[p].v[j];
+        }
+      }
+      T* dst = xrow + (int64_t)iw * ldx + cg * VN;
+      if (acc) {
+        if (!any) continue;
+        const Vec<T> o = Vec<T>::load(dst);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) g.v[j] += o.v[j];
+      }
+      g.store(dst);
     }
-    g.store(dx + px * ldx + cg * VN);
   }
 }
 
@@ -922,6 +961,7 @@ int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* arg
   int pt, pl;
   same_pad_3s2(x->h, y->h, &pt);
   same_pad_3s2(x->w, y->w, &pl);
+  BASI_CHECK_ARG(pixels(x) * (int64_t)x->c < ((int64_t)1 << 31), "maxpool fwd: tensor too large for 32-bit indexing");
   DISPATCH_T(x->dtype, {
     int64_t total = pixels(y) * (y->c / Vec<T>::N);
     basi::launch(maxpool3s2_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld, x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, pt, pl, argmax, total);
@@ -938,6 +978,7 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
   int pt, pl;
   same_pad_3s2(dx->h, dy->h, &pt);
   same_pad_3s2(dx->w, dy->w, &pl);
+  BASI_CHECK_ARG(pixels(dx) * (int64_t)dx->c < ((int64_t)1 << 31), "maxpool bwd: tensor too large for 32-bit indexing");
   DISPATCH_T(dx->dtype, {
     int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
     basi::launch(maxpool3s2_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld, dy->h, dy->w, argmax, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, pt, pl, accumulate,
@@ -1037,9 +1078,10 @@ int basi_avgpool_multi_bwd(const basi_tensor* const* dys, int n_pools, const int
   int rc = fill_multipool(&mp, dx, n_pools, ks, dys, "avgpool_multi bwd");
   if (rc) return rc;
   DISPATCH_T(dx->dtype, {
-    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
-    basi::launch(avgpool_multi_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mp, (T*)dx->ptr, dx->ld,
-                 dx->h, dx->w, dx->c, accumulate, total);
+    int threads = dx->c / Vec<T>::N;
+    threads = threads >= 256 ? 256 : (threads < 32 ? 32 : (threads + 31) / 32 * 32);
+    basi::launch(avgpool_multi_bwd_kernel<T>, dim3((unsigned)(dx->n * dx->h)), dim3(threads), 0, (cudaStream_t)stream, mp,
+                 (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate);
   })
   BASI_CHECK_LAUNCH("avgpool_multi_bwd");
   return BASI_OK;
