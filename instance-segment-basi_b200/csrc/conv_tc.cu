@@ -940,10 +940,12 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     const basi_tensor* dstt = b;
     const int ndim = dstt->c, kdim = src->c;
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
-    // N = 256 tiles: the N = 128 main loop is bound by shared-memory operand reads (4 KB A + 4 KB B per 64-cycle
-    // MMA = 128 B/clk); N = 256 needs 96 B/clk.  Measured on conv5_4 dgrad: 975 -> 1404 TFLOP/s.  Per k-step a 256
-    // tile costs ~1.4x a 128 tile and there are half as many tiles: pick the cheaper wave count; small-K layers
-    // (overhead-bound) stay at 128.
+    // (narrower channel tiles for the tiny pyramid-branch maps, to spread the weight traffic over more SMs, measured
+    // no change: those launches are 6 us of launch + 6 us of pipeline latency; BASI_TC_SMALL_M=<tiles> re-enables it)
+    {
+      const int few = getenv("BASI_TC_SMALL_M") ? atoi(getenv("BASI_TC_SMALL_M")) : 0;
+      while (bn > 32 && ndim % (bn / 2) == 0 && (long)m_tiles * (ndim / bn) < few) bn /= 2;
+    }
     const int bn256_mink = getenv("BASI_TC_BN256_MINK") ? atoi(getenv("BASI_TC_BN256_MINK")) : 8;
     if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !getenv("BASI_TC_NO_BN256")) {
       const long t128 = ((long)m_tiles * (ndim / 128) + sms - 1) / sms * 10;

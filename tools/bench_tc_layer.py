@@ -20,6 +20,8 @@ SHAPES = [  # name, k, dil, cin, cout, H, B
     ("conv5_4", 3, 1, 2048, 256, 40, 16),
     ("conv1_3", 3, 1, 32, 64, 160, 16),
     ("conv2_3x3", 3, 1, 32, 32, 80, 16),
+    ("psp_pool1_conv", 1, 1, 1024, 128, 1, 16),
+    ("psp_pool6_conv", 1, 1, 1024, 128, 6, 16),
 ]
 if len(sys.argv) > 1:
     SHAPES = [s_ for s_ in SHAPES if s_[0] in sys.argv[1:]]
