@@ -1147,7 +1147,25 @@ static bool launch_bwd_coop(bool dry, const basi_tensor* dout, const basi_tensor
   if (!g1.ok || !g2.ok) return false;
   const size_t smem = g1.smem > g2.smem ? g1.smem : g2.smem;
   if (smem > 110 * 1024) return false;                     // two CTAs per SM must stay co-resident
-  if (dry) return true;
+  if (dry) {
+    // the grid barrier needs all 2 x #SMs CTAs co-resident: ask the occupancy calculator (another context sharing the
+    // GPU, or a smaller shared-memory carve-out, makes this fail -> the caller uses the two-launch pair)
+    int nb = 0;
+#define BASI_COOP_OCC(MK, DA)                                                                                      \
+  do {                                                                                                             \
+    allow_smem(bn_bwd_coop_kernel<T, MK, DA>, smem);                                                               \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_bwd_coop_kernel<T, MK, DA>, 256, smem);                  \
+  } while (0)
+    if (bits && acc) BASI_COOP_OCC(2, true);
+    else if (bits) BASI_COOP_OCC(2, false);
+    else if (out && acc) BASI_COOP_OCC(1, true);
+    else if (out) BASI_COOP_OCC(1, false);
+    else if (acc) BASI_COOP_OCC(0, true);
+    else BASI_COOP_OCC(0, false);
+#undef BASI_COOP_OCC
+    if (cudaGetLastError() != cudaSuccess) return false;
+    return nb >= 2;
+  }
   StreamArgs a1{}, a2{};
   fill_stream_args(&a1, g1, R, x->c, es, 0);
   fill_stream_args(&a2, g2, R, x->c, es, 1);
@@ -1490,7 +1508,24 @@ int basi_bn_bwd_coop(const basi_tensor* dout, const basi_tensor* out, const unsi
 
 int basi_bn_bwd_fused_supported(const basi_tensor* x) {
   if (!x || !vec_ok(x) || !dense_rows(x)) return 0;
-  return resident_geom(pixels(x), x->c, x->dtype == BASI_F32 ? 4 : 2).ok ? 1 : 0;
+  ResidentGeom g = resident_geom(pixels(x), x->c, x->dtype == BASI_F32 ? 4 : 2);
+  if (!g.ok) return 0;
+  // one CTA per SM must fit (the grid barrier needs the whole grid co-resident)
+  int nb = 0;
+  DISPATCH_T(x->dtype, {
+    if (g.threads == 1024) {
+      allow_smem(bn_bwd_resident_kernel<T, 1024>, g.smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_bwd_resident_kernel<T, 1024>, g.threads, g.smem);
+    } else if (g.threads == 512) {
+      allow_smem(bn_bwd_resident_kernel<T, 512>, g.smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_bwd_resident_kernel<T, 512>, g.threads, g.smem);
+    } else {
+      allow_smem(bn_bwd_resident_kernel<T, 256>, g.smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_bwd_resident_kernel<T, 256>, g.threads, g.smem);
+    }
+  })
+  if (cudaGetLastError() != cudaSuccess) return 0;
+  return (nb >= 1 && g.grid <= nb * sm_count()) ? 1 : 0;
 }
 
 int basi_bn_bwd_fused(const basi_tensor* dout, const basi_tensor* x, const float* bnp, int relu_from_x, double* dsums,
