@@ -803,6 +803,9 @@ class Engine(object):
         if kind == _lib.TC_WGRAD:
             meta["writes"] = [op["w"]]
             meta["side"] = True
+        skip = os.environ.get("BASI_DEBUG_SKIP_WGRAD")     # timing experiment only (gradients become wrong)
+        if kind == _lib.TC_WGRAD and skip and op["name"].startswith(tuple(skip.split(","))):
+            return handle
         lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))
         return handle
 
