@@ -552,12 +552,14 @@ struct WgradParams {
   int stages;
 };
 
-template <int BN>
+template <int BN, int GBOX>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG,
                 float* __restrict__ dw, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int GB = 2 * A_BYTES;            // 128 co = two 64-channel boxes of [128 px][128 B]
+  // 128 co = two 64-channel boxes of [128 px][128 B]; layers with at most 64 output channels (GBOX == 1) load one box
+  // and alias the second 64-row block of the MMA onto it (LBO = 0): its accumulator rows are never read
+  constexpr int GB = GBOX * A_BYTES;
   constexpr int XB = (BN / 64) * A_BYTES;    // BN ci = BN/64 boxes
   constexpr int STAGE = GB + XB;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -615,7 +617,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, STAGE);
         tma_load_4d(sa, &mapG, fb, cot * 128, w0, h0, n0);
-        tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
+        if (GBOX == 2) tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
         const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, cit * BN + j * 64, xw, xh, n0);
@@ -635,7 +637,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
         // MN-major: LBO = 16 KB between 64-channel blocks, SBO = 1 KB between groups of 8 pixel rows
-        const uint64_t adesc = make_desc(sa, A_BYTES, 1024);
+        const uint64_t adesc = make_desc(sa, GBOX == 2 ? A_BYTES : 0, 1024);
         const uint64_t bdesc = make_desc(sa + GB, A_BYTES, 1024);
 #pragma unroll
         for (int k = 0; k < BM / 16; ++k) {
@@ -831,6 +833,7 @@ struct basi_tc_conv {
   int bn;
   int cluster;
   int mt;        // pixel tiles per work item (1 or 2)
+  int gbox;      // wgrad: 64-channel boxes of the output-gradient operand (1 when Cout <= 64)
   CUtensorMap mapA, mapB, mapD;
   ConvParams cp;
   WgradParams wp;
@@ -885,10 +888,14 @@ template <int BN>
 static int launch_wgrad(basi_tc_conv* pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(wgrad_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(wgrad_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  basi::launch(wgrad_tc_kernel<BN>, dim3(pl->grid), dim3(NTHREADS), pl->smem, st, pl->mapA, pl->mapB, pl->dw, pl->wp);
+  if (pl->gbox == 1)
+    basi::launch(wgrad_tc_kernel<BN, 1>, dim3(pl->grid), dim3(NTHREADS), pl->smem, st, pl->mapA, pl->mapB, pl->dw, pl->wp);
+  else
+    basi::launch(wgrad_tc_kernel<BN, 2>, dim3(pl->grid), dim3(NTHREADS), pl->smem, st, pl->mapA, pl->mapB, pl->dw, pl->wp);
   return BASI_OK;
 }
 
@@ -1054,7 +1061,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (m_tiles + splits - 1) / splits;
     wp.splits = (m_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
-    const int stage_bytes = 2 * A_BYTES + (bn / 64) * A_BYTES;
+    pl->gbox = (cout <= 64 && !getenv("BASI_TC_WGRAD_GBOX2")) ? 1 : 2;
+    const int stage_bytes = pl->gbox * A_BYTES + (bn / 64) * A_BYTES;
     int stages = (int)((227 * 1024 - 2048) / stage_bytes);
     if (stages > 6) stages = 6;
     wp.stages = stages;
