@@ -20,6 +20,9 @@ SHAPES = [  # name, k, dil, cin, cout, H, B
     ("conv5_4", 3, 1, 2048, 256, 40, 16),
     ("conv1_3", 3, 1, 32, 64, 160, 16),
     ("conv2_3x3", 3, 1, 32, 32, 80, 16),
+    ("x_c64_160", 3, 1, 64, 64, 160, 16),
+    ("x_c128_160", 3, 1, 128, 128, 160, 16),
+    ("x_1x1_c32_160", 1, 1, 32, 64, 160, 16),
     ("psp_pool1_conv", 1, 1, 1024, 128, 1, 16),
     ("psp_pool6_conv", 1, 1, 1024, 128, 6, 16),
 ]
