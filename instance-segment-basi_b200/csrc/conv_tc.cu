@@ -167,6 +167,11 @@ struct ConvParams {
   int off_h, off_w, step;
   int accumulate;
   int stages;
+  int ring_bytes; // bytes of the operand rings in front of the barriers
+  // halo mode (3x3, stride 1): per pixel tile (8 cols x 16 rows x 1 image) and 64-channel chunk ONE activation box
+  // of 16 x (16 + 2*dil) pixels is loaded and all nine taps read it through row-shifted descriptors
+  // (start = halo + (dr * 16 + dc) * 128 B, SBO = 2048 B); stages = nh halo slots + nb weight slots
+  int halo, dil, halo_bytes, nh, nb;
   int out_bufs;   // 1 or 2 output staging buffers (2: the TMA store of tile i overlaps the epilogue of tile i+1)
   int debug;      // timing experiments only: 1 = skip the statistics atomics, 2 = skip the column sums too
   // optional fused batch-norm statistics of the produced tensor (fprop): per-channel sum / sum of squares of the
@@ -222,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr uint32_t TMEM_COLS = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
   static_assert(2 * MT * BN <= 512, "TMEM has 512 columns");
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base slot
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
@@ -230,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [row groups][2*BN] = 1024 floats
   // output staging for the TMA store: NBOX boxes of [128 px][64 ch] bf16, SWIZZLE_128B, 1024-B aligned
   constexpr int NBOX = (BN + 63) / 64;
-  uint8_t* stage_out = smem + (size_t)p.stages * STAGE + 1024 + 1024 * sizeof(float);
+  uint8_t* stage_out = smem + (size_t)p.ring_bytes + 1024 + 1024 * sizeof(float);
   stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_out) + 1023) & ~(uintptr_t)1023);
   volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -284,7 +289,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      // halo mode: per (tile, 64-channel chunk) one activation halo box + nine weight boxes
+      constexpr int B_BYTES = BN * 128;
+      int hs = 0, bs = 0;
+      uint32_t hph = 0, bph = 0;
+      for (int t = cid; t < total_tiles; t += ncl) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.TW, h0 = th * p.TH;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(empty0 + 8 * hs, hph ^ 1);
+          mbar_expect_tx(full0 + 8 * hs, p.halo_bytes);
+          tma_load_4d(smem_u32(smem + (size_t)hs * p.halo_bytes), &mapA, full0 + 8 * hs, kc * KC, w0 - p.dil, h0 - p.dil,
+                      tn);
+          if (++hs == p.nh) {
+            hs = 0;
+            hph ^= 1;
+          }
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int bi = p.nh + bs;
+            mbar_wait(empty0 + 8 * bi, bph ^ 1);
+            mbar_expect_tx(full0 + 8 * bi, B_BYTES);
+            tma_load_3d(smem_u32(smem + (size_t)p.nh * p.halo_bytes + (size_t)bs * B_BYTES), &mapB, full0 + 8 * bi, kc * KC,
+                        nt * BN, tap);
+            if (++bs == p.nb) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cid; t < total_tiles; t += ncl) {
@@ -326,7 +362,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && crank == 0) {
+    if (lane == 0 && p.halo) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0, BM);
+      constexpr int B_BYTES = BN * 128;
+      int hs = 0, bs = 0;
+      uint32_t hph = 0, bph = 0;
+      int it = 0;
+      for (int t = cid; t < total_tiles; t += ncl, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(full0 + 8 * hs, hph);
+          tc_fence_after();
+          const uint32_t ha = smem_u32(smem + (size_t)hs * p.halo_bytes);
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = tap / p.kw, sx = tap - r * p.kw;
+            int dr = p.off_h + r * p.step + p.dil, dc = p.off_w + sx * p.step + p.dil;
+            if (p.debug == 20) dr = dc = 0;          // timing experiment: aligned descriptor starts (wrong results)
+            if (p.debug == 21) dc = 0;               // timing experiment: 1024-B aligned starts only
+            const int bi = p.nh + bs;
+            mbar_wait(full0 + 8 * bi, bph);
+            tc_fence_after();
+            // rows of the tile's 8-pixel groups: 16 halo pixels (2048 B) apart; the tap only moves the start row
+            const uint64_t adesc = make_desc(ha + (uint32_t)(dr * 16 + dc) * 128, 16, 2048);
+            const uint64_t bdesc = make_desc(smem_u32(smem + (size_t)p.nh * p.halo_bytes + (size_t)bs * B_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+            umma_commit(empty0 + 8 * bi);
+            if (++bs == p.nb) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+          umma_commit(empty0 + 8 * hs);      // every tap has read the halo
+          if (++hs == p.nh) {
+            hs = 0;
+            hph ^= 1;
+          }
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    } else if (lane == 0 && crank == 0) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       int stage = 0;
       uint32_t phase = 0;
@@ -937,8 +1017,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
   pl->kind = kind;
   int TW, TH, TN;
   pick_tile(x->n, x->h, x->w, &TW, &TH, &TN);
-  const int tiles_w = (x->w + TW - 1) / TW, tiles_h = (x->h + TH - 1) / TH, tiles_n = (x->n + TN - 1) / TN;
-  const int m_tiles = tiles_w * tiles_h * tiles_n;
+  int tiles_w = (x->w + TW - 1) / TW, tiles_h = (x->h + TH - 1) / TH, tiles_n = (x->n + TN - 1) / TN;
+  int m_tiles = tiles_w * tiles_h * tiles_n;
   const int sms = basi::sm_count();
   int rc = BASI_OK;
   if (kind == BASI_TC_FPROP || kind == BASI_TC_DGRAD) {
@@ -982,7 +1062,24 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       if (env_mt && atoi(env_mt) == 1) pl->mt = 1;
       if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2) pl->mt = 2;   // tests
     }
-    rc = make_act_map(&pl->mapA, src, TW, TH, TN);
+    // halo mode for 3x3 convolutions (see ConvParams): tile = 8 x 16 pixels of one image, one activation box of
+    // 16 x (16 + 2 dil) pixels per 64-channel chunk serves all nine taps
+    bool halo = false;
+    {
+      const char* env_h = getenv("BASI_TC_HALO");
+      const bool can = d->kh == 3 && d->kw == 3 && d->dil >= 1 && d->dil <= 4 && d->pad_t == d->dil &&
+                       d->pad_l == d->dil && pl->cluster == 1 && bn <= 128;
+      halo = can && env_h && atoi(env_h) == 1;
+    }
+    if (halo) {
+      TW = 8; TH = 16; TN = 1;
+      tiles_w = (x->w + TW - 1) / TW; tiles_h = (x->h + TH - 1) / TH; tiles_n = x->n;
+      m_tiles = tiles_w * tiles_h * tiles_n;
+      pl->mt = 1;
+      rc = make_act_map(&pl->mapA, src, 16, 16 + 2 * d->dil, 1);
+    } else {
+      rc = make_act_map(&pl->mapA, src, TW, TH, TN);
+    }
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, pl->cluster == 2 ? bn / 2 : bn);
     if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
     if (rc != BASI_OK) {
@@ -1012,7 +1109,25 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     if (getenv("BASI_TC_STAGES") && atoi(getenv("BASI_TC_STAGES")) >= 2 && atoi(getenv("BASI_TC_STAGES")) < stages)
       stages = atoi(getenv("BASI_TC_STAGES"));   // experiment: bytes in flight vs main-loop time
     cp.stages = stages;
+    cp.ring_bytes = stages * stage_bytes;
     pl->smem = (size_t)stages * stage_bytes + fixed;
+    if (halo) {
+      cp.halo = 1; cp.dil = d->dil;
+      cp.halo_bytes = 16 * (16 + 2 * d->dil) * 128;
+      cp.nh = 2;
+      const int b_bytes = bn * 128;
+      int nb = (227 * 1024 - fixed - cp.nh * cp.halo_bytes) / b_bytes;
+      if (nb > 9) nb = 9;
+      if (nb < 2) {
+        delete pl;
+        set_error("tc_conv_create: halo mode does not fit in shared memory");
+        return BASI_E_INVALID;
+      }
+      cp.nb = nb;
+      cp.stages = cp.nh + cp.nb;
+      cp.ring_bytes = cp.nh * cp.halo_bytes + cp.nb * b_bytes;
+      pl->smem = (size_t)cp.ring_bytes + fixed;
+    }
     pl->dst = (bf16*)dstt->ptr;
     if (pl->mt == 2) {
       const int total = ((cp.m_tiles + 1) / 2) * cp.n_tiles;     // double tiles

@@ -104,6 +104,7 @@ TC_MODES = {
     "single": {"BASI_TC_MT": "1", "BASI_TC_CLUSTER": "0"},     # one 128-pixel tile per work item
     "double": {"BASI_TC_MT": "2", "BASI_TC_CLUSTER": "0"},     # two pixel tiles share the weight box
     "pairs": {"BASI_TC_CLUSTER": "1"},                          # cta_group::2: one M = 256 MMA per CTA pair
+    "halo": {"BASI_TC_HALO": "1", "BASI_TC_CLUSTER": "0"},      # 3x3: one activation halo box serves all nine taps
 }
 
 
