@@ -172,6 +172,8 @@ struct ConvParams {
   // of 16 x (16 + 2*dil) pixels is loaded and all nine taps read it through row-shifted descriptors
   // (start = halo + (dr * 16 + dc) * 128 B, SBO = 2048 B); stages = nh halo slots + nb weight slots
   int halo, dil, halo_bytes, nh, nb;
+  int bres;       // halo mode, one 64-channel chunk, one channel tile: the nine weight boxes stay resident in shared
+                  // memory for the whole CTA (loaded once), a tile only pulls its activation halo
   int out_bufs;   // 1 or 2 output staging buffers (2: the TMA store of tile i overlaps the epilogue of tile i+1)
   int debug;      // timing experiments only: 1 = skip the statistics atomics, 2 = skip the column sums too
   // optional fused batch-norm statistics of the produced tensor (fprop): per-channel sum / sum of squares of the
@@ -184,6 +186,10 @@ struct ConvParams {
   double bn_count;
   float bn_eps;
 };
+
+// BASI_TC_DEBUG_STATS=30: CTA 0 accumulates the cycles its roles spend waiting (see basi_tc_conv_run)
+__device__ unsigned long long g_tc_dbg[16];
+__device__ __forceinline__ long long dbg_clock() { return clock64(); }
 
 // transpose-reduce across the 32 lanes of a warp: on return v[0] of lane l is the sum over all lanes of their v[l]
 __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
@@ -294,6 +300,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr int B_BYTES = BN * 128;
       int hs = 0, bs = 0;
       uint32_t hph = 0, bph = 0;
+      if (p.bres && cid < total_tiles) {
+        // resident weights: all taps of the (only) channel tile and chunk, once
+        mbar_expect_tx(full0 + 8 * p.nh, p.taps * B_BYTES);
+        for (int tap = 0; tap < p.taps; ++tap)
+          tma_load_3d(smem_u32(smem + (size_t)p.nh * p.halo_bytes + (size_t)tap * B_BYTES), &mapB, full0 + 8 * p.nh, 0, 0,
+                      tap);
+      }
       for (int t = cid; t < total_tiles; t += ncl) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -307,6 +320,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             hs = 0;
             hph ^= 1;
           }
+          if (p.bres) continue;
           for (int tap = 0; tap < p.taps; ++tap) {
             const int bi = p.nh + bs;
             mbar_wait(empty0 + 8 * bi, bph ^ 1);
@@ -368,16 +382,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int hs = 0, bs = 0;
       uint32_t hph = 0, bph = 0;
       int it = 0;
+      if (p.bres && cid < total_tiles) {
+        mbar_wait(full0 + 8 * p.nh, 0);          // the resident weight boxes have landed
+        tc_fence_after();
+      }
       for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const bool dbg = p.debug == 30 && blockIdx.x == 0;
+        long long m0 = dbg ? dbg_clock() : 0;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(full0 + 8 * hs, hph);
+          if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[5] += m1 - m0; m0 = m1; }
           tc_fence_after();
           const uint32_t ha = smem_u32(smem + (size_t)hs * p.halo_bytes);
+          if (p.bres) {
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const int r = tap / p.kw, sx = tap - r * p.kw;
+              const int dr = p.off_h + r * p.step + p.dil, dc = p.off_w + sx * p.step + p.dil;
+              const uint64_t adesc = make_desc(ha + (uint32_t)(dr * 16 + dc) * 128, 16, 2048);
+              const uint64_t bdesc =
+                  make_desc(smem_u32(smem + (size_t)p.nh * p.halo_bytes + (size_t)tap * B_BYTES), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0);
+            }
+            umma_commit(empty0 + 8 * hs);
+            if (++hs == p.nh) {
+              hs = 0;
+              hph ^= 1;
+            }
+            continue;
+          }
           for (int tap = 0; tap < p.taps; ++tap) {
             const int r = tap / p.kw, sx = tap - r * p.kw;
             int dr = p.off_h + r * p.step + p.dil, dc = p.off_w + sx * p.step + p.dil;
@@ -414,11 +454,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const bool dbg = p.debug == 30 && blockIdx.x == 0;
+        long long m0 = dbg ? dbg_clock() : 0;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+        if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ks = 0; ks < ksteps; ++ks) {
+          if (dbg) m0 = dbg_clock();
           mbar_wait(full0 + 8 * stage, phase);
+          if (dbg) g_tc_dbg[5] += dbg_clock() - m0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
           const uint64_t bdesc = make_desc(sa + MT * A_BYTES, 16, 1024);
@@ -461,7 +506,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.n_tiles;
+      const bool dbg = p.debug == 30 && blockIdx.x == 0 && issuer;
+      long long c0 = dbg ? dbg_clock() : 0;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
+      if (dbg) { const long long c1 = dbg_clock(); g_tc_dbg[0] += c1 - c0; g_tc_dbg[1] += 1; c0 = c1; }
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub, ++sidx) {
@@ -472,8 +520,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // the TMA store that last used this staging buffer must have finished reading it
       const uint32_t so = so_base + (p.out_bufs == 2 ? (uint32_t)(sidx & 1) * (NBOX * A_BYTES) : 0u);
       if (issuer) {
+        const long long w0c = dbg ? dbg_clock() : 0;
         if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (dbg) g_tc_dbg[2] += dbg_clock() - w0c;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + sub * BN;
@@ -566,6 +616,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       }   // sub
+      if (dbg) g_tc_dbg[3] += dbg_clock() - c0;     // epilogue work of this tile (after the accumulator arrived)
     }
     if (do_stats && run_nt >= 0 && (int)threadIdx.x - 128 < BN && p.debug == 0) {
       double* rep = p.bn_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * p.Cdst;
@@ -1116,17 +1167,30 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       cp.halo_bytes = 16 * (16 + 2 * d->dil) * 128;
       cp.nh = 2;
       const int b_bytes = bn * 128;
+      if (cp.k_chunks == 1 && cp.n_tiles == 1 && !getenv("BASI_TC_HALO_NO_BRES")) {
+        // resident weights: the nine boxes once per CTA, the rest of the shared memory for activation halos
+        int nh = (227 * 1024 - fixed - cp.taps * b_bytes) / cp.halo_bytes;
+        if (nh > 4) nh = 4;
+        if (nh >= 2) {
+          cp.bres = 1; cp.nh = nh; cp.nb = 1;
+          cp.stages = cp.nh + 1;
+          cp.ring_bytes = cp.nh * cp.halo_bytes + cp.taps * b_bytes;
+          pl->smem = (size_t)cp.ring_bytes + fixed;
+        }
+      }
       int nb = (227 * 1024 - fixed - cp.nh * cp.halo_bytes) / b_bytes;
       if (nb > 9) nb = 9;
-      if (nb < 2) {
+      if (nb < 2 && !cp.bres) {
         delete pl;
         set_error("tc_conv_create: halo mode does not fit in shared memory");
         return BASI_E_INVALID;
       }
-      cp.nb = nb;
-      cp.stages = cp.nh + cp.nb;
-      cp.ring_bytes = cp.nh * cp.halo_bytes + cp.nb * b_bytes;
-      pl->smem = (size_t)cp.ring_bytes + fixed;
+      if (!cp.bres) {
+        cp.nb = nb;
+        cp.stages = cp.nh + cp.nb;
+        cp.ring_bytes = cp.nh * cp.halo_bytes + cp.nb * b_bytes;
+        pl->smem = (size_t)cp.ring_bytes + fixed;
+      }
     }
     pl->dst = (bf16*)dstt->ptr;
     if (pl->mt == 2) {
@@ -1216,6 +1280,17 @@ int basi_tc_conv_run(basi_tc_conv* pl, void* stream) {
     else launch_conv<32>(pl, st);
   }
   BASI_CHECK_LAUNCH("tc_conv_run");
+  if (pl->kind != BASI_TC_WGRAD && pl->cp.debug == 30) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
+    const double n = h[1] ? (double)h[1] : 1.0;
+    fprintf(stderr, "tc debug (CTA 0, %llu tiles, cycles per tile): epilogue waits accumulator %.0f | waits store-read %.0f | "
+            "epilogue work %.0f || MMA waits epilogue %.0f | MMA waits operands %.0f\n",
+            h[1], h[0] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
+  }
   return BASI_OK;
 }
 
