@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbasi_b200.so")
+LIB_PATH = os.environ.get("BASI_LIB") or os.path.join(_HERE, "libbasi_b200.so")   # BASI_LIB: A/B another build
 
 F32, BF16 = 0, 1
 TC_FPROP, TC_DGRAD, TC_WGRAD = 0, 1, 2

@@ -214,7 +214,10 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------------
-template <int BN, int CL, int MT>
+// VAR: 0 = the production kernel, 1 = halo mode (+ role timers), 2 = production kernel with the role timers
+// (compile-time so that the experimental paths cost the production kernel nothing: as run-time branches they
+// measured 1.8 % of the training step)
+template <int BN, int CL, int MT, int VAR>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
@@ -228,6 +231,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // bound by L2 -> SM bytes (148 SMs x 32 KB per 0.37 us k-step = the ~12 TB/s L2 cap); sharing the weight box cuts
   // the bytes per flop by 25 %.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr bool HALO = VAR == 1, TIMERS = VAR != 0;
+  static_assert(!HALO || (CL == 1 && MT == 1), "halo mode: one tile per CTA, no pairs");
   constexpr int STAGE = SmemLayout<BN, MT, CL>::STAGE;
   static_assert(CL == 1 || MT == 1, "pairs take one pixel tile per CTA");
   constexpr uint32_t TMEM_COLS = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
@@ -295,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && p.halo) {
+    if (lane == 0 && HALO) {
       // halo mode: per (tile, 64-channel chunk) one activation halo box + nine weight boxes
       constexpr int B_BYTES = BN * 128;
       int hs = 0, bs = 0;
@@ -376,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && p.halo) {
+    if (lane == 0 && HALO) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, BM);
       constexpr int B_BYTES = BN * 128;
       int hs = 0, bs = 0;
@@ -389,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const bool dbg = p.debug == 30 && blockIdx.x == 0;
+        const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0;
         long long m0 = dbg ? dbg_clock() : 0;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
@@ -454,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const bool dbg = p.debug == 30 && blockIdx.x == 0;
+        const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0;
         long long m0 = dbg ? dbg_clock() : 0;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
@@ -506,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.n_tiles;
-      const bool dbg = p.debug == 30 && blockIdx.x == 0 && issuer;
+      const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && issuer;
       long long c0 = dbg ? dbg_clock() : 0;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       if (dbg) { const long long c1 = dbg_clock(); g_tc_dbg[0] += c1 - c0; g_tc_dbg[1] += 1; c0 = c1; }
@@ -996,23 +1001,29 @@ static bool tc_geometry_ok(int kind, const basi_conv_desc* d, const basi_tensor*
 template <int BN>
 static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
   static bool attr_set = false;
+  constexpr int BNS = BN <= 128 ? BN : 128;      // channel-tile widths the two-tile / halo variants exist for
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<BN, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (BN <= 128)
-      cudaFuncSetAttribute(conv_tc_kernel<(BN <= 128 ? BN : 128), 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BNS, 1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BNS, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<BNS, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  if (pl->mt == 2 && BN <= 128)
-    basi::launch(conv_tc_kernel<(BN <= 128 ? BN : 128), 1, 2>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA,
-                 pl->mapB, pl->mapD, pl->cp);
-  else if (pl->cluster == 2)
-    basi::launch_ex(conv_tc_kernel<BN, 2, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, 2, pl->mapA, pl->mapB,
-                    pl->mapD, pl->cp);
+  const dim3 grid(pl->grid), block(NTHREADS_CONV);
+  const bool timers = pl->cp.debug == 30;
+  if (pl->cp.halo && BN <= 128)
+    basi::launch(conv_tc_kernel<BNS, 1, 1, 1>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  else if (pl->mt == 2 && BN <= 128) {
+    if (timers) basi::launch(conv_tc_kernel<BNS, 1, 2, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    else basi::launch(conv_tc_kernel<BNS, 1, 2, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  } else if (pl->cluster == 2)
+    basi::launch_ex(conv_tc_kernel<BN, 2, 1, 0>, grid, block, pl->smem, st, 2, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+  else if (timers)
+    basi::launch(conv_tc_kernel<BN, 1, 1, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
   else
-    basi::launch(conv_tc_kernel<BN, 1, 1>, dim3(pl->grid), dim3(NTHREADS_CONV), pl->smem, st, pl->mapA, pl->mapB, pl->mapD,
-                 pl->cp);
+    basi::launch(conv_tc_kernel<BN, 1, 1, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
   return BASI_OK;
 }
 template <int BN>
