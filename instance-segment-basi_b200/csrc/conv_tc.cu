@@ -105,6 +105,14 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// one lane of a fully converged warp (elect.sync): the MMA-issuing warp runs its loops warp-uniformly and only the
+// tcgen05 instructions themselves are predicated on the elected lane, so the compiler keeps descriptors and barrier
+// addresses in uniform registers instead of wrapping every uniform-datapath instruction in a per-thread loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -451,7 +459,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         umma_commit(tfull0 + 8 * acc);
       }
-    } else if (lane == 0 && crank == 0) {
+    } else if (!HALO && crank == 0) {
+      // all 32 lanes run the loops (warp-uniform control flow); the elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       int stage = 0;
       uint32_t phase = 0;
@@ -459,7 +468,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = cid; t < total_tiles; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0;
+        const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && lane == 0;
         long long m0 = dbg ? dbg_clock() : 0;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
@@ -472,27 +481,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
           const uint64_t bdesc = make_desc(sa + MT * A_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int sub = 0; sub < MT; ++sub) {
-            const uint64_t adesc = make_desc(sa + sub * A_BYTES, 16, 1024);
+            for (int sub = 0; sub < MT; ++sub) {
+              const uint64_t adesc = make_desc(sa + sub * A_BYTES, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-              if (CL == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
-              else umma_f16(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+              for (int k = 0; k < KC / 16; ++k) {
+                // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+                if (CL == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                else umma_f16(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+              }
             }
+            // frees the smem slot (pair: in both CTAs)
+            if (CL == 2) umma_commit_pair(empty0 + 8 * stage, (uint16_t)3);
+            else umma_commit(empty0 + 8 * stage);
           }
-          // frees the smem slot (pair: in both CTAs)
-          if (CL == 2) umma_commit_pair(empty0 + 8 * stage, (uint16_t)3);
-          else umma_commit(empty0 + 8 * stage);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator complete -> epilogue (pair: of both CTAs)
-        if (CL == 2) umma_commit_pair(tfull0 + 8 * acc, (uint16_t)3);
-        else umma_commit(tfull0 + 8 * acc);
+        if (elect_one()) {
+          if (CL == 2) umma_commit_pair(tfull0 + 8 * acc, (uint16_t)3);
+          else umma_commit(tfull0 + 8 * acc);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
