@@ -779,7 +779,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loops, the elected lane issues (see elect_one)
+    {
       constexpr uint32_t idesc = make_idesc(BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -790,18 +791,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         // MN-major: LBO = 16 KB between 64-channel blocks, SBO = 1 KB between groups of 8 pixel rows
         const uint64_t adesc = make_desc(sa, GBOX == 2 ? A_BYTES : 0, 1024);
         const uint64_t bdesc = make_desc(sa + GB, A_BYTES, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BM / 16; ++k) {
-          // 16 pixels (K) further = 16 rows of 128 B = 2 KB -> +128 in 16-B units
-          umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (st | k) != 0);
+          for (int k = 0; k < BM / 16; ++k) {
+            // 16 pixels (K) further = 16 rows of 128 B = 2 KB -> +128 in 16-B units
+            umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (st | k) != 0);
+          }
+          umma_commit(empty0 + 8 * stage);
         }
-        umma_commit(empty0 + 8 * stage);
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q = warp - 4;
