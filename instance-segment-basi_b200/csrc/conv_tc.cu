@@ -347,7 +347,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
-    } else if (lane == 0) {
+    } else if (!HALO) {
+      // warp-uniform loops, the elected lane issues the copies (see elect_one)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cid; t < total_tiles; t += ncl) {
@@ -365,20 +366,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
-            if (CL == 2) {
-              // both CTAs' bytes are counted on the leader's barrier
-              const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
-              if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE);
-              tma_load_4d_pair(sa, &mapA, fb, kc * KC, w0[0] + dw, h0[0] + dh, n0[0]);
-              tma_load_3d_pair(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap);
-            } else {
-              const uint32_t fb = full0 + 8 * stage;
-              mbar_expect_tx(fb, STAGE);
+            if (elect_one()) {
+              if (CL == 2) {
+                // both CTAs' bytes are counted on the leader's barrier
+                const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+                if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE);
+                tma_load_4d_pair(sa, &mapA, fb, kc * KC, w0[0] + dw, h0[0] + dh, n0[0]);
+                tma_load_3d_pair(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap);
+              } else {
+                const uint32_t fb = full0 + 8 * stage;
+                mbar_expect_tx(fb, STAGE);
 #pragma unroll
-              for (int sub = 0; sub < MT; ++sub)
-                tma_load_4d(sa + sub * A_BYTES, &mapA, fb, kc * KC, w0[sub] + dw, h0[sub] + dh, n0[sub]);
-              tma_load_3d(sa + MT * A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+                for (int sub = 0; sub < MT; ++sub)
+                  tma_load_4d(sa + sub * A_BYTES, &mapA, fb, kc * KC, w0[sub] + dw, h0[sub] + dh, n0[sub]);
+                tma_load_3d(sa + MT * A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
+              }
             }
+            __syncwarp();
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -757,7 +761,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   const int nsteps = mt_end - mt_beg;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int mt = mt_beg; mt < mt_end; ++mt) {
@@ -766,12 +770,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
         const uint32_t fb = full0 + 8 * stage;
-        mbar_expect_tx(fb, STAGE);
-        tma_load_4d(sa, &mapG, fb, cot * 128, w0, h0, n0);
-        if (GBOX == 2) tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
-        const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
+        if (elect_one()) {
+          mbar_expect_tx(fb, STAGE);
+          tma_load_4d(sa, &mapG, fb, cot * 128, w0, h0, n0);
+          if (GBOX == 2) tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
+          const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, cit * BN + j * 64, xw, xh, n0);
+          for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, cit * BN + j * 64, xw, xh, n0);
+        }
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
