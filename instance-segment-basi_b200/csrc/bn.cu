@@ -460,11 +460,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs& a, Body&& body) {
       }
     }
   };
-  if (tid == 0)
-    for (long long k = 0; k < nk && k < a.nst - 1; ++k) issue(k);
+  const bool warp0 = tid < 32;           // warp 0 issues the copies warp-uniformly through its elected lane
+  if (warp0) {
+    for (long long k = 0; k < nk && k < a.nst - 1; ++k) {
+      if (elect_one()) issue(k);
+      __syncwarp();
+    }
+  }
   for (long long k = 0; k < nk; ++k) {
     const int st = (int)(k % a.nst);
-    if (tid == 0 && k + a.nst - 1 < nk) issue(k + a.nst - 1);   // refills the stage consumed in iteration k-1
+    if (warp0 && k + a.nst - 1 < nk) {   // refills the stage consumed in iteration k-1
+      if (elect_one()) issue(k + a.nst - 1);
+      __syncwarp();
+    }
     mbar_wait(bar0 + 8 * st, (uint32_t)((k / a.nst) & 1));
     const long long row0 = slab_of(k) * SR;
     const int rows = (int)min((long long)SR, a.R - row0);

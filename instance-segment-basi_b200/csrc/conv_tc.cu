@@ -105,14 +105,6 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-// one lane of a fully converged warp (elect.sync): the MMA-issuing warp runs its loops warp-uniformly and only the
-// tcgen05 instructions themselves are predicated on the elected lane, so the compiler keeps descriptors and barrier
-// addresses in uniform registers instead of wrapping every uniform-datapath instruction in a per-thread loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

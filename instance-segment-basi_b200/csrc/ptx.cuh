@@ -47,6 +47,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a fully converged warp (elect.sync).  Code that issues bulk / tensor copies or tcgen05 instructions runs
+// warp-uniformly and predicates only the instruction on the elected lane: the compiler then keeps the addresses in
+// uniform registers instead of wrapping every uniform-datapath instruction of a single-lane branch in an
+// ELECT / R2UR / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 }  // namespace basi
