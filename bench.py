@@ -3,11 +3,14 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N>1: under torchrun)
   python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference (oracle)
+  python bench.py --workload cfg2|cfg3|cfg4|cfg5 ...       # the other BASELINE.json configs as first-class lines
 
-Workload = BASELINE.json configs[1]: segment-only training (1NoClass head, pos_weight=3), synthetic
-VOC-shaped 320x320 inputs, batch 16 per GPU, random-init weights; N>1 is weak scaling (16 per GPU),
-data-parallel with a bucketed NCCL gradient all-reduce.  One step = click-map pack + forward + fused loss
-+ backward + SGD.  Prints ONE JSON line (rank 0).
+Default workload = cfg3, the configuration BASELINE.json quotes the 1/2/4/8-GPU metric on: segment + attention-class
+joint training (2AddClass: pos_weight-3 weighted BCE + 0.2 x class CE, 21 classes), synthetic VOC-shaped 320x320
+inputs, batch 16 per GPU, random-init weights, plain SGD; N>1 is weak scaling (16 per GPU), data-parallel with a
+bucketed NCCL gradient all-reduce (118 MB).  At N=1 the line also carries cfg2 (segment only, round 1's headline)
+under "also".  One step = click-map pack + forward + fused losses + backward + SGD.  Prints ONE JSON line (rank 0)
+on the real stdout; everything else any library prints (NCCL_DEBUG output included) goes to stderr.
 """
 from __future__ import annotations
 
@@ -26,9 +29,35 @@ for p in (ROOT, os.path.join(ROOT, "instance-segment-basi_b200")):
 
 METRIC = "train images/sec at 320^2"
 UNIT = "images/s"
-S, P, BATCH, FILTERS = 320, 40, 16, 32
-VARIANT, NSEG, CLASSES = "1NoClass", 1, 21
-FLOP_PER_IMAGE = 153.3e9       # fwd+bwd conv FLOPs per image at 320^2
+FILTERS = 32
+# fwd+bwd conv FLOPs per image (3 x forward, conv1_1 has no dgrad)
+WORKLOADS = {
+    "cfg2": dict(variant="1NoClass", S=320, batch=16, classes=21, flop_per_image=153.2e9,
+                 text="cfg2: BAISNet segment-only training (1NoClass head, pos_weight=3), synthetic VOC-shape 320x320, "
+                      "batch 16 per GPU, F=32, SGD"),
+    "cfg3": dict(variant="2AddClass", S=320, batch=16, classes=21, flop_per_image=153.3e9,
+                 text="cfg3: segment + attention-class joint training (2AddClass, pos_weight=3, 0.2*loss_classes, "
+                      "21 VOC classes), synthetic VOC-shape 320x320, batch 16 per GPU, F=32, SGD"),
+    "cfg4": dict(variant="4BorderClass", S=512, batch=4, classes=21, flop_per_image=392.3e9,
+                 text="cfg4: 4-class border variant (4BorderClass head, softmax CE + 0.1*loss_classes), synthetic "
+                      "512x512, batch 4 per GPU (32 on 8 GPUs), F=32, SGD"),
+    "cfg5": dict(variant="5COCO", S=640, batch=16, classes=81, flop_per_image=612.9e9,
+                 text="cfg5: COCO-shape joint training (5COCO head, 81 classes, sigma 20, 0.2*loss_classes), synthetic "
+                      "640x640, batch 16 per GPU (128 on 8 GPUs), F=32, SGD"),
+}
+DEFAULT_WORKLOAD = "cfg3"
+GOLDEN_IMAGE = os.path.join(ROOT, "tests", "golden", "input_7.jpg")     # the reference's input/7.jpg (cfg1)
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (NCCL_DEBUG=INFO, which the driver may set to check the rank
+    count) and other libraries write to file descriptor 1, so fd 1 is pointed at stderr for the whole process and
+    the JSON line is written to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+    return os.fdopen(real, "w", buffering=1)
 
 
 def peaks():
@@ -84,7 +113,12 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_oracle_rate(batch, steps, warmup=1):
+def _snapshot(variant):
+    from basi_b200.BAISRunnerTrain import SNAPSHOT
+    return SNAPSHOT[variant]
+
+
+def cpu_oracle_rate(wl, batch, steps, warmup=1):
     """Oracle (CPU restatement of the reference, TF unavailable) timed on the host cores: images/s."""
     import numpy as np
     import torch
@@ -92,14 +126,18 @@ def cpu_oracle_rate(batch, steps, warmup=1):
     from oracle import basi_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = SyntheticData(batch, (S, S), 8, CLASSES, NSEG, seed=0)
-    params = O.init_params(O.param_specs(VARIANT, CLASSES, NSEG, FILTERS), 0)
+    variant, S, classes = wl["variant"], wl["S"], wl["classes"]
+    snap = _snapshot(variant)
+    nseg = snap["num_segment"]
+    sd = SyntheticData(batch, (S, S), 8, classes, nseg, sigma=20 if variant == "5COCO" else 30, seed=0)
+    params = O.init_params(O.param_specs(variant, classes, nseg, FILTERS), 0)
     times = []
     for i in range(warmup + steps):
         img, clicks, lab, cls = sd.next_batch()
         t0 = time.perf_counter()
-        data = np.stack([O.pack_input(img[b], clicks[b]) for b in range(batch)])
-        r = O.train_step(params, data, lab, cls, VARIANT, NSEG, P, 3.0, 0.0, 5e-3, torch.float32)
+        data = np.stack([O.pack_input(img[b], clicks[b], sd.sigma) for b in range(batch)])
+        r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, snap["pos_weight"], snap["class_weight"],
+                         5e-3, torch.float32)
         params = r["new_params"]
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -108,36 +146,62 @@ def cpu_oracle_rate(batch, steps, warmup=1):
 
 
 def click_latency(torch, precision, n=30):
-    """cfg 1: single-click inference (RunnerGUI semantics, 4BorderClass head, S=320, B=1): host image + click in,
-    thresholded full-resolution mask + class out.  p50 / p90 wall-clock latency in ms."""
+    """cfg 1: single-click inference on the reference's own fixture input/7.jpg (262x200) with RunnerGUI semantics
+    (4BorderClass head, S=320, B=1): run_image = PIL decode + bicubic resize to 320x320 + click + H2D + CUDA-graph
+    forward + legacy-bilinear upsample + argmax + D2H + nearest resize back.  p50 / p90 wall-clock in ms, with the
+    host-side image work (decode + resize) reported separately."""
     import numpy as np
+    from PIL import Image
     from basi_b200.BAISRunnerOne import RunnerGUI
+    S, P = 320, 40
     gui = RunnerGUI(None, last_pool_size=P, variant="4BorderClass", num_classes=21, num_segment=4,
                     filter_number=FILTERS, precision=precision)
+    have_fixture = os.path.exists(GOLDEN_IMAGE)
+    raw = np.array(Image.open(GOLDEN_IMAGE).convert("RGB")) if have_fixture else \
+        np.random.RandomState(0).randint(0, 256, size=(200, 262, 3), dtype=np.uint8)
+    img320 = np.asarray(Image.fromarray(raw).resize((S, S), Image.BICUBIC), dtype=np.uint8)
     rng = np.random.RandomState(0)
-    img = rng.randint(0, 256, size=(S, S, 3), dtype=np.uint8)
     for _ in range(3):
-        gui.click(img, [160, 160])
-    ts = []
+        gui.click(img320, [160, 160])
+    t_click, t_full, t_host = [], [], []
     for i in range(n):
-        where = [int(rng.randint(0, S)), int(rng.randint(0, S))]
+        xy = [int(rng.randint(0, raw.shape[1])), int(rng.randint(0, raw.shape[0]))]
         t0 = time.perf_counter()
-        gui.click(img, where)
-        ts.append((time.perf_counter() - t0) * 1e3)
-    ts.sort()
-    return {"p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "n": n,
+        if have_fixture:
+            seg, cls, where = gui.run_image(GOLDEN_IMAGE, xy)          # decode + resize + click + resize back
+        else:
+            seg, cls, where = gui.run_image(raw, xy)
+        t_full.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        gui.click(img320, where)                                      # the click-to-mask compute alone
+        t_click.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        d = np.array(Image.open(GOLDEN_IMAGE)) if have_fixture else raw
+        np.asarray(Image.fromarray(d.astype(np.uint8)).convert("RGB").resize((S, S), Image.BICUBIC), dtype=np.uint8)
+        t_host.append((time.perf_counter() - t0) * 1e3)
+    for t in (t_click, t_full, t_host):
+        t.sort()
+    return {"p50_ms": t_click[len(t_click) // 2], "p90_ms": t_click[int(len(t_click) * 0.9)], "n": n,
+            "run_image_p50_ms": t_full[len(t_full) // 2], "decode_resize_p50_ms": t_host[len(t_host) // 2],
             "h2d_bytes": S * S * 3 + 8, "d2h_bytes": S * S * 4 + 4,
-            "workload": "cfg1: RunnerGUI single click, 320x320, batch 1, 4BorderClass head, CUDA-graph forward"}
+            "image": "tests/golden/input_7.jpg (reference input/7.jpg, 262x200, PIL BICUBIC to 320x320)"
+                     if have_fixture else "random 262x200 image (fixture missing)",
+            "workload": "cfg1: RunnerGUI single click, 320x320, batch 1, 4BorderClass head, CUDA-graph forward; "
+                        "p50_ms = click() (H2D + forward + upsample/argmax + D2H), run_image adds decode + resizes"}
 
 
 def cpu_click_latency(n=3):
     import numpy as np
     import torch
+    from PIL import Image
     from oracle import basi_oracle as O
+    S, P = 320, 40
     torch.set_num_threads(os.cpu_count() or 1)
     params = O.to_torch(O.init_params(O.param_specs("4BorderClass", 21, 4, FILTERS), 0), torch.float32)
-    rng = np.random.RandomState(0)
-    img = rng.randint(0, 256, size=(S, S, 3), dtype=np.uint8)
+    if os.path.exists(GOLDEN_IMAGE):
+        img = np.asarray(Image.open(GOLDEN_IMAGE).convert("RGB").resize((S, S), Image.BICUBIC), dtype=np.uint8)
+    else:
+        img = np.random.RandomState(0).randint(0, 256, size=(S, S, 3), dtype=np.uint8)
     ts = []
     with torch.no_grad():
         for i in range(n + 1):
@@ -151,22 +215,29 @@ def cpu_click_latency(n=3):
     return ts[len(ts) // 2]
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
     batch = 2
-    rate, cores, sec = cpu_oracle_rate(batch, max(1, args.steps), 1)
-    sample = "oracle fwd+bwd+SGD, S=320, batch %d per step, float32 torch-CPU (%d threads)" % (batch, cores)
+    rate, cores, sec = cpu_oracle_rate(wl, batch, max(1, args.steps), 1)
+    sample = "oracle fwd+bwd+SGD, S=%d, batch %d per step (GPU arm: %d), float32 torch-CPU (%d threads)" % (
+        wl["S"], batch, wl["batch"], cores)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: segment-only training (1NoClass, pos_weight=3), 320x320, CPU sample batch 2",
+            "config": {"workload": wl["text"] + " -- CPU arm: bounded sample, batch %d per step" % batch,
                        "note": "reference TF1 cannot run here; this is the CPU oracle restating it"},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+KERNEL_GROUP = {"basi_tc_conv_run:0": "conv_tc_kernel(fprop+dgrad)", "basi_tc_conv_run:1": "conv_tc_kernel(fprop+dgrad)",
+                "basi_tc_conv_run:2": "wgrad_tc_kernel"}
 
 
 def kernel_profile(eng, torch, detail_path=None):
@@ -186,8 +257,7 @@ def kernel_profile(eng, torch, detail_path=None):
         for i, (name, fn, a, meta) in enumerate(lst):
             ms = evs[i].elapsed_time(evs[i + 1])
             # fprop (:0) and dgrad (:1) plans run the same kernel, conv_tc_kernel; wgrad (:2) is wgrad_tc_kernel
-            name = {"basi_tc_conv_run:0": "conv_tc_kernel(fprop+dgrad)", "basi_tc_conv_run:1": "conv_tc_kernel(fprop+dgrad)",
-                    "basi_tc_conv_run:2": "wgrad_tc_kernel"}.get(name, name)
+            name = KERNEL_GROUP.get(name, name)
             d = agg.setdefault(name, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
             d["ms"] += ms
             d["n"] += 1
@@ -202,35 +272,87 @@ def kernel_profile(eng, torch, detail_path=None):
     return agg
 
 
-def run_ours(args):
+def hbm_microbench(torch, pk):
+    """SURVEY section 8(d) / BASELINE.md section 3: the fused loss, gating and SGD kernels on >= 64 M-element tensors
+    (the training step's own loss tensor has 25 600 elements: latency-bound).  Working sets of 0.4-1.6 GB exceed the
+    126 MB L2, so every iteration streams from HBM.  Algorithmic bytes: one read per input, one write per output."""
+    import ctypes as C
+    from basi_b200 import _lib
+    from basi_b200.engine import Act
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    n = 64 << 20
+    res = {}
+
+    def timed(fn, nbytes, reps=8):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"elements": n, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / pk["hbm"], 3),
+                "algorithmic_bytes": int(nbytes)}
+
+    # fused weighted BCE forward + gradient: logits f32 + labels f32 in, dlogits f32 out = 12 B / logit
+    logits = torch.randn(n, device=dev)
+    labels = (torch.rand(n, device=dev) > 0.7).float()
+    dlog = torch.empty(n, device=dev)
+    acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    res["wbce_fwd_bwd_f32"] = timed(lambda: _lib.call(
+        "basi_wbce_fwd_bwd", logits.data_ptr(), labels.data_ptr(), C.c_float(3.0), C.c_double(1.0 / n),
+        C.c_float(1.0 / n), C.c_int64(n), acc.data_ptr(), dlog.data_ptr(), st), 12.0 * n)
+    del logits, labels, dlog
+    # SGD: w f32 + g f32 in, w out = 12 B / parameter
+    w = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev)
+    lr = torch.full((1,), 1e-3, device=dev)
+    res["sgd_step_f32"] = timed(lambda: _lib.call(
+        "basi_sgd_step", w.data_ptr(), g.data_ptr(), lr.data_ptr(), C.c_int64(n), None, st), 12.0 * n)
+    del w, g
+    # attention gate (class head): relu(feat) * logit, bf16 features [65536 px][1024 ch] = 64 Mi elements
+    px, ch = 65536, 1024
+    feat = Act(torch.randn(16, 64, 64, ch, device=dev).to(torch.bfloat16))
+    outp = Act(torch.empty(16, 64, 64, ch, device=dev, dtype=torch.bfloat16))
+    lg = torch.randn(16, 64, 64, 1, device=dev)
+    res["gate_mul_fwd_bf16"] = timed(lambda: _lib.call(
+        "basi_gate_mul_fwd", feat.ref, lg.data_ptr(), 1, 0, outp.ref, st), 2.0 * px * ch * 2 + px * 4)
+    dfeat = Act(torch.empty(16, 64, 64, ch, device=dev, dtype=torch.bfloat16))
+    dlg = torch.zeros(16, 64, 64, 1, device=dev)
+    res["gate_mul_bwd_bf16"] = timed(lambda: _lib.call(
+        "basi_gate_mul_bwd", outp.ref, feat.ref, lg.data_ptr(), 1, 0, dfeat.ref, 0, dlg.data_ptr(), st),
+        3.0 * px * ch * 2 + 2 * px * 4)
+    return res
+
+
+def measure(args, wl_name, dp, device, dev_index, rank, world, want_profile):
+    """Builds the workload, times the device-resident and the end-to-end step; returns the result dict."""
     import numpy as np
     import torch
     from basi_b200 import _lib
     from basi_b200.BAISRunnerTrain import Train
-    from basi_b200.dp import DataParallel
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    os.environ.pop("NCCL_DEBUG", None)         # keep NCCL's version banner off stdout (one JSON line only)
-    dp = DataParallel() if world > 1 else None
-    rank = dp.rank if dp else 0
-    dev_index = dp.local_rank if dp else 0
-    torch.cuda.set_device(dev_index)
-    device = "cuda:%d" % dev_index
-    tr = Train(batch_size=BATCH, last_pool_size=P, input_size=[S, S], log_dir="/tmp/basi_bench_%d" % rank,
-               variant=VARIANT, num_classes=CLASSES, precision=args.precision, filter_number=FILTERS, seed=0,
-               device=device, dp=dp, use_cuda_graph=not args.no_graph, use_tc=not args.no_tc)
+    wl = WORKLOADS[wl_name]
+    S, B = wl["S"], wl["batch"]
+    tr = Train(batch_size=B, last_pool_size=S // 8, input_size=[S, S], log_dir="/tmp/basi_bench_%d" % rank,
+               variant=wl["variant"], num_classes=wl["classes"], precision=args.precision, filter_number=FILTERS,
+               seed=0, device=device, dp=dp, use_cuda_graph=not args.no_graph, use_tc=not args.no_tc)
     eng = tr.engine
-    if dp:
-        dp.broadcast(eng.params_flat)
     sd = tr.data_reader
     # ---- pinned host batches (a small ring, refilled round-robin)
     ring = []
     for _ in range(4):
         img, clicks, lab, cls = sd.next_batch()
         ring.append((torch.from_numpy(img).pin_memory(), torch.from_numpy(clicks).pin_memory(),
-                     torch.from_numpy(np.ascontiguousarray(lab, dtype=np.float32)).pin_memory(), cls))
-    h2d = int(ring[0][0].numel() + ring[0][1].numel() * 4 + ring[0][2].numel() * 4 + 4)
-    d2h = 8 * 4
+                     torch.from_numpy(np.ascontiguousarray(
+                         lab, dtype=np.float32 if eng.label_seg.dtype == torch.float32 else np.int32)).pin_memory(),
+                     torch.from_numpy(np.ascontiguousarray(cls, dtype=np.int32)).pin_memory()))
+    h2d = int(ring[0][0].numel() + ring[0][1].numel() * 4 + ring[0][2].numel() * 4 +
+              (ring[0][3].numel() * 4 if eng.label_cls is not None else 0) + 4)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,7 +370,7 @@ def run_ours(args):
 
     # warm-up (also captures the CUDA graph)
     eng.feed_clicks(ring[0][0], ring[0][1])
-    eng.feed(None, ring[0][2], None, 5e-3)
+    eng.feed(None, ring[0][2], ring[0][3], 5e-3)
     if tr.use_cuda_graph:
         try:
             eng.capture(train=True, sync_grads=dp)
@@ -262,7 +384,7 @@ def run_ours(args):
         device_step()
     barrier()
 
-    sampler = ClockSampler(dev_index) if rank == 0 else None
+    sampler = ClockSampler(dev_index) if (rank == 0 and want_profile) else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
@@ -277,20 +399,23 @@ def run_ours(args):
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = _lib.LAUNCHES - launches0
-    # ---- (2) end to end through Train.run_step-equivalent: pinned H2D of every step's inputs, D2H of the loss
+    # ---- (2) end to end through the public API, Train.run_step(fetch=True) == the reference's
+    # sess.run([train_op, losses, raw_output_segment, pred_segment, ...], feed_dict): pinned H2D of every step's
+    # images / clicks / labels, the step, D2H of losses + segment logits + predictions (+ class logits / predictions)
+    for i in range(2):
+        tr.run_step(i, ring[i % len(ring)], fetch=True)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    last_loss = None
+    fetched = None
     for i in range(args.steps):
-        img, clicks, lab, cls = ring[i % len(ring)]
-        eng.feed_clicks(img, clicks)
-        eng.feed(None, lab, None, 5e-3)
-        device_step()
-        last_loss = eng.losses()          # D2H read of the step's loss (synchronises)
+        fetched = tr.run_step(i, ring[i % len(ring)], fetch=True)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    d2h = 32
+    for k in ("raw_output_segment", "pred_segment", "raw_output_classes", "pred_classes"):
+        if fetched is not None and k in fetched:
+            d2h += int(fetched[k].nbytes)
     if sampler:
         sampler.stop()
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
@@ -298,71 +423,103 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
-        return
-    pk = peaks()
-    images = world * BATCH * args.steps
-    value = images / (ms_dev * 1e-3)
-    e2e = images / (ms_e2e * 1e-3)
-    # ---- roofline of the dominant kernel (per-launch CUDA-event times of one eager step)
-    agg = kernel_profile(eng, torch, args.detail)
-    total_ms = sum(d["ms"] for d in agg.values())
-    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-    name, d = top
-    if d["flops"] > 0:
-        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
-                "launches_per_step": d["n"], "share_of_step": d["ms"] / total_ms}
-    else:
-        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"],
-                "launches_per_step": d["n"], "share_of_step": d["ms"] / total_ms}
-    # DRAM bytes per launch of that kernel group from the committed ncu capture of the same workload
-    # (profiles/traffic_r01.json, made by tools/make_traffic.py from the launch list of tools/profile_step.py)
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            grp = json.load(f).get("groups", {}).get(name)
-        if grp:
-            roof["traffic"] = grp["dram_bytes_per_launch"]
-            roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/traffic_r01.json"
-    except (OSError, ValueError):
-        pass
-    breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"],
-                     "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None,
-                     "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
-                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]}
-    # ---- CPU baseline (bounded sample on the host cores)
-    cpu = None
-    if not args.no_cpu:
-        rate, cores, sec = cpu_oracle_rate(2, 2, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle fwd+bwd+SGD at S=320, batch 2 x 2 steps, float32 torch-CPU (%.1f s/step)" % sec}
-    use_graph, tc_layers = bool(tr.use_cuda_graph), eng.tc_layers
+    images = world * B * args.steps
+    res = dict(wl=wl, value=images / (ms_dev * 1e-3), e2e=images / (ms_e2e * 1e-3), ms_dev=ms_dev / args.steps,
+               ms_e2e=ms_e2e / args.steps, launches=int(launches), h2d=h2d, d2h=d2h,
+               loss=fetched["loss"] if fetched else None, use_graph=bool(tr.use_cuda_graph), tc_layers=eng.tc_layers,
+               clocks=sampler.summary() if sampler else None, storage=eng.storage_policy,
+               launches_per_step=eng.launches_per_step())
+    if rank == 0 and want_profile:
+        pk = peaks()
+        agg = kernel_profile(eng, torch, args.detail)
+        total_ms = sum(d["ms"] for d in agg.values())
+        name, d = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        if d["flops"] > 0:
+            # the per-launch times come from one isolated eager step (no power cap, boost clocks): burst peak
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["source"] + " burst bf16 (cuBLAS)",
+                    "frac_of_sustained_peak": ach / pk["tensor_sustained"],
+                    "launches_per_step": d["n"], "share_of_step": d["ms"] / total_ms}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+                    "launches_per_step": d["n"], "share_of_step": d["ms"] / total_ms}
+        # DRAM bytes per launch of that kernel group from the committed ncu capture of the same workload
+        for tf in ("traffic_r02.json", "traffic_r01.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tf)) as f:
+                    grp = json.load(f).get("groups", {}).get(name)
+                if grp:
+                    roof["traffic"] = grp["dram_bytes_per_launch"]
+                    roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/" + tf
+                    break
+            except (OSError, ValueError):
+                pass
+        res["roofline"] = roof
+        res["whole_step_tflops"] = res["value"] * wl["flop_per_image"] / 1e12
+        res["breakdown"] = {k: {"ms": round(v["ms"], 3), "n": v["n"],
+                                "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None,
+                                "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
+                            for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:14]}
     del tr, eng
     torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, out):
+    import torch
+    from basi_b200.dp import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dp = DataParallel() if world > 1 else None
+    rank = dp.rank if dp else 0
+    dev_index = dp.local_rank if dp else 0
+    torch.cuda.set_device(dev_index)
+    device = "cuda:%d" % dev_index
+    r = measure(args, args.workload, dp, device, dev_index, rank, world, True)
+    also = {}
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_also:
+        a = measure(args, "cfg2", None, device, dev_index, 0, 1, False)
+        also["cfg2"] = {"workload": a["wl"]["text"], "value": a["value"], "unit": UNIT, "ms_per_step": a["ms_dev"],
+                        "e2e": a["e2e"], "whole_step_tflops": a["value"] * a["wl"]["flop_per_image"] / 1e12}
+    if rank != 0:
+        return
+    wl = r["wl"]
+    pk = peaks()
+    micro = None
+    if world == 1 and not args.no_micro:
+        micro = hbm_microbench(torch, pk)
+    cpu = None
+    if not args.no_cpu:
+        rate, cores, sec = cpu_oracle_rate(wl, 2, 2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle fwd+bwd+SGD of the same workload at batch 2 x 2 steps (GPU arm: batch %d), float32 "
+                         "torch-CPU (%.1f s/step)" % (wl["batch"], sec)}
     click = None
     if world == 1 and not args.no_click:
         click = click_latency(torch, args.precision)
         if not args.no_cpu:
             click["cpu_oracle_p50_ms"] = cpu_click_latency()
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": r["ms_dev"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "cfg2: BAISNet segment-only training (1NoClass head, pos_weight=3), synthetic "
-                                   "VOC-shape 320x320, batch 16 per GPU, F=32, SGD",
-                       "global_batch": world * BATCH, "parallelism": "dp%d" % world,
+            "config": {"workload": wl["text"], "global_batch": world * wl["batch"], "parallelism": "dp%d" % world,
                        "l2": "per-step working set (~3 GB of activations) exceeds the 126 MB L2",
-                       "cuda_graph": use_graph, "tc_layers": tc_layers,
-                       "model_tflops": value * FLOP_PER_IMAGE / 1e12},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "loss": last_loss[0] if last_loss else None},
-            "gpu_launches": int(launches),
-            "roofline": roof, "kernel_breakdown_ms_per_step": breakdown, "cpu_baseline": cpu,
-            "click_to_mask": click,
-            "clocks": sampler.summary() if sampler else None}
-    print(json.dumps(line), flush=True)
+                       "cuda_graph": r["use_graph"], "tc_layers": r["tc_layers"], "storage_policy": r["storage"],
+                       "launches_per_step": r["launches_per_step"],
+                       "model_tflops": r["value"] * wl["flop_per_image"] / 1e12},
+            "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": r["ms_e2e"], "loss": r["loss"],
+                    "api": "Train.run_step(step, batch, fetch=True): pinned H2D of images/clicks/labels, graph replay, "
+                           "D2H of losses + segment logits + predictions (+ class logits/predictions)"},
+            "gpu_launches": r["launches"],
+            "roofline": r.get("roofline"), "kernel_breakdown_ms_per_step": r.get("breakdown"),
+            "hbm_microbench_64M": micro, "cpu_baseline": cpu, "click_to_mask": click, "also": also or None,
+            "clocks": r["clocks"]}
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -371,17 +528,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-tc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
     ap.add_argument("--no-click", action="store_true", help="skip the click-to-mask latency leg (cfg 1)")
+    ap.add_argument("--no-micro", action="store_true", help="skip the 64 M-element HBM microbenchmarks")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra cfg2 measurement at N=1")
     ap.add_argument("--detail", default=None, help="write per-call CUDA-event timings of one eager step to this file")
     args = ap.parse_args()
+    out = claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out)
     else:
-        run_ours(args)
+        run_ours(args, out)
     try:
         import torch.distributed as dist
         if dist.is_initialized():

@@ -208,7 +208,10 @@ int basi_resize_nearest_fwd(const basi_tensor* x, const basi_tensor* y, void* st
 int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int accumulate, void* stream);
 
 /* ---- A11: class_attention_conv (5x5 s5 on a 5x5 map) and Network.fc (:175-189) as skinny GEMMs ----
- * y[m][n] = act(sum_k a[m][k] w[k][n] + bias[n]), m <= 64. a may be f32/bf16 (dtype_a), y float32. */
+ * y[m][n] = act(sum_k a[m][k] w[k][n] + bias[n]). a may be f32/bf16 (dtype_a), y float32.  Any M (= batch): rows
+ * are processed in chunks that fit the kernels' register / shared-memory budgets.  basi_skinny_supported is the
+ * single predicate the host lowering asks (1 = the three entry points below accept this shape). */
+int basi_skinny_supported(int M, int K, int N);
 int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,
                     int M, int K, int N, int relu, void* stream);
 /* da[m][k] (+)= sum_n dy[m][n] w[k][n]   (da dtype_a) */

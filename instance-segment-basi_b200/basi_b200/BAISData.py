@@ -32,7 +32,11 @@ class Data(object):
     def __init__(self, data_list="ImageSets/Segmentation/train.txt", data_path="JPEGImages/",
                  data_root_path="./VOC2012/", annotation_path="SegmentationObject/",
                  class_path="SegmentationClass/", batch_size=4, image_size=(720, 720), ratio=8, is_test=False,
-                 sigma=30):
+                 sigma=30, rank=0, world=1, seed=None):
+        # data parallelism: every rank reads the annotations rank::world of one common (per-epoch seeded) order, so
+        # the ranks see disjoint batches; rank=0, world=1 is the reference's single-process behaviour
+        self.rank, self.world = int(rank), max(1, int(world))
+        self._epoch, self._seed = 0, seed
         self.batch_size = batch_size
         self.image_size = image_size
         self.ratio = ratio
@@ -45,13 +49,23 @@ class Data(object):
         self._annotations = self._read_annotation(self._annotation_list, self._class_list, self.image_size,
                                                   self.ratio)
         self._images_data = self._read_image(self._data_list, self.image_size)
-        self.number_patch = len(self._annotations) // self.batch_size
-        self._random_index = list(range(0, len(self._annotations)))
+        self._order = list(range(0, len(self._annotations)))
+        self._random_index = self._order[self.rank::self.world]
+        self.number_patch = len(self._random_index) // self.batch_size
         self._now = 0
+
+    def _reshuffle(self):
+        self._epoch += 1
+        if self.world == 1 and self._seed is None:
+            np.random.shuffle(self._random_index)            # the reference's in-place shuffle (BAISData.py:52-54)
+            return
+        order = list(self._order)
+        np.random.RandomState((0 if self._seed is None else self._seed) + self._epoch).shuffle(order)
+        self._random_index = order[self.rank::self.world]    # same permutation on every rank, disjoint slices
 
     def _pick(self, train):
         if train and self._now >= self.number_patch:
-            np.random.shuffle(self._random_index)
+            self._reshuffle()
             self._now = 0
         idx = self._random_index[self._now * self.batch_size: (self._now + 1) * self.batch_size]
         return [self._annotations[i] for i in idx]

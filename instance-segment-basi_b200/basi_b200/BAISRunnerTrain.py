@@ -65,12 +65,15 @@ class Train(object):
         else:
             self.data_reader = Data(data_root_path=data_root_path, data_list=train_list, data_path=data_path,
                                     annotation_path=annotation_path, class_path=class_path,
-                                    batch_size=batch_size, image_size=input_size, is_test=is_test)
+                                    batch_size=batch_size, image_size=input_size, is_test=is_test,
+                                    rank=dp.rank if dp else 0, world=dp.world if dp else 1, seed=seed)
         self.loss_cfg = dict(kind=snap["kind"],
                              pos_weight=snap["pos_weight"] if pos_weight is None else pos_weight,
                              class_weight=snap["class_weight"] if class_weight is None else class_weight)
         self.net, self.engine = self.build_net(precision, device, use_tc)
         self.engine.init_params(seed)
+        if dp is not None:
+            self.engine.broadcast_params(dp)       # every replica starts from rank 0's weights
 
     def build_net(self, precision="bf16", device=None, use_tc=True):
         image_placeholder = Placeholder((None, self.input_size[0], self.input_size[1], 4))
@@ -126,12 +129,15 @@ class Train(object):
 
     def train(self, save_pred_freq, begin_step=0, max_steps=None):
         Tools.restore_if_y(self.engine, self.log_dir)
+        if self.dp is not None:
+            self.engine.broadcast_params(self.dp)
+        is_writer = self.dp is None or self.dp.rank == 0     # one checkpoint writer
         end = self.num_steps if max_steps is None else min(self.num_steps, begin_step + max_steps)
         r = None
         for step in range(begin_step, end):
             start_time = time.time()
             r = self.run_step(step)
-            if step % save_pred_freq == 0:
+            if step % save_pred_freq == 0 and is_writer:
                 Tools.save(self.engine, self.checkpoint_path, step)
                 Tools.print_info('The checkpoint has been created.')
             duration = time.time() - start_time

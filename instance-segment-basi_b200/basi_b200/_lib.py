@@ -81,6 +81,7 @@ SIGNATURES = {
     "basi_softmax_gate_bwd": [_P, _P, _i64, _i, _i, _f, _P, _i, _P],
     "basi_resize_nearest_fwd": [_TP, _TP, _P],
     "basi_resize_nearest_bwd": [_TP, _TP, _i, _P],
+    "basi_skinny_supported": [_i, _i, _i],
     "basi_skinny_fwd": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _i, _P],
     "basi_skinny_dgrad": [_P, _P, _P, _i, _i64, _i, _i, _i, _i, _P],
     "basi_skinny_wgrad": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _P],

@@ -96,6 +96,12 @@ class DataParallel(object):
             self._plan = self.plan_buckets(engine.param_index, engine.bwd, engine.n_flat,
                                            max(1, self.bucket_bytes // 4))
         calls = engine.bwd
+        if self.comm_stream is None:
+            # no side stream (gloo / CPU-side tests): backward, then one averaged all-reduce of the whole buffer
+            engine._run(calls, st)
+            engine.join_side()
+            self.all_reduce_mean(engine.grads_flat)
+            return
         cur = torch.cuda.current_stream(self.device)
         pos = 0
         for ready, start, end in self._plan:

@@ -38,6 +38,22 @@ def _same_pad_before(n_in, k, s, d):
     return total // 2
 
 
+def _exp_env(name):
+    """Experiment switches count only together with BASI_EXPERIMENTS=1 -- a stray variable in a
+    training job must not change results silently (same rule as basi::exp_env in the library)."""
+    v = os.environ.get(name)
+    if v is None:
+        return None
+    if os.environ.get("BASI_EXPERIMENTS") == "1":
+        return v
+    if name not in _WARNED:
+        _WARNED.add(name)
+        import sys
+        sys.stderr.write("basi_b200: %s is set but ignored (experiment switches need BASI_EXPERIMENTS=1)\n" % name)
+    return None
+
+
+_WARNED = set()
 _PSP_BRANCH = re.compile(r"^conv5_3_pool(\d)")     # pool1 / pool2 / pool3 / pool6 -> branch stream 0 / 1 / 2 / 3
 
 
@@ -85,6 +101,8 @@ class Engine(object):
         self.B = int(batch_size)
         self.precision = precision
         self.adt = torch.float32 if precision == "f32" else torch.bfloat16
+        # which tensors are stored in 16 bits (names of oracle.ROUNDING_POLICIES; tests hold the path to that model)
+        self.storage_policy = "none" if precision == "f32" else "round1"
         self.training = training
         self.loss_cfg = loss
         if device is None:
@@ -94,13 +112,13 @@ class Engine(object):
         self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
-        self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run and not os.environ.get("BASI_NO_OVERLAP")
+        self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run and not _exp_env("BASI_NO_OVERLAP")
         self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
         # independent sub-graphs (the four PSP branches) can run on their own streams, forked/joined with events.
         # Measured inside the step graph: 10.27 ms with the branch streams vs 10.08 ms without (the extra cross-stream
         # dependencies cost more than the ~0.3 ms of tiny kernels they overlap), so this is opt-in.
         self._bstreams = None
-        if not self.dry_run and os.environ.get("BASI_BRANCH_STREAMS"):
+        if not self.dry_run and _exp_env("BASI_BRANCH_STREAMS"):
             self._bstreams = [torch.cuda.Stream(self.device) for _ in range(4)]
         self._side_dirty = False
         self._tc_plans = []
@@ -110,9 +128,9 @@ class Engine(object):
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
-        self.mask_bits = not os.environ.get("BASI_NO_MASK_BITS")
-        self.fuse_pools = not os.environ.get("BASI_NO_POOL_FUSION")
-        self.coop_bn_bwd = not os.environ.get("BASI_NO_COOP_BN")
+        self.mask_bits = not _exp_env("BASI_NO_MASK_BITS")
+        self.fuse_pools = not _exp_env("BASI_NO_POOL_FUSION")
+        self.coop_bn_bwd = not _exp_env("BASI_NO_COOP_BN")
         self.fused_bn_bwd = 0
         self._tc_weights = []
         self._pack_table = None
@@ -136,9 +154,9 @@ class Engine(object):
         self.n_flat = off
         self.n_params = sum(int(np.prod(s)) for _, s in self.param_index.values())
         dev = self.device
-        self.params_flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grads_flat = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
-        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.params_flat = self._zeros(off, torch.float32)
+        self.grads_flat = self._zeros(off, torch.float32) if self.training else None
+        self.lr_dev = self._zeros(1, torch.float32)
 
     def _pptr(self, name):
         return self.params_flat.data_ptr() + 4 * self.param_index[name][0]
@@ -160,6 +178,11 @@ class Engine(object):
             if tuple(v.shape) != tuple(shape):
                 raise ValueError("variable %s: shape %s != %s" % (name, v.shape, shape))
             self.param_view(name).copy_(torch.from_numpy(v))
+        self._refresh_weight_copies()
+
+    def broadcast_params(self, dp, src=0):
+        """Data parallelism: rank `src`'s parameters to every replica, then refresh the bf16 tensor-core copies."""
+        dp.broadcast(self.params_flat, src)
         self._refresh_weight_copies()
 
     def get_params(self):
@@ -190,15 +213,28 @@ class Engine(object):
         self.set_params(p)
 
     # ------------------------------------------------------------------ allocation helpers
+    def _zeros(self, shape, dtype):
+        """Zero-initialised device buffer: torch.empty + basi_memset (a stream memset, not a fill kernel -- the plan
+        has ~700 buffers and a fill kernel per buffer would bury our kernels in a profiler's launch list)."""
+        if isinstance(shape, int):
+            shape = (shape,)
+        if self.dry_run or self.device.type != "cuda":
+            return torch.zeros(*shape, dtype=dtype, device=self.device)
+        t = torch.empty(*shape, dtype=dtype, device=self.device)
+        if t.numel():
+            _lib.call("basi_memset", t.data_ptr(), 0, C.c_int64(t.numel() * t.element_size()),
+                      torch.cuda.current_stream(self.device).cuda_stream)
+        return t
+
     def _alloc(self, shape, dtype=None):
-        return torch.zeros(*shape, dtype=dtype or self.adt, device=self.device)
+        return self._zeros(tuple(shape), dtype or self.adt)
 
     def _new_act(self, h, w, c, dtype=None):
         return Act(self._alloc((self.B, h, w, c), dtype))
 
     def _grad_of(self, act):
         if act.grad is None:
-            act.grad = Act(torch.zeros_like(act.t))
+            act.grad = Act(self._zeros(tuple(act.t.shape), act.t.dtype))
         return act.grad
 
     def _call(self, lst, name, *args, **meta):
@@ -221,8 +257,8 @@ class Engine(object):
         # BN statistic scratch: [fwd sums | bwd sums] as doubles, zeroed once per step
         tot_c = sum(n.shape[-1] for n in nodes if n.op == "batch_normalization")
         n_bn = sum(1 for n in nodes if n.op == "batch_normalization")
-        self.bn_scratch = torch.zeros(4 * tot_c * BN_REPLICAS + 8, dtype=torch.float64, device=self.device)
-        self.bn_counters = torch.zeros(2 * n_bn + 2, dtype=torch.int32, device=self.device)   # last-block tickets
+        self.bn_scratch = self._zeros(4 * tot_c * BN_REPLICAS + 8, torch.float64)
+        self.bn_counters = self._zeros(2 * n_bn + 2, torch.int32)   # last-block tickets
         self._bn_off = 0
         self._bn_idx = 0
         # concat: producers write into slices
@@ -306,7 +342,8 @@ class Engine(object):
         wname, bname = a["weights"], a["biases"]
         # class_attention_conv pattern: 5x5/s5 over a dense 5x5 map -> skinny GEMM
         if (k == 5 and s == 5 and x.shape[1] == 5 and x.shape[2] == 5 and pt == 0 and oh == 1 and ow == 1
-                and x.desc.ld == x.shape[3] and self.B <= 64):
+                and x.desc.ld == x.shape[3]
+                and _lib.load().basi_skinny_supported(self.B, 25 * x.shape[3], co) == 1):
             y = Act(self._alloc((self.B, 1, 1, co), torch.float32))
             self._acts[n.index] = y
             self._ops.append(("skinny", dict(x=x, y=y, w=wname, b=bname, relu=bool(a["relu"]),
@@ -393,7 +430,7 @@ class Engine(object):
     def _lower_max_pool(self, n):
         x = self._acts[n.inputs[0].index]
         y = self._out_act(n)
-        amax = torch.zeros(self.B * n.shape[0] * n.shape[1] * n.shape[2], dtype=torch.uint8, device=self.device)
+        amax = self._zeros(self.B * n.shape[0] * n.shape[1] * n.shape[2], torch.uint8)
         op = dict(x=x, y=y, amax=amax)
         self._acts[n.index] = y
         self._ops.append(("maxpool", op))
@@ -430,7 +467,7 @@ class Engine(object):
     def _emit_pool_group_fwd(self, grp):
         x = grp["x"]
         cells = sum(o["y"].shape[1] * o["y"].shape[2] for o in grp["ops"])
-        grp["scratch"] = torch.zeros(self.B * cells * x.shape[3], dtype=torch.float32, device=self.device)
+        grp["scratch"] = self._zeros(self.B * cells * x.shape[3], torch.float32)
         n, ks, ptrs = self._pool_group_args(grp, False)
         br, self._cur_branch = self._cur_branch, None          # the shared pass runs before the branches fork
         self._call(self.fwd, "basi_avgpool_multi_fwd", x.ref, n, ks, ptrs, grp["scratch"].data_ptr(),
@@ -466,6 +503,9 @@ class Engine(object):
         x = self._acts[n.inputs[0].index]
         assert x.t.dtype == torch.float32 and x.shape[1] == 1 and x.shape[2] == 1
         co = n.shape[0]
+        if _lib.load().basi_skinny_supported(self.B, x.shape[3], co) != 1:
+            raise _lib.BasiError("fc %s: shape (B=%d, K=%d, N=%d) not supported by the skinny GEMM"
+                                 % (n.name, self.B, x.shape[3], co))      # fails at plan time, never mid-step
         y = Act(self._alloc((self.B, 1, 1, co), torch.float32))
         self._acts[n.index] = y
         op = dict(x=x, y=y, w=n.attrs["weights"], b=n.attrs["biases"], relu=bool(n.attrs["relu"]),
@@ -527,7 +567,7 @@ class Engine(object):
                 and _lib.load().basi_bn_maskbits_supported(main.x.ref) == 1):
             # residual junction: also emit the packed ReLU mask, the backward pair reads it instead of `out`
             n_, h_, w_, c_ = main.x.shape
-            op["bits"] = torch.zeros(n_ * h_ * w_ * (c_ // 8), dtype=torch.uint8, device=self.device)
+            op["bits"] = self._zeros(n_ * h_ * w_ * (c_ // 8), torch.uint8)
             self._call(self.fwd, "basi_bn_apply_bits", main.x.ref, main.bnp.data_ptr(), res.ref,
                        res_bn.bnp.data_ptr() if res_bn is not None else None, 1, op["out"].ref,
                        op["bits"].data_ptr(), bytes=self._nbytes(main.x) * (3 + 1.0 / 16))
@@ -563,9 +603,9 @@ class Engine(object):
         self.cls_logits = self._acts[self.net.layers[clsname].index] if clsname else None
         B, P_h, P_w, nseg = self.seg_logits.shape
         dev = self.device
-        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
-        self.pred_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.int32, device=dev)
-        self.pred_cls = torch.zeros((B,), dtype=torch.int32, device=dev) if self.cls_logits is not None else None
+        self.loss_acc = self._zeros(4, torch.float64)
+        self.pred_seg = self._zeros((B, P_h, P_w, 1), torch.int32)
+        self.pred_cls = self._zeros((B,), torch.int32) if self.cls_logits is not None else None
         self.post = []
         lp = self.seg_logits.t.data_ptr()
         if nseg == 1:
@@ -586,17 +626,17 @@ class Engine(object):
         self.seg_logits.gw = True
         if kind == "bce":
             assert nseg == 1
-            self.label_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.float32, device=dev)
+            self.label_seg = self._zeros((B, P_h, P_w, 1), torch.float32)
             self._call(self.lossl, "basi_wbce_fwd_bwd", lp, self.label_seg.data_ptr(),
                        C.c_float(cfg.get("pos_weight", 3.0)), C.c_double(1.0 / N), C.c_float(1.0 / N),
                        C.c_int64(N), self.loss_acc.data_ptr(), g.t.data_ptr())
         else:
-            self.label_seg = torch.zeros((B, P_h, P_w, 1), dtype=torch.int32, device=dev)
+            self.label_seg = self._zeros((B, P_h, P_w, 1), torch.int32)
             self._call(self.lossl, "basi_softmax_ce_fwd_bwd", lp, self.label_seg.data_ptr(), C.c_int64(N), nseg,
                        C.c_double(1.0 / N), C.c_float(1.0 / N), self.loss_acc.data_ptr(), g.t.data_ptr())
         self.class_weight = float(cfg.get("class_weight", 0.2))
         if self.cls_logits is not None:
-            self.label_cls = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self.label_cls = self._zeros((B,), torch.int32)
             gc = self._grad_of(self.cls_logits)
             self.cls_logits.gw = True
             ncls = self.cls_logits.shape[3]
@@ -693,7 +733,8 @@ class Engine(object):
                            bits_t.data_ptr() if bits_t is not None else None, x.ref, rec.bnp.data_ptr(), from_x,
                            rec.dsums, C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta),
                            rec.coef.data_ptr(), rec.cnt_b, dx.ref, dres, dacc,
-                           bytes=nb * (2 * nr + 1 + (0 if dres is None else (2 if dacc else 1))),
+                           # algorithmic bytes: every input once (the second pass re-reads are not algorithmic)
+                           bytes=nb * (nr + 1 + (0 if dres is None else (2 if dacc else 1))),
                            writes=[rec.gamma, rec.beta])
                 continue
             if op.get("bits") is not None:
@@ -782,8 +823,8 @@ class Engine(object):
         off, shape = self.param_index[op["w"]]
         taps, cin, cout = shape[0] * shape[1], shape[2], shape[3]
         if "w_io" not in op:
-            op["w_io"] = torch.zeros(taps * cin * cout, dtype=torch.bfloat16, device=self.device)
-            op["w_oi"] = torch.zeros(taps * cin * cout, dtype=torch.bfloat16, device=self.device)
+            op["w_io"] = self._zeros(taps * cin * cout, torch.bfloat16)
+            op["w_oi"] = self._zeros(taps * cin * cout, torch.bfloat16)
             self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout))
         x, y = op["x"], op["y"]
         handle = C.c_void_p()
@@ -803,7 +844,7 @@ class Engine(object):
         if kind == _lib.TC_WGRAD:
             meta["writes"] = [op["w"]]
             meta["side"] = True
-        skip = os.environ.get("BASI_DEBUG_SKIP_WGRAD")     # timing experiment only (gradients become wrong)
+        skip = _exp_env("BASI_DEBUG_SKIP_WGRAD")     # timing experiment only (gradients become wrong)
         if kind == _lib.TC_WGRAD and skip and op["name"].startswith(tuple(skip.split(","))):
             return handle
         lst.append(("basi_tc_conv_run:%d" % kind, lib.basi_tc_conv_run, (handle,), meta))
@@ -904,8 +945,8 @@ class Engine(object):
         B, H, W, _ = self.input.shape
         lut = click_lut((H, W), sigma)
         self.lut_dev = torch.from_numpy(lut).to(self.device)
-        self.img_u8 = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device)
-        self.clicks_dev = torch.zeros((B, 2), dtype=torch.int32, device=self.device)
+        self.img_u8 = self._zeros((B, H, W, 3), torch.uint8)
+        self.clicks_dev = self._zeros((B, 2), torch.int32)
         self.pre = []
         self._call(self.pre, "basi_clickmap_pack", self.img_u8.data_ptr(), 0, self.clicks_dev.data_ptr(),
                    self.lut_dev.data_ptr(), C.c_int64(lut.size), self.input.t.data_ptr(), B, H, W)
@@ -986,6 +1027,23 @@ class Engine(object):
             self.label_cls.copy_(_as_tensor(label_cls, torch.int32).view(self.label_cls.shape), non_blocking=True)
         if lr is not None:
             self.lr_dev.fill_(float(lr))
+
+    def fetch(self, name, grad=False):
+        """Value (or, grad=True, the loss gradient) of a named layer as a float32 NHWC numpy array -- the analogue of
+        fetching a symbolic tensor through ``sess.run``.  BN layers fused into a following ReLU / junction return the
+        fused output (the tensor the next layer reads)."""
+        a = self._acts[self.net.layers[name].index]
+        if isinstance(a, tuple):
+            if a[0] in ("fused_into_relu", "pre_relu_of"):
+                a = a[1]
+            else:
+                raise KeyError("layer %s is not materialised (%s)" % (name, a[0]))
+        if grad:
+            if a.grad is None:
+                raise KeyError("layer %s has no gradient buffer" % name)
+            a = a.grad
+        torch.cuda.synchronize(self.device)
+        return a.t.float().cpu().numpy()
 
     def losses(self):
         acc = self.loss_acc.cpu().numpy()

@@ -680,7 +680,7 @@ static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem,
   // 8 KB stages x 4-6 deep = 10.8 ms, 16 KB stages x 2-3 deep = 10.25 ms, 32 KB stages (ring too shallow) = 12.0 ms.
   static int sr_env = -1;
   if (sr_env < 0) {
-    const char* e = getenv("BASI_BN_STAGE_ROWS");
+    const char* e = exp_env("BASI_BN_STAGE_ROWS");
     sr_env = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 0;
   }
   int sr_mult = sr_env ? sr_env : (12 / nt < 4 ? 12 / nt : 4);
@@ -692,12 +692,12 @@ static StreamGeom stream_geom(int64_t R, int C, int es, int nt, size_t min_smem,
     // a small single-tensor pass (forward BN+ReLU of the conv2..conv5 bottleneck layers: ~22 KB per CTA) gains
     // nothing from the ring; the register-staged kernel measured 0.07 ms/step faster there
     static int min1 = -1;
-    if (min1 < 0) min1 = getenv("BASI_BN_STREAM_MIN1") ? atoi(getenv("BASI_BN_STREAM_MIN1")) : 1000;
+    if (min1 < 0) min1 = exp_env("BASI_BN_STREAM_MIN1") ? atoi(exp_env("BASI_BN_STREAM_MIN1")) : 1000;
     if (nt == 1 && n_slabs < min1) return g;
   }
   static int ring_kb = 0;
   if (!ring_kb) {
-    const char* e = getenv("BASI_BN_RING_KB");
+    const char* e = exp_env("BASI_BN_RING_KB");
     ring_kb = (e && atoi(e) >= 32 && atoi(e) <= 220) ? atoi(e) : 96;
   }
   int nst = (int)(((size_t)ring_kb * 1024) / ((size_t)nt * SR * row_bytes));
@@ -730,7 +730,7 @@ static void allow_smem(K kernel, size_t bytes) {
 }
 static bool stream_disabled() {
   static int v = -1;
-  if (v < 0) v = getenv("BASI_BN_DIRECT") ? 1 : 0;
+  if (v < 0) v = exp_env("BASI_BN_DIRECT") ? 1 : 0;
   return v == 1;
 }
 
@@ -1134,7 +1134,7 @@ bn_bwd_coop_kernel(const StreamArgs a1, const StreamArgs a2, const float* __rest
 
 static bool coop_disabled() {
   static int v = -1;
-  if (v < 0) v = getenv("BASI_BN_NO_COOP") ? 1 : 0;
+  if (v < 0) v = exp_env("BASI_BN_NO_COOP") ? 1 : 0;
   return v == 1;
 }
 
@@ -1221,7 +1221,7 @@ struct ResidentGeom {
 };
 static bool resident_disabled() {
   static int v = -1;
-  if (v < 0) v = getenv("BASI_BN_NO_RESIDENT") ? 1 : 0;
+  if (v < 0) v = exp_env("BASI_BN_NO_RESIDENT") ? 1 : 0;
   return v == 1;
 }
 static ResidentGeom resident_geom(int64_t R, int C, int es) {
@@ -1236,7 +1236,7 @@ static ResidentGeom resident_geom(int64_t R, int C, int es) {
   // block reduction + atomics 2.2, grid barrier 1.6, coefficients 1.5 / 1.1, dx 1.6.  512 / 1024 threads make the
   // block reduction longer (2.2 -> 6.3 us) without speeding the row pass up, so 256 it is.
   static int thr_env = -1;
-  if (thr_env < 0) thr_env = getenv("BASI_BN_RESIDENT_THREADS") ? atoi(getenv("BASI_BN_RESIDENT_THREADS")) : 0;
+  if (thr_env < 0) thr_env = exp_env("BASI_BN_RESIDENT_THREADS") ? atoi(exp_env("BASI_BN_RESIDENT_THREADS")) : 0;
   int threads = (thr_env == 256 || thr_env == 512 || thr_env == 1024) ? thr_env : 256;
   while (threads > 256 && threads / bx > rpc) threads /= 2;
   if (threads < bx) threads = bx;
@@ -1274,7 +1274,7 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   a.R = pixels(x);
   a.row_bytes = x->c * (int)sizeof(T);
   a.rows_per_cta = g.rows_per_cta; a.chunk_rows = g.chunk_rows; a.n_chunks = g.n_chunks;
-  a.debug = getenv("BASI_BN_RESIDENT_DEBUG") ? 1 : 0;
+  a.debug = exp_env("BASI_BN_RESIDENT_DEBUG") ? 1 : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g.grid);
   cfg.blockDim = dim3(g.bx, g.by);
@@ -1284,7 +1284,7 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("BASI_BN_RESIDENT_NOCOOP") ? 0 : 1;   // experiment only: without the attribute co-residency is not guaranteed
+  cfg.numAttrs = exp_env("BASI_BN_RESIDENT_NOCOOP") ? 0 : 1;   // experiment only: without the attribute co-residency is not guaranteed
 #define BASI_LAUNCH_RESIDENT(NT_)                                                                                  \
   do {                                                                                                             \
     allow_smem(bn_bwd_resident_kernel<T, NT_>, g.smem);                                                            \

@@ -10,6 +10,10 @@
 namespace basi {
 
 void set_error(const char* fmt, ...);
+// Experiment switches are honoured only when BASI_EXPERIMENTS=1 is also set: a stray BASI_*
+// variable in a training job must not silently change kernel configuration or results.  Returns the value of `name`
+// or nullptr; a set-but-ignored variable is reported once on stderr.
+const char* exp_env(const char* name);
 
 #define BASI_CHECK_ARG(cond, ...)      \
   do {                                 \

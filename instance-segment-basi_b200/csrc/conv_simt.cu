@@ -910,7 +910,7 @@ static int check_conv(const basi_conv_desc* d, const basi_tensor* x, const basi_
 static bool stem_shape(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
   return x->dtype == BASI_F32 && x->c == 4 && x->ld == 4 && aligned16(x->ptr) && d->kh == 3 && d->kw == 3 &&
          d->dil == 1 && d->stride <= 2 && (y->c == 32 || y->c == 64) && y->ld % 4 == 0 && aligned16(y->ptr) &&
-         getenv("BASI_NO_STEM") == nullptr;
+         exp_env("BASI_NO_STEM") == nullptr;
 }
 static StemConv stem_args(const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
   StemConv s{};
@@ -939,7 +939,7 @@ static bool head_shape(const basi_conv_desc* d, const basi_tensor* x, const basi
   const int vn = x->dtype == BASI_F32 ? 4 : 8;
   return d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && y->c >= 1 && y->c <= 4 &&
          y->dtype == BASI_F32 && x->h == y->h && x->w == y->w && basi::vec_ok(x) && x->c / vn <= 256 &&
-         getenv("BASI_NO_HEAD") == nullptr;
+         exp_env("BASI_NO_HEAD") == nullptr;
 }
 #define BASI_HEAD_CO(co, ...)                    \
   switch (co) {                                  \
@@ -1137,9 +1137,21 @@ int basi_conv_wgrad(const basi_conv_desc* d, const basi_tensor* x, const basi_te
   return BASI_OK;
 }
 
+// Rows (M = batch) are independent in fwd / dgrad and additive in wgrad, so any M is served in chunks of rows that fit
+// the kernels' register / shared-memory budgets (<= 64 rows; dgrad: M_chunk * N * 4 bytes <= 96 KB).
+static int skinny_rows_per_chunk(int N) {
+  int mc = (int)((96 * 1024) / ((size_t)N * 4));
+  if (mc > 64) mc = 64;
+  return mc;
+}
+
+int basi_skinny_supported(int M, int K, int N) {
+  return (M > 0 && K > 0 && N > 0 && skinny_rows_per_chunk(N) >= 1) ? 1 : 0;
+}
+
 int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y, int M, int K,
                     int N, int relu, void* stream) {
-  BASI_CHECK_ARG(a && w && y && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_fwd: bad argument (M must be <= 64)");
+  BASI_CHECK_ARG(a && w && y && basi_skinny_supported(M, K, N), "skinny_fwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
   const int nslabs = (K + SK_KT - 1) / SK_KT, gx = (N + 127) / 128;
@@ -1148,8 +1160,14 @@ int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, con
   if (gy > nslabs) gy = nslabs;
   const int spb = (nslabs + gy - 1) / gy;
   dim3 grid(gx, (nslabs + spb - 1) / spb);
-  if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)a, lda, w, y, M, K, N, spb);
-  else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)a, lda, w, y, M, K, N, spb);
+  const size_t es = dtype_a == BASI_F32 ? 4 : 2;
+  for (int m0 = 0; m0 < M; m0 += 64) {
+    const int mc = M - m0 < 64 ? M - m0 : 64;
+    const char* ap = (const char*)a + (size_t)m0 * lda * es;
+    float* yp = y + (size_t)m0 * N;
+    if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb);
+    else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)ap, lda, w, yp, mc, K, N, spb);
+  }
   BASI_CHECK_LAUNCH("skinny_fwd");
   basi::launch(bias_act_kernel, (M * N + 255) / 256, 256, 0, st, y, bias, M, N, relu);
   BASI_CHECK_LAUNCH("skinny_fwd(bias)");
@@ -1158,21 +1176,27 @@ int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, con
 
 int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, int64_t lda, int M, int K, int N,
                       int accumulate, void* stream) {
-  BASI_CHECK_ARG(dy && w && da && M > 0 && M <= 64 && K > 0 && N > 0 && (size_t)M * N * 4 <= 96 * 1024,
-                 "skinny_dgrad: bad argument");
+  BASI_CHECK_ARG(dy && w && da && basi_skinny_supported(M, K, N), "skinny_dgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  size_t smem = sizeof(float) * (size_t)M * N;
+  const int rows = skinny_rows_per_chunk(N);
   int blocks = (K + 15) / 16;
   int cap = basi::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  if (dtype_a == BASI_F32) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(skinny_dgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    basi::launch(skinny_dgrad_kernel<float>, blocks, 256, smem, st, dy, w, (float*)da, lda, M, K, N, accumulate);
-  } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(skinny_dgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    basi::launch(skinny_dgrad_kernel<bf16>, blocks, 256, smem, st, dy, w, (bf16*)da, lda, M, K, N, accumulate);
+  const size_t es = dtype_a == BASI_F32 ? 4 : 2;
+  for (int m0 = 0; m0 < M; m0 += rows) {
+    const int mc = M - m0 < rows ? M - m0 : rows;
+    const size_t smem = sizeof(float) * (size_t)mc * N;
+    const float* dyp = dy + (size_t)m0 * N;
+    char* dap = (char*)da + (size_t)m0 * lda * es;
+    if (dtype_a == BASI_F32) {
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(skinny_dgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      basi::launch(skinny_dgrad_kernel<float>, blocks, 256, smem, st, dyp, w, (float*)dap, lda, mc, K, N, accumulate);
+    } else {
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(skinny_dgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      basi::launch(skinny_dgrad_kernel<bf16>, blocks, 256, smem, st, dyp, w, (bf16*)dap, lda, mc, K, N, accumulate);
+    }
   }
   BASI_CHECK_LAUNCH("skinny_dgrad");
   return BASI_OK;
@@ -1180,15 +1204,21 @@ int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, in
 
 int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, float* dw, float* dbias, int M, int K,
                       int N, void* stream) {
-  BASI_CHECK_ARG(a && dy && dw && M > 0 && M <= 64 && K > 0 && N > 0, "skinny_wgrad: bad argument");
+  BASI_CHECK_ARG(a && dy && dw && basi_skinny_supported(M, K, N), "skinny_wgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + 127) / 128, (K + SK_KT - 1) / SK_KT);
-  if (M <= 16) {
-    if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 16>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
-    else basi::launch(skinny_wgrad_kernel<bf16, 16>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
-  } else {
-    if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 64>, grid, 128, 0, st, (const float*)a, lda, dy, dw, dbias, M, K, N);
-    else basi::launch(skinny_wgrad_kernel<bf16, 64>, grid, 128, 0, st, (const bf16*)a, lda, dy, dw, dbias, M, K, N);
+  const size_t es = dtype_a == BASI_F32 ? 4 : 2;
+  for (int m0 = 0; m0 < M; m0 += 64) {       // dw += ... : the row chunks simply add up (stream order)
+    const int mc = M - m0 < 64 ? M - m0 : 64;
+    const char* ap = (const char*)a + (size_t)m0 * lda * es;
+    const float* dyp = dy + (size_t)m0 * N;
+    if (mc <= 16) {
+      if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 16>, grid, 128, 0, st, (const float*)ap, lda, dyp, dw, dbias, mc, K, N);
+      else basi::launch(skinny_wgrad_kernel<bf16, 16>, grid, 128, 0, st, (const bf16*)ap, lda, dyp, dw, dbias, mc, K, N);
+    } else {
+      if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 64>, grid, 128, 0, st, (const float*)ap, lda, dyp, dw, dbias, mc, K, N);
+      else basi::launch(skinny_wgrad_kernel<bf16, 64>, grid, 128, 0, st, (const bf16*)ap, lda, dyp, dw, dbias, mc, K, N);
+    }
   }
   BASI_CHECK_LAUNCH("skinny_wgrad");
   return BASI_OK;

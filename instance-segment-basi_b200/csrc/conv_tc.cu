@@ -1111,11 +1111,11 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // (narrower channel tiles for the tiny pyramid-branch maps, to spread the weight traffic over more SMs, measured
     // no change: those launches are 6 us of launch + 6 us of pipeline latency; BASI_TC_SMALL_M=<tiles> re-enables it)
     {
-      const int few = getenv("BASI_TC_SMALL_M") ? atoi(getenv("BASI_TC_SMALL_M")) : 0;
+      const int few = exp_env("BASI_TC_SMALL_M") ? atoi(exp_env("BASI_TC_SMALL_M")) : 0;
       while (bn > 32 && ndim % (bn / 2) == 0 && (long)m_tiles * (ndim / bn) < few) bn /= 2;
     }
-    const int bn256_mink = getenv("BASI_TC_BN256_MINK") ? atoi(getenv("BASI_TC_BN256_MINK")) : 8;
-    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !getenv("BASI_TC_NO_BN256")) {
+    const int bn256_mink = exp_env("BASI_TC_BN256_MINK") ? atoi(exp_env("BASI_TC_BN256_MINK")) : 8;
+    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !exp_env("BASI_TC_NO_BN256")) {
       const long t128 = ((long)m_tiles * (ndim / 128) + sms - 1) / sms * 10;
       const long t256 = ((long)m_tiles * (ndim / 256) + sms - 1) / sms * 14;
       if (t256 < t128) bn = 256;
@@ -1127,7 +1127,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // and the lock-step of the two epilogues, so pairs are used for long main loops on 256-wide tiles only.
     {
       const int ksteps = d->kh * d->kw * ((kdim + 63) / 64);
-      const char* env_cl = getenv("BASI_TC_CLUSTER");
+      const char* env_cl = exp_env("BASI_TC_CLUSTER");
       pl->cluster = (m_tiles >= 2 && bn == 256 && ksteps >= 32) ? 2 : 1;
       if (env_cl) pl->cluster = (atoi(env_cl) >= 1 && m_tiles >= 2) ? 2 : 1;   // 1: force pairs, 0: never
     }
@@ -1137,8 +1137,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     {
       const int ksteps = d->kh * d->kw * ((kdim + 63) / 64);
       const long items2 = (long)((m_tiles + 1) / 2) * (ndim / bn);
-      const char* env_mt = getenv("BASI_TC_MT");
-      int min_k = getenv("BASI_TC_MT_MINK") ? atoi(getenv("BASI_TC_MT_MINK")) : 4;
+      const char* env_mt = exp_env("BASI_TC_MT");
+      int min_k = exp_env("BASI_TC_MT_MINK") ? atoi(exp_env("BASI_TC_MT_MINK")) : 4;
       if (bn <= 128 && pl->cluster == 1 && m_tiles >= 2 && items2 * 3 >= (long)sms * 2 && ksteps >= min_k) pl->mt = 2;
       if (env_mt && atoi(env_mt) == 1) pl->mt = 1;
       if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2) pl->mt = 2;   // tests
@@ -1147,7 +1147,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // 16 x (16 + 2 dil) pixels per 64-channel chunk serves all nine taps
     bool halo = false;
     {
-      const char* env_h = getenv("BASI_TC_HALO");
+      const char* env_h = exp_env("BASI_TC_HALO");
       const bool can = d->kh == 3 && d->kw == 3 && d->dil >= 1 && d->dil <= 4 && d->pad_t == d->dil &&
                        d->pad_l == d->dil && pl->cluster == 1 && bn <= 128;
       halo = can && env_h && atoi(env_h) == 1;
@@ -1187,8 +1187,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 1024 * (int)sizeof(float) + 1024 /*align*/ + out_stage;
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
-    if (getenv("BASI_TC_STAGES") && atoi(getenv("BASI_TC_STAGES")) >= 2 && atoi(getenv("BASI_TC_STAGES")) < stages)
-      stages = atoi(getenv("BASI_TC_STAGES"));   // experiment: bytes in flight vs main-loop time
+    if (exp_env("BASI_TC_STAGES") && atoi(exp_env("BASI_TC_STAGES")) >= 2 && atoi(exp_env("BASI_TC_STAGES")) < stages)
+      stages = atoi(exp_env("BASI_TC_STAGES"));   // experiment: bytes in flight vs main-loop time
     cp.stages = stages;
     cp.ring_bytes = stages * stage_bytes;
     pl->smem = (size_t)stages * stage_bytes + fixed;
@@ -1197,7 +1197,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       cp.halo_bytes = 16 * (16 + 2 * d->dil) * 128;
       cp.nh = 2;
       const int b_bytes = bn * 128;
-      if (cp.k_chunks == 1 && cp.n_tiles == 1 && !getenv("BASI_TC_HALO_NO_BRES")) {
+      if (cp.k_chunks == 1 && cp.n_tiles == 1 && !exp_env("BASI_TC_HALO_NO_BRES")) {
         // resident weights: the nine boxes once per CTA, the rest of the shared memory for activation halos
         int nh = (227 * 1024 - fixed - cp.taps * b_bytes) / cp.halo_bytes;
         if (nh > 4) nh = 4;
@@ -1234,8 +1234,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       const int total = cp.m_tiles * cp.n_tiles;
       pl->grid = total < sms ? total : sms;
     }
-    if (getenv("BASI_TC_DEBUG_EMPTY")) cp.m_tiles = 0;   // timing experiment: prologue + teardown only
-    cp.debug = getenv("BASI_TC_DEBUG_STATS") ? atoi(getenv("BASI_TC_DEBUG_STATS")) : 0;
+    if (exp_env("BASI_TC_DEBUG_EMPTY")) cp.m_tiles = 0;   // timing experiment: prologue + teardown only
+    cp.debug = exp_env("BASI_TC_DEBUG_STATS") ? atoi(exp_env("BASI_TC_DEBUG_STATS")) : 0;
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
     const int cin = a->c, cout = b->c;
@@ -1257,7 +1257,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
     // split-K over pixel tiles.  Every split adds |dW| fp32 atomics, so tiny gradients (conv4 1x1: 65 K elements)
     // want a single wave of CTAs (measured 22.6 -> 16.7 us); long pixel loops want two waves for balance.
-    const char* env_w = getenv("BASI_TC_WGRAD_WAVES");
+    const char* env_w = exp_env("BASI_TC_WGRAD_WAVES");
     int waves = 1;
     {
       const int s1 = (sms + out_tiles - 1) / out_tiles;
@@ -1265,12 +1265,12 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     }
     if (env_w) waves = atoi(env_w);
     int splits = (waves * sms + out_tiles - 1) / out_tiles;
-    if (getenv("BASI_TC_WGRAD_SPLITS")) splits = atoi(getenv("BASI_TC_WGRAD_SPLITS"));   // experiment
+    if (exp_env("BASI_TC_WGRAD_SPLITS")) splits = atoi(exp_env("BASI_TC_WGRAD_SPLITS"));   // experiment
     if (splits > m_tiles) splits = m_tiles;
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (m_tiles + splits - 1) / splits;
     wp.splits = (m_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
-    pl->gbox = (cout <= 64 && !getenv("BASI_TC_WGRAD_GBOX2")) ? 1 : 2;
+    pl->gbox = (cout <= 64 && !exp_env("BASI_TC_WGRAD_GBOX2")) ? 1 : 2;
     const int stage_bytes = pl->gbox * A_BYTES + (bn / 64) * A_BYTES;
     int stages = (int)((227 * 1024 - 2048) / stage_bytes);
     if (stages > 6) stages = 6;

@@ -18,6 +18,19 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+const char* exp_env(const char* name) {
+  const char* v = getenv(name);
+  if (!v) return nullptr;
+  const char* on = getenv("BASI_EXPERIMENTS");
+  if (on && atoi(on) == 1) return v;
+  static thread_local char warned[1024] = "";
+  if (!strstr(warned, name) && strlen(warned) + strlen(name) + 2 < sizeof(warned)) {
+    strcat(warned, name);
+    strcat(warned, ",");
+    fprintf(stderr, "basi_b200: %s is set but ignored (experiment switches need BASI_EXPERIMENTS=1)\n", name);
+  }
+  return nullptr;
+}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -26,7 +39,7 @@ bool pdl_enabled() {
     // kernel's tail wherever the SM still has room.  While every kernel used the whole shared memory this measured
     // nothing (12.31 vs 12.29 ms); with the register-staged BN kernels and the other small-footprint kernels between
     // the tcgen05 launches it is worth 0.37 ms of a 9.2 ms step.
-    const char* e = getenv("BASI_PDL");
+    const char* e = exp_env("BASI_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;

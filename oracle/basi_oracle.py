@@ -33,6 +33,8 @@ What each function restates (paths relative to /root/reference):
                              5COCO/BAISPSPNet.py:716-737
 * ``losses`` / ``train_step``back/{1NoClass,2AddClass,4BorderClass,5COCO}/BAISRunnerTrain.py
                              build_net (loss, poly LR, plain SGD)
+* ``pspnet_forward_rounded`` the same forward with 16-bit storage roundings injected (no reference counterpart:
+                             the noise model the bf16 CUDA path is measured against)
 * ``predict_*``              back/2AddClass/BAISRunnerTrain.py:88-89,
                              back/4BorderClass/BAISRunnerOne.py:40-45,
                              back/4BorderClass/BAISRunnerGUI.py:29-34,84
@@ -364,6 +366,90 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
         out[k_] = v.permute(0, 2, 3, 1) if v.dim() == 4 else v
     out["__nchw__"] = {k_: L[k_] for k_ in keep}     # graph tensors (for activation gradients)
     return out
+
+
+# --------------------------------------------------------------------------
+# Storage-rounding model of a 16-bit tensor-core path (test infrastructure for the bf16 parity bars)
+# --------------------------------------------------------------------------
+
+ROUNDING_POLICIES = {
+    # what the CUDA bf16 path rounds to bf16 (everything else is float32): see pspnet_forward_rounded
+    "round1": frozenset({"w", "conv", "act", "junc", "inc"}),           # round 1: every stored tensor
+    "fused": frozenset({"w", "act", "junc", "inc"}),                    # BN applied from the fp32 accumulators
+    "fused_fp32_trunk": frozenset({"w", "act", "junc_op", "inc"}),      # ... and the shortcut kept in float32
+    "operands_only": frozenset({"w", "act", "junc_op"}),                # the floor of any bf16-operand MMA path
+    "weights_only": frozenset({"w"}),
+    "none": frozenset(),
+}
+
+
+def pspnet_forward_rounded(params, data_nhwc, last_pool_size, policy, seg_name="conv6_n",
+                           r16_dtype=torch.bfloat16):
+    """The forward pass of ``pspnet_forward`` (segment path) in the dtype of ``params`` with 16-bit roundings
+    injected where a 16-bit tensor-core implementation stores or feeds 16-bit values.  It answers "how far from the
+    float64 result does ANY implementation with this storage policy land" -- the bar the CUDA bf16 path is held to
+    (tests/test_gpu_net.py), and the evidence for which roundings are irreducible (profiles/parity_r02.md).
+
+    policy flags:  'w' bf16 weights of the tensor-core convolutions;  'conv' conv outputs rounded before BN;
+    'act' BN-apply / pool / bilinear outputs rounded;  'junc' junction outputs (residual trunk) rounded;
+    'junc_op' only the convolution-operand copy of the trunk rounded, the shortcut stays float32;
+    'inc' the increase / projection conv outputs feeding a junction rounded.
+    Returns {layer name: NCHW tensor} for the stage outputs and 'logits'."""
+    def r16(t):
+        return t.to(r16_dtype).to(t.dtype)
+
+    ident = (lambda t: t)
+    rw = r16 if "w" in policy else ident
+    rc = r16 if "conv" in policy else ident
+    ra = r16 if "act" in policy else ident
+    ri = r16 if "inc" in policy else ident
+    L = {}
+
+    def W(n):
+        return params[n + "/weights"]
+
+    def BN(x, n, relu):
+        return batch_norm(x, params["%s/%s/gamma" % (n, n)], params["%s/%s/beta" % (n, n)], relu)
+
+    x = data_nhwc.permute(0, 3, 1, 2)
+    x = ra(F.relu(BN(rc(conv2d(x, W("conv1_1_3x3_s2_n"), 2, "SAME")), "conv1_1_3x3_s2_bn", False)))   # fp32 stem
+    x = ra(BN(rc(conv2d(x, rw(W("conv1_2_3x3")), 1, "SAME")), "conv1_2_3x3_bn", True))
+    x = ra(BN(rc(conv2d(x, rw(W("conv1_3_3x3")), 1, "SAME")), "conv1_3_3x3_bn", True))
+    L["conv1_3_3x3_bn"] = x
+    x = max_pool_3x3_s2_same(x)
+    x_sc = x
+    for stage, blocks, _, stride, dil in STAGES:
+        for b in range(1, blocks + 1):
+            p = "conv%d_%d" % (stage, b)
+            s = stride if b == 1 else 1
+            if b == 1:
+                sc = BN(ri(conv2d(x, rw(W(p + "_1x1_proj")), s)), p + "_1x1_proj_bn", False)
+            else:
+                sc = x_sc
+            y = ra(BN(rc(conv2d(x, rw(W(p + "_1x1_reduce")), s)), p + "_1x1_reduce_bn", True))
+            y = ra(BN(rc(conv2d(y, rw(W(p + "_3x3")), 1, dil, dil)), p + "_3x3_bn", True))
+            y = BN(ri(conv2d(y, rw(W(p + "_1x1_increase")), 1)), p + "_1x1_increase_bn", False)
+            t = F.relu(sc + y)
+            if "junc" in policy:
+                x = x_sc = r16(t)
+            elif "junc_op" in policy:
+                x, x_sc = r16(t), t
+            else:
+                x = x_sc = t
+            L[p + "/relu"] = x
+    c53 = x
+    size = c53.shape[2:4]
+    br = {}
+    for lvl in PSP_LEVELS:
+        n = "conv5_3_pool%d" % lvl
+        y = ra(avg_pool(c53, last_pool_size // lvl))
+        y = ra(BN(rc(conv2d(y, rw(W(n + "_conv")), 1)), n + "_conv_bn", True))
+        br[lvl] = ra(resize_bilinear_ac(y, size))
+    cat = torch.cat([c53, br[6], br[3], br[2], br[1]], dim=1)
+    y = ra(BN(rc(conv2d(cat, rw(W("conv5_4")), 1, "SAME")), "conv5_4_bn", True))
+    L["conv5_4_bn"] = y
+    L["logits"] = conv2d(y, W(seg_name), 1, bias=params[seg_name + "/biases"])      # fp32 head
+    return L
 
 
 # --------------------------------------------------------------------------

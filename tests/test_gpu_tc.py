@@ -112,6 +112,7 @@ TC_MODES = {
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
 def test_tc_conv_matches_oracle(case, mode, monkeypatch):
     from gpu_util import rel_err
+    monkeypatch.setenv("BASI_EXPERIMENTS", "1")       # scheduling switches are experiment-gated
     for k_, v_ in TC_MODES[mode].items():
         monkeypatch.setenv(k_, v_)
     r = _tc_case(case)
@@ -161,6 +162,7 @@ def test_tc_fprop_fused_bn_statistics(case, mode, monkeypatch):
     from basi_b200._lib import ConvDesc
     from basi_b200.engine import Act
     from gpu_util import bf16_round, call, dev, host, rel_err
+    monkeypatch.setenv("BASI_EXPERIMENTS", "1")       # scheduling switches are experiment-gated
     for k_, v_ in TC_MODES[mode].items():
         monkeypatch.setenv(k_, v_)
     k, d, cin, cout, H, W, B = case
