@@ -108,7 +108,11 @@ class Engine(object):
         if device is None:
             device = "cuda:%d" % torch.cuda.current_device()
         self.device = torch.device(device)
-        self.use_tc = bool(use_tc) and precision != "f32"
+        self.use_tc = bool(use_tc)
+        # f32 mode on the tensor cores: float32 storage, convolutions on bf16 [hi|mid|lo] split operands (six bf16
+        # tcgen05 MMAs per product, fp32 TMEM accumulation) -- the reference's precision on the Blackwell-native path
+        self.split_tc = self.use_tc and precision == "f32"
+        self._split_cache = {}
         self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
@@ -129,7 +133,10 @@ class Engine(object):
         self.fused_stats = 0
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.mask_bits = not _exp_env("BASI_NO_MASK_BITS")
-        self.fuse_pools = not _exp_env("BASI_NO_POOL_FUSION")
+        # (the fused pyramid pooling accumulates with fp32 atomics: order noise of one ulp, which float32 storage keeps
+        # and the batch-stat BN of the 1x1 pyramid branch -- statistics over only B samples -- amplifies; the f32
+        # parity mode therefore uses the four separate, order-free pools)
+        self.fuse_pools = not _exp_env("BASI_NO_POOL_FUSION") and precision != "f32"
         self.coop_bn_bwd = not _exp_env("BASI_NO_COOP_BN")
         self.fused_bn_bwd = 0
         self._tc_weights = []
@@ -527,6 +534,12 @@ class Engine(object):
                 op["tc_fprop"] = self._emit_tc(op, _lib.TC_FPROP, self.fwd)
                 self._tc_producer[id(y)] = op
                 return
+        if self.split_tc and x.dtype == _lib.F32 and y.dtype == _lib.F32 and not op["b"] and not self.dry_run:
+            if _lib.load().basi_tc_conv_supported_split(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
+                op["split"] = True
+                op["tc_fprop"] = self._emit_tc(op, _lib.TC_FPROP, self.fwd)
+                self._tc_producer[id(y)] = op
+                return
         if (not op["b"] and not self.dry_run and self.fuse_bn_stats
                 and _lib.load().basi_stem_fprop_stats_supported(C.byref(op["desc"]), x.ref, y.ref) == 1):
             self._stem_producer[id(y)] = (len(self.fwd), op)       # _emit_bn_stats may upgrade this call
@@ -679,6 +692,21 @@ class Engine(object):
         need_dx = x is not self.input
         tc_ok = self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]
         lib = _lib.load()
+        if op.get("split"):
+            # fp32-grade tensor-core path: dy is split once, wgrad and dgrad both read the parts
+            if lib.basi_tc_conv_supported_split(_lib.TC_WGRAD, dptr, x.ref, y.ref) == 1:
+                self._emit_tc(op, _lib.TC_WGRAD, self.bwd)
+            else:
+                self._call(self.bwd, "basi_conv_wgrad", dptr, x.ref, dy.ref, self._gptr(op["w"]), None,
+                           flops=self._conv_flops(op), writes=[op["w"]], side=True)
+            if need_dx:
+                acc = self._acc_flag(x)
+                if lib.basi_tc_conv_supported_split(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1:
+                    self._emit_tc(op, _lib.TC_DGRAD, self.bwd, acc)
+                else:
+                    self._call(self.bwd, "basi_conv_dgrad", dptr, dy.ref, self._pptr(op["w"]), x.grad.ref, acc,
+                               flops=self._conv_flops(op))
+            return
         if tc_ok and lib.basi_tc_conv_supported(_lib.TC_WGRAD, dptr, x.ref, y.ref) == 1:
             self._emit_tc(op, _lib.TC_WGRAD, self.bwd)
         else:
@@ -818,17 +846,44 @@ class Engine(object):
                    C.c_int64(op["lda"]), self.B, op["K"], op["N"], acc)
 
     # ------------------------------------------------------------------ tcgen05 plans
+    def _split3(self, act, lst):
+        """bf16 [hi|mid|lo] parts of a float32 activation (3C channels); the split kernel is emitted into `lst` the
+        first time the tensor is needed (forward inputs stay valid for the weight-gradient pass)."""
+        key = id(act)
+        if key not in self._split_cache:
+            n, h, w, c = act.shape
+            a3 = Act(self._zeros((n, h, w, 3 * c), torch.bfloat16))
+            self._split_cache[key] = (a3, act)            # (keeps `act` alive: the key is its id)
+            self._call(lst, "basi_split3_bf16", act.ref, a3.ref, bytes=self._nbytes(act) * 2.5)
+        return self._split_cache[key][0]
+
     def _emit_tc(self, op, kind, lst, acc=0):
         lib = _lib.load()
         off, shape = self.param_index[op["w"]]
         taps, cin, cout = shape[0] * shape[1], shape[2], shape[3]
+        split = bool(op.get("split"))
         if "w_io" not in op:
-            op["w_io"] = self._zeros(taps * cin * cout, torch.bfloat16)
-            op["w_oi"] = self._zeros(taps * cin * cout, torch.bfloat16)
-            self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout))
+            kd = lib.basi_tc_split_kcols(cout) if split else cout      # dgrad layout [tap][cin][kd]
+            kf = lib.basi_tc_split_kcols(cin) if split else cin        # fprop layout [tap][cout][kf]
+            op["w_io"] = self._zeros(taps * cin * kd, torch.bfloat16)
+            op["w_oi"] = self._zeros(taps * cout * kf, torch.bfloat16)
+            self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout, 1 if split else 0))
         x, y = op["x"], op["y"]
         handle = C.c_void_p()
-        if kind == _lib.TC_FPROP:
+        if split:
+            if kind == _lib.TC_FPROP:
+                x3 = self._split3(x, lst)
+                _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), x3.ref, y.ref, op["w_oi"].data_ptr(),
+                          None, 0, C.byref(handle))
+            elif kind == _lib.TC_DGRAD:
+                dy3 = self._split3(y.grad, lst)
+                _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), dy3.ref, x.grad.ref,
+                          op["w_io"].data_ptr(), None, acc, C.byref(handle))
+            else:
+                x3, dy3 = self._split3(x, lst), self._split3(y.grad, lst)
+                _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), x3.ref, dy3.ref, None,
+                          self._gptr(op["w"]), 1, C.byref(handle))
+        elif kind == _lib.TC_FPROP:
             _lib.call("basi_tc_conv_create", kind, C.byref(op["desc"]), x.ref, y.ref, op["w_oi"].data_ptr(), None, 0,
                       C.byref(handle))
         elif kind == _lib.TC_DGRAD:
@@ -858,9 +913,10 @@ class Engine(object):
         if self._pack_table is None:
             entries = (_lib.PackEntry * len(self._tc_weights))()
             blocks = 0
-            for i, (wptr, w_io, w_oi, taps, cin, cout) in enumerate(self._tc_weights):
+            for i, (wptr, w_io, w_oi, taps, cin, cout, mode) in enumerate(self._tc_weights):
                 tco, tci = -(-cout // 32), -(-cin // 32)
-                entries[i] = _lib.PackEntry(wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, blocks, tco, tci, 0, 0)
+                entries[i] = _lib.PackEntry(wptr, w_io.data_ptr(), w_oi.data_ptr(), taps, cin, cout, blocks, tco, tci,
+                                            mode, 0)
                 blocks += taps * tco * tci
             raw = np.frombuffer(bytes(entries), dtype=np.uint8).copy()
             self._pack_table = torch.from_numpy(raw).to(self.device)

@@ -161,7 +161,18 @@ struct ConvParams {
   int ldd;                         // destination pixel stride (elements)
   int Cdst;                        // destination channels
   int taps, kw;
-  int k_chunks;                    // source channels / 64
+  int k_chunks;                    // source channels / 64 (split mode: chunks of all passes, see a_wrap0)
+  // split-operand (fp32-grade) mode: the source tensor holds [hi | mid | lo] bf16 parts of an fp32 tensor (3C
+  // channels) and the main loop runs three passes over it against [w_hi | w_mid | w_lo]-style weight columns: the
+  // activation chunk of k-chunk kc is kc, kc - a_wrap0 or kc - a_wrap1 (the weight chunk is always kc).  Plain bf16
+  // mode: both = INT_MAX.
+  int a_wrap0, a_wrap1;
+  // split mode, accumulation groups: tcgen05 adds into the fp32 accumulator with truncation (measured: ~0.4 ulp of
+  // bias per MMA, 2e-5 relative after the 864 MMAs of a 3x3x256 split convolution), so the k-steps whose products
+  // have full magnitude (hi x hi: the first big_chunks chunks of every tap) run LAST, in groups of group_steps
+  // k-steps that each start a fresh TMEM accumulator; the epilogue warps add every finished group into fp32
+  // registers (round to nearest).  All small k-steps (cross terms, 2^-8 .. 2^-16 of the result) form the first group.
+  int big_chunks, group_steps;
   // source coordinate of tap (r,s) for destination pixel p: p*1 + off0 + r*step (fprop: off0=-pad, step=dil;
   // dgrad: off0=+pad, step=-dil)
   int off_h, off_w, step;
@@ -217,7 +228,35 @@ struct SmemLayout {
 // VAR: 0 = the production kernel, 1 = halo mode (+ role timers), 2 = production kernel with the role timers
 // (compile-time so that the experimental paths cost the production kernel nothing: as run-time branches they
 // measured 1.8 % of the training step)
-template <int BN, int CL, int MT, int VAR>
+// k-step ks of a tile -> (filter tap, k-chunk).  Plain mode: tap-major.  Split mode: small k-steps first, then the
+// full-magnitude ones (see ConvParams::big_chunks).
+__device__ __forceinline__ void kstep_coords(const ConvParams& p, int ks, int& tap, int& kc) {
+  if (p.big_chunks == 0) {
+    tap = ks / p.k_chunks;
+    kc = ks - tap * p.k_chunks;
+    return;
+  }
+  const int small_per_tap = p.k_chunks - p.big_chunks, n_small = p.taps * small_per_tap;
+  if (ks < n_small) {
+    tap = ks / small_per_tap;
+    kc = p.big_chunks + (ks - tap * small_per_tap);
+  } else {
+    const int j = ks - n_small;
+    tap = j / p.big_chunks;
+    kc = j - tap * p.big_chunks;
+  }
+}
+// end (exclusive) of the accumulation group that starts at k-step gs
+__device__ __forceinline__ int group_end(const ConvParams& p, int gs, int ksteps) {
+  if (p.big_chunks == 0) return ksteps;
+  const int n_small = p.taps * (p.k_chunks - p.big_chunks);
+  if (gs < n_small) return n_small;
+  return min(ksteps, gs + p.group_steps);
+}
+
+// OUT32: the destination tensor is float32 (split-operand mode): fp32 staging boxes of [128 px][32 ch], TMA store /
+// reduce-add of float32, statistics from the fp32 values.
+template <int BN, int CL, int MT, int VAR, bool OUT32 = false>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
@@ -245,7 +284,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
   float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [row groups][2*BN] = 1024 floats
   // output staging for the TMA store: NBOX boxes of [128 px][64 ch] bf16, SWIZZLE_128B, 1024-B aligned
-  constexpr int NBOX = (BN + 63) / 64;
+  constexpr int NBOX = OUT32 ? BN / 32 : (BN + 63) / 64;
+  constexpr int BOXC = OUT32 ? 32 : 64;      // channels per output box (128-byte rows)
+  static_assert(!OUT32 || (CL == 1 && VAR == 0 && BN <= 128), "fp32 output: single CTA, production variant, BN <= 128");
   uint8_t* stage_out = smem + (size_t)p.ring_bytes + 1024 + 1024 * sizeof(float);
   stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_out) + 1023) & ~(uintptr_t)1023);
   volatile uint32_t* s_is_last = tmem_slot + 1;   // (no static __shared__: the dynamic window is the full 227 KB)
@@ -352,25 +393,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
           w0[sub] = tw * p.TW; h0[sub] = th * p.TH; n0[sub] = tn * p.TN;
         }
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          const int dh = p.off_h + r * p.step, dw = p.off_w + s * p.step;
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
+        {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            int tap, kc;
+            kstep_coords(p, ks, tap, kc);
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            const int dh = p.off_h + r * p.step, dw = p.off_w + s * p.step;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+            const int ac = kc >= p.a_wrap1 ? kc - p.a_wrap1 : (kc >= p.a_wrap0 ? kc - p.a_wrap0 : kc);
             if (elect_one()) {
               if (CL == 2) {
                 // both CTAs' bytes are counted on the leader's barrier
                 const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
                 if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE);
-                tma_load_4d_pair(sa, &mapA, fb, kc * KC, w0[0] + dw, h0[0] + dh, n0[0]);
+                tma_load_4d_pair(sa, &mapA, fb, ac * KC, w0[0] + dw, h0[0] + dh, n0[0]);
                 tma_load_3d_pair(sa + A_BYTES, &mapB, fb, kc * KC, nt * BN + crank * (BN / 2), tap);
               } else {
                 const uint32_t fb = full0 + 8 * stage;
                 mbar_expect_tx(fb, STAGE);
 #pragma unroll
                 for (int sub = 0; sub < MT; ++sub)
-                  tma_load_4d(sa + sub * A_BYTES, &mapA, fb, kc * KC, w0[sub] + dw, h0[sub] + dh, n0[sub]);
+                  tma_load_4d(sa + sub * A_BYTES, &mapA, fb, ac * KC, w0[sub] + dw, h0[sub] + dh, n0[sub]);
                 tma_load_3d(sa + MT * A_BYTES, &mapB, fb, kc * KC, nt * BN, tap);
               }
             }
@@ -460,8 +504,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = cid; t < total_tiles; t += ncl, ++it) {
+      int it = 0;      // accumulation groups issued so far (plain mode: one group per tile)
+      for (int t = cid; t < total_tiles; t += ncl)
+      for (int gs = 0; gs < ksteps; ++it) {
+        const int ge = group_end(p, gs, ksteps);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && lane == 0;
@@ -470,7 +516,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-        for (int ks = 0; ks < ksteps; ++ks) {
+        const int ks0 = gs;
+        for (int ks = ks0; ks < ge; ++ks) {
           if (dbg) m0 = dbg_clock();
           mbar_wait(full0 + 8 * stage, phase);
           if (dbg) g_tc_dbg[5] += dbg_clock() - m0;
@@ -484,8 +531,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
                 // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-                if (CL == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
-                else umma_f16(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                if (CL == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((ks - ks0) | k) != 0);
+                else umma_f16(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, idesc, ((ks - ks0) | k) != 0);
               }
             }
             // frees the smem slot (pair: in both CTAs)
@@ -504,6 +551,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           else umma_commit(tfull0 + 8 * acc);
         }
         __syncwarp();
+        gs = ge;
       }
     }
   } else if (warp >= 4) {
@@ -518,15 +566,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int it = 0, sidx = 0;
     int run_nt = -1;              // fused statistics: channel tile of the running sums below
     float run1 = 0.f, run2 = 0.f;
+    double rund1 = 0.0, rund2 = 0.0;   // (fp32-output mode keeps the running sums in double)
     for (int t = cid; t < total_tiles; t += ncl, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      int acc = it & 1;
+      uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.n_tiles;
       const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && issuer;
       long long c0 = dbg ? dbg_clock() : 0;
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      if (dbg) { const long long c1 = dbg_clock(); g_tc_dbg[0] += c1 - c0; g_tc_dbg[1] += 1; c0 = c1; }
-      tc_fence_after();
+      // fp32 output (split mode): the tile arrives as a sequence of accumulation groups, each in a fresh TMEM
+      // accumulator; they are summed here in fp32 registers (round to nearest) -- see ConvParams::big_chunks
+      constexpr int NCH = OUT32 ? (BN >= 64 ? BN / 64 : 1) : 1;
+      float accv[NCH][32];
+      if constexpr (OUT32) {
+        static_assert(!OUT32 || MT == 1, "split mode: one pixel tile per work item");
+        bool first = true;
+        for (int gs = 0; gs < ksteps; ++it) {
+          const int ge = group_end(p, gs, ksteps);
+          acc = it & 1;
+          acc_phase = (it >> 1) & 1;
+          mbar_wait(tfull0 + 8 * acc, acc_phase);
+          tc_fence_after();
+          const uint32_t ga = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN);
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            if ((c & 1) != half && BN >= 64) continue;
+            if (BN < 64 && half != 0) continue;
+            uint32_t r[32];
+            tmem_ld32(ga + c * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              accv[c >> 1][j] = first ? __uint_as_float(r[j]) : accv[c >> 1][j] + __uint_as_float(r[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);      // this accumulator may be overwritten
+          first = false;
+          gs = ge;
+        }
+        --it;      // (the tile loop increments once more)
+      } else {
+        mbar_wait(tfull0 + 8 * acc, acc_phase);
+        if (dbg) { const long long c1 = dbg_clock(); g_tc_dbg[0] += c1 - c0; g_tc_dbg[1] += 1; c0 = c1; }
+        tc_fence_after();
+      }
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub, ++sidx) {
       const int mt = ((t / p.n_tiles) * CL + crank) * MT + sub;
@@ -548,6 +630,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if ((c & 1) != half && BN >= 64) continue;
         if (BN < 64 && half != 0) continue;
         uint32_t r[32];
+        if constexpr (OUT32) {
+          // fp32 box c: row `row` is one 128-byte line of 32 floats, 16-byte chunks XOR-swizzled with (row & 7)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = (do_stats && !valid) ? 0u : __float_as_uint(accv[c >> 1][j]);
+          const uint32_t line32 = so + (uint32_t)c * A_BYTES + (uint32_t)row * 128;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line32 + (uint32_t)((v ^ (row & 7)) << 4)),
+                         "r"(r[4 * v]), "r"(r[4 * v + 1]), "r"(r[4 * v + 2]), "r"(r[4 * v + 3])
+                         : "memory");
+          }
+          continue;
+        }
         tmem_ld32(taddr + c * 32, r);
         uint32_t pk[16];
 #pragma unroll
@@ -571,7 +666,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0 && sub == MT - 1) {                                 // TMEM accumulator is free again
+      if (!OUT32 && lane == 0 && sub == MT - 1) {                       // TMEM accumulator is free again
         if (CL == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));
         else mbar_arrive(tempty0 + 8 * acc);
       }
@@ -580,8 +675,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (issuer) {
 #pragma unroll
         for (int j = 0; j < NBOX; ++j) {
-          if (p.accumulate) tma_reduce_add_4d(&mapD, so + j * A_BYTES, nt * BN + j * 64, w0, h0, n0);
-          else tma_store_4d(&mapD, so + j * A_BYTES, nt * BN + j * 64, w0, h0, n0);
+          if (p.accumulate) tma_reduce_add_4d(&mapD, so + j * A_BYTES, nt * BN + j * BOXC, w0, h0, n0);
+          else tma_store_4d(&mapD, so + j * A_BYTES, nt * BN + j * BOXC, w0, h0, n0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -590,8 +685,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // pair, group of rows): one conflict-free 32-bit shared-memory load per row (a warp reads 32 consecutive
         // words of one 128-byte line) -- the 4 x 31-shuffle transpose-reduce this replaces cost 6 of the 8 us the
         // statistics added to a conv4 1x1-increase fprop.
+        const int te = (int)threadIdx.x - 128;
+        if constexpr (OUT32) {
+          // thread = (column, group of rows); a warp reads 32 consecutive floats of one 128-byte line per row
+          constexpr int RG32 = 256 / BN, RPG32 = BM / RG32;
+          const int col = te % BN, rg32 = te / BN;
+          const uint32_t cb = so + (uint32_t)(col >> 5) * A_BYTES + (uint32_t)(col & 3) * 4;
+          const int cw = (col & 31) >> 2;
+          // float32 mode: the sums (and the variance E[x^2] - mean^2 derived from them) are accumulated in double
+          double s0 = 0.0, q0 = 0.0;
+#pragma unroll 8
+          for (int r = rg32 * RPG32; r < (rg32 + 1) * RPG32; ++r) {
+            float a;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(cb + (uint32_t)r * 128 + (uint32_t)((cw ^ (r & 7)) << 4)));
+            s0 += (double)a; q0 = fma((double)a, (double)a, q0);
+          }
+          double* stat_d = reinterpret_cast<double*>(stat_s);          // [row groups][2*BN] = 512 doubles
+          stat_d[rg32 * (2 * BN) + col] = s0;
+          stat_d[rg32 * (2 * BN) + BN + col] = q0;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (te < BN) {
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int g2 = 0; g2 < RG32; ++g2) {
+              t1 += stat_d[g2 * (2 * BN) + te];
+              t2 += stat_d[g2 * (2 * BN) + BN + te];
+            }
+            if (nt != run_nt) {
+              if (run_nt >= 0 && p.debug == 0) {
+                double* rep = p.bn_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * p.Cdst;
+                atomicAdd(rep + run_nt * BN + te, rund1);
+                atomicAdd(rep + p.Cdst + run_nt * BN + te, rund2);
+              }
+              run_nt = nt; rund1 = 0.0; rund2 = 0.0;
+            }
+            rund1 += t1;
+            rund2 += t2;
+          }
+          continue;
+        }
         constexpr int CP = BN / 2, RG = 256 / CP, RPG = BM / RG;
-        const int te = (int)threadIdx.x - 128, cp = te % CP, rg = te / CP;
+        const int cp = te % CP, rg = te / CP;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         const uint32_t colbase = BN >= 64 ? so + (uint32_t)(cp >> 5) * A_BYTES : so;
 #pragma unroll 8
@@ -636,8 +770,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (do_stats && run_nt >= 0 && (int)threadIdx.x - 128 < BN && p.debug == 0) {
       double* rep = p.bn_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * p.Cdst;
-      atomicAdd(rep + run_nt * BN + ((int)threadIdx.x - 128), (double)run1);
-      atomicAdd(rep + p.Cdst + run_nt * BN + ((int)threadIdx.x - 128), (double)run2);
+      atomicAdd(rep + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund1 : (double)run1);
+      atomicAdd(rep + p.Cdst + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund2 : (double)run2);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
     if (p.bn_sums != nullptr) __threadfence();
@@ -697,6 +831,7 @@ struct WgradParams {
   int off_h, off_w, step;   // x coordinate = p + off + r*step (fprop mapping)
   int Cin, Cout;
   int stages;
+  int nterms;               // 1, or 6 in split-operand mode: (dy part, x part) = (0,0) (0,1) (1,0) (0,2) (2,0) (1,1)
 };
 
 template <int BN, int GBOX>
@@ -750,30 +885,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   const int r = tap / p.kw, s = tap - r * p.kw;
   const int mt_beg = split * p.tiles_per_split;
   const int mt_end = min(p.m_tiles, mt_beg + p.tiles_per_split);
-  const int nsteps = mt_end - mt_beg;
+  const int nsteps = (mt_end - mt_beg) * p.nterms;
 
   if (warp == 0) {
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int mt = mt_beg; mt < mt_end; ++mt) {
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
-        const uint32_t fb = full0 + 8 * stage;
-        if (elect_one()) {
-          mbar_expect_tx(fb, STAGE);
-          tma_load_4d(sa, &mapG, fb, cot * 128, w0, h0, n0);
-          if (GBOX == 2) tma_load_4d(sa + A_BYTES, &mapG, fb, cot * 128 + 64, w0, h0, n0);
-          const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
+      // split-operand mode: the six significant products of (dy_hi + dy_mid + dy_lo) x (x_hi + x_mid + x_lo), the
+      // small ones first and hi x hi last (tcgen05 accumulates with truncation: small terms added to a full-size
+      // accumulator would lose their low bits); plain mode runs only the last term
+      for (int term = 6 - p.nterms; term < 6; ++term) {
+        const int gpart = term == 0 ? 1 : (term == 1 ? 2 : (term == 3 ? 1 : 0));     // (1,1) (2,0) (0,2) (1,0) (0,1) (0,0)
+        const int xpart = term == 0 ? 1 : (term == 2 ? 2 : (term == 4 ? 1 : 0));
+        const int gc = gpart * p.Cout + cot * 128, xc = xpart * p.Cin + cit * BN;
+        for (int mt = mt_beg; mt < mt_end; ++mt) {
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
+          const uint32_t fb = full0 + 8 * stage;
+          if (elect_one()) {
+            mbar_expect_tx(fb, STAGE);
+            tma_load_4d(sa, &mapG, fb, gc, w0, h0, n0);
+            if (GBOX == 2) tma_load_4d(sa + A_BYTES, &mapG, fb, gc + 64, w0, h0, n0);
+            const int xw = w0 + p.off_w + s * p.step, xh = h0 + p.off_h + r * p.step;
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, cit * BN + j * 64, xw, xh, n0);
-        }
-        __syncwarp();
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+            for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + GB + j * A_BYTES, &mapX, fb, xc + j * 64, xw, xh, n0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -888,6 +1031,48 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
   const int tap = b;
   const int ci0 = cit * 32, co0 = cot * 32;
   const size_t base = (size_t)tap * e.cin * e.cout;
+  if (e.pad0 == 1) {
+    // split-operand layout (fp32-grade mode): w = hi + mid + lo (bf16 each).  The operand tensor of the convolution
+    // holds [hi|mid|lo] channel blocks and the main loop runs three passes of 64-column chunks over it; the weight
+    // column of (pass p, operand part q, channel c) is (passoff[p] * 64 + q * C + c) and holds w_hi for p = 0
+    // (q = 0,1,2), w_mid for p = 1 (q = 0,1), w_lo for p = 2 (q = 0): the six significant products.  Every other
+    // column stays zero (the buffers are zero-initialised once).
+    //   w_oi: fprop layout [tap][co][Kf], reduced channel C = cin;   w_io: dgrad layout [tap][ci][Kd], C = cout
+    const int f0 = (3 * e.cin + 63) / 64, f1 = (2 * e.cin + 63) / 64, f2 = (e.cin + 63) / 64;
+    const int d0 = (3 * e.cout + 63) / 64, d1 = (2 * e.cout + 63) / 64, d2 = (e.cout + 63) / 64;
+    const size_t Kf = (size_t)(f0 + f1 + f2) * 64, Kd = (size_t)(d0 + d1 + d2) * 64;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int ci = ci0 + i, co = co0 + threadIdx.x;
+      const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
+      tile[i][threadIdx.x] = v;
+      if (ci < e.cin && co < e.cout) {
+        const bf16 h = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h);
+        const bf16 m = __float2bfloat16_rn(r1);
+        const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        bf16* row = e.w_io + ((size_t)tap * e.cin + ci) * Kd;
+        row[co] = h; row[e.cout + co] = h; row[2 * e.cout + co] = h;
+        row[(size_t)d0 * 64 + co] = m; row[(size_t)d0 * 64 + e.cout + co] = m;
+        row[(size_t)(d0 + d1) * 64 + co] = l;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int co = co0 + i, ci = ci0 + threadIdx.x;
+      if (ci < e.cin && co < e.cout) {
+        const float v = tile[threadIdx.x][i];
+        const bf16 h = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h);
+        const bf16 m = __float2bfloat16_rn(r1);
+        const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        bf16* row = e.w_oi + ((size_t)tap * e.cout + co) * Kf;
+        row[ci] = h; row[e.cin + ci] = h; row[2 * e.cin + ci] = h;
+        row[(size_t)f0 * 64 + ci] = m; row[(size_t)f0 * 64 + e.cin + ci] = m;
+        row[(size_t)(f0 + f1) * 64 + ci] = l;
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int ci = ci0 + i, co = co0 + threadIdx.x;
     const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
@@ -927,12 +1112,17 @@ static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, in
     set_error("tc: cuTensorMapEncodeTiled not available");
     return BASI_E_CUDA;
   }
+  // bf16: 64-channel boxes (128-byte rows); float32 (split-operand mode outputs): 32-channel boxes (128-byte rows)
+  const bool f32 = t->dtype == BASI_F32;
+  const cuuint64_t es_b = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
-  cuuint64_t strides[3] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->ld * 2 * t->w, (cuuint64_t)t->ld * 2 * t->w * t->h};
+  cuuint64_t strides[3] = {(cuuint64_t)t->ld * es_b, (cuuint64_t)t->ld * es_b * t->w,
+                           (cuuint64_t)t->ld * es_b * t->w * t->h};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (uint64_t)box_c * es_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc: cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
@@ -989,6 +1179,7 @@ struct basi_tc_conv {
   int cluster;
   int mt;        // pixel tiles per work item (1 or 2)
   int gbox;      // wgrad: 64-channel boxes of the output-gradient operand (1 when Cout <= 64)
+  int split;     // split-operand (fp32-grade) mode: bf16 [hi|mid|lo] operands, float32 destination
   CUtensorMap mapA, mapB, mapD;
   ConvParams cp;
   WgradParams wp;
@@ -1017,6 +1208,23 @@ static bool tc_geometry_ok(int kind, const basi_conv_desc* d, const basi_tensor*
   return false;
 }
 
+// split-operand mode: x, y are the logical float32 tensors (the bf16 [hi|mid|lo] operand tensors have 3x the channels)
+static bool tc_geometry_ok_split(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  if (!d || !x || !y) return false;
+  if (x->dtype != BASI_F32 || y->dtype != BASI_F32) return false;
+  if (d->stride != 1 || d->kh != d->kw || d->relu) return false;
+  if (x->n != y->n) return false;
+  const int span = (d->kh - 1) * d->dil;
+  if (y->h != x->h || y->w != x->w || 2 * d->pad_t != span || 2 * d->pad_l != span) return false;
+  if (x->ld % 4 || y->ld % 4) return false;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
+  const int cin = x->c, cout = y->c;
+  if (kind == BASI_TC_FPROP) return cin % 8 == 0 && cin >= 16 && cout % 32 == 0;
+  if (kind == BASI_TC_DGRAD) return cout % 8 == 0 && cout >= 16 && cin % 32 == 0;
+  if (kind == BASI_TC_WGRAD) return cin % 8 == 0 && cin >= 16 && cout % 8 == 0 && cout >= 16;
+  return false;
+}
+
 template <int BN>
 static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
   static bool attr_set = false;
@@ -1031,6 +1239,17 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     attr_set = true;
   }
   const dim3 grid(pl->grid), block(NTHREADS_CONV);
+  if (pl->split) {
+    if constexpr (BN <= 128) {
+      static bool attr32 = false;
+      if (!attr32) {
+        cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr32 = true;
+      }
+      basi::launch(conv_tc_kernel<BN, 1, 1, 0, true>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    }
+    return BASI_OK;
+  }
   const bool timers = pl->cp.debug == 30;
   if (pl->cp.halo && BN <= 128)
     basi::launch(conv_tc_kernel<BNS, 1, 1, 1>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
@@ -1087,15 +1306,34 @@ int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_bl
 /* kind FPROP: a = x, b = y (written), w_bf16 = [tap][Cout][Cin]
  * kind DGRAD: a = dy, b = dx (written / accumulated), w_bf16 = [tap][Cin][Cout]
  * kind WGRAD: a = x, b = dy, dw = HWIO float32 gradient (added into) */
-int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
-                        const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out) {
+}  // extern "C"
+
+static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
+                       const void* w_bf16, float* dw, int accumulate, int split, basi_tc_conv** out) {
   BASI_CHECK_ARG(d && a && b && out, "tc_conv_create: null argument");
   const basi_tensor* x = (kind == BASI_TC_DGRAD) ? b : a;   // forward input geometry
   const basi_tensor* y = (kind == BASI_TC_DGRAD) ? a : b;   // forward output geometry
-  BASI_CHECK_ARG(tc_geometry_ok(kind, d, x, y), "tc_conv_create: geometry not supported by the tcgen05 path");
+  if (split) {
+    // operands are bf16 [hi|mid|lo] tensors with 3x the logical channels; destinations are float32
+    basi_tensor xl = *x, yl = *y;
+    if (kind == BASI_TC_FPROP || kind == BASI_TC_WGRAD) {
+      BASI_CHECK_ARG(a->dtype == BASI_BF16 && a->c % 3 == 0, "tc_conv_create_split: a must be a bf16 [hi|mid|lo] tensor");
+      xl.c = a->c / 3; xl.dtype = BASI_F32; xl.ld = (xl.c + 3) / 4 * 4;
+    }
+    if (kind == BASI_TC_DGRAD || kind == BASI_TC_WGRAD) {
+      const basi_tensor* g = kind == BASI_TC_DGRAD ? a : b;
+      BASI_CHECK_ARG(g->dtype == BASI_BF16 && g->c % 3 == 0, "tc_conv_create_split: dy must be a bf16 [hi|mid|lo] tensor");
+      yl.c = g->c / 3; yl.dtype = BASI_F32; yl.ld = (yl.c + 3) / 4 * 4;
+    }
+    BASI_CHECK_ARG((a->ld % 8 == 0) && (((uintptr_t)a->ptr & 15) == 0), "tc_conv_create_split: operand alignment");
+    BASI_CHECK_ARG(tc_geometry_ok_split(kind, d, &xl, &yl), "tc_conv_create_split: geometry not supported");
+  } else {
+    BASI_CHECK_ARG(tc_geometry_ok(kind, d, x, y), "tc_conv_create: geometry not supported by the tcgen05 path");
+  }
   basi_tc_conv* pl = new basi_tc_conv();
   memset(pl, 0, sizeof(*pl));
   pl->kind = kind;
+  pl->split = split;
   int TW, TH, TN;
   pick_tile(x->n, x->h, x->w, &TW, &TH, &TN);
   int tiles_w = (x->w + TW - 1) / TW, tiles_h = (x->h + TH - 1) / TH, tiles_n = (x->n + TN - 1) / TN;
@@ -1106,7 +1344,13 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     BASI_CHECK_ARG(w_bf16, "tc_conv_create: null weights");
     const basi_tensor* src = a;
     const basi_tensor* dstt = b;
-    const int ndim = dstt->c, kdim = src->c;
+    const int ndim = dstt->c;
+    // split mode: three passes over the [hi|mid|lo] operand (all parts x w_hi, hi+mid x w_mid, hi x w_lo)
+    const int csrc = split ? src->c / 3 : src->c;
+    const int n0 = split ? (3 * csrc + 63) / 64 : (csrc + 63) / 64;
+    const int n1 = split ? (2 * csrc + 63) / 64 : 0, n2 = split ? (csrc + 63) / 64 : 0;
+    const int kchunks_all = n0 + n1 + n2;
+    const int kdim = split ? kchunks_all * 64 : src->c;     // weight columns
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
     // (narrower channel tiles for the tiny pyramid-branch maps, to spread the weight traffic over more SMs, measured
     // no change: those launches are 6 us of launch + 6 us of pipeline latency; BASI_TC_SMALL_M=<tiles> re-enables it)
@@ -1115,7 +1359,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       while (bn > 32 && ndim % (bn / 2) == 0 && (long)m_tiles * (ndim / bn) < few) bn /= 2;
     }
     const int bn256_mink = exp_env("BASI_TC_BN256_MINK") ? atoi(exp_env("BASI_TC_BN256_MINK")) : 8;
-    if (ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !exp_env("BASI_TC_NO_BN256")) {
+    if (!split && ndim % 256 == 0 && d->kh * d->kw * ((kdim + 63) / 64) >= bn256_mink && !exp_env("BASI_TC_NO_BN256")) {
       const long t128 = ((long)m_tiles * (ndim / 128) + sms - 1) / sms * 10;
       const long t256 = ((long)m_tiles * (ndim / 256) + sms - 1) / sms * 14;
       if (t256 < t128) bn = 256;
@@ -1140,8 +1384,9 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       const char* env_mt = exp_env("BASI_TC_MT");
       int min_k = exp_env("BASI_TC_MT_MINK") ? atoi(exp_env("BASI_TC_MT_MINK")) : 4;
       if (bn <= 128 && pl->cluster == 1 && m_tiles >= 2 && items2 * 3 >= (long)sms * 2 && ksteps >= min_k) pl->mt = 2;
+      if (split) pl->mt = 1;     // the epilogue keeps the running fp32 sums of ONE tile in registers
       if (env_mt && atoi(env_mt) == 1) pl->mt = 1;
-      if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2) pl->mt = 2;   // tests
+      if (env_mt && atoi(env_mt) == 2 && bn <= 128 && pl->cluster == 1 && m_tiles >= 2 && !split) pl->mt = 2;   // tests
     }
     // halo mode for 3x3 convolutions (see ConvParams): tile = 8 x 16 pixels of one image, one activation box of
     // 16 x (16 + 2 dil) pixels per 64-channel chunk serves all nine taps
@@ -1150,7 +1395,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       const char* env_h = exp_env("BASI_TC_HALO");
       const bool can = d->kh == 3 && d->kw == 3 && d->dil >= 1 && d->dil <= 4 && d->pad_t == d->dil &&
                        d->pad_l == d->dil && pl->cluster == 1 && bn <= 128;
-      halo = can && env_h && atoi(env_h) == 1;
+      halo = can && env_h && atoi(env_h) == 1 && !split;
     }
     if (halo) {
       TW = 8; TH = 16; TN = 1;
@@ -1162,7 +1407,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
       rc = make_act_map(&pl->mapA, src, TW, TH, TN);
     }
     if (rc == BASI_OK) rc = make_w_map(&pl->mapB, w_bf16, d->kh * d->kw, ndim, kdim, pl->cluster == 2 ? bn / 2 : bn);
-    if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, bn >= 64 ? 64 : bn);
+    if (rc == BASI_OK) rc = make_act_map(&pl->mapD, dstt, TW, TH, TN, split ? 32 : (bn >= 64 ? 64 : bn));
     if (rc != BASI_OK) {
       delete pl;
       return rc;
@@ -1173,6 +1418,11 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     cp.m_tiles = m_tiles; cp.n_tiles = ndim / bn;
     cp.N = dstt->n; cp.H = dstt->h; cp.W = dstt->w; cp.ldd = dstt->ld; cp.Cdst = dstt->c;
     cp.taps = d->kh * d->kw; cp.kw = d->kw; cp.k_chunks = (kdim + 63) / 64;
+    cp.a_wrap0 = split ? n0 : 0x7fffffff;
+    cp.a_wrap1 = split ? n0 + n1 : 0x7fffffff;
+    cp.big_chunks = split ? n2 : 0;
+    cp.group_steps = exp_env("BASI_TC_SPLIT_GROUP") ? atoi(exp_env("BASI_TC_SPLIT_GROUP")) : 4;
+    if (cp.group_steps < 1) cp.group_steps = 1;
     if (kind == BASI_TC_FPROP) {
       cp.off_h = -d->pad_t; cp.off_w = -d->pad_l; cp.step = d->dil;
     } else {
@@ -1183,7 +1433,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     // small-K layers are paced by the epilogue: give them two output staging buffers; large-K layers keep the
     // shared memory for pipeline stages
     cp.out_bufs = (cp.taps * cp.k_chunks <= 8 || pl->mt == 2) ? 2 : 1;
-    const int out_stage = cp.out_bufs * ((bn + 63) / 64) * A_BYTES;
+    if (split && bn == 128) cp.out_bufs = 1;             // fp32 staging: 64 KB per 128-channel tile
+    const int out_stage = cp.out_bufs * (split ? bn / 32 : (bn + 63) / 64) * A_BYTES;
     const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 1024 * (int)sizeof(float) + 1024 /*align*/ + out_stage;
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -1238,7 +1489,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     cp.debug = exp_env("BASI_TC_DEBUG_STATS") ? atoi(exp_env("BASI_TC_DEBUG_STATS")) : 0;
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
-    const int cin = a->c, cout = b->c;
+    const int cin = split ? a->c / 3 : a->c, cout = split ? b->c / 3 : b->c;
     int bn = cin > 64 ? 128 : 64;            // ci tile (UMMA N); co is the UMMA M = 128
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, a, TW, TH, TN);
@@ -1254,6 +1505,7 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
     wp.ci_tiles = (cin + bn - 1) / bn; wp.co_tiles = (cout + 127) / 128;
     wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
     wp.Cin = cin; wp.Cout = cout;
+    wp.nterms = split ? 6 : 1;
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
     // split-K over pixel tiles.  Every split adds |dW| fp32 atomics, so tiny gradients (conv4 1x1: 65 K elements)
     // want a single wave of CTAs (measured 22.6 -> 16.7 us); long pixel loops want two waves for balance.
@@ -1281,6 +1533,32 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
   }
   *out = pl;
   return BASI_OK;
+}
+
+extern "C" {
+
+int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
+                        const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out) {
+  return create_plan(kind, d, a, b, w_bf16, dw, accumulate, 0, out);
+}
+
+/* Split-operand (fp32-grade) plans: operands are bf16 [hi|mid|lo] tensors produced by basi_split3_bf16 (3C channels),
+ * weights are the packed split layout of basi_tc_pack_weights_multi (mode 1), destinations are float32.
+ *   FPROP: a = x3, b = y (f32, written)      DGRAD: a = dy3, b = dx (f32, written / accumulated)
+ *   WGRAD: a = x3, b = dy3, dw = HWIO float32 gradient (added into) */
+int basi_tc_conv_create_split(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
+                              const void* w_split, float* dw, int accumulate, basi_tc_conv** out) {
+  return create_plan(kind, d, a, b, w_split, dw, accumulate, 1, out);
+}
+
+int basi_tc_conv_supported_split(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
+  return tc_geometry_ok_split(kind, d, x, y) ? 1 : 0;
+}
+
+/* number of bf16 weight columns (K') of the split layout for a reduced channel count c: three passes of 64-channel
+ * chunks over [hi|mid|lo] (3c), [hi|mid] (2c) and [hi] (c) */
+int basi_tc_split_kcols(int c) {
+  return (((3 * c + 63) / 64) + ((2 * c + 63) / 64) + ((c + 63) / 64)) * 64;
 }
 
 int basi_tc_conv_set_bn_stats(basi_tc_conv* pl, double* sums, const float* gamma, const float* beta, double count,

@@ -445,6 +445,7 @@ def pspnet_forward_rounded(params, data_nhwc, last_pool_size, policy, seg_name="
         y = ra(avg_pool(c53, last_pool_size // lvl))
         y = ra(BN(rc(conv2d(y, rw(W(n + "_conv")), 1)), n + "_conv_bn", True))
         br[lvl] = ra(resize_bilinear_ac(y, size))
+        L[n + "_interp"] = br[lvl]
     cat = torch.cat([c53, br[6], br[3], br[2], br[1]], dim=1)
     y = ra(BN(rc(conv2d(cat, rw(W("conv5_4")), 1, "SAME")), "conv5_4_bn", True))
     L["conv5_4_bn"] = y

@@ -20,7 +20,7 @@ for p in (ROOT, os.path.join(ROOT, "instance-segment-basi_b200")):
 from oracle import basi_oracle as O  # noqa: E402
 
 STAGES = ["conv1_3_3x3_bn", "conv2_3/relu", "conv3_4/relu", "conv4_8/relu", "conv4_23/relu", "conv5_3/relu",
-          "conv5_4_bn"]
+          "conv5_3_pool1_interp", "conv5_3_pool6_interp", "conv5_4_bn"]
 
 
 def rel2(a, b):
@@ -75,6 +75,14 @@ def compare(out, ref, variant):
     gb = np.concatenate([ref["grads"][n].reshape(-1) for n in ref["grads"]]).astype(np.float64)
     row["grad_cos"] = float(ga @ gb / (np.linalg.norm(ga) * np.linalg.norm(gb)))
     row["grad_rel2"] = rel2(ga, gb)
+    tot = float(np.linalg.norm(gb))
+    worst = sorted(((rel2(out["grads"][n], ref["grads"][n]), float(np.linalg.norm(ref["grads"][n])) / tot, n)
+                    for n in ref["grads"] if np.linalg.norm(ref["grads"][n]) > 0), reverse=True)
+    row["grad_worst"] = worst[:8]
+    # error share: which tensors carry the overall gradient error
+    share = sorted(((float(np.linalg.norm(np.asarray(out["grads"][n], np.float64) - ref["grads"][n])) /
+                     max(float(np.linalg.norm(ga - gb)), 1e-300), n) for n in ref["grads"]), reverse=True)
+    row["grad_err_share"] = share[:8]
     row["loss_rel"] = abs(out["loss"][0] - ref["loss"]) / abs(ref["loss"])
     return row
 
@@ -104,7 +112,7 @@ def model_rows(params, data, P, seg_name, ref_stage, policies):
 def fmt_table(title, rows):
     cols = STAGES + ["logits"]
     lines = ["### " + title, "",
-             "| path | " + " | ".join(c.replace("_3x3_bn", "").replace("/relu", "") for c in cols) +
+             "| path | " + " | ".join(c.replace("_3x3_bn", "").replace("/relu", "").replace("conv5_3_", "").replace("_interp", "") for c in cols) +
              " | mask agree / IoU | grad cos | grad rel-l2 | loss rel |",
              "|---|" + "---|" * (len(cols) + 4)]
     for name, r in rows:
@@ -142,8 +150,10 @@ def main():
     for prec in args.precisions.split(","):
         out = engine_run(variant, nseg, S, F, B, classes, prec, dict(kind=kind, pos_weight=pw, class_weight=cw),
                          params, data, lab, cls, lr)
-        rows.append(("CUDA %s (%d tcgen05 plans, storage %s)" % (prec, out["tc_layers"], out["storage"]),
-                     compare(out, ref, variant)))
+        r = compare(out, ref, variant)
+        rows.append(("CUDA %s (%d tcgen05 plans, storage %s)" % (prec, out["tc_layers"], out["storage"]), r))
+        print("%s: worst gradient tensors (rel-l2, share of |g|, name): %s" % (prec, r["grad_worst"]))
+        print("%s: largest shares of the gradient error (share, name): %s" % (prec, r["grad_err_share"]))
     for name, r in model_rows(params, data, S // 8, O.VARIANTS[variant][0], ref, args.models.split(",")).items():
         rows.append(("model: %s" % name, r))
     text = fmt_table("%s, S=%d, F=%d, B=%d, trained-like weights: rel-l2 error vs the float64 oracle" % (

@@ -199,3 +199,129 @@ def test_tc_fprop_fused_bn_statistics(case, mode, monkeypatch):
     assert rel_err(got[2 * cout:3 * cout], gamma * istd) < 1e-4
     assert np.array_equal(got[3 * cout:], beta)
     assert int(host(cnt)[0]) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# split-operand ("bf16x6") mode: float32 tensors, bf16 [hi|mid|lo] operands, fp32-grade products on tcgen05
+# ---------------------------------------------------------------------------------------------------------------
+SPLIT_CASES = [
+    (1, 1, 64, 128, 16, 16, 2),
+    (3, 1, 32, 32, 80, 80, 1),      # 32-channel layers: [hi|mid] share a 64-channel box
+    (3, 2, 128, 128, 40, 40, 3),    # conv4 dilated, odd batch
+    (1, 1, 512, 128, 40, 40, 2),
+    (1, 1, 128, 512, 40, 40, 2),
+    (3, 1, 256, 64, 20, 12, 2),     # ragged map
+    (1, 1, 32, 128, 80, 80, 2),
+    (3, 4, 256, 256, 24, 24, 1),
+]
+
+
+def _split_case(case, with_stats=False):
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc, PackEntry
+    from basi_b200.engine import Act
+    from gpu_util import call, dev, host
+    k, d, cin, cout, H, W, B = case
+    rng = np.random.RandomState(sum(case) + 1)
+    x = rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    dy = rng.uniform(-1, 1, (B, H, W, cout)).astype(np.float32)
+    pad = d * (k - 1) // 2
+    desc = ConvDesc(k, k, 1, d, pad, pad, 0)
+    lib = _lib.load()
+    f32, bt = torch.float32, torch.bfloat16
+    xa = Act(torch.from_numpy(x).to("cuda:0"))
+    ya = Act(torch.full((B, H, W, cout), 3.0, dtype=f32, device="cuda:0"))
+    dya = Act(torch.from_numpy(dy).to("cuda:0"))
+    dxa = Act(torch.full((B, H, W, cin), 1.0, dtype=f32, device="cuda:0"))
+    x3 = Act(torch.zeros((B, H, W, 3 * cin), dtype=bt, device="cuda:0"))
+    dy3 = Act(torch.zeros((B, H, W, 3 * cout), dtype=bt, device="cuda:0"))
+    call("basi_split3_bf16", xa.ref, x3.ref)
+    call("basi_split3_bf16", dya.ref, dy3.ref)
+    # the parts add up to the float32 value (to 2^-24 relative)
+    parts = host(x3).astype(np.float64).reshape(B, H, W, 3, cin).sum(3)
+    assert np.max(np.abs(parts - x)) <= 2.0 ** -23 * np.max(np.abs(x))
+    wd = dev(w)
+    kf, kd = lib.basi_tc_split_kcols(cin), lib.basi_tc_split_kcols(cout)
+    w_io = torch.zeros(k * k * cin * kd, dtype=bt, device="cuda:0")
+    w_oi = torch.zeros(k * k * cout * kf, dtype=bt, device="cuda:0")
+    tco, tci = -(-cout // 32), -(-cin // 32)
+    ent = (PackEntry * 1)(PackEntry(wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout, 0, tco, tci, 1, 0))
+    table = torch.from_numpy(np.frombuffer(bytes(ent), dtype=np.uint8).copy()).to("cuda:0")
+    call("basi_tc_pack_weights_multi", table.data_ptr(), 1, k * k * tco * tci)
+    res = {}
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    yref = O.conv2d(xt, wt, 1, pad, d)
+    (yref * torch.from_numpy(dy).permute(0, 3, 1, 2).double()).sum().backward()
+    res["y_ref"] = yref.detach().permute(0, 2, 3, 1).numpy()
+    res["dx_ref"] = xt.grad.permute(0, 2, 3, 1).numpy()
+    res["dw_ref"] = wt.grad.numpy()
+    handles = []
+    assert lib.basi_tc_conv_supported_split(0, C.byref(desc), xa.ref, ya.ref) == 1
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create_split", 0, C.byref(desc), x3.ref, ya.ref, w_oi.data_ptr(), None, 0, C.byref(h))
+    if with_stats:
+        gamma, beta = rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.uniform(-1, 1, cout).astype(np.float32)
+        gd, bd = dev(gamma), dev(beta)
+        sums = torch.zeros(2 * cout * 8, dtype=torch.float64, device="cuda:0")
+        bnp = torch.zeros(4 * cout, device="cuda:0")
+        cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+        _lib.call("basi_tc_conv_set_bn_stats", h, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(),
+                  C.c_double(float(B * H * W)), C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
+    call("basi_tc_conv_run", h)
+    res["y"] = host(ya)
+    handles.append(h)
+    if with_stats:
+        res["bnp"], res["gamma"], res["beta"] = host(bnp), gamma, beta
+    if lib.basi_tc_conv_supported_split(1, C.byref(desc), xa.ref, ya.ref) == 1:
+        h = C.c_void_p()
+        _lib.call("basi_tc_conv_create_split", 1, C.byref(desc), dy3.ref, dxa.ref, w_io.data_ptr(), None, 0, C.byref(h))
+        call("basi_tc_conv_run", h)
+        res["dx"] = host(dxa)
+        h2 = C.c_void_p()
+        _lib.call("basi_tc_conv_create_split", 1, C.byref(desc), dy3.ref, dxa.ref, w_io.data_ptr(), None, 1, C.byref(h2))
+        call("basi_tc_conv_run", h2)
+        res["dx_acc"] = host(dxa)
+        handles += [h, h2]
+    assert lib.basi_tc_conv_supported_split(2, C.byref(desc), xa.ref, ya.ref) == 1
+    dw = torch.zeros((k, k, cin, cout), dtype=f32, device="cuda:0")
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create_split", 2, C.byref(desc), x3.ref, dy3.ref, None, dw.data_ptr(), 1, C.byref(h))
+    call("basi_tc_conv_run", h)
+    res["dw"] = host(dw)
+    handles.append(h)
+    torch.cuda.synchronize()
+    for h in handles:
+        lib.basi_tc_conv_destroy(h)
+    return res
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_split_conv_is_fp32_grade(case):
+    """fprop / dgrad / wgrad on bf16 [hi|mid|lo] operands against float64: the error must be that of a float32
+    convolution (a few 2^-24 times sqrt(K)), three orders of magnitude below a bf16 convolution's 2^-9."""
+    from gpu_util import rel_err
+    r = _split_case(case)
+    tol = 2e-6
+    assert rel_err(r["y"], r["y_ref"]) < tol, rel_err(r["y"], r["y_ref"])
+    if "dx" in r:
+        assert rel_err(r["dx"], r["dx_ref"]) < tol, rel_err(r["dx"], r["dx_ref"])
+        assert rel_err(r["dx_acc"], 2 * r["dx_ref"]) < 2 * tol
+    assert rel_err(r["dw"], r["dw_ref"]) < 5e-6, rel_err(r["dw"], r["dw_ref"])
+
+
+@pytest.mark.parametrize("case", [(3, 2, 128, 128, 40, 40, 3), (1, 1, 64, 32, 80, 80, 1), (3, 1, 32, 64, 48, 48, 1)],
+                         ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_split_fprop_fused_bn_statistics(case):
+    from gpu_util import rel_err
+    r = _split_case(case, with_stats=True)
+    cout = case[3]
+    y = r["y"].astype(np.float64).reshape(-1, cout)
+    mean, var = y.mean(0), y.var(0)
+    istd = 1 / np.sqrt(var + 1e-5)
+    got = r["bnp"]
+    assert np.max(np.abs(got[:cout] - mean)) < 1e-5 * max(1.0, np.max(np.abs(mean)))
+    assert rel_err(got[cout:2 * cout], istd) < 1e-4
+    assert rel_err(got[2 * cout:3 * cout], r["gamma"] * istd) < 1e-4
+    assert np.array_equal(got[3 * cout:], r["beta"])

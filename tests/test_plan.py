@@ -104,7 +104,7 @@ def test_synthetic_batches_are_reference_shaped():
 def test_psp_branches_are_tagged_and_their_pool_adjoints_deferred():
     """The four pyramid branches run on their own streams: every call of a branch carries its tag, the shared-tensor
     read-modify-write (avgpool adjoint) carries none and is emitted after the last branch call."""
-    eng = Engine(build("1NoClass", S=64, F=8), 2, precision="f32", dry_run=True,
+    eng = Engine(build("1NoClass", S=64, F=8), 2, precision="bf16", dry_run=True,       # (f32: four order-free pools)
                  loss=dict(kind="bce", pos_weight=3.0))
     for lst in (eng.fwd, eng.bwd):
         tags = [m.get("branch") for _, _, _, m in lst]
