@@ -287,6 +287,10 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
  * last CTA writes bnp when it is non-NULL), which removes the separate statistics pass over the conv output. */
 int basi_tc_conv_set_bn_stats(basi_tc_conv* plan, double* sums, const float* gamma, const float* beta, double count,
                               float eps, float* bnp, uint32_t* counter);
+/* A6 fused into A4: an fprop plan with fused statistics additionally writes out = [relu](BN(y)) -- normalised from the
+ * fp32 TMEM accumulators behind a grid barrier (cooperative launch) -- and publishes bnp.  Returns 1 if the plan was
+ * switched (then no basi_bn_apply is needed for this layer), 0 if the layer cannot be fused. */
+int basi_tc_conv_set_bn_apply(basi_tc_conv* plan, const basi_tensor* out, int relu);
 int basi_tc_conv_run(basi_tc_conv* plan, void* stream);
 void basi_tc_conv_destroy(basi_tc_conv* plan);
 

@@ -105,7 +105,7 @@ SIGNATURES = {
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
-            "basi_tc_conv_destroy": ([_P], None), "basi_tc_split_kcols": ([_i], _i),
+            "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i), "basi_tc_split_kcols": ([_i], _i),
             "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
 
 _lib = None

@@ -131,6 +131,8 @@ class Engine(object):
         self._tc_producer = {}
         self.fuse_bn_stats = fuse_bn_stats
         self.fused_stats = 0
+        self.fuse_bn_apply = not self.dry_run and precision != "f32" and not _exp_env("BASI_NO_FUSED_APPLY")
+        self.fused_apply = 0
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.mask_bits = not _exp_env("BASI_NO_MASK_BITS")
         # (the fused pyramid pooling accumulates with fp32 atomics: order noise of one ulp, which float32 storage keeps
@@ -149,6 +151,8 @@ class Engine(object):
         self._lower()
         if training:
             self._emit_backward()
+        if self.fused_apply >= 40:
+            self.storage_policy = "fused"      # most BN inputs are never rounded: normalised from the accumulators
 
     # ------------------------------------------------------------------ parameters
     def _build_params(self):
@@ -400,6 +404,13 @@ class Engine(object):
         self._emit_bn_stats(rec)
         op = dict(main=rec, res=None, res_bn=None, relu=relu, out=out)
         self._ops.append(("bnact", op))
+        prod = self._tc_producer.get(id(rec.x))
+        if (prod is not None and self.fuse_bn_stats and self.fuse_bn_apply and not prod.get("split")
+                and _lib.load().basi_tc_conv_set_bn_apply(prod["tc_fprop"], out.ref, 1 if relu else 0) == 1):
+            # conv -> statistics -> grid barrier -> normalise + ReLU from the fp32 TMEM accumulators, one launch
+            op["fused_apply"] = True
+            self.fused_apply += 1
+            return
         self._emit_bnact_fwd(op)
 
     def _lower_relu(self, n):

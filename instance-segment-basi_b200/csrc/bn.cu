@@ -849,23 +849,6 @@ struct ResidentArgs {
                        // coefficients ready, end) into g_resident_dbg
 };
 
-__device__ __forceinline__ void grid_barrier_thread0(unsigned int* ctr) {
-  __threadfence();
-  const unsigned int old = atomicAdd(ctr, 1u);
-  const unsigned int target = (old / gridDim.x + 1u) * gridDim.x;
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if ((int)(v - target) >= 0) break;
-    if (clock64() - t0 > 8000000000LL) {
-      printf("basi: grid barrier timed out (block %d, counter %u, target %u)\n", blockIdx.x, v, target);
-      __trap();
-    }
-  }
-  __threadfence();
-}
-
 __device__ unsigned long long g_resident_dbg[8];
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;

@@ -173,6 +173,12 @@ struct ConvParams {
   // k-steps that each start a fresh TMEM accumulator; the epilogue warps add every finished group into fp32
   // registers (round to nearest).  All small k-steps (cross terms, 2^-8 .. 2^-16 of the result) form the first group.
   int big_chunks, group_steps;
+  // fused BN apply (bf16 mode): every accumulator of this CTA stays in TMEM (fresh columns per work item), the
+  // statistics are flushed, the grid meets at a barrier on bn_counter (cooperative launch), every CTA derives
+  // scale / shift of its channel tile from the final sums and a second epilogue pass writes
+  // relu(scale * acc + shift) -- normalised from the fp32 accumulators -- through mapD2.  Removes the separate
+  // bn_apply launch, one read pass over the conv output and one rounding per layer.
+  int fuse_apply, apply_relu;
   // source coordinate of tap (r,s) for destination pixel p: p*1 + off0 + r*step (fprop: off0=-pad, step=dil;
   // dgrad: off0=+pad, step=-dil)
   int off_h, off_w, step;
@@ -259,7 +265,7 @@ __device__ __forceinline__ int group_end(const ConvParams& p, int gs, int ksteps
 template <int BN, int CL, int MT, int VAR, bool OUT32 = false>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapD, const ConvParams p) {
+               const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapD2, const ConvParams p) {
   // CL == 2: a CTA pair (tcgen05 cta_group::2).  The two CTAs own adjacent pixel tiles of the same channel tile;
   // each loads its own activation box and HALF of the weight box into its own shared memory, the leader (rank 0)
   // issues ONE M = 256 MMA per K slice that reads both CTAs' shared memory and writes both CTAs' TMEM.  The main
@@ -274,8 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(!HALO || (CL == 1 && MT == 1), "halo mode: one tile per CTA, no pairs");
   constexpr int STAGE = SmemLayout<BN, MT, CL>::STAGE;
   static_assert(CL == 1 || MT == 1, "pairs take one pixel tile per CTA");
-  constexpr uint32_t TMEM_COLS = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
+  constexpr uint32_t TMEM_COLS2 = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
   static_assert(2 * MT * BN <= 512, "TMEM has 512 columns");
+  const uint32_t TMEM_COLS = p.fuse_apply ? 512u : TMEM_COLS2;   // fused apply: one accumulator per work item
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base slot
@@ -297,6 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD) : "memory");
+    if (p.fuse_apply) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD2) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -512,10 +520,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && lane == 0;
         long long m0 = dbg ? dbg_clock() : 0;
-        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+        if (!p.fuse_apply) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        const uint32_t d_tmem = tmem_base + (p.fuse_apply ? it : acc) * (MT * BN);
         const int ks0 = gs;
         for (int ks = ks0; ks < ge; ++ks) {
           if (dbg) m0 = dbg_clock();
@@ -624,7 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (dbg) g_tc_dbg[2] += dbg_clock() - w0c;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + sub * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (p.fuse_apply ? it : acc) * (MT * BN) + sub * BN;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         if ((c & 1) != half && BN >= 64) continue;
@@ -666,7 +674,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (!OUT32 && lane == 0 && sub == MT - 1) {                       // TMEM accumulator is free again
+      if (!OUT32 && !p.fuse_apply && lane == 0 && sub == MT - 1) {      // TMEM accumulator is free again
         if (CL == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));
         else mbar_arrive(tempty0 + 8 * acc);
       }
@@ -773,6 +781,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       atomicAdd(rep + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund1 : (double)run1);
       atomicAdd(rep + p.Cdst + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund2 : (double)run2);
     }
+    if constexpr (!OUT32 && CL == 1 && VAR == 0) {
+      if (p.fuse_apply) {
+        // ---- grid barrier: every CTA's statistics are in the global sums
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 128) grid_barrier_thread0(p.bn_counter);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- second pass: y = relu(scale * acc + shift) straight from the fp32 accumulators
+        const int te = (int)threadIdx.x - 128;
+        float* sc_s = stat_s;              // [BN] scale, [BN] shift of the current channel tile
+        int it2 = 0, cur_nt = -1;
+        for (int t = cid; t < total_tiles; t += ncl, ++it2) {
+          const int nt = t % p.n_tiles;
+          if (nt != cur_nt) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // the previous tile's readers of sc_s are done
+            if (te < BN) {
+              const int C = p.Cdst, c = nt * BN + te;
+              double s1 = 0, s2 = 0;
+#pragma unroll
+              for (int r = 0; r < BASI_BN_REPLICAS; ++r) {
+                s1 += __ldcg(p.bn_sums + (size_t)r * 2 * C + c);
+                s2 += __ldcg(p.bn_sums + (size_t)r * 2 * C + C + c);
+              }
+              const double mean = s1 / p.bn_count;
+              double var = s2 / p.bn_count - mean * mean;
+              if (var < 0) var = 0;
+              const double istd = 1.0 / sqrt(var + (double)p.bn_eps);
+              const float g = p.bn_gamma[c], b = p.bn_beta[c];
+              const float scl = (float)((double)g * istd);
+              sc_s[te] = scl;
+              sc_s[BN + te] = (float)((double)b - mean * (double)g * istd);
+              if (t / p.n_tiles == 0 && p.bn_bnp != nullptr) {     // one CTA per channel tile publishes the parameters
+                p.bn_bnp[c] = (float)mean;
+                p.bn_bnp[C + c] = (float)istd;
+                p.bn_bnp[2 * C + c] = scl;
+                p.bn_bnp[3 * C + c] = b;
+              }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            cur_nt = nt;
+          }
+#pragma unroll 1
+          for (int sub = 0; sub < MT; ++sub, ++sidx) {
+            const int mt = (t / p.n_tiles) * MT + sub;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+            const uint32_t so = so_base + (p.out_bufs == 2 ? (uint32_t)(sidx & 1) * (NBOX * A_BYTES) : 0u);
+            if (issuer) {
+              if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + it2 * (MT * BN) + sub * BN;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+              if ((c & 1) != half && BN >= 64) continue;
+              if (BN < 64 && half != 0) continue;
+              uint32_t r[32];
+              tmem_ld32(taddr + c * 32, r);
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = c * 32 + 2 * j;
+                float v0 = fmaf(__uint_as_float(r[2 * j]), sc_s[col], sc_s[BN + col]);
+                float v1 = fmaf(__uint_as_float(r[2 * j + 1]), sc_s[col + 1], sc_s[BN + col + 1]);
+                if (p.apply_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * (BN >= 64 ? 128 : 2 * BN);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const uint32_t chunk = BN >= 64 ? (uint32_t)(((c & 1) * 4 + v) ^ (row & 7)) : (uint32_t)v;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[4 * v]),
+                             "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                             : "memory");
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (issuer) {
+#pragma unroll
+              for (int j = 0; j < NBOX; ++j) tma_store_4d(&mapD2, so + j * A_BYTES, nt * BN + j * BOXC, w0, h0, n0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+        tc_fence_before();
+      }
+    }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
     if (p.bn_sums != nullptr) __threadfence();
   }
@@ -786,7 +884,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
-  if (p.bn_sums != nullptr && p.bn_bnp != nullptr) {
+  if (p.bn_sums != nullptr && p.bn_bnp != nullptr && !p.fuse_apply) {
     // last CTA to finish turns the sums into the per-channel parameters (fused finalize)
     if (threadIdx.x == 0) {
       const unsigned int t = atomicAdd(p.bn_counter, 1u);
@@ -1180,8 +1278,9 @@ struct basi_tc_conv {
   int mt;        // pixel tiles per work item (1 or 2)
   int gbox;      // wgrad: 64-channel boxes of the output-gradient operand (1 when Cout <= 64)
   int split;     // split-operand (fp32-grade) mode: bf16 [hi|mid|lo] operands, float32 destination
-  CUtensorMap mapA, mapB, mapD;
+  CUtensorMap mapA, mapB, mapD, mapD2;
   ConvParams cp;
+  int TW, TH, TN;   // pixel tile (for the second output map of the fused BN apply)
   WgradParams wp;
   bf16* dst;
   float* dw;
@@ -1246,22 +1345,40 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
         cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr32 = true;
       }
-      basi::launch(conv_tc_kernel<BN, 1, 1, 0, true>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+      basi::launch(conv_tc_kernel<BN, 1, 1, 0, true>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
     }
     return BASI_OK;
   }
   const bool timers = pl->cp.debug == 30;
+  if (pl->cp.fuse_apply) {
+    // grid barrier inside: cooperative launch (all CTAs co-resident; grid <= #SMs at one CTA per SM)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pl->mt == 2 && BN <= 128)
+      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BNS, 1, 2, 0>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+    else
+      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 1, 0>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+    return BASI_OK;
+  }
   if (pl->cp.halo && BN <= 128)
-    basi::launch(conv_tc_kernel<BNS, 1, 1, 1>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    basi::launch(conv_tc_kernel<BNS, 1, 1, 1>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
   else if (pl->mt == 2 && BN <= 128) {
-    if (timers) basi::launch(conv_tc_kernel<BNS, 1, 2, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
-    else basi::launch(conv_tc_kernel<BNS, 1, 2, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    if (timers) basi::launch(conv_tc_kernel<BNS, 1, 2, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+    else basi::launch(conv_tc_kernel<BNS, 1, 2, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
   } else if (pl->cluster == 2)
-    basi::launch_ex(conv_tc_kernel<BN, 2, 1, 0>, grid, block, pl->smem, st, 2, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    basi::launch_ex(conv_tc_kernel<BN, 2, 1, 0>, grid, block, pl->smem, st, 2, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
   else if (timers)
-    basi::launch(conv_tc_kernel<BN, 1, 1, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    basi::launch(conv_tc_kernel<BN, 1, 1, 2>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
   else
-    basi::launch(conv_tc_kernel<BN, 1, 1, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->cp);
+    basi::launch(conv_tc_kernel<BN, 1, 1, 0>, grid, block, pl->smem, st, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
   return BASI_OK;
 }
 template <int BN>
@@ -1412,6 +1529,8 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
       delete pl;
       return rc;
     }
+    pl->mapD2 = pl->mapD;
+    pl->TW = TW; pl->TH = TH; pl->TN = TN;
     ConvParams& cp = pl->cp;
     cp.TW = TW; cp.TH = TH; cp.TN = TN;
     cp.tiles_w = tiles_w; cp.tiles_h = tiles_h; cp.tiles_n = tiles_n;
@@ -1573,6 +1692,29 @@ int basi_tc_conv_set_bn_stats(basi_tc_conv* pl, double* sums, const float* gamma
   pl->cp.bn_count = count;
   pl->cp.bn_eps = eps;
   return BASI_OK;
+}
+
+/* Fused BN apply for an fprop plan that already has basi_tc_conv_set_bn_stats: the kernel additionally writes
+ * out = [relu](gamma * (y - mean) * istd + beta), normalised from the fp32 accumulators, after a grid barrier.
+ * Returns 1 when the plan was switched to the fused mode, 0 when this layer cannot be fused (accumulators of a CTA's
+ * work items exceed the 512 TMEM columns, CTA pairs, halo mode, fp32 output) -- the caller then runs basi_bn_apply. */
+int basi_tc_conv_set_bn_apply(basi_tc_conv* pl, const basi_tensor* out, int relu) {
+  if (!pl || !out || pl->kind != BASI_TC_FPROP || !pl->cp.bn_sums || !pl->cp.bn_bnp) return 0;
+  if (pl->split || pl->cluster != 1 || pl->cp.halo || pl->cp.accumulate) return 0;
+  if (exp_env("BASI_TC_NO_FUSED_APPLY")) return 0;
+  if (out->dtype != BASI_BF16 || out->c != pl->cp.Cdst || out->n != pl->cp.N || out->h != pl->cp.H || out->w != pl->cp.W)
+    return 0;
+  if (out->ld % 8 || ((uintptr_t)out->ptr & 15)) return 0;
+  const ConvParams& cp = pl->cp;
+  const int items = ((cp.m_tiles + pl->mt - 1) / pl->mt) * cp.n_tiles;
+  if (items <= 0 || pl->grid <= 0) return 0;
+  const int per_cta = (items + pl->grid - 1) / pl->grid;
+  if (per_cta * pl->mt * pl->bn > 512) return 0;
+  if (pl->grid > basi::sm_count()) return 0;
+  if (make_act_map(&pl->mapD2, out, pl->TW, pl->TH, pl->TN, pl->bn >= 64 ? 64 : pl->bn) != BASI_OK) return 0;
+  pl->cp.fuse_apply = 1;
+  pl->cp.apply_relu = relu ? 1 : 0;
+  return 1;
 }
 
 int basi_tc_conv_run(basi_tc_conv* pl, void* stream) {

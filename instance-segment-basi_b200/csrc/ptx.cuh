@@ -56,6 +56,26 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
   return pred != 0;
 }
+// Grid-wide barrier for kernels whose CTAs are all co-resident (cooperative launch): called by ONE thread per CTA,
+// bracketed by CTA-level barriers.  The counter only ever grows (the target is the next multiple of gridDim.x), so it
+// can be reused by the next barrier of the same launch; it must be zero at the first launch of a step.
+__device__ __forceinline__ void grid_barrier_thread0(unsigned int* ctr) {
+  __threadfence();
+  const unsigned int old = atomicAdd(ctr, 1u);
+  const unsigned int target = (old / gridDim.x + 1u) * gridDim.x;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (clock64() - t0 > 8000000000LL) {
+      printf("basi: grid barrier timed out (block %d, counter %u, target %u)\n", blockIdx.x, v, target);
+      __trap();
+    }
+  }
+  __threadfence();
+}
+
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 }  // namespace basi

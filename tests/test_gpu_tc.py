@@ -325,3 +325,62 @@ def test_tc_split_fprop_fused_bn_statistics(case):
     assert rel_err(got[cout:2 * cout], istd) < 1e-4
     assert rel_err(got[2 * cout:3 * cout], r["gamma"] * istd) < 1e-4
     assert np.array_equal(got[3 * cout:], r["beta"])
+
+
+@pytest.mark.parametrize("relu", [1, 0])
+@pytest.mark.parametrize("case", [(3, 2, 128, 128, 40, 40, 16), (1, 1, 512, 128, 40, 40, 16), (1, 1, 64, 32, 80, 80, 16),
+                                  (3, 1, 32, 32, 80, 80, 3), (1, 1, 1024, 256, 40, 40, 16), (1, 1, 1024, 256, 2, 2, 16),
+                                  (3, 1, 64, 64, 40, 40, 16)],
+                         ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_fprop_fused_bn_apply(case, relu):
+    """conv -> statistics -> grid barrier -> BN apply (+ReLU) from the fp32 TMEM accumulators, one cooperative launch
+    (basi_tc_conv_set_bn_apply): the raw output, the published parameters and the activated output must match a
+    float64 batch-norm of the float64 convolution within bf16 storage rounding."""
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    from basi_b200.engine import Act
+    from gpu_util import bf16_round, call, dev, host, rel_err
+    k, d, cin, cout, H, W, B = case
+    rng = np.random.RandomState(5)
+    x = bf16_round(rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32) + 0.3)
+    w = bf16_round((rng.uniform(-1, 1, (k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32))
+    gamma, beta = rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.uniform(-1, 1, cout).astype(np.float32)
+    pad = d * (k - 1) // 2
+    desc = ConvDesc(k, k, 1, d, pad, pad, 0)
+    bt = torch.bfloat16
+    xa = Act(torch.from_numpy(x).to("cuda:0").to(bt).contiguous())
+    ya = Act(torch.zeros((B, H, W, cout), dtype=bt, device="cuda:0"))
+    oa = Act(torch.full((B, H, W, cout), 7.0, dtype=bt, device="cuda:0"))
+    wd, gd, bd = dev(w), dev(gamma), dev(beta)
+    w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    call("basi_tc_pack_weights", wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout)
+    sums = torch.zeros(2 * cout * 8, dtype=torch.float64, device="cuda:0")
+    bnp = torch.zeros(4 * cout, device="cuda:0")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create", 0, C.byref(desc), xa.ref, ya.ref, w_oi.data_ptr(), None, 0, C.byref(h))
+    R = float(B * H * W)
+    _lib.call("basi_tc_conv_set_bn_stats", h, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R),
+              C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
+    fused = _lib.load().basi_tc_conv_set_bn_apply(h, oa.ref, relu)
+    assert fused == 1, "this shape must take the fused path"
+    for rep in range(2):          # twice: the barrier counter keeps counting within a step, sums are re-zeroed
+        sums.zero_()
+        call("basi_tc_conv_run", h)
+    torch.cuda.synchronize()
+    y, out, got = host(ya).astype(np.float64), host(oa).astype(np.float64), host(bnp)
+    _lib.load().basi_tc_conv_destroy(h)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    yref = O.conv2d(xt, torch.from_numpy(w).double(), 1, pad, d).permute(0, 2, 3, 1).numpy()
+    assert rel_err(y, yref) < 1e-2
+    yr = yref.reshape(-1, cout)
+    mean, var = yr.mean(0), yr.var(0)
+    istd = 1 / np.sqrt(var + 1e-5)
+    assert np.max(np.abs(got[:cout] - mean)) < 5e-3 * max(1.0, np.max(np.abs(mean)))
+    assert rel_err(got[cout:2 * cout], istd) < 1e-2
+    ref = (yref - mean) * istd * gamma + beta
+    if relu:
+        ref = np.maximum(ref, 0)
+    assert rel_err(out, ref) < 1.5e-2, rel_err(out, ref)
+    assert not np.any(out == 7.0)                                   # every element was written
