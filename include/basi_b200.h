@@ -68,6 +68,23 @@ int basi_version(void);
 int basi_sm_count(void);
 int basi_memset(void* ptr, int value, int64_t bytes, void* stream);
 
+/* ---- A3 / F3: label encodings and click sampling on the device (integer work, bit-exact) ----
+ * ann: uint8 [B][per_image] instance-id maps at P x P (0 background, 255 border, k instance k); nums[b]: the attended
+ * instance.  mode 0 binary (back/2AddClass/BAISData.py:150-151); mode 1 the 4-class border encoding with its uint8
+ * wrap-around (back/4BorderClass/BAISData.py:143-160, has_255=True: 0 other, 1 attention, 2 border, 3 background);
+ * mode 2 the 3-class encoding (same file, has_255=False); mode 3 COCO (back/5COCO/BAISData.py:361-369: ann = uint8 sum
+ * of all instance masks, attention = the attended mask: 0 background, 1 other, 2 attention).  Writes int32 and / or
+ * float32 labels (either pointer may be NULL). */
+int basi_label_encode(const uint8_t* ann, const uint8_t* attention, const int32_t* nums, int mode, int32_t* out_i32,
+                      float* out_f32, int B, int64_t per_image, void* stream);
+/* Click sampling (back/2AddClass/BAISData.py:63-66: where = np.argwhere(ann == 1); where[np.random.randint(0, len)] * ratio):
+ * basi_click_count gives len(where) per image (the host draws k with the reference's own RNG call),
+ * basi_click_select writes ratio * (row, col) of the k-th matching pixel in row-major order. */
+int basi_click_count(const void* labels, int labels_are_f32, int target, int B, int per_image, int32_t* counts,
+                     void* stream);
+int basi_click_select(const void* labels, int labels_are_f32, int target, int B, int H, int W, const int32_t* k,
+                      int ratio, int32_t* clicks, void* stream);
+
 /* ---- A1/A2: Data._mask_gaussian + np.concatenate (back/2AddClass/BAISData.py:189-202, :79-80) ----
  * img: uint8 [B,H,W,3] (img_is_f32 = 0) or float32 [B,H,W,3] already /255 (img_is_f32 = 1).
  * clicks: int32 [B][2] = (y0, x0).  lut: float32 table indexed by d2 = (x-x0)^2 + (y-y0)^2,
@@ -291,6 +308,14 @@ int basi_tc_conv_set_bn_stats(basi_tc_conv* plan, double* sums, const float* gam
  * fp32 TMEM accumulators behind a grid barrier (cooperative launch) -- and publishes bnp.  Returns 1 if the plan was
  * switched (then no basi_bn_apply is needed for this layer), 0 if the layer cannot be fused. */
 int basi_tc_conv_set_bn_apply(basi_tc_conv* plan, const basi_tensor* out, int relu);
+/* A6 backward fused into the A4/A5 input adjoint: a dgrad plan whose destination dx is the gradient wrt the raw conv
+ * output x of the BN(+ReLU) layer feeding this convolution computes dA in TMEM, reduces sum(g) and sum(g * xhat) (mask
+ * recomputed from x), meets the grid at a barrier (cooperative launch) and writes dx = BN'(dA); dgamma / dbeta are
+ * added into their slots.  bnp = [mean | istd | gamma*istd | beta] of that layer, dsums = [BASI_BN_REPLICAS][2C]
+ * doubles and *counter zero at the start of a step.  Returns 1 if the plan was switched (then no basi_bn_bwd_* call is
+ * needed for that layer), 0 if it cannot be fused. */
+int basi_tc_conv_set_bn_bwd(basi_tc_conv* plan, const basi_tensor* x, const float* bnp, int relu, double* dsums,
+                            double count, float* dgamma, float* dbeta, uint32_t* counter);
 int basi_tc_conv_run(basi_tc_conv* plan, void* stream);
 void basi_tc_conv_destroy(basi_tc_conv* plan);
 

@@ -43,6 +43,9 @@ _i, _i64, _f, _d = C.c_int, C.c_int64, C.c_float, C.c_double
 # name -> argtypes.  Every symbol include/basi_b200.h declares is listed here; tests check the two agree.
 SIGNATURES = {
     "basi_memset": [_P, _i, _i64, _P],
+    "basi_label_encode": [_P, _P, _P, _i, _P, _P, _i, _i64, _P],
+    "basi_click_count": [_P, _i, _i, _i, _i, _P, _P],
+    "basi_click_select": [_P, _i, _i, _i, _i, _i, _P, _i, _P, _P],
     "basi_clickmap_pack": [_P, _i, _P, _P, _i64, _P, _i, _i, _i, _P],
     "basi_conv_fprop": [_DP, _TP, _P, _P, _TP, _P],
     "basi_conv_dgrad": [_DP, _TP, _P, _TP, _i, _P],
@@ -105,7 +108,8 @@ SIGNATURES = {
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
-            "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i), "basi_tc_split_kcols": ([_i], _i),
+            "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i),
+            "basi_tc_conv_set_bn_bwd": ([_P, _TP, _P, _i, _P, _d, _P, _P, _P], _i), "basi_tc_split_kcols": ([_i], _i),
             "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
 
 _lib = None

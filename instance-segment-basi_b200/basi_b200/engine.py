@@ -113,6 +113,12 @@ class Engine(object):
         # tcgen05 MMAs per product, fp32 TMEM accumulation) -- the reference's precision on the Blackwell-native path
         self.split_tc = self.use_tc and precision == "f32"
         self._split_cache = {}
+        self._bnact_of = {}
+        # dgrad + BN backward in one cooperative launch (basi_tc_conv_set_bn_bwd): correct and tested, but measured
+        # SLOWER than the separate resident BN-backward kernel (10.28 vs 9.09 ms/step: the two extra passes run on the
+        # 8 epilogue warps of a one-CTA-per-SM kernel) -- opt-in experiment, BASI_FUSED_BWD=1
+        self.fuse_bn_dgrad = not self.dry_run and precision != "f32" and _exp_env("BASI_FUSED_BWD") == "1"
+        self.fused_bn_dgrad = 0
         self.fwd, self.bwd, self.pre = [], [], []
         self._keep = []          # ctypes objects that must outlive the plan
         self._ops = []
@@ -404,6 +410,8 @@ class Engine(object):
         self._emit_bn_stats(rec)
         op = dict(main=rec, res=None, res_bn=None, relu=relu, out=out)
         self._ops.append(("bnact", op))
+        outnode = followers[0] if (len(followers) == 1 and followers[0].op == "relu") else n
+        self._bnact_of[id(out)] = (op, len(self._cons[outnode.index]))     # for the fused BN backward (see _bwd_conv)
         prod = self._tc_producer.get(id(rec.x))
         if (prod is not None and self.fuse_bn_stats and self.fuse_bn_apply and not prod.get("split")
                 and _lib.load().basi_tc_conv_set_bn_apply(prod["tc_fprop"], out.ref, 1 if relu else 0) == 1):
@@ -725,6 +733,10 @@ class Engine(object):
                        self._gptr(op["b"]) if op["b"] else None, flops=self._conv_flops(op),
                        writes=[op["w"]] + ([op["b"]] if op["b"] else []), side=True)
         if need_dx:
+            if (tc_ok and self.fuse_bn_dgrad and not x.gw and id(x) in self._bnact_of
+                    and lib.basi_tc_conv_supported(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1
+                    and self._try_fused_bn_dgrad(op)):
+                return
             acc = self._acc_flag(x)
             if tc_ok and lib.basi_tc_conv_supported(_lib.TC_DGRAD, dptr, x.ref, y.ref) == 1:
                 self._emit_tc(op, _lib.TC_DGRAD, self.bwd, acc)
@@ -732,7 +744,44 @@ class Engine(object):
                 self._call(self.bwd, "basi_conv_dgrad", dptr, dy.ref, self._pptr(op["w"]), x.grad.ref, acc,
                            flops=self._conv_flops(op))
 
+    def _try_fused_bn_dgrad(self, op):
+        """dgrad of this convolution + the whole BN(+ReLU) backward of the layer that produced its input, one
+        cooperative tcgen05 launch (basi_tc_conv_set_bn_bwd): the destination is the gradient wrt that layer's RAW
+        conv output, the gradient wrt the activated tensor never exists in memory."""
+        lib = _lib.load()
+        x = op["x"]
+        bn_op, n_cons = self._bnact_of[id(x)]
+        if n_cons != 1 or bn_op["res"] is not None or bn_op["res_bn"] is not None:
+            return False
+        rec = bn_op["main"]
+        if rec.x.gw or rec.x.dtype != _lib.BF16 or rec.x.shape != x.shape:
+            return False
+        dxl = self._grad_of(rec.x)
+        handle = C.c_void_p()
+        if "w_io" not in op:
+            return False
+        _lib.call("basi_tc_conv_create", _lib.TC_DGRAD, C.byref(op["desc"]), op["y"].grad.ref, dxl.ref,
+                  op["w_io"].data_ptr(), None, 0, C.byref(handle))
+        self._tc_plans.append(handle)
+        ok = lib.basi_tc_conv_set_bn_bwd(handle, rec.x.ref, rec.bnp.data_ptr(), 1 if bn_op["relu"] else 0, rec.dsums,
+                                         C.c_double(rec.count), self._gptr(rec.gamma), self._gptr(rec.beta), rec.cnt_b)
+        if ok != 1:
+            return False
+        rec.x.gw = True
+        x.gw = True
+        bn_op["bwd_fused"] = True
+        self.fused_bn_dgrad += 1
+        self.tc_layers += 1
+        meta = dict(flops=self._conv_flops(op), layer=op["name"], writes=[rec.gamma, rec.beta],
+                    bytes_bn=self._nbytes(rec.x) * 2)
+        if getattr(self, "_cur_branch", None) is not None:
+            meta["branch"] = self._cur_branch
+        self.bwd.append(("basi_tc_conv_run:%d" % _lib.TC_DGRAD, lib.basi_tc_conv_run, (handle,), meta))
+        return True
+
     def _bwd_bnact(self, op):
+        if op.get("bwd_fused"):
+            return                         # done inside the consumer's dgrad kernel
         out = op["out"]
         dout = out.grad
         assert dout is not None and out.gw
@@ -1017,6 +1066,51 @@ class Engine(object):
         self.pre = []
         self._call(self.pre, "basi_clickmap_pack", self.img_u8.data_ptr(), 0, self.clicks_dev.data_ptr(),
                    self.lut_dev.data_ptr(), C.c_int64(lut.size), self.input.t.data_ptr(), B, H, W)
+
+    LABEL_MODES = {"binary": 0, "border": 1, "three": 2, "coco": 3}
+
+    def enable_label_input(self, encoding="binary", target=None, ratio=8):
+        """Device-side label decode + click sampling (A3 / F3): uint8 instance-id maps at P x P in, the encoded
+        segment labels and the sampled clicks out (basi_label_encode, basi_click_count / _select)."""
+        B, P_h, P_w, _ = self.label_seg.shape
+        self._lab_mode = self.LABEL_MODES[encoding]
+        self._lab_target = (2 if encoding == "coco" else 1) if target is None else int(target)
+        self._lab_ratio = int(ratio)
+        self.ann_u8 = self._zeros((B, P_h, P_w), torch.uint8)
+        self.att_u8 = self._zeros((B, P_h, P_w), torch.uint8) if encoding == "coco" else None
+        self.nums_dev = self._zeros((B,), torch.int32)
+        self.counts_dev = self._zeros((B,), torch.int32)
+        self.k_dev = self._zeros((B,), torch.int32)
+
+    def feed_annotations(self, ann_u8, nums=None, attention_u8=None, rng=None):
+        """ann_u8: [B,P,P] uint8 instance-id maps (COCO: uint8 sum of the instance masks), nums: attended instance per
+        image (COCO: attention_u8 masks instead).  Encodes the labels on the device, then samples one click per image
+        exactly like the reference: k = rng.randint(0, len(np.argwhere(label == target))) drawn on the host in batch
+        order (np.random by default), the k-th matching pixel (row-major) times the ratio selected on the device."""
+        rng = np.random if rng is None else rng
+        st = self._stream()
+        B, P_h, P_w, _ = self.label_seg.shape
+        self.ann_u8.copy_(_as_tensor(ann_u8, torch.uint8).view(self.ann_u8.shape), non_blocking=True)
+        if self.att_u8 is not None:
+            self.att_u8.copy_(_as_tensor(attention_u8, torch.uint8).view(self.att_u8.shape), non_blocking=True)
+        else:
+            self.nums_dev.copy_(_as_tensor(nums, torch.int32).view(self.nums_dev.shape), non_blocking=True)
+        f32 = self.label_seg.dtype == torch.float32
+        _lib.call("basi_label_encode", self.ann_u8.data_ptr(),
+                  self.att_u8.data_ptr() if self.att_u8 is not None else None,
+                  None if self.att_u8 is not None else self.nums_dev.data_ptr(), self._lab_mode,
+                  None if f32 else self.label_seg.data_ptr(), self.label_seg.data_ptr() if f32 else None,
+                  B, C.c_int64(P_h * P_w), st)
+        _lib.call("basi_click_count", self.label_seg.data_ptr(), 1 if f32 else 0, self._lab_target, B, P_h * P_w,
+                  self.counts_dev.data_ptr(), st)
+        counts = self.counts_dev.cpu().numpy()
+        if np.any(counts <= 0):
+            raise ValueError("feed_annotations: an image has no pixel of the attended instance")
+        k = np.asarray([rng.randint(0, int(c)) for c in counts], dtype=np.int32)
+        self.k_dev.copy_(torch.from_numpy(k), non_blocking=True)
+        _lib.call("basi_click_select", self.label_seg.data_ptr(), 1 if f32 else 0, self._lab_target, B, P_h, P_w,
+                  self.k_dev.data_ptr(), self._lab_ratio, self.clicks_dev.data_ptr(), st)
+        return k
 
     def feed_clicks(self, images_u8, clicks):
         self.img_u8.copy_(_as_tensor(images_u8, torch.uint8).view(self.img_u8.shape), non_blocking=True)

@@ -881,6 +881,7 @@ bn_bwd_resident_kernel(const ResidentArgs a, const float* __restrict__ bnp, int 
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_prologue();     // launched with the cooperative AND the programmatic-serialization attribute (see launch site)
   if (tid == 0) {
     for (int k = 0; k < a.n_chunks; ++k) {
       const int r0 = k * a.chunk_rows;
@@ -1014,6 +1015,7 @@ bn_bwd_coop_kernel(const StreamArgs a1, const StreamArgs a2, const float* __rest
   constexpr int NT2 = NT1 + (DRES_ACC ? 1 : 0);
   const int c0 = threadIdx.x * VN;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  pdl_prologue();     // cooperative + programmatic-serialization launch: the launch latency overlaps the predecessor
   float mean[VN], A[VN], beta[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
@@ -1175,11 +1177,13 @@ static bool launch_bwd_coop(bool dry, const basi_tensor* dout, const basi_tensor
   cfg.blockDim = g1.block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (pdl_enabled() && !(exp_env("BASI_BN_COOP_PDL") && atoi(exp_env("BASI_BN_COOP_PDL")) == 0)) ? 2 : 1;
 #define BASI_LAUNCH_COOP(MK, DA)                                                                                      \
   do {                                                                                                                \
     allow_smem(bn_bwd_coop_kernel<T, MK, DA>, smem);                                                                  \
@@ -1263,11 +1267,16 @@ static void launch_bwd_resident(const ResidentGeom& g, const basi_tensor* dout, 
   cfg.blockDim = dim3(g.bx, g.by);
   cfg.dynamicSmemBytes = g.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
+  // ... and programmatic dependent launch on top: the prologue (barrier init, launch latency) overlaps the tail of
+  // the producing dgrad kernel; the kernel touches nothing before its griddepcontrol.wait (BASI_BN_COOP_PDL=0: off)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  const bool coop_pdl = pdl_enabled() && !(exp_env("BASI_BN_COOP_PDL") && atoi(exp_env("BASI_BN_COOP_PDL")) == 0);
   cfg.attrs = attr;
-  cfg.numAttrs = exp_env("BASI_BN_RESIDENT_NOCOOP") ? 0 : 1;   // experiment only: without the attribute co-residency is not guaranteed
+  cfg.numAttrs = exp_env("BASI_BN_RESIDENT_NOCOOP") ? 0 : (coop_pdl ? 2 : 1);   // (NOCOOP: experiment only)
 #define BASI_LAUNCH_RESIDENT(NT_)                                                                                  \
   do {                                                                                                             \
     allow_smem(bn_bwd_resident_kernel<T, NT_>, g.smem);                                                            \

@@ -14,6 +14,7 @@
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -179,6 +180,20 @@ struct ConvParams {
   // relu(scale * acc + shift) -- normalised from the fp32 accumulators -- through mapD2.  Removes the separate
   // bn_apply launch, one read pass over the conv output and one rounding per layer.
   int fuse_apply, apply_relu;
+  int keep_acc;      // fuse_apply || fuse_bwd: accumulators stay in TMEM (one column block and one barrier per work item)
+  // fused BN backward (dgrad plans): the accumulator is dA, the gradient wrt the activated output of the layer that
+  // produced this plan's destination.  Pass 1 loads the matching tile of that layer's raw conv output x (mapD2),
+  // masks (ReLU recomputed from x) and accumulates sum(g), sum(g * (x - mean)) per channel; grid barrier; pass 2
+  // writes dx = A g - A S1/N - (x - mean) A istd S2/N (A = gamma * istd) to the destination and publishes dgamma /
+  // dbeta.  dA itself never goes to memory, and the cooperative bn_bwd launch of that layer disappears.
+  int fuse_bwd, bwd_relu;
+  int xbuf_off, coef_off, xbar_off;   // byte offsets from the output staging area: x tile buffer, coefficient table, barrier
+  const float* bwd_bnp;      // [mean | istd | gamma*istd | beta]
+  double* bwd_sums;          // [BASI_BN_REPLICAS][2C], zero at the start of a step
+  float* bwd_dgamma;
+  float* bwd_dbeta;
+  double bwd_count;
+  unsigned int* bwd_counter;
   // source coordinate of tap (r,s) for destination pixel p: p*1 + off0 + r*step (fprop: off0=-pad, step=dil;
   // dgrad: off0=+pad, step=-dil)
   int off_h, off_w, step;
@@ -282,14 +297,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(CL == 1 || MT == 1, "pairs take one pixel tile per CTA");
   constexpr uint32_t TMEM_COLS2 = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;
   static_assert(2 * MT * BN <= 512, "TMEM has 512 columns");
-  const uint32_t TMEM_COLS = p.fuse_apply ? 512u : TMEM_COLS2;   // fused apply: one accumulator per work item
+  const uint32_t TMEM_COLS = p.keep_acc ? 512u : TMEM_COLS2;   // fused apply: one accumulator per work item
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes);
-  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  // bars: full[stages], empty[stages], tmem_full[NTF], tmem_empty[2], then the TMEM base slot.  (tmem_full: two are
+  // used in turn by the double-buffered accumulators; the fused-apply mode keeps every accumulator of the CTA and
+  // uses one barrier per work item -- the MMA warp may run several items ahead of the epilogue, and an mbarrier
+  // that completes two phases before it is waited on can no longer be distinguished.)
+  constexpr int NTF = 16;
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
-  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
-  float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // [row groups][2*BN] = 1024 floats
+  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 8 * NTF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + NTF + 2);
+  float* stat_s = reinterpret_cast<float*>(bars + 2 * p.stages + NTF + 4);   // [row groups][2*BN] = 1024 floats
   // output staging for the TMA store: NBOX boxes of [128 px][64 ch] bf16, SWIZZLE_128B, 1024-B aligned
   constexpr int NBOX = OUT32 ? BN / 32 : (BN + 63) / 64;
   constexpr int BOXC = OUT32 ? 32 : 64;      // channels per output box (128-byte rows)
@@ -304,17 +323,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD) : "memory");
-    if (p.fuse_apply) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD2) : "memory");
+    if (p.keep_acc) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD2) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(full0 + 8 * i, 1);    // pair: only the leader's is used (it expects the bytes of both CTAs)
       mbar_init(empty0 + 8 * i, 1);   // pair: the leader's commit is multicast to both CTAs
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull0 + 8 * i, 1);
+    for (int i = 0; i < (p.keep_acc ? NTF : 2); ++i) mbar_init(tfull0 + 8 * i, 1);
+    if (p.fuse_bwd) mbar_init(smem_u32(stage_out) + (uint32_t)p.xbar_off, 1);
+    for (int i = 0; i < 2; ++i)
       mbar_init(tempty0 + 8 * i, 8 * CL);   // one arrive per epilogue warp (pair: of both CTAs, on the leader's)
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2 && p.debug != 11) {
@@ -402,11 +421,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           w0[sub] = tw * p.TW; h0[sub] = th * p.TH; n0[sub] = tn * p.TN;
         }
         {
+          int tap = 0, kc = 0, tr = 0, ts = 0;          // plain mode: tap-major counters, no divisions in the loop
           for (int ks = 0; ks < ksteps; ++ks) {
-            int tap, kc;
-            kstep_coords(p, ks, tap, kc);
-            const int r = tap / p.kw, s = tap - r * p.kw;
-            const int dh = p.off_h + r * p.step, dw = p.off_w + s * p.step;
+            if constexpr (OUT32) {
+              kstep_coords(p, ks, tap, kc);
+              tr = tap / p.kw;
+              ts = tap - tr * p.kw;
+            }
+            const int dh = p.off_h + tr * p.step, dw = p.off_w + ts * p.step;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE);
             const int ac = kc >= p.a_wrap1 ? kc - p.a_wrap1 : (kc >= p.a_wrap0 ? kc - p.a_wrap0 : kc);
@@ -430,6 +452,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
+            }
+            if constexpr (!OUT32) {
+              if (++kc == p.k_chunks) {
+                kc = 0;
+                ++tap;
+                if (++ts == p.kw) { ts = 0; ++tr; }
+              }
             }
           }
         }
@@ -520,10 +549,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         const bool dbg = TIMERS && p.debug == 30 && blockIdx.x == 0 && lane == 0;
         long long m0 = dbg ? dbg_clock() : 0;
-        if (!p.fuse_apply) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+        if (!p.keep_acc) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
         if (dbg) { const long long m1 = dbg_clock(); g_tc_dbg[4] += m1 - m0; m0 = m1; }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (p.fuse_apply ? it : acc) * (MT * BN);
+        const uint32_t d_tmem = tmem_base + (p.keep_acc ? it : acc) * (MT * BN);
         const int ks0 = gs;
         for (int ks = ks0; ks < ge; ++ks) {
           if (dbg) m0 = dbg_clock();
@@ -556,7 +585,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // accumulator complete -> epilogue (pair: of both CTAs)
         if (elect_one()) {
           if (CL == 2) umma_commit_pair(tfull0 + 8 * acc, (uint16_t)3);
-          else umma_commit(tfull0 + 8 * acc);
+          else umma_commit(tfull0 + 8 * (p.keep_acc ? it : acc));
         }
         __syncwarp();
         gs = ge;
@@ -575,7 +604,183 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int run_nt = -1;              // fused statistics: channel tile of the running sums below
     float run1 = 0.f, run2 = 0.f;
     double rund1 = 0.0, rund2 = 0.0;   // (fp32-output mode keeps the running sums in double)
-    for (int t = cid; t < total_tiles; t += ncl, ++it) {
+    bool bwd_done = false;
+    if constexpr (!OUT32 && CL == 1 && VAR == 0) {
+      if (p.fuse_bwd) {
+        // =============== dgrad + batch-norm backward of the produced gradient's layer (see ConvParams::fuse_bwd) ====
+        bwd_done = true;
+        const int te = (int)threadIdx.x - 128;
+        const uint32_t so = so_base;                                     // one staging buffer [NBOX][128 px][64 ch]
+        const uint32_t xb = so_base + (uint32_t)p.xbuf_off;              // the x tile, same layout (TMA, SWIZZLE_128B)
+        float* cf = reinterpret_cast<float*>(stage_out + p.coef_off);    // [5][BN] per-channel coefficients
+        const uint32_t xbar = so_base + (uint32_t)p.xbar_off;
+        uint32_t xphase = 0;
+        const int C = p.Cdst;
+        constexpr int CP = BN / 2, RG = 256 / CP, RPG = BM / RG;
+        const int cp = te % CP, rg = te / CP;
+        // ---- per (work item, sub tile): x tile -> mask -> g = dA * mask (bf16, staged) -> column sums
+        for (int pass = 0; pass < 2; ++pass) {
+          int itb = 0, cur_nt = -1;
+          for (int t = cid; t < total_tiles; t += ncl, ++itb) {
+            const int nt = t % p.n_tiles;
+            if (nt != cur_nt) {
+              asm volatile("bar.sync 1, 256;" ::: "memory");             // readers of the previous table are done
+              if (te < BN) {
+                const int c = nt * BN + te;
+                const float mean = p.bwd_bnp[c], istd = p.bwd_bnp[C + c], A = p.bwd_bnp[2 * C + c];
+                cf[te] = mean;
+                cf[BN + te] = A;
+                cf[2 * BN + te] = p.bwd_bnp[3 * C + c];
+                if (pass == 1) {
+                  double s1 = 0, s2 = 0;
+#pragma unroll
+                  for (int r = 0; r < BASI_BN_REPLICAS; ++r) {
+                    s1 += __ldcg(p.bwd_sums + (size_t)r * 2 * C + c);
+                    s2 += __ldcg(p.bwd_sums + (size_t)r * 2 * C + C + c);
+                  }
+                  cf[3 * BN + te] = A * (float)(s1 / p.bwd_count);                    // Bc
+                  cf[4 * BN + te] = A * istd * (float)(s2 / p.bwd_count);             // Cc
+                  if (t / p.n_tiles == 0) {                                           // one CTA per channel tile
+                    p.bwd_dbeta[c] += (float)s1;
+                    p.bwd_dgamma[c] += (float)s2;
+                  }
+                }
+              }
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              cur_nt = nt;
+            }
+#pragma unroll 1
+            for (int sub = 0; sub < MT; ++sub) {
+              const int mt = (t / p.n_tiles) * MT + sub;
+              const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+              const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+              const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
+              if (issuer) {
+                // (pass 2) the TMA store of the previous tile must have read the staging buffer; then fetch the x tile
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_expect_tx(xbar, BN >= 64 ? NBOX * A_BYTES : BM * 2 * BN);   // (32-channel tiles: 64-byte rows)
+#pragma unroll
+                for (int j = 0; j < NBOX; ++j)
+                  tma_load_4d(xb + j * A_BYTES, &mapD2, xbar, nt * BN + j * BOXC, w0, h0, n0);
+              }
+              if (pass == 0 && sub == 0) {
+                mbar_wait(tfull0 + 8 * itb, 0);
+                tc_fence_after();
+              }
+              asm volatile("bar.sync 1, 256;" ::: "memory");             // staging buffer free (issuer waited)
+              mbar_wait(xbar, xphase);
+              xphase ^= 1;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + itb * (MT * BN) + sub * BN;
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c) {
+                if ((c & 1) != half && BN >= 64) continue;
+                if (BN < 64 && half != 0) continue;
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                const uint32_t xline = xb + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * (BN >= 64 ? 128 : 2 * BN);
+                const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * (BN >= 64 ? 128 : 2 * BN);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                  const uint32_t chunk = BN >= 64 ? (uint32_t)(((c & 1) * 4 + v) ^ (row & 7)) : (uint32_t)v;
+                  uint32_t xw[4], pk[4];
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xw[0]), "=r"(xw[1]), "=r"(xw[2]), "=r"(xw[3])
+                               : "r"(xline + chunk * 16));
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int col = c * 32 + v * 8 + 2 * e;
+                    float res[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      const float xv = __uint_as_float(h ? (xw[e] & 0xffff0000u) : (xw[e] << 16));
+                      const float xc = xv - cf[col + h];
+                      float g = __uint_as_float(r[v * 8 + 2 * e + h]);
+                      if (!valid) g = 0.f;
+                      if (p.bwd_relu) g = fmaf(xc, cf[BN + col + h], cf[2 * BN + col + h]) > 0.f ? g : 0.f;
+                      res[h] = pass == 0 ? g : fmaf(cf[BN + col + h], g, -cf[3 * BN + col + h]) - xc * cf[4 * BN + col + h];
+                    }
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(res[0], res[1]);
+                    pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[0]), "r"(pk[1]),
+                               "r"(pk[2]), "r"(pk[3])
+                               : "memory");
+                }
+              }
+              if (pass == 1) {
+                tc_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (issuer) {
+#pragma unroll
+                  for (int j = 0; j < NBOX; ++j) {
+                    if (p.accumulate) tma_reduce_add_4d(&mapD, so + j * A_BYTES, nt * BN + j * BOXC, w0, h0, n0);
+                    else tma_store_4d(&mapD, so + j * A_BYTES, nt * BN + j * BOXC, w0, h0, n0);
+                  }
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+              }
+              asm volatile("bar.sync 1, 256;" ::: "memory");             // g staged
+              // column sums of g and g * (x - mean): thread = (column pair, group of rows), conflict-free word loads
+              float s0 = 0.f, s1v = 0.f, q0 = 0.f, q1 = 0.f;
+              {
+                const uint32_t colb = (BN >= 64 ? (uint32_t)(cp >> 5) * A_BYTES : 0u);
+                const float m0 = cf[2 * cp], m1 = cf[2 * cp + 1];
+#pragma unroll 8
+                for (int r = rg * RPG; r < (rg + 1) * RPG; ++r) {
+                  const uint32_t off = BN >= 64 ? colb + (uint32_t)r * 128 + (uint32_t)((((cp & 31) >> 2) ^ (r & 7)) << 4) +
+                                                      (uint32_t)(cp & 3) * 4
+                                                : (uint32_t)r * (2 * BN) + (uint32_t)cp * 4;
+                  uint32_t wg, wx;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wg) : "r"(so + off));
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wx) : "r"(xb + off));
+                  const float ga = __uint_as_float(wg << 16), gb = __uint_as_float(wg & 0xffff0000u);
+                  const float xa = __uint_as_float(wx << 16) - m0, xbv = __uint_as_float(wx & 0xffff0000u) - m1;
+                  s0 += ga; q0 = fmaf(ga, xa, q0);
+                  s1v += gb; q1 = fmaf(gb, xbv, q1);
+                }
+              }
+              stat_s[rg * (2 * BN) + 2 * cp] = s0;
+              stat_s[rg * (2 * BN) + 2 * cp + 1] = s1v;
+              stat_s[rg * (2 * BN) + BN + 2 * cp] = q0;
+              stat_s[rg * (2 * BN) + BN + 2 * cp + 1] = q1;
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+              if (te < BN) {
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int g2 = 0; g2 < RG; ++g2) {
+                  t1 += stat_s[g2 * (2 * BN) + te];
+                  t2 += stat_s[g2 * (2 * BN) + BN + te];
+                }
+                if (nt != run_nt) {
+                  if (run_nt >= 0) {
+                    double* rep = p.bwd_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * C;
+                    atomicAdd(rep + run_nt * BN + te, (double)run1);
+                    atomicAdd(rep + C + run_nt * BN + te, (double)run2 * (double)p.bwd_bnp[C + run_nt * BN + te]);
+                  }
+                  run_nt = nt; run1 = 0.f; run2 = 0.f;
+                }
+                run1 += t1;
+                run2 += t2;
+              }
+            }
+          }
+          if (pass == 0) {
+            if (run_nt >= 0 && te < BN) {
+              double* rep = p.bwd_sums + (size_t)(cid % BASI_BN_REPLICAS) * 2 * C;
+              atomicAdd(rep + run_nt * BN + te, (double)run1);
+              atomicAdd(rep + C + run_nt * BN + te, (double)run2 * (double)p.bwd_bnp[C + run_nt * BN + te]);
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 128) grid_barrier_thread0(p.bwd_counter);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+        }
+        tc_fence_before();
+      }
+    }
+    for (int t = cid; t < total_tiles && !bwd_done; t += ncl, ++it) {
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.n_tiles;
@@ -613,7 +818,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         --it;      // (the tile loop increments once more)
       } else {
-        mbar_wait(tfull0 + 8 * acc, acc_phase);
+        if (p.fuse_apply) mbar_wait(tfull0 + 8 * it, 0);     // one barrier per work item, each completes once
+        else mbar_wait(tfull0 + 8 * acc, acc_phase);
         if (dbg) { const long long c1 = dbg_clock(); g_tc_dbg[0] += c1 - c0; g_tc_dbg[1] += 1; c0 = c1; }
         tc_fence_after();
       }
@@ -871,7 +1077,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_before();
       }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
+    // the staging buffers must have been READ before the CTA exits; the writes themselves complete with the grid
+    // (waiting for them here put ~1.5 us of HBM write latency on every launch's tail; BASI_TC_DEBUG_STATS=40: old wait)
+    if (issuer) {
+      if (p.debug == 40) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     if (p.bn_sums != nullptr) __threadfence();
   }
   tc_fence_before();
@@ -1350,18 +1561,32 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     return BASI_OK;
   }
   const bool timers = pl->cp.debug == 30;
-  if (pl->cp.fuse_apply) {
+  if (pl->cp.fuse_apply || pl->cp.fuse_bwd) {
     // grid barrier inside: cooperative launch (all CTAs co-resident; grid <= #SMs at one CTA per SM)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = pl->smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    // BASI_TC_FUSED_LAUNCH (experiment): "coop" cooperative only, "pdl" programmatic dependent launch only (co-residency
+    // then rests on grid <= #SMs at one CTA per SM), "both" (default)
+    const char* mode = exp_env("BASI_TC_FUSED_LAUNCH");
+    const bool want_coop = !mode || strcmp(mode, "pdl") != 0;
+    const bool want_pdl = (!mode || strcmp(mode, "coop") != 0) && pdl_enabled();
+    if (want_coop) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    if (want_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     if (pl->mt == 2 && BN <= 128)
       cudaLaunchKernelEx(&cfg, conv_tc_kernel<BNS, 1, 2, 0>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
     else
@@ -1709,11 +1934,57 @@ int basi_tc_conv_set_bn_apply(basi_tc_conv* pl, const basi_tensor* out, int relu
   const int items = ((cp.m_tiles + pl->mt - 1) / pl->mt) * cp.n_tiles;
   if (items <= 0 || pl->grid <= 0) return 0;
   const int per_cta = (items + pl->grid - 1) / pl->grid;
-  if (per_cta * pl->mt * pl->bn > 512) return 0;
+  if (per_cta * pl->mt * pl->bn > 512 || per_cta > 16) return 0;     // TMEM columns; one tmem_full barrier per item
   if (pl->grid > basi::sm_count()) return 0;
   if (make_act_map(&pl->mapD2, out, pl->TW, pl->TH, pl->TN, pl->bn >= 64 ? 64 : pl->bn) != BASI_OK) return 0;
   pl->cp.fuse_apply = 1;
+  pl->cp.keep_acc = 1;
   pl->cp.apply_relu = relu ? 1 : 0;
+  return 1;
+}
+
+/* Fused BN backward for a dgrad plan whose destination `dx` is the gradient wrt the RAW conv output x of the layer
+ * that feeds this convolution through BN(+ReLU): the kernel computes dA in TMEM, reduces sum(g), sum(g * xhat) with
+ * the ReLU mask recomputed from x, meets the grid at a barrier and writes dx = BN'(dA) directly; dgamma / dbeta are
+ * added into their gradient slots.  Returns 1 if the plan was switched, 0 if it cannot be fused. */
+int basi_tc_conv_set_bn_bwd(basi_tc_conv* pl, const basi_tensor* x, const float* bnp, int relu, double* dsums,
+                            double count, float* dgamma, float* dbeta, uint32_t* counter) {
+  if (!pl || !x || !bnp || !dsums || !dgamma || !dbeta || !counter || count <= 0) return 0;
+  if (pl->kind != BASI_TC_DGRAD || pl->split || pl->cluster != 1 || pl->cp.halo || pl->cp.accumulate) return 0;
+  if (pl->bn > 128 || exp_env("BASI_TC_NO_FUSED_BWD")) return 0;
+  ConvParams& cp = pl->cp;
+  if (x->dtype != BASI_BF16 || x->c != cp.Cdst || x->n != cp.N || x->h != cp.H || x->w != cp.W) return 0;
+  if (x->ld % 8 || ((uintptr_t)x->ptr & 15)) return 0;
+  const int items = ((cp.m_tiles + pl->mt - 1) / pl->mt) * cp.n_tiles;
+  if (items <= 0 || pl->grid <= 0 || pl->grid > basi::sm_count()) return 0;
+  const int per_cta = (items + pl->grid - 1) / pl->grid;
+  if (per_cta * pl->mt * pl->bn > 512 || per_cta > 16) return 0;
+  // shared memory: one output staging buffer + the x tile buffer + the coefficient table + one mbarrier
+  const int nbox = (pl->bn + 63) / 64;
+  const int staging = nbox * A_BYTES;
+  const int out_area = 2 * staging + 5 * pl->bn * 4 + 64;
+  const int fixed = 1024 + 1024 + 1024 * (int)sizeof(float) + 1024 + out_area;
+  const int stage_bytes = pl->mt * A_BYTES + pl->bn * 128;
+  int stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return 0;
+  if (make_act_map(&pl->mapD2, x, pl->TW, pl->TH, pl->TN, pl->bn >= 64 ? 64 : pl->bn) != BASI_OK) return 0;
+  cp.stages = stages;
+  cp.ring_bytes = stages * stage_bytes;
+  cp.out_bufs = 1;
+  pl->smem = (size_t)cp.ring_bytes + fixed;
+  cp.xbuf_off = staging;
+  cp.coef_off = 2 * staging;
+  cp.xbar_off = 2 * staging + 5 * pl->bn * 4;
+  cp.fuse_bwd = 1;
+  cp.keep_acc = 1;
+  cp.bwd_relu = relu ? 1 : 0;
+  cp.bwd_bnp = bnp;
+  cp.bwd_sums = dsums;
+  cp.bwd_dgamma = dgamma;
+  cp.bwd_dbeta = dbeta;
+  cp.bwd_count = count;
+  cp.bwd_counter = counter;
   return 1;
 }
 

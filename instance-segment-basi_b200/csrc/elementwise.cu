@@ -982,6 +982,101 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// A3 / F3: label encodings and click sampling on the device (integer work, bit-exact with the numpy expressions).
+//   mode 0  binary            back/2AddClass/BAISData.py:150-151     (ann == num) ? 1 : 0
+//   mode 1  4-class border    back/4BorderClass/BAISData.py:143-160  has_255=True: 255 -> 171, num -> 85, (v - 1) // 84
+//                             in uint8 arithmetic: 0 wraps to 255 -> 3 (background), 85 -> 1, 171 -> 2, others (k-1)//84
+//   mode 2  3-class           same file, has_255=False: 255 -> 0, num -> 128, (v - 1) // 127 (0 wraps to 255 -> 2)
+//   mode 3  COCO              back/5COCO/BAISData.py:361-369         attention > 0 ? 2 : (sum > 0 ? 1 : 0)
+// ------------------------------------------------------------------------------------------
+__global__ void label_encode_kernel(const uint8_t* __restrict__ ann, const uint8_t* __restrict__ att,
+                                    const int32_t* __restrict__ nums, int mode, int32_t* __restrict__ out_i32,
+                                    float* __restrict__ out_f32, int64_t per_image, int64_t total) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_image);
+    uint8_t v = ann[i];
+    int lab;
+    if (mode == 0) {
+      lab = (int)v == nums[b] ? 1 : 0;
+    } else if (mode == 1) {
+      if (v == 255) v = 171;
+      if ((int)v == nums[b]) v = 85;
+      lab = (uint8_t)(v - 1) / 84;
+    } else if (mode == 2) {
+      if (v == 255) v = 0;
+      if ((int)v == nums[b]) v = 128;
+      lab = (uint8_t)(v - 1) / 127;
+    } else {
+      lab = att[i] > 0 ? 2 : (v > 0 ? 1 : 0);
+    }
+    if (out_i32) out_i32[i] = lab;
+    if (out_f32) out_f32[i] = (float)lab;
+  }
+}
+
+// counts[b] = number of pixels of image b whose label equals `target` (np.argwhere(ann == target) has that many rows)
+template <typename TL>
+__global__ void __launch_bounds__(256) click_count_kernel(const TL* __restrict__ lab, TL target, int per_image,
+                                                          int32_t* __restrict__ counts) {
+  pdl_prologue();
+  __shared__ int wsum[8];
+  const TL* p = lab + (int64_t)blockIdx.x * per_image;
+  int c = 0;
+  for (int i = threadIdx.x; i < per_image; i += 256) c += p[i] == target ? 1 : 0;
+  c = (int)warp_sum((float)c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// clicks[b] = ratio * (row, col) of the k[b]-th pixel (row-major order) of image b whose label equals `target` --
+// np.argwhere(ann == target)[k] * ratio (back/2AddClass/BAISData.py:63-66); k out of range leaves (-1, -1)
+template <typename TL>
+__global__ void __launch_bounds__(256) click_select_kernel(const TL* __restrict__ lab, TL target, int H, int W,
+                                                           const int32_t* __restrict__ k, int ratio,
+                                                           int32_t* __restrict__ clicks) {
+  pdl_prologue();
+  __shared__ int wcnt[8];
+  __shared__ int base_s;
+  const int per_image = H * W;
+  const TL* p = lab + (int64_t)blockIdx.x * per_image;
+  const int want = k[blockIdx.x];
+  if (threadIdx.x == 0) {
+    base_s = 0;
+    clicks[2 * blockIdx.x] = -1;
+    clicks[2 * blockIdx.x + 1] = -1;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < per_image; i0 += 256) {       // 256 consecutive pixels per round, ranked with ballots
+    const int i = i0 + threadIdx.x;
+    const bool hit = i < per_image && p[i] == target;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    int before = base_s;
+    for (int w = 0; w < warp; ++w) before += wcnt[w];
+    const int rank = before + __popc(m & ((1u << lane) - 1u));
+    if (hit && rank == want) {
+      clicks[2 * blockIdx.x] = (i / W) * ratio;
+      clicks[2 * blockIdx.x + 1] = (i % W) * ratio;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += wcnt[w];
+      base_s += t;
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" {
 
 const char* basi_last_error(void) { return g_err; }
@@ -1001,6 +1096,45 @@ int basi_memset(void* ptr, int value, int64_t bytes, void* stream) {
     set_error("basi_memset: %s", cudaGetErrorString(e));
     return BASI_E_CUDA;
   }
+  return BASI_OK;
+}
+
+int basi_label_encode(const uint8_t* ann, const uint8_t* attention, const int32_t* nums, int mode, int32_t* out_i32,
+                      float* out_f32, int B, int64_t per_image, void* stream) {
+  BASI_CHECK_ARG(ann && (out_i32 || out_f32) && B > 0 && per_image > 0 && mode >= 0 && mode <= 3,
+                 "label_encode: bad argument");
+  BASI_CHECK_ARG(mode == 3 ? attention != nullptr : nums != nullptr, "label_encode: mode 3 needs the attention map, "
+                 "modes 0-2 the instance numbers");
+  const int64_t total = (int64_t)B * per_image;
+  basi::launch(label_encode_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, ann, attention, nums, mode,
+               out_i32, out_f32, per_image, total);
+  BASI_CHECK_LAUNCH("label_encode");
+  return BASI_OK;
+}
+
+int basi_click_count(const void* labels, int labels_are_f32, int target, int B, int per_image, int32_t* counts,
+                     void* stream) {
+  BASI_CHECK_ARG(labels && counts && B > 0 && per_image > 0, "click_count: bad argument");
+  if (labels_are_f32)
+    basi::launch(click_count_kernel<float>, B, 256, 0, (cudaStream_t)stream, (const float*)labels, (float)target,
+                 per_image, counts);
+  else
+    basi::launch(click_count_kernel<int32_t>, B, 256, 0, (cudaStream_t)stream, (const int32_t*)labels, (int32_t)target,
+                 per_image, counts);
+  BASI_CHECK_LAUNCH("click_count");
+  return BASI_OK;
+}
+
+int basi_click_select(const void* labels, int labels_are_f32, int target, int B, int H, int W, const int32_t* k,
+                      int ratio, int32_t* clicks, void* stream) {
+  BASI_CHECK_ARG(labels && k && clicks && B > 0 && H > 0 && W > 0 && ratio > 0, "click_select: bad argument");
+  if (labels_are_f32)
+    basi::launch(click_select_kernel<float>, B, 256, 0, (cudaStream_t)stream, (const float*)labels, (float)target, H, W,
+                 k, ratio, clicks);
+  else
+    basi::launch(click_select_kernel<int32_t>, B, 256, 0, (cudaStream_t)stream, (const int32_t*)labels, (int32_t)target,
+                 H, W, k, ratio, clicks);
+  BASI_CHECK_LAUNCH("click_select");
   return BASI_OK;
 }
 

@@ -20,7 +20,8 @@ What each function restates (paths relative to /root/reference):
 * ``mask_gaussian``          back/2AddClass/BAISData.py:189-202 (sigma=30),
                              back/5COCO/BAISData.py:405-417 (sigma=20)
 * ``pack_input``             back/2AddClass/BAISData.py:79-80
-* ``encode_labels_border``   back/4BorderClass/BAISData.py:143-165
+* ``encode_labels_border``   back/4BorderClass/BAISData.py:143-165 (``_three``: the has_255=False branch,
+                             ``_coco``: back/5COCO/BAISData.py:361-369, ``sample_click``: 2AddClass :63-66)
 * ``conv2d`` / ``atrous``    back/2AddClass/BAISPSPNet.py:118-146 (tf.nn.conv2d /
                              tf.pad + tf.nn.atrous_conv2d, NHWC, HWIO weights)
 * ``batch_norm``             back/2AddClass/BAISPSPNet.py:204-236 (training=True always)
@@ -95,6 +96,27 @@ def encode_labels_border(ann_u8, num):
 
 def encode_labels_binary(ann_u8, num):
     return np.where(np.asarray(ann_u8) == num, 1, 0)
+
+
+def encode_labels_three(ann_u8, num):
+    """3-class label map (has_255=False branch of back/4BorderClass/BAISData.py:146-160; the 3ThreeClass snapshot):
+    border -> background, 0 other instance, 1 attended instance, 2 background (uint8 wrap of (0 - 1) // 127)."""
+    ann = np.asarray(ann_u8, dtype=np.uint8)
+    ann = np.where(ann == 255, 0, ann).astype(np.uint8)
+    one = np.where(ann == num, 128, ann).astype(np.uint8)
+    return ((one - np.uint8(1)) // np.uint8(127)).astype(np.uint8)
+
+
+def encode_labels_coco(ann_sum_u8, attention_u8):
+    """COCO label map (back/5COCO/BAISData.py:361-369): 0 background, 1 other instance, 2 attended instance."""
+    lab = np.where(np.asarray(ann_sum_u8) > 0, 1, 0)
+    return np.where(np.asarray(attention_u8) > 0, 2, lab)
+
+
+def sample_click(label_map, k, ratio=8, target=1):
+    """where = np.argwhere(ann == target)[k] * ratio (back/2AddClass/BAISData.py:63-66 with the drawn index k)."""
+    where = np.argwhere(np.asarray(label_map) == target)
+    return [int(where[k][0]) * ratio, int(where[k][1]) * ratio]
 
 
 # --------------------------------------------------------------------------

@@ -314,3 +314,27 @@ def test_step_is_reproducible_at_benchmark_size(prec, monkeypatch):
         assert abs(loss - loss0) <= 1e-6 * abs(loss0), (loss, loss0)
         rel = float((g - g0).norm() / g0.norm())
         assert rel < gtol, rel
+
+
+def test_fused_bn_backward_in_dgrad_matches_separate_kernels(monkeypatch):
+    """BASI_FUSED_BWD=1 (opt-in): the BN backward of the reduce / 3x3 layers runs inside the consumer's dgrad kernel.
+    Same step, same weights: losses identical, gradients equal up to bf16 storage of the intermediate gradient."""
+    variant, nseg, S, F, B, classes = "1NoClass", 1, 320, 32, 2, 21
+    params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BASI_EXPERIMENTS", "1")
+        monkeypatch.setenv("BASI_FUSED_BWD", mode)
+        eng = _engine(variant, nseg, S, F, B, classes, "bf16", dict(kind="bce", pos_weight=3.0))
+        eng.set_params(params)
+        eng.feed(data, lab, None, 5e-3)
+        eng.step_device()
+        torch.cuda.synchronize()
+        res[mode] = (eng.losses()[0], eng.grads_flat.double().cpu().numpy(), eng.fused_bn_dgrad)
+        del eng
+        torch.cuda.empty_cache()
+    assert res["0"][2] == 0 and res["1"][2] >= 50, (res["0"][2], res["1"][2])
+    assert abs(res["0"][0] - res["1"][0]) <= 1e-6 * abs(res["0"][0])
+    a, b = res["0"][1], res["1"][1]
+    cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.98, cos

@@ -899,3 +899,103 @@ def test_stem_conv_fused_bn_statistics(out_dtype, cout, H, W, B):
     istd = 1.0 / np.sqrt(var + 1e-5)
     assert rel_err(got[0], mean) < 1e-5 and rel_err(got[1], istd) < 1e-5
     assert rel_err(got[2], gamma * istd) < 1e-5 and np.array_equal(got[3], beta)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A3 / F3: label encodings and click sampling on the device (bit-exact integer work)
+# ---------------------------------------------------------------------------------------------------------------
+def _instance_maps(B, P, rng, ids=(1, 2, 7, 85, 86, 170, 200, 254)):
+    ann = np.zeros((B, P, P), dtype=np.uint8)
+    nums = []
+    for b in range(B):
+        chosen = rng.choice(ids, size=3, replace=False)
+        for j, k in enumerate(chosen):
+            y0, x0 = rng.randint(0, P - 6), rng.randint(0, P - 6)
+            ann[b, y0:y0 + rng.randint(3, 6), x0:x0 + rng.randint(3, 6)] = k
+        ann[b, rng.randint(0, P, 20), rng.randint(0, P, 20)] = 255          # border pixels
+        present = [k for k in chosen if np.any(ann[b] == k)]
+        nums.append(int(present[rng.randint(0, len(present))]))
+    return ann, np.asarray(nums, dtype=np.int32)
+
+
+@pytest.mark.parametrize("mode", ["binary", "border", "three", "coco"])
+def test_label_encode_bit_exact(mode):
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(11)
+    B, P = 5, 40
+    ann, nums = _instance_maps(B, P, rng)
+    att = None
+    if mode == "coco":
+        att = (ann == nums[:, None, None]).astype(np.uint8)
+        ann = ((ann > 0) & (ann < 255)).astype(np.uint8) * rng.randint(1, 4, size=ann.shape).astype(np.uint8)
+        ref = np.stack([O.encode_labels_coco(ann[b], att[b]) for b in range(B)])
+    else:
+        fn = {"binary": O.encode_labels_binary, "border": O.encode_labels_border, "three": O.encode_labels_three}[mode]
+        ref = np.stack([fn(ann[b], nums[b]) for b in range(B)])
+    if mode == "border":
+        # the uint8 wrap-around and the aliasing quirk of instance ids >= 85 are part of the reference semantics
+        assert set(np.unique(ref)) <= {0, 1, 2, 3} and np.all(ref[ann == 0] == 3) and np.all(ref[ann == 255] == 2)
+    code = {"binary": 0, "border": 1, "three": 2, "coco": 3}[mode]
+    oi = torch.full((B, P, P), -7, dtype=torch.int32, device="cuda:0")
+    of = torch.full((B, P, P), -7.0, dtype=torch.float32, device="cuda:0")
+    annd, numd = dev(ann), dev(nums)
+    attd = dev(att) if att is not None else None
+    call("basi_label_encode", annd.data_ptr(), attd.data_ptr() if attd is not None else None,
+         None if attd is not None else numd.data_ptr(), code, oi.data_ptr(), of.data_ptr(), B, C.c_int64(P * P))
+    assert np.array_equal(host(oi), ref.astype(np.int32))
+    assert np.array_equal(host(of), ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("f32", [0, 1])
+def test_click_sampling_matches_argwhere(f32):
+    """k-th pixel (row-major) of the attended instance times the ratio == np.argwhere(ann == 1)[k] * ratio, for
+    every valid k of small maps and for the RNG-drawn k of the reference's sampling loop."""
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(3)
+    B, H, W, ratio = 6, 23, 40, 8
+    lab = (rng.rand(B, H, W) < 0.07).astype(np.int32)
+    lab[0] = 0
+    lab[0, H - 1, W - 1] = 1                     # a single pixel, the last one
+    lab[1] = 1                                   # every pixel
+    labd = dev(lab.astype(np.float32) if f32 else lab)
+    counts = torch.zeros(B, dtype=torch.int32, device="cuda:0")
+    call("basi_click_count", labd.data_ptr(), f32, 1, B, H * W, counts.data_ptr())
+    cnt = host(counts)
+    assert np.array_equal(cnt, lab.reshape(B, -1).sum(1))
+    clicks = torch.zeros((B, 2), dtype=torch.int32, device="cuda:0")
+    for trial in range(6):
+        k = np.asarray([0 if trial == 0 else (c - 1 if trial == 1 else rng.randint(0, c)) for c in cnt], dtype=np.int32)
+        kd = dev(k)
+        call("basi_click_select", labd.data_ptr(), f32, 1, B, H, W, kd.data_ptr(), ratio, clicks.data_ptr())
+        got = host(clicks)
+        ref = np.asarray([O.sample_click(lab[b], int(k[b]), ratio) for b in range(B)], dtype=np.int32)
+        assert np.array_equal(got, ref), (trial, got, ref)
+    kd = dev(np.asarray(cnt, dtype=np.int32))    # k == count: out of range -> (-1, -1)
+    call("basi_click_select", labd.data_ptr(), f32, 1, B, H, W, kd.data_ptr(), ratio, clicks.data_ptr())
+    assert np.all(host(clicks) == -1)
+
+
+def test_engine_label_input_feeds_border_labels_and_reference_clicks():
+    """Engine.feed_annotations: uint8 instance maps -> 4-class labels + clicks on the device, clicks identical to the
+    reference's host loop run with the same numpy RNG state."""
+    from basi_b200.BAISPSPNet import PSPNet, Placeholder
+    from basi_b200.engine import Engine
+    S, F, B, P = 64, 8, 3, 8
+    net = PSPNet({'data': Placeholder((None, S, S, 4))}, num_classes=21, num_segment=4, is_training=True,
+                 last_pool_size=P, filter_number=F, variant="4BorderClass")
+    eng = Engine(net, B, "bf16", True, dict(kind="softmax", class_weight=0.1))
+    eng.enable_click_input(30)
+    eng.enable_label_input("border")
+    rng = np.random.RandomState(5)
+    ann, nums = _instance_maps(B, P, rng, ids=(1, 2, 3))
+    k = eng.feed_annotations(ann, nums, rng=np.random.RandomState(42))
+    torch.cuda.synchronize()
+    ref_lab = np.stack([O.encode_labels_border(ann[b], nums[b]) for b in range(B)])
+    assert np.array_equal(eng.label_seg.cpu().numpy()[..., 0], ref_lab.astype(np.int32))
+    r2 = np.random.RandomState(42)
+    ref_clicks = []
+    for b in range(B):                                   # the reference loop (BAISData.py:63-66)
+        where = np.argwhere(ref_lab[b] == 1)
+        where = where[r2.randint(0, len(where))]
+        ref_clicks.append([where[0] * 8, where[1] * 8])
+    assert np.array_equal(eng.clicks_dev.cpu().numpy(), np.asarray(ref_clicks, dtype=np.int32))

@@ -350,7 +350,7 @@ def test_tc_fprop_fused_bn_apply(case, relu):
     bt = torch.bfloat16
     xa = Act(torch.from_numpy(x).to("cuda:0").to(bt).contiguous())
     ya = Act(torch.zeros((B, H, W, cout), dtype=bt, device="cuda:0"))
-    oa = Act(torch.full((B, H, W, cout), 7.0, dtype=bt, device="cuda:0"))
+    oa = Act(torch.full((B, H, W, cout), 1e30, dtype=bt, device="cuda:0"))      # sentinel no BN output can equal
     wd, gd, bd = dev(w), dev(gamma), dev(beta)
     w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
     w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
@@ -383,4 +383,66 @@ def test_tc_fprop_fused_bn_apply(case, relu):
     if relu:
         ref = np.maximum(ref, 0)
     assert rel_err(out, ref) < 1.5e-2, rel_err(out, ref)
-    assert not np.any(out == 7.0)                                   # every element was written
+    miss = np.argwhere(out > 1e29)
+    assert len(miss) == 0, "unwritten elements: %d, first %s, last %s, images %s, channels %s" % (
+        len(miss), miss[0], miss[-1], sorted(set(miss[:, 0]))[:8], sorted(set(miss[:, 3]))[:8])
+
+
+@pytest.mark.parametrize("relu", [1, 0])
+@pytest.mark.parametrize("case", [(3, 2, 128, 128, 40, 40, 16), (1, 1, 128, 512, 40, 40, 16), (1, 1, 32, 128, 80, 80, 16),
+                                  (3, 1, 32, 32, 80, 80, 3), (3, 1, 64, 64, 40, 40, 16), (1, 1, 64, 256, 40, 40, 5)],
+                         ids=lambda c: "k%dd%d_%dto%d_%dx%d_B%d" % c)
+def test_tc_dgrad_fused_bn_backward(case, relu):
+    """dgrad + the BN(+ReLU) backward of the layer feeding the convolution in one cooperative launch
+    (basi_tc_conv_set_bn_bwd): dx (gradient wrt the raw conv output of that layer), dgamma and dbeta against float64."""
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    from basi_b200.engine import Act
+    from gpu_util import bf16_round, call, dev, host, rel_err
+    k, d, cin, cout, H, W, B = case
+    rng = np.random.RandomState(9)
+    xraw = bf16_round(rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32) * 1.5 + 0.2)     # raw conv output of layer L
+    w = bf16_round((rng.uniform(-1, 1, (k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32))
+    dy = bf16_round(rng.uniform(-1, 1, (B, H, W, cout)).astype(np.float32))
+    gamma, beta = rng.uniform(0.5, 1.5, cin).astype(np.float32), rng.uniform(-0.5, 0.5, cin).astype(np.float32)
+    pad = d * (k - 1) // 2
+    desc = ConvDesc(k, k, 1, d, pad, pad, 0)
+    bt = torch.bfloat16
+    # float64 reference: a = [relu](bn(x)); y = conv(a, w); L = sum(y * dy)
+    xt = torch.from_numpy(xraw).permute(0, 3, 1, 2).double().requires_grad_(True)
+    gt = torch.from_numpy(gamma).double().requires_grad_(True)
+    bt_ = torch.from_numpy(beta).double().requires_grad_(True)
+    a = O.batch_norm(xt, gt, bt_, bool(relu))
+    yref = O.conv2d(a, torch.from_numpy(w).double(), 1, pad, d)
+    (yref * torch.from_numpy(dy).permute(0, 3, 1, 2).double()).sum().backward()
+    dx_ref = xt.grad.permute(0, 2, 3, 1).numpy()
+    xr = xraw.astype(np.float64).reshape(-1, cin)
+    mean, var = xr.mean(0), xr.var(0)
+    istd = 1 / np.sqrt(var + 1e-5)
+    bnp = np.concatenate([mean, istd, gamma * istd, beta]).astype(np.float32)
+    xa = Act(torch.from_numpy(xraw).to("cuda:0").to(bt).contiguous())
+    dya = Act(torch.from_numpy(dy).to("cuda:0").to(bt).contiguous())
+    dxa = Act(torch.full((B, H, W, cin), 1e30, dtype=bt, device="cuda:0"))
+    wd, bnpd = dev(w), dev(bnp)
+    w_io = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    w_oi = torch.zeros(k * k * cin * cout, dtype=bt, device="cuda:0")
+    call("basi_tc_pack_weights", wd.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), k * k, cin, cout)
+    dsums = torch.zeros(2 * cin * 8, dtype=torch.float64, device="cuda:0")
+    dgam = torch.zeros(cin, device="cuda:0")
+    dbet = torch.zeros(cin, device="cuda:0")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create", 1, C.byref(desc), dya.ref, dxa.ref, w_io.data_ptr(), None, 0, C.byref(h))
+    ok = _lib.load().basi_tc_conv_set_bn_bwd(h, xa.ref, bnpd.data_ptr(), relu, dsums.data_ptr(),
+                                             C.c_double(float(B * H * W)), dgam.data_ptr(), dbet.data_ptr(), cnt.data_ptr())
+    assert ok == 1, "this shape must take the fused path"
+    for rep in range(2):
+        dsums.zero_(); dgam.zero_(); dbet.zero_()
+        call("basi_tc_conv_run", h)
+    torch.cuda.synchronize()
+    dx = host(dxa).astype(np.float64)
+    _lib.load().basi_tc_conv_destroy(h)
+    assert not np.any(np.abs(dx) > 1e29), "unwritten elements"
+    assert rel_err(dx, dx_ref) < 2e-2, rel_err(dx, dx_ref)
+    assert rel_err(host(dbet), bt_.grad.numpy()) < 1e-2
+    assert rel_err(host(dgam), gt.grad.numpy()) < 1e-2
