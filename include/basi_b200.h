@@ -176,6 +176,14 @@ int basi_bn_bwd_fused(const basi_tensor* dout, const basi_tensor* x, const float
                       double count, float* dgamma, float* dbeta, float* coef, uint32_t* barrier,
                       const basi_tensor* dx, void* stream);
 
+/* F1: tf.one_hot(labels, depth=2) as float32 pairs (targets of the 2-channel weighted CE of variant B,
+ * back/90AttentionSingle2/BAISRunnerTrain.py:128-131); labels float32 {0,1}, out float32 [n][2]. */
+int basi_onehot2_f32(const float* labels, float* out, int64_t n, void* stream);
+/* F1 (variant B trunk): slim.max_pool2d(net, [2, 2]) of vgg_16 (slim/nets/vgg.py:188-196): 2x2 / stride 2 VALID,
+ * y = [N, H/2, W/2, C]; argmax: one byte per output element (window index of the first maximum). */
+int basi_maxpool2s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream);
+int basi_maxpool2s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,
+                        void* stream);
 /* ---- A8: Network.max_pool 3x3 s2 SAME (:152-155, :269), Network.avg_pool k=s VALID (:157-160) ---- */
 int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream);
 int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,

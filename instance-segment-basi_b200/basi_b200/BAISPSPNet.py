@@ -152,10 +152,30 @@ class Network(object):
 
     @layer
     def max_pool(self, input, k_h, k_w, s_h, s_w, name, padding="VALID"):
-        if not (k_h == 3 and k_w == 3 and s_h == 2 and s_w == 2 and padding == "SAME"):
-            raise NotImplementedError("max_pool: only 3x3 s2 SAME is on the hot path")
         h, w, c = input.shape
-        return self._node("max_pool", name, [input], (_same_out(h, 2), _same_out(w, 2), c))
+        if k_h == 2 and k_w == 2 and s_h == 2 and s_w == 2 and padding == "VALID":
+            return self._node("max_pool", name, [input], (h // 2, w // 2, c), k=2)     # slim vgg_16 pools (variant B)
+        if not (k_h == 3 and k_w == 3 and s_h == 2 and s_w == 2 and padding == "SAME"):
+            raise NotImplementedError("max_pool: only 3x3 s2 SAME and 2x2 s2 VALID are on the hot path")
+        return self._node("max_pool", name, [input], (_same_out(h, 2), _same_out(w, 2), c), k=3)
+
+    @layer
+    def resize_nearest(self, input, size, name):
+        """tf.image.resize_nearest_neighbor (TF1 default)."""
+        return self._node("resize_nearest", name, [input], (int(size[0]), int(size[1]), input.shape[2]))
+
+    @layer
+    def mask_multiply(self, inputs, name):
+        """tf.multiply(feature, mask): a 1-channel float32 map broadcast over the feature channels."""
+        feature, mask = inputs
+        assert mask.shape[2] == 1 and mask.shape[:2] == feature.shape[:2], (feature.shape, mask.shape)
+        return self._node("mask_multiply", name, [feature, mask], feature.shape)
+
+    @layer
+    def softmax_gate(self, input, name, sel=1, thr=0.9):
+        """softmax over the channels -> channel `sel` -> tf.where(p > thr, p, 0) (LinkNet._attention)."""
+        h, w, c = input.shape
+        return self._node("softmax_gate", name, [input], (h, w, 1), sel=sel, thr=thr)
 
     @layer
     def avg_pool(self, input, k_h, k_w, s_h, s_w, name, padding="VALID"):
@@ -165,10 +185,11 @@ class Network(object):
         return self._node("avg_pool", name, [input], (h // k_h, w // k_w, c), k=k_h)
 
     @layer
-    def concat(self, inputs, axis, name):
+    def concat(self, inputs, axis, name, dtype=None):
         assert axis in (-1, 3)
         h, w, _ = inputs[0].shape
-        return self._node("concat", name, inputs, (h, w, sum(i.shape[2] for i in inputs)))
+        assert len(set(id(i) for i in inputs)) == len(inputs), "concat of one tensor with itself: feed two nodes"
+        return self._node("concat", name, inputs, (h, w, sum(i.shape[2] for i in inputs)), dtype=dtype)
 
     @layer
     def add(self, inputs, name):
@@ -184,9 +205,10 @@ class Network(object):
     @layer
     def batch_normalization(self, input, name, scale_offset=True, relu=False):
         c = input.shape[-1]
-        # tf.layers.batch_normalization(name=name) inside tf.variable_scope(name): doubled scope
-        g = self.make_var('%s/%s/gamma' % (name, name), [c])
-        b = self.make_var('%s/%s/beta' % (name, name), [c])
+        # tf.layers.batch_normalization(name=name) inside tf.variable_scope(name): doubled (leaf) scope
+        leaf = name.split('/')[-1]
+        g = self.make_var('%s/%s/gamma' % (name, leaf), [c])
+        b = self.make_var('%s/%s/beta' % (name, leaf), [c])
         return self._node("batch_normalization", name, [input], input.shape, relu=relu, gamma=g, beta=b,
                           momentum=0.95, epsilon=1e-5)
 

@@ -283,7 +283,7 @@ class Engine(object):
         for n in nodes:
             if n.op == "concat":
                 h, w, ctot = n.shape
-                buf = self._new_act(h, w, ctot)
+                buf = self._new_act(h, w, ctot, torch.float32 if n.attrs.get("dtype") == "f32" else None)
                 self._acts[n.index] = buf
                 o = 0
                 for i in n.inputs:
@@ -322,8 +322,13 @@ class Engine(object):
 
     def _lower_data(self, n):
         h, w, c = n.shape
-        self.input = Act(self._alloc((self.B, h, w, c), torch.float32))
-        self._acts[n.index] = self.input
+        a = Act(self._alloc((self.B, h, w, c), torch.float32))
+        self._acts[n.index] = a
+        if n.name == "mask":              # variant B: the click map is a separate 1-channel input (no gradient)
+            self.input_mask = a
+            a.no_grad = True
+        else:
+            self.input = a
 
     def _lower_zero_padding(self, n):
         self._acts[n.index] = ("pad", self._acts[n.inputs[0].index], n.attrs["pad"])
@@ -455,6 +460,13 @@ class Engine(object):
 
     def _lower_max_pool(self, n):
         x = self._acts[n.inputs[0].index]
+        if n.attrs.get("k", 3) == 2:       # slim vgg_16 pools (variant B)
+            y = self._out_act(n, x.t.dtype)
+            amax = self._zeros(self.B * n.shape[0] * n.shape[1] * n.shape[2], torch.uint8)
+            self._acts[n.index] = y
+            self._ops.append(("maxpool2", dict(x=x, y=y, amax=amax)))
+            self._call(self.fwd, "basi_maxpool2s2_fwd", x.ref, y.ref, amax.data_ptr())
+            return
         y = self._out_act(n)
         amax = self._zeros(self.B * n.shape[0] * n.shape[1] * n.shape[2], torch.uint8)
         op = dict(x=x, y=y, amax=amax)
@@ -521,6 +533,46 @@ class Engine(object):
         self._acts[n.index] = y
         self._ops.append(("gate", op))
         self._call(self.fwd, "basi_gate_mul_fwd", feat.ref, logits.t.data_ptr(), nseg, att, y.ref)
+
+    # ---- variant B (F1): nearest resize, click / attention gating, softmax gate
+    def _mask_grad(self, act):
+        """1-channel float32 maps (attention gates and their resized copies) collect gradient from several consumers
+        through kernels that always ADD (basi_mask_mul_bwd): the buffer is zeroed every step."""
+        if getattr(act, "no_grad", False):
+            return None
+        if act.grad is None:
+            self._zero_grads.append(self._grad_of(act))
+            act.gw = True
+        return act.grad
+
+    def _lower_resize_nearest(self, n):
+        x = self._acts[n.inputs[0].index]
+        y = self._out_act(n, x.t.dtype)
+        if getattr(x, "no_grad", False):
+            y.no_grad = True
+        self._acts[n.index] = y
+        self._ops.append(("nearest", dict(x=x, y=y)))
+        self._call(self.fwd, "basi_resize_nearest_fwd", x.ref, y.ref)
+
+    def _lower_mask_multiply(self, n):
+        feat = self._acts[n.inputs[0].index]
+        mask = self._acts[n.inputs[1].index]
+        assert mask.t.dtype == torch.float32 and mask.shape[3] == 1
+        y = self._out_act(n, feat.t.dtype)
+        self._acts[n.index] = y
+        self._ops.append(("maskmul", dict(feat=feat, mask=mask, y=y)))
+        self._call(self.fwd, "basi_mask_mul_fwd", feat.ref, mask.t.data_ptr(), 1, 0, y.ref)
+
+    def _lower_softmax_gate(self, n):
+        logits = self._acts[n.inputs[0].index]
+        assert logits.t.dtype == torch.float32
+        h, w, c = n.inputs[0].shape
+        gate = Act(self._alloc((self.B, h, w, 1), torch.float32))
+        self._acts[n.index] = gate
+        op = dict(logits=logits, gate=gate, C=c, sel=int(n.attrs["sel"]), thr=float(n.attrs["thr"]))
+        self._ops.append(("softgate", op))
+        self._call(self.fwd, "basi_softmax_gate_fwd", logits.t.data_ptr(), C.c_int64(self.B * h * w), c, op["sel"],
+                   C.c_float(op["thr"]), gate.t.data_ptr())
 
     def _lower_squeeze(self, n):
         self._acts[n.index] = self._acts[n.inputs[0].index]
@@ -617,7 +669,67 @@ class Engine(object):
                    1 if op["relu"] else 0)
 
     # ---- loss
+    def _lower_loss_linknet(self):
+        """cal_loss of variant B (back/90AttentionSingle2/BAISRunnerTrain.py:116-156): every attention map against the
+        nearest-resized labels as 2-channel weighted CE (pos_weight 3, mean over 2N elements), averaged over the maps,
+        plus the class-head softmax CE (weight 1)."""
+        cfg = self.loss_cfg or {}
+        net = self.net
+        heads = [self._acts[nd.index] for nd in net.attentions]
+        self.att_logits = heads
+        self.seg_logits = heads[-1]
+        self.seg_name = "attention_1"
+        self.cls_logits = self._acts[net.classes[0].index] if net.classes else None
+        self.cls_name = "class_attention_fc" if net.classes else None
+        B = self.B
+        S_h, S_w = self.input.shape[1], self.input.shape[2]
+        P_h, P_w = S_h // 8, S_w // 8
+        self.loss_acc = self._zeros(4, torch.float64)
+        self.pred_seg = self._zeros((B, heads[-1].shape[1], heads[-1].shape[2], 1), torch.int32)
+        self.pred_cls = self._zeros((B,), torch.int32) if self.cls_logits is not None else None
+        self.post = []
+        fin = heads[-1]
+        self._call(self.post, "basi_argmax", fin.t.data_ptr(), C.c_int64(B * fin.shape[1] * fin.shape[2]), 2,
+                   self.pred_seg.data_ptr())
+        if self.cls_logits is not None:
+            self._call(self.post, "basi_argmax", self.cls_logits.t.data_ptr(), C.c_int64(B),
+                       self.cls_logits.shape[3], self.pred_cls.data_ptr())
+        if not self.training:
+            return
+        self.label_seg = self._zeros((B, P_h, P_w, 1), torch.float32)
+        lab = Act(self.label_seg)
+        self.lossl = []
+        self._lab_scaled = []
+        pw = float(cfg.get("pos_weight", 3.0))
+        for a in heads:
+            _, h, w, c = a.shape
+            assert c == 2
+            li = Act(self._zeros((B, h, w, 1), torch.float32))
+            ti = self._zeros((B, h, w, 2), torch.float32)
+            self._lab_scaled.append((li, ti))
+            n2 = 2 * B * h * w
+            g = self._grad_of(a)
+            a.gw = True
+            self._call(self.lossl, "basi_resize_nearest_fwd", lab.ref, li.ref)
+            self._call(self.lossl, "basi_onehot2_f32", li.t.data_ptr(), ti.data_ptr(), C.c_int64(B * h * w))
+            self._call(self.lossl, "basi_wbce_fwd_bwd", a.t.data_ptr(), ti.data_ptr(), C.c_float(pw),
+                       C.c_double(1.0 / (len(heads) * n2)), C.c_float(1.0 / (len(heads) * n2)), C.c_int64(n2),
+                       self.loss_acc.data_ptr(), g.t.data_ptr())
+        self.class_weight = float(cfg.get("class_weight", 1.0))
+        if self.cls_logits is not None:
+            self.label_cls = self._zeros((B,), torch.int32)
+            gc = self._grad_of(self.cls_logits)
+            self.cls_logits.gw = True
+            ncls = self.cls_logits.shape[3]
+            self._call(self.lossl, "basi_softmax_ce_fwd_bwd", self.cls_logits.t.data_ptr(),
+                       self.label_cls.data_ptr(), C.c_int64(B), ncls, C.c_double(1.0 / B),
+                       C.c_float(self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
+        else:
+            self.label_cls = None
+
     def _lower_loss(self):
+        if (self.loss_cfg or {}).get("kind") == "linknet_b" or hasattr(self.net, "attentions"):
+            return self._lower_loss_linknet()
         cfg = self.loss_cfg
         segname = (cfg or {}).get("seg")
         if segname is None:
@@ -699,9 +811,47 @@ class Engine(object):
         self.bwd.extend(self._deferred_bwd)
         self._deferred_bwd = []
 
+    def _bwd_maxpool2(self, op):
+        x, y = op["x"], op["y"]
+        if y.grad is None or not y.gw:
+            return
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_maxpool2s2_bwd", y.grad.ref, op["amax"].data_ptr(), x.grad.ref, acc)
+
+    def _bwd_nearest(self, op):
+        x, y = op["x"], op["y"]
+        if y.grad is None or not y.gw or getattr(x, "no_grad", False):
+            return                                   # unused output (finest level) or the click map
+        if x.shape[3] == 1 and x.t.dtype == torch.float32:
+            self._mask_grad(x)                       # gates: pre-zeroed, every writer adds
+            acc = 1
+        else:
+            acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_resize_nearest_bwd", y.grad.ref, x.grad.ref, acc)
+
+    def _bwd_maskmul(self, op):
+        feat, mask, y = op["feat"], op["mask"], op["y"]
+        if y.grad is None or not y.gw:
+            return
+        dmask = self._mask_grad(mask)
+        acc = self._acc_flag(feat)
+        self._call(self.bwd, "basi_mask_mul_bwd", y.grad.ref, feat.ref, mask.t.data_ptr(), 1, 0, feat.grad.ref, acc,
+                   dmask.t.data_ptr() if dmask is not None else None)
+
+    def _bwd_softgate(self, op):
+        logits, gate = op["logits"], op["gate"]
+        if gate.grad is None:
+            return
+        assert logits.gw, "the attention loss gradient must be written before the gate adjoint adds to it"
+        n, h, w, _ = gate.shape
+        self._call(self.bwd, "basi_softmax_gate_bwd", logits.t.data_ptr(), gate.grad.t.data_ptr(), C.c_int64(n * h * w),
+                   op["C"], op["sel"], C.c_float(op["thr"]), logits.grad.t.data_ptr(), 1)
+
     def _bwd_conv(self, op):
         x, y = op["x"], op["y"]
         dy = y.grad
+        if hasattr(self.net, "attentions") and (dy is None or not y.gw):
+            return                                   # variant B: the finest attention output feeds nothing
         assert dy is not None and y.gw, "conv %s: no gradient reaches its output" % op["name"]
         if op["relu"]:
             assert y.dtype == _lib.F32
@@ -1177,10 +1327,12 @@ class Engine(object):
         _lib.LAUNCHES += self.launches_per_step()
 
     # ---- host-facing helpers
-    def feed(self, data=None, label_seg=None, label_cls=None, lr=None):
+    def feed(self, data=None, label_seg=None, label_cls=None, lr=None, mask=None):
         """Copies host arrays (numpy or pinned torch tensors) into the static device buffers."""
         if data is not None:
             self.input.t.copy_(_as_tensor(data, torch.float32).view(self.input.t.shape), non_blocking=True)
+        if mask is not None:      # variant B: the click map is a separate 1-channel input
+            self.input_mask.t.copy_(_as_tensor(mask, torch.float32).view(self.input_mask.t.shape), non_blocking=True)
         if label_seg is not None:
             self.label_seg.copy_(_as_tensor(label_seg, self.label_seg.dtype).view(self.label_seg.shape),
                                  non_blocking=True)

@@ -1077,6 +1077,87 @@ __global__ void __launch_bounds__(256) click_select_kernel(const TL* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 2x2 / stride 2 VALID max-pool (slim.max_pool2d(net, [2, 2]) in vgg_16, slim/nets/vgg.py:188-196; variant B trunk).
+// Non-overlapping windows: the window index of the maximum (first maximum wins, row-major) is kept in one byte per
+// element; the adjoint routes dy to that element and writes zeros elsewhere (also into a dropped odd row / column).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2s2_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C, T* __restrict__ y, int ldy,
+                                      int OH, int OW, uint8_t* __restrict__ amax, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t p = i / cgs;
+    const int ow = (int)(p % OW);
+    const int64_t t = p / OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float best[VN];
+    uint8_t bi[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        Vec<T> v = Vec<T>::load(x + (((int64_t)n * H + oh * 2 + r) * W + ow * 2 + q) * ldx + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (v.v[j] > best[j]) { best[j] = v.v[j]; bi[j] = (uint8_t)(r * 2 + q); }
+      }
+    Vec<T> o;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o.v[j] = best[j];
+    o.store(y + p * ldy + cg * VN);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) amax[p * C + cg * VN + j] = bi[j];
+  }
+}
+
+template <typename T>
+__global__ void maxpool2s2_bwd_kernel(const T* __restrict__ dy, int lddy, int OH, int OW, const uint8_t* __restrict__ amax,
+                                      T* __restrict__ dx, int lddx, int H, int W, int C, int accumulate, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t p = i / cgs;
+    const int iw = (int)(p % W);
+    const int64_t t = p / W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    const int oh = ih >> 1, ow = iw >> 1;
+    Vec<T> o = Vec<T>::zero();
+    if (oh < OH && ow < OW) {
+      const int64_t op = ((int64_t)n * OH + oh) * OW + ow;
+      Vec<T> g = Vec<T>::load(dy + op * lddy + cg * VN);
+      const int pos = (ih & 1) * 2 + (iw & 1);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] = amax[op * C + cg * VN + j] == pos ? g.v[j] : 0.f;
+    }
+    T* d = dx + p * lddx + cg * VN;
+    if (accumulate) {
+      Vec<T> old = Vec<T>::load(d);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] += old.v[j];
+    }
+    o.store(d);
+  }
+}
+
+// t[i] = one_hot(label[i], 2) as float32 pairs [1 - z, z] (tf.one_hot(labels, depth=2), variant B cal_loss)
+__global__ void onehot2_kernel(const float* __restrict__ lab, float2* __restrict__ out, int64_t n) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float z = lab[i] > 0.5f ? 1.f : 0.f;
+    out[i] = make_float2(1.f - z, z);
+  }
+}
+
 extern "C" {
 
 const char* basi_last_error(void) { return g_err; }
@@ -1152,6 +1233,38 @@ static void same_pad_3s2(int in, int out, int* before) {
   int total = (out - 1) * 2 + 3 - in;
   if (total < 0) total = 0;
   *before = total / 2;
+}
+
+int basi_onehot2_f32(const float* labels, float* out, int64_t n, void* stream) {
+  BASI_CHECK_ARG(labels && out && n > 0 && (((uintptr_t)out) & 7) == 0, "onehot2: bad argument");
+  basi::launch(onehot2_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, labels, (float2*)out, n);
+  BASI_CHECK_LAUNCH("onehot2");
+  return BASI_OK;
+}
+
+int basi_maxpool2s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream) {
+  BASI_CHECK_ARG(x && y && argmax && vec_ok(x) && vec_ok(y) && x->dtype == y->dtype && x->c == y->c && x->n == y->n &&
+                     y->h == x->h / 2 && y->w == x->w / 2 && y->h > 0 && y->w > 0, "maxpool2s2 fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    int64_t total = pixels(y) * (y->c / Vec<T>::N);
+    basi::launch(maxpool2s2_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld,
+                 x->h, x->w, x->c, (T*)y->ptr, y->ld, y->h, y->w, argmax, total);
+  })
+  BASI_CHECK_LAUNCH("maxpool2s2_fwd");
+  return BASI_OK;
+}
+
+int basi_maxpool2s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi_tensor* dx, int accumulate,
+                        void* stream) {
+  BASI_CHECK_ARG(dy && dx && argmax && vec_ok(dy) && vec_ok(dx) && dx->dtype == dy->dtype && dx->c == dy->c &&
+                     dx->n == dy->n && dy->h == dx->h / 2 && dy->w == dx->w / 2, "maxpool2s2 bwd: bad tensors");
+  DISPATCH_T(dx->dtype, {
+    int64_t total = pixels(dx) * (dx->c / Vec<T>::N);
+    basi::launch(maxpool2s2_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld,
+                 dy->h, dy->w, argmax, (T*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, accumulate, total);
+  })
+  BASI_CHECK_LAUNCH("maxpool2s2_bwd");
+  return BASI_OK;
 }
 
 int basi_maxpool3s2_fwd(const basi_tensor* x, const basi_tensor* y, uint8_t* argmax, void* stream) {

@@ -34,6 +34,8 @@ What each function restates (paths relative to /root/reference):
                              5COCO/BAISPSPNet.py:716-737
 * ``losses`` / ``train_step``back/{1NoClass,2AddClass,4BorderClass,5COCO}/BAISRunnerTrain.py
                              build_net (loss, poly LR, plain SGD)
+* ``linknet_b_*``            variant B: slim/nets/vgg.py:187-196 (vgg_16 trunk), back/90AttentionSingle2/BAISNet.py
+                             :653-810 (LinkNet._attention / _classifies / build), BAISRunnerTrain.py:116-156 (cal_loss)
 * ``pspnet_forward_rounded`` the same forward with 16-bit storage roundings injected (no reference counterpart:
                              the noise model the bf16 CUDA path is measured against)
 * ``predict_*``              back/2AddClass/BAISRunnerTrain.py:88-89,
@@ -388,6 +390,139 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
         out[k_] = v.permute(0, 2, 3, 1) if v.dim() == 4 else v
     out["__nchw__"] = {k_: L[k_] for k_ in keep}     # graph tensors (for activation gradients)
     return out
+
+
+# --------------------------------------------------------------------------
+# F1: variant B -- slim vgg_16 trunk + click-gated attention cascade (back/90AttentionSingle2/BAISNet.py:653-810)
+# --------------------------------------------------------------------------
+
+VGG_BLOCKS = ((1, 2, 64), (2, 2, 128), (3, 3, 256), (4, 3, 512), (5, 3, 512))      # slim/nets/vgg.py:187-196
+
+
+def linknet_b_specs(num_classes=21, width=1.0):
+    """Ordered {tf variable name: shape}.  width scales the vgg_16 channel counts (1.0 = the reference; tests use
+    narrower trunks).  Attention / decoder scopes as in LinkNet.build (:756-810) and _attention / _classifies."""
+    specs = OrderedDict()
+
+    def conv(name, k, cin, cout, biased):
+        specs[name + "/weights"] = (k, k, cin, cout)
+        if biased:
+            specs[name + "/biases"] = (cout,)
+
+    def bn(name, c):      # tf.layers.batch_normalization(name=leaf) inside variable_scope(leaf): doubled leaf scope
+        leaf = name.split("/")[-1]
+        specs["%s/%s/gamma" % (name, leaf)] = (c,)
+        specs["%s/%s/beta" % (name, leaf)] = (c,)
+
+    cin = 3
+    ch = {}
+    for blk, reps, c in VGG_BLOCKS:
+        c = max(8, int(c * width))
+        for r in range(1, reps + 1):
+            conv("vgg_16/conv%d/conv%d_%d" % (blk, blk, r), 3, cin, c, True)
+            cin = c
+        ch[blk] = c
+    c1, c2, c3, c4 = ch[2], ch[3], ch[4], ch[5]          # block1..block4 = conv2_2, conv3_3, conv4_3, conv5_3
+    for lvl, cin_a, c_in_size, c_out in ((4, 2 * c4, c4, c3), (3, c3 + c3, c3, c2), (2, c2 + c2, c2, c1),
+                                         (1, c1 + c1, c1, c1)):
+        sc = "attention_%d/attention_%d_attention" % (lvl, lvl)
+        conv(sc + "/a_conv_1", 3, cin_a, c_in_size // 4, False); bn(sc + "/a_conv_1_bn", c_in_size // 4)
+        conv(sc + "/a_conv_2", 3, c_in_size // 4, 32, False); bn(sc + "/a_conv_2_bn", 32)
+        conv(sc + "/a_conv_3", 1, 32, 2, True)
+        conv(sc + "/a_conv_o", 1, cin_a, c_out, False)
+        if lvl == 4:
+            dc = "attention_4/segment_attention_4_decoder"
+            conv(dc + "/d_c_conv_1", 3, c3, c4, False); bn(dc + "/d_c_conv_1_bn", c4)
+            conv(dc + "/d_c_conv_2", 3, c4, 2 * c4, False); bn(dc + "/d_c_conv_2_bn", 2 * c4)
+            conv(dc + "/class_attention_conv", 3, 2 * c4, 4 * c4, True)
+            specs[dc + "/class_attention_fc/weights"] = (4 * c4, num_classes)
+            specs[dc + "/class_attention_fc/biases"] = (num_classes,)
+    return specs
+
+
+def linknet_b_forward(params, image_nhwc, mask_nhw1, p_size=None, thr=0.9):
+    """LinkNet.build of snapshot 90AttentionSingle2 (:756-810): returns (attention logits [4 x NHWC, coarse -> fine],
+    class logits).  p_size: class-head pooling window (reference 15 at S = 720; default block4 size // 3)."""
+    def W(n):
+        return params[n + "/weights"]
+
+    def BN(x, n, relu):
+        leaf = n.split("/")[-1]
+        return batch_norm(x, params["%s/%s/gamma" % (n, leaf)], params["%s/%s/beta" % (n, leaf)], relu)
+
+    x = image_nhwc.permute(0, 3, 1, 2)
+    mask = mask_nhw1.permute(0, 3, 1, 2)
+    blocks = {}
+    for blk, reps, _ in VGG_BLOCKS:
+        for r in range(1, reps + 1):
+            n = "vgg_16/conv%d/conv%d_%d" % (blk, blk, r)
+            x = F.relu(conv2d(x, W(n), 1, "SAME", bias=params[n + "/biases"]))
+        blocks[blk] = x
+        if blk < 5:
+            x = F.max_pool2d(x, 2, 2)
+    b1, b2, b3, b4 = blocks[2], blocks[3], blocks[4], blocks[5]
+    attentions = []
+    p = resize_nearest(mask, b4.shape[2:4])
+    f4 = mask_multiply(b4, p)
+    feat = torch.cat([f4, f4], dim=1)
+    cls = None
+    up = None
+    for lvl, blk, nxt in ((4, b4, b3), (3, b3, b2), (2, b2, b1), (1, b1, b1)):
+        if lvl != 4:
+            feat = torch.cat([mask_multiply(blk, p), up], dim=1)
+        sc = "attention_%d/attention_%d_attention" % (lvl, lvl)
+        a = BN(conv2d(feat, W(sc + "/a_conv_1"), 1, "SAME"), sc + "/a_conv_1_bn", True)
+        a = BN(conv2d(a, W(sc + "/a_conv_2"), 1, "SAME"), sc + "/a_conv_2_bn", True)
+        logit = conv2d(a, W(sc + "/a_conv_3"), 1, bias=params[sc + "/a_conv_3/biases"])
+        attentions.append(logit.permute(0, 2, 3, 1))
+        gate = attention_gate(logit, 1, thr)
+        out = conv2d(mask_multiply(feat, gate), W(sc + "/a_conv_o"), 1)
+        if lvl == 4:
+            dc = "attention_4/segment_attention_4_decoder"
+            c = BN(conv2d(out, W(dc + "/d_c_conv_1"), 1, "SAME"), dc + "/d_c_conv_1_bn", True)
+            c = BN(conv2d(c, W(dc + "/d_c_conv_2"), 1, "SAME"), dc + "/d_c_conv_2_bn", True)
+            ps = p_size if p_size is not None else c.shape[2] // 3
+            c = avg_pool(c, ps)
+            c = F.relu(conv2d(c, W(dc + "/class_attention_conv"), 3, bias=params[dc + "/class_attention_conv/biases"]))
+            assert c.shape[2] == 1 and c.shape[3] == 1
+            cls = c[:, :, 0, 0] @ params[dc + "/class_attention_fc/weights"] + params[dc + "/class_attention_fc/biases"]
+        up = resize_nearest(out, nxt.shape[2:4])
+        p = resize_nearest(gate, nxt.shape[2:4])
+    return attentions, cls
+
+
+def linknet_b_losses(attentions, cls_logits, label_seg_nhw1, label_cls, pos_weight=3.0):
+    """cal_loss of back/90AttentionSingle2/BAISRunnerTrain.py:116-156: per attention map the labels are nearest-resized,
+    one-hot (depth 2) and scored with weighted_cross_entropy_with_logits(pos_weight=3) averaged over ALL 2N elements;
+    loss = mean over the maps + mean softmax CE of the class head."""
+    lab = label_seg_nhw1.permute(0, 3, 1, 2).to(attentions[0].dtype)
+    terms = []
+    for a in attentions:
+        z = resize_nearest(lab, a.shape[1:3]).permute(0, 2, 3, 1).reshape(-1).long()
+        t = F.one_hot(z, 2).to(a.dtype)
+        terms.append(weighted_cross_entropy_with_logits(t, a.reshape(-1, 2), pos_weight).mean())
+    loss_att = sum(terms) / len(terms)
+    loss_cls = F.cross_entropy(cls_logits, label_cls.long(), reduction="mean")
+    return loss_att + loss_cls, loss_att, loss_cls
+
+
+def linknet_b_train_step(params_np, image, mask, label_seg, label_cls, lr=5e-3, dtype=torch.float64, p_size=None,
+                         pos_weight=3.0):
+    p = to_torch(params_np, dtype, requires_grad=True)
+    att, cls = linknet_b_forward(p, torch.as_tensor(np.asarray(image)).to(dtype),
+                                 torch.as_tensor(np.asarray(mask)).to(dtype), p_size)
+    loss, la, lc = linknet_b_losses(att, cls, torch.as_tensor(np.asarray(label_seg)), torch.as_tensor(np.asarray(label_cls)),
+                                    pos_weight)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    g, new = OrderedDict(), OrderedDict()
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(p[n]) if gr is None else gr
+        g[n] = gr.detach().numpy()
+        new[n] = (p[n].detach() - torch.tensor(lr, dtype=dtype) * gr).numpy()
+    return {"loss": float(loss.detach()), "loss_attention": float(la.detach()), "loss_classes": float(lc.detach()),
+            "attentions": [a.detach().numpy() for a in att], "cls_logits": cls.detach().numpy(), "grads": g,
+            "new_params": new}
 
 
 # --------------------------------------------------------------------------

@@ -338,3 +338,91 @@ def test_fused_bn_backward_in_dgrad_matches_separate_kernels(monkeypatch):
     a, b = res["0"][1], res["1"][1]
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos > 0.98, cos
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F1: variant B (slim vgg_16 trunk + click-gated attention cascade, back/90AttentionSingle2)
+# ---------------------------------------------------------------------------------------------------------------
+def _variant_b_case(S, B, width, seed=0):
+    rng = np.random.RandomState(seed)
+    img = rng.rand(B, S, S, 3).astype(np.float32)
+    clicks = [[int(rng.randint(S // 4, 3 * S // 4)), int(rng.randint(S // 4, 3 * S // 4))] for _ in range(B)]
+    mask = np.stack([O.mask_gaussian((S, S), c) for c in clicks])[..., None]
+    lab = np.zeros((B, S // 8, S // 8, 1), dtype=np.float32)
+    for b in range(B):
+        cy, cx = clicks[b][0] // 8, clicks[b][1] // 8
+        lab[b, max(0, cy - 2):cy + 3, max(0, cx - 2):cx + 3, 0] = 1
+    cls = rng.randint(1, 21, size=(B,)).astype(np.int32)
+    params = O.init_params(O.linknet_b_specs(21, width), seed + 1, trained_like=True)
+    # lower the attention threshold's effect: make a_conv_3 biases favour channel 1 so the hard gate passes pixels
+    for lvl in (4, 3, 2, 1):
+        params["attention_%d/attention_%d_attention/a_conv_3/biases" % (lvl, lvl)] = np.asarray([-2.0, 2.0], np.float32)
+    return img, mask, lab, cls, params
+
+
+@pytest.mark.parametrize("precision", ["f32"])
+def test_variant_b_train_step_matches_oracle(precision):
+    """Whole variant-B net (vgg_16 trunk at 1/8 width, attention cascade x4, class head) forward / loss / backward /
+    SGD against the float64 oracle (oracle.linknet_b_train_step)."""
+    from basi_b200.BAISNet import LinkNet, Placeholder
+    from basi_b200.engine import Engine
+    S, B, width = 96, 2, 0.125
+    img, mask, lab, cls, params = _variant_b_case(S, B, width)
+    net = LinkNet(Placeholder((None, S, S, 3)), Placeholder((None, S, S, 1), name="mask"), num_classes=21, width=width)
+    eng = Engine(net, B, precision, True, dict(kind="linknet_b", pos_weight=3.0, class_weight=1.0))
+    eng.set_params(params)
+    lr = 5e-3
+    eng.feed(img, lab, cls, lr, mask=mask)
+    eng.step_device()
+    torch.cuda.synchronize()
+    ref = O.linknet_b_train_step(params, img, mask, lab, cls, lr, torch.float64)
+    r32 = O.linknet_b_train_step(params, img, mask, lab, cls, lr, torch.float32)
+    loss, latt, lcls = eng.losses()
+    assert abs(latt - ref["loss_attention"]) < F32_TOL * max(1, abs(ref["loss_attention"])), (latt, ref["loss_attention"])
+    assert abs(lcls - ref["loss_classes"]) < F32_TOL * max(1, abs(ref["loss_classes"])), (lcls, ref["loss_classes"])
+    for i, a in enumerate(eng.att_logits):
+        e = _rel(a.t.cpu().numpy(), ref["attentions"][i])
+        assert e < F32_TOL + 3 * _rel(r32["attentions"][i], ref["attentions"][i]), (i, e)
+    # the hard gate lets a useful fraction of the pixels through (otherwise the cascade is untested)
+    gates = [float((torch.softmax(torch.from_numpy(a), -1)[..., 1] > 0.9).float().mean()) for a in ref["attentions"]]
+    assert max(gates) > 0.05, gates
+    grads = eng.get_grads()
+    bad = []
+    for n in grads:
+        if np.max(np.abs(ref["grads"][n])) <= 1e-12:
+            assert np.max(np.abs(grads[n])) <= 1e-12, n          # dead-end tensors (finest a_conv_o) stay zero
+            continue
+        e, floor = _rel2(grads[n], ref["grads"][n]), _rel2(r32["grads"][n], ref["grads"][n])
+        if e > F32_TOL + 10 * floor:
+            bad.append((n, e, floor))
+    assert not bad, bad[:5]
+    new = eng.get_params()
+    worst = max((_rel(new[n], ref["new_params"][n]) - 10 * _rel(r32["new_params"][n], ref["new_params"][n]), n) for n in new)
+    assert worst[0] < F32_TOL, worst
+    pred = np.argmax(eng.att_logits[-1].t.cpu().numpy(), -1)
+    assert np.array_equal(eng.pred_seg.cpu().numpy()[..., 0], pred.astype(np.int32))
+
+
+def test_variant_b_bf16_runs_and_tracks_f32():
+    """bf16 storage for the BN'd attention / decoder layers (tcgen05 where the shapes allow): finite, close to f32."""
+    from basi_b200.BAISNet import LinkNet, Placeholder
+    from basi_b200.engine import Engine
+    S, B, width = 96, 2, 0.25
+    img, mask, lab, cls, params = _variant_b_case(S, B, width, seed=3)
+    out = {}
+    for prec in ("f32", "bf16"):
+        net = LinkNet(Placeholder((None, S, S, 3)), Placeholder((None, S, S, 1), name="mask"), num_classes=21, width=width)
+        eng = Engine(net, B, prec, True, dict(kind="linknet_b"))
+        eng.set_params(params)
+        eng.feed(img, lab, cls, 5e-3, mask=mask)
+        eng.step_device()
+        torch.cuda.synchronize()
+        out[prec] = (eng.losses(), eng.att_logits[0].t.float().cpu().numpy(), eng.att_logits[-1].t.float().cpu().numpy())
+        assert all(np.isfinite(v).all() for v in eng.get_grads().values())
+        del eng
+    assert abs(out["bf16"][0][0] - out["f32"][0][0]) < 5e-2 * abs(out["f32"][0][0])
+    # the coarsest attention map sees no gate: bf16 storage noise only.  Finer maps sit behind the hard gate
+    # tf.where(p > 0.9, p, 0): a pixel whose p crosses 0.9 under bf16 noise switches its whole feature column on or
+    # off, so they are only required to stay in the same ballpark
+    assert _rel2(out["bf16"][1], out["f32"][1]) < 5e-2
+    assert _rel2(out["bf16"][2], out["f32"][2]) < 0.6
