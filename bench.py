@@ -45,6 +45,10 @@ WORKLOADS = {
                  text="cfg5: COCO-shape joint training (5COCO head, 81 classes, sigma 20, 0.2*loss_classes), synthetic "
                       "640x640, batch 16 per GPU (128 on 8 GPUs), F=32, SGD"),
 }
+WORKLOADS["variantB"] = dict(
+    variant="90AttentionSingle2", S=320, batch=8, classes=21, flop_per_image=3 * 2 * 31.0e9 * (320.0 / 224.0) ** 2,
+    text="F1: variant B (slim vgg_16 trunk + click-gated attention cascade, 90AttentionSingle2), synthetic 320x320, "
+         "batch 8 per GPU, SGD; the biased vgg convolutions run on the CUDA-core fp32 path")
 DEFAULT_WORKLOAD = "cfg3"
 GOLDEN_IMAGE = os.path.join(ROOT, "tests", "golden", "input_7.jpg")     # the reference's input/7.jpg (cfg1)
 
@@ -130,14 +134,18 @@ def cpu_oracle_rate(wl, batch, steps, warmup=1):
     snap = _snapshot(variant)
     nseg = snap["num_segment"]
     sd = SyntheticData(batch, (S, S), 8, classes, nseg, sigma=20 if variant == "5COCO" else 30, seed=0)
-    params = O.init_params(O.param_specs(variant, classes, nseg, FILTERS), 0)
+    vb = variant == "90AttentionSingle2"
+    params = O.init_params(O.linknet_b_specs(classes, 1.0) if vb else O.param_specs(variant, classes, nseg, FILTERS), 0)
     times = []
     for i in range(warmup + steps):
         img, clicks, lab, cls = sd.next_batch()
         t0 = time.perf_counter()
         data = np.stack([O.pack_input(img[b], clicks[b], sd.sigma) for b in range(batch)])
-        r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, snap["pos_weight"], snap["class_weight"],
-                         5e-3, torch.float32)
+        if vb:
+            r = O.linknet_b_train_step(params, data[..., :3], data[..., 3:4], lab, cls, 5e-3, torch.float32)
+        else:
+            r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, snap["pos_weight"], snap["class_weight"],
+                             5e-3, torch.float32)
         params = r["new_params"]
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -339,7 +347,8 @@ def measure(args, wl_name, dp, device, dev_index, rank, world, want_profile):
     wl = WORKLOADS[wl_name]
     S, B = wl["S"], wl["batch"]
     tr = Train(batch_size=B, last_pool_size=S // 8, input_size=[S, S], log_dir="/tmp/basi_bench_%d" % rank,
-               variant=wl["variant"], num_classes=wl["classes"], precision=args.precision, filter_number=FILTERS,
+               variant=wl["variant"], num_classes=wl["classes"], precision=args.precision,
+               filter_number=64 if wl["variant"] == "90AttentionSingle2" else FILTERS,
                seed=0, device=device, dp=dp, use_cuda_graph=not args.no_graph, use_tc=not args.no_tc)
     eng = tr.engine
     sd = tr.data_reader

@@ -176,6 +176,14 @@ int basi_bn_bwd_fused(const basi_tensor* dout, const basi_tensor* x, const float
                       double count, float* dgamma, float* dbeta, float* coef, uint32_t* barrier,
                       const basi_tensor* dx, void* stream);
 
+/* F1: adjoint of the slim conv2d epilogue y = relu(conv + bias): dy *= (y > 0) in place (relu != 0) and
+ * dbias[c] += sum of the masked dy over the pixels (dbias may be NULL). */
+int basi_bias_relu_bwd(const basi_tensor* dy, const basi_tensor* y, int relu, float* dbias, void* stream);
+/* F2: Net.add of the top-level LinkNet (BAISNet.py:244, tf.add_n of two tensors, no batch norm) and its adjoint:
+ * da (+)= dout, db (+)= dout (either may be NULL). */
+int basi_add_fwd(const basi_tensor* a, const basi_tensor* b, const basi_tensor* out, void* stream);
+int basi_add_bwd(const basi_tensor* dout, const basi_tensor* da, int acc_a, const basi_tensor* db, int acc_b,
+                 void* stream);
 /* F1: tf.one_hot(labels, depth=2) as float32 pairs (targets of the 2-channel weighted CE of variant B,
  * back/90AttentionSingle2/BAISRunnerTrain.py:128-131); labels float32 {0,1}, out float32 [n][2]. */
 int basi_onehot2_f32(const float* labels, float* out, int64_t n, void* stream);
@@ -324,6 +332,8 @@ int basi_tc_conv_set_bn_apply(basi_tc_conv* plan, const basi_tensor* out, int re
  * needed for that layer), 0 if it cannot be fused. */
 int basi_tc_conv_set_bn_bwd(basi_tc_conv* plan, const basi_tensor* x, const float* bnp, int relu, double* dsums,
                             double count, float* dgamma, float* dbeta, uint32_t* counter);
+/* fprop plans: y = [relu](conv(x, w) + bias[c]) in the epilogue (slim/nets/vgg.py:187-196 convolutions of variant B) */
+int basi_tc_conv_set_bias(basi_tc_conv* plan, const float* bias, int relu);
 int basi_tc_conv_run(basi_tc_conv* plan, void* stream);
 void basi_tc_conv_destroy(basi_tc_conv* plan);
 

@@ -71,7 +71,7 @@ class LinkNet(Network):
         self.feed(blocks[4], 'mask_block4').mask_multiply(name='block4_attention_multiply_add')
         self.feed(blocks[4], 'mask_block4').mask_multiply(name='block4_attention_multiply_add_b')
         (self.feed('block4_attention_multiply_add', 'block4_attention_multiply_add_b')
-         .concat(axis=-1, dtype="f32", name='attention_4_concat'))
+         .concat(axis=-1, name='attention_4_concat'))
         sc = self._attention(4, 'attention_4_concat', c4, c3, hw[3])
         # class decoder on the coarsest attention output
         dc = "attention_4/segment_attention_4_decoder"
@@ -90,5 +90,63 @@ class LinkNet(Network):
             (self.feed(blocks[lvl], sc + '/gate_resize')
              .mask_multiply(name='block%d_attention_multiply_add' % lvl))
             (self.feed('block%d_attention_multiply_add' % lvl, sc + '/a_conv_o_resize')
-             .concat(axis=-1, dtype="f32", name='attention_%d_concat' % lvl))
+             .concat(axis=-1, name='attention_%d_concat' % lvl))
             sc = self._attention(lvl, 'attention_%d_concat' % lvl, c_blk, c_out, hw[nxt])
+
+
+class LinkNetTop(Network):
+    """The current-HEAD network (BAISNet.py:117-269: ``LinkNet(input_data, is_training, num_classes).build()`` ->
+    ``(segments, features)``): vgg_16 trunk, per level a deep-supervised side head
+    (1x1 -> nearest resize -> 3x3 -> 1x1 -> 3x3 to 2 logits) and a decoder (1x1 -> nearest resize -> 3x3 -> 1x1), one
+    residual add at block1, a final 3x3 head; every convolution has bias (+ReLU except the logit heads), no BN.
+    Labels are full-resolution {0,1} maps (label_stride 1); the loss is ``cal_loss`` of BAISRunnerTrain.py:97-115."""
+
+    label_stride = 1
+
+    def __init__(self, input_data, is_training=True, num_classes=21, width=1.0):
+        self.width = width
+        self.attentions, self.classes, self.segments = [], [], []     # (attentions: the engine's name for the 2-ch heads)
+        Network.__init__(self, {'data': input_data}, num_classes, 2, True, is_training)
+
+    def build(self):
+        return self.segments, {"segment": self.decoder_outputs}
+
+    def _decoder(self, source, scope, c_in, c_out, out_hw, head):
+        (self.feed(source)
+         .conv(1, 1, c_in // 4, 1, 1, biased=True, relu=True, padding='SAME', name=scope + '/d_s_conv_1')
+         .resize_nearest(out_hw, name=scope + '/resize')
+         .conv(3, 3, c_in // 4, 1, 1, biased=True, relu=True, padding='SAME', name=scope + '/d_s_conv_2')
+         .conv(1, 1, c_out, 1, 1, biased=True, relu=True, name=scope + '/d_s_conv_3'))
+        if head:
+            self.conv(3, 3, 2, 1, 1, biased=True, relu=False, name=scope + '/d_s_conv_4')     # (VALID: the map shrinks by 2)
+            return scope + '/d_s_conv_4'
+        return scope + '/d_s_conv_3'
+
+    def setup(self, is_training, num_classes, num_segment, last_pool_size, filter_number):
+        ch = {}
+        self.feed('data')
+        for blk, reps, c in VGG_BLOCKS:
+            c = max(8, int(c * self.width))
+            for r in range(1, reps + 1):
+                self.conv(3, 3, c, 1, 1, biased=True, relu=True, padding='SAME',
+                          name='vgg_16/conv%d/conv%d_%d' % (blk, blk, r))
+            ch[blk] = c
+            if blk < 5:
+                self.max_pool(2, 2, 2, 2, name='vgg_16/pool%d' % blk)
+        blocks = {1: 'vgg_16/conv2/conv2_2', 2: 'vgg_16/conv3/conv3_3', 3: 'vgg_16/conv4/conv4_3',
+                  4: 'vgg_16/conv5/conv5_3'}
+        c = {1: ch[2], 2: ch[3], 3: ch[4], 4: ch[5]}
+        hw = {k: self.layers[v].shape[:2] for k, v in blocks.items()}
+        self.decoder_outputs = []
+        cur = blocks[4]
+        for lvl, nxt in ((4, 3), (3, 2), (2, 1), (1, 1)):
+            if lvl == 1:
+                self.feed(blocks[1], cur).add(name='attention_1/add')
+                cur = 'attention_1/add'
+            head = self._decoder(cur, "attention_%d/segment_side_%d" % (lvl, lvl), c[lvl], c[nxt], hw[nxt], True)
+            self.attentions.append(self.layers[head])
+            cur = self._decoder(cur, "attention_%d/%d" % (lvl, lvl), c[lvl], c[nxt], hw[nxt], False)
+            self.decoder_outputs.append(self.layers[cur])
+        self.feed(cur).conv(3, 3, 2, 1, 1, biased=True, relu=False, name='attention_0')
+        self.attentions.append(self.layers['attention_0'])
+        self.segments = list(self.attentions)

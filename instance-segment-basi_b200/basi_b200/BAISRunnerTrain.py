@@ -24,6 +24,10 @@ SNAPSHOT = {
     "3ThreeClass": dict(num_segment=3, kind="softmax", pos_weight=1.0, class_weight=0.1, lr=5e-3, num_steps=500001),
     "4BorderClass": dict(num_segment=4, kind="softmax", pos_weight=1.0, class_weight=0.1, lr=5e-3, num_steps=500001),
     "5COCO": dict(num_segment=3, kind="softmax", pos_weight=1.0, class_weight=0.2, lr=5e-3, num_steps=1000001),
+    # variant B (back/90AttentionSingle2/BAISRunnerTrain.py:30-52,116-156): vgg_16 trunk + attention cascade,
+    # loss = mean 2-channel weighted CE of the four attention maps + class CE
+    "90AttentionSingle2": dict(num_segment=1, kind="linknet_b", pos_weight=3.0, class_weight=1.0, lr=5e-3,
+                               num_steps=500001),
 }
 
 
@@ -76,6 +80,17 @@ class Train(object):
             self.engine.broadcast_params(dp)       # every replica starts from rank 0's weights
 
     def build_net(self, precision="bf16", device=None, use_tc=True):
+        if self.variant == "90AttentionSingle2":
+            from .BAISNet import LinkNet
+            net = LinkNet(Placeholder((None, self.input_size[0], self.input_size[1], 3)),
+                          Placeholder((None, self.input_size[0], self.input_size[1], 1), name="mask"),
+                          is_training=True, num_classes=self.num_classes, width=self.filter_number / 64.0)
+            engine = Engine(net, self.batch_size, precision, True, self.loss_cfg, device, use_tc)
+            if self.synthetic:
+                engine.enable_click_input(self.data_reader.sigma)
+            self.raw_output_segment = net.attentions[-1]
+            self.raw_output_classes = net.classes[0]
+            return net, engine
         image_placeholder = Placeholder((None, self.input_size[0], self.input_size[1], 4))
         net = PSPNet({'data': image_placeholder}, is_training=True, num_classes=self.num_classes,
                      num_segment=self.num_segment, last_pool_size=self.last_pool_size,
@@ -115,8 +130,14 @@ class Train(object):
         pred_seg = eng.pred_seg.cpu().numpy()
         out = dict(loss=loss, loss_segment=loss_seg, loss_classes=loss_cls, learning_rate=lr,
                    raw_output_segment=raw, pred_segment=pred_seg)
-        lab = np.asarray(label_seg).reshape(pred_seg.shape)
-        if self.num_segment == 1:
+        if self.variant == "90AttentionSingle2":
+            out["raw_output_attentions"] = [a.t.cpu().numpy() for a in eng.att_logits]
+            lab = None
+        else:
+            lab = np.asarray(label_seg).reshape(pred_seg.shape)
+        if lab is None:
+            pass
+        elif self.num_segment == 1:
             out["accuracy_0"] = float(np.mean(raw.reshape(-1) > 0.5))
             out["accuracy_1"] = float(np.mean(lab.reshape(-1) > 0.5))
         else:

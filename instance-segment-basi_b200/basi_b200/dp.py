@@ -37,6 +37,8 @@ class DataParallel(object):
                 kw["device_id"] = self.device
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
         self.bucket_bytes = int(bucket_bytes)
+        if os.environ.get("BASI_EXPERIMENTS") == "1" and os.environ.get("BASI_DP_BUCKET_MB"):
+            self.bucket_bytes = int(float(os.environ["BASI_DP_BUCKET_MB"]) * (1 << 20))     # experiment: bucket size
         self.comm_stream = torch.cuda.Stream(self.device) if backend == "nccl" else None
         self._plan = None
 

@@ -322,9 +322,16 @@ class Engine(object):
 
     def _lower_data(self, n):
         h, w, c = n.shape
-        a = Act(self._alloc((self.B, h, w, c), torch.float32))
+        if hasattr(self.net, "attentions"):
+            # variant B: image (3 ch) and click map (1 ch) are two placeholders; both are channel-slice views of ONE
+            # NHWC4 float32 buffer so that basi_clickmap_pack (uint8 image + click -> NHWC4) feeds them directly
+            if getattr(self, "_input4", None) is None:
+                self._input4 = self._alloc((self.B, h, w, 4), torch.float32)
+            a = Act(self._input4[..., 3:4] if n.name == "mask" else self._input4[..., 0:3])
+        else:
+            a = Act(self._alloc((self.B, h, w, c), torch.float32))
         self._acts[n.index] = a
-        if n.name == "mask":              # variant B: the click map is a separate 1-channel input (no gradient)
+        if n.name == "mask":              # the click map needs no gradient
             self.input_mask = a
             a.no_grad = True
         else:
@@ -372,7 +379,10 @@ class Engine(object):
                                              K=25 * x.shape[3], N=co)))
             self._emit_skinny_fwd(self._ops[-1][1])
             return
-        f32_out = (not has_bn)
+        # slim conv2d of the vgg_16 trunk (variant B): bias + ReLU, no BN.  In bf16 mode these stay bf16 so that they
+        # run on the tcgen05 path (bias + ReLU in its epilogue); every other BN-less conv is a float32 head
+        vgg_like = (hasattr(self.net, "attentions") and self.precision == "bf16" and not has_bn and s == 1 and co > 4)
+        f32_out = (not has_bn) and not vgg_like
         y = self._out_act(n, torch.float32 if f32_out else None)
         desc = ConvDesc(k, a["k_w"], s, d, pt, pl, 1 if (a["relu"] and not has_bn) else 0)
         self._keep.append(desc)
@@ -453,7 +463,15 @@ class Engine(object):
         self._emit_bnact_fwd(op)
 
     def _lower_add(self, n):
-        pass  # materialised by the following relu (junction)
+        ins = [self._acts[i.index] for i in n.inputs]
+        if len(ins) == 2 and all(isinstance(i, Act) for i in ins):
+            # plain tensor add without batch norm (top-level LinkNet, BAISNet.py:244)
+            a, b = ins
+            y = self._out_act(n, a.t.dtype)
+            self._acts[n.index] = y
+            self._ops.append(("add", dict(a=a, b=b, y=y)))
+            self._call(self.fwd, "basi_add_fwd", a.ref, b.ref, y.ref)
+        # else: a residual junction, materialised by the following relu
 
     def _lower_concat(self, n):
         pass  # producers already wrote into the slices
@@ -600,10 +618,19 @@ class Engine(object):
     def _emit_conv_fwd(self, op):
         x, y = op["x"], op["y"]
         bptr = self._pptr(op["b"]) if op["b"] else None
-        if self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]:
-            if _lib.load().basi_tc_conv_supported(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
+        if self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and (not op["b"] or op["relu"]):
+            # (the descriptor's relu flag belongs to the CUDA-core path; the tcgen05 plan takes bias / ReLU separately)
+            d0 = ConvDesc(op["desc"].kh, op["desc"].kw, op["desc"].stride, op["desc"].dil, op["desc"].pad_t,
+                          op["desc"].pad_l, 0)
+            if _lib.load().basi_tc_conv_supported(_lib.TC_FPROP, C.byref(d0), x.ref, y.ref) == 1:
+                if op["b"]:
+                    self._keep.append(d0)
+                    op["desc_simt"], op["desc"], op["tc_bias"] = op["desc"], d0, True
                 op["tc_fprop"] = self._emit_tc(op, _lib.TC_FPROP, self.fwd)
-                self._tc_producer[id(y)] = op
+                if op["b"]:
+                    _lib.call("basi_tc_conv_set_bias", op["tc_fprop"], bptr, 1 if op["relu"] else 0)
+                else:
+                    self._tc_producer[id(y)] = op
                 return
         if self.split_tc and x.dtype == _lib.F32 and y.dtype == _lib.F32 and not op["b"] and not self.dry_run:
             if _lib.load().basi_tc_conv_supported_split(_lib.TC_FPROP, C.byref(op["desc"]), x.ref, y.ref) == 1:
@@ -683,7 +710,8 @@ class Engine(object):
         self.cls_name = "class_attention_fc" if net.classes else None
         B = self.B
         S_h, S_w = self.input.shape[1], self.input.shape[2]
-        P_h, P_w = S_h // 8, S_w // 8
+        stride = int(getattr(net, "label_stride", 8))          # variant B: labels at S/8; top-level LinkNet: full size
+        P_h, P_w = S_h // stride, S_w // stride
         self.loss_acc = self._zeros(4, torch.float64)
         self.pred_seg = self._zeros((B, heads[-1].shape[1], heads[-1].shape[2], 1), torch.int32)
         self.pred_cls = self._zeros((B,), torch.int32) if self.cls_logits is not None else None
@@ -811,6 +839,13 @@ class Engine(object):
         self.bwd.extend(self._deferred_bwd)
         self._deferred_bwd = []
 
+    def _bwd_add(self, op):
+        a, b, y = op["a"], op["b"], op["y"]
+        if y.grad is None or not y.gw:
+            return
+        acc_a, acc_b = self._acc_flag(a), self._acc_flag(b)
+        self._call(self.bwd, "basi_add_bwd", y.grad.ref, a.grad.ref, acc_a, b.grad.ref, acc_b)
+
     def _bwd_maxpool2(self, op):
         x, y = op["x"], op["y"]
         if y.grad is None or not y.gw:
@@ -853,13 +888,17 @@ class Engine(object):
         if hasattr(self.net, "attentions") and (dy is None or not y.gw):
             return                                   # variant B: the finest attention output feeds nothing
         assert dy is not None and y.gw, "conv %s: no gradient reaches its output" % op["name"]
-        if op["relu"]:
-            assert y.dtype == _lib.F32
+        if op["relu"] and y.dtype == _lib.F32 and y.desc.ld == y.desc.c:
             n = int(np.prod(y.shape))
             self._call(self.bwd, "basi_relu_bwd_f32", dy.t.data_ptr(), y.t.data_ptr(), C.c_int64(n))
+        elif op["relu"]:
+            # 16-bit (or strided) outputs: mask dy in place; on the tcgen05 path the same pass also reduces dbias
+            self._call(self.bwd, "basi_bias_relu_bwd", dy.ref, y.ref, 1,
+                       self._gptr(op["b"]) if op.get("tc_bias") else None,
+                       writes=[op["b"]] if op.get("tc_bias") else [])
         dptr = C.byref(op["desc"])
         need_dx = x is not self.input
-        tc_ok = self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and not op["b"]
+        tc_ok = self.use_tc and x.dtype == _lib.BF16 and y.dtype == _lib.BF16 and (not op["b"] or op.get("tc_bias"))
         lib = _lib.load()
         if op.get("split"):
             # fp32-grade tensor-core path: dy is split once, wgrad and dgrad both read the parts

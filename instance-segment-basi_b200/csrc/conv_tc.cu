@@ -180,6 +180,8 @@ struct ConvParams {
   // relu(scale * acc + shift) -- normalised from the fp32 accumulators -- through mapD2.  Removes the separate
   // bn_apply launch, one read pass over the conv output and one rounding per layer.
   int fuse_apply, apply_relu;
+  const float* bias;     // fprop: optional per-channel bias added in the epilogue (slim vgg_16 convolutions, variant B)
+  int bias_relu;         // ... followed by ReLU
   int keep_acc;      // fuse_apply || fuse_bwd: accumulators stay in TMEM (one column block and one barrier per work item)
   // fused BN backward (dgrad plans): the accumulator is dA, the gradient wrt the activated output of the layer that
   // produced this plan's destination.  Pass 1 loads the matching tile of that layer's raw conv output x (mapD2),
@@ -858,6 +860,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           continue;
         }
         tmem_ld32(taddr + c * 32, r);
+        if (p.bias != nullptr) {
+          const float* bp = p.bias + nt * BN + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + __ldg(bp + j);
+            if (p.bias_relu) v = fmaxf(v, 0.f);
+            r[j] = __float_as_uint(v);
+          }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -1986,6 +1997,14 @@ int basi_tc_conv_set_bn_bwd(basi_tc_conv* pl, const basi_tensor* x, const float*
   cp.bwd_count = count;
   cp.bwd_counter = counter;
   return 1;
+}
+
+/* fprop plans: y = [relu](conv(x, w) + bias) -- the slim conv2d of vgg_16 (bias + ReLU, no batch norm) */
+int basi_tc_conv_set_bias(basi_tc_conv* pl, const float* bias, int relu) {
+  BASI_CHECK_ARG(pl && pl->kind == BASI_TC_FPROP && bias && !pl->split, "tc_conv_set_bias: needs a bf16 fprop plan");
+  pl->cp.bias = bias;
+  pl->cp.bias_relu = relu ? 1 : 0;
+  return BASI_OK;
 }
 
 int basi_tc_conv_run(basi_tc_conv* pl, void* stream) {

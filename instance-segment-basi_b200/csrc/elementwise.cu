@@ -1158,6 +1158,85 @@ __global__ void onehot2_kernel(const float* __restrict__ lab, float2* __restrict
   }
 }
 
+// Adjoint of y = relu(conv + bias) for 16-bit / float32 activations: dy *= (y > 0) in place and
+// dbias[c] += sum over pixels of the masked dy (block partial sums in shared memory, one atomic per channel and block)
+template <typename T>
+__global__ void __launch_bounds__(256) bias_relu_bwd_kernel(T* __restrict__ dy, int lddy, const T* __restrict__ y, int ldy,
+                                                            int C, int64_t R, int relu, float* __restrict__ dbias) {
+  pdl_prologue();
+  extern __shared__ float bsum[];          // [C]
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bsum[c] = 0.f;
+  __syncthreads();
+  const int64_t total = R * cgs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t r = i / cgs;
+    Vec<T> g = Vec<T>::load(dy + r * lddy + cg * VN);
+    if (relu) {
+      Vec<T> v = Vec<T>::load(y + r * ldy + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) g.v[j] = v.v[j] > 0.f ? g.v[j] : 0.f;
+      g.store(dy + r * lddy + cg * VN);
+    }
+    if (dbias) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) atomicAdd(&bsum[cg * VN + j], g.v[j]);
+    }
+  }
+  __syncthreads();
+  if (dbias)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, bsum[c]);
+}
+
+// Plain tensor add (Net.add of the top-level LinkNet, BAISNet.py:244) and its adjoint (dA (+)= dOut, dB (+)= dOut)
+template <typename T>
+__global__ void add_fwd_kernel(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb, T* __restrict__ o,
+                               int ldo, int C, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t r = i / cgs;
+    Vec<T> x = Vec<T>::load(a + r * lda + cg * VN), y = Vec<T>::load(b + r * ldb + cg * VN);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) x.v[j] += y.v[j];
+    x.store(o + r * ldo + cg * VN);
+  }
+}
+template <typename T>
+__global__ void add_bwd_kernel(const T* __restrict__ g, int ldg, T* __restrict__ da, int lda, int acc_a, T* __restrict__ db,
+                               int ldb, int acc_b, int C, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t r = i / cgs;
+    const Vec<T> x = Vec<T>::load(g + r * ldg + cg * VN);
+    if (da) {
+      Vec<T> o = x;
+      if (acc_a) {
+        Vec<T> old = Vec<T>::load(da + r * lda + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o.v[j] += old.v[j];
+      }
+      o.store(da + r * lda + cg * VN);
+    }
+    if (db) {
+      Vec<T> o = x;
+      if (acc_b) {
+        Vec<T> old = Vec<T>::load(db + r * ldb + cg * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o.v[j] += old.v[j];
+      }
+      o.store(db + r * ldb + cg * VN);
+    }
+  }
+}
+
 extern "C" {
 
 const char* basi_last_error(void) { return g_err; }
@@ -1233,6 +1312,46 @@ static void same_pad_3s2(int in, int out, int* before) {
   int total = (out - 1) * 2 + 3 - in;
   if (total < 0) total = 0;
   *before = total / 2;
+}
+
+int basi_bias_relu_bwd(const basi_tensor* dy, const basi_tensor* y, int relu, float* dbias, void* stream) {
+  BASI_CHECK_ARG(dy && y && vec_ok(dy) && vec_ok(y) && same_shape(dy, y) && dy->dtype == y->dtype && dy->c <= 8192,
+                 "bias_relu_bwd: bad tensors");
+  const int64_t R = pixels(dy);
+  DISPATCH_T(dy->dtype, {
+    const int64_t total = R * (dy->c / Vec<T>::N);
+    basi::launch(bias_relu_bwd_kernel<T>, grid_for(total, 256, 4), 256, (size_t)dy->c * sizeof(float), (cudaStream_t)stream,
+                 (T*)dy->ptr, dy->ld, (const T*)y->ptr, y->ld, dy->c, R, relu, dbias);
+  })
+  BASI_CHECK_LAUNCH("bias_relu_bwd");
+  return BASI_OK;
+}
+
+int basi_add_fwd(const basi_tensor* a, const basi_tensor* b, const basi_tensor* out, void* stream) {
+  BASI_CHECK_ARG(a && b && out && vec_ok(a) && vec_ok(b) && vec_ok(out) && same_shape(a, b) && same_shape(a, out) &&
+                     a->dtype == b->dtype && a->dtype == out->dtype, "add fwd: bad tensors");
+  DISPATCH_T(a->dtype, {
+    const int64_t total = pixels(a) * (a->c / Vec<T>::N);
+    basi::launch(add_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)a->ptr, a->ld,
+                 (const T*)b->ptr, b->ld, (T*)out->ptr, out->ld, a->c, total);
+  })
+  BASI_CHECK_LAUNCH("add_fwd");
+  return BASI_OK;
+}
+
+int basi_add_bwd(const basi_tensor* dout, const basi_tensor* da, int acc_a, const basi_tensor* db, int acc_b,
+                 void* stream) {
+  BASI_CHECK_ARG(dout && vec_ok(dout) && (da || db), "add bwd: bad tensors");
+  BASI_CHECK_ARG((!da || (vec_ok(da) && same_shape(da, dout) && da->dtype == dout->dtype)) &&
+                     (!db || (vec_ok(db) && same_shape(db, dout) && db->dtype == dout->dtype)), "add bwd: bad tensors");
+  DISPATCH_T(dout->dtype, {
+    const int64_t total = pixels(dout) * (dout->c / Vec<T>::N);
+    basi::launch(add_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dout->ptr, dout->ld,
+                 da ? (T*)da->ptr : (T*)nullptr, da ? da->ld : 0, acc_a, db ? (T*)db->ptr : (T*)nullptr, db ? db->ld : 0,
+                 acc_b, dout->c, total);
+  })
+  BASI_CHECK_LAUNCH("add_bwd");
+  return BASI_OK;
 }
 
 int basi_onehot2_f32(const float* labels, float* out, int64_t n, void* stream) {

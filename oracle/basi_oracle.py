@@ -36,6 +36,8 @@ What each function restates (paths relative to /root/reference):
                              build_net (loss, poly LR, plain SGD)
 * ``linknet_b_*``            variant B: slim/nets/vgg.py:187-196 (vgg_16 trunk), back/90AttentionSingle2/BAISNet.py
                              :653-810 (LinkNet._attention / _classifies / build), BAISRunnerTrain.py:116-156 (cal_loss)
+* ``linknet_top_*``          the current-HEAD path: BAISNet.py:117-269 (LinkNet._feature / _decoder / _segment / build),
+                             BAISRunnerTrain.py:97-115 (cal_loss, pos_weight 1)
 * ``pspnet_forward_rounded`` the same forward with 16-bit storage roundings injected (no reference counterpart:
                              the noise model the bf16 CUDA path is measured against)
 * ``predict_*``              back/2AddClass/BAISRunnerTrain.py:88-89,
@@ -523,6 +525,95 @@ def linknet_b_train_step(params_np, image, mask, label_seg, label_cls, lr=5e-3, 
     return {"loss": float(loss.detach()), "loss_attention": float(la.detach()), "loss_classes": float(lc.detach()),
             "attentions": [a.detach().numpy() for a in att], "cls_logits": cls.detach().numpy(), "grads": g,
             "new_params": new}
+
+
+# --------------------------------------------------------------------------
+# F2: the top-level (current HEAD) LinkNet: vgg_16 trunk + deep-supervised U-shape (BAISNet.py:117-269) and its
+# cal_loss (BAISRunnerTrain.py:97-115)
+# --------------------------------------------------------------------------
+
+
+def linknet_top_specs(width=1.0):
+    specs = OrderedDict()
+
+    def conv(name, k, cin, cout):
+        specs[name + "/weights"] = (k, k, cin, cout)
+        specs[name + "/biases"] = (cout,)
+
+    cin, ch = 3, {}
+    for blk, reps, c in VGG_BLOCKS:
+        c = max(8, int(c * width))
+        for r in range(1, reps + 1):
+            conv("vgg_16/conv%d/conv%d_%d" % (blk, blk, r), 3, cin, c)
+            cin = c
+        ch[blk] = c
+    c1, c2, c3, c4 = ch[2], ch[3], ch[4], ch[5]
+    for lvl, c_in, c_out in ((4, c4, c3), (3, c3, c2), (2, c2, c1), (1, c1, c1)):
+        for scope, has4 in (("attention_%d/segment_side_%d" % (lvl, lvl), True), ("attention_%d/%d" % (lvl, lvl), False)):
+            conv(scope + "/d_s_conv_1", 1, c_in, c_in // 4)
+            conv(scope + "/d_s_conv_2", 3, c_in // 4, c_in // 4)
+            conv(scope + "/d_s_conv_3", 1, c_in // 4, c_out)
+            if has4:
+                conv(scope + "/d_s_conv_4", 3, c_out, 2)
+    conv("attention_0", 3, c1, 2)
+    return specs
+
+
+def linknet_top_forward(params, image_nhwc):
+    """LinkNet.build (BAISNet.py:169-269): returns the five segment logit maps [NHWC, 2 channels], coarse to fine."""
+    def cv(x, n, stride=1, padding="SAME", relu=True):
+        y = conv2d(x, params[n + "/weights"], stride, padding, bias=params[n + "/biases"])
+        return F.relu(y) if relu else y
+
+    x = image_nhwc.permute(0, 3, 1, 2)
+    blocks = {}
+    for blk, reps, _ in VGG_BLOCKS:
+        for r in range(1, reps + 1):
+            x = cv(x, "vgg_16/conv%d/conv%d_%d" % (blk, blk, r))
+        blocks[blk] = x
+        if blk < 5:
+            x = F.max_pool2d(x, 2, 2)
+    b1, b2, b3, b4 = blocks[2], blocks[3], blocks[4], blocks[5]
+
+    def decoder(x, scope, out_hw, with_head):
+        y = cv(x, scope + "/d_s_conv_1")
+        y = resize_nearest(y, out_hw)
+        y = cv(y, scope + "/d_s_conv_2")
+        y = cv(y, scope + "/d_s_conv_3", padding="VALID")
+        if with_head:
+            return cv(y, scope + "/d_s_conv_4", padding="VALID", relu=False)
+        return y
+
+    segments = []
+    cur = b4
+    for lvl, nxt in ((4, b3), (3, b2), (2, b1), (1, b1)):
+        if lvl == 1:
+            cur = b1 + cur                                          # Net.add([block1, net_output]) (:244)
+        hw = nxt.shape[2:4]
+        segments.append(decoder(cur, "attention_%d/segment_side_%d" % (lvl, lvl), hw, True).permute(0, 2, 3, 1))
+        cur = decoder(cur, "attention_%d/%d" % (lvl, lvl), hw, False)
+    segments.append(cv(cur, "attention_0", padding="VALID", relu=False).permute(0, 2, 3, 1))
+    return segments
+
+
+def linknet_top_train_step(params_np, image, label_seg, lr=5e-3, dtype=torch.float64, pos_weight=1.0):
+    p = to_torch(params_np, dtype, requires_grad=True)
+    segs = linknet_top_forward(p, torch.as_tensor(np.asarray(image)).to(dtype))
+    lab = torch.as_tensor(np.asarray(label_seg)).permute(0, 3, 1, 2).to(dtype)
+    terms = []
+    for a in segs:
+        z = resize_nearest(lab, a.shape[1:3]).permute(0, 2, 3, 1).reshape(-1).long()
+        terms.append(weighted_cross_entropy_with_logits(F.one_hot(z, 2).to(dtype), a.reshape(-1, 2), pos_weight).mean())
+    loss = sum(terms) / len(terms)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    g, new = OrderedDict(), OrderedDict()
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(p[n]) if gr is None else gr
+        g[n] = gr.detach().numpy()
+        new[n] = (p[n].detach() - torch.tensor(lr, dtype=dtype) * gr).numpy()
+    return {"loss": float(loss.detach()), "loss_segments": [float(t.detach()) for t in terms],
+            "segments": [a.detach().numpy() for a in segs], "grads": g, "new_params": new}
 
 
 # --------------------------------------------------------------------------

@@ -426,3 +426,47 @@ def test_variant_b_bf16_runs_and_tracks_f32():
     # off, so they are only required to stay in the same ballpark
     assert _rel2(out["bf16"][1], out["f32"][1]) < 5e-2
     assert _rel2(out["bf16"][2], out["f32"][2]) < 0.6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F2: the top-level (current HEAD) LinkNet: vgg_16 trunk + deep-supervised U-shape, cal_loss with pos_weight 1
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_linknet_top_train_step_matches_oracle(precision):
+    from basi_b200.BAISNet import LinkNetTop, Placeholder
+    from basi_b200.engine import Engine
+    S, B, width = 64, 2, 0.125
+    rng = np.random.RandomState(4)
+    img = rng.rand(B, S, S, 3).astype(np.float32)
+    lab = np.zeros((B, S, S, 1), dtype=np.float32)
+    lab[0, 10:40, 20:50] = 1
+    lab[1, 30:60, 5:25] = 1
+    params = O.init_params(O.linknet_top_specs(width), 2)
+    net = LinkNetTop(Placeholder((None, S, S, 3)), width=width)
+    eng = Engine(net, B, precision, True, dict(kind="linknet_b", pos_weight=1.0))
+    eng.set_params(params)
+    lr = 5e-3
+    eng.feed(img, lab, None, lr)
+    eng.step_device()
+    torch.cuda.synchronize()
+    ref = O.linknet_top_train_step(params, img, lab, lr, torch.float64)
+    loss = eng.losses()[1]
+    if precision == "f32":
+        assert abs(loss - ref["loss"]) < F32_TOL * max(1, abs(ref["loss"])), (loss, ref["loss"])
+        r32 = O.linknet_top_train_step(params, img, lab, lr, torch.float32)
+        for i, a in enumerate(eng.att_logits):
+            assert _rel(a.t.cpu().numpy(), ref["segments"][i]) < F32_TOL + 3 * _rel(r32["segments"][i], ref["segments"][i]), i
+        grads = eng.get_grads()
+        bad = [(n, _rel2(grads[n], ref["grads"][n])) for n in grads
+               if np.max(np.abs(ref["grads"][n])) > 1e-12 and
+               _rel2(grads[n], ref["grads"][n]) > F32_TOL + 10 * _rel2(r32["grads"][n], ref["grads"][n])]
+        assert not bad, bad[:5]
+    else:
+        assert eng.tc_layers > 20, eng.tc_layers                   # biased vgg / decoder convs on the tcgen05 path
+        assert abs(loss - ref["loss"]) < 2e-2 * max(1, abs(ref["loss"])), (loss, ref["loss"])
+        for i, a in enumerate(eng.att_logits):
+            assert _rel2(a.t.float().cpu().numpy(), ref["segments"][i]) < 5e-2, i
+        g = eng.get_grads()
+        ga = np.concatenate([g[n].reshape(-1) for n in g]).astype(np.float64)
+        gb = np.concatenate([ref["grads"][n].reshape(-1) for n in g]).astype(np.float64)
+        assert float(ga @ gb / (np.linalg.norm(ga) * np.linalg.norm(gb))) > 0.98
