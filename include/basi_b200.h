@@ -278,7 +278,7 @@ int basi_argmax(const float* logits, int64_t rows, int C, int32_t* out, void* st
 int basi_upsample_legacy_argmax(const float* logits, int B, int P_h, int P_w, int C, int S_h, int S_w,
                                 int32_t* out, void* stream);
 /* Split-operand (fp32-grade) mode: x float32 [N,H,W,C] -> y bf16 [N,H,W,3C] = [hi | mid | lo], x == hi + mid + lo to
- * 2^-24: the operand format of basi_tc_conv_create_split (A4/A5 at the reference's float32 precision on tcgen05). */
+ * 2^-24 (or [N,H,W,2C] = [hi | mid], x == hi + mid to 2^-17): the operand format of basi_tc_conv_create_split (A4/A5 at the reference's float32 precision on tcgen05). */
 int basi_split3_bf16(const basi_tensor* x, const basi_tensor* y, void* stream);
 /* dst[i] = (bf16) src[i] / (f32) src[i] helpers */
 int basi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
@@ -308,11 +308,13 @@ int basi_tc_pack_weights_multi(const void* table_dev, int n_layers, int total_bl
  * Table entries with pad0 = 1 make basi_tc_pack_weights_multi write the matching split weight layouts
  * (w_oi: [taps][Cout][basi_tc_split_kcols(Cin)] for fprop, w_io: [taps][Cin][basi_tc_split_kcols(Cout)] for dgrad;
  * the buffers must be zero-initialised once).  x / y of *_supported_split are the logical float32 tensors.
- *   FPROP: a = x3, b = y (f32)    DGRAD: a = dy3, b = dx (f32, written / accumulated)    WGRAD: a = x3, b = dy3 */
+ *   FPROP: a = x3, b = y (f32)    DGRAD: a = dy3, b = dx (f32, written / accumulated)    WGRAD: a = x3, b = dy3
+ * parts = 3: [hi|mid|lo] operands, six products (float32-exact); parts = 2: [hi|mid] operands, three products
+ * (hi*hi, hi*mid, mid*hi: 2^-17 unbiased representation error per operand), table entries with pad0 = 2. */
 int basi_tc_conv_supported_split(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y);
-int basi_tc_split_kcols(int c);
+int basi_tc_split_kcols(int c, int parts);
 int basi_tc_conv_create_split(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
-                              const void* w_split, float* dw, int accumulate, basi_tc_conv** out);
+                              const void* w_split, float* dw, int accumulate, int parts, basi_tc_conv** out);
 int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
                         const void* w_bf16, float* dw, int accumulate, basi_tc_conv** out);
 /* fprop plans only: also accumulate the batch-norm statistics of the produced tensor in the epilogue (same

@@ -110,13 +110,13 @@ SIGNATURES = {
     "basi_tc_pack_weights_multi": [_P, _i, _i, _P],
     "basi_tc_conv_create": [_i, _DP, _TP, _TP, _P, _P, _i, C.POINTER(_P)],
     "basi_tc_conv_supported_split": [_i, _DP, _TP, _TP],
-    "basi_tc_conv_create_split": [_i, _DP, _TP, _TP, _P, _P, _i, C.POINTER(_P)],
+    "basi_tc_conv_create_split": [_i, _DP, _TP, _TP, _P, _P, _i, _i, C.POINTER(_P)],
     "basi_tc_conv_set_bn_stats": [_P, _P, _P, _P, _d, _f, _P, _P],
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
             "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i),
-            "basi_tc_conv_set_bn_bwd": ([_P, _TP, _P, _i, _P, _d, _P, _P, _P], _i), "basi_tc_split_kcols": ([_i], _i),
+            "basi_tc_conv_set_bn_bwd": ([_P, _TP, _P, _i, _P, _d, _P, _P, _P], _i), "basi_tc_split_kcols": ([_i, _i], _i),
             "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
 
 _lib = None

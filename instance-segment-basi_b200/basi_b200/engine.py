@@ -112,7 +112,16 @@ class Engine(object):
         # f32 mode on the tensor cores: float32 storage, convolutions on bf16 [hi|mid|lo] split operands (six bf16
         # tcgen05 MMAs per product, fp32 TMEM accumulation) -- the reference's precision on the Blackwell-native path
         self.split_tc = self.use_tc and precision == "f32"
+        # operand parts of the split mode: 3 = [hi|mid|lo], six products, float32-exact; 2 = [hi|mid], three products
+        # (half the tensor-core work; 2^-17 unbiased operand error that averages out over the reduction)
+        # Default: exact forward (3 parts: logits within 4e-6 of float64 at the benchmark shape) and three-product
+        # backward (2 parts: its 4e-6 per-layer error is far below the 5e-3 the float32 reference itself loses on the
+        # gradients there); BASI_SPLIT_PARTS=3 / 2 forces both passes
+        sp = _exp_env("BASI_SPLIT_PARTS")
+        self.split_parts = int(sp) if sp else 3
+        self.split_parts_bwd = int(sp) if sp else 2
         self._split_cache = {}
+        self._train_ranges = None
         self._bnact_of = {}
         # dgrad + BN backward in one cooperative launch (basi_tc_conv_set_bn_bwd): correct and tested, but measured
         # SLOWER than the separate resident BN-backward kernel (10.28 vs 9.09 ms/step: the two extra passes run on the
@@ -196,6 +205,28 @@ class Engine(object):
                 raise ValueError("variable %s: shape %s != %s" % (name, v.shape, shape))
             self.param_view(name).copy_(torch.from_numpy(v))
         self._refresh_weight_copies()
+
+    def set_trainable(self, substring=None):
+        """A17: ``GradientDescentOptimizer.minimize(loss, var_list=[v for v in trainable if substring in v.name])`` --
+        the class-only op of back/2AddClass/BAISRunnerTrain.py:120-121 ('class_attention') and the segment-side op of
+        BAISRunnerTrain.py:54-58 ('segment_side').  None restores training of every variable.  Takes effect at the
+        next step_device / capture."""
+        if substring is None:
+            self._train_ranges = None
+            return 0
+        ranges = []
+        for name, (off, shape) in self.param_index.items():
+            if substring in name:
+                n = -(-int(np.prod(shape)) // _ALIGN) * _ALIGN
+                if ranges and ranges[-1][0] + ranges[-1][1] == off:
+                    ranges[-1][1] += n
+                else:
+                    ranges.append([off, n])
+        if not ranges:
+            raise KeyError("no variable name contains %r" % (substring,))
+        self._train_ranges = [tuple(r) for r in ranges]
+        self._graph = None                      # a captured step has the old optimizer launches
+        return len(ranges)
 
     def broadcast_params(self, dp, src=0):
         """Data parallelism: rank `src`'s parameters to every replica, then refresh the bf16 tensor-core copies."""
@@ -1095,13 +1126,14 @@ class Engine(object):
                    C.c_int64(op["lda"]), self.B, op["K"], op["N"], acc)
 
     # ------------------------------------------------------------------ tcgen05 plans
-    def _split3(self, act, lst):
-        """bf16 [hi|mid|lo] parts of a float32 activation (3C channels); the split kernel is emitted into `lst` the
-        first time the tensor is needed (forward inputs stay valid for the weight-gradient pass)."""
-        key = id(act)
+    def _split3(self, act, lst, parts=None):
+        """bf16 [hi|mid(|lo)] parts of a float32 activation (parts x C channels); the split kernel is emitted into `lst`
+        the first time the tensor is needed (forward inputs stay valid for the weight-gradient pass)."""
+        parts = parts or self.split_parts
+        key = (id(act), parts)
         if key not in self._split_cache:
             n, h, w, c = act.shape
-            a3 = Act(self._zeros((n, h, w, 3 * c), torch.bfloat16))
+            a3 = Act(self._zeros((n, h, w, parts * c), torch.bfloat16))
             self._split_cache[key] = (a3, act)            # (keeps `act` alive: the key is its id)
             self._call(lst, "basi_split3_bf16", act.ref, a3.ref, bytes=self._nbytes(act) * 2.5)
         return self._split_cache[key][0]
@@ -1112,26 +1144,29 @@ class Engine(object):
         taps, cin, cout = shape[0] * shape[1], shape[2], shape[3]
         split = bool(op.get("split"))
         if "w_io" not in op:
-            kd = lib.basi_tc_split_kcols(cout) if split else cout      # dgrad layout [tap][cin][kd]
-            kf = lib.basi_tc_split_kcols(cin) if split else cin        # fprop layout [tap][cout][kf]
+            fp, bp = self.split_parts, self.split_parts_bwd
+            kd = lib.basi_tc_split_kcols(cout, bp) if split else cout      # dgrad layout [tap][cin][kd]
+            kf = lib.basi_tc_split_kcols(cin, fp) if split else cin        # fprop layout [tap][cout][kf]
             op["w_io"] = self._zeros(taps * cin * kd, torch.bfloat16)
             op["w_oi"] = self._zeros(taps * cout * kf, torch.bfloat16)
-            self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout, 1 if split else 0))
+            self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout,
+                                     {(3, 3): 1, (2, 2): 2, (3, 2): 3}[(fp, bp)] if split else 0))
         x, y = op["x"], op["y"]
         handle = C.c_void_p()
         if split:
             if kind == _lib.TC_FPROP:
                 x3 = self._split3(x, lst)
                 _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), x3.ref, y.ref, op["w_oi"].data_ptr(),
-                          None, 0, C.byref(handle))
+                          None, 0, self.split_parts, C.byref(handle))
             elif kind == _lib.TC_DGRAD:
-                dy3 = self._split3(y.grad, lst)
+                dy3 = self._split3(y.grad, lst, self.split_parts_bwd)
                 _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), dy3.ref, x.grad.ref,
-                          op["w_io"].data_ptr(), None, acc, C.byref(handle))
+                          op["w_io"].data_ptr(), None, acc, self.split_parts_bwd, C.byref(handle))
             else:
-                x3, dy3 = self._split3(x, lst), self._split3(y.grad, lst)
+                x3, dy3 = self._split3(x, lst), self._split3(y.grad, lst, self.split_parts_bwd)
+                fp, bp = self.split_parts, self.split_parts_bwd
                 _lib.call("basi_tc_conv_create_split", kind, C.byref(op["desc"]), x3.ref, dy3.ref, None,
-                          self._gptr(op["w"]), 1, C.byref(handle))
+                          self._gptr(op["w"]), 1, fp if fp == bp else 10 * fp + bp, C.byref(handle))
         elif kind == _lib.TC_FPROP:
             _lib.call("basi_tc_conv_create", kind, C.byref(op["desc"]), x.ref, y.ref, op["w_oi"].data_ptr(), None, 0,
                       C.byref(handle))
@@ -1330,8 +1365,15 @@ class Engine(object):
                 sync_grads(self.grads_flat)
         self.join_side()
         self._side_dirty = False
-        _lib.call("basi_sgd_step", self.params_flat.data_ptr(), self.grads_flat.data_ptr(), self.lr_dev.data_ptr(),
-                  C.c_int64(self.n_flat), None, st)
+        if self._train_ranges is None:
+            _lib.call("basi_sgd_step", self.params_flat.data_ptr(), self.grads_flat.data_ptr(), self.lr_dev.data_ptr(),
+                      C.c_int64(self.n_flat), None, st)
+        else:
+            # minimize(loss, var_list=...): only the selected variables move (the gradients of the others are
+            # computed, like TF does for the shared graph, and ignored)
+            for off, n in self._train_ranges:
+                _lib.call("basi_sgd_step", self.params_flat.data_ptr() + 4 * off, self.grads_flat.data_ptr() + 4 * off,
+                          self.lr_dev.data_ptr(), C.c_int64(n), None, st)
         self._refresh_weight_copies(st)
 
     def launches_per_step(self):

@@ -1351,29 +1351,36 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
   const int tap = b;
   const int ci0 = cit * 32, co0 = cot * 32;
   const size_t base = (size_t)tap * e.cin * e.cout;
-  if (e.pad0 == 1) {
-    // split-operand layout (fp32-grade mode): w = hi + mid + lo (bf16 each).  The operand tensor of the convolution
-    // holds [hi|mid|lo] channel blocks and the main loop runs three passes of 64-column chunks over it; the weight
-    // column of (pass p, operand part q, channel c) is (passoff[p] * 64 + q * C + c) and holds w_hi for p = 0
-    // (q = 0,1,2), w_mid for p = 1 (q = 0,1), w_lo for p = 2 (q = 0): the six significant products.  Every other
-    // column stays zero (the buffers are zero-initialised once).
-    //   w_oi: fprop layout [tap][co][Kf], reduced channel C = cin;   w_io: dgrad layout [tap][ci][Kd], C = cout
-    const int f0 = (3 * e.cin + 63) / 64, f1 = (2 * e.cin + 63) / 64, f2 = (e.cin + 63) / 64;
-    const int d0 = (3 * e.cout + 63) / 64, d1 = (2 * e.cout + 63) / 64, d2 = (e.cout + 63) / 64;
-    const size_t Kf = (size_t)(f0 + f1 + f2) * 64, Kd = (size_t)(d0 + d1 + d2) * 64;
+  if (e.pad0 != 0) {
+    // split-operand layouts (fp32-grade mode): w = hi + mid (+ lo), bf16 each.  The operand tensor of the convolution
+    // holds `parts` channel blocks [hi|mid(|lo)] and the main loop runs `parts` passes of 64-column chunks over its
+    // first parts, parts-1, .. blocks; the weight column of (pass p, operand part q, channel c) is
+    // (passoff[p] * 64 + q * C + c) and holds weight part p for q = 0 .. parts-1-p: the significant products
+    // (parts = 3: six, float32-exact; parts = 2: three).  Every other column stays zero (zero-initialised buffers).
+    //   w_oi: fprop layout [tap][co][Kf], reduced channel C = cin, fparts;  w_io: dgrad layout [tap][ci][Kd], C = cout,
+    //   dparts.  pad0 = 1: (3, 3), 2: (2, 2), 3: (3, 2) -- exact forward, three-product backward.
+    const int fparts = e.pad0 == 2 ? 2 : 3, dparts = e.pad0 == 1 ? 3 : 2;
+    int foff[3], doff[3];
+    int accf = 0, accd = 0;
+    for (int p = 0; p < 3; ++p) {
+      foff[p] = accf; doff[p] = accd;
+      if (p < fparts) accf += ((fparts - p) * e.cin + 63) / 64;
+      if (p < dparts) accd += ((dparts - p) * e.cout + 63) / 64;
+    }
+    const size_t Kf = (size_t)accf * 64, Kd = (size_t)accd * 64;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int ci = ci0 + i, co = co0 + threadIdx.x;
       const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
       tile[i][threadIdx.x] = v;
       if (ci < e.cin && co < e.cout) {
-        const bf16 h = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(h);
-        const bf16 m = __float2bfloat16_rn(r1);
-        const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        bf16 part[3];
+        part[0] = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(part[0]);
+        part[1] = __float2bfloat16_rn(r1);
+        part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
         bf16* row = e.w_io + ((size_t)tap * e.cin + ci) * Kd;
-        row[co] = h; row[e.cout + co] = h; row[2 * e.cout + co] = h;
-        row[(size_t)d0 * 64 + co] = m; row[(size_t)d0 * 64 + e.cout + co] = m;
-        row[(size_t)(d0 + d1) * 64 + co] = l;
+        for (int p = 0; p < dparts; ++p)
+          for (int q = 0; q < dparts - p; ++q) row[(size_t)doff[p] * 64 + (size_t)q * e.cout + co] = part[p];
       }
     }
     __syncthreads();
@@ -1381,14 +1388,14 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
       const int co = co0 + i, ci = ci0 + threadIdx.x;
       if (ci < e.cin && co < e.cout) {
         const float v = tile[threadIdx.x][i];
-        const bf16 h = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(h);
-        const bf16 m = __float2bfloat16_rn(r1);
-        const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        bf16 part[3];
+        part[0] = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(part[0]);
+        part[1] = __float2bfloat16_rn(r1);
+        part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
         bf16* row = e.w_oi + ((size_t)tap * e.cout + co) * Kf;
-        row[ci] = h; row[e.cin + ci] = h; row[2 * e.cin + ci] = h;
-        row[(size_t)f0 * 64 + ci] = m; row[(size_t)f0 * 64 + e.cin + ci] = m;
-        row[(size_t)(f0 + f1) * 64 + ci] = l;
+        for (int p = 0; p < fparts; ++p)
+          for (int q = 0; q < fparts - p; ++q) row[(size_t)foff[p] * 64 + (size_t)q * e.cin + ci] = part[p];
       }
     }
     return;
@@ -1669,14 +1676,18 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
   if (split) {
     // operands are bf16 [hi|mid|lo] tensors with 3x the logical channels; destinations are float32
     basi_tensor xl = *x, yl = *y;
+    const int px = (kind == BASI_TC_WGRAD && split >= 10) ? split / 10 : split;
+    const int pg = (kind == BASI_TC_WGRAD && split >= 10) ? split % 10 : split;
+    BASI_CHECK_ARG((px == 2 || px == 3) && (pg == 2 || pg == 3),
+                   "tc_conv_create_split: parts must be 2 ([hi|mid]) or 3 ([hi|mid|lo])");
     if (kind == BASI_TC_FPROP || kind == BASI_TC_WGRAD) {
-      BASI_CHECK_ARG(a->dtype == BASI_BF16 && a->c % 3 == 0, "tc_conv_create_split: a must be a bf16 [hi|mid|lo] tensor");
-      xl.c = a->c / 3; xl.dtype = BASI_F32; xl.ld = (xl.c + 3) / 4 * 4;
+      BASI_CHECK_ARG(a->dtype == BASI_BF16 && a->c % px == 0, "tc_conv_create_split: a must be a bf16 parts tensor");
+      xl.c = a->c / px; xl.dtype = BASI_F32; xl.ld = (xl.c + 3) / 4 * 4;
     }
     if (kind == BASI_TC_DGRAD || kind == BASI_TC_WGRAD) {
       const basi_tensor* g = kind == BASI_TC_DGRAD ? a : b;
-      BASI_CHECK_ARG(g->dtype == BASI_BF16 && g->c % 3 == 0, "tc_conv_create_split: dy must be a bf16 [hi|mid|lo] tensor");
-      yl.c = g->c / 3; yl.dtype = BASI_F32; yl.ld = (yl.c + 3) / 4 * 4;
+      BASI_CHECK_ARG(g->dtype == BASI_BF16 && g->c % pg == 0, "tc_conv_create_split: dy must be a bf16 parts tensor");
+      yl.c = g->c / pg; yl.dtype = BASI_F32; yl.ld = (yl.c + 3) / 4 * 4;
     }
     BASI_CHECK_ARG((a->ld % 8 == 0) && (((uintptr_t)a->ptr & 15) == 0), "tc_conv_create_split: operand alignment");
     BASI_CHECK_ARG(tc_geometry_ok_split(kind, d, &xl, &yl), "tc_conv_create_split: geometry not supported");
@@ -1699,9 +1710,12 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     const basi_tensor* dstt = b;
     const int ndim = dstt->c;
     // split mode: three passes over the [hi|mid|lo] operand (all parts x w_hi, hi+mid x w_mid, hi x w_lo)
-    const int csrc = split ? src->c / 3 : src->c;
-    const int n0 = split ? (3 * csrc + 63) / 64 : (csrc + 63) / 64;
-    const int n1 = split ? (2 * csrc + 63) / 64 : 0, n2 = split ? (csrc + 63) / 64 : 0;
+    // (parts = 3: passes over [hi|mid|lo], [hi|mid], [hi] = six products; parts = 2: passes over [hi|mid], [hi] = the
+    // three products hi*hi, mid*hi, hi*mid -- 16 mantissa bits per operand, unbiased 2^-17 representation error)
+    const int csrc = split ? src->c / split : src->c;
+    const int n0 = split ? (split * csrc + 63) / 64 : (csrc + 63) / 64;
+    const int n1 = split ? ((split - 1) * csrc + 63) / 64 : 0, n2 = split == 3 ? (csrc + 63) / 64 : 0;
+    const int nbig = split ? (csrc + 63) / 64 : 0;
     const int kchunks_all = n0 + n1 + n2;
     const int kdim = split ? kchunks_all * 64 : src->c;     // weight columns
     int bn = ndim % 128 == 0 ? 128 : (ndim % 64 == 0 ? 64 : 32);
@@ -1775,7 +1789,7 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     cp.taps = d->kh * d->kw; cp.kw = d->kw; cp.k_chunks = (kdim + 63) / 64;
     cp.a_wrap0 = split ? n0 : 0x7fffffff;
     cp.a_wrap1 = split ? n0 + n1 : 0x7fffffff;
-    cp.big_chunks = split ? n2 : 0;
+    cp.big_chunks = nbig;
     cp.group_steps = exp_env("BASI_TC_SPLIT_GROUP") ? atoi(exp_env("BASI_TC_SPLIT_GROUP")) : 4;
     if (cp.group_steps < 1) cp.group_steps = 1;
     if (kind == BASI_TC_FPROP) {
@@ -1844,7 +1858,9 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     cp.debug = exp_env("BASI_TC_DEBUG_STATS") ? atoi(exp_env("BASI_TC_DEBUG_STATS")) : 0;
   } else {
     BASI_CHECK_ARG(dw, "tc_conv_create: null dw");
-    const int cin = split ? a->c / 3 : a->c, cout = split ? b->c / 3 : b->c;
+    // (split mode, weight gradient: parts may be 10 * x_parts + dy_parts when the two operands were split differently)
+    const int pa = split >= 10 ? split / 10 : split, pb = split >= 10 ? split % 10 : split;
+    const int cin = split ? a->c / pa : a->c, cout = split ? b->c / pb : b->c;
     int bn = cin > 64 ? 128 : 64;            // ci tile (UMMA N); co is the UMMA M = 128
     pl->bn = bn;
     rc = make_act_map(&pl->mapA, a, TW, TH, TN);
@@ -1860,7 +1876,7 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     wp.ci_tiles = (cin + bn - 1) / bn; wp.co_tiles = (cout + 127) / 128;
     wp.off_h = -d->pad_t; wp.off_w = -d->pad_l; wp.step = d->dil;
     wp.Cin = cin; wp.Cout = cout;
-    wp.nterms = split ? 6 : 1;
+    wp.nterms = split == 0 ? 1 : ((pa == 3 && pb == 3) ? 6 : 3);
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
     // split-K over pixel tiles.  Every split adds |dW| fp32 atomics, so tiny gradients (conv4 1x1: 65 K elements)
     // want a single wave of CTAs (measured 22.6 -> 16.7 us); long pixel loops want two waves for balance.
@@ -1902,8 +1918,8 @@ int basi_tc_conv_create(int kind, const basi_conv_desc* d, const basi_tensor* a,
  *   FPROP: a = x3, b = y (f32, written)      DGRAD: a = dy3, b = dx (f32, written / accumulated)
  *   WGRAD: a = x3, b = dy3, dw = HWIO float32 gradient (added into) */
 int basi_tc_conv_create_split(int kind, const basi_conv_desc* d, const basi_tensor* a, const basi_tensor* b,
-                              const void* w_split, float* dw, int accumulate, basi_tc_conv** out) {
-  return create_plan(kind, d, a, b, w_split, dw, accumulate, 1, out);
+                              const void* w_split, float* dw, int accumulate, int parts, basi_tc_conv** out) {
+  return create_plan(kind, d, a, b, w_split, dw, accumulate, parts, out);
 }
 
 int basi_tc_conv_supported_split(int kind, const basi_conv_desc* d, const basi_tensor* x, const basi_tensor* y) {
@@ -1912,7 +1928,8 @@ int basi_tc_conv_supported_split(int kind, const basi_conv_desc* d, const basi_t
 
 /* number of bf16 weight columns (K') of the split layout for a reduced channel count c: three passes of 64-channel
  * chunks over [hi|mid|lo] (3c), [hi|mid] (2c) and [hi] (c) */
-int basi_tc_split_kcols(int c) {
+int basi_tc_split_kcols(int c, int parts) {
+  if (parts == 2) return (((2 * c + 63) / 64) + ((c + 63) / 64)) * 64;
   return (((3 * c + 63) / 64) + ((2 * c + 63) / 64) + ((c + 63) / 64)) * 64;
 }
 

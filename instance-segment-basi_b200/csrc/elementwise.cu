@@ -959,7 +959,7 @@ using namespace basi;
 // lo = bf16(x - hi - mid) (both differences are exact in float32).  The operands of the split-operand (fp32-grade)
 // tcgen05 convolutions: six bf16 MMAs (hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid) reproduce the float32 product.
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int ldx, int C, bf16* __restrict__ y,
-                                                     int ldy, int64_t total) {
+                                                     int ldy, int64_t total, int parts) {
   pdl_prologue();
   const int q = C / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
     bf16* o = y + px * ldy + c;
     *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
     *reinterpret_cast<uint2*>(o + C) = *reinterpret_cast<const uint2*>(m);
-    *reinterpret_cast<uint2*>(o + 2 * C) = *reinterpret_cast<const uint2*>(l);
+    if (parts == 3) *reinterpret_cast<uint2*>(o + 2 * C) = *reinterpret_cast<const uint2*>(l);
   }
 }
 
@@ -1727,13 +1727,14 @@ int basi_upsample_legacy_argmax(const float* logits, int B, int P_h, int P_w, in
 
 int basi_split3_bf16(const basi_tensor* x, const basi_tensor* y, void* stream) {
   BASI_CHECK_ARG(x && y && x->ptr && y->ptr, "split3_bf16: null argument");
-  BASI_CHECK_ARG(x->dtype == BASI_F32 && y->dtype == BASI_BF16 && y->c == 3 * x->c && x->n == y->n && x->h == y->h &&
-                     x->w == y->w, "split3_bf16: y must be a bf16 tensor with 3x the channels of the float32 x");
+  BASI_CHECK_ARG(x->dtype == BASI_F32 && y->dtype == BASI_BF16 && (y->c == 3 * x->c || y->c == 2 * x->c) &&
+                     x->n == y->n && x->h == y->h && x->w == y->w,
+                 "split3_bf16: y must be a bf16 tensor with 2x or 3x the channels of the float32 x");
   BASI_CHECK_ARG(x->c % 4 == 0 && x->ld % 4 == 0 && y->ld % 4 == 0 && (((uintptr_t)x->ptr | (uintptr_t)y->ptr) & 15) == 0,
                  "split3_bf16: channels / strides must be multiples of 4 and pointers 16-byte aligned");
   const int64_t total = pixels(x) * (x->c / 4);
   basi::launch(split3_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const float*)x->ptr, x->ld, x->c,
-               (bf16*)y->ptr, y->ld, total);
+               (bf16*)y->ptr, y->ld, total, y->c / x->c);
   BASI_CHECK_LAUNCH("split3_bf16");
   return BASI_OK;
 }

@@ -470,3 +470,43 @@ def test_linknet_top_train_step_matches_oracle(precision):
         ga = np.concatenate([g[n].reshape(-1) for n in g]).astype(np.float64)
         gb = np.concatenate([ref["grads"][n].reshape(-1) for n in g]).astype(np.float64)
         assert float(ga @ gb / (np.linalg.norm(ga) * np.linalg.norm(gb))) > 0.98
+
+
+def test_class_only_optimizer_moves_only_the_class_head():
+    """A17: train_classes_op = minimize(loss, var_list=[v for v in trainable_variables() if 'class_attention' in v.name])
+    (back/2AddClass/BAISRunnerTrain.py:120-121)."""
+    variant, nseg, S, F, B, classes = "2AddClass", 1, 64, 8, 2, 21
+    params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
+    eng = _engine(variant, nseg, S, F, B, classes, "f32", dict(kind="bce", pos_weight=3.0, class_weight=0.2))
+    eng.set_params(params)
+    assert eng.set_trainable("class_attention") >= 1
+    eng.feed(data, lab, cls, 1e-2)
+    eng.step_device()
+    torch.cuda.synchronize()
+    new = eng.get_params()
+    ref = O.train_step(params, data, lab, cls, variant, nseg, S // 8, 3.0, 0.2, 1e-2, torch.float64)
+    for n in new:
+        if "class_attention" in n:
+            assert _rel(new[n], ref["new_params"][n]) < 1e-4, n
+            assert not np.array_equal(new[n], params[n]), n
+        else:
+            assert np.array_equal(new[n], params[n]), n
+
+
+def test_inference_runner_top_level_linknet(tmp_path):
+    """BAISRunnerTest.Inference on the reference's own fixture image (input/7.jpg): mask == argmax of the oracle's
+    coarsest head for the same weights."""
+    import os
+    from basi_b200.BAISRunnerTest import Inference
+    S, width = 64, 0.125
+    inf = Inference([S, S], None, str(tmp_path / "model"), width=width, precision="f32")
+    params = O.init_params(O.linknet_top_specs(width), 5)
+    inf.engine.set_params(params)
+    path = os.path.join(os.path.dirname(__file__), "golden", "input_7.jpg")
+    pred = inf.inference(path, 0, str(tmp_path / "out"))
+    assert os.path.exists(str(tmp_path / "out" / "input_7.bmp"))
+    im = Inference.load_data(path, [S, S])
+    with torch.no_grad():
+        segs = O.linknet_top_forward(O.to_torch(params, torch.float64), torch.from_numpy(im[None]).double())
+    ref = np.argmax(segs[0].numpy()[0], -1)
+    assert pred.shape == ref.shape and np.mean(pred == ref) >= 0.999
