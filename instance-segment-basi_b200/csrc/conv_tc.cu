@@ -248,7 +248,8 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------------
-// VAR: 0 = the production kernel, 1 = halo mode (+ role timers), 2 = production kernel with the role timers
+// VAR: 0 = the production kernel, 1 = halo mode (+ role timers), 2 = production kernel with the role timers,
+// 3 = dgrad + fused batch-norm backward (opt-in, see ConvParams::fuse_bwd), 4 = fprop + fused batch-norm apply
 // (compile-time so that the experimental paths cost the production kernel nothing: as run-time branches they
 // measured 1.8 % of the training step)
 // k-step ks of a tile -> (filter tap, k-chunk).  Plain mode: tap-major.  Split mode: small k-steps first, then the
@@ -293,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // bound by L2 -> SM bytes (148 SMs x 32 KB per 0.37 us k-step = the ~12 TB/s L2 cap); sharing the weight box cuts
   // the bytes per flop by 25 %.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr bool HALO = VAR == 1, TIMERS = VAR != 0;
+  constexpr bool HALO = VAR == 1, TIMERS = (VAR == 1 || VAR == 2);
   static_assert(!HALO || (CL == 1 && MT == 1), "halo mode: one tile per CTA, no pairs");
   constexpr int STAGE = SmemLayout<BN, MT, CL>::STAGE;
   static_assert(CL == 1 || MT == 1, "pairs take one pixel tile per CTA");
@@ -607,7 +608,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     float run1 = 0.f, run2 = 0.f;
     double rund1 = 0.0, rund2 = 0.0;   // (fp32-output mode keeps the running sums in double)
     bool bwd_done = false;
-    if constexpr (!OUT32 && CL == 1 && VAR == 0) {
+    // (a separate template variant, VAR == 3: merely compiling this path into the production kernel cost the
+    // ordinary fprop / dgrad launches 0.41 ms per step -- 5.81 vs 5.19 ms of conv time, A/B on the same GPU)
+    if constexpr (!OUT32 && CL == 1 && VAR == 3) {
       if (p.fuse_bwd) {
         // =============== dgrad + batch-norm backward of the produced gradient's layer (see ConvParams::fuse_bwd) ====
         bwd_done = true;
@@ -998,7 +1001,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       atomicAdd(rep + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund1 : (double)run1);
       atomicAdd(rep + p.Cdst + run_nt * BN + ((int)threadIdx.x - 128), OUT32 ? rund2 : (double)run2);
     }
-    if constexpr (!OUT32 && CL == 1 && VAR == 0) {
+    if constexpr (!OUT32 && CL == 1 && VAR == 4) {      // (own template variant, like VAR == 3)
       if (p.fuse_apply) {
         // ---- grid barrier: every CTA's statistics are in the global sums
         __threadfence();
@@ -1605,10 +1608,31 @@ static int launch_conv(basi_tc_conv* pl, cudaStream_t st) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
+    if (pl->cp.fuse_bwd) {
+      if constexpr (BN <= 128) {
+        static bool attr3 = false;
+        if (!attr3) {
+          cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          attr3 = true;
+        }
+        if (pl->mt == 2)
+          cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 2, 3>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+        else
+          cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 1, 3>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+      }
+      return BASI_OK;
+    }
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(conv_tc_kernel<BNS, 1, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr4 = true;
+    }
     if (pl->mt == 2 && BN <= 128)
-      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BNS, 1, 2, 0>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BNS, 1, 2, 4>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
     else
-      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 1, 0>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
+      cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 1, 4>, pl->mapA, pl->mapB, pl->mapD, pl->mapD2, pl->cp);
     return BASI_OK;
   }
   if (pl->cp.halo && BN <= 128)
