@@ -64,6 +64,9 @@ typedef struct basi_conv_desc {
 
 const char* basi_last_error(void);
 int basi_version(void);
+/* 0 = this build's 16-bit storage type (dtype BASI_BF16 in basi_tensor) is bfloat16 (libbasi_b200.so), 1 = IEEE fp16
+ * (libbasi_b200_f16.so: the same kernels compiled with -DBASI_HALF_FP16; engine precision "f16"). */
+int basi_half_format(void);
 /* number of SMs of the current device (148 on B200), negative on error */
 int basi_sm_count(void);
 int basi_memset(void* ptr, int value, int64_t bytes, void* stream);

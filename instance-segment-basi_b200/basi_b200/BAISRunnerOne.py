@@ -24,7 +24,7 @@ from .engine import Engine
 class RunnerGUI(object):
 
     def __init__(self, log_dir, last_pool_size=90, variant="4BorderClass", num_classes=21, num_segment=4,
-                 filter_number=32, precision="bf16", device=None, seed=0, use_tc=True):
+                 filter_number=32, precision="f16", device=None, seed=0, use_tc=True):
         self.log_dir = log_dir
         self.last_pool_size = last_pool_size
         self.input_size = [self.last_pool_size * 8, self.last_pool_size * 8]
@@ -92,7 +92,7 @@ class Runner(object):
         loaded = Data.load_image(image_filename, where=where, annotation_filename=annotation_filename,
                                  ann_index=ann_index, image_size=self.input_size)
         final_batch_data, data_raw, gaussian_mask = loaded[:3]
-        kw = dict(variant="4BorderClass", num_classes=21, num_segment=4, filter_number=32, precision="bf16")
+        kw = dict(variant="4BorderClass", num_classes=21, num_segment=4, filter_number=32, precision="f16")
         kw.update(self.net_kwargs)
         ph = Placeholder((None, self.input_size[0], self.input_size[1], 4))
         net = PSPNet({'data': ph}, is_training=True, num_classes=kw["num_classes"],

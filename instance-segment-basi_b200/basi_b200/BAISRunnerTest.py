@@ -21,7 +21,7 @@ from .engine import Engine
 class Inference(object):
 
     def __init__(self, input_size, summary_dir=None, log_dir="./model", model_name="model.ckpt", width=1.0,
-                 precision="bf16", device=None, seed=0):
+                 precision="f16", device=None, seed=0):
         self.log_dir = Tools.new_dir(log_dir)
         self.model_name = model_name
         self.checkpoint_path = os.path.join(self.log_dir, self.model_name)

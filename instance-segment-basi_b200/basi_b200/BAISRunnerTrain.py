@@ -41,7 +41,7 @@ class Train(object):
 
     def __init__(self, batch_size, last_pool_size, input_size, log_dir, data_root_path=None, train_list=None,
                  data_path=None, annotation_path=None, class_path=None, model_name="model.ckpt", is_test=False,
-                 variant="2AddClass", num_classes=21, precision="bf16", filter_number=32, pos_weight=None,
+                 variant="2AddClass", num_classes=21, precision="f16", filter_number=32, pos_weight=None,
                  class_weight=None, learning_rate=None, num_steps=None, seed=0, device=None, dp=None,
                  use_cuda_graph=True, use_tc=True):
         snap = SNAPSHOT[variant]
@@ -79,7 +79,7 @@ class Train(object):
         if dp is not None:
             self.engine.broadcast_params(dp)       # every replica starts from rank 0's weights
 
-    def build_net(self, precision="bf16", device=None, use_tc=True):
+    def build_net(self, precision="f16", device=None, use_tc=True):
         if self.variant == "90AttentionSingle2":
             from .BAISNet import LinkNet
             net = LinkNet(Placeholder((None, self.input_size[0], self.input_size[1], 3)),

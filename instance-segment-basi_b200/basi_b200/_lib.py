@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BASI_LIB") or os.path.join(_HERE, "libbasi_b200.so")   # BASI_LIB: A/B another build
+# the same kernels with IEEE fp16 as the 16-bit storage type (csrc/build.sh, -DBASI_HALF_FP16): precision "f16"
+LIB_PATHS = {"bf16": LIB_PATH, "f16": os.path.join(_HERE, "libbasi_b200_f16.so")}
 
 F32, BF16 = 0, 1
 TC_FPROP, TC_DGRAD, TC_WGRAD = 0, 1, 2
@@ -115,22 +117,34 @@ SIGNATURES = {
     "basi_tc_conv_run": [_P, _P],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
+            "basi_half_format": ([], _i),
             "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i),
             "basi_tc_conv_set_bn_bwd": ([_P, _TP, _P, _i, _P, _d, _P, _P, _P], _i), "basi_tc_split_kcols": ([_i, _i], _i),
             "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
 
-_lib = None
+_libs = {}
+_current = "bf16"
 
 
-def load():
-    """dlopen the in-tree library; raises BasiError when it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise BasiError("libbasi_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                        "(or instance-segment-basi_b200/csrc/build.sh)")
-    lib = C.CDLL(LIB_PATH)
+def use(fmt):
+    """Selects which build of the library `load()` / `call()` address: "bf16" (default) or "f16".  An Engine binds
+    its plan to one build and re-selects it at every entry point, so engines of both formats can coexist."""
+    global _current
+    if fmt not in LIB_PATHS:
+        raise BasiError("unknown library format %r" % (fmt,))
+    _current = fmt
+
+
+def load(fmt=None):
+    """dlopen the in-tree library (of the selected 16-bit format); raises BasiError when it has not been built."""
+    fmt = fmt or _current
+    if fmt in _libs:
+        return _libs[fmt]
+    path = LIB_PATHS[fmt]
+    if not os.path.exists(path):
+        raise BasiError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or instance-segment-basi_b200/csrc/build.sh)" % os.path.basename(path))
+    lib = C.CDLL(path)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -139,7 +153,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    _lib = lib
+    if lib.basi_half_format() != (1 if fmt == "f16" else 0):
+        raise BasiError("%s was built for the other 16-bit format" % path)
+    _libs[fmt] = lib
     return lib
 
 

@@ -96,11 +96,19 @@ class Engine(object):
             device, use_tc = "cpu", False
         elif not torch.cuda.is_available():
             raise _lib.BasiError("basi_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        if precision not in ("bf16", "f16", "f32"):
+            raise ValueError("precision must be 'bf16', 'f16' or 'f32'")
+        # precision "f16": the same kernels built for IEEE fp16 storage (libbasi_b200_f16.so).  3 more mantissa bits than
+        # bf16 -- on this network the difference between missing and meeting the 2e-2 bar of a 16-bit path -- and a
+        # narrower range: the loss gradient is scaled by `loss_scale` and the learning rate fed to SGD divided by it
+        self.lib_fmt = "f16" if precision == "f16" else "bf16"
+        _lib.use(self.lib_fmt)
         _lib.load()
         self.net = net
         self.B = int(batch_size)
         self.precision = precision
-        self.adt = torch.float32 if precision == "f32" else torch.bfloat16
+        self.loss_scale = 8192.0 if precision == "f16" else 1.0
+        self.adt = torch.float32 if precision == "f32" else (torch.float16 if precision == "f16" else torch.bfloat16)
         # which tensors are stored in 16 bits (names of oracle.ROUNDING_POLICIES; tests hold the path to that model)
         self.storage_policy = "none" if precision == "f32" else "round1"
         self.training = training
@@ -237,7 +245,9 @@ class Engine(object):
         return OrderedDict((n, self.param_view(n).cpu().numpy().copy()) for n in self.param_index)
 
     def get_grads(self):
-        return OrderedDict((n, self.param_view(n, True).cpu().numpy().copy()) for n in self.param_index)
+        """Parameter gradients of the last step (the loss scale of the f16 mode divided out)."""
+        inv = 1.0 / self.loss_scale
+        return OrderedDict((n, self.param_view(n, True).cpu().numpy() * np.float32(inv)) for n in self.param_index)
 
     def init_params(self, seed=0):
         """glorot_uniform for weights and biases (tf.get_variable default, BAISPSPNet.py:111-113), gamma=1, beta=0."""
@@ -412,7 +422,7 @@ class Engine(object):
             return
         # slim conv2d of the vgg_16 trunk (variant B): bias + ReLU, no BN.  In bf16 mode these stay bf16 so that they
         # run on the tcgen05 path (bias + ReLU in its epilogue); every other BN-less conv is a float32 head
-        vgg_like = (hasattr(self.net, "attentions") and self.precision == "bf16" and not has_bn and s == 1 and co > 4)
+        vgg_like = (hasattr(self.net, "attentions") and self.precision != "f32" and not has_bn and s == 1 and co > 4)
         f32_out = (not has_bn) and not vgg_like
         y = self._out_act(n, torch.float32 if f32_out else None)
         desc = ConvDesc(k, a["k_w"], s, d, pt, pl, 1 if (a["relu"] and not has_bn) else 0)
@@ -772,7 +782,7 @@ class Engine(object):
             self._call(self.lossl, "basi_resize_nearest_fwd", lab.ref, li.ref)
             self._call(self.lossl, "basi_onehot2_f32", li.t.data_ptr(), ti.data_ptr(), C.c_int64(B * h * w))
             self._call(self.lossl, "basi_wbce_fwd_bwd", a.t.data_ptr(), ti.data_ptr(), C.c_float(pw),
-                       C.c_double(1.0 / (len(heads) * n2)), C.c_float(1.0 / (len(heads) * n2)), C.c_int64(n2),
+                       C.c_double(1.0 / (len(heads) * n2)), C.c_float(self.loss_scale / (len(heads) * n2)), C.c_int64(n2),
                        self.loss_acc.data_ptr(), g.t.data_ptr())
         self.class_weight = float(cfg.get("class_weight", 1.0))
         if self.cls_logits is not None:
@@ -782,7 +792,7 @@ class Engine(object):
             ncls = self.cls_logits.shape[3]
             self._call(self.lossl, "basi_softmax_ce_fwd_bwd", self.cls_logits.t.data_ptr(),
                        self.label_cls.data_ptr(), C.c_int64(B), ncls, C.c_double(1.0 / B),
-                       C.c_float(self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
+                       C.c_float(self.loss_scale * self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
         else:
             self.label_cls = None
 
@@ -831,12 +841,12 @@ class Engine(object):
             assert nseg == 1
             self.label_seg = self._zeros((B, P_h, P_w, 1), torch.float32)
             self._call(self.lossl, "basi_wbce_fwd_bwd", lp, self.label_seg.data_ptr(),
-                       C.c_float(cfg.get("pos_weight", 3.0)), C.c_double(1.0 / N), C.c_float(1.0 / N),
+                       C.c_float(cfg.get("pos_weight", 3.0)), C.c_double(1.0 / N), C.c_float(self.loss_scale / N),
                        C.c_int64(N), self.loss_acc.data_ptr(), g.t.data_ptr())
         else:
             self.label_seg = self._zeros((B, P_h, P_w, 1), torch.int32)
             self._call(self.lossl, "basi_softmax_ce_fwd_bwd", lp, self.label_seg.data_ptr(), C.c_int64(N), nseg,
-                       C.c_double(1.0 / N), C.c_float(1.0 / N), self.loss_acc.data_ptr(), g.t.data_ptr())
+                       C.c_double(1.0 / N), C.c_float(self.loss_scale / N), self.loss_acc.data_ptr(), g.t.data_ptr())
         self.class_weight = float(cfg.get("class_weight", 0.2))
         if self.cls_logits is not None:
             self.label_cls = self._zeros((B,), torch.int32)
@@ -845,7 +855,7 @@ class Engine(object):
             ncls = self.cls_logits.shape[3]
             self._call(self.lossl, "basi_softmax_ce_fwd_bwd", self.cls_logits.t.data_ptr(),
                        self.label_cls.data_ptr(), C.c_int64(B), ncls, C.c_double(1.0 / B),
-                       C.c_float(self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
+                       C.c_float(self.loss_scale * self.class_weight / B), self.loss_acc.data_ptr() + 8, gc.t.data_ptr())
         else:
             self.label_cls = None
 
@@ -1147,8 +1157,9 @@ class Engine(object):
             fp, bp = self.split_parts, self.split_parts_bwd
             kd = lib.basi_tc_split_kcols(cout, bp) if split else cout      # dgrad layout [tap][cin][kd]
             kf = lib.basi_tc_split_kcols(cin, fp) if split else cin        # fprop layout [tap][cout][kf]
-            op["w_io"] = self._zeros(taps * cin * kd, torch.bfloat16)
-            op["w_oi"] = self._zeros(taps * cout * kf, torch.bfloat16)
+            wdt = torch.float16 if (self.precision == "f16" and not split) else torch.bfloat16
+            op["w_io"] = self._zeros(taps * cin * kd, wdt)
+            op["w_oi"] = self._zeros(taps * cout * kf, wdt)
             self._tc_weights.append((self._pptr(op["w"]), op["w_io"], op["w_oi"], taps, cin, cout,
                                      {(3, 3): 1, (2, 2): 2, (3, 2): 3}[(fp, bp)] if split else 0))
         x, y = op["x"], op["y"]
@@ -1193,6 +1204,7 @@ class Engine(object):
         """bf16 copies (both layouts) of every tensor-core layer's weights: one launch for all layers."""
         if not self._tc_weights:
             return
+        _lib.use(self.lib_fmt)
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         if self._pack_table is None:
             entries = (_lib.PackEntry * len(self._tc_weights))()
@@ -1312,6 +1324,7 @@ class Engine(object):
         exactly like the reference: k = rng.randint(0, len(np.argwhere(label == target))) drawn on the host in batch
         order (np.random by default), the k-th matching pixel (row-major) times the ratio selected on the device."""
         rng = np.random if rng is None else rng
+        _lib.use(self.lib_fmt)
         st = self._stream()
         B, P_h, P_w, _ = self.label_seg.shape
         self.ann_u8.copy_(_as_tensor(ann_u8, torch.uint8).view(self.ann_u8.shape), non_blocking=True)
@@ -1342,6 +1355,7 @@ class Engine(object):
 
     def forward_device(self):
         """Forward only, inputs already in self.input (device)."""
+        _lib.use(self.lib_fmt)
         st = self._stream()
         self._zero_step_state(st)
         self._run(self.pre, st)
@@ -1350,6 +1364,7 @@ class Engine(object):
 
     def step_device(self, sync_grads=None):
         """One training step on inputs already resident in the static device buffers."""
+        _lib.use(self.lib_fmt)
         st = self._stream()
         self._zero_step_state(st)
         self._run(self.pre, st)
@@ -1420,7 +1435,7 @@ class Engine(object):
         if label_cls is not None and self.label_cls is not None:
             self.label_cls.copy_(_as_tensor(label_cls, torch.int32).view(self.label_cls.shape), non_blocking=True)
         if lr is not None:
-            self.lr_dev.fill_(float(lr))
+            self.lr_dev.fill_(float(lr) / self.loss_scale)      # (gradients carry the loss scale)
 
     def fetch(self, name, grad=False):
         """Value (or, grad=True, the loss gradient) of a named layer as a float32 NHWC numpy array -- the analogue of

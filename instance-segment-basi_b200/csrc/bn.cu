@@ -172,11 +172,10 @@ struct Pack<bf16> {
   __device__ __forceinline__ uint32_t word(int w) const { return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w)); }
   __device__ __forceinline__ float get(int i) const {
     const uint32_t w = word(i >> 1);
-    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+    return (i & 1) ? h16_hi(w) : h16_lo(w);
   }
   __device__ __forceinline__ void set2(int i2, float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const uint32_t w = *reinterpret_cast<uint32_t*>(&h);
+    const uint32_t w = h16_pack(a, b);
     if (i2 == 0) r.x = w; else if (i2 == 1) r.y = w; else if (i2 == 2) r.z = w; else r.w = w;
   }
 };

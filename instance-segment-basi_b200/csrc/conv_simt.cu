@@ -52,8 +52,8 @@ __device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
 template <>
 __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&o)[4]) {
   uint2 t = *reinterpret_cast<const uint2*>(p);
-  o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xffff0000u);
-  o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xffff0000u);
+  o[0] = h16_lo(t.x); o[1] = h16_hi(t.x);
+  o[2] = h16_lo(t.y); o[3] = h16_hi(t.y);
 }
 
 template <typename T>
@@ -64,8 +64,7 @@ __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
 }
 template <>
 __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&v)[4]) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  *reinterpret_cast<uint2*>(p) = make_uint2(h16_pack(v[0], v[1]), h16_pack(v[2], v[3]));
 }
 
 // source coordinate of (dest coordinate d, tap offset r) along one axis; returns false if invalid

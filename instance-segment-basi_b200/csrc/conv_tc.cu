@@ -149,7 +149,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor: D=f32, A=B=bf16, M=128 (256 for a CTA pair)
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = BM) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+  // (bits 7-9 / 10-12: A / B format of kind::f16 -- 0 = fp16, 1 = bf16)
+  constexpr uint32_t fmt = BASI_H16_FP16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -696,15 +698,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     float res[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                      const float xv = __uint_as_float(h ? (xw[e] & 0xffff0000u) : (xw[e] << 16));
+                      const float xv = h ? h16_hi(xw[e]) : h16_lo(xw[e]);
                       const float xc = xv - cf[col + h];
                       float g = __uint_as_float(r[v * 8 + 2 * e + h]);
                       if (!valid) g = 0.f;
                       if (p.bwd_relu) g = fmaf(xc, cf[BN + col + h], cf[2 * BN + col + h]) > 0.f ? g : 0.f;
                       res[h] = pass == 0 ? g : fmaf(cf[BN + col + h], g, -cf[3 * BN + col + h]) - xc * cf[4 * BN + col + h];
                     }
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(res[0], res[1]);
-                    pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                    pk[e] = h16_pack(res[0], res[1]);
                   }
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + chunk * 16), "r"(pk[0]), "r"(pk[1]),
                                "r"(pk[2]), "r"(pk[3])
@@ -739,8 +740,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   uint32_t wg, wx;
                   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wg) : "r"(so + off));
                   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wx) : "r"(xb + off));
-                  const float ga = __uint_as_float(wg << 16), gb = __uint_as_float(wg & 0xffff0000u);
-                  const float xa = __uint_as_float(wx << 16) - m0, xbv = __uint_as_float(wx & 0xffff0000u) - m1;
+                  const float ga = h16_lo(wg), gb = h16_hi(wg);
+                  const float xa = h16_lo(wx) - m0, xbv = h16_hi(wx) - m1;
                   s0 += ga; q0 = fmaf(ga, xa, q0);
                   s1v += gb; q1 = fmaf(gb, xbv, q1);
                 }
@@ -875,8 +876,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          pk[j] = h16_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           // rows outside the tensor are never stored (TMA clips them) but the statistics below are summed from the
           // staging tile: for k > 1 such rows hold phantom outputs of the padded convolution, so they are zeroed
           if (do_stats && !valid) pk[j] = 0u;
@@ -963,7 +963,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                          : colbase + (uint32_t)r * (2 * BN) + (uint32_t)cp * 4;
           uint32_t w;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
-          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          const float a = h16_lo(w), b = h16_hi(w);
           s0 += a; q0 = fmaf(a, a, q0);
           s1 += b; q1 = fmaf(b, b, q1);
         }
@@ -1067,8 +1067,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 float v0 = fmaf(__uint_as_float(r[2 * j]), sc_s[col], sc_s[BN + col]);
                 float v1 = fmaf(__uint_as_float(r[2 * j + 1]), sc_s[col + 1], sc_s[BN + col + 1]);
                 if (p.apply_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                pk[j] = h16_pack(v0, v1);
               }
               const uint32_t line = so + (uint32_t)(c >> 1) * A_BYTES + (uint32_t)row * (BN >= 64 ? 128 : 2 * BN);
 #pragma unroll
@@ -1315,13 +1314,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     int ci = ci0 + i, co = co0 + threadIdx.x;
     float v = (ci < cin && co < cout) ? src[(size_t)ci * cout + co] : 0.f;
     tile[i][threadIdx.x] = v;
-    if (ci < cin && co < cout) w_io[(size_t)tap * cin * cout + (size_t)ci * cout + co] = __float2bfloat16_rn(v);
+    if (ci < cin && co < cout) w_io[(size_t)tap * cin * cout + (size_t)ci * cout + co] = h16_from(v);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int co = co0 + i, ci = ci0 + threadIdx.x;
     if (ci < cin && co < cout)
-      w_oi[(size_t)tap * cin * cout + (size_t)co * cin + ci] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+      w_oi[(size_t)tap * cin * cout + (size_t)co * cin + ci] = h16_from(tile[threadIdx.x][i]);
   }
 }
 
@@ -1376,12 +1375,12 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
       const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
       tile[i][threadIdx.x] = v;
       if (ci < e.cin && co < e.cout) {
-        bf16 part[3];
+        __nv_bfloat16 part[3];
         part[0] = __float2bfloat16_rn(v);
         const float r1 = v - __bfloat162float(part[0]);
         part[1] = __float2bfloat16_rn(r1);
         part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
-        bf16* row = e.w_io + ((size_t)tap * e.cin + ci) * Kd;
+        __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(e.w_io) + ((size_t)tap * e.cin + ci) * Kd;
         for (int p = 0; p < dparts; ++p)
           for (int q = 0; q < dparts - p; ++q) row[(size_t)doff[p] * 64 + (size_t)q * e.cout + co] = part[p];
       }
@@ -1391,12 +1390,12 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
       const int co = co0 + i, ci = ci0 + threadIdx.x;
       if (ci < e.cin && co < e.cout) {
         const float v = tile[threadIdx.x][i];
-        bf16 part[3];
+        __nv_bfloat16 part[3];
         part[0] = __float2bfloat16_rn(v);
         const float r1 = v - __bfloat162float(part[0]);
         part[1] = __float2bfloat16_rn(r1);
         part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
-        bf16* row = e.w_oi + ((size_t)tap * e.cout + co) * Kf;
+        __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(e.w_oi) + ((size_t)tap * e.cout + co) * Kf;
         for (int p = 0; p < fparts; ++p)
           for (int q = 0; q < fparts - p; ++q) row[(size_t)foff[p] * 64 + (size_t)q * e.cin + ci] = part[p];
       }
@@ -1407,12 +1406,12 @@ __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table, i
     const int ci = ci0 + i, co = co0 + threadIdx.x;
     const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;
     tile[i][threadIdx.x] = v;
-    if (ci < e.cin && co < e.cout) e.w_io[base + (size_t)ci * e.cout + co] = __float2bfloat16_rn(v);
+    if (ci < e.cin && co < e.cout) e.w_io[base + (size_t)ci * e.cout + co] = h16_from(v);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int co = co0 + i, ci = ci0 + threadIdx.x;
-    if (ci < e.cin && co < e.cout) e.w_oi[base + (size_t)co * e.cin + ci] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (ci < e.cin && co < e.cout) e.w_oi[base + (size_t)co * e.cin + ci] = h16_from(tile[threadIdx.x][i]);
   }
 }
 
@@ -1450,7 +1449,8 @@ static int make_act_map(CUtensorMap* m, const basi_tensor* t, int TW, int TH, in
                            (cuuint64_t)t->ld * es_b * t->w * t->h};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (BASI_H16_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
+                   4, t->ptr, dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    (uint64_t)box_c * es_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1471,7 +1471,8 @@ static int make_w_map(CUtensorMap* m, const void* w, int taps, int ndim, int kdi
   cuuint64_t strides[2] = {(cuuint64_t)kdim * 2, (cuuint64_t)kdim * 2 * ndim};
   cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, es,
+  CUresult r = enc(m, BASI_H16_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(w), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1697,6 +1698,9 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
   BASI_CHECK_ARG(d && a && b && out, "tc_conv_create: null argument");
   const basi_tensor* x = (kind == BASI_TC_DGRAD) ? b : a;   // forward input geometry
   const basi_tensor* y = (kind == BASI_TC_DGRAD) ? a : b;   // forward output geometry
+#if BASI_H16_FP16
+  BASI_CHECK_ARG(!split, "tc_conv_create_split: the split-operand (f32) mode lives in the bfloat16 build of the library");
+#endif
   if (split) {
     // operands are bf16 [hi|mid|lo] tensors with 3x the logical channels; destinations are float32
     basi_tensor xl = *x, yl = *y;

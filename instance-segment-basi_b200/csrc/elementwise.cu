@@ -859,15 +859,14 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, c
     a.w -= lr * b.w;
     reinterpret_cast<float4*>(w)[i] = a;
     if (wb) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-      reinterpret_cast<uint2*>(wb)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      reinterpret_cast<uint2*>(wb)[i] = make_uint2(h16_pack(a.x, a.y), h16_pack(a.z, a.w));
     }
   }
   if (blockIdx.x == 0) {
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       float a = w[i] - lr * g[i];
       w[i] = a;
-      if (wb) wb[i] = __float2bfloat16_rn(a);
+      if (wb) wb[i] = h16_from(a);
     }
   }
 }
@@ -929,12 +928,12 @@ __global__ void upsample_legacy_argmax_kernel(const float* __restrict__ x, int B
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    d[i] = __float2bfloat16_rn(s[i]);
+    d[i] = h16_from(s[i]);
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, int64_t n) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    d[i] = __bfloat162float(s[i]);
+    d[i] = h16_to(s[i]);
 }
 __global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ y, int64_t n) {
   pdl_prologue();
@@ -958,8 +957,8 @@ using namespace basi;
 // x (float32) -> [hi | mid | lo] bf16 parts with x == hi + mid + lo up to 2^-24 |x|: hi = bf16(x), mid = bf16(x - hi),
 // lo = bf16(x - hi - mid) (both differences are exact in float32).  The operands of the split-operand (fp32-grade)
 // tcgen05 convolutions: six bf16 MMAs (hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid) reproduce the float32 product.
-__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int ldx, int C, bf16* __restrict__ y,
-                                                     int ldy, int64_t total, int parts) {
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int ldx, int C,
+                                                     __nv_bfloat16* __restrict__ y, int ldy, int64_t total, int parts) {
   pdl_prologue();
   const int q = C / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -967,7 +966,7 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
     const int c = (int)(i - px * q) * 4;
     const float4 v = *reinterpret_cast<const float4*>(x + px * ldx + c);
     const float in[4] = {v.x, v.y, v.z, v.w};
-    bf16 h[4], m[4], l[4];
+    __nv_bfloat16 h[4], m[4], l[4];     // (always bfloat16: the parts rely on its float32 exponent range)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       h[j] = __float2bfloat16_rn(in[j]);
@@ -975,7 +974,7 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
       m[j] = __float2bfloat16_rn(r1);
       l[j] = __float2bfloat16_rn(r1 - __bfloat162float(m[j]));
     }
-    bf16* o = y + px * ldy + c;
+    __nv_bfloat16* o = y + px * ldy + c;
     *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
     *reinterpret_cast<uint2*>(o + C) = *reinterpret_cast<const uint2*>(m);
     if (parts == 3) *reinterpret_cast<uint2*>(o + 2 * C) = *reinterpret_cast<const uint2*>(l);
@@ -1250,6 +1249,7 @@ int basi_sm_count(void) {
   }
   return n;
 }
+int basi_half_format(void) { return BASI_H16_FP16; }   /* 0: the 16-bit storage type of this build is bfloat16, 1: IEEE fp16 */
 int basi_memset(void* ptr, int value, int64_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(ptr, value, (size_t)bytes, (cudaStream_t)stream);
   if (e != cudaSuccess) {
@@ -1733,8 +1733,12 @@ int basi_split3_bf16(const basi_tensor* x, const basi_tensor* y, void* stream) {
   BASI_CHECK_ARG(x->c % 4 == 0 && x->ld % 4 == 0 && y->ld % 4 == 0 && (((uintptr_t)x->ptr | (uintptr_t)y->ptr) & 15) == 0,
                  "split3_bf16: channels / strides must be multiples of 4 and pointers 16-byte aligned");
   const int64_t total = pixels(x) * (x->c / 4);
+#if BASI_H16_FP16
+  set_error("split3_bf16: the split-operand (f32) mode lives in the bfloat16 build of the library");
+  return BASI_E_INVALID;
+#endif
   basi::launch(split3_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const float*)x->ptr, x->ld, x->c,
-               (bf16*)y->ptr, y->ld, total, y->c / x->c);
+               (__nv_bfloat16*)y->ptr, y->ld, total, y->c / x->c);
   BASI_CHECK_LAUNCH("split3_bf16");
   return BASI_OK;
 }

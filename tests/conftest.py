@@ -25,3 +25,15 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _default_library_format():
+    """Kernel-level tests address the bfloat16 build; an f16 Engine of an earlier test must not leave the fp16 build
+    selected."""
+    try:
+        from basi_b200 import _lib
+        _lib.use("bf16")
+    except Exception:
+        pass
+    yield

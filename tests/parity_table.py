@@ -87,13 +87,13 @@ def compare(out, ref, variant):
     return row
 
 
-def model_rows(params, data, P, seg_name, ref_stage, policies):
+def model_rows(params, data, P, seg_name, ref_stage, policies, r16=torch.bfloat16):
     rows = {}
     with torch.no_grad():
         p32 = O.to_torch(params, torch.float32)
         x32 = torch.from_numpy(data).float()
         for name in policies:
-            out = O.pspnet_forward_rounded(p32, x32, P, O.ROUNDING_POLICIES[name], seg_name)
+            out = O.pspnet_forward_rounded(p32, x32, P, O.ROUNDING_POLICIES[name], seg_name, r16_dtype=r16)
             r = {}
             for s in STAGES:
                 r[s] = rel2(out[s].permute(0, 2, 3, 1).numpy(), ref_stage[s])
@@ -155,7 +155,11 @@ def main():
         print("%s: worst gradient tensors (rel-l2, share of |g|, name): %s" % (prec, r["grad_worst"]))
         print("%s: largest shares of the gradient error (share, name): %s" % (prec, r["grad_err_share"]))
     for name, r in model_rows(params, data, S // 8, O.VARIANTS[variant][0], ref, args.models.split(",")).items():
-        rows.append(("model: %s" % name, r))
+        rows.append(("model (bf16 roundings): %s" % name, r))
+    if "f16" in args.precisions.split(","):
+        for name, r in model_rows(params, data, S // 8, O.VARIANTS[variant][0], ref,
+                                  [m for m in args.models.split(",") if m != "none"], torch.float16).items():
+            rows.append(("model (fp16 roundings): %s" % name, r))
     text = fmt_table("%s, S=%d, F=%d, B=%d, trained-like weights: rel-l2 error vs the float64 oracle" % (
         variant, S, F, B), rows)
     print(text)

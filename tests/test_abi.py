@@ -23,6 +23,13 @@ def test_library_loads_and_exports_header_symbols():
     assert lib.basi_version() >= 100
 
 
+def test_fp16_build_exports_the_same_symbols():
+    lib = _lib.load("f16")
+    assert lib.basi_half_format() == 1 and _lib.load("bf16").basi_half_format() == 0
+    for s in header_symbols():
+        assert hasattr(lib, s), "missing export %s in the fp16 build" % s
+
+
 def test_binding_table_matches_header():
     assert sorted(_lib.exported_symbols()) == header_symbols()
 

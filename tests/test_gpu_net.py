@@ -133,7 +133,8 @@ def _bench_shape_run(variant, precision):
     out = T.engine_run(variant, nseg, S, F, B, classes, precision, dict(kind="bce", pos_weight=pw, class_weight=cw),
                        params, data, lab, cls, lr)
     row = T.compare(out, ref, variant)
-    model = T.model_rows(params, data, S // 8, O.VARIANTS[variant][0], ref, [out["storage"], "weights_only"])
+    model = T.model_rows(params, data, S // 8, O.VARIANTS[variant][0], ref, [out["storage"], "weights_only"],
+                         torch.float16 if precision == "f16" else torch.bfloat16)
     print("\n" + T.fmt_table("%s %s at S=320 F=32 B=4 vs float64 oracle" % (variant, precision),
                              [("CUDA " + precision, row)] + [("model " + k, v) for k, v in model.items()]))
     _bench_shape_cache[key] = (row, model, out)
@@ -163,6 +164,21 @@ def test_bf16_path_vs_oracle_at_benchmark_shape(variant, cfg):
     assert row["mask_agree"] >= m["mask_agree"] - 0.01
     # (no storage model exists for the backward pass; measured 0.81 / 0.82 with every gradient tensor stored in bf16)
     assert row["grad_cos"] > 0.75, row["grad_cos"]
+
+
+@pytest.mark.parametrize("variant,cfg", BENCH_SHAPE_CASES, ids=[c[1] for c in BENCH_SHAPE_CASES])
+def test_f16_path_meets_the_16bit_logit_tolerance_at_benchmark_shape(variant, cfg):
+    """precision "f16": the same tcgen05 kernels with IEEE fp16 storage (libbasi_b200_f16.so), loss-scaled gradients.
+    A 16-bit path that MEETS north_star's 2e-2 on the logits at the benchmark shape (bf16 cannot: its weights alone
+    cost 3e-2); masks and gradients are held to the fp16 storage model and to fixed floors."""
+    row, model, out = _bench_shape_run(variant, "f16")
+    assert out["tc_layers"] > 150
+    m = model[out["storage"]]
+    assert row["logits"] <= BF16_TOL, row["logits"]                       # north_star's 16-bit tolerance
+    assert row["logits"] <= 1.5 * m["logits"] + 1e-3, (row["logits"], m["logits"])
+    assert row["loss_rel"] < BF16_TOL
+    assert row["mask_agree"] >= m["mask_agree"] - 0.003 and row["mask_iou"] >= 0.995, (row["mask_agree"], row["mask_iou"])
+    assert row["grad_cos"] > 0.98, row["grad_cos"]
 
 
 @pytest.mark.xfail(strict=False, reason="bf16 operands cannot meet north_star's 2e-2 / IoU 0.999 on this network: "
