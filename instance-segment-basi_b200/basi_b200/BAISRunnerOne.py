@@ -53,7 +53,7 @@ class RunnerGUI(object):
     def click(self, image_u8_resized, where):
         """image: uint8 [S,S,3] already resized to input_size; where=[y,x].  Returns (mask uint8 [S,S], class id)."""
         eng = self.engine
-        self.pin_img.copy_(torch.from_numpy(np.ascontiguousarray(image_u8_resized)).view(self.pin_img.shape))
+        self.pin_img.copy_(torch.from_numpy(np.array(image_u8_resized, dtype=np.uint8)).view(self.pin_img.shape))
         self.pin_click[0, 0], self.pin_click[0, 1] = int(where[0]), int(where[1])
         eng.feed_clicks(self.pin_img, self.pin_click)
         if eng._graph is None:
