@@ -125,3 +125,106 @@ def test_psp_branches_are_tagged_and_their_pool_adjoints_deferred():
     ftags = [m.get("branch") for _, _, _, m in eng.fwd]
     fp = fnames.index("basi_avgpool_multi_fwd")
     assert ftags[fp] is None and fp + 1 == min(i for i, t in enumerate(ftags) if t is not None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: host logic of the new paths (all CPU, dry-run plans)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [16, 64, 128])
+def test_class_head_lowers_to_skinny_gemms_at_any_batch(B):
+    """the skinny-GEMM lowering used to accept batch sizes its kernels rejected (B = 49..64, B > 64).  One
+    predicate (basi_skinny_supported) now gates both lowerings and the kernels chunk the rows."""
+    from basi_b200 import _lib
+    lib = _lib.load()
+    assert lib.basi_skinny_supported(B, 25 * 1024, 512) == 1 and lib.basi_skinny_supported(B, 512, 21) == 1
+    e = Engine(build(), B, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
+    f = Counter(n for n, _, _, _ in e.fwd)
+    assert f["basi_skinny_fwd"] == 2
+
+
+def test_experiment_switches_need_the_master_switch(monkeypatch, capsys):
+    from basi_b200 import engine as E
+    monkeypatch.delenv("BASI_EXPERIMENTS", raising=False)
+    monkeypatch.setenv("BASI_NO_MASK_BITS", "1")
+    E._WARNED.discard("BASI_NO_MASK_BITS")
+    assert E._exp_env("BASI_NO_MASK_BITS") is None
+    assert "ignored" in capsys.readouterr().err
+    monkeypatch.setenv("BASI_EXPERIMENTS", "1")
+    assert E._exp_env("BASI_NO_MASK_BITS") == "1"
+
+
+def test_variant_b_plan_and_inventory():
+    from basi_b200.BAISNet import LinkNet
+    net = LinkNet(Placeholder((None, 320, 320, 3)), Placeholder((None, 320, 320, 1), name="mask"), num_classes=21)
+    spec = O.linknet_b_specs(21, 1.0)
+    assert list(net.variables.items()) == [(k, tuple(v)) for k, v in spec.items()]
+    segs, atts, classes = net.build()
+    assert [a.shape for a in atts] == [(20, 20, 2), (40, 40, 2), (80, 80, 2), (160, 160, 2)] and classes[0].shape == (21,)
+    e = Engine(net, 2, "f32", True, dict(kind="linknet_b"), dry_run=True)
+    f, b = Counter(n for n, _, _, _ in e.fwd), Counter(n for n, _, _, _ in e.bwd)
+    assert f["basi_maxpool2s2_fwd"] == 4 and f["basi_softmax_gate_fwd"] == 4 and f["basi_mask_mul_fwd"] == 9
+    assert f["basi_resize_nearest_fwd"] == 9
+    # the finest attention output and both of its resized copies feed nothing: no adjoint is emitted for them
+    assert b["basi_softmax_gate_bwd"] == 3 and b["basi_resize_nearest_bwd"] == 6 and b["basi_mask_mul_bwd"] == 8
+    losses = Counter(n for n, _, _, _ in e.lossl)
+    assert losses["basi_wbce_fwd_bwd"] == 4 and losses["basi_onehot2_f32"] == 4 and losses["basi_softmax_ce_fwd_bwd"] == 1
+
+
+def test_top_level_linknet_plan_and_inventory():
+    from basi_b200.BAISNet import LinkNetTop
+    net = LinkNetTop(Placeholder((None, 320, 320, 3)))
+    spec = O.linknet_top_specs(1.0)
+    assert list(net.variables.items()) == [(k, tuple(v)) for k, v in spec.items()]
+    segs, feats = net.build()
+    assert [s.shape for s in segs] == [(38, 38, 2), (78, 78, 2), (158, 158, 2), (158, 158, 2), (158, 158, 2)]
+    e = Engine(net, 2, "f32", True, dict(kind="linknet_b", pos_weight=1.0), dry_run=True)
+    f, b = Counter(n for n, _, _, _ in e.fwd), Counter(n for n, _, _, _ in e.bwd)
+    assert f["basi_add_fwd"] == 1 and b["basi_add_bwd"] == 1 and f["basi_resize_nearest_fwd"] == 8
+    assert e.label_seg.shape == (2, 320, 320, 1)                  # full-resolution labels (BAISRunnerTrain.py:38)
+
+
+def test_set_trainable_ranges_cover_exactly_the_named_variables():
+    e = Engine(build(), 2, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
+    n = e.set_trainable("class_attention")
+    assert n == 1                                                  # the class head's variables are contiguous
+    off, length = e._train_ranges[0]
+    names = [k for k in e.param_index if "class_attention" in k]
+    assert off == e.param_index[names[0]][0] and off + length == e.n_flat
+    with pytest.raises(KeyError):
+        e.set_trainable("no_such_scope")
+    assert e.set_trainable(None) == 0 and e._train_ranges is None
+
+
+def test_label_encodings_known_answers():
+    """uint8 semantics of back/4BorderClass/BAISData.py:143-160 and back/5COCO/BAISData.py:361-369."""
+    ann = np.array([[0, 1, 2, 255, 85, 86, 170, 254]], dtype=np.uint8)
+    # has_255=True, attended instance 2: background (0) wraps to 255 // 84 = 3, border 255 -> 171 -> 2, instance 2 -> 85
+    # -> 1, other instances: (k - 1) // 84  (ids >= 85 alias: 85 -> 1, 86 -> 1, 170 -> 2, 254 -> 3: reference quirk)
+    assert O.encode_labels_border(ann, 2).tolist() == [[3, 0, 1, 2, 1, 1, 2, 3]]
+    # has_255=False: border -> background -> (255) // 127 = 2, instance 2 -> 128 -> 1, others (k - 1) // 127
+    assert O.encode_labels_three(ann, 2).tolist() == [[2, 0, 1, 2, 0, 0, 1, 1]]
+    assert O.encode_labels_binary(ann, 2).tolist() == [[0, 0, 1, 0, 0, 0, 0, 0]]
+    s = np.array([[0, 1, 3, 0]], dtype=np.uint8)
+    a = np.array([[0, 0, 1, 1]], dtype=np.uint8)
+    assert O.encode_labels_coco(s, a).tolist() == [[0, 1, 2, 2]]
+    lab = np.array([[0, 1, 0], [1, 1, 0]])
+    assert O.sample_click(lab, 0, 8) == [0, 8] and O.sample_click(lab, 2, 8) == [8, 8]
+
+
+def test_data_reader_shards_annotations_by_rank():
+    from basi_b200.BAISData import Data
+    readers = []
+    for rank in range(2):
+        d = Data.__new__(Data)                                     # the sharding logic without a dataset on disk
+        d.rank, d.world, d._epoch, d._seed, d.batch_size = rank, 2, 0, 7, 2
+        d._annotations = list(range(10))
+        d._order = list(range(10))
+        d._random_index = d._order[rank::2]
+        d.number_patch = len(d._random_index) // d.batch_size
+        d._now = 0
+        readers.append(d)
+    assert readers[0]._random_index == [0, 2, 4, 6, 8] and readers[1]._random_index == [1, 3, 5, 7, 9]
+    for d in readers:
+        d._reshuffle()
+    a, b = readers[0]._random_index, readers[1]._random_index
+    assert sorted(a + b) == list(range(10)) and not set(a) & set(b)     # same permutation, disjoint slices
