@@ -267,6 +267,14 @@ int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight
 int basi_softmax_ce_fwd_bwd(const float* logits, const int32_t* labels, int64_t rows, int C, double scale,
                             float grad_scale, double* loss_acc, float* dlogits, void* stream);
 
+/* ---- (e) multi-GPU: averaged all-reduce of the flat gradient over NVLink peer memory ----
+ * The data-parallel exchange of SURVEY section 8(e) as ONE full-machine kernel per rank instead of NCCL launches that
+ * the persistent backward kernels starve.  bufs[q] / flags[q]: this process's mappings of rank
+ * q's symmetric gradient buffer and flag array (uint32[world], zero at start-up); seq_dev: device uint32, 0 at
+ * start-up on every rank.  Collective: every rank calls it once per step on its stream. */
+int basi_p2p_allreduce_mean(void* const* bufs, void* const* flags, int rank, int world, int64_t n, uint32_t* seq_dev,
+                            void* stream);
+
 /* ---- A17: GradientDescentOptimizer (2AddClass/BAISRunnerTrain.py:115-117): w -= lr*g ----
  * lr is read from device memory so a captured graph can be replayed with a new rate.
  * w_bf16 (optional) receives the bf16 copy of the updated weights. */

@@ -107,7 +107,7 @@ class Engine(object):
         self.net = net
         self.B = int(batch_size)
         self.precision = precision
-        self.loss_scale = 8192.0 if precision == "f16" else 1.0
+        self.loss_scale = 1.0          # f16: set by _pick_loss_scale once the number of logits is known
         self.adt = torch.float32 if precision == "f32" else (torch.float16 if precision == "f16" else torch.bfloat16)
         # which tensors are stored in 16 bits (names of oracle.ROUNDING_POLICIES; tests hold the path to that model)
         self.storage_policy = "none" if precision == "f32" else "round1"
@@ -737,6 +737,17 @@ class Engine(object):
                    1 if op["relu"] else 0)
 
     # ---- loss
+    def _pick_loss_scale(self, n_logits):
+        """f16 mode: static loss scale, a power of two that puts the scaled loss gradient of one logit (scale / N) near
+        0.25 -- 4096 at the benchmark shape (N = 25 600), 32 for a 64 x 64 toy batch -- so that neither the small
+        activation gradients underflow fp16 nor the batch-norm adjoints (x gamma * istd) overflow it."""
+        if self.precision != "f16":
+            return
+        s = 1.0
+        while s * 2 <= min(8192.0, n_logits / 4.0):
+            s *= 2
+        self.loss_scale = s
+
     def _lower_loss_linknet(self):
         """cal_loss of variant B (back/90AttentionSingle2/BAISRunnerTrain.py:116-156): every attention map against the
         nearest-resized labels as 2-channel weighted CE (pos_weight 3, mean over 2N elements), averaged over the maps,
@@ -767,6 +778,7 @@ class Engine(object):
             return
         self.label_seg = self._zeros((B, P_h, P_w, 1), torch.float32)
         lab = Act(self.label_seg)
+        self._pick_loss_scale(B * heads[0].shape[1] * heads[0].shape[2] * 2)
         self.lossl = []
         self._lab_scaled = []
         pw = float(cfg.get("pos_weight", 3.0))
@@ -834,6 +846,7 @@ class Engine(object):
         assert cfg is not None, "training needs a loss configuration"
         kind = cfg.get("kind", "bce" if nseg == 1 else "softmax")
         N = B * P_h * P_w
+        self._pick_loss_scale(N)
         self.lossl = []
         g = self._grad_of(self.seg_logits)
         self.seg_logits.gw = True
