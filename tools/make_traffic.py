@@ -16,6 +16,7 @@ GROUPS = [  # bench.py kernel-group name, regex on the demangled kernel name
     ("basi_bn_bwd_reduce", r"^bn_bwd_reduce"),
     ("basi_bn_bwd_apply", r"^bn_bwd_apply"),
     ("basi_bn_bwd_fused", r"^bn_bwd_resident"),
+    ("basi_bn_bwd_coop", r"^bn_bwd_coop"),
     ("basi_bn_apply", r"^bn_apply"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
