@@ -263,6 +263,14 @@ int basi_relu_bwd_f32(float* dy, const float* y, int64_t n, void* stream);
  * loss_acc[0] += scale * sum(loss_i) (double);  dlogits = grad_scale * dloss_i/dx. */
 int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight, double scale,
                       float grad_scale, int64_t n, double* loss_acc, float* dlogits, void* stream);
+/* F4 (back/8AttentionU/BAISRunnerTrain.py:176-180): the same loss on channel `sel` of C-channel rows
+ * (tf.split(segment, 2, axis=3)[1]); dlogits [rows][C] gets the gradient in channel `sel` and zeros elsewhere. */
+int basi_wbce_sel_fwd_bwd(const float* logits, int C, int sel, const float* labels, float pos_weight, double scale,
+                          float grad_scale, int64_t rows, double* loss_acc, float* dlogits, void* stream);
+/* F4: Net.sigmoid of the decoder logits (back/8AttentionU/BAISNet.py:527) -- cal_loss consumes the sigmoid outputs
+ * as "logits" -- and its adjoint dx (+)= dy * y * (1 - y).  float32, n elements. */
+int basi_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+int basi_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, int accumulate, void* stream);
 /* ---- A15/A16: tf.reduce_mean(sparse_softmax_cross_entropy_with_logits) (4BorderClass :111-116) ---- */
 int basi_softmax_ce_fwd_bwd(const float* logits, const int32_t* labels, int64_t rows, int C, double scale,
                             float grad_scale, double* loss_acc, float* dlogits, void* stream);

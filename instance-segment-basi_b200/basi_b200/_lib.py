@@ -99,6 +99,9 @@ SIGNATURES = {
     "basi_skinny_wgrad": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _P],
     "basi_relu_bwd_f32": [_P, _P, _i64, _P],
     "basi_wbce_fwd_bwd": [_P, _P, _f, _d, _f, _i64, _P, _P, _P],
+    "basi_wbce_sel_fwd_bwd": [_P, _i, _i, _P, _f, _d, _f, _i64, _P, _P, _P],
+    "basi_sigmoid_fwd": [_P, _P, _i64, _P],
+    "basi_sigmoid_bwd": [_P, _P, _P, _i64, _i, _P],
     "basi_softmax_ce_fwd_bwd": [_P, _P, _i64, _i, _d, _f, _P, _P, _P],
     "basi_p2p_allreduce_mean": [_P, _P, _i, _i, _i64, _P, _P],
     "basi_sgd_step": [_P, _P, _P, _i64, _P, _P],

@@ -845,6 +845,41 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_
   block_sum_atomic(acc * scale, loss_acc);
 }
 
+// F4 (back/8AttentionU): Net.sigmoid on the C-channel decoder logits and its adjoint; weighted BCE that reads channel
+// `sel` of C-channel "logits" (cal_loss takes tf.split(segment, 2, axis=3)[1]) and writes a full-width gradient.
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float e = expf(-fabsf(v));
+    y[i] = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+  }
+}
+
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                   int64_t n, int accumulate) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = y[i];
+    const float g = dy[i] * s * (1.f - s);
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wbce_sel_kernel(const float* __restrict__ logits, int C, int sel, const float* __restrict__ labels, float q,
+                double scale, float gscale, int64_t rows, double* __restrict__ loss_acc, float* __restrict__ dlogits) {
+  pdl_prologue();
+  double acc = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float g;
+    acc += (double)wbce_term(logits[r * C + sel], labels[r], q, gscale, g);
+    if (dlogits)
+      for (int c = 0; c < C; ++c) dlogits[r * C + c] = c == sel ? g : 0.f;
+  }
+  block_sum_atomic(acc * scale, loss_acc);
+}
+
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ lr_dev,
                            int64_t n, bf16* __restrict__ wb) {
   pdl_prologue();
@@ -1680,6 +1715,29 @@ int basi_wbce_fwd_bwd(const float* logits, const float* labels, float pos_weight
   basi::launch(wbce_kernel, grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream, logits, labels, pos_weight, scale, grad_scale, n,
                                                                     loss_acc, dlogits);
   BASI_CHECK_LAUNCH("wbce_fwd_bwd");
+  return BASI_OK;
+}
+
+int basi_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
+  BASI_CHECK_ARG(x && y && n > 0, "sigmoid_fwd: bad argument");
+  basi::launch(sigmoid_fwd_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, x, y, n);
+  BASI_CHECK_LAUNCH("sigmoid_fwd");
+  return BASI_OK;
+}
+
+int basi_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && y && dx && n > 0, "sigmoid_bwd: bad argument");
+  basi::launch(sigmoid_bwd_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, dy, y, dx, n, accumulate);
+  BASI_CHECK_LAUNCH("sigmoid_bwd");
+  return BASI_OK;
+}
+
+int basi_wbce_sel_fwd_bwd(const float* logits, int C, int sel, const float* labels, float pos_weight, double scale,
+                          float grad_scale, int64_t rows, double* loss_acc, float* dlogits, void* stream) {
+  BASI_CHECK_ARG(logits && labels && loss_acc && rows > 0 && C > 0 && sel >= 0 && sel < C, "wbce_sel: bad argument");
+  basi::launch(wbce_sel_kernel, grid_for(rows, 256, 4), 256, 0, (cudaStream_t)stream, logits, C, sel, labels, pos_weight,
+               scale, grad_scale, rows, loss_acc, dlogits);
+  BASI_CHECK_LAUNCH("wbce_sel_fwd_bwd");
   return BASI_OK;
 }
 
