@@ -50,6 +50,10 @@ WORKLOADS["variantB"] = dict(
     variant="90AttentionSingle2", S=320, batch=8, classes=21, flop_per_image=3 * 2 * 31.0e9 * (320.0 / 224.0) ** 2,
     text="F1: variant B (slim vgg_16 trunk + click-gated attention cascade, 90AttentionSingle2), synthetic 320x320, "
          "batch 8 per GPU, SGD; the biased vgg convolutions run on the CUDA-core fp32 path")
+WORKLOADS["cascade"] = dict(
+    variant="8AttentionU", S=320, batch=16, classes=21, flop_per_image=107.9e9 + 4 * 45.4e9,
+    text="F4: cascaded attention re-decoding (8AttentionU: 2AddClass trunk + four pyramid decoders + four class "
+         "heads, cal_loss on the sigmoid outputs), synthetic 320x320, batch 16 per GPU, F=32, SGD")
 DEFAULT_WORKLOAD = "cfg3"
 GOLDEN_IMAGE = os.path.join(ROOT, "tests", "golden", "input_7.jpg")     # the reference's input/7.jpg (cfg1)
 
@@ -135,8 +139,10 @@ def cpu_oracle_rate(wl, batch, steps, warmup=1):
     snap = _snapshot(variant)
     nseg = snap["num_segment"]
     sd = SyntheticData(batch, (S, S), 8, classes, nseg, sigma=20 if variant == "5COCO" else 30, seed=0)
-    vb = variant == "90AttentionSingle2"
-    params = O.init_params(O.linknet_b_specs(classes, 1.0) if vb else O.param_specs(variant, classes, nseg, FILTERS), 0)
+    vb, casc = variant == "90AttentionSingle2", variant == "8AttentionU"
+    params = O.init_params(O.linknet_b_specs(classes, 1.0) if vb else
+                           O.attention_u_specs(classes, nseg, FILTERS, 2) if casc else
+                           O.param_specs(variant, classes, nseg, FILTERS), 0)
     times = []
     for i in range(warmup + steps):
         img, clicks, lab, cls = sd.next_batch()
@@ -144,6 +150,9 @@ def cpu_oracle_rate(wl, batch, steps, warmup=1):
         data = np.stack([O.pack_input(img[b], clicks[b], sd.sigma) for b in range(batch)])
         if vb:
             r = O.linknet_b_train_step(params, data[..., :3], data[..., 3:4], lab, cls, 5e-3, torch.float32)
+        elif casc:
+            r = O.attention_u_train_step(params, data, lab, (lab == 1).astype(np.float32), cls, S // 8, 5e-3,
+                                         torch.float32)
         else:
             r = O.train_step(params, data, lab, cls, variant, nseg, S // 8, snap["pos_weight"], snap["class_weight"],
                              5e-3, torch.float32)

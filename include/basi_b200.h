@@ -205,7 +205,9 @@ int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int ac
 /* All pyramid pools of one tensor in ONE pass (BAISPSPNet.py:683-710: windows 40/20/13/6 of conv5_3 at 320^2): ks[p]
  * is the window (= stride) of pool p, ys[p] its output ([n, h/k, w/k, c]).  `scratch` holds
  * basi_avgpool_multi_scratch_floats() zero-initialised floats; the call leaves it zeroed again.  The adjoint adds
- * (accumulate != 0) or writes every pool's contribution to dx in one read-modify-write pass.  At most 4 pools. */
+ * (accumulate != 0) or writes every pool's contribution to dx in one read-modify-write pass.  At most 4 pools and
+ * 96 output cells in total; basi_avgpool_multi_scratch_floats returns -1 for a group the pass cannot take (the caller
+ * then uses basi_avgpool_fwd / _bwd per pool). */
 int64_t basi_avgpool_multi_scratch_floats(const basi_tensor* x, int n_pools, const int* ks);
 int basi_avgpool_multi_fwd(const basi_tensor* x, int n_pools, const int* ks, const basi_tensor* const* ys,
                            float* scratch, void* stream);

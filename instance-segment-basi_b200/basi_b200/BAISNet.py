@@ -17,7 +17,7 @@ the four attention logit maps (coarse to fine) and the class logits.
 """
 from __future__ import annotations
 
-from .BAISPSPNet import Network, Placeholder  # noqa: F401
+from .BAISPSPNet import Network, Placeholder, PSPNet  # noqa: F401
 
 VGG_BLOCKS = ((1, 2, 64), (2, 2, 128), (3, 3, 256), (4, 3, 512), (5, 3, 512))
 
@@ -150,3 +150,68 @@ class LinkNetTop(Network):
         self.feed(cur).conv(3, 3, 2, 1, 1, biased=True, relu=False, name='attention_0')
         self.attentions.append(self.layers['attention_0'])
         self.segments = list(self.attentions)
+
+
+class BAISNet(PSPNet):
+    """Cascaded attention re-decoding: back/8AttentionU/BAISNet.py:13-650,
+    ``BAISNet(input_data, is_training, num_classes, num_segment, segment_attention, last_pool_size, filter_number,
+    attention_module_num).build()`` -> ``(segments, attentions, classes)``.
+
+    The 2AddClass trunk, then four pyramid decoders (:487-530) in the scopes '', attention_1, attention_2,
+    attention_3; the last ``attention_module_num`` decode 2 channels, the others ``num_segment``.  Decoder k reads the
+    feature multiplied by the softmax attention channel of decoder k-1 (:584-637), every gated feature also feeds a
+    class head (:533-544).  ``segments`` are the SIGMOID outputs -- ``cal_loss`` consumes them as logits."""
+
+    cascade = True
+    SCOPES = ('', 'attention_1/', 'attention_2/', 'attention_3/')
+
+    def __init__(self, input_data, is_training=True, num_classes=21, num_segment=4, segment_attention=1,
+                 last_pool_size=90, filter_number=32, attention_module_num=2):
+        self.variant = "4BorderClass"
+        self.attention_class = None
+        self.num_classes, self.num_segment = num_classes, num_segment
+        self.segment_attention, self.attention_module_num = segment_attention, attention_module_num
+        self.last_pool_size, self.filter_number = last_pool_size, filter_number
+        self.segments, self.attentions, self.classes = [], [], []
+        self.segment_logits = []
+        Network.__init__(self, {'data': input_data}, num_classes, num_segment, True, is_training, last_pool_size,
+                         filter_number)
+
+    def build(self):
+        return self.segments, self.attentions, self.classes
+
+    def _decoder(self, source, scope, nseg):
+        F, P = self.filter_number, self.last_pool_size
+        lg = self._pyramid_decoder(source, F, P, nseg, 'conv6_n_4', scope)
+        self.feed(lg).sigmoid(name=lg + '/sigmoid')
+        self.segment_logits.append(self.layers[lg])
+        self.segments.append(self.layers[lg + '/sigmoid'])
+        return lg
+
+    def _classifies(self, source, scope):
+        F, P = self.filter_number, self.last_pool_size
+        pool_ratio = 5
+        ps = P // pool_ratio
+        (self.feed(source)
+         .avg_pool(ps, ps, ps, ps, name=scope + 'class_attention_pool')
+         .conv(pool_ratio, pool_ratio, F * 16, pool_ratio, pool_ratio, name=scope + 'class_attention_conv')
+         .squeeze(name=scope + 'class_attention_squeeze')
+         .fc(num_out=self.num_classes, relu=False, name=scope + 'class_attention_fc'))
+        self.classes.append(self.layers[scope + 'class_attention_fc'])
+
+    def setup(self, is_training, num_classes, num_segment, last_pool_size, filter_number):
+        feat = self._trunk(filter_number)
+        n = len(self.SCOPES)
+        first_two = n - self.attention_module_num            # decoders with index >= first_two have 2 channels
+        lg = self._decoder(feat, '', num_segment if first_two > 0 else 2)
+        for i in range(1, n + 1):
+            sc = self.SCOPES[i] if i < n else ''
+            sel = self.segment_attention if (i - 1) < first_two else 1
+            gate = lg + '/softmax_attention'
+            self.feed(lg).softmax_gate(sel=sel, thr=-1.0, name=gate)       # tf.split(softmax, n)[sel], no threshold
+            self.attentions.append(self.layers[gate])
+            (self.feed(feat, gate).mask_multiply(name=sc + 'class_attention_multiply'))
+            feat = sc + 'class_attention_multiply'                         # (the reference's "multiply * 1")
+            self._classifies(feat, sc)
+            if i < n:
+                lg = self._decoder(feat, sc, num_segment if i < first_two else 2)

@@ -178,6 +178,11 @@ class Network(object):
         return self._node("softmax_gate", name, [input], (h, w, 1), sel=sel, thr=thr)
 
     @layer
+    def sigmoid(self, input, name):
+        """tf.nn.sigmoid on a float32 logit map (back/8AttentionU/BAISNet.py:527)."""
+        return self._node("sigmoid", name, [input], input.shape)
+
+    @layer
     def avg_pool(self, input, k_h, k_w, s_h, s_w, name, padding="VALID"):
         if not (k_h == k_w == s_h == s_w and padding == "VALID"):
             raise NotImplementedError("avg_pool: only k == s VALID is on the hot path")
@@ -282,9 +287,8 @@ class PSPNet(Network):
          .relu(name=prefix + '/relu'))
         return prefix + '/relu'
 
-    def setup(self, is_training, num_classes, num_segment, last_pool_size, filter_number):
-        v = VARIANTS[self.variant]
-        F = filter_number
+    def _trunk(self, F):
+        """conv1_1 .. conv5_3/relu (2AddClass/BAISPSPNet.py:173-470); returns the name of the last layer."""
         (self.feed('data')
          .conv(3, 3, F, 2, 2, biased=False, relu=False, padding='SAME', name='conv1_1_3x3_s2_n')
          .batch_normalization(relu=False, name='conv1_1_3x3_s2_bn')
@@ -300,22 +304,34 @@ class PSPNet(Network):
             for b in range(1, blocks + 1):
                 cur = self._bottleneck('conv%d_%d' % (stage, b), cur, F * mult, stride if b == 1 else 1, dilation,
                                        project=(b == 1))
-        shape = self.layers['conv5_3/relu'].shape[0:2]
+        return cur
+
+    def _pyramid_decoder(self, source, F, last_pool_size, num_segment, seg_name, scope=''):
+        """Pyramid pooling (levels 1/2/3/6) + conv5_4 + the 1x1 segment head on `source`; layer and variable names are
+        prefixed with `scope` (the cascade of back/8AttentionU builds four of these)."""
+        shape = self.layers[source].shape[0:2]
         ofn = F * 32 // 4
         for level in (1, 2, 3, 6):
             k = last_pool_size // level
-            p = 'conv5_3_pool%d' % level
-            (self.feed('conv5_3/relu')
+            p = scope + 'conv5_3_pool%d' % level
+            (self.feed(source)
              .avg_pool(k, k, k, k, name=p)
              .conv(1, 1, ofn, 1, 1, biased=False, relu=False, name=p + '_conv')
              .batch_normalization(relu=True, name=p + '_conv_bn')
              .resize_bilinear(shape, name=p + '_interp'))
-        (self.feed('conv5_3/relu', 'conv5_3_pool6_interp', 'conv5_3_pool3_interp', 'conv5_3_pool2_interp',
-                   'conv5_3_pool1_interp')
-         .concat(axis=-1, name='conv5_3_concat')
-         .conv(3, 3, ofn, 1, 1, biased=False, relu=False, padding='SAME', name='conv5_4')
-         .batch_normalization(relu=True, name='conv5_4_bn')
-         .conv(1, 1, num_segment, 1, 1, biased=True, relu=False, name=v["seg"]))
+        (self.feed(source, scope + 'conv5_3_pool6_interp', scope + 'conv5_3_pool3_interp',
+                   scope + 'conv5_3_pool2_interp', scope + 'conv5_3_pool1_interp')
+         .concat(axis=-1, name=scope + 'conv5_3_concat')
+         .conv(3, 3, ofn, 1, 1, biased=False, relu=False, padding='SAME', name=scope + 'conv5_4')
+         .batch_normalization(relu=True, name=scope + 'conv5_4_bn')
+         .conv(1, 1, num_segment, 1, 1, biased=True, relu=False, name=scope + seg_name))
+        return scope + seg_name
+
+    def setup(self, is_training, num_classes, num_segment, last_pool_size, filter_number):
+        v = VARIANTS[self.variant]
+        F = filter_number
+        self._trunk(F)
+        self._pyramid_decoder('conv5_3/relu', F, last_pool_size, num_segment, v["seg"])
         if v["fc"] is None:
             return
         place = self.attention_class if self.attention_class is not None else v["place"]

@@ -28,6 +28,9 @@ SNAPSHOT = {
     # loss = mean 2-channel weighted CE of the four attention maps + class CE
     "90AttentionSingle2": dict(num_segment=1, kind="linknet_b", pos_weight=3.0, class_weight=1.0, lr=5e-3,
                                num_steps=500001),
+    # cascaded attention re-decoding (back/8AttentionU/BAISRunnerTrain.py:28-38,161-193): 2AddClass trunk + four
+    # pyramid decoders; loss on the sigmoid outputs (2 x softmax CE, 2 x doubled weighted BCE) + 0.1 * four class CEs
+    "8AttentionU": dict(num_segment=4, kind="cascade", pos_weight=3.0, class_weight=0.1, lr=5e-3, num_steps=500001),
 }
 
 
@@ -91,6 +94,19 @@ class Train(object):
             self.raw_output_segment = net.attentions[-1]
             self.raw_output_classes = net.classes[0]
             return net, engine
+        if self.variant == "8AttentionU":
+            from .BAISNet import BAISNet
+            net = BAISNet(Placeholder((None, self.input_size[0], self.input_size[1], 4)), is_training=True,
+                          num_classes=self.num_classes, num_segment=self.num_segment, segment_attention=1,
+                          last_pool_size=self.last_pool_size, filter_number=self.filter_number,
+                          attention_module_num=2)
+            engine = Engine(net, self.batch_size, precision, True, self.loss_cfg, device, use_tc)
+            if self.synthetic:
+                engine.enable_click_input(self.data_reader.sigma)
+            self.segments, self.attentions, self.classes = net.build()
+            self.raw_output_segment = self.segments[0]           # final_segment_logit / final_class_logit (:63-64)
+            self.raw_output_classes = self.classes[0]
+            return net, engine
         image_placeholder = Placeholder((None, self.input_size[0], self.input_size[1], 4))
         net = PSPNet({'data': image_placeholder}, is_training=True, num_classes=self.num_classes,
                      num_segment=self.num_segment, last_pool_size=self.last_pool_size,
@@ -103,6 +119,12 @@ class Train(object):
         self.raw_output_classes = net.layers[fc] if fc else None
         return net, engine
 
+    def _attention_labels(self, label_seg):
+        """8AttentionU: ann_attention = (ann == 1) next to the 4-class labels (back/8AttentionU/BAISData.py:67)."""
+        if self.variant != "8AttentionU":
+            return None
+        return (np.asarray(label_seg) == 1).astype(np.float32)
+
     def run_step(self, step, batch=None, fetch=True):
         """One reference ``sess.run([... train_op ...], feed_dict)``; returns the fetched values."""
         eng = self.engine
@@ -110,11 +132,12 @@ class Train(object):
         if self.synthetic:
             images, clicks, label_seg, label_cls = batch if batch is not None else self.data_reader.next_batch()
             eng.feed_clicks(images, clicks)
-            eng.feed(None, label_seg, label_cls, lr)
+            eng.feed(None, label_seg, label_cls, lr, label_att=self._attention_labels(label_seg))
         else:
             data, ann, cls, _, _ = batch if batch is not None else self.data_reader.next_batch_train()
             label_cls, label_seg = cls, np.asarray(ann)
-            eng.feed(np.asarray(data, dtype=np.float32), label_seg, np.asarray(cls, dtype=np.int32), lr)
+            eng.feed(np.asarray(data, dtype=np.float32), label_seg, np.asarray(cls, dtype=np.int32), lr,
+                     label_att=self._attention_labels(label_seg))
         if self.use_cuda_graph:
             if eng._graph is None:
                 eng.capture(train=True, sync_grads=self.dp)

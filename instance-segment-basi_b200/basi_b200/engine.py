@@ -54,7 +54,7 @@ def _exp_env(name):
 
 
 _WARNED = set()
-_PSP_BRANCH = re.compile(r"^conv5_3_pool(\d)")     # pool1 / pool2 / pool3 / pool6 -> branch stream 0 / 1 / 2 / 3
+_PSP_BRANCH = re.compile(r"(?:^|/)conv5_3_pool(\d)")     # pool1 / pool2 / pool3 / pool6 -> branch stream 0 / 1 / 2 / 3
 
 
 class Act(object):
@@ -105,6 +105,9 @@ class Engine(object):
         _lib.use(self.lib_fmt)
         _lib.load()
         self.net = net
+        # vgg_16 family (variant B, top-level LinkNet): split image / click-map inputs, biased slim convolutions,
+        # per-map 2-channel losses.  (The cascade of back/8AttentionU also has `.attentions` but is a PSPNet.)
+        self._vgg_family = hasattr(net, "attentions") and not getattr(net, "cascade", False)
         self.B = int(batch_size)
         self.precision = precision
         self.loss_scale = 1.0          # f16: set by _pick_loss_scale once the number of logits is known
@@ -337,7 +340,7 @@ class Engine(object):
         for n in nodes:
             # the four pyramid-pooling branches (pool -> 1x1 conv -> BN -> bilinear into a concat slice) are independent
             # chains of tiny kernels: their calls are tagged and run on per-branch streams (see _run)
-            m = _PSP_BRANCH.match(n.name or "")
+            m = _PSP_BRANCH.search(n.name or "")
             self._cur_branch = {1: 0, 2: 1, 3: 2, 6: 3}.get(int(m.group(1)), int(m.group(1)) % 4) if m else None
             first_op = len(self._ops)
             getattr(self, "_lower_" + n.op)(n)
@@ -363,7 +366,7 @@ class Engine(object):
 
     def _lower_data(self, n):
         h, w, c = n.shape
-        if hasattr(self.net, "attentions"):
+        if self._vgg_family:
             # variant B: image (3 ch) and click map (1 ch) are two placeholders; both are channel-slice views of ONE
             # NHWC4 float32 buffer so that basi_clickmap_pack (uint8 image + click -> NHWC4) feeds them directly
             if getattr(self, "_input4", None) is None:
@@ -422,7 +425,7 @@ class Engine(object):
             return
         # slim conv2d of the vgg_16 trunk (variant B): bias + ReLU, no BN.  In bf16 mode these stay bf16 so that they
         # run on the tcgen05 path (bias + ReLU in its epilogue); every other BN-less conv is a float32 head
-        vgg_like = (hasattr(self.net, "attentions") and self.precision != "f32" and not has_bn and s == 1 and co > 4)
+        vgg_like = (self._vgg_family and self.precision != "f32" and not has_bn and s == 1 and co > 4)
         f32_out = (not has_bn) and not vgg_like
         y = self._out_act(n, torch.float32 if f32_out else None)
         desc = ConvDesc(k, a["k_w"], s, d, pt, pl, 1 if (a["relu"] and not has_bn) else 0)
@@ -539,7 +542,9 @@ class Engine(object):
         x = self._acts[n.inputs[0].index]
         # pyramid pooling: every avg_pool reading this tensor is computed in ONE pass, emitted at the first of them
         sibs = [c for c in self._cons[n.inputs[0].index] if c.op == "avg_pool"]
-        if self.fuse_pools and 2 <= len(sibs) <= 4:
+        if len(sibs) > 4:      # the cascade (F4): a gated feature feeds a class-head pool and the next decoder's pyramid
+            sibs = [c for c in sibs if _PSP_BRANCH.search(c.name or "")]
+        if self.fuse_pools and 2 <= len(sibs) <= 4 and n in sibs and self._pool_group_fits(x, sibs):
             grp = dict(x=x, ops=[])
             for sib in sibs:
                 op = dict(x=x, y=self._out_act(sib), k=sib.attrs["k"], group=grp)
@@ -553,6 +558,10 @@ class Engine(object):
         self._acts[n.index] = y
         self._ops.append(("avgpool", op))
         self._call(self.fwd, "basi_avgpool_fwd", x.ref, op["k"], y.ref)
+
+    def _pool_group_fits(self, x, sibs):
+        ks = (C.c_int * len(sibs))(*[sb.attrs["k"] for sb in sibs])
+        return _lib.load().basi_avgpool_multi_scratch_floats(C.byref(x.desc), len(sibs), ks) > 0
 
     def _pool_group_args(self, grp, grads):
         ops = grp["ops"]
@@ -632,6 +641,15 @@ class Engine(object):
         self._ops.append(("softgate", op))
         self._call(self.fwd, "basi_softmax_gate_fwd", logits.t.data_ptr(), C.c_int64(self.B * h * w), c, op["sel"],
                    C.c_float(op["thr"]), gate.t.data_ptr())
+
+    def _lower_sigmoid(self, n):
+        x = self._acts[n.inputs[0].index]
+        assert x.t.dtype == torch.float32
+        h, w, c = n.shape
+        y = Act(self._alloc((self.B, h, w, c), torch.float32))
+        self._acts[n.index] = y
+        self._ops.append(("sigmoid", dict(x=x, y=y, n=self.B * h * w * c)))
+        self._call(self.fwd, "basi_sigmoid_fwd", x.t.data_ptr(), y.t.data_ptr(), C.c_int64(self.B * h * w * c))
 
     def _lower_squeeze(self, n):
         self._acts[n.index] = self._acts[n.inputs[0].index]
@@ -808,8 +826,62 @@ class Engine(object):
         else:
             self.label_cls = None
 
+    def _lower_loss_cascade(self):
+        """cal_loss of the cascade (back/8AttentionU/BAISRunnerTrain.py:161-193) on the SIGMOID outputs: softmax CE
+        against the 4-class labels for the first decoders, 2 x weighted BCE (pos_weight 3) of channel 1 against the
+        attention labels for the last `attention_module_num`; loss = mean(segment terms) + 0.1 * mean(class CEs).
+        Predictions come from segments[0] / classes[0] (:63-69)."""
+        cfg = self.loss_cfg or {}
+        net = self.net
+        segs = [self._acts[nd.index] for nd in net.segments]
+        clss = [self._acts[nd.index] for nd in net.classes]
+        self.segments, self.classes_logits = segs, clss
+        self.seg_logits, self.seg_name = segs[0], net.segments[0].name
+        self.cls_logits, self.cls_name = clss[0], net.classes[0].name
+        B, P_h, P_w, nseg = segs[0].shape
+        N = B * P_h * P_w
+        self.loss_acc = self._zeros(4, torch.float64)
+        self.pred_seg = self._zeros((B, P_h, P_w, 1), torch.int32)
+        self.pred_cls = self._zeros((B,), torch.int32)
+        self.post = []
+        self._call(self.post, "basi_argmax", segs[0].t.data_ptr(), C.c_int64(N), nseg, self.pred_seg.data_ptr())
+        self._call(self.post, "basi_argmax", clss[0].t.data_ptr(), C.c_int64(B), clss[0].shape[3],
+                   self.pred_cls.data_ptr())
+        if not self.training:
+            return
+        self._pick_loss_scale(N)
+        self.label_seg = self._zeros((B, P_h, P_w, 1), torch.int32)
+        self.label_att = self._zeros((B, P_h, P_w, 1), torch.float32)
+        self.label_cls = self._zeros((B,), torch.int32)
+        self.lossl = []
+        pw = float(cfg.get("pos_weight", 3.0))
+        n_ce = len(segs) - int(net.attention_module_num)
+        for i, a in enumerate(segs):
+            g = self._grad_of(a)
+            a.gw = True
+            c = a.shape[3]
+            if i < n_ce:
+                self._call(self.lossl, "basi_softmax_ce_fwd_bwd", a.t.data_ptr(), self.label_seg.data_ptr(),
+                           C.c_int64(N), c, C.c_double(1.0 / (len(segs) * N)),
+                           C.c_float(self.loss_scale / (len(segs) * N)), self.loss_acc.data_ptr(), g.t.data_ptr())
+            else:
+                self._call(self.lossl, "basi_wbce_sel_fwd_bwd", a.t.data_ptr(), c, 1, self.label_att.data_ptr(),
+                           C.c_float(pw), C.c_double(2.0 / (len(segs) * N)),
+                           C.c_float(2.0 * self.loss_scale / (len(segs) * N)), C.c_int64(N),
+                           self.loss_acc.data_ptr(), g.t.data_ptr())
+        self.class_weight = float(cfg.get("class_weight", 0.1))
+        for a in clss:
+            g = self._grad_of(a)
+            a.gw = True
+            self._call(self.lossl, "basi_softmax_ce_fwd_bwd", a.t.data_ptr(), self.label_cls.data_ptr(), C.c_int64(B),
+                       a.shape[3], C.c_double(1.0 / (len(clss) * B)),
+                       C.c_float(self.loss_scale * self.class_weight / (len(clss) * B)),
+                       self.loss_acc.data_ptr() + 8, g.t.data_ptr())
+
     def _lower_loss(self):
-        if (self.loss_cfg or {}).get("kind") == "linknet_b" or hasattr(self.net, "attentions"):
+        if getattr(self.net, "cascade", False):
+            return self._lower_loss_cascade()
+        if (self.loss_cfg or {}).get("kind") == "linknet_b" or self._vgg_family:
             return self._lower_loss_linknet()
         cfg = self.loss_cfg
         segname = (cfg or {}).get("seg")
@@ -931,15 +1003,23 @@ class Engine(object):
         logits, gate = op["logits"], op["gate"]
         if gate.grad is None:
             return
-        assert logits.gw, "the attention loss gradient must be written before the gate adjoint adds to it"
+        acc = self._acc_flag(logits)        # (the loss / sigmoid adjoint may or may not have written it already)
         n, h, w, _ = gate.shape
         self._call(self.bwd, "basi_softmax_gate_bwd", logits.t.data_ptr(), gate.grad.t.data_ptr(), C.c_int64(n * h * w),
-                   op["C"], op["sel"], C.c_float(op["thr"]), logits.grad.t.data_ptr(), 1)
+                   op["C"], op["sel"], C.c_float(op["thr"]), logits.grad.t.data_ptr(), acc)
+
+    def _bwd_sigmoid(self, op):
+        x, y = op["x"], op["y"]
+        if y.grad is None or not y.gw:
+            return
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_sigmoid_bwd", y.grad.t.data_ptr(), y.t.data_ptr(), x.grad.t.data_ptr(),
+                   C.c_int64(op["n"]), acc)
 
     def _bwd_conv(self, op):
         x, y = op["x"], op["y"]
         dy = y.grad
-        if hasattr(self.net, "attentions") and (dy is None or not y.gw):
+        if self._vgg_family and (dy is None or not y.gw):
             return                                   # variant B: the finest attention output feeds nothing
         assert dy is not None and y.gw, "conv %s: no gradient reaches its output" % op["name"]
         if op["relu"] and y.dtype == _lib.F32 and y.desc.ld == y.desc.c:
@@ -1436,7 +1516,7 @@ class Engine(object):
         _lib.LAUNCHES += self.launches_per_step()
 
     # ---- host-facing helpers
-    def feed(self, data=None, label_seg=None, label_cls=None, lr=None, mask=None):
+    def feed(self, data=None, label_seg=None, label_cls=None, lr=None, mask=None, label_att=None):
         """Copies host arrays (numpy or pinned torch tensors) into the static device buffers."""
         if data is not None:
             self.input.t.copy_(_as_tensor(data, torch.float32).view(self.input.t.shape), non_blocking=True)
@@ -1445,6 +1525,8 @@ class Engine(object):
         if label_seg is not None:
             self.label_seg.copy_(_as_tensor(label_seg, self.label_seg.dtype).view(self.label_seg.shape),
                                  non_blocking=True)
+        if label_att is not None:     # the cascade (F4): {0,1} attention labels next to the 4-class segment labels
+            self.label_att.copy_(_as_tensor(label_att, torch.float32).view(self.label_att.shape), non_blocking=True)
         if label_cls is not None and self.label_cls is not None:
             self.label_cls.copy_(_as_tensor(label_cls, torch.int32).view(self.label_cls.shape), non_blocking=True)
         if lr is not None:

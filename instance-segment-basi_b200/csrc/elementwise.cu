@@ -1517,6 +1517,7 @@ int64_t basi_avgpool_multi_scratch_floats(const basi_tensor* x, int n_pools, con
   if (!x || !ks || n_pools < 1 || n_pools > MP_MAX) return -1;
   int64_t cells = 0;
   for (int p = 0; p < n_pools; ++p) cells += (int64_t)(x->h / ks[p]) * (x->w / ks[p]);
+  if (cells * MP_CH * (int64_t)sizeof(float) > 48 * 1024) return -1;   // the per-block cell table must fit shared memory
   return (int64_t)x->n * cells * x->c;
 }
 

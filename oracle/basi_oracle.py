@@ -312,17 +312,8 @@ def init_params(specs, seed=0, dtype=np.float32, trained_like=False):
 # --------------------------------------------------------------------------
 
 
-def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_pool_size=40,
-                   attention_channel=None, keep=()):
-    """Forward pass.  params: {tf name: torch tensor}; data: [B,S,S,4] torch tensor (NHWC).
-
-    Returns dict with NHWC tensors: the segment logits under the variant's head
-    name, class logits (if any) and any layer named in ``keep``.
-    """
-    seg_name, fc_name, has_class, _ = VARIANTS[variant]
-    if attention_channel is None:
-        attention_channel = {"3ThreeClass": 1, "4BorderClass": 1, "5COCO": 2}.get(variant, 0)
-    L = {}
+def _pspnet_trunk(params, x, L):
+    """conv1_1 .. conv5_3/relu of the half-width dilated ResNet-101 (NCHW in, NCHW out); fills L with the named layers."""
 
     def W(n):
         return params[n + "/weights"]
@@ -330,7 +321,6 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
     def BN(x, n, relu):
         return batch_norm(x, params["%s/%s/gamma" % (n, n)], params["%s/%s/beta" % (n, n)], relu)
 
-    x = data_nhwc.permute(0, 3, 1, 2)
     x = _relu(BN(conv2d(x, W("conv1_1_3x3_s2_n"), 2, "SAME"), "conv1_1_3x3_s2_bn", False))
     x = BN(conv2d(x, W("conv1_2_3x3"), 1, "SAME"), "conv1_2_3x3_bn", True)
     x = BN(conv2d(x, W("conv1_3_3x3"), 1, "SAME"), "conv1_3_3x3_bn", True)
@@ -359,7 +349,28 @@ def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_p
             x = _relu(pre)
             L[p] = pre
             L[p + "/relu"] = x
-    c53 = x
+    return x
+
+
+def pspnet_forward(params, data_nhwc, variant="2AddClass", num_segment=1, last_pool_size=40,
+                   attention_channel=None, keep=()):
+    """Forward pass.  params: {tf name: torch tensor}; data: [B,S,S,4] torch tensor (NHWC).
+
+    Returns dict with NHWC tensors: the segment logits under the variant's head
+    name, class logits (if any) and any layer named in ``keep``.
+    """
+    seg_name, fc_name, has_class, _ = VARIANTS[variant]
+    if attention_channel is None:
+        attention_channel = {"3ThreeClass": 1, "4BorderClass": 1, "5COCO": 2}.get(variant, 0)
+    L = {}
+
+    def W(n):
+        return params[n + "/weights"]
+
+    def BN(x, n, relu):
+        return batch_norm(x, params["%s/%s/gamma" % (n, n)], params["%s/%s/beta" % (n, n)], relu)
+
+    c53 = _pspnet_trunk(params, data_nhwc.permute(0, 3, 1, 2), L)
     P = last_pool_size
     size = c53.shape[2:4]
     branches = {}
@@ -699,6 +710,140 @@ def pspnet_forward_rounded(params, data_nhwc, last_pool_size, policy, seg_name="
     L["conv5_4_bn"] = y
     L["logits"] = conv2d(y, W(seg_name), 1, bias=params[seg_name + "/biases"])      # fp32 head
     return L
+
+
+# --------------------------------------------------------------------------
+# F4: cascaded attention re-decoding (back/8AttentionU/BAISNet.py:485-650, BAISRunnerTrain.py:56-78,161-193):
+# the 2AddClass trunk, then FOUR pyramid decoders.  Decoder k reads the feature gated by the softmax attention channel
+# of decoder k-1 and every gate also feeds a class head; cal_loss scores the SIGMOID outputs (softmax CE on the two
+# 4-channel ones, pos_weight-3 weighted BCE x 2 on channel 1 of the two 2-channel ones) and averages.
+# --------------------------------------------------------------------------
+
+CASCADE_SCOPES = ("", "attention_1/", "attention_2/", "attention_3/")
+
+
+def attention_u_specs(num_classes=21, num_segment=4, filter_number=32, attention_module_num=2):
+    """Ordered {tf variable name: shape}: trunk (2AddClass names), decoders in scopes '', attention_1..3 (the last
+    `attention_module_num` with 2 output channels), class heads in attention_1..3 and at the top level."""
+    base = param_specs("4BorderClass", num_classes, num_segment, filter_number)
+    specs = OrderedDict((k, v) for k, v in base.items()
+                        if not (k.startswith("conv5_3_pool") or k.startswith("conv5_4") or k.startswith("conv6_n_4")
+                                or k.startswith("class_attention")))
+    Fn = filter_number
+    cin, psp = 32 * Fn, 8 * Fn
+
+    def bn(name, c):
+        leaf = name.split("/")[-1]
+        specs["%s/%s/gamma" % (name, leaf)] = (c,)
+        specs["%s/%s/beta" % (name, leaf)] = (c,)
+
+    def decoder(sc, nseg):
+        for lvl in PSP_LEVELS:
+            specs[sc + "conv5_3_pool%d_conv/weights" % lvl] = (1, 1, cin, psp)
+            bn(sc + "conv5_3_pool%d_conv_bn" % lvl, psp)
+        specs[sc + "conv5_4/weights"] = (3, 3, 2 * cin, psp)
+        bn(sc + "conv5_4_bn", psp)
+        specs[sc + "conv6_n_4/weights"] = (1, 1, psp, nseg)
+        specs[sc + "conv6_n_4/biases"] = (nseg,)
+
+    def classifier(sc):
+        specs[sc + "class_attention_conv/weights"] = (5, 5, cin, 16 * Fn)
+        specs[sc + "class_attention_conv/biases"] = (16 * Fn,)
+        specs[sc + "class_attention_fc/weights"] = (16 * Fn, num_classes)
+        specs[sc + "class_attention_fc/biases"] = (num_classes,)
+
+    n = len(CASCADE_SCOPES)
+    for i, sc in enumerate(CASCADE_SCOPES):
+        if i > 0:
+            classifier(sc)             # (inside the scope the classifier comes before the decoder, :593-599)
+        decoder(sc, 2 if i >= n - attention_module_num else num_segment)
+    classifier("")                     # the last gate's class head sits outside any scope (:640-646)
+    return specs
+
+
+def attention_u_forward(params, data_nhwc, last_pool_size=40, num_segment=4, segment_attention=1,
+                        attention_module_num=2):
+    """-> (segments, attentions, classes): sigmoid outputs NHWC, gates N1HW, class logits, in build() order."""
+    c53 = _pspnet_trunk(params, data_nhwc.permute(0, 3, 1, 2), {})
+    P = last_pool_size
+    size = c53.shape[2:4]
+
+    def BN(x, n, relu):
+        leaf = n.split("/")[-1]
+        return batch_norm(x, params["%s/%s/gamma" % (n, leaf)], params["%s/%s/beta" % (n, leaf)], relu)
+
+    def decoder(feat, sc):
+        br = {}
+        for lvl in PSP_LEVELS:
+            n = sc + "conv5_3_pool%d" % lvl
+            y = avg_pool(feat, P // lvl)
+            y = BN(conv2d(y, params[n + "_conv/weights"], 1), n + "_conv_bn", True)
+            br[lvl] = resize_bilinear_ac(y, size)
+        cat = torch.cat([feat, br[6], br[3], br[2], br[1]], dim=1)
+        y = BN(conv2d(cat, params[sc + "conv5_4/weights"], 1, "SAME"), sc + "conv5_4_bn", True)
+        lg = conv2d(y, params[sc + "conv6_n_4/weights"], 1, bias=params[sc + "conv6_n_4/biases"])
+        return torch.sigmoid(lg), torch.softmax(lg, dim=1)
+
+    def classifier(m, sc):
+        m = avg_pool(m, P // 5)
+        m = F.relu(conv2d(m, params[sc + "class_attention_conv/weights"], 5,
+                          bias=params[sc + "class_attention_conv/biases"]))
+        assert m.shape[2] == 1 and m.shape[3] == 1
+        return m[:, :, 0, 0] @ params[sc + "class_attention_fc/weights"] + params[sc + "class_attention_fc/biases"]
+
+    segments, attentions, classes = [], [], []
+    feat = c53
+    n = len(CASCADE_SCOPES)
+    sig, soft = decoder(feat, "")
+    segments.append(sig.permute(0, 2, 3, 1))
+    for i in range(1, n + 1):
+        sel = segment_attention if (i - 1) < n - attention_module_num else 1      # (:586,603 vs :620,637)
+        att = soft[:, sel:sel + 1]
+        attentions.append(att)
+        feat = feat * att
+        sc = CASCADE_SCOPES[i] if i < n else ""
+        classes.append(classifier(feat, sc))
+        if i < n:
+            sig, soft = decoder(feat, sc)
+            segments.append(sig.permute(0, 2, 3, 1))
+    return segments, attentions, classes
+
+
+def attention_u_losses(segments, classes, label_segment, label_attention, label_classes, num_segment=4,
+                       attention_module_num=2, pos_weight=3.0):
+    """cal_loss (back/8AttentionU/BAISRunnerTrain.py:161-193) -> (loss, loss_segment_all, loss_class_all)."""
+    ls = label_segment.reshape(-1).long()
+    la = label_attention.reshape(-1)
+    terms = []
+    for i, sg in enumerate(segments):
+        if i < len(segments) - attention_module_num:
+            terms.append(F.cross_entropy(sg.reshape(-1, num_segment), ls, reduction="mean"))
+        else:
+            x = sg[..., 1].reshape(-1)
+            terms.append(weighted_cross_entropy_with_logits(la.to(x.dtype), x, pos_weight).mean() * 2)
+    lcs = [F.cross_entropy(c, label_classes.long(), reduction="mean") for c in classes]
+    lseg, lcls = sum(terms) / len(terms), sum(lcs) / len(lcs)
+    return lseg + 0.1 * lcls, lseg, lcls
+
+
+def attention_u_train_step(params_np, data_nhwc, label_segment, label_attention, label_classes, last_pool_size=40,
+                           lr=5e-3, dtype=torch.float64, num_segment=4, segment_attention=1, attention_module_num=2):
+    p = to_torch(params_np, dtype, requires_grad=True)
+    segs, atts, cls = attention_u_forward(p, torch.as_tensor(np.asarray(data_nhwc)).to(dtype), last_pool_size,
+                                          num_segment, segment_attention, attention_module_num)
+    loss, lseg, lcls = attention_u_losses(segs, cls, torch.as_tensor(np.asarray(label_segment)),
+                                          torch.as_tensor(np.asarray(label_attention)),
+                                          torch.as_tensor(np.asarray(label_classes)), num_segment, attention_module_num)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    g, new = OrderedDict(), OrderedDict()
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(p[n]) if gr is None else gr
+        g[n] = gr.detach().numpy()
+        new[n] = (p[n].detach() - torch.tensor(lr, dtype=dtype) * gr).numpy()
+    return {"loss": float(loss.detach()), "loss_segment": float(lseg.detach()), "loss_classes": float(lcls.detach()),
+            "segments": [t.detach().numpy() for t in segs], "attentions": [t.detach().numpy() for t in atts],
+            "classes": [t.detach().numpy() for t in cls], "grads": g, "new_params": new}
 
 
 # --------------------------------------------------------------------------

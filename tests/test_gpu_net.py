@@ -526,3 +526,122 @@ def test_inference_runner_top_level_linknet(tmp_path):
         segs = O.linknet_top_forward(O.to_torch(params, torch.float64), torch.from_numpy(im[None]).double())
     ref = np.argmax(segs[0].numpy()[0], -1)
     assert pred.shape == ref.shape and np.mean(pred == ref) >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F4: cascaded attention re-decoding (back/8AttentionU): trunk + four pyramid decoders gated by softmax attention
+# ---------------------------------------------------------------------------------------------------------------
+def _cascade_case(S, B, F, seed=0):
+    rng = np.random.RandomState(seed)
+    from basi_b200.BAISData import SyntheticData
+    images, clicks, lab, cls = SyntheticData(B, (S, S), 8, 21, 4, seed=seed).next_batch()
+    data = np.stack([O.pack_input(images[b], clicks[b]) for b in range(B)]).astype(np.float32)
+    params = O.init_params(O.attention_u_specs(21, 4, F, 2), seed + 1, trained_like=True)
+    att = (lab == 1).astype(np.float32)
+    return params, data, lab.astype(np.int32), att, cls
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16"])
+def test_cascade_train_step_matches_oracle(precision):
+    """Whole cascade (2AddClass trunk, 4 decoders, 4 class heads, cal_loss on the sigmoid outputs) forward / loss /
+    backward / SGD against the float64 oracle (oracle.attention_u_train_step)."""
+    from basi_b200.BAISNet import BAISNet, Placeholder
+    from basi_b200.engine import Engine
+    S, B, F = 80, 2, 8
+    params, data, lab, att, cls = _cascade_case(S, B, F)
+    net = BAISNet(Placeholder((None, S, S, 4)), is_training=True, num_classes=21, num_segment=4, segment_attention=1,
+                  last_pool_size=S // 8, filter_number=F, attention_module_num=2)
+    segs, atts, clss = net.build()
+    assert len(segs) == 4 and len(atts) == 4 and len(clss) == 4
+    eng = Engine(net, B, precision, True, dict(kind="cascade", pos_weight=3.0, class_weight=0.1))
+    eng.set_params(params)
+    lr = 5e-3
+    eng.feed(data, lab, cls, lr, label_att=att)
+    eng.step_device()
+    torch.cuda.synchronize()
+    ref = O.attention_u_train_step(params, data, lab, att, cls, S // 8, lr, torch.float64)
+    loss, lseg, lcls = eng.losses()
+    got_segs = [a.t.float().cpu().numpy() for a in eng.segments]
+    got_cls = [a.t.float().cpu().numpy().reshape(B, -1) for a in eng.classes_logits]
+    g = eng.get_grads()
+    if precision == "f32":
+        r32 = O.attention_u_train_step(params, data, lab, att, cls, S // 8, lr, torch.float32)
+        assert abs(lseg - ref["loss_segment"]) < F32_TOL * max(1, abs(ref["loss_segment"])), (lseg, ref["loss_segment"])
+        assert abs(lcls - ref["loss_classes"]) < F32_TOL * max(1, abs(ref["loss_classes"])), (lcls, ref["loss_classes"])
+        assert abs(loss - ref["loss"]) < F32_TOL * max(1, abs(ref["loss"]))
+        for i in range(4):
+            assert _rel(got_segs[i], ref["segments"][i]) < F32_TOL + 3 * _rel(r32["segments"][i], ref["segments"][i]), i
+            assert _rel(got_cls[i], ref["classes"][i]) < F32_TOL + 3 * _rel(r32["classes"][i], ref["classes"][i]), i
+        bad = []
+        for n in g:
+            e, floor = _rel2(g[n], ref["grads"][n]), _rel2(r32["grads"][n], ref["grads"][n])
+            if e > F32_TOL + 10 * floor:
+                bad.append((n, e, floor))
+        assert not bad, bad[:5]
+        new = eng.get_params()
+        worst = max((_rel(new[n], ref["new_params"][n]) - 10 * _rel(r32["new_params"][n], ref["new_params"][n]), n)
+                    for n in new)
+        assert worst[0] < F32_TOL, worst
+        pred = np.argmax(got_segs[0], -1)
+        assert np.array_equal(eng.pred_seg.cpu().numpy()[..., 0], pred.astype(np.int32))
+    else:
+        assert abs(loss - ref["loss"]) < 2e-2 * max(1, abs(ref["loss"])), (loss, ref["loss"])
+        for i in range(4):
+            assert _rel2(got_segs[i], ref["segments"][i]) < 2e-2, (i, _rel2(got_segs[i], ref["segments"][i]))
+        # (a toy net with batch-stat BN over 2 x 1 x 1 pyramid cells is chaotic in 16 bits -- like the other toy-net
+        # 16-bit tests this one checks forward, loss and finiteness; the gradient check is the benchmark-shape test)
+        assert all(np.isfinite(v).all() for v in g.values())
+
+
+def test_cascade_f16_vs_oracle_at_benchmark_shape():
+    """The cascade on the tcgen05 path (precision f16) at S=320, F=32 against the float64 oracle, trained-like
+    weights, B=2: sigmoid outputs of all four decoders, class logits, loss and the whole gradient."""
+    from basi_b200.BAISNet import BAISNet, Placeholder
+    from basi_b200.engine import Engine
+    S, B, F = 320, 2, 32
+    params, data, lab, att, cls = _cascade_case(S, B, F, seed=2)
+    net = BAISNet(Placeholder((None, S, S, 4)), is_training=True, num_classes=21, num_segment=4, segment_attention=1,
+                  last_pool_size=S // 8, filter_number=F, attention_module_num=2)
+    eng = Engine(net, B, "f16", True, dict(kind="cascade", pos_weight=3.0, class_weight=0.1))
+    assert eng.tc_layers > 150, eng.tc_layers
+    eng.set_params(params)
+    eng.feed(data, lab, cls, 5e-3, label_att=att)
+    eng.step_device()
+    torch.cuda.synchronize()
+    ref = O.attention_u_train_step(params, data, lab, att, cls, S // 8, 5e-3, torch.float64)
+    loss, lseg, lcls = eng.losses()
+    errs = [_rel2(a.t.float().cpu().numpy(), ref["segments"][i]) for i, a in enumerate(eng.segments)]
+    cerr = [_rel2(a.t.float().cpu().numpy().reshape(B, -1), ref["classes"][i]) for i, a in enumerate(eng.classes_logits)]
+    g = eng.get_grads()
+    ga = np.concatenate([g[n].reshape(-1) for n in g]).astype(np.float64)
+    gb = np.concatenate([ref["grads"][n].reshape(-1) for n in g]).astype(np.float64)
+    cos = float(ga @ gb / (np.linalg.norm(ga) * np.linalg.norm(gb)))
+    print("cascade f16 at S=320 F=32 B=2: segments rel-l2 %s, class logits rel-l2 %s, loss %.6f vs %.6f, grad cosine %.4f"
+          % (["%.2e" % e for e in errs], ["%.2e" % e for e in cerr], loss, ref["loss"], cos))
+    assert abs(loss - ref["loss"]) < BF16_TOL * max(1, abs(ref["loss"])), (loss, ref["loss"])
+    # segments[0] is final_segment_logit (predictions); every later decoder reads features gated by the previous
+    # decoder's softmax, so the 16-bit error compounds down the cascade (measured 3.8e-3, 8.5e-3, 2.6e-2, 1.8e-2)
+    assert max(errs[:2]) < BF16_TOL and max(errs[2:]) < 2 * BF16_TOL, errs
+    assert max(cerr) < BF16_TOL, cerr
+    assert np.all(np.isfinite(ga)) and cos > 0.9, cos          # measured 0.962
+
+
+def test_cascade_train_runner_steps_at_bench_shape():
+    """Train(variant='8AttentionU') at 320^2 / F=32 (tcgen05 path, CUDA graph): finite losses that fall over a few
+    steps on a fixed batch, reference-shaped fetches."""
+    from basi_b200.BAISRunnerTrain import Train
+    import tempfile
+    tr = Train(batch_size=4, last_pool_size=40, input_size=[320, 320], log_dir=tempfile.mkdtemp(), variant="8AttentionU",
+               precision="f16", learning_rate=1e-2)
+    assert tr.engine.tc_layers > 100
+    batch = tr.data_reader.next_batch()
+    first = last = None
+    for step in range(6):
+        r = tr.run_step(step, batch)
+        assert np.isfinite(r["loss"]), r
+        first = r["loss"] if first is None else first
+        last = r["loss"]
+    assert last < first, (first, last)
+    assert r["raw_output_segment"].shape == (4, 40, 40, 4) and r["pred_segment"].shape == (4, 40, 40, 1)
+    assert r["raw_output_classes"].shape == (4, 21)
+    assert 0.0 <= r["raw_output_segment"].min() and r["raw_output_segment"].max() <= 1.0     # sigmoid outputs

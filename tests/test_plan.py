@@ -228,3 +228,45 @@ def test_data_reader_shards_annotations_by_rank():
         d._reshuffle()
     a, b = readers[0]._random_index, readers[1]._random_index
     assert sorted(a + b) == list(range(10)) and not set(a) & set(b)     # same permutation, disjoint slices
+
+
+def test_cascade_plan_and_inventory():
+    """F4 (back/8AttentionU): four decoders in the scopes '', attention_1..3, four class heads, variables named like
+    the reference's; the plan has one fused pyramid-pool pass per decoder and the cal_loss kernels."""
+    from basi_b200.BAISNet import BAISNet
+    S, F = 320, 32
+    net = BAISNet(Placeholder((None, S, S, 4)), is_training=True, num_classes=21, num_segment=4, segment_attention=1,
+                  last_pool_size=S // 8, filter_number=F, attention_module_num=2)
+    segs, atts, clss = net.build()
+    assert [s.shape for s in segs] == [(40, 40, 4), (40, 40, 4), (40, 40, 2), (40, 40, 2)]
+    assert [a.shape for a in atts] == [(40, 40, 1)] * 4 and [c.shape for c in clss] == [(21,)] * 4
+    spec = O.attention_u_specs(21, 4, F, 2)
+    assert list(net.variables.keys()) == list(spec.keys())
+    assert dict(net.variables) == {k: tuple(v) for k, v in spec.items()}
+    assert "attention_2/conv5_4_bn/conv5_4_bn/gamma" in net.variables and "class_attention_fc/weights" in net.variables
+    e = Engine(net, 2, "bf16", True, dict(kind="cascade"), dry_run=True)
+    fwd = Counter(c[0] for c in e.fwd)
+    assert fwd["basi_avgpool_multi_fwd"] == 4 and fwd["basi_sigmoid_fwd"] == 4 and fwd["basi_softmax_gate_fwd"] == 4
+    loss = Counter(c[0] for c in e.lossl)
+    assert loss == {"basi_softmax_ce_fwd_bwd": 6, "basi_wbce_sel_fwd_bwd": 2}
+    bwd = Counter(c[0] for c in e.bwd)
+    assert bwd["basi_sigmoid_bwd"] == 4 and bwd["basi_softmax_gate_bwd"] == 4 and bwd["basi_mask_mul_bwd"] == 4
+
+
+def test_cascade_oracle_known_answers():
+    """cal_loss of the cascade on hand-checkable inputs: uniform sigmoid outputs 0.5 give CE = log(4) for the
+    4-channel maps and 2 * mean(wbce(0.5)) for the 2-channel ones; loss = mean + 0.1 * mean class CE."""
+    import torch
+    B, P = 1, 2
+    segs = [torch.full((B, P, P, 4), 0.5, dtype=torch.float64)] * 2 + [torch.full((B, P, P, 2), 0.5, dtype=torch.float64)] * 2
+    cls = [torch.zeros((B, 21), dtype=torch.float64)] * 4
+    ls = torch.zeros((B, P, P, 1), dtype=torch.int64)
+    la = torch.tensor([1.0, 0.0, 0.0, 1.0], dtype=torch.float64).reshape(B, P, P, 1)
+    loss, lseg, lcls = O.attention_u_losses(segs, cls, ls, la, torch.zeros((B,), dtype=torch.int64))
+    sp = np.log1p(np.exp(-0.5))                    # softplus(-0.5)
+    w1 = 3 * sp                                    # z = 1: 0 * x + 3 * softplus(-x)
+    w0 = 0.5 + sp                                  # z = 0: x + softplus(-x)
+    expect_seg = (2 * np.log(4.0) + 2 * 2 * (w1 + w0) / 2) / 4
+    assert abs(float(lseg) - expect_seg) < 1e-12
+    assert abs(float(lcls) - np.log(21.0)) < 1e-12
+    assert abs(float(loss) - (expect_seg + 0.1 * np.log(21.0))) < 1e-12
