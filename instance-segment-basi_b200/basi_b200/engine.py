@@ -144,6 +144,15 @@ class Engine(object):
         self._ops = []
         self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run and not _exp_env("BASI_NO_OVERLAP")
         self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
+        # weight-gradient scheduling: `wgrad_streams` side streams used round-robin (independent weight gradients can
+        # then overlap each other's tails), and `defer_wgrad` moves every tensor-core weight gradient behind the
+        # dgrad / batch-norm chain (they no longer compete with the chain for SMs; their operands stay alive)
+        ws = _exp_env("BASI_WGRAD_STREAMS")
+        self.wgrad_streams = max(1, int(ws)) if ws else 1
+        self.defer_wgrad = bool(_exp_env("BASI_DEFER_WGRAD")) and self.overlap_wgrad
+        self._sides = ([self._side] + [torch.cuda.Stream(self.device) for _ in range(self.wgrad_streams - 1)]
+                       if self.overlap_wgrad else [])
+        self._side_rr = 0
         # independent sub-graphs (the four PSP branches) can run on their own streams, forked/joined with events.
         # Measured inside the step graph: 10.27 ms with the branch streams vs 10.08 ms without (the extra cross-stream
         # dependencies cost more than the ~0.3 ms of tiny kernels they overlap), so this is opt-in.
@@ -964,6 +973,8 @@ class Engine(object):
         self._cur_branch = None
         self.bwd.extend(self._deferred_bwd)
         self._deferred_bwd = []
+        if self.defer_wgrad:
+            self.bwd = [c for c in self.bwd if not c[3].get("side")] + [c for c in self.bwd if c[3].get("side")]
 
     def _bwd_add(self, op):
         a, b, y = op["a"], op["b"], op["y"]
@@ -1346,6 +1357,8 @@ class Engine(object):
                     forked[b] = True
                 rc = fn(*args, branches[b].cuda_stream)
             elif side is not None and meta.get("side"):
+                side = self._sides[self._side_rr % len(self._sides)]
+                self._side_rr += 1
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 side.wait_event(ev)
@@ -1368,7 +1381,8 @@ class Engine(object):
     def join_side(self, waiter=None):
         """Makes `waiter` (default: the current stream) wait for the side-stream work issued so far."""
         if self._side is not None and self._side_dirty:
-            (waiter or torch.cuda.current_stream(self.device)).wait_stream(self._side)
+            for sd in self._sides:
+                (waiter or torch.cuda.current_stream(self.device)).wait_stream(sd)
 
     def _stream(self):
         if self.dry_run:
