@@ -6,7 +6,10 @@ reference computes on its hot path.  It is the *checker*: only ``tests/``,
 reference`` legs may import it.  Nothing under ``instance-segment-basi_b200/``
 (the product) imports it.
 
-PARITY UNPINNED.  The reference's arithmetic lives in TensorFlow 1.x, which is
+PARITY: the DATA functions (``mask_gaussian``, ``pack_input``, ``encode_labels_binary`` / ``_three`` / ``_border``,
+``sample_click``) are PINNED bit for bit against outputs of the reference's own BAISData.py code, which is numpy + PIL
+and runs in the build container (tests/golden/make_reference_golden.py -> tests/golden/reference_data.npz ->
+tests/test_reference_golden.py).  The NETWORK ARITHMETIC is UNPINNED: it lives in TensorFlow 1.x, which is
 third-party, un-vendored and un-pinned (no requirements file; TF1 is implied by
 ``tf.contrib.slim`` / ``tf.placeholder``), it cannot be imported in this
 container, and the reference ships no test, golden vector or fixture for this
