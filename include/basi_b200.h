@@ -202,12 +202,13 @@ int basi_maxpool3s2_bwd(const basi_tensor* dy, const uint8_t* argmax, const basi
 int basi_avgpool_fwd(const basi_tensor* x, int k, const basi_tensor* y, void* stream);
 int basi_avgpool_bwd(const basi_tensor* dy, int k, const basi_tensor* dx, int accumulate, void* stream);
 
-/* All pyramid pools of one tensor in ONE pass (BAISPSPNet.py:683-710: windows 40/20/13/6 of conv5_3 at 320^2): ks[p]
- * is the window (= stride) of pool p, ys[p] its output ([n, h/k, w/k, c]).  `scratch` holds
- * basi_avgpool_multi_scratch_floats() zero-initialised floats; the call leaves it zeroed again.  The adjoint adds
- * (accumulate != 0) or writes every pool's contribution to dx in one read-modify-write pass.  At most 4 pools and
- * 96 output cells in total; basi_avgpool_multi_scratch_floats returns -1 for a group the pass cannot take (the caller
- * then uses basi_avgpool_fwd / _bwd per pool). */
+/* All pyramid pools of one tensor together (BAISPSPNet.py:683-710: windows 40/20/13/6 of conv5_3 at 320^2): ks[p]
+ * is the window (= stride) of pool p, ys[p] its output ([n, h/k, w/k, c]).  Forward: one pass over x writes the
+ * per-row window sums of every pool to `scratch` (basi_avgpool_multi_scratch_floats() floats, no initialisation
+ * needed), a second small pass adds the rows of each cell in a fixed order -- no atomics, bit-reproducible.  The
+ * adjoint adds (accumulate != 0) or writes every pool's contribution to dx in one read-modify-write pass.  At most
+ * 4 pools; basi_avgpool_multi_scratch_floats returns -1 for a group it cannot take (the caller then uses
+ * basi_avgpool_fwd / _bwd per pool). */
 int64_t basi_avgpool_multi_scratch_floats(const basi_tensor* x, int n_pools, const int* ks);
 int basi_avgpool_multi_fwd(const basi_tensor* x, int n_pools, const int* ks, const basi_tensor* const* ys,
                            float* scratch, void* stream);
@@ -252,6 +253,13 @@ int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int ac
 int basi_skinny_supported(int M, int K, int N);
 int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,
                     int M, int K, int N, int relu, void* stream);
+/* The same with a caller-provided workspace of basi_skinny_fwd_workspace_floats(M, K, N) floats: the k-split partial
+ * sums are written there and added in a fixed order, so the result is bit-reproducible (basi_skinny_fwd adds them
+ * with fp32 atomics, whose order -- and therefore last-bit rounding -- varies from run to run).  workspace == NULL
+ * is basi_skinny_fwd. */
+int64_t basi_skinny_fwd_workspace_floats(int M, int K, int N);
+int basi_skinny_fwd_ws(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,
+                       int M, int K, int N, int relu, float* workspace, void* stream);
 /* da[m][k] (+)= sum_n dy[m][n] w[k][n]   (da dtype_a) */
 int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, int64_t lda, int M, int K, int N,
                       int accumulate, void* stream);

@@ -95,6 +95,7 @@ SIGNATURES = {
     "basi_resize_nearest_bwd": [_TP, _TP, _i, _P],
     "basi_skinny_supported": [_i, _i, _i],
     "basi_skinny_fwd": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _i, _P],
+    "basi_skinny_fwd_ws": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _i, _P, _P],
     "basi_skinny_dgrad": [_P, _P, _P, _i, _i64, _i, _i, _i, _i, _P],
     "basi_skinny_wgrad": [_P, _i, _i64, _P, _P, _P, _i, _i, _i, _P],
     "basi_relu_bwd_f32": [_P, _P, _i64, _P],
@@ -124,7 +125,8 @@ _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi
             "basi_half_format": ([], _i),
             "basi_tc_conv_destroy": ([_P], None), "basi_tc_conv_set_bn_apply": ([_P, _TP, _i], _i),
             "basi_tc_conv_set_bn_bwd": ([_P, _TP, _P, _i, _P, _d, _P, _P, _P], _i), "basi_tc_split_kcols": ([_i, _i], _i),
-            "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64)}
+            "basi_avgpool_multi_scratch_floats": ([_TP, _i, _P], C.c_int64),
+            "basi_skinny_fwd_workspace_floats": ([_i, _i, _i], C.c_int64)}
 
 _libs = {}
 _current = "bf16"

@@ -144,11 +144,11 @@ class Engine(object):
         self._ops = []
         self.overlap_wgrad = bool(overlap_wgrad) and not self.dry_run and not _exp_env("BASI_NO_OVERLAP")
         self._side = torch.cuda.Stream(self.device) if self.overlap_wgrad else None
-        # weight-gradient scheduling: `wgrad_streams` side streams used round-robin (independent weight gradients can
-        # then overlap each other's tails), and `defer_wgrad` moves every tensor-core weight gradient behind the
-        # dgrad / batch-norm chain (they no longer compete with the chain for SMs; their operands stay alive)
+        # weight-gradient scheduling: `wgrad_streams` side streams used round-robin -- the tensor-core weight-gradient
+        # plans launch ~64 CTAs each, so two of them share the GPU (cfg3: 9.13 -> 8.81 ms/step).  `defer_wgrad`
+        # (experiment, slower) moves every tensor-core weight gradient behind the dgrad / batch-norm chain
         ws = _exp_env("BASI_WGRAD_STREAMS")
-        self.wgrad_streams = max(1, int(ws)) if ws else 1
+        self.wgrad_streams = max(1, int(ws)) if ws else 2
         self.defer_wgrad = bool(_exp_env("BASI_DEFER_WGRAD")) and self.overlap_wgrad
         self._sides = ([self._side] + [torch.cuda.Stream(self.device) for _ in range(self.wgrad_streams - 1)]
                        if self.overlap_wgrad else [])
@@ -581,9 +581,9 @@ class Engine(object):
 
     def _emit_pool_group_fwd(self, grp):
         x = grp["x"]
-        cells = sum(o["y"].shape[1] * o["y"].shape[2] for o in grp["ops"])
-        grp["scratch"] = self._zeros(self.B * cells * x.shape[3], torch.float32)
         n, ks, ptrs = self._pool_group_args(grp, False)
+        nfl = int(_lib.load().basi_avgpool_multi_scratch_floats(x.ref, n, ks))    # per-row window sums [n][h][cells][c]
+        grp["scratch"] = self._zeros(nfl, torch.float32)
         br, self._cur_branch = self._cur_branch, None          # the shared pass runs before the branches fork
         self._call(self.fwd, "basi_avgpool_multi_fwd", x.ref, n, ks, ptrs, grp["scratch"].data_ptr(),
                    bytes=self._nbytes(x))
@@ -759,9 +759,13 @@ class Engine(object):
         x, y = op["x"], op["y"]
         lda = x.t.stride(0) if x.shape[0] > 1 else op["K"]
         op["lda"] = lda
-        self._call(self.fwd, "basi_skinny_fwd", x.t.data_ptr(), x.dtype, C.c_int64(lda), self._pptr(op["w"]),
+        # the workspace variant adds the k-split partial sums in a fixed order: with the atomic variant the class logits
+        # differ by 1e-7 from run to run, which the 16-bit backward amplifies to 1.5e-2 on the weight gradients
+        nws = int(_lib.load().basi_skinny_fwd_workspace_floats(self.B, op["K"], op["N"]))
+        op["ws"] = self._zeros((max(nws, 1),), torch.float32)
+        self._call(self.fwd, "basi_skinny_fwd_ws", x.t.data_ptr(), x.dtype, C.c_int64(lda), self._pptr(op["w"]),
                    self._pptr(op["b"]) if op["b"] else None, y.t.data_ptr(), self.B, op["K"], op["N"],
-                   1 if op["relu"] else 0)
+                   1 if op["relu"] else 0, op["ws"].data_ptr())
 
     # ---- loss
     def _pick_loss_scale(self, n_logits):

@@ -433,7 +433,8 @@ constexpr int SK_KT = 64;  // k-slab per block (fwd / wgrad)
 template <typename TA>
 __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ a, int64_t lda,
                                                          const float* __restrict__ w, float* __restrict__ y, int M,
-                                                         int K, int N, int slabs_per_block) {
+                                                         int K, int N, int slabs_per_block,
+                                                         float* __restrict__ part) {
   // block = (128 output columns, a run of k-slabs); the partial sums of the run stay in registers and are added to y
   // once (with one slab per block the 52 MB class_attention_conv GEMV was bound by its 3.3 M atomics, not by HBM)
   pdl_prologue();
@@ -463,11 +464,27 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
       }
     }
     if (n < N) {
+      // part != nullptr: this block's partial sums go to their own slice [blockIdx.y][M][N] and are added up in a fixed
+      // order by skinny_reduce_bias_act_kernel (deterministic); else fp32 atomics into y (order-dependent rounding)
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (mb + i < M) atomicAdd(y + (int64_t)(mb + i) * N + n, acc[i]);
+        if (mb + i < M) {
+          if (part) part[((int64_t)blockIdx.y * M + mb + i) * N + n] = acc[i];
+          else atomicAdd(y + (int64_t)(mb + i) * N + n, acc[i]);
+        }
     }
   }
+}
+
+__global__ void skinny_reduce_bias_act_kernel(const float* __restrict__ part, int parts, float* __restrict__ y,
+                                              const float* __restrict__ bias, int M, int N, int relu) {
+  pdl_prologue();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float v = 0.f;
+  for (int p = 0; p < parts; ++p) v += part[(int64_t)p * M * N + i];
+  v += bias ? bias[i % N] : 0.f;
+  y[i] = relu ? fmaxf(v, 0.f) : v;
 }
 
 __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int M, int N, int relu) {
@@ -1148,29 +1165,55 @@ int basi_skinny_supported(int M, int K, int N) {
   return (M > 0 && K > 0 && N > 0 && skinny_rows_per_chunk(N) >= 1) ? 1 : 0;
 }
 
-int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y, int M, int K,
-                    int N, int relu, void* stream) {
+// k-slab partition of the forward GEMV: about 4 blocks per SM in total; every block walks `spb` consecutive k-slabs
+static void skinny_fwd_geometry(int K, int N, int* gx, int* gy, int* spb) {
+  const int nslabs = (K + SK_KT - 1) / SK_KT;
+  *gx = (N + 127) / 128;
+  int y = (4 * basi::sm_count() + *gx - 1) / *gx;
+  if (y > nslabs) y = nslabs;
+  *spb = (nslabs + y - 1) / y;
+  *gy = (nslabs + *spb - 1) / *spb;
+}
+
+int64_t basi_skinny_fwd_workspace_floats(int M, int K, int N) {
+  if (!basi_skinny_supported(M, K, N)) return -1;
+  int gx, gy, spb;
+  skinny_fwd_geometry(K, N, &gx, &gy, &spb);
+  return (int64_t)gy * M * N;
+}
+
+int basi_skinny_fwd_ws(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y, int M,
+                       int K, int N, int relu, float* workspace, void* stream) {
   BASI_CHECK_ARG(a && w && y && basi_skinny_supported(M, K, N), "skinny_fwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
-  const int nslabs = (K + SK_KT - 1) / SK_KT, gx = (N + 127) / 128;
-  // about 4 blocks per SM in total; every block walks `spb` consecutive k-slabs
-  int gy = (4 * basi::sm_count() + gx - 1) / gx;
-  if (gy > nslabs) gy = nslabs;
-  const int spb = (nslabs + gy - 1) / gy;
-  dim3 grid(gx, (nslabs + spb - 1) / spb);
+  int gx, gy, spb;
+  skinny_fwd_geometry(K, N, &gx, &gy, &spb);
+  if (!workspace) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
+  dim3 grid(gx, gy);
   const size_t es = dtype_a == BASI_F32 ? 4 : 2;
   for (int m0 = 0; m0 < M; m0 += 64) {
     const int mc = M - m0 < 64 ? M - m0 : 64;
     const char* ap = (const char*)a + (size_t)m0 * lda * es;
     float* yp = y + (size_t)m0 * N;
-    if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb);
-    else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)ap, lda, w, yp, mc, K, N, spb);
+    // every row chunk owns a [gy][mc][N] block of the workspace (the blocks add up to gy * M * N floats)
+    float* pp = workspace ? workspace + (size_t)gy * m0 * N : nullptr;
+    if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb, pp);
+    else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)ap, lda, w, yp, mc, K, N, spb, pp);
+    if (workspace) {
+      basi::launch(skinny_reduce_bias_act_kernel, (mc * N + 255) / 256, 256, 0, st, (const float*)pp, gy, yp, bias, mc, N, relu);
+    }
   }
   BASI_CHECK_LAUNCH("skinny_fwd");
-  basi::launch(bias_act_kernel, (M * N + 255) / 256, 256, 0, st, y, bias, M, N, relu);
-  BASI_CHECK_LAUNCH("skinny_fwd(bias)");
+  if (!workspace) {
+    basi::launch(bias_act_kernel, (M * N + 255) / 256, 256, 0, st, y, bias, M, N, relu);
+    BASI_CHECK_LAUNCH("skinny_fwd(bias)");
+  }
   return BASI_OK;
+}
+
+int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y, int M, int K,
+                    int N, int relu, void* stream) {
+  return basi_skinny_fwd_ws(a, dtype_a, lda, w, bias, y, M, K, N, relu, nullptr, stream);
 }
 
 int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, int64_t lda, int M, int K, int N,

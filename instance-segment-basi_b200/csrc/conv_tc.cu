@@ -1906,17 +1906,28 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     wp.Cin = cin; wp.Cout = cout;
     wp.nterms = split == 0 ? 1 : ((pa == 3 && pb == 3) ? 6 : 3);
     const int out_tiles = wp.taps * wp.ci_tiles * wp.co_tiles;
-    // split-K over pixel tiles.  Every split adds |dW| fp32 atomics, so tiny gradients (conv4 1x1: 65 K elements)
-    // want a single wave of CTAs (measured 22.6 -> 16.7 us); long pixel loops want two waves for balance.
-    const char* env_w = exp_env("BASI_TC_WGRAD_WAVES");
-    int waves = 1;
-    {
+    // split-K over pixel tiles.  Every split adds |dW| fp32 atomics and every CTA pays its prologue / pipeline fill /
+    // epilogue, so the 16-bit plans aim at ~64 CTAs per launch: weight gradients of neighbouring layers run on two
+    // side streams and share the GPU (measured on cfg3: 9.13 -> 8.81 ms/step against one full wave per launch;
+    // 48 / 74 / 96 CTAs: 8.95 / 8.88 / 8.81, tools/wgrad_sched.py).  The split-operand (float32-grade) plans keep
+    // the round-1 rule: a single wave for tiny gradients, two waves for long pixel loops (the new rule is neutral there).
+    int splits;
+    if (exp_env("BASI_TC_WGRAD_SPLITS")) {
+      splits = atoi(exp_env("BASI_TC_WGRAD_SPLITS"));                                      // experiment
+    } else if (split == 0 && !exp_env("BASI_TC_WGRAD_WAVES")) {
+      const int target = exp_env("BASI_TC_WGRAD_TARGET") ? atoi(exp_env("BASI_TC_WGRAD_TARGET")) : 64;
+      splits = (target + out_tiles - 1) / out_tiles;
+      if (exp_env("BASI_TC_WGRAD_MAXTILES")) {  // experiment: no CTA loops over more than this many pixel tiles
+        const int mx = atoi(exp_env("BASI_TC_WGRAD_MAXTILES"));
+        if (mx > 0 && (m_tiles + mx - 1) / mx > splits) splits = (m_tiles + mx - 1) / mx;
+      }
+    } else {
+      int waves = 1;
       const int s1 = (sms + out_tiles - 1) / out_tiles;
       if (m_tiles / (s1 > 0 ? s1 : 1) > 10) waves = 2;
+      if (exp_env("BASI_TC_WGRAD_WAVES")) waves = atoi(exp_env("BASI_TC_WGRAD_WAVES"));
+      splits = (waves * sms + out_tiles - 1) / out_tiles;
     }
-    if (env_w) waves = atoi(env_w);
-    int splits = (waves * sms + out_tiles - 1) / out_tiles;
-    if (exp_env("BASI_TC_WGRAD_SPLITS")) splits = atoi(exp_env("BASI_TC_WGRAD_SPLITS"));   // experiment
     if (splits > m_tiles) splits = m_tiles;
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (m_tiles + splits - 1) / splits;

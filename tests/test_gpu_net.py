@@ -645,3 +645,31 @@ def test_cascade_train_runner_steps_at_bench_shape():
     assert r["raw_output_segment"].shape == (4, 40, 40, 4) and r["pred_segment"].shape == (4, 40, 40, 1)
     assert r["raw_output_classes"].shape == (4, 21)
     assert 0.0 <= r["raw_output_segment"].min() and r["raw_output_segment"].max() <= 1.0     # sigmoid outputs
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+def test_two_engine_instances_agree(prec):
+    """Two separately built engines (different buffers, plans, streams) on the same trained-like parameters and batch
+    at S=320 / F=32: same loss and logits, gradients equal up to the order of the floating-point atomics (fused
+    pyramid pooling, split-K weight gradients, class-head GEMMs).  Guards against reads of uninitialised memory and
+    against address-dependent behaviour; with the RANDOM-INIT weights bench.py uses the network is chaotic and the
+    same comparison gives 4e-3 .. 3e-2 (tools/wgrad_sched.py prints it)."""
+    variant, nseg, S, F, B, classes = "2AddClass", 1, 320, 32, 4, 21
+    params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
+    outs = []
+    keep = []
+    for i in range(2):
+        eng = _engine(variant, nseg, S, F, B, classes, prec, dict(kind="bce", pos_weight=3.0, class_weight=0.2))
+        keep.append(torch.empty(64 << 20, dtype=torch.uint8, device="cuda:0").fill_(0xFF))   # shift later allocations
+        eng.set_params(params)
+        eng.feed(data, lab, cls, 5e-3)
+        eng.step_device()
+        torch.cuda.synchronize()
+        outs.append((eng.losses()[0], eng.seg_logits.t.float().cpu().numpy().copy(), eng.grads_flat.double().cpu().numpy()))
+    (l0, s0, g0), (l1, s1, g1) = outs
+    rel_logits = _rel2(s1, s0)
+    rel_grads = float(np.linalg.norm(g1 - g0) / np.linalg.norm(g0))
+    print("two %s engine instances: loss %.9f vs %.9f, logits rel-l2 %.2e, gradient rel-l2 %.2e"
+          % (prec, l0, l1, rel_logits, rel_grads))
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    assert rel_logits < 1e-6 and rel_grads < 1e-5, (rel_logits, rel_grads)

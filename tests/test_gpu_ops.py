@@ -431,6 +431,19 @@ def test_skinny_gemms(dtype, M, K, N, relu):
     call("basi_skinny_fwd", ad.data_ptr(), code, C.c_int64(K), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), M, K, N,
          1 if relu else 0)
     assert rel_err(host(yd), y.detach().numpy()) < 2e-5
+    # workspace variant: same result, and bit-identical from call to call (fixed summation order)
+    from basi_b200 import _lib
+    nws = int(_lib.load().basi_skinny_fwd_workspace_floats(M, K, N))
+    assert nws >= M * N
+    ws = torch.full((nws,), 7.0, device="cuda:0")
+    runs = []
+    for _ in range(3):
+        yw = torch.full((M, N), -3.0, device="cuda:0")
+        call("basi_skinny_fwd_ws", ad.data_ptr(), code, C.c_int64(K), wd.data_ptr(), bd.data_ptr(), yw.data_ptr(), M, K,
+             N, 1 if relu else 0, ws.data_ptr())
+        runs.append(host(yw))
+    assert rel_err(runs[0], y.detach().numpy()) < 2e-5
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
     dyd = dev(dy)
     if relu:
         call("basi_relu_bwd_f32", dyd.data_ptr(), yd.data_ptr(), C.c_int64(M * N))
@@ -762,15 +775,19 @@ def test_avgpool_multi_forward_backward(dtype, B, H, Cc, ks):
     karr = (C.c_int * len(ks))(*ks)
     yptr = (C.POINTER(Tensor) * len(ks))(*[C.pointer(y.desc) for y in ys])
     nfl = _lib.load().basi_avgpool_multi_scratch_floats(xa.ref, len(ks), karr)
-    assert nfl == B * sum((H // k) ** 2 for k in ks) * Cc
-    scratch = torch.zeros(nfl, dtype=torch.float32, device="cuda:0")
+    assert nfl == B * H * sum(H // k for k in ks) * Cc         # per-row window sums [n][h][row cells][c]
+    scratch = torch.full((nfl,), 5.0, dtype=torch.float32, device="cuda:0")   # (needs no initialisation)
     tol = 1e-5 if dtype == "f32" else 1e-2
-    for _ in range(2):                                      # twice: the scratch must come back zeroed
+    first = None
+    for _ in range(3):                                      # no atomics: bit-identical from call to call
         call("basi_avgpool_multi_fwd", xa.ref, len(ks), karr, yptr, scratch.data_ptr())
         for k, y in zip(ks, ys):
             want = nhwc(O.avg_pool(nchw(x).double(), k))
             assert rel_err(host(y), want) < tol
-    assert float(scratch.abs().max()) == 0.0
+        got = [host(y).copy() for y in ys]
+        if first is None:
+            first = got
+        assert all(np.array_equal(a, b) for a, b in zip(first, got))
     # adjoint: every pool adds its share to dx in one pass
     dys = [_u(rng, B, H // k, H // k, Cc) for k in ks]
     if dtype == "bf16":

@@ -49,7 +49,7 @@ def test_lowered_plan_structure():
     e = Engine(build(), 2, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
     f, b = Counter(n for n, _, _, _ in e.fwd), Counter(n for n, _, _, _ in e.bwd)
     assert e.n_params == 29571606
-    assert f["basi_conv_fprop"] == 112 and f["basi_skinny_fwd"] == 2
+    assert f["basi_conv_fprop"] == 112 and f["basi_skinny_fwd_ws"] == 2
     assert f["basi_bn_stats"] == 111 and f["basi_bn_apply"] == 107          # 4 proj BNs folded into junctions
     assert f["basi_bn_finalize"] == 0 and b["basi_bn_bwd_finalize"] == 0    # finalize fused into the reductions
     assert b["basi_conv_wgrad"] == 112 and b["basi_conv_dgrad"] == 111      # conv1_1 needs no dgrad
@@ -139,7 +139,7 @@ def test_class_head_lowers_to_skinny_gemms_at_any_batch(B):
     assert lib.basi_skinny_supported(B, 25 * 1024, 512) == 1 and lib.basi_skinny_supported(B, 512, 21) == 1
     e = Engine(build(), B, "bf16", True, dict(kind="bce", pos_weight=3.0, class_weight=0.2), dry_run=True)
     f = Counter(n for n, _, _, _ in e.fwd)
-    assert f["basi_skinny_fwd"] == 2
+    assert f["basi_skinny_fwd_ws"] == 2
 
 
 def test_experiment_switches_need_the_master_switch(monkeypatch, capsys):

@@ -22,12 +22,20 @@ ap.add_argument("--precision", default="f16")
 ap.add_argument("--variant", default="2AddClass")
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=30)
-ap.add_argument("--modes", default="1:0,2:0,3:0,1:1,2:1,3:1,4:1,6:1")
+ap.add_argument("--modes", default="1:0,2:0,3:0,1:1,2:1,3:1,4:1,6:1",
+                help="comma list of streams:defer[:wgrad_splits[:wgrad_waves[:wgrad_target_ctas]]]")
 a = ap.parse_args()
 
 ref = None
 for mode in a.modes.split(","):
-    k, d = mode.split(":")
+    parts = mode.split(":") + ["", "", "", ""]
+    k, d, sp, wv, tg, mx = parts[0], parts[1], parts[2], parts[3], parts[4], parts[5]
+    for name, val in (("BASI_TC_WGRAD_SPLITS", sp), ("BASI_TC_WGRAD_WAVES", wv), ("BASI_TC_WGRAD_TARGET", tg),
+                      ("BASI_TC_WGRAD_MAXTILES", mx)):
+        if val:
+            os.environ[name] = val
+        else:
+            os.environ.pop(name, None)
     os.environ["BASI_WGRAD_STREAMS"] = k
     if d == "1":
         os.environ["BASI_DEFER_WGRAD"] = "1"
@@ -56,7 +64,8 @@ for mode in a.modes.split(","):
         eng.replay()
     e1.record()
     torch.cuda.synchronize()
-    print("wgrad streams %s defer %s: %.3f ms/step, gradient rel-l2 vs default schedule %.2e" %
-          (k, d, e0.elapsed_time(e1) / a.steps, err), flush=True)
+    print("wgrad streams %s defer %s splits %s waves %s target %s maxtiles %s: %.3f ms/step, gradient rel-l2 vs default "
+          "schedule %.2e" % (k, d, sp or "-", wv or "-", tg or "-", mx or "-", e0.elapsed_time(e1) / a.steps, err),
+          flush=True)
     del tr, eng
     torch.cuda.empty_cache()
