@@ -1936,6 +1936,9 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     const int stage_bytes = pl->gbox * A_BYTES + (bn / 64) * A_BYTES;
     int stages = (int)((227 * 1024 - 2048) / stage_bytes);
     if (stages > 6) stages = 6;
+    if (exp_env("BASI_TC_WGRAD_STAGES") && atoi(exp_env("BASI_TC_WGRAD_STAGES")) >= 2 &&
+        atoi(exp_env("BASI_TC_WGRAD_STAGES")) < stages)
+      stages = atoi(exp_env("BASI_TC_WGRAD_STAGES"));   // experiment: smaller footprint -> co-residency with BN kernels
     wp.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + 1024 + 256;
     pl->dw = dw;

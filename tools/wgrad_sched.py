@@ -28,10 +28,10 @@ a = ap.parse_args()
 
 ref = None
 for mode in a.modes.split(","):
-    parts = mode.split(":") + ["", "", "", ""]
-    k, d, sp, wv, tg, mx = parts[0], parts[1], parts[2], parts[3], parts[4], parts[5]
+    parts = mode.split(":") + ["", "", "", "", ""]
+    k, d, sp, wv, tg, mx, sg = parts[0], parts[1], parts[2], parts[3], parts[4], parts[5], parts[6]
     for name, val in (("BASI_TC_WGRAD_SPLITS", sp), ("BASI_TC_WGRAD_WAVES", wv), ("BASI_TC_WGRAD_TARGET", tg),
-                      ("BASI_TC_WGRAD_MAXTILES", mx)):
+                      ("BASI_TC_WGRAD_MAXTILES", mx), ("BASI_TC_WGRAD_STAGES", sg)):
         if val:
             os.environ[name] = val
         else:
@@ -64,8 +64,8 @@ for mode in a.modes.split(","):
         eng.replay()
     e1.record()
     torch.cuda.synchronize()
-    print("wgrad streams %s defer %s splits %s waves %s target %s maxtiles %s: %.3f ms/step, gradient rel-l2 vs default "
-          "schedule %.2e" % (k, d, sp or "-", wv or "-", tg or "-", mx or "-", e0.elapsed_time(e1) / a.steps, err),
-          flush=True)
+    print("wgrad streams %s defer %s splits %s waves %s target %s maxtiles %s stages %s: %.3f ms/step, gradient rel-l2 vs "
+          "first mode %.2e" % (k, d, sp or "-", wv or "-", tg or "-", mx or "-", sg or "-",
+                               e0.elapsed_time(e1) / a.steps, err), flush=True)
     del tr, eng
     torch.cuda.empty_cache()
