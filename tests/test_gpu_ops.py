@@ -1016,3 +1016,92 @@ def test_engine_label_input_feeds_border_labels_and_reference_clicks():
         where = where[r2.randint(0, len(where))]
         ref_clicks.append([where[0] * 8, where[1] * 8])
     assert np.array_equal(eng.clicks_dev.cpu().numpy(), np.asarray(ref_clicks, dtype=np.int32))
+
+
+# ------------------------------------------------------------------ F4 ops (cascade): sigmoid, channel-select weighted BCE
+def _guarded(n, dtype=torch.float32, guard=64, fill=-77.0):
+    """a device buffer of n elements between two guard bands (the kernels must not touch the bands)"""
+    full = torch.full((n + 2 * guard,), fill, dtype=dtype, device="cuda:0")
+    return full, full[guard:guard + n]
+
+
+def _guards_intact(full, n, guard=64, fill=-77.0):
+    torch.cuda.synchronize()
+    return bool((full[:guard] == fill).all()) and bool((full[guard + n:] == fill).all())
+
+
+@pytest.mark.parametrize("n", [1, 7, 4 * 40 * 40 * 4, 100003])
+def test_sigmoid_forward_backward(n):
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(n)
+    x = (rng.randn(n) * 6).astype(np.float32)
+    x[: min(n, 4)] = [0.0, -90.0, 90.0, 1e-8][: min(n, 4)]
+    dy = rng.randn(n).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    yt = torch.sigmoid(xt)
+    (yt * torch.from_numpy(dy).double()).sum().backward()
+    xd, dyd = dev(x), dev(dy)
+    fy, y = _guarded(n)
+    call("basi_sigmoid_fwd", xd.data_ptr(), y.data_ptr(), C.c_int64(n))
+    assert _guards_intact(fy, n)
+    assert np.max(np.abs(host(y) - yt.detach().numpy())) < 2e-7
+    fdx, dx = _guarded(n)
+    call("basi_sigmoid_bwd", dyd.data_ptr(), y.data_ptr(), dx.data_ptr(), C.c_int64(n), 0)
+    assert _guards_intact(fdx, n)
+    assert np.max(np.abs(host(dx) - xt.grad.numpy())) < 1e-6
+    call("basi_sigmoid_bwd", dyd.data_ptr(), y.data_ptr(), dx.data_ptr(), C.c_int64(n), 1)      # accumulate
+    assert np.max(np.abs(host(dx) - 2 * xt.grad.numpy())) < 2e-6
+    assert _guards_intact(fdx, n)
+
+
+@pytest.mark.parametrize("rows,Cn,sel", [(1, 2, 1), (4 * 40 * 40, 2, 1), (1001, 4, 2), (50000, 2, 0)])
+def test_wbce_channel_select(rows, Cn, sel):
+    """cal_loss of the cascade: weighted_cross_entropy_with_logits on tf.split(segment, C, axis=3)[sel]
+    (back/8AttentionU/BAISRunnerTrain.py:176-180); the gradient goes to channel `sel`, zeros to the others."""
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(rows)
+    x = rng.rand(rows, Cn).astype(np.float32)                  # (sigmoid outputs are what the reference feeds)
+    z = (rng.rand(rows) < 0.3).astype(np.float32)
+    pw, lw, gw = 3.0, 2.0 / (4 * rows), 0.37
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    loss = O.weighted_cross_entropy_with_logits(torch.from_numpy(z).double(), xt[:, sel], pw).sum() * lw
+    loss.backward()
+    xd, zd = dev(x), dev(z)
+    acc = torch.zeros(4, dtype=torch.float64, device="cuda:0")
+    fg, g = _guarded(rows * Cn)
+    call("basi_wbce_sel_fwd_bwd", xd.data_ptr(), Cn, sel, zd.data_ptr(), C.c_float(pw), C.c_double(lw), C.c_float(gw),
+         C.c_int64(rows), acc.data_ptr(), g.data_ptr())
+    assert _guards_intact(fg, rows * Cn)
+    got = host(g).reshape(rows, Cn)
+    assert abs(float(acc[0]) - float(loss.detach())) < 1e-6 * max(1.0, abs(float(loss.detach())))
+    want = xt.grad.numpy() * (gw / lw)
+    assert np.max(np.abs(got - want)) < 1e-5 * max(1.0, np.abs(want).max())
+    assert np.all(got[:, [c for c in range(Cn) if c != sel]] == 0.0)
+
+
+def test_deterministic_pool_and_gemv_do_not_touch_their_neighbours():
+    """The rows/cells pyramid pooling writes exactly basi_avgpool_multi_scratch_floats() floats of scratch and the
+    workspace GEMV exactly basi_skinny_fwd_workspace_floats() (guard bands around both stay intact)."""
+    from gpu_util import act, call, dev, empty_act, host
+    from basi_b200 import _lib
+    from basi_b200._lib import Tensor
+    rng = np.random.RandomState(2)
+    B, H, Cc, ks = 3, 40, 64, (40, 20, 13, 6)
+    xa = act(_u(rng, B, H, H, Cc), torch.bfloat16)
+    ys = [empty_act((B, H // k, H // k, Cc), torch.bfloat16, fill=9.0) for k in ks]
+    karr = (C.c_int * len(ks))(*ks)
+    yptr = (C.POINTER(Tensor) * len(ks))(*[C.pointer(y.desc) for y in ys])
+    nfl = int(_lib.load().basi_avgpool_multi_scratch_floats(xa.ref, len(ks), karr))
+    full, scratch = _guarded(nfl)
+    call("basi_avgpool_multi_fwd", xa.ref, len(ks), karr, yptr, scratch.data_ptr())
+    assert _guards_intact(full, nfl)
+    M, K, N = 5, 25 * 64, 96
+    a, w, b = _u(rng, M, K), _u(rng, K, N) / 40, _u(rng, N)
+    nws = int(_lib.load().basi_skinny_fwd_workspace_floats(M, K, N))
+    fullw, ws = _guarded(nws)
+    fully, y = _guarded(M * N)
+    ad, wd, bd = dev(a), dev(w), dev(b)
+    call("basi_skinny_fwd_ws", ad.data_ptr(), 0, C.c_int64(K), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), M, K, N, 0,
+         ws.data_ptr())
+    assert _guards_intact(fullw, nws) and _guards_intact(fully, M * N)
+    assert np.max(np.abs(host(y).reshape(M, N) - (a.astype(np.float64) @ w + b))) < 1e-4
