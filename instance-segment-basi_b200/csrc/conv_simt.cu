@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
   // block = (128 output columns, a run of k-slabs); the partial sums of the run stay in registers and are added to y
   // once (with one slab per block the 52 MB class_attention_conv GEMV was bound by its 3.3 M atomics, not by HBM)
   pdl_prologue();
-  __shared__ float sa[64][SK_KT + 1];
+  __shared__ __align__(16) float sa[16][SK_KT + 4];      // (row stride 68 floats: 16-byte aligned rows, shifted banks)
   const int n = blockIdx.x * 128 + threadIdx.x;
   for (int mb = 0; mb < M; mb += 16) {
     float acc[16];
@@ -455,8 +455,23 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
       }
       __syncthreads();
       if (n < N) {
-#pragma unroll 4
-        for (int k = 0; k < kt; ++k) {
+        // four weight rows per step: 4 coalesced loads in flight, one 128-bit (broadcast) shared-memory read per batch
+        // row feeds 4 FMAs (the scalar version issued one shared-memory load per FMA)
+        int k = 0;
+        for (; k + 8 <= kt; k += 8) {
+          const float* wp = w + (int64_t)(k0 + k) * N + n;
+          float wv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wv[j] = __ldg(wp + (int64_t)j * N);       // eight rows in flight
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sa[i][k]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sa[i][k + 4]);
+            float t = fmaf(a0.x, wv[0], fmaf(a0.y, wv[1], fmaf(a0.z, wv[2], fmaf(a0.w, wv[3], acc[i]))));
+            acc[i] = fmaf(a1.x, wv[4], fmaf(a1.y, wv[5], fmaf(a1.z, wv[6], fmaf(a1.w, wv[7], t))));
+          }
+        }
+        for (; k < kt; ++k) {
           const float wv = __ldg(w + (int64_t)(k0 + k) * N + n);
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = fmaf(sa[i][k], wv, acc[i]);
@@ -482,7 +497,8 @@ __global__ void skinny_reduce_bias_act_kernel(const float* __restrict__ part, in
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   float v = 0.f;
-  for (int p = 0; p < parts; ++p) v += part[(int64_t)p * M * N + i];
+#pragma unroll 8
+  for (int p = 0; p < parts; ++p) v += part[(int64_t)p * M * N + i];      // (fixed order: bit-reproducible)
   v += bias ? bias[i % N] : 0.f;
   y[i] = relu ? fmaxf(v, 0.f) : v;
 }
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
   // a warp takes TWO weight rows k per iteration against 16 batch rows: every dy value read from shared memory feeds
   // two FMAs, and the 32 partial sums (2 k x 16 m) are reduced across the lanes with one 31-shuffle transpose-reduce
   pdl_prologue();
-  extern __shared__ float sdy[];  // [M][N]
+  extern __shared__ __align__(16) float sdy[];  // [M][N]
   for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -529,13 +545,29 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
       float acc[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-      for (int n = lane; n < N; n += 32) {
-        const float wa = __ldg(w0 + n), wb = __ldg(w1 + n);
+      if ((N & 127) == 0) {
+        // 128-bit loads: a lane takes 4 consecutive columns per step (the 52 MB class_attention_conv weight matrix is
+        // read once; with scalar loads the kernel was bound by load / shared-memory instructions, not by HBM)
+        for (int n = lane * 4; n < N; n += 128) {
+          const float4 wa = __ldg(reinterpret_cast<const float4*>(w0 + n));
+          const float4 wb = __ldg(reinterpret_cast<const float4*>(w1 + n));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float g = mb + i < M ? sdy[(mb + i) * N + n] : 0.f;
-          acc[i] = fmaf(g, wa, acc[i]);
-          acc[16 + i] = fmaf(g, wb, acc[16 + i]);
+          for (int i = 0; i < 16; ++i) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mb + i < M) g = *reinterpret_cast<const float4*>(sdy + (mb + i) * N + n);
+            acc[i] = fmaf(g.x, wa.x, fmaf(g.y, wa.y, fmaf(g.z, wa.z, fmaf(g.w, wa.w, acc[i]))));
+            acc[16 + i] = fmaf(g.x, wb.x, fmaf(g.y, wb.y, fmaf(g.z, wb.z, fmaf(g.w, wb.w, acc[16 + i]))));
+          }
+        }
+      } else {
+        for (int n = lane; n < N; n += 32) {
+          const float wa = __ldg(w0 + n), wb = __ldg(w1 + n);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float g = mb + i < M ? sdy[(mb + i) * N + n] : 0.f;
+            acc[i] = fmaf(g, wa, acc[i]);
+            acc[16 + i] = fmaf(g, wb, acc[16 + i]);
+          }
         }
       }
       warp_transpose_sums(acc, lane);          // lane l now holds the total of entry l: (k + l / 16, mb + l % 16)
@@ -556,13 +588,13 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict_
                                                            const float* __restrict__ dy, float* __restrict__ dw,
                                                            float* __restrict__ dbias, int M, int K, int N) {
   pdl_prologue();
-  __shared__ float sa[MB][SK_KT + 1];
+  __shared__ __align__(16) float sa[SK_KT][MB];           // [k][m]: the MB batch values of one k are contiguous
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int k0 = blockIdx.y * SK_KT;
   const int kt = min(SK_KT, K - k0);
   for (int i = threadIdx.x; i < MB * SK_KT; i += 128) {   // rows >= M are zero-filled (they are multiplied)
     int m = i / SK_KT, k = i - m * SK_KT;
-    sa[m][k] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+    sa[k][m] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
   }
   __syncthreads();
   if (n >= N) return;
@@ -574,12 +606,27 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict_
     bs += g[m];
   }
   if (dbias && blockIdx.y == 0) dbias[n] += bs;
-#pragma unroll 4
-  for (int k = 0; k < kt; ++k) {
-    float acc = 0.f;
+  // eight k rows per step: the eight read-modify-writes of dw are independent and in flight together (one dependent
+  // load -> add -> store per k made the 512 x 21 fc gradient a 40 us chain of 64 global round trips)
+  for (int kb = 0; kb < kt; kb += 8) {
+    float acc[8], old[8];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) acc = fmaf(sa[m][k], g[m], acc);
-    dw[(int64_t)(k0 + k) * N + n] += acc;
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = 0.f;
+      old[j] = kb + j < kt ? dw[(int64_t)(k0 + kb + j) * N + n] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kb + j >= kt) break;
+#pragma unroll
+      for (int m4 = 0; m4 < MB; m4 += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&sa[kb + j][m4]);
+        acc[j] = fmaf(av.x, g[m4], fmaf(av.y, g[m4 + 1], fmaf(av.z, g[m4 + 2], fmaf(av.w, g[m4 + 3], acc[j]))));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (kb + j < kt) dw[(int64_t)(k0 + kb + j) * N + n] = old[j] + acc[j];
   }
 }
 

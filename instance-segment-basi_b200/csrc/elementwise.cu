@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) avgpool_multi_rows_kernel(const T* __rest
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[p][j] = 0.f;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int w = 0; w < W; ++w) {
       const Vec<T> v = Vec<T>::load(xr + (int64_t)w * ldx);
 #pragma unroll
@@ -327,6 +327,7 @@ __global__ void avgpool_multi_cells_kernel(const MultiPool mp, int H, int C, int
     float sum[VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) sum[j] = 0.f;
+#pragma unroll 4
     for (int h = oh * mp.k[p]; h < (oh + 1) * mp.k[p]; ++h) {
       const float* sp = scratch + (((size_t)n * H + h) * rcells + rc0 + ow) * C + cg * VN;
 #pragma unroll
