@@ -290,6 +290,40 @@ def kernel_profile(eng, torch, detail_path=None):
     return agg
 
 
+def in_graph_marginal(eng, torch, names, steps=20):
+    """Marginal time of a group of calls INSIDE the captured step (tools/ablate_step.py): the step graph is captured
+    and replayed with and without the calls whose entry point is in `names`; the difference is what those launches cost
+    with programmatic dependent launch and the weight-gradient side streams active -- the per-launch CUDA-event sums
+    of kernel_profile() time every launch in isolation instead.  The ablated step computes garbage (only its time is
+    read), so this runs last, on an engine that is discarded afterwards."""
+    def timed():
+        eng._graph = None
+        eng.capture(train=True)
+        for _ in range(3):
+            eng.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            eng.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    fwd, bwd = eng.fwd, eng.bwd
+    full = timed()
+    group = [c for c in fwd + bwd if c[0] in names]
+    eng.fwd = [c for c in fwd if c[0] not in names]
+    eng.bwd = [c for c in bwd if c[0] not in names]
+    try:
+        without = timed()
+    finally:
+        eng.fwd, eng.bwd = fwd, bwd
+        eng._graph = None
+    return dict(ms_full=full, ms_without=without, ms=full - without, n=len(group),
+                flops=sum(c[3].get("flops", 0.0) for c in group))
+
+
 def hbm_microbench(torch, pk):
     """SURVEY section 8(d) / BASELINE.md section 3: the fused loss, gating and SGD kernels on >= 64 M-element tensors
     (the training step's own loss tensor has 25 600 elements: latency-bound).  Working sets of 0.4-1.6 GB exceed the
@@ -477,6 +511,19 @@ def measure(args, wl_name, dp, device, dev_index, rank, world, want_profile):
                     break
             except (OSError, ValueError):
                 pass
+        if d["flops"] > 0 and tr.use_cuda_graph and not dp:
+            try:
+                mg = in_graph_marginal(eng, torch, [k for k, v in KERNEL_GROUP.items() if v == name])
+                if mg["ms"] > 0:
+                    ach_g = mg["flops"] / (mg["ms"] * 1e-3) / 1e12
+                    roof["in_graph"] = {
+                        "ms_per_step": round(mg["ms"], 3), "achieved": ach_g,
+                        "frac_of_sustained_peak": ach_g / pk["tensor_sustained"], "frac_of_burst_peak": ach_g / pk["tensor"],
+                        "step_ms_with": round(mg["ms_full"], 3), "step_ms_without": round(mg["ms_without"], 3),
+                        "how": "step graph re-captured without the %d launches of this group; marginal time inside "
+                               "the real graph (PDL + side streams), tools/ablate_step.py" % mg["n"]}
+            except Exception as e:      # explanatory number only: never fail the bench line for it
+                roof["in_graph"] = {"error": str(e)[:200]}
         res["roofline"] = roof
         res["whole_step_tflops"] = res["value"] * wl["flop_per_image"] / 1e12
         res["breakdown"] = {k: {"ms": round(v["ms"], 3), "n": v["n"],

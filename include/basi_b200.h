@@ -69,6 +69,11 @@ int basi_version(void);
 int basi_half_format(void);
 /* number of SMs of the current device (148 on B200), negative on error */
 int basi_sm_count(void);
+/* SM partition for the backward pass (no reference counterpart: TF's stream executor schedules its own kernels).
+ * While main_sms > 0 every grid-size rule of the library (plan creation and launch) sees main_sms SMs instead of the
+ * hardware count; wgrad_ctas > 0 is the CTA target of the tensor-core weight-gradient plans created meanwhile.
+ * (0, 0) restores the defaults.  Process-wide, not thread-safe: the engine sets it around plan creation / enqueue. */
+int basi_set_sm_budget(int main_sms, int wgrad_ctas);
 int basi_memset(void* ptr, int value, int64_t bytes, void* stream);
 
 /* ---- A3 / F3: label encodings and click sampling on the device (integer work, bit-exact) ----

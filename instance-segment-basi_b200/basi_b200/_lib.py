@@ -120,6 +120,7 @@ SIGNATURES = {
     "basi_tc_conv_create_split": [_i, _DP, _TP, _TP, _P, _P, _i, _i, C.POINTER(_P)],
     "basi_tc_conv_set_bn_stats": [_P, _P, _P, _P, _d, _f, _P, _P],
     "basi_tc_conv_run": [_P, _P],
+    "basi_set_sm_budget": [_i, _i],
 }
 _NOCHECK = {"basi_last_error": ([], C.c_char_p), "basi_version": ([], _i), "basi_sm_count": ([], _i),
             "basi_half_format": ([], _i),

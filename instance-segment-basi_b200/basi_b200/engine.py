@@ -153,6 +153,11 @@ class Engine(object):
         self._sides = ([self._side] + [torch.cuda.Stream(self.device) for _ in range(self.wgrad_streams - 1)]
                        if self.overlap_wgrad else [])
         self._side_rr = 0
+        # SM partition of the backward pass (basi_set_sm_budget): the main chain (dgrad / batch-norm backward) sizes its
+        # grids for `sm_main` SMs, every tensor-core weight gradient launches `sm_wgrad` CTAs, so the side stream owns
+        # the remaining SMs instead of time-slicing with full-machine launches.  0 = off.
+        self.sm_main = int(_exp_env("BASI_SM_MAIN") or 0) if self.overlap_wgrad else 0
+        self.sm_wgrad = int(_exp_env("BASI_SM_WGRAD") or 0) if self.sm_main else 0
         # independent sub-graphs (the four PSP branches) can run on their own streams, forked/joined with events.
         # Measured inside the step graph: 10.27 ms with the branch streams vs 10.08 ms without (the extra cross-stream
         # dependencies cost more than the ~0.3 ms of tiny kernels they overlap), so this is opt-in.
@@ -185,7 +190,15 @@ class Engine(object):
         self._build_params()
         self._lower()
         if training:
-            self._emit_backward()
+            if self.sm_main:
+                _lib.load().basi_set_sm_budget(self.sm_main, self.sm_wgrad)
+            try:
+                self._emit_backward()
+            finally:
+                if self.sm_main:
+                    _lib.load().basi_set_sm_budget(0, 0)
+            for c in self.bwd:
+                c[3]["bwd"] = True
         if self.fused_apply >= 40:
             self.storage_policy = "fused"      # most BN inputs are never rounded: normalised from the accumulators
 
@@ -1347,6 +1360,17 @@ class Engine(object):
         cur = torch.cuda.current_stream(self.device)
         branches = self._bstreams
         forked, fork_ev = {}, None
+        part = self.sm_main > 0 and len(lst) > 0 and lst[0][3].get("bwd")
+        if part:        # launch-time grid rules (batch-norm backward, CUDA-core kernels) see the same budget as the plans
+            _lib.load().basi_set_sm_budget(self.sm_main, self.sm_wgrad)
+        try:
+            self._run_calls(lst, st, side, cur, branches, forked, fork_ev)
+        finally:
+            if part:
+                _lib.load().basi_set_sm_budget(0, 0)
+        _lib.LAUNCHES += len(lst)
+
+    def _run_calls(self, lst, st, side, cur, branches, forked, fork_ev):
         for name, fn, args, meta in lst:
             b = meta.get("branch") if branches is not None else None
             if b is None and forked:
@@ -1374,7 +1398,6 @@ class Engine(object):
                 raise _lib.BasiError("%s failed (%d): %s" % (name, rc, _lib.last_error()))
         if forked:
             self._join_branches(cur, forked)
-        _lib.LAUNCHES += len(lst)
 
     def _join_branches(self, cur, forked):
         for b in forked:

@@ -33,7 +33,8 @@ const char* exp_env(const char* name);
     }                                                                        \
   } while (0)
 
-int sm_count();
+int sm_count();          // SMs the grid-size rules may use (hardware count unless basi_set_sm_budget set fewer)
+int wgrad_cta_target();  // CTAs per tensor-core weight-gradient launch (0: the default rule)
 
 // The library's 16-bit storage type.  Default build: bfloat16 (libbasi_b200.so).  -DBASI_HALF_FP16 builds the same
 // kernels for IEEE half (libbasi_b200_f16.so, precision "f16" of the engine): 3 more mantissa bits -- on this network

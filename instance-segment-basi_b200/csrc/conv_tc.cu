@@ -1915,7 +1915,8 @@ static int create_plan(int kind, const basi_conv_desc* d, const basi_tensor* a, 
     if (exp_env("BASI_TC_WGRAD_SPLITS")) {
       splits = atoi(exp_env("BASI_TC_WGRAD_SPLITS"));                                      // experiment
     } else if (split == 0 && !exp_env("BASI_TC_WGRAD_WAVES")) {
-      const int target = exp_env("BASI_TC_WGRAD_TARGET") ? atoi(exp_env("BASI_TC_WGRAD_TARGET")) : 64;
+      const int target = exp_env("BASI_TC_WGRAD_TARGET") ? atoi(exp_env("BASI_TC_WGRAD_TARGET"))
+                         : (basi::wgrad_cta_target() > 0 ? basi::wgrad_cta_target() : 64);
       splits = (target + out_tiles - 1) / out_tiles;
       if (exp_env("BASI_TC_WGRAD_MAXTILES")) {  // experiment: no CTA loops over more than this many pixel tiles
         const int mx = atoi(exp_env("BASI_TC_WGRAD_MAXTILES"));

@@ -44,7 +44,10 @@ bool pdl_enabled() {
   }
   return v == 1;
 }
-int sm_count() {
+// SM partition (basi_set_sm_budget): while a budget is set, every grid-size rule of the library sees that many SMs, so
+// the main chain of the backward pass leaves the rest of the machine to the weight gradients on the side stream.
+static int g_sm_budget = 0, g_wgrad_ctas = 0;
+static int hw_sm_count() {
   static int cached = 0;
   if (cached > 0) return cached;
   int dev = 0, n = 0;
@@ -56,6 +59,11 @@ int sm_count() {
   cached = n;
   return n;
 }
+int sm_count() {
+  const int hw = hw_sm_count();
+  return (g_sm_budget > 0 && g_sm_budget < hw) ? g_sm_budget : hw;
+}
+int wgrad_cta_target() { return g_wgrad_ctas; }
 
 // ------------------------------------------------------------------------------------------
 // Pooling
@@ -1271,6 +1279,15 @@ int basi_sm_count(void) {
     return BASI_E_NOGPU;
   }
   return n;
+}
+int basi_set_sm_budget(int main_sms, int wgrad_ctas) {
+  if (main_sms < 0 || wgrad_ctas < 0) {
+    set_error("basi_set_sm_budget: negative argument");
+    return BASI_E_INVALID;
+  }
+  basi::g_sm_budget = main_sms;
+  basi::g_wgrad_ctas = wgrad_ctas;
+  return BASI_OK;
 }
 int basi_half_format(void) { return BASI_H16_FP16; }   /* 0: the 16-bit storage type of this build is bfloat16, 1: IEEE fp16 */
 int basi_memset(void* ptr, int value, int64_t bytes, void* stream) {

@@ -23,15 +23,17 @@ ap.add_argument("--variant", default="2AddClass")
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--modes", default="1:0,2:0,3:0,1:1,2:1,3:1,4:1,6:1",
-                help="comma list of streams:defer[:wgrad_splits[:wgrad_waves[:wgrad_target_ctas]]]")
+                help="comma list of streams:defer[:wgrad_splits[:wgrad_waves[:wgrad_target_ctas[:maxtiles[:stages[:sm_main[:sm_wgrad]]]]]]]")
 a = ap.parse_args()
 
 ref = None
 for mode in a.modes.split(","):
-    parts = mode.split(":") + ["", "", "", "", ""]
+    parts = mode.split(":") + ["", "", "", "", "", "", ""]
     k, d, sp, wv, tg, mx, sg = parts[0], parts[1], parts[2], parts[3], parts[4], parts[5], parts[6]
+    sm_main, sm_wg = parts[7], parts[8]
     for name, val in (("BASI_TC_WGRAD_SPLITS", sp), ("BASI_TC_WGRAD_WAVES", wv), ("BASI_TC_WGRAD_TARGET", tg),
-                      ("BASI_TC_WGRAD_MAXTILES", mx), ("BASI_TC_WGRAD_STAGES", sg)):
+                      ("BASI_TC_WGRAD_MAXTILES", mx), ("BASI_TC_WGRAD_STAGES", sg), ("BASI_SM_MAIN", sm_main),
+                      ("BASI_SM_WGRAD", sm_wg)):
         if val:
             os.environ[name] = val
         else:
@@ -64,8 +66,9 @@ for mode in a.modes.split(","):
         eng.replay()
     e1.record()
     torch.cuda.synchronize()
-    print("wgrad streams %s defer %s splits %s waves %s target %s maxtiles %s stages %s: %.3f ms/step, gradient rel-l2 vs "
-          "first mode %.2e" % (k, d, sp or "-", wv or "-", tg or "-", mx or "-", sg or "-",
-                               e0.elapsed_time(e1) / a.steps, err), flush=True)
+    print("wgrad streams %s defer %s splits %s waves %s target %s maxtiles %s stages %s sm_main %s sm_wgrad %s: %.3f ms/step, "
+          "gradient rel-l2 vs first mode %.2e" % (k, d, sp or "-", wv or "-", tg or "-", mx or "-", sg or "-",
+                                                  sm_main or "-", sm_wg or "-", e0.elapsed_time(e1) / a.steps, err),
+          flush=True)
     del tr, eng
     torch.cuda.empty_cache()
