@@ -125,14 +125,24 @@ class Train(object):
             return None
         return (np.asarray(label_seg) == 1).astype(np.float32)
 
-    def run_step(self, step, batch=None, fetch=True):
-        """One reference ``sess.run([... train_op ...], feed_dict)``; returns the fetched values."""
+    def run_step(self, step, batch=None, fetch=True, prefetch=None):
+        """One reference ``sess.run([... train_op ...], feed_dict)``; returns the fetched values.
+
+        `prefetch` (synthetic / click-input batches): the batch of the NEXT call -- its host-to-device copies are
+        started on a copy stream as soon as this step is enqueued, so they overlap it; the next call must then pass
+        that same object as `batch`."""
         eng = self.engine
         lr = poly_learning_rate(self.learning_rate, step, self.num_steps)
+        staged = getattr(self, "_staged_batch", None)
+        self._staged_batch = None
         if self.synthetic:
             images, clicks, label_seg, label_cls = batch if batch is not None else self.data_reader.next_batch()
-            eng.feed_clicks(images, clicks)
-            eng.feed(None, label_seg, label_cls, lr, label_att=self._attention_labels(label_seg))
+            if staged is not None and batch is staged:
+                eng.commit_staged()
+                eng.set_lr(lr)
+            else:
+                eng.feed_clicks(images, clicks)
+                eng.feed(None, label_seg, label_cls, lr, label_att=self._attention_labels(label_seg))
         else:
             data, ann, cls, _, _ = batch if batch is not None else self.data_reader.next_batch_train()
             label_cls, label_seg = cls, np.asarray(ann)
@@ -146,15 +156,21 @@ class Train(object):
             eng.step_device(sync_grads=self.dp)
         else:
             eng.step_device()
+        if prefetch is not None and self.synthetic:
+            p_img, p_clicks, p_seg, p_cls = prefetch
+            eng.stage_batch(p_img, p_clicks, p_seg, p_cls, self._attention_labels(p_seg))
+            self._staged_batch = prefetch
         if not fetch:
             return None
-        loss, loss_seg, loss_cls = eng.losses()
-        raw = eng.seg_logits.t.cpu().numpy()
-        pred_seg = eng.pred_seg.cpu().numpy()
+        att = ([("raw_output_attentions_%d" % i, a.t) for i, a in enumerate(eng.att_logits)]
+               if self.variant == "90AttentionSingle2" else [])
+        got = eng.fetch_step(att)          # one synchronisation for the whole fetch list
+        loss, loss_seg, loss_cls = eng.losses_from(got["loss_acc"])
+        raw, pred_seg = got["raw_output_segment"], got["pred_segment"]
         out = dict(loss=loss, loss_segment=loss_seg, loss_classes=loss_cls, learning_rate=lr,
                    raw_output_segment=raw, pred_segment=pred_seg)
         if self.variant == "90AttentionSingle2":
-            out["raw_output_attentions"] = [a.t.cpu().numpy() for a in eng.att_logits]
+            out["raw_output_attentions"] = [got[k] for k, _ in att]
             lab = None
         else:
             lab = np.asarray(label_seg).reshape(pred_seg.shape)
@@ -166,8 +182,8 @@ class Train(object):
         else:
             out["accuracy_segment"] = float(np.mean(pred_seg == lab))
         if eng.cls_logits is not None:
-            out["raw_output_classes"] = eng.cls_logits.t.cpu().numpy().reshape(self.batch_size, -1)
-            out["pred_classes"] = eng.pred_cls.cpu().numpy()
+            out["raw_output_classes"] = got["raw_output_classes"].reshape(self.batch_size, -1)
+            out["pred_classes"] = got["pred_classes"]
             out["accuracy_classes"] = float(np.mean(out["pred_classes"] == np.asarray(label_cls)))
         return out
 
@@ -178,9 +194,12 @@ class Train(object):
         is_writer = self.dp is None or self.dp.rank == 0     # one checkpoint writer
         end = self.num_steps if max_steps is None else min(self.num_steps, begin_step + max_steps)
         r = None
+        # synthetic / click-input batches are drawn one step ahead and prefetched (same draw order as without)
+        nxt = self.data_reader.next_batch() if (self.synthetic and begin_step < end) else None
         for step in range(begin_step, end):
             start_time = time.time()
-            r = self.run_step(step)
+            cur, nxt = nxt, (self.data_reader.next_batch() if (self.synthetic and step + 1 < end) else None)
+            r = self.run_step(step, cur, prefetch=nxt)
             if step % save_pred_freq == 0 and is_writer:
                 Tools.save(self.engine, self.checkpoint_path, step)
                 Tools.print_info('The checkpoint has been created.')

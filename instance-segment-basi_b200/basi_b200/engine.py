@@ -1590,6 +1590,71 @@ class Engine(object):
         torch.cuda.synchronize(self.device)
         return a.t.float().cpu().numpy()
 
+    # ---- host pipeline of the training loop: prefetch of the next batch, one packed read-back per step
+    def stage_batch(self, images_u8, clicks, label_seg=None, label_cls=None, label_att=None):
+        """Prefetch: starts the host-to-device copies of the NEXT step's inputs (pinned tensors or numpy arrays) into
+        staging buffers on a copy stream, so they overlap the step that is running; commit_staged() moves them into the
+        static input buffers of the step plan.  (The reference feeds synchronously through feed_dict,
+        back/2AddClass/BAISRunnerTrain.py:158-168; a TF input queue is the closest analogue.)"""
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage = {}
+            self._stage_ev = torch.cuda.Event()
+            self._commit_ev = None
+        srcs = dict(img_u8=(images_u8, getattr(self, "img_u8", None)), clicks=(clicks, getattr(self, "clicks_dev", None)),
+                    label_seg=(label_seg, getattr(self, "label_seg", None)),
+                    label_cls=(label_cls, getattr(self, "label_cls", None)),
+                    label_att=(label_att, getattr(self, "label_att", None)))
+        cs = self._copy_stream
+        if self._commit_ev is not None:
+            cs.wait_event(self._commit_ev)          # the previous commit has read the staging buffers
+        self._staged = []
+        with torch.cuda.stream(cs):
+            for key, (src, dst) in srcs.items():
+                if src is None or dst is None:
+                    continue
+                if key not in self._stage:
+                    self._stage[key] = torch.empty_like(dst)
+                self._stage[key].copy_(_as_tensor(src, dst.dtype).view(dst.shape), non_blocking=True)
+                self._staged.append((self._stage[key], dst))
+            self._stage_ev.record(cs)
+
+    def commit_staged(self):
+        """Device-to-device copies of the staged batch into the static input buffers, on the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_ev)
+        for src, dst in self._staged:
+            dst.copy_(src, non_blocking=True)
+        self._commit_ev = torch.cuda.Event()
+        self._commit_ev.record(cur)
+        self._staged = []
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr) / self.loss_scale)
+
+    def fetch_step(self, extra=()):
+        """The per-step read-back of a reference ``sess.run`` fetch list in ONE synchronisation: losses, segment
+        logits, predictions (+ class logits / predictions, + `extra` tensors) are copied to pinned host buffers
+        asynchronously, the stream is synchronised once, numpy copies are returned."""
+        items = [("loss_acc", self.loss_acc), ("raw_output_segment", self.seg_logits.t), ("pred_segment", self.pred_seg)]
+        if self.cls_logits is not None:
+            items += [("raw_output_classes", self.cls_logits.t), ("pred_classes", self.pred_cls)]
+        items += list(extra)
+        if not hasattr(self, "_fetch_pinned"):
+            self._fetch_pinned = {}
+        for name, t in items:
+            h = self._fetch_pinned.get(name)
+            if h is None or h.shape != t.shape or h.dtype != t.dtype:
+                h = self._fetch_pinned[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {name: self._fetch_pinned[name].numpy().copy() for name, _ in items}
+
+    def losses_from(self, acc):
+        seg, cls = float(acc[0]), float(acc[1])
+        total = seg + (self.class_weight * cls if self.cls_logits is not None else 0.0)
+        return total, seg, cls
+
     def losses(self):
         acc = self.loss_acc.cpu().numpy()
         seg, cls = float(acc[0]), float(acc[1])

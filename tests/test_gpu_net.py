@@ -356,6 +356,35 @@ def test_fused_bn_backward_in_dgrad_matches_separate_kernels(monkeypatch):
     assert cos > 0.98, cos
 
 
+def test_sm_partitioned_backward_matches_default(monkeypatch):
+    """BASI_SM_MAIN / BASI_SM_WGRAD (opt-in, basi_set_sm_budget): the backward main chain sizes its grids for fewer SMs
+    and every weight gradient launches a fixed number of CTAs.  Only the launch geometry changes: same loss, gradients
+    equal up to the summation order of the split weight-gradient reductions; the budget is restored afterwards."""
+    from basi_b200 import _lib
+    variant, nseg, S, F, B, classes = "2AddClass", 1, 320, 32, 2, 21
+    params, img, clicks, data, lab, cls, sigma = _setup(variant, nseg, S, F, B, classes)
+    res = {}
+    for mode in ("off", "on"):
+        monkeypatch.setenv("BASI_EXPERIMENTS", "1")
+        if mode == "on":
+            monkeypatch.setenv("BASI_SM_MAIN", "100")
+            monkeypatch.setenv("BASI_SM_WGRAD", "24")
+        eng = _engine(variant, nseg, S, F, B, classes, "bf16", dict(kind="bce", pos_weight=3.0, class_weight=0.2))
+        assert eng.sm_main == (100 if mode == "on" else 0)
+        eng.set_params(params)
+        eng.feed(data, lab, cls, 5e-3)
+        eng.step_device()
+        torch.cuda.synchronize()
+        res[mode] = (eng.losses()[0], eng.grads_flat.double().cpu().numpy())
+        assert _lib.load().basi_sm_count() >= 100
+        del eng
+        torch.cuda.empty_cache()
+    assert abs(res["off"][0] - res["on"][0]) <= 1e-6 * abs(res["off"][0])
+    a, b = res["off"][1], res["on"][1]
+    rel = float(np.linalg.norm(a - b) / np.linalg.norm(a))
+    assert rel < 5e-2, rel      # (measured 3e-3 at batch 16: reordered fp32 atomics flip single 16-bit roundings)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # F1: variant B (slim vgg_16 trunk + click-gated attention cascade, back/90AttentionSingle2)
 # ---------------------------------------------------------------------------------------------------------------
@@ -645,6 +674,43 @@ def test_cascade_train_runner_steps_at_bench_shape():
     assert r["raw_output_segment"].shape == (4, 40, 40, 4) and r["pred_segment"].shape == (4, 40, 40, 1)
     assert r["raw_output_classes"].shape == (4, 21)
     assert 0.0 <= r["raw_output_segment"].min() and r["raw_output_segment"].max() <= 1.0     # sigmoid outputs
+
+
+def test_prefetched_steps_equal_directly_fed_steps():
+    """Train.run_step(..., prefetch=next_batch) (copy-stream H2D into staging buffers + device-side commit, one
+    synchronised read-back) returns exactly what the synchronous feed path returns, step by step, and Train.train()
+    (which prefetches) ends with the same parameters as a loop of plain run_step calls."""
+    from basi_b200.BAISRunnerTrain import Train
+    import tempfile
+    runs = []
+    for mode in ("direct", "prefetch", "train"):
+        tr = Train(batch_size=2, last_pool_size=8, input_size=[64, 64], log_dir=tempfile.mkdtemp(), variant="2AddClass",
+                   precision="f32", learning_rate=1e-2, seed=3, filter_number=16)
+        batches = [tr.data_reader.next_batch() for _ in range(4)]
+        outs = []
+        if mode == "train":
+            tr.data_reader.next_batch = iter(batches).__next__        # the same four batches, in order
+            outs.append(tr.train(save_pred_freq=10 ** 9, begin_step=0, max_steps=4))
+        else:
+            for step in range(4):
+                nxt = batches[step + 1] if (mode == "prefetch" and step + 1 < 4) else None
+                outs.append(tr.run_step(step, batches[step], prefetch=nxt))
+        torch.cuda.synchronize()
+        runs.append((outs, tr.engine.params_flat.cpu().numpy().copy()))
+    (d_out, d_par), (p_out, p_par), (t_out, t_par) = runs
+    # (the first step is bit-identical; later ones differ by the fp32-atomic order of the split weight gradients)
+    assert d_out[0]["loss"] == p_out[0]["loss"]
+    assert np.array_equal(d_out[0]["raw_output_segment"], p_out[0]["raw_output_segment"])
+    assert np.array_equal(d_out[0]["pred_classes"], p_out[0]["pred_classes"])
+    # (a 2-sample batch-norm net amplifies that 1e-7 noise: 2e-5 on the loss after three steps, measured)
+    for a, b in zip(d_out, p_out):
+        assert abs(a["loss"] - b["loss"]) <= 1e-3 * abs(a["loss"]), (a["loss"], b["loss"])
+        assert _rel2(a["raw_output_segment"], b["raw_output_segment"]) < 1e-2
+        assert _rel2(a["raw_output_classes"], b["raw_output_classes"]) < 1e-2
+        assert np.mean(a["pred_segment"] == b["pred_segment"]) > 0.99
+    assert np.linalg.norm(d_par - p_par) <= 1e-3 * np.linalg.norm(d_par)
+    assert abs(t_out[0]["loss"] - d_out[-1]["loss"]) <= 1e-3 * abs(d_out[-1]["loss"])
+    assert np.linalg.norm(d_par - t_par) <= 1e-3 * np.linalg.norm(d_par)
 
 
 @pytest.mark.parametrize("prec", ["f16", "bf16"])
