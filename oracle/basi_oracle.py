@@ -9,14 +9,16 @@ reference`` legs may import it.  Nothing under ``instance-segment-basi_b200/``
 PARITY: the DATA functions (``mask_gaussian``, ``pack_input``, ``encode_labels_binary`` / ``_three`` / ``_border``,
 ``sample_click``) are PINNED bit for bit against outputs of the reference's own BAISData.py code, which is numpy + PIL
 and runs in the build container (tests/golden/make_reference_golden.py -> tests/golden/reference_data.npz ->
-tests/test_reference_golden.py).  The NETWORK ARITHMETIC is UNPINNED: it lives in TensorFlow 1.x, which is
-third-party, un-vendored and un-pinned (no requirements file; TF1 is implied by
-``tf.contrib.slim`` / ``tf.placeholder``), it cannot be imported in this
-container, and the reference ships no test, golden vector or fixture for this
-path.  The oracle therefore follows the reference's
-own call sites plus the published TF1 op semantics, and is pinned only by
-hand-computed known-answer cases and fp64 finite-difference checks
-(tests/test_oracle.py).
+tests/test_reference_golden.py).  The CONVOLUTION PADDING / STRIDE SEMANTICS (``conv2d`` with 'SAME' at stride 1 and 2 on
+even and odd inputs, explicit padding + 'VALID', the strided 1x1 convolution = subsample; ``tf_same_pad``) are PINNED
+against the numeric golden vectors of the reference's own vendored TF-slim tests (slim/nets/resnet_v1_test.py:58-153,
+extracted by tests/golden/make_slim_golden.py -> tests/golden/slim_reference_tests.json).  The REST OF THE NETWORK
+ARITHMETIC is UNPINNED: it lives in TensorFlow 1.x, which is third-party, un-vendored and un-pinned (no requirements
+file; TF1 is implied by ``tf.contrib.slim`` / ``tf.placeholder``), it cannot be imported in this container, and the
+reference ships no other numeric test, golden vector or fixture for this path.  For
+batch norm, pooling, resize, gating, the losses and SGD the oracle therefore follows the reference's own call sites
+plus the published TF1 op semantics, and is pinned only by hand-computed known-answer cases and fp64
+finite-difference checks (tests/test_oracle.py).
 
 What each function restates (paths relative to /root/reference):
 

@@ -187,3 +187,189 @@ def test_engine_annotation_feed_reproduces_reference_batch(G):
     torch.cuda.synchronize()
     assert np.array_equal(eng.label_seg.cpu().numpy().astype(np.int64), G[tag + "/step0/ann"])
     assert np.array_equal(_bits(eng.input.t.cpu().numpy()), _bits(ref))
+
+
+# ===============================================================================================================
+# Golden vectors of the reference's own (vendored TF-slim) tests for ops on the hot path:
+# tests/golden/slim_reference_tests.json, extracted by tests/golden/make_slim_golden.py from
+# slim/nets/resnet_v1_test.py:58-153 (ResnetUtilsTest: subsample, conv2d 'SAME' stride 1 / 2 on even and odd inputs,
+# conv2d_same = explicit padding + 'VALID') and slim/nets/vgg_test.py:230-333 (vgg_16 end points / variable names).
+# They pin the TF padding semantics of Network.conv (back/2AddClass/BAISPSPNet.py:118-146) -- in particular the
+# asymmetric (0 before, 1 after) 'SAME' padding of conv1_1_3x3_s2 on an even input -- and the strided 1x1 convolution
+# (= subsample) in the oracle, in the host lowering rule and in the CUDA kernels.  All values are small integers:
+# exact in float32, bfloat16 and fp16, so every comparison is bit for bit.
+# ===============================================================================================================
+@pytest.fixture(scope="module")
+def SLIM():
+    import json
+    with open(os.path.join(HERE, "golden", "slim_reference_tests.json")) as f:
+        return json.load(f)
+
+
+def _mesh(n):
+    """create_test_input(1, n, n, 1): x[h, w] = h + w (slim/nets/resnet_v1_test.py:30-53)"""
+    return (np.arange(n).reshape(n, 1) + np.arange(n).reshape(1, n)).astype(np.float32)
+
+
+@pytest.mark.parametrize("case", ["conv2d_same_even", "conv2d_same_odd"])
+def test_oracle_conv_padding_semantics_equal_slim_golden(SLIM, case):
+    import torch
+    g = SLIM["resnet_utils"][case]
+    n = g["n"]
+    x = torch.from_numpy(_mesh(n)).view(1, 1, n, n)
+    w = torch.from_numpy(_mesh(3)).view(3, 3, 1, 1)                       # HWIO
+    want = {k: np.asarray(g[k], np.float32) for k in ("y1_expected", "y2_expected", "y3_expected", "y4_expected")}
+    y1 = O.conv2d(x, w, 1, "SAME")
+    assert np.array_equal(y1[0, 0].numpy(), want["y1_expected"])
+    # resnet_utils.subsample(y1, 2) == the strided 1x1 'VALID' convolution of the trunk with a unit weight
+    y2 = O.conv2d(y1, torch.ones(1, 1, 1, 1), 2, "VALID")
+    assert np.array_equal(y2[0, 0].numpy(), want["y2_expected"])
+    assert np.array_equal(y1[0, 0, ::2, ::2].numpy(), want["y2_expected"])
+    # conv2d_same(stride 2) = pad (k-1)//2 on both sides, then 'VALID': Network.zero_padding(1) + conv(..., 'VALID')
+    y3 = O.conv2d(x, w, 2, 1)
+    assert np.array_equal(y3[0, 0].numpy(), want["y3_expected"])
+    # tf 'SAME' with stride 2: (0, 1) padding on the even input, (1, 1) on the odd one
+    y4 = O.conv2d(x, w, 2, "SAME")
+    assert np.array_equal(y4[0, 0].numpy(), want["y4_expected"])
+    if n % 2 == 0:
+        assert not np.array_equal(want["y4_expected"], want["y2_expected"])       # the trap is real on even inputs
+        assert O.tf_same_pad(n, 3, 2) == (0, 1)
+    else:
+        assert O.tf_same_pad(n, 3, 2) == (1, 1)
+
+
+def test_oracle_subsample_equals_slim_golden(SLIM):
+    for key in ("subsample_3x3", "subsample_4x4"):
+        g = SLIM["resnet_utils"][key]
+        x = np.arange(g["range"], dtype=np.float32).reshape(g["shape"])
+        got = x[:, ::g["factor"], ::g["factor"], :]
+        assert got.shape == tuple(g["expected_shape"])
+        assert np.array_equal(got.reshape(-1), np.asarray(g["expected"], np.float32))
+
+
+def test_host_same_padding_rule_equals_oracle_and_slim_golden(SLIM):
+    """engine._same_pad_before is what the lowering writes into basi_conv_desc.pad_t / pad_l"""
+    from basi_b200.engine import _same_pad_before
+    assert _same_pad_before(SLIM["resnet_utils"]["conv2d_same_even"]["n"], 3, 2, 1) == 0
+    assert _same_pad_before(SLIM["resnet_utils"]["conv2d_same_odd"]["n"], 3, 2, 1) == 1
+    for n in range(1, 70):
+        for k in (1, 2, 3, 5, 7):
+            for s in (1, 2, 3, 5):
+                for d in (1, 2, 4):
+                    assert _same_pad_before(n, k, s, d) == O.tf_same_pad(n, k, s, d)[0], (n, k, s, d)
+
+
+def test_variant_b_trunk_names_equal_slim_vgg16_test_lists(SLIM):
+    """The vgg_16 trunk of variant B (slim/nets/vgg.py:187-196 up to conv5_3) creates exactly the convolution
+    variables and end points slim's own vgg_16 tests expect (everything before pool5 / fc6)."""
+    from basi_b200.BAISNet import LinkNet
+    from basi_b200.BAISPSPNet import Placeholder
+    net = LinkNet(Placeholder((None, 64, 64, 3)), Placeholder((None, 64, 64, 1)), True, 21)
+    net.build()
+    want_vars = [v for v in SLIM["vgg_16"]["model_variables"] if "/fc" not in v]
+    got_vars = [v for v in net.variables if v.startswith("vgg_16/")]
+    assert len(want_vars) == 26 and set(got_vars) == set(want_vars)
+    want_eps = [e for e in SLIM["vgg_16"]["end_points"] if "/fc" not in e and not e.endswith("pool5")]
+    got_eps = [e for e in net.layers if e.startswith("vgg_16/")]
+    assert set(got_eps) == set(want_eps), set(got_eps) ^ set(want_eps)
+    # shapes: five stride-2 stages minus pool5 -> conv5_3 at 1/16 resolution, slim channel widths
+    assert tuple(net.layers["vgg_16/conv5/conv5_3"].shape) == (4, 4, 512)
+    assert tuple(net.layers["vgg_16/pool1"].shape) == (32, 32, 64)
+
+
+# ------------------------------------------------------------------ GPU: the CUDA kernels against the same vectors
+def _embed(a_hw, c, n=1):
+    """[H, W] -> NHWC with the values in channel 0 and zeros elsewhere"""
+    out = np.zeros((n,) + a_hw.shape + (c,), np.float32)
+    out[..., 0] = a_hw
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f32", "h16"])
+@pytest.mark.parametrize("case", ["conv2d_same_even", "conv2d_same_odd"])
+def test_cuda_conv_kernels_equal_slim_golden(SLIM, case, dtype):
+    """basi_conv_fprop (the CUDA-core path every shape can take) for y1 / y3 / y4, basi_subsample_fwd for y2 and the
+    conv1_1 stem kernel (basi_stem_fprop_stats: 4 -> 32 channels, 'SAME' stride 2) for y4, through the C ABI."""
+    import torch
+    from gpu_util import act, call, dev, empty_act, host
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    g = SLIM["resnet_utils"][case]
+    n, n2 = g["n"], g["n2"]
+    want = {k: np.asarray(g[k], np.float32) for k in ("y1_expected", "y2_expected", "y3_expected", "y4_expected")}
+    td = torch.float32 if dtype == "f32" else torch.bfloat16        # (dtype code 1 = the build's 16-bit type)
+    cin, cout = 8, 8
+    x = _embed(_mesh(n), cin)
+    w = np.zeros((3, 3, cin, cout), np.float32)
+    w[:, :, 0, 0] = _mesh(3)
+    xa, wd = act(x, td), dev(w)
+
+    def conv(stride, pt, pl, out_n):
+        ya = empty_act((1, out_n, out_n, cout), td, fill=7.0)
+        desc = ConvDesc(3, 3, stride, 1, pt, pl, 0)
+        call("basi_conv_fprop", C.byref(desc), xa.ref, wd.data_ptr(), None, ya.ref)
+        y = host(ya)
+        assert not np.any(y[..., 1:])                               # the other output channels have zero weights
+        return y[0, :, :, 0], ya
+
+    y1, y1a = conv(1, 1, 1, n)
+    assert np.array_equal(y1, want["y1_expected"])
+    y2a = empty_act((1, n2, n2, cout), td, fill=7.0)
+    call("basi_subsample_fwd", y1a.ref, 2, y2a.ref)
+    assert np.array_equal(host(y2a)[0, :, :, 0], want["y2_expected"])
+    y3, _ = conv(2, 1, 1, n2)                                       # explicit padding 1, then 'VALID'
+    assert np.array_equal(y3, want["y3_expected"])
+    pad = O.tf_same_pad(n, 3, 2)[0]
+    y4, _ = conv(2, pad, pad, n2)                                   # tf 'SAME', stride 2
+    assert np.array_equal(y4, want["y4_expected"])
+    # the stem kernel: float32 NHWC4 input, 32 output channels, fused batch-norm statistics
+    x4 = act(_embed(_mesh(n), 4))
+    w4 = np.zeros((3, 3, 4, 32), np.float32)
+    w4[:, :, 0, 0] = _mesh(3)
+    ys = empty_act((1, n2, n2, 32), td, fill=7.0)
+    desc = ConvDesc(3, 3, 2, 1, pad, pad, 0)
+    if _lib.load().basi_stem_fprop_stats_supported(C.byref(desc), x4.ref, ys.ref) == 1:
+        sums = torch.zeros(2 * 32 * 8, dtype=torch.float64, device="cuda:0")
+        bnp = torch.zeros(4 * 32, device="cuda:0")
+        cnt = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+        gd, bd = dev(np.ones(32, np.float32)), dev(np.zeros(32, np.float32))
+        call("basi_stem_fprop_stats", C.byref(desc), x4.ref, dev(w4).data_ptr(), ys.ref, sums.data_ptr(), gd.data_ptr(),
+             bd.data_ptr(), C.c_double(n2 * n2), C.c_float(1e-5), bnp.data_ptr(), cnt.data_ptr())
+        assert np.array_equal(host(ys)[0, :, :, 0], want["y4_expected"])
+        assert abs(float(host(bnp)[0]) - float(want["y4_expected"].mean())) < 1e-4      # fused mean of channel 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["conv2d_same_even", "conv2d_same_odd"])
+def test_tcgen05_conv_equals_slim_golden(SLIM, case):
+    """The tensor-core implicit-GEMM plan (TMA zero fill is the padding) on the same vectors: 3x3 stride 1 'SAME' with
+    the golden image in channel 0 of a 64-channel tensor.  Small integers: exact in the 16-bit operands."""
+    import torch
+    from gpu_util import act, call, empty_act, host, stream
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    g = SLIM["resnet_utils"][case]
+    n = g["n"]
+    cin = cout = 64
+    x = _embed(_mesh(n), cin)
+    w = np.zeros((3, 3, cin, cout), np.float32)
+    w[:, :, 0, 0] = _mesh(3)
+    xa, ya = act(x, torch.bfloat16), empty_act((1, n, n, cout), torch.bfloat16, fill=7.0)
+    desc = ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    lib = _lib.load()
+    if lib.basi_tc_conv_supported(_lib.TC_FPROP, C.byref(desc), xa.ref, ya.ref) != 1:
+        pytest.skip("shape not on the tcgen05 path")
+    wt = torch.from_numpy(w).to("cuda:0")
+    w_oi = torch.zeros(9 * cout * cin, dtype=torch.bfloat16, device="cuda:0")
+    w_io = torch.zeros(9 * cin * cout, dtype=torch.bfloat16, device="cuda:0")
+    call("basi_tc_pack_weights", wt.data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), 9, cin, cout)
+    h = C.c_void_p()
+    _lib.call("basi_tc_conv_create", _lib.TC_FPROP, C.byref(desc), xa.ref, ya.ref, w_oi.data_ptr(), None, 0, C.byref(h))
+    try:
+        assert lib.basi_tc_conv_run(h, stream()) == 0
+        y = host(ya)
+    finally:
+        lib.basi_tc_conv_destroy(h)
+    assert np.array_equal(y[0, :, :, 0], np.asarray(g["y1_expected"], np.float32))
+    assert not np.any(y[..., 1:])
