@@ -373,3 +373,71 @@ def test_tcgen05_conv_equals_slim_golden(SLIM, case):
         lib.basi_tc_conv_destroy(h)
     assert np.array_equal(y[0, :, :, 0], np.asarray(g["y1_expected"], np.float32))
     assert not np.any(y[..., 1:])
+
+
+# ------------------------------------------------------------------ the reference's own PROPERTY test of the atrous path
+# slim/nets/resnet_v1_test.py:197-244 (testAtrousValuesBottleneck, 30 x 31 input: one odd and one even dimension):
+# "dense feature extraction by atrous convolution followed by subsampling gives identical results to feature
+# extraction at the nominal stride".  Restated on the primitives of this path (A5: zero_padding(d) + atrous conv d,
+# back/2AddClass/BAISPSPNet.py:135-146): subsample(atrous_d(x), d) == conv_1(subsample(x, d)) with shared weights.
+@pytest.mark.parametrize("rate", [2, 4])
+def test_oracle_atrous_then_subsample_equals_nominal_stride(rate):
+    import torch
+    rng = np.random.RandomState(rate)
+    x = torch.from_numpy(rng.uniform(-1, 1, (2, 6, 30, 31))).double()
+    w = torch.from_numpy(rng.uniform(-1, 1, (3, 3, 6, 5))).double()
+    dense = O.conv2d(x, w, 1, rate, rate)[:, :, ::rate, ::rate]
+    nominal = O.conv2d(x[:, :, ::rate, ::rate], w, 1, 1, 1)
+    assert dense.shape == nominal.shape
+    assert float((dense - nominal).abs().max()) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rate,ch,path", [(2, 16, "simt"), (4, 16, "simt"), (2, 128, "tc"), (4, 64, "tc")])
+def test_cuda_atrous_then_subsample_equals_nominal_stride(rate, ch, path):
+    """The same property through the C ABI: CUDA-core fp32 convolution and the tcgen05 plan (TMA zero fill = the
+    zero_padding(d) of the reference).  Same products in the same k order for every output pixel: bit for bit."""
+    import torch
+    from gpu_util import act, bf16_round, call, dev, empty_act, host, stream
+    from basi_b200 import _lib
+    from basi_b200._lib import ConvDesc
+    rng = np.random.RandomState(10 * rate + ch)
+    B, H, W = 2, 30, 31
+    x = rng.uniform(-1, 1, (B, H, W, ch)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (3, 3, ch, ch)) / np.sqrt(9 * ch)).astype(np.float32)
+    td = torch.float32 if path == "simt" else torch.bfloat16
+    if path == "tc":
+        x, w = bf16_round(x), bf16_round(w)
+    xs = np.ascontiguousarray(x[:, ::rate, ::rate, :])
+    hs, ws = xs.shape[1], xs.shape[2]
+    lib = _lib.load()
+
+    def run(xin, d, oh, ow):
+        xa, ya = act(xin, td), empty_act((B, oh, ow, ch), td, fill=7.0)
+        desc = ConvDesc(3, 3, 1, d, d, d, 0)
+        if path == "simt":
+            call("basi_conv_fprop", C.byref(desc), xa.ref, dev(w).data_ptr(), None, ya.ref)
+            return host(ya)
+        if lib.basi_tc_conv_supported(_lib.TC_FPROP, C.byref(desc), xa.ref, ya.ref) != 1:
+            pytest.skip("shape not on the tcgen05 path")
+        w_oi = torch.zeros(9 * ch * ch, dtype=td, device="cuda:0")
+        w_io = torch.zeros(9 * ch * ch, dtype=td, device="cuda:0")
+        call("basi_tc_pack_weights", dev(w).data_ptr(), w_io.data_ptr(), w_oi.data_ptr(), 9, ch, ch)
+        h = C.c_void_p()
+        _lib.call("basi_tc_conv_create", _lib.TC_FPROP, C.byref(desc), xa.ref, ya.ref, w_oi.data_ptr(), None, 0,
+                  C.byref(h))
+        try:
+            assert lib.basi_tc_conv_run(h, stream()) == 0
+            return host(ya)
+        finally:
+            lib.basi_tc_conv_destroy(h)
+
+    dense = run(x, rate, H, W)[:, ::rate, ::rate, :]
+    nominal = run(xs, 1, hs, ws)
+    assert dense.shape == nominal.shape
+    assert np.array_equal(dense, nominal)
+    # and both equal the oracle (float64) within the storage precision
+    import torch as _t
+    ref = O.conv2d(_t.from_numpy(xs).permute(0, 3, 1, 2).double(), _t.from_numpy(w).double(), 1, 1, 1)
+    err = np.abs(nominal - ref.permute(0, 2, 3, 1).numpy()).max()
+    assert err < (1e-5 if path == "simt" else 2e-2), err
