@@ -77,7 +77,10 @@ class DataParallel(object):
         self.bucket_bytes = int(bucket_bytes)
         if os.environ.get("BASI_EXPERIMENTS") == "1" and os.environ.get("BASI_DP_BUCKET_MB"):
             self.bucket_bytes = int(float(os.environ["BASI_DP_BUCKET_MB"]) * (1 << 20))     # experiment: bucket size
-        self.comm_stream = torch.cuda.Stream(self.device) if backend == "nccl" else None
+        # (experiment BASI_DP_COMM_PRIORITY=1: the all-reduce stream at the highest priority, so the few NCCL CTAs win
+        # the free SM slots at the kernel boundaries of the persistent backward kernels)
+        prio = -1 if (os.environ.get("BASI_EXPERIMENTS") == "1" and os.environ.get("BASI_DP_COMM_PRIORITY") == "1") else 0
+        self.comm_stream = torch.cuda.Stream(self.device, priority=prio) if backend == "nccl" else None
         self._plan = None
         # gradient exchange: "nccl" (default: bucketed NCCL all-reduce overlapped with the backward pass) or "p2p"
         # (BASI_DP_EXCHANGE=p2p: our peer-memory all-reduce after the backward pass; measured 0.36 ms of exposed time
