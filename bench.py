@@ -523,7 +523,10 @@ def measure(args, wl_name, dp, device, dev_index, rank, world, want_profile):
                         "frac_of_sustained_peak": ach_g / pk["tensor_sustained"], "frac_of_burst_peak": ach_g / pk["tensor"],
                         "step_ms_with": round(mg["ms_full"], 3), "step_ms_without": round(mg["ms_without"], 3),
                         "how": "step graph re-captured without the %d launches of this group; marginal time inside "
-                               "the real graph (PDL + side streams), tools/ablate_step.py" % mg["n"]}
+                               "the real graph (PDL + side streams), tools/ablate_step.py; work of other streams that "
+                               "was hidden behind these launches becomes exposed in the ablated step, so this is a "
+                               "LOWER bound of the group's time (cfg3: the groups are additive, profiles/ablation_r02.txt)"
+                               % mg["n"]}
             except Exception as e:      # explanatory number only: never fail the bench line for it
                 roof["in_graph"] = {"error": str(e)[:200]}
         res["roofline"] = roof
