@@ -491,16 +491,95 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const TA* __restrict__ 
   }
 }
 
-__global__ void skinny_reduce_bias_act_kernel(const float* __restrict__ part, int parts, float* __restrict__ y,
-                                              const float* __restrict__ bias, int M, int N, int relu) {
+// Vectorised forward GEMV for N % 4 == 0 (class_attention_conv: a 25600 x 512 float32 matrix, 52 MB, streamed once).
+// A thread owns FOUR consecutive columns and keeps eight 128-bit weight loads in flight; a block (128 threads = 512
+// columns) owns one contiguous run of at most SK4_KB k rows whose 16 x run activations are staged in shared memory ONCE,
+// so nothing but the weight stream is on the critical path (the scalar kernel above stalled at a barrier + a dependent
+// activation load every 64 rows and had 4 bytes per load in flight: 1.2 TB/s).
+constexpr int SK4_KB = 192;
+
+template <typename TA>
+__global__ void __launch_bounds__(128) skinny_fwd4_kernel(const TA* __restrict__ a, int64_t lda,
+                                                          const float* __restrict__ w, float* __restrict__ y, int M,
+                                                          int K, int N, int k_per_block, float* __restrict__ part) {
   pdl_prologue();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
+  __shared__ __align__(16) float sa[16][SK4_KB + 4];
+  const int n4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int kbeg = blockIdx.y * k_per_block;
+  const int kend = min(K, kbeg + k_per_block);
+  const int kn = kend - kbeg;               // 1 .. SK4_KB (the launch geometry leaves no empty block)
+  const int kpad = (kn + 7) & ~7;           // rows kn .. kpad-1 are multiplied by zero-filled activations
+  for (int mb = 0; mb < M; mb += 16) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * kpad; i += 128) {
+      const int m = i / kpad, k = i - m * kpad;
+      sa[m][k] = (mb + m < M && k < kn) ? to_f32(a[(int64_t)(mb + m) * lda + kbeg + k]) : 0.f;
+    }
+    __syncthreads();
+    if (n4 >= N) continue;
+    float4 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kpad; k += 8) {
+      float4 wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = min(kbeg + k + j, kend - 1);
+        wv[j] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)kk * N + n4));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&sa[i][k]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&sa[i][k + 4]);
+        float4 t = acc[i];
+        t.x = fmaf(a0.x, wv[0].x, fmaf(a0.y, wv[1].x, fmaf(a0.z, wv[2].x, fmaf(a0.w, wv[3].x, t.x))));
+        t.y = fmaf(a0.x, wv[0].y, fmaf(a0.y, wv[1].y, fmaf(a0.z, wv[2].y, fmaf(a0.w, wv[3].y, t.y))));
+        t.z = fmaf(a0.x, wv[0].z, fmaf(a0.y, wv[1].z, fmaf(a0.z, wv[2].z, fmaf(a0.w, wv[3].z, t.z))));
+        t.w = fmaf(a0.x, wv[0].w, fmaf(a0.y, wv[1].w, fmaf(a0.z, wv[2].w, fmaf(a0.w, wv[3].w, t.w))));
+        t.x = fmaf(a1.x, wv[4].x, fmaf(a1.y, wv[5].x, fmaf(a1.z, wv[6].x, fmaf(a1.w, wv[7].x, t.x))));
+        t.y = fmaf(a1.x, wv[4].y, fmaf(a1.y, wv[5].y, fmaf(a1.z, wv[6].y, fmaf(a1.w, wv[7].y, t.y))));
+        t.z = fmaf(a1.x, wv[4].z, fmaf(a1.y, wv[5].z, fmaf(a1.z, wv[6].z, fmaf(a1.w, wv[7].z, t.z))));
+        t.w = fmaf(a1.x, wv[4].w, fmaf(a1.y, wv[5].w, fmaf(a1.z, wv[6].w, fmaf(a1.w, wv[7].w, t.w))));
+        acc[i] = t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (mb + i < M) {
+        if (part) {
+          *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.y * M + mb + i) * N + n4) = acc[i];
+        } else {
+          float* yp = y + (int64_t)(mb + i) * N + n4;
+          atomicAdd(yp, acc[i].x); atomicAdd(yp + 1, acc[i].y); atomicAdd(yp + 2, acc[i].z); atomicAdd(yp + 3, acc[i].w);
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) skinny_reduce_bias_act_kernel(const float* __restrict__ part, int parts,
+                                                                     float* __restrict__ y,
+                                                                     const float* __restrict__ bias, int M, int N,
+                                                                     int relu) {
+  // block = 32 consecutive outputs x 8 groups of partial sums: group g adds the slices g, g + 8, ... in order, the eight
+  // group sums are added in order -- a fixed summation tree (bit-reproducible) with 256 blocks of loads in flight
+  // (one thread per output walking all ~300 slices serially made this 8 KB reduction a 35 us kernel)
+  pdl_prologue();
+  __shared__ float sm[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   float v = 0.f;
-#pragma unroll 8
-  for (int p = 0; p < parts; ++p) v += part[(int64_t)p * M * N + i];      // (fixed order: bit-reproducible)
-  v += bias ? bias[i % N] : 0.f;
-  y[i] = relu ? fmaxf(v, 0.f) : v;
+  if (i < M * N) {
+#pragma unroll 4
+    for (int p = ty; p < parts; p += 8) v += part[(int64_t)p * M * N + i];
+  }
+  sm[ty][tx] = v;
+  __syncthreads();
+  if (ty == 0 && i < M * N) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) v += sm[g][tx];
+    v += bias ? bias[i % N] : 0.f;
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
 }
 
 __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int M, int N, int relu) {
@@ -534,9 +613,71 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
   // two FMAs, and the 32 partial sums (2 k x 16 m) are reduced across the lanes with one 31-shuffle transpose-reduce
   pdl_prologue();
   extern __shared__ __align__(16) float sdy[];  // [M][N]
-  for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
+  if (((M * N) & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    for (int i = threadIdx.x * 4; i < M * N; i += blockDim.x * 4)
+      *reinterpret_cast<float4*>(sdy + i) = __ldg(reinterpret_cast<const float4*>(dy + i));
+  } else {
+    for (int i = threadIdx.x; i < M * N; i += blockDim.x) sdy[i] = dy[i];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if ((N & 127) == 0 && N <= 512) {
+    // Software-pipelined path (class_attention_conv, N = 512): the 2 x N weights of the NEXT pair of k rows are loaded
+    // (up to eight 128-bit loads per lane) before the current pair is multiplied, reduced and stored, so the weight
+    // stream never waits for the shuffle reduction.  The grid is two blocks per SM (one wave): every warp walks
+    // several pairs and the shared-memory copy of dy is made 2 x SMs times, not K / 16 times.
+    const int ns = N >> 7;
+    const int kstride = gridDim.x * 16;
+    float4 wa[4], wb[4];
+    int k = (blockIdx.x * 8 + wid) * 2;
+    auto load_pair = [&](int kk, float4 (&xa)[4], float4 (&xb)[4]) {
+      const float* w0 = w + (int64_t)kk * N + lane * 4;
+      const float* w1 = w + (int64_t)(kk + 1 < K ? kk + 1 : kk) * N + lane * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < ns) {
+          xa[q] = __ldg(reinterpret_cast<const float4*>(w0 + q * 128));
+          xb[q] = __ldg(reinterpret_cast<const float4*>(w1 + q * 128));
+        }
+    };
+    if (k < K) load_pair(k, wa, wb);
+    for (; k < K; k += kstride) {
+      float4 na[4], nb[4];
+      if (k + kstride < K) load_pair(k + kstride, na, nb);
+      const bool two = k + 1 < K;
+      for (int mb = 0; mb < M; mb += 16) {
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < ns) {
+            const int n = q * 128 + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (mb + i < M) g = *reinterpret_cast<const float4*>(sdy + (mb + i) * N + n);
+              acc[i] = fmaf(g.x, wa[q].x, fmaf(g.y, wa[q].y, fmaf(g.z, wa[q].z, fmaf(g.w, wa[q].w, acc[i]))));
+              acc[16 + i] = fmaf(g.x, wb[q].x, fmaf(g.y, wb[q].y, fmaf(g.z, wb[q].z, fmaf(g.w, wb[q].w, acc[16 + i]))));
+            }
+          }
+        warp_transpose_sums(acc, lane);
+        const int kk = k + (lane >> 4), m = mb + (lane & 15);
+        if (m < M && kk < K && (two || lane < 16)) {
+          TA* dst = da + (int64_t)m * lda + kk;
+          float v = acc[0];
+          if (acc_flag) v += to_f32(*dst);
+          *dst = from_f32<TA>(v);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        wa[q] = na[q];
+        wb[q] = nb[q];
+      }
+    }
+    return;
+  }
   for (int k = (blockIdx.x * 8 + wid) * 2; k < K; k += gridDim.x * 16) {
     const bool two = k + 1 < K;
     const float* w0 = w + (int64_t)k * N;
@@ -579,6 +720,76 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
         *dst = from_f32<TA>(v);
       }
     }
+  }
+}
+
+// Register-resident variant for N in {128, 256, 512} and at most 16 batch rows (class_attention_conv).  In the kernel
+// above every weight is multiplied with 16 dy values read from SHARED memory (64 bytes of shared-memory traffic per
+// 4-byte weight: the kernel is bound by the shared-memory pipe at ~1.3 TB/s of weight stream).  Here a warp owns ONE
+// group of 128 columns for the whole kernel, so its 16 x 4 dy values live in registers; the inner loop is a 128-bit
+// weight load + 64 FMAs per row, the next iteration's eight rows are loaded before the current eight are multiplied,
+// and the partial dot products of the NQ column groups are combined through a 4 KB shared-memory exchange once per
+// block iteration (8 * 8 / NQ rows).  The combine step writes runs of consecutive k per batch row.
+template <typename TA, int NQ>
+__global__ void __launch_bounds__(256, 1) skinny_dgrad_reg_kernel(const float* __restrict__ dy,
+                                                                  const float* __restrict__ w, TA* __restrict__ da,
+                                                                  int64_t lda, int M, int K, int N, int acc_flag) {
+  pdl_prologue();
+  constexpr int WG = 8 / NQ;            // warps per column group = row sub-blocks per iteration
+  constexpr int RB = WG * 8;            // k rows per block iteration
+  __shared__ float part_s[2][8][4][32]; // [buffer][warp][row pair][lane]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = wid % NQ, rsub = wid / NQ;
+  const int col = q * 128 + lane * 4;
+  float4 g[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    g[i] = i < M ? __ldg(reinterpret_cast<const float4*>(dy + (int64_t)i * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nblk = (K + RB - 1) / RB;
+  auto load_rows = [&](int rb, float4 (&x)[8]) {
+    const int r0 = rb * RB + rsub * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = min(r0 + j, K - 1);                 // (rows past the end are computed and dropped at the store)
+      x[j] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)r * N + col));
+    }
+  };
+  float4 wv[8], wn[8];
+  int rb = blockIdx.x, it = 0;
+  if (rb < nblk) load_rows(rb, wv);
+  for (; rb < nblk; rb += gridDim.x, ++it) {
+    if (rb + (int)gridDim.x < nblk) load_rows(rb + gridDim.x, wn);
+    float (*ps)[4][32] = part_s[it & 1];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 a = wv[2 * p], b = wv[2 * p + 1];
+        acc[i] = fmaf(g[i].x, a.x, fmaf(g[i].y, a.y, fmaf(g[i].z, a.z, g[i].w * a.w)));
+        acc[16 + i] = fmaf(g[i].x, b.x, fmaf(g[i].y, b.y, fmaf(g[i].z, b.z, g[i].w * b.w)));
+      }
+      warp_transpose_sums(acc, lane);     // lane l: row 2p + l / 16, batch row l % 16, over this warp's 128 columns
+      ps[wid][p][lane] = acc[0];
+    }
+    __syncthreads();                      // (double-buffered exchange: one barrier per iteration)
+    // combine the NQ column groups; thread -> (batch row m, row r of this block iteration): consecutive threads write
+    // consecutive k of one batch row
+    for (int t = threadIdx.x; t < 16 * RB; t += 256) {
+      const int m = t / RB, r = t - m * RB;
+      const int rs = r >> 3, j = r & 7;              // row sub-block, row inside it
+      const int kk = rb * RB + r;
+      if (m < M && kk < K) {
+        float v = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < NQ; ++qq) v += ps[rs * NQ + qq][j >> 1][(j & 1) * 16 + m];
+        TA* dst = da + (int64_t)m * lda + kk;
+        if (acc_flag) v += to_f32(*dst);
+        *dst = from_f32<TA>(v);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = wn[j];
   }
 }
 
@@ -627,6 +838,64 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const TA* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (kb + j < kt) dw[(int64_t)(k0 + kb + j) * N + n] = old[j] + acc[j];
+  }
+}
+
+// Vectorised variant for N % 4 == 0 and at most 16 batch rows: a thread owns four consecutive columns, eight 128-bit
+// read-modify-writes of dw in flight (the 52 MB class_attention_conv gradient: 105 MB of traffic per step).
+template <typename TA>
+__global__ void __launch_bounds__(128) skinny_wgrad4_kernel(const TA* __restrict__ a, int64_t lda,
+                                                            const float* __restrict__ dy, float* __restrict__ dw,
+                                                            float* __restrict__ dbias, int M, int K, int N) {
+  pdl_prologue();
+  constexpr int MB = 16;
+  __shared__ __align__(16) float sa[SK_KT][MB];
+  const int n4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int k0 = blockIdx.y * SK_KT;
+  const int kt = min(SK_KT, K - k0);
+  for (int i = threadIdx.x; i < MB * SK_KT; i += 128) {
+    int m = i / SK_KT, k = i - m * SK_KT;
+    sa[k][m] = (m < M && k < kt) ? to_f32(a[(int64_t)m * lda + k0 + k]) : 0.f;
+  }
+  __syncthreads();
+  if (n4 >= N) return;
+  float4 g[MB];
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    g[m] = m < M ? __ldg(reinterpret_cast<const float4*>(dy + (int64_t)m * N + n4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bs.x += g[m].x; bs.y += g[m].y; bs.z += g[m].z; bs.w += g[m].w;
+  }
+  if (dbias && blockIdx.y == 0) {
+    dbias[n4] += bs.x; dbias[n4 + 1] += bs.y; dbias[n4 + 2] += bs.z; dbias[n4 + 3] += bs.w;
+  }
+  for (int kb = 0; kb < kt; kb += 8) {
+    float4 old[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      old[j] = kb + j < kt ? *reinterpret_cast<const float4*>(dw + (int64_t)(k0 + kb + j) * N + n4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kb + j >= kt) break;
+#pragma unroll
+      for (int m4 = 0; m4 < MB; m4 += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&sa[kb + j][m4]);
+        float4 t = acc[j];
+        t.x = fmaf(av.x, g[m4].x, fmaf(av.y, g[m4 + 1].x, fmaf(av.z, g[m4 + 2].x, fmaf(av.w, g[m4 + 3].x, t.x))));
+        t.y = fmaf(av.x, g[m4].y, fmaf(av.y, g[m4 + 1].y, fmaf(av.z, g[m4 + 2].y, fmaf(av.w, g[m4 + 3].y, t.y))));
+        t.z = fmaf(av.x, g[m4].z, fmaf(av.y, g[m4 + 1].z, fmaf(av.z, g[m4 + 2].z, fmaf(av.w, g[m4 + 3].z, t.z))));
+        t.w = fmaf(av.x, g[m4].w, fmaf(av.y, g[m4 + 1].w, fmaf(av.z, g[m4 + 2].w, fmaf(av.w, g[m4 + 3].w, t.w))));
+        acc[j] = t;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (kb + j < kt)
+        *reinterpret_cast<float4*>(dw + (int64_t)(k0 + kb + j) * N + n4) =
+            make_float4(old[j].x + acc[j].x, old[j].y + acc[j].y, old[j].z + acc[j].z, old[j].w + acc[j].w);
   }
 }
 
@@ -1213,7 +1482,25 @@ int basi_skinny_supported(int M, int K, int N) {
 }
 
 // k-slab partition of the forward GEMV: about 4 blocks per SM in total; every block walks `spb` consecutive k-slabs
+static bool skinny_vec4(int N, const void* w) { return (N & 3) == 0 && (((uintptr_t)w) & 15) == 0; }
+
+// the vectorised kernel (N % 4 == 0): a block = 512 columns x one run of `kpb` (<= SK4_KB, multiple of 8) k rows,
+// about two blocks per SM
+static void skinny_fwd4_geometry(int K, int N, int* gx, int* gy, int* kpb) {
+  *gx = (N + 511) / 512;
+  int y = (2 * basi::sm_count() + *gx - 1) / *gx;
+  int k = ((K + y - 1) / y + 7) & ~7;
+  if (k > SK4_KB) k = SK4_KB;
+  if (k < 8) k = 8;
+  *kpb = k;
+  *gy = (K + k - 1) / k;
+}
+
 static void skinny_fwd_geometry(int K, int N, int* gx, int* gy, int* spb) {
+  if ((N & 3) == 0) {        // (the workspace size must not depend on pointer alignment: see basi_skinny_fwd_ws)
+    skinny_fwd4_geometry(K, N, gx, gy, spb);
+    return;
+  }
   const int nslabs = (K + SK_KT - 1) / SK_KT;
   *gx = (N + 127) / 128;
   int y = (4 * basi::sm_count() + *gx - 1) / *gx;
@@ -1235,6 +1522,9 @@ int basi_skinny_fwd_ws(const void* a, int dtype_a, int64_t lda, const float* w, 
   cudaStream_t st = (cudaStream_t)stream;
   int gx, gy, spb;
   skinny_fwd_geometry(K, N, &gx, &gy, &spb);
+  const bool vec4 = (N & 3) == 0;
+  BASI_CHECK_ARG(!vec4 || (skinny_vec4(N, w) && (!workspace || (((uintptr_t)workspace) & 15) == 0)),
+                 "skinny_fwd: weights / workspace must be 16-byte aligned when N is a multiple of 4");
   if (!workspace) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
   dim3 grid(gx, gy);
   const size_t es = dtype_a == BASI_F32 ? 4 : 2;
@@ -1244,10 +1534,13 @@ int basi_skinny_fwd_ws(const void* a, int dtype_a, int64_t lda, const float* w, 
     float* yp = y + (size_t)m0 * N;
     // every row chunk owns a [gy][mc][N] block of the workspace (the blocks add up to gy * M * N floats)
     float* pp = workspace ? workspace + (size_t)gy * m0 * N : nullptr;
-    if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb, pp);
+    if (vec4) {
+      if (dtype_a == BASI_F32) basi::launch(skinny_fwd4_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb, pp);
+      else basi::launch(skinny_fwd4_kernel<bf16>, grid, 128, 0, st, (const bf16*)ap, lda, w, yp, mc, K, N, spb, pp);
+    } else if (dtype_a == BASI_F32) basi::launch(skinny_fwd_kernel<float>, grid, 128, 0, st, (const float*)ap, lda, w, yp, mc, K, N, spb, pp);
     else basi::launch(skinny_fwd_kernel<bf16>, grid, 128, 0, st, (const bf16*)ap, lda, w, yp, mc, K, N, spb, pp);
     if (workspace) {
-      basi::launch(skinny_reduce_bias_act_kernel, (mc * N + 255) / 256, 256, 0, st, (const float*)pp, gy, yp, bias, mc, N, relu);
+      basi::launch(skinny_reduce_bias_act_kernel, (mc * N + 31) / 32, 256, 0, st, (const float*)pp, gy, yp, bias, mc, N, relu);
     }
   }
   BASI_CHECK_LAUNCH("skinny_fwd");
@@ -1269,9 +1562,26 @@ int basi_skinny_dgrad(const float* dy, const float* w, void* da, int dtype_a, in
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = skinny_rows_per_chunk(N);
   int blocks = (K + 15) / 16;
-  int cap = basi::sm_count() * 8;
+  // (the pipelined N <= 512 path keeps ~110 registers per thread: two blocks per SM are one full wave)
+  int cap = basi::sm_count() * (((N & 127) == 0 && N <= 512) ? 2 : 8);
   if (blocks > cap) blocks = cap;
   const size_t es = dtype_a == BASI_F32 ? 4 : 2;
+  if (M <= 16 && (N == 128 || N == 256 || N == 512) && (((uintptr_t)dy | (uintptr_t)w) & 15) == 0) {
+    // register-resident kernel: one block per SM, every block walks K / (RB * SMs) row blocks
+    const int nq = N / 128, rb = (8 / nq) * 8;
+    int grid = (K + rb - 1) / rb;
+    if (grid > basi::sm_count()) grid = basi::sm_count();
+#define BASI_DGRAD_REG(TT, NQ) \
+  basi::launch(skinny_dgrad_reg_kernel<TT, NQ>, grid, 256, 0, st, dy, w, (TT*)da, lda, M, K, N, accumulate)
+    if (dtype_a == BASI_F32) {
+      if (nq == 1) BASI_DGRAD_REG(float, 1); else if (nq == 2) BASI_DGRAD_REG(float, 2); else BASI_DGRAD_REG(float, 4);
+    } else {
+      if (nq == 1) BASI_DGRAD_REG(bf16, 1); else if (nq == 2) BASI_DGRAD_REG(bf16, 2); else BASI_DGRAD_REG(bf16, 4);
+    }
+#undef BASI_DGRAD_REG
+    BASI_CHECK_LAUNCH("skinny_dgrad");
+    return BASI_OK;
+  }
   for (int m0 = 0; m0 < M; m0 += rows) {
     const int mc = M - m0 < rows ? M - m0 : rows;
     const size_t smem = sizeof(float) * (size_t)mc * N;
@@ -1301,7 +1611,11 @@ int basi_skinny_wgrad(const void* a, int dtype_a, int64_t lda, const float* dy, 
     const int mc = M - m0 < 64 ? M - m0 : 64;
     const char* ap = (const char*)a + (size_t)m0 * lda * es;
     const float* dyp = dy + (size_t)m0 * N;
-    if (mc <= 16) {
+    if (mc <= 16 && skinny_vec4(N, dw) && (((uintptr_t)dyp) & 15) == 0) {
+      dim3 grid4((N + 511) / 512, (K + SK_KT - 1) / SK_KT);
+      if (dtype_a == BASI_F32) basi::launch(skinny_wgrad4_kernel<float>, grid4, 128, 0, st, (const float*)ap, lda, dyp, dw, dbias, mc, K, N);
+      else basi::launch(skinny_wgrad4_kernel<bf16>, grid4, 128, 0, st, (const bf16*)ap, lda, dyp, dw, dbias, mc, K, N);
+    } else if (mc <= 16) {
       if (dtype_a == BASI_F32) basi::launch(skinny_wgrad_kernel<float, 16>, grid, 128, 0, st, (const float*)ap, lda, dyp, dw, dbias, mc, K, N);
       else basi::launch(skinny_wgrad_kernel<bf16, 16>, grid, 128, 0, st, (const bf16*)ap, lda, dyp, dw, dbias, mc, K, N);
     } else {
