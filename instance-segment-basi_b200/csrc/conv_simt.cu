@@ -520,13 +520,17 @@ __global__ void __launch_bounds__(128) skinny_fwd4_kernel(const TA* __restrict__
     float4 acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < kpad; k += 8) {
-      float4 wv[8];
+    float4 wv[8], wn[8];
+    auto load8 = [&](int k, float4 (&x)[8]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int kk = min(kbeg + k + j, kend - 1);
-        wv[j] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)kk * N + n4));
+        x[j] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)kk * N + n4));
       }
+    };
+    load8(0, wv);
+    for (int k = 0; k < kpad; k += 8) {
+      if (k + 8 < kpad) load8(k + 8, wn);       // the next eight rows are in flight while these are multiplied
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float4 a0 = *reinterpret_cast<const float4*>(&sa[i][k]);
@@ -542,6 +546,8 @@ __global__ void __launch_bounds__(128) skinny_fwd4_kernel(const TA* __restrict__
         t.w = fmaf(a1.x, wv[4].w, fmaf(a1.y, wv[5].w, fmaf(a1.z, wv[6].w, fmaf(a1.w, wv[7].w, t.w))));
         acc[i] = t;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = wn[j];
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i)

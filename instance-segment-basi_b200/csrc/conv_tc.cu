@@ -1421,6 +1421,30 @@ __device__ __forceinline__ void pack_tile(const PackEntry& e, int blk, float (*t
     }
     return;
   }
+  if (((e.cin | e.cout) & 3) == 0 && ((reinterpret_cast<uintptr_t>(e.w) & 15) == 0) &&
+      (((reinterpret_cast<uintptr_t>(e.w_io) | reinterpret_cast<uintptr_t>(e.w_oi)) & 7) == 0)) {
+    // one 128-bit load per thread covers the whole 4 KB tile at once (the row loop below is not unrolled -- its bound
+    // is blockDim.y -- so a thread had ONE 4-byte load in flight: 1 KB per block, 1.8 TB/s for the whole refresh)
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int r = tid >> 3, c4 = (tid & 7) * 4;
+    {
+      const int ci = ci0 + r, co = co0 + c4;
+      const bool ok = ci < e.cin && co < e.cout;          // (cout % 4 == 0: the four columns are valid together)
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = __ldg(reinterpret_cast<const float4*>(e.w + base + (size_t)ci * e.cout + co));
+      tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+      if (ok)
+        *reinterpret_cast<uint2*>(e.w_io + base + (size_t)ci * e.cout + co) = make_uint2(h16_pack(v.x, v.y), h16_pack(v.z, v.w));
+    }
+    __syncthreads();
+    {
+      const int co = co0 + r, ci = ci0 + c4;              // transposed: row = output channel, four input channels
+      if (co < e.cout && ci < e.cin)
+        *reinterpret_cast<uint2*>(e.w_oi + base + (size_t)co * e.cin + ci) =
+            make_uint2(h16_pack(tile[c4][r], tile[c4 + 1][r]), h16_pack(tile[c4 + 2][r], tile[c4 + 3][r]));
+    }
+    return;
+  }
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int ci = ci0 + i, co = co0 + threadIdx.x;
     const float v = (ci < e.cin && co < e.cout) ? e.w[base + (size_t)ci * e.cout + co] : 0.f;

@@ -464,3 +464,37 @@ def test_tc_dgrad_fused_bn_backward(case, relu):
     assert rel_err(dx, dx_ref) < 2e-2, rel_err(dx, dx_ref)
     assert rel_err(host(dbet), bt_.grad.numpy()) < 1e-2
     assert rel_err(host(dgam), gt.grad.numpy()) < 1e-2
+
+
+@pytest.mark.gpu
+def test_pack_weights_multi_equals_single_layer_packing():
+    """basi_tc_pack_weights_multi (persistent grid, layer table in shared memory, 128-bit tile path for channel counts
+    that are multiples of 4, scalar path otherwise) writes bit for bit what the single-layer basi_tc_pack_weights
+    writes, for several layers of one table incl. ragged tiles, and touches nothing else."""
+    from basi_b200._lib import PackEntry
+    from gpu_util import call, dev, host
+    rng = np.random.RandomState(3)
+    layers = [(9, 128, 128), (1, 512, 128), (9, 24, 40), (1, 6, 10), (9, 64, 32), (1, 36, 100)]     # (taps, cin, cout)
+    bt = torch.bfloat16
+    ents, keep, blocks = [], [], 0
+    for taps, cin, cout in layers:
+        w = rng.uniform(-1, 1, (taps, cin, cout)).astype(np.float32)
+        wd = dev(w)
+        n = taps * cin * cout
+        bufs = [torch.full((n + 64,), 7.0, dtype=bt, device="cuda:0") for _ in range(4)]    # multi io/oi, single io/oi
+        tco, tci = -(-cout // 32), -(-cin // 32)
+        ents.append(PackEntry(wd.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), taps, cin, cout, blocks, tco, tci, 0, 0))
+        blocks += taps * tco * tci
+        call("basi_tc_pack_weights", wd.data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), taps, cin, cout)
+        keep.append((wd, bufs, n))
+    arr = (PackEntry * len(ents))(*ents)
+    table = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to("cuda:0")
+    call("basi_tc_pack_weights_multi", table.data_ptr(), len(ents), blocks)
+    for (taps, cin, cout), (wd, bufs, n) in zip(layers, keep):
+        io_m, oi_m, io_s, oi_s = [host(b) for b in bufs]
+        assert np.array_equal(io_m[:n], io_s[:n]) and np.array_equal(oi_m[:n], oi_s[:n]), (taps, cin, cout)
+        assert np.all(io_m[n:] == 7.0) and np.all(oi_m[n:] == 7.0)                            # guard band intact
+        w = host(wd)
+        want = torch.from_numpy(w).to(bt).float().numpy()
+        assert np.array_equal(io_m[:n].reshape(taps, cin, cout), want)
+        assert np.array_equal(oi_m[:n].reshape(taps, cout, cin), want.transpose(0, 2, 1))
