@@ -254,7 +254,9 @@ int basi_resize_nearest_bwd(const basi_tensor* dy, const basi_tensor* dx, int ac
 /* ---- A11: class_attention_conv (5x5 s5 on a 5x5 map) and Network.fc (:175-189) as skinny GEMMs ----
  * y[m][n] = act(sum_k a[m][k] w[k][n] + bias[n]). a may be f32/bf16 (dtype_a), y float32.  Any M (= batch): rows
  * are processed in chunks that fit the kernels' register / shared-memory budgets.  basi_skinny_supported is the
- * single predicate the host lowering asks (1 = the three entry points below accept this shape). */
+ * single predicate the host lowering asks (1 = the three entry points below accept this shape).
+ * When N is a multiple of 4 the forward runs 128-bit kernels: w (and the workspace) must then be 16-byte aligned
+ * (BASI_E_INVALID otherwise); dgrad / wgrad fall back to their scalar kernels on unaligned pointers. */
 int basi_skinny_supported(int M, int K, int N);
 int basi_skinny_fwd(const void* a, int dtype_a, int64_t lda, const float* w, const float* bias, float* y,
                     int M, int K, int N, int relu, void* stream);
