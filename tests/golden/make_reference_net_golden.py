@@ -1,0 +1,186 @@
+"""Golden vectors from the REFERENCE's own network and training code, run in the build container.
+
+TensorFlow 1.x cannot be installed here, but the reference's model definition and training graph are plain Python on
+top of ~60 `tf.*` calls.  This script puts tests/golden/tf1_shim (an EAGER float64 stand-in for exactly that API
+surface; see its docstring for what it is and is not) in front of sys.path, imports the UNMODIFIED reference modules
+from /root/reference (read-only, never copied) and calls the reference's own `Train.build_net()` -- which builds
+`PSPNet({'data': image}, ...)`, the predictions, the label resize, the losses, the poly learning rate and
+`GradientDescentOptimizer(lr).minimize(loss[, var_list])` -- on a small seeded batch.  What it records:
+
+  * every layer the reference's builder registered (`net.layers`, in creation order) with its shape and a 3-number
+    summary of its value; a few layers in full
+  * every variable the reference's code created (TF name, shape, trainable)
+  * the sequence of primitive ops the reference's code issued, with their arguments (kernel, stride, rate, padding,
+    bias / ReLU, pool windows, concat widths, ...)
+  * losses, learning rate, accuracies, logits, predictions; per-variable gradient summaries (a few gradients in full),
+    the variable list of `train_classes_op`
+
+tests/test_reference_net_golden.py then holds, to float64 round-off, oracle/basi_oracle.py (forward, losses,
+gradients, SGD) -- and the product's graph builder (layer names, shapes, variable inventory, op sequence) -- to
+these files; tests/test_gpu_net.py holds the CUDA f32 path to them.  So the STRUCTURE of the path is pinned to the
+reference's own code executed here; the primitive op semantics remain a restatement (two independent ones that agree).
+
+    python tests/golden/make_reference_net_golden.py [snapshot ...]
+
+/root/reference does not exist on the GPU box; only this script reads it.
+"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+
+import tensorflow as tf                                   # noqa: E402  (the shim)
+from ref_net_common import make_inputs, param_value, summary   # noqa: E402
+
+REF_MODULES = ("BAISData", "BAISPSPNet", "BAISNet", "BAISTools", "BAISRunnerTrain", "nets", "nets.nets_factory")
+
+# what the reference's Train.__init__ would set before calling build_net (shrunk: S=80, F=8, B=2)
+S, F, B = 80, 8, 2
+SNAPSHOTS = {
+    "2AddClass": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=21, num_segment=1, ratio=8,
+                                 last_pool_size=S // 8, filter_number=F, learning_rate=5e-3, num_steps=500001),
+                      label_values=2, label_dtype="float", seg="conv6_n", fc="class_attention_fc", step=1234,
+                      ret=("image_placeholder", "label_segment_placeholder", "label_classes_placeholder",
+                           "raw_output_segment", "raw_output_classes", "pred_segment", "pred_classes",
+                           "loss_segment", "loss_classes", "loss", "accuracy_0", "accuracy_1", "accuracy_classes",
+                           "step_ph", "train_op", "train_classes_op", "learning_rate")),
+    "4BorderClass": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=21, num_segment=4, ratio=8,
+                                    last_pool_size=S // 8, filter_number=F, learning_rate=5e-3, num_steps=500001),
+                         label_values=4, label_dtype="int", seg="conv6_n_4", fc="class_attention_fc", step=77,
+                         ret=("image_placeholder", "label_segment_placeholder", "label_classes_placeholder",
+                              "raw_output_segment", "raw_output_classes", "pred_segment", "pred_classes",
+                              "loss_segment", "loss_classes", "loss", "accuracy_segment", "accuracy_classes",
+                              "step_ph", "train_op", "train_classes_op", "learning_rate")),
+    "5COCO": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=81, num_segment=3, ratio=8,
+                             attention_class=2, last_pool_size=S // 8, filter_number=F, learning_rate=5e-3,
+                             num_steps=1000001),
+                  label_values=3, label_dtype="int", seg="conv6_n_3_coco", fc="class_attention_fc_coco", step=500000,
+                  ret=("image_placeholder", "label_segment_placeholder", "label_classes_placeholder",
+                       "raw_output_segment", "raw_output_classes", "pred_segment", "pred_classes",
+                       "loss_segment", "loss_classes", "loss", "accuracy_segment", "accuracy_classes",
+                       "step_ph", "train_op", "train_classes_op", "learning_rate")),
+}
+FULL_LAYERS = ("conv1_1_3x3_s2_bn_relu", "conv5_3_pool3_interp", "conv5_4_bn", "class_attention_multiply",
+               "class_attention_pool", "class_attention_squeeze")
+FULL_GRADS = ("conv1_1_3x3_s2_n/weights", "conv1_1_3x3_s2_bn/conv1_1_3x3_s2_bn/gamma", "conv3_1_1x1_proj/weights",
+              "conv4_7_3x3_bn/conv4_7_3x3_bn/beta", "conv5_3_pool6_conv/weights", "conv5_4_bn/conv5_4_bn/gamma")
+
+
+def stub_missing_data_dependencies():
+    """The 5COCO reader imports skimage / pycocotools at module level; neither is installed here and neither is on
+    the path (the reader is not run): empty stand-in modules let `from BAISData import Data, COCOData` succeed."""
+    import types
+    for name in ("skimage", "skimage.io", "pycocotools", "pycocotools.coco", "pycocotools.mask"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            m = types.ModuleType(name)
+            m.COCO = None
+            sys.modules[name] = m
+            if "." in name:
+                setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
+
+
+def import_reference(snapshot):
+    """Import the snapshot's BAISRunnerTrain from /root/reference with the shim as `tensorflow`."""
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m.startswith("nets."):
+            del sys.modules[m]
+    d = os.path.join(REF, "back", snapshot) if snapshot else REF
+    sys.path.insert(0, d)
+    try:
+        mod = importlib.import_module("BAISRunnerTrain")
+    finally:
+        sys.path.remove(d)
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(d)), mod.__file__
+    return mod
+
+
+def val(x):
+    return x.t.detach().numpy() if isinstance(x, tf.Tensor) else np.asarray(x)
+
+
+def run_pspnet_snapshot(snapshot, cfg):
+    mod = import_reference(snapshot)
+    captured = []
+    ref_net_cls = mod.PSPNet
+
+    class Recording(ref_net_cls):                          # keeps a handle on the net build_net creates locally
+        def __init__(self, *a, **k):
+            ref_net_cls.__init__(self, *a, **k)
+            captured.append(self)
+            self.ops_issued = len(tf.shim_state().trace)   # what follows in the trace is build_net's loss code
+
+    mod.PSPNet = Recording
+    data, lab, cls = make_inputs(B, S, seed=11, n_label_values=cfg["label_values"],
+                                 num_classes=cfg["attrs"]["num_classes"])
+    lab_feed = lab.astype(np.float32) if cfg["label_dtype"] == "float" else lab
+    tf.shim_reset(param_value, [data, lab_feed, cls, np.float32(cfg["step"])])
+
+    tr = mod.Train.__new__(mod.Train)                      # no __init__: that one opens sessions / readers / writers
+    for k, v in cfg["attrs"].items():
+        setattr(tr, k, v)
+    ret = dict(zip(cfg["ret"], tr.build_net()))
+    assert len(captured) == 1
+    net = captured[0]
+    st = tf.shim_state()
+
+    arrays = {"in/data": data, "in/label_segment": lab_feed, "in/label_classes": cls,
+              "in/step": np.float32(cfg["step"])}
+    for k in cfg["ret"]:
+        if k.endswith("_placeholder") or k in ("step_ph", "train_op", "train_classes_op"):
+            continue
+        arrays["out/" + k] = val(ret[k])
+    layer_names, layer_shapes, layer_stats = [], [], []
+    for name, t in net.layers.items():
+        if name == "data":
+            continue
+        layer_names.append(name)
+        layer_shapes.append([int(s) for s in t.t.shape])
+        layer_stats.append(summary(name, val(t)))
+        if name in FULL_LAYERS or name in (cfg["seg"], cfg["fc"]):
+            arrays["layer/" + name] = val(t)
+    arrays["layer_stats"] = np.stack(layer_stats)
+
+    top, tcls = ret["train_op"], ret["train_classes_op"]
+    arrays["grad_stats"] = np.stack([summary(n, top.grads[n]) for n in top.var_names])
+    arrays["new_value_stats"] = np.stack([summary(n, top.new_values[n]) for n in top.var_names])
+    full = [n for n in top.var_names if (n in FULL_GRADS or n.startswith(("class_attention", cfg["seg"])))
+            and top.grads[n].size <= 20000]                # (class_attention_conv/weights is 0.8 M values: summary only)
+    for n in full:
+        arrays["grad/" + n] = top.grads[n]
+    for n in tcls.var_names:                               # the class-only op must produce the same gradients
+        assert np.array_equal(tcls.grads[n], top.grads[n])
+
+    meta = {
+        "snapshot": snapshot, "reference_files": [os.path.relpath(mod.__file__, REF),
+                                                  os.path.relpath(sys.modules["BAISPSPNet"].__file__, REF)],
+        "config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg["attrs"].items()},
+        "seg": cfg["seg"], "fc": cfg["fc"], "step": cfg["step"],
+        "layers": [[n, s] for n, s in zip(layer_names, layer_shapes)],
+        "variables": [[v.full_name, [int(s) for s in v.t.shape], bool(v.trainable)] for v in st.variables.values()],
+        "train_op_vars": top.var_names, "train_classes_op_vars": tcls.var_names,
+        "trace": [[op, attrs] for op, attrs in st.trace[:net.ops_issued]],
+        "trace_train": [[op, attrs] for op, attrs in st.trace[net.ops_issued:]],
+    }
+    out = os.path.join(HERE, "reference_net_%s" % snapshot)
+    np.savez_compressed(out + ".npz", **arrays)
+    with open(out + ".json", "w") as f:
+        json.dump(meta, f, separators=(",", ":"))
+    print("%s: %d layers, %d variables (%d trained), %d primitive ops; loss %.9f (segment %.9f, classes %.9f), lr %.9g"
+          % (snapshot, len(layer_names), len(st.variables), len(top.var_names), len(st.trace),
+             float(val(ret["loss"])), float(val(ret["loss_segment"])), float(val(ret["loss_classes"])),
+             float(val(ret["learning_rate"]))))
+
+
+if __name__ == "__main__":
+    for snap in (sys.argv[1:] or list(SNAPSHOTS)):
+        run_pspnet_snapshot(snap, SNAPSHOTS[snap])

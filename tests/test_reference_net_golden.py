@@ -1,0 +1,247 @@
+"""The oracle and the product's graph builder against the REFERENCE's own network / training code.
+
+tests/golden/reference_net_<snapshot>.{npz,json} were produced by tests/golden/make_reference_net_golden.py, which
+imports the unmodified reference modules (back/<snapshot>/BAISRunnerTrain.py, BAISPSPNet.py) in the build container
+over an eager float64 stand-in for the ~60 `tf.*` calls they make and runs the reference's own `Train.build_net()`.
+Held to those files here (CPU, no reference needed at test time):
+
+  * oracle/basi_oracle.py: parameter inventory (names, shapes, creation order), every layer it exposes, logits,
+    predictions, losses, learning rate, every gradient and the SGD update -- to float64 round-off
+  * the product's host side: `basi_b200.BAISPSPNet.PSPNet` registers the same layers (name, shape, order), the same
+    variables and issues the same primitive-op sequence as the reference's builder; `BAISRunnerTrain.SNAPSHOT` holds
+    the loss weights / learning-rate constants the reference's build_net used; `Engine.set_trainable`'s class-only
+    subset equals the `var_list` of the reference's `train_classes_op`
+
+The -m gpu counterpart (CUDA f32 path against the same files) is tests/test_gpu_net.py::test_train_step_matches_reference_code.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+from oracle import basi_oracle as O                       # noqa: E402
+from ref_net_common import kind_of, param_value, summary  # noqa: E402
+
+SNAPSHOTS = ("2AddClass", "4BorderClass", "5COCO")
+
+
+def load(snapshot):
+    base = os.path.join(HERE, "golden", "reference_net_%s" % snapshot)
+    with open(base + ".json") as f:
+        meta = json.load(f)
+    return meta, np.load(base + ".npz")
+
+
+def reference_params(meta):
+    """{tf name: float32 array} for every TRAINABLE variable the reference's code created."""
+    return {n: param_value(n, s, kind_of(n)) for n, s, trainable in meta["variables"] if trainable}
+
+
+def close(a, b, tol=1e-9):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(float(np.abs(b).max()) if b.size else 0.0, 1e-30)
+    err = float(np.abs(a - b).max()) / scale if b.size else 0.0
+    assert err <= tol, "rel-max error %.3e > %.1e" % (err, tol)
+    return err
+
+
+def product_snapshot_table():
+    from basi_b200.BAISRunnerTrain import SNAPSHOT
+    return SNAPSHOT
+
+
+# --------------------------------------------------------------------------------------------------------------
+# oracle <-> reference code
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_oracle_parameter_inventory_is_the_reference_codes(snapshot):
+    meta, _ = load(snapshot)
+    cfg = meta["config"]
+    specs = O.param_specs(snapshot, cfg["num_classes"], cfg["num_segment"], cfg["filter_number"])
+    ref = [(n, tuple(s)) for n, s, trainable in meta["variables"] if trainable]
+    assert [(n, tuple(s)) for n, s in specs.items()] == ref          # names, shapes AND creation order
+    # what the reference's code creates besides: the moving statistics of every tf.layers.batch_normalization
+    rest = [n for n, _, trainable in meta["variables"] if not trainable]
+    assert all(n.endswith(("/moving_mean", "/moving_variance")) for n in rest)
+    assert len(rest) == 2 * sum(1 for n, _ in ref if n.endswith("/gamma"))
+    # minimize(loss) touches every trainable variable; minimize(loss, var_list=...) the class head only
+    assert meta["train_op_vars"] == [n for n, _ in ref]
+    assert meta["train_classes_op_vars"] == [n for n, _ in ref if "class_attention" in n]
+
+
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_oracle_train_step_reproduces_the_reference_code(snapshot):
+    meta, z = load(snapshot)
+    cfg = meta["config"]
+    snap = product_snapshot_table()[snapshot]
+    assert snap["lr"] == cfg["learning_rate"] and snap["num_steps"] == cfg["num_steps"]
+    assert snap["num_segment"] == cfg["num_segment"]
+    params = reference_params(meta)
+    layers = [n for n, _ in meta["layers"]]
+    keep = [n for n in layers if n not in (meta["seg"], meta["fc"])]
+    lr = float(O.poly_lr(cfg["learning_rate"], float(z["in/step"]), cfg["num_steps"]))
+    close(lr, z["out/learning_rate"], 1e-6)                # the TF graph computes it in float32
+    r = _oracle_step(params, z, meta, snap, lr, keep)
+    stats = {n: z["layer_stats"][i] for i, (n, _) in enumerate(meta["layers"])}
+    shapes = {n: s for n, s in meta["layers"]}
+    compared = 0
+    for n in r["__kept__"]:
+        assert list(r[n].shape) == shapes[n], (n, r[n].shape, shapes[n])
+        close(summary(n, r[n]), stats[n], 1e-9)
+        if "layer/" + n in z.files:
+            close(r[n], z["layer/" + n], 1e-9)
+        compared += 1
+    assert compared >= 270, compared                       # every bottleneck convolution / batch norm / junction, the branches, heads
+    close(r["seg_logits"], z["out/raw_output_segment"], 1e-9)
+    close(r["cls_logits"], z["out/raw_output_classes"], 1e-9)
+    close(r["loss"], z["out/loss"], 1e-11)
+    close(r["loss_segment"], z["out/loss_segment"], 1e-11)
+    close(r["loss_classes"], z["out/loss_classes"], 1e-11)
+    pred, pcls = O.predict_train(r["seg_logits"], r["cls_logits"])
+    assert np.array_equal(pred, z["out/pred_segment"]) and np.array_equal(pcls, z["out/pred_classes"])
+    # the weight of the class term is whatever the reference's add_n used
+    w = (float(z["out/loss"]) - float(z["out/loss_segment"])) / float(z["out/loss_classes"])
+    assert abs(w - snap["class_weight"]) < 1e-12
+    # every gradient and the SGD update
+    names = meta["train_op_vars"]
+    worst = 0.0
+    for i, n in enumerate(names):
+        worst = max(worst, close(summary(n, r["grads"][n]), z["grad_stats"][i], 1e-7))
+        close(summary(n, r["new_params"][n]), z["new_value_stats"][i], 1e-7)
+        if "grad/" + n in z.files:
+            close(r["grads"][n], z["grad/" + n], 1e-8)
+    print("%s: %d layers, %d gradients; worst gradient-summary error %.2e" % (snapshot, compared, len(names), worst))
+
+
+def _oracle_step(params, z, meta, snap, lr, keep):
+    """oracle.train_step returning every named layer the oracle exposes."""
+    cfg = meta["config"]
+    exposed = _exposed_layers(params, z, meta)
+    have = [n for n in keep if n in exposed]
+    r = O.train_step(params, z["in/data"], z["in/label_segment"], z["in/label_classes"], meta["snapshot"],
+                     cfg["num_segment"], cfg["last_pool_size"], snap["pos_weight"], snap["class_weight"], lr,
+                     torch.float64, cfg.get("attention_class"), keep=tuple(have))
+    r["__kept__"] = have
+    return r
+
+
+def _exposed_layers(params, z, meta):
+    """Names in the oracle's layer dictionary (it is local to the forward: one run with a spy on the trunk)."""
+    cfg = meta["config"]
+    rec = {}
+    orig = O._pspnet_trunk
+
+    def spy(p, x, L):
+        rec["L"] = L
+        return orig(p, x, L)
+    O._pspnet_trunk = spy
+    try:
+        O.pspnet_forward(O.to_torch(params, torch.float64), torch.as_tensor(z["in/data"][:1]).to(torch.float64),
+                         meta["snapshot"], cfg["num_segment"], cfg["last_pool_size"], cfg.get("attention_class"))
+    finally:
+        O._pspnet_trunk = orig
+    return set(rec["L"].keys())
+
+
+# --------------------------------------------------------------------------------------------------------------
+# product graph builder <-> reference code
+# --------------------------------------------------------------------------------------------------------------
+def build_product_net(meta):
+    from basi_b200.BAISPSPNet import Placeholder, PSPNet
+    cfg = meta["config"]
+    S = cfg["input_size"][0]
+    return PSPNet({"data": Placeholder((None, S, S, 4))}, is_training=True, num_classes=cfg["num_classes"],
+                  num_segment=cfg["num_segment"], last_pool_size=cfg["last_pool_size"],
+                  filter_number=cfg["filter_number"], attention_class=cfg.get("attention_class"),
+                  variant=meta["snapshot"])
+
+
+def product_trace(net):
+    """The primitive-op sequence of the product's recorded graph, in the vocabulary of the shim's trace."""
+    out = []
+    for nd in net.nodes:
+        a = nd.attrs
+        if nd.op == "data":
+            continue
+        if nd.op == "zero_padding":
+            out.append(["pad", {"paddings": [[0, 0], [a["pad"]] * 2, [a["pad"]] * 2, [0, 0]]}])
+        elif nd.op == "conv":
+            kh, kw, cin, cout = net.variables[a["weights"]]
+            out.append(["conv2d", {"k": [kh, kw], "cin": cin, "cout": cout, "strides": [a["stride"]] * 2,
+                                   "padding": a["padding"], "rate": a["dilation"]}])
+            if a["biases"]:
+                out.append(["bias_add", {"c": cout}])
+            if a["relu"]:
+                out.append(["relu", {}])
+        elif nd.op == "batch_normalization":
+            out.append(["batch_normalization", {"c": nd.shape[-1], "momentum": a["momentum"], "epsilon": a["epsilon"],
+                                                "training": True}])
+            if a["relu"]:
+                out.append(["relu", {}])
+        elif nd.op == "relu":
+            out.append(["relu", {}])
+        elif nd.op == "max_pool":
+            out.append(["max_pool", {"k": [a["k"]] * 2, "strides": [2, 2], "padding": "SAME" if a["k"] == 3 else "VALID"}])
+        elif nd.op == "avg_pool":
+            out.append(["avg_pool", {"k": [a["k"]] * 2, "strides": [a["k"]] * 2, "padding": "VALID"}])
+        elif nd.op == "resize_bilinear":
+            out.append(["resize_bilinear", {"align_corners": True}])
+        elif nd.op == "concat":
+            out.append(["concat", {"axis": -1, "n": len(nd.inputs), "channels": [i.shape[2] for i in nd.inputs]}])
+        elif nd.op == "add":
+            out.append(["add_n", {"n": len(nd.inputs)}])
+        elif nd.op == "multiply":
+            out.append(["relu", {}])                       # the ReLU hidden inside Network.multiply
+            out.append(["multiply", {"channels": [nd.inputs[0].shape[2], 1]}])
+        elif nd.op == "squeeze":
+            out.append(["squeeze", {"axis": [1, 2]}])
+        elif nd.op == "fc":
+            out.append(["relu_layer" if a["relu"] else "xw_plus_b", {"shape": list(net.variables[a["weights"]])}])
+        else:
+            raise AssertionError("op %s has no reference counterpart in this network" % nd.op)
+    return out
+
+
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_product_builder_registers_the_reference_codes_graph(snapshot):
+    meta, _ = load(snapshot)
+    net = build_product_net(meta)
+    # layers: same names, same order, same shapes (the explicit zero-padding layers are numbered differently:
+    # the reference names them padding1..padding33, the builder after their block)
+    ref_layers = [(n, tuple(s[1:])) for n, s in meta["layers"] if not n.startswith("padding")]
+    ref_pads = [tuple(s[1:]) for n, s in meta["layers"] if n.startswith("padding")]
+    mine = [(n, tuple(nd.shape)) for n, nd in net.layers.items() if n != "data" and not n.startswith("padding")]
+    my_pads = [tuple(nd.shape) for n, nd in net.layers.items() if n.startswith("padding")]
+    assert mine == ref_layers
+    assert my_pads == ref_pads and len(ref_pads) == 33
+    # variables: names, shapes, creation order
+    ref_vars = [(n, tuple(s)) for n, s, trainable in meta["variables"] if trainable]
+    assert list(net.variables.items()) == ref_vars
+    # the primitive ops, one for one
+    assert product_trace(net) == meta["trace"]
+    # ... and what build_net issued after the network: label resize, the two losses with the constants of the
+    # product's per-snapshot table, the two-term sum
+    snap = product_snapshot_table()[snapshot]
+    cfg = meta["config"]
+    seg_loss = (["weighted_cross_entropy_with_logits", {"pos_weight": snap["pos_weight"]}] if snap["kind"] == "bce"
+                else ["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_segment"]}])
+    assert meta["trace_train"] == [["resize_nearest_neighbor", {"align_corners": False}], seg_loss,
+                                   ["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_classes"]}],
+                                   ["add_n", {"n": 2}]]
+
+
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_product_class_only_subset_is_the_reference_var_list(snapshot):
+    """A17: `minimize(loss, var_list=[v for v in trainable_variables() if 'class_attention' in v.name])`."""
+    meta, _ = load(snapshot)
+    net = build_product_net(meta)
+    # Engine.set_trainable('class_attention') selects by the same substring rule over the same names
+    assert [n for n in net.variables if "class_attention" in n] == meta["train_classes_op_vars"]
+    assert len(meta["train_classes_op_vars"]) == 4
