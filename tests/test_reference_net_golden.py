@@ -245,3 +245,93 @@ def test_product_class_only_subset_is_the_reference_var_list(snapshot):
     # Engine.set_trainable('class_attention') selects by the same substring rule over the same names
     assert [n for n in net.variables if "class_attention" in n] == meta["train_classes_op_vars"]
     assert len(meta["train_classes_op_vars"]) == 4
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CUDA f32 path <-> reference code (runs last in the -m gpu suite)
+# --------------------------------------------------------------------------------------------------------------
+F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _rel2(a, b):
+    a, b = np.asarray(a, np.float64).reshape(-1), np.asarray(b, np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_cuda_train_step_matches_the_reference_code(snapshot):
+    """The f32 mode of the CUDA path (tcgen05 split operands) through the C ABI against what the reference's own
+    build_net computed: layers, logits, predictions, losses, gradients, SGD update."""
+    from basi_b200.BAISPSPNet import Placeholder, PSPNet           # noqa: F401
+    from basi_b200.engine import Engine
+    meta, z = load(snapshot)
+    cfg = meta["config"]
+    snap = product_snapshot_table()[snapshot]
+    B = cfg["batch_size"]
+    params = reference_params(meta)
+    net = build_product_net(meta)
+    eng = Engine(net, B, "f32", True, dict(kind=snap["kind"], pos_weight=snap["pos_weight"],
+                                           class_weight=snap["class_weight"]))
+    eng.set_params(params)
+    from basi_b200.BAISRunnerTrain import poly_learning_rate
+    lr = float(poly_learning_rate(snap["lr"], float(z["in/step"]), snap["num_steps"]))
+    assert abs(lr - float(z["out/learning_rate"])) < 1e-6 * lr
+    eng.feed(z["in/data"], z["in/label_segment"], z["in/label_classes"], lr)
+    eng.step_device()
+    torch.cuda.synchronize()
+    # float32 noise floor of this input: the oracle in float32 against the reference-code numbers
+    r32 = O.train_step(params, z["in/data"], z["in/label_segment"], z["in/label_classes"], snapshot,
+                       cfg["num_segment"], cfg["last_pool_size"], snap["pos_weight"], snap["class_weight"], lr,
+                       torch.float32, cfg.get("attention_class"))
+    loss, lseg, lcls = eng.losses()
+    assert abs(lseg - float(z["out/loss_segment"])) < F32_TOL * max(1, abs(float(z["out/loss_segment"])))
+    assert abs(lcls - float(z["out/loss_classes"])) < F32_TOL * max(1, abs(float(z["out/loss_classes"])))
+    assert abs(loss - float(z["out/loss"])) < F32_TOL * max(1, abs(float(z["out/loss"])))
+    logits = eng.seg_logits.t.cpu().numpy()
+    e_seg = _rel(logits.reshape(z["out/raw_output_segment"].shape), z["out/raw_output_segment"])
+    assert e_seg < F32_TOL, e_seg
+    cl = eng.cls_logits.t.cpu().numpy().reshape(B, -1)
+    e_cls = _rel(cl, z["out/raw_output_classes"])
+    assert e_cls < F32_TOL + 3 * _rel(r32["cls_logits"], z["out/raw_output_classes"]), e_cls
+    assert np.array_equal(eng.pred_seg.cpu().numpy().reshape(-1), z["out/pred_segment"].reshape(-1))
+    assert np.array_equal(eng.pred_cls.cpu().numpy().reshape(-1), z["out/pred_classes"].reshape(-1))
+    # layers stored in full
+    checked = []
+    for key in z.files:
+        if not key.startswith("layer/"):
+            continue
+        n = key[len("layer/"):]
+        try:
+            v = eng.fetch(n)
+        except KeyError:
+            continue                                       # fused away by the lowering (not materialised)
+        e = _rel(v.reshape(z[key].shape), z[key])
+        assert e < F32_TOL, (n, e)
+        checked.append(n)
+    assert meta["seg"] in checked and len(checked) >= 3, checked
+    # gradients: stored in full -> element-wise criterion of the oracle test; all of them -> their norms
+    grads = eng.get_grads()
+    names = meta["train_op_vars"]
+    assert list(grads.keys()) == names
+    bad = []
+    for i, n in enumerate(names):
+        ref_norm = float(z["grad_stats"][i][1])
+        if ref_norm <= 1e-12:
+            continue
+        if "grad/" + n in z.files:
+            e, fl = _rel2(grads[n], z["grad/" + n]), _rel2(r32["grads"][n], z["grad/" + n])
+            if e > F32_TOL + 10 * fl:
+                bad.append((n, e, fl))
+        e_norm = abs(float(np.linalg.norm(grads[n].astype(np.float64))) - ref_norm) / ref_norm
+        fl_norm = abs(float(np.linalg.norm(r32["grads"][n].astype(np.float64))) - ref_norm) / ref_norm
+        if e_norm > 10 * F32_TOL + 10 * fl_norm:
+            bad.append((n, "norm", e_norm, fl_norm))
+    assert not bad, bad[:5]
+    print("%s: CUDA f32 vs reference code: logits %.2e, class logits %.2e, %d layers, %d gradients"
+          % (snapshot, e_seg, e_cls, len(checked), len(names)))
