@@ -317,8 +317,15 @@ def init_params(specs, seed=0, dtype=np.float32, trained_like=False):
 # --------------------------------------------------------------------------
 
 
-def _pspnet_trunk(params, x, L):
-    """conv1_1 .. conv5_3/relu of the half-width dilated ResNet-101 (NCHW in, NCHW out); fills L with the named layers."""
+def _pspnet_trunk(params, x, L, wiring="2AddClass"):
+    """conv1_1 .. conv5_3/relu of the half-width dilated ResNet-101 (NCHW in, NCHW out); fills L with the named layers.
+
+    wiring="8AttentionU": back/8AttentionU/BAISNet.py:133-480 unrolls the same trunk by hand, and there the variable
+    `net_input` still holds the junction SUM when the next convolution is built (:163-165 ``net_input = Net.add(...)``,
+    ``net_input_conv2_2_relu = Net.relu(net_input, ...)``, ``Net.conv(net_input, ... 'conv2_3_1x1_reduce')``): the
+    1x1_reduce of every non-entry block except conv2_2 and the 1x1_proj of conv3_1 / conv4_1 / conv5_1 read the
+    PRE-ReLU sum of the previous junction; the shortcuts, conv2_2_1x1_reduce and the 1x1_reduce of the entry blocks read
+    its ReLU.  Pinned by running that file (tests/golden/reference_net_8AttentionU.json, key "wiring")."""
 
     def W(n):
         return params[n + "/weights"]
@@ -332,14 +339,19 @@ def _pspnet_trunk(params, x, L):
     L["conv1_3_3x3_bn"] = x
     x = max_pool_3x3_s2_same(x)
     L["pool1_3x3_s2"] = x
+    pre_sum = None                                          # the previous junction before its ReLU
     for stage, blocks, _, stride, dil in STAGES:
         for b in range(1, blocks + 1):
             p = "conv%d_%d" % (stage, b)
             s = stride if b == 1 else 1
+            reads_sum = wiring == "8AttentionU" and pre_sum is not None and p != "conv2_2"
+            red_in = x
             if b == 1:
-                sc = BN(conv2d(x, W(p + "_1x1_proj"), s), p + "_1x1_proj_bn", False)
+                sc = BN(conv2d(pre_sum if reads_sum else x, W(p + "_1x1_proj"), s), p + "_1x1_proj_bn", False)
             else:
                 sc = x
+                if reads_sum:
+                    red_in = pre_sum
             def step(t, conv_name, relu, *conv_args):
                 c = conv2d(t, W(conv_name), *conv_args)
                 L[conv_name] = c
@@ -347,10 +359,11 @@ def _pspnet_trunk(params, x, L):
                 L[conv_name + "_bn"] = o
                 return o
 
-            y = step(x, p + "_1x1_reduce", True, s)
+            y = step(red_in, p + "_1x1_reduce", True, s)
             y = step(y, p + "_3x3", True, 1, dil, dil)                            # tf.pad(d) + (atrous) VALID
             y = step(y, p + "_1x1_increase", False, 1)
             pre = sc + y
+            pre_sum = pre
             x = _relu(pre)
             L[p] = pre
             L[p + "/relu"] = x
@@ -769,7 +782,7 @@ def attention_u_specs(num_classes=21, num_segment=4, filter_number=32, attention
 def attention_u_forward(params, data_nhwc, last_pool_size=40, num_segment=4, segment_attention=1,
                         attention_module_num=2):
     """-> (segments, attentions, classes): sigmoid outputs NHWC, gates N1HW, class logits, in build() order."""
-    c53 = _pspnet_trunk(params, data_nhwc.permute(0, 3, 1, 2), {})
+    c53 = _pspnet_trunk(params, data_nhwc.permute(0, 3, 1, 2), {}, wiring="8AttentionU")
     P = last_pool_size
     size = c53.shape[2:4]
 

@@ -181,6 +181,116 @@ def run_pspnet_snapshot(snapshot, cfg):
              float(val(ret["learning_rate"]))))
 
 
+def save(name, arrays, meta):
+    out = os.path.join(HERE, "reference_net_%s" % name)
+    np.savez_compressed(out + ".npz", **arrays)
+    with open(out + ".json", "w") as f:
+        json.dump(meta, f, separators=(",", ":"))
+
+
+def grad_arrays(arrays, top, always=()):
+    arrays["grad_stats"] = np.stack([summary(n, top.grads[n]) for n in top.var_names])
+    arrays["new_value_stats"] = np.stack([summary(n, top.new_values[n]) for n in top.var_names])
+    for n in top.var_names:
+        if (n in FULL_GRADS or n.startswith(always)) and top.grads[n].size <= 20000:
+            arrays["grad/" + n] = top.grads[n]
+
+
+def run_attention_u():
+    """back/8AttentionU: the WHOLE unmodified Train.__init__ -- the reference's Data reader on tests/golden/voc_mini
+    (has_255 four-class labels, attention labels, click sampling, Gaussian map), BAISNet(...).build() (trunk + four
+    pyramid decoders + four class heads), cal_loss on the sigmoid outputs, both optimizers -- at the script's own
+    filter_number = 32; the batch it feeds is its own reader's next_batch_train()."""
+    import tempfile
+    mod = import_reference("8AttentionU")
+    readers = []
+    ref_data_cls = mod.Data
+
+    class RecordingData(ref_data_cls):
+        def __init__(self, *a, **k):
+            ref_data_cls.__init__(self, *a, **k)
+            readers.append(self)
+
+    mod.Data = RecordingData
+    # who reads whom: every Net.<layer>(input, ..., name=...) call of the reference's builder, by tensor identity
+    Net = sys.modules["BAISNet"].Net
+    wiring, produced, alive = [], {}, []                    # (`alive` keeps the tensors so that no id() is reused)
+
+    def recording(fn_name):
+        orig = getattr(Net, fn_name)
+
+        def f(*a, **k):
+            out = orig(*a, **k)
+            scope = tf.get_variable_scope().name
+            name = (scope + "/" if scope else "") + k["name"]
+            ins = a[0] if isinstance(a[0], (list, tuple)) else [a[0]]
+            wiring.append([name, fn_name, [produced.get(id(t), "?") for t in ins]])
+            produced[id(out)] = name
+            alive.extend([out] + list(ins))
+            return out
+        setattr(Net, fn_name, staticmethod(f))
+    for fn_name in ("conv", "atrous_conv", "batch_normalization", "add", "relu", "max_pool", "avg_pool", "zero_padding",
+                    "concat", "resize_bilinear", "sigmoid", "softmax", "squeeze", "fc"):
+        recording(fn_name)
+    batch = {}
+    step = 4321
+
+    def feeds(i, dtype, shape):
+        # placeholder order in Train.__init__: image, label_segment, label_attention, label_classes, step
+        if not batch:
+            np.random.seed(5)
+            data, ann, att, cls, _, _ = readers[0].next_batch_train()
+            batch.update(data=np.asarray(data, dtype=np.float32), ann=np.asarray(ann).astype(np.int64),
+                         att=np.asarray(att).astype(np.int64), cls=np.asarray(cls).astype(np.int64))
+        return [batch["data"], batch["ann"], batch["att"], batch["cls"], np.float32(step)][i]
+
+    tf.shim_reset(param_value, feeds)
+    voc = os.path.join(HERE, "voc_mini") + "/"
+    with tempfile.TemporaryDirectory() as tmp:
+        tr = mod.Train(batch_size=B, last_pool_size=S // 8, input_size=[S, S], log_dir=os.path.join(tmp, "log"),
+                       data_root_path=voc, train_list="ImageSets/Segmentation/train.txt", data_path="JPEGImages/",
+                       annotation_path="SegmentationObject/", class_path="SegmentationClass/", is_test=False)
+    st = tf.shim_state()
+    arrays = {"in/data": batch["data"], "in/label_segment": batch["ann"], "in/label_attention": batch["att"],
+              "in/label_classes": batch["cls"], "in/step": np.float32(step)}
+    for i in range(4):
+        arrays["out/segment_%d" % i] = val(tr.segments[i])
+        arrays["out/attention_%d" % i] = val(tr.attentions[i])
+        arrays["out/class_%d" % i] = val(tr.classes[i])
+        arrays["out/loss_segment_%d" % i] = val(tr.loss_segments[i])
+        arrays["out/loss_class_%d" % i] = val(tr.loss_classes[i])
+    for k in ("loss", "loss_segment_all", "loss_class_all", "pred_segment", "pred_classes", "accuracy_segment",
+              "accuracy_classes", "learning_rate"):
+        arrays["out/" + k] = val(getattr(tr, k))
+    grad_arrays(arrays, tr.train_op, always=("conv6_n_4", "attention_3/conv6_n_4", "class_attention_fc",
+                                             "attention_2/class_attention_fc"))
+    meta = {
+        "snapshot": "8AttentionU",
+        "reference_files": ["back/8AttentionU/BAISRunnerTrain.py", "back/8AttentionU/BAISNet.py",
+                            "back/8AttentionU/BAISData.py"],
+        "config": dict(input_size=[S, S], batch_size=B, num_classes=tr.num_classes, num_segment=tr.num_segment,
+                       segment_attention=tr.segment_attention, attention_module_num=tr.attention_module_num,
+                       last_pool_size=tr.last_pool_size, filter_number=tr.filter_number, learning_rate=5e-3,
+                       num_steps=tr.num_steps, ratio=tr.ratio),
+        "step": step,
+        "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)] for v in st.variables.values()],
+        "train_op_vars": tr.train_op.var_names, "train_attention_op_vars": tr.train_attention_op.var_names,
+        "trace": [[op, attrs] for op, attrs in st.trace],
+        "wiring": wiring,
+    }
+    save("8AttentionU", arrays, meta)
+    print("8AttentionU: %d variables (%d trained, %d by the attention-only op), %d primitive ops; loss %.9f "
+          "(segment %.9f, classes %.9f)" % (len(st.variables), len(tr.train_op.var_names),
+                                            len(tr.train_attention_op.var_names), len(st.trace),
+                                            float(val(tr.loss)), float(val(tr.loss_segment_all)),
+                                            float(val(tr.loss_class_all))))
+
+
+OTHERS = {"8AttentionU": run_attention_u}
+
 if __name__ == "__main__":
-    for snap in (sys.argv[1:] or list(SNAPSHOTS)):
-        run_pspnet_snapshot(snap, SNAPSHOTS[snap])
+    for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):
+        if snap in OTHERS:
+            OTHERS[snap]()
+        else:
+            run_pspnet_snapshot(snap, SNAPSHOTS[snap])

@@ -248,6 +248,86 @@ def test_product_class_only_subset_is_the_reference_var_list(snapshot):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# F4: the cascade of back/8AttentionU -- the reference's whole Train.__init__ (its own Data reader on voc_mini,
+# BAISNet(...).build(), cal_loss, both optimizers) at its own filter_number = 32
+# --------------------------------------------------------------------------------------------------------------
+def test_cascade_inventory_is_the_reference_codes():
+    meta, _ = load("8AttentionU")
+    cfg = meta["config"]
+    ref = [(n, tuple(s)) for n, s, trainable in meta["variables"] if trainable]
+    specs = O.attention_u_specs(cfg["num_classes"], cfg["num_segment"], cfg["filter_number"],
+                                cfg["attention_module_num"])
+    assert [(n, tuple(s)) for n, s in specs.items()] == ref
+    assert meta["train_op_vars"] == [n for n, _ in ref]
+    # "单独训练最后的attention": var_list = names containing 'attention' (BAISRunnerTrain.py:91-95)
+    assert meta["train_attention_op_vars"] == [n for n, _ in ref if "attention" in n]
+    from basi_b200.BAISNet import BAISNet
+    from basi_b200.BAISPSPNet import Placeholder
+    S = cfg["input_size"][0]
+    net = BAISNet(Placeholder((None, S, S, 4)), is_training=True, num_classes=cfg["num_classes"],
+                  num_segment=cfg["num_segment"], segment_attention=cfg["segment_attention"],
+                  last_pool_size=cfg["last_pool_size"], filter_number=cfg["filter_number"],
+                  attention_module_num=cfg["attention_module_num"])
+    assert list(net.variables.items()) == ref
+    # the arithmetic ops, one for one (the reference additionally builds an unused ReLU of every decoder output and
+    # takes softmax -> split -> multiply where the builder records softmax_gate -> mask_multiply: compared by value
+    # in the oracle test below and in tests/test_gpu_net.py)
+    skip = ("relu", "softmax", "multiply")
+    k = [t[0] for t in meta["trace"]].index("resize_nearest_neighbor")      # the network ends, the loss code begins
+    ref_ops = [t for t in meta["trace"][:k] if t[0] not in skip]
+    mine = []
+    for nd in net.nodes:
+        if nd.op in ("softmax_gate", "mask_multiply"):
+            continue
+        if nd.op == "sigmoid":
+            mine.append(["sigmoid", {}])
+            continue
+        sub = type("N", (), {"nodes": [nd], "variables": net.variables})()
+        mine += [t for t in product_trace(sub) if t[0] not in skip]
+    assert mine == ref_ops
+    nc = cfg["num_classes"]
+    assert meta["trace"][k:k + 12] == (
+        [["resize_nearest_neighbor", {"align_corners": False}]] * 2
+        + [["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_segment"]}]] * 2
+        + [["weighted_cross_entropy_with_logits", {"pos_weight": 3.0}]] * 2
+        + [["sparse_softmax_cross_entropy_with_logits", {"classes": nc}]] * 4 + [["add_n", {"n": 4}]] * 2)
+
+
+def test_cascade_oracle_train_step_reproduces_the_reference_code():
+    meta, z = load("8AttentionU")
+    cfg = meta["config"]
+    snap = product_snapshot_table()["8AttentionU"]
+    assert snap["lr"] == cfg["learning_rate"] and snap["num_steps"] == cfg["num_steps"]
+    params = reference_params(meta)
+    lr = float(O.poly_lr(cfg["learning_rate"], float(z["in/step"]), cfg["num_steps"]))
+    close(lr, z["out/learning_rate"], 1e-6)
+    # the batch came out of the reference's own reader: attention labels are (label == 1), labels are 0..3
+    assert np.array_equal(z["in/label_attention"], (z["in/label_segment"] == 1).astype(np.int64))
+    assert z["in/label_segment"].max() <= 3 and z["in/data"].dtype == np.float32
+    r = O.attention_u_train_step(params, z["in/data"], z["in/label_segment"], z["in/label_attention"],
+                                 z["in/label_classes"], cfg["last_pool_size"], lr, torch.float64, cfg["num_segment"],
+                                 cfg["segment_attention"], cfg["attention_module_num"])
+    for i in range(4):
+        close(r["segments"][i], z["out/segment_%d" % i], 1e-9)
+        close(np.transpose(r["attentions"][i], (0, 2, 3, 1)), z["out/attention_%d" % i], 1e-9)
+        close(r["classes"][i], z["out/class_%d" % i], 1e-9)
+    close(r["loss"], z["out/loss"], 1e-11)
+    close(r["loss_segment"], z["out/loss_segment_all"], 1e-11)
+    close(r["loss_classes"], z["out/loss_class_all"], 1e-11)
+    w = (float(z["out/loss"]) - float(z["out/loss_segment_all"])) / float(z["out/loss_class_all"])
+    assert abs(w - snap["class_weight"]) < 1e-12
+    assert np.array_equal(np.argmax(r["segments"][0], -1)[..., None], z["out/pred_segment"])
+    assert np.array_equal(np.argmax(r["classes"][0], -1), z["out/pred_classes"])
+    worst = 0.0
+    for i, n in enumerate(meta["train_op_vars"]):
+        worst = max(worst, close(summary(n, r["grads"][n]), z["grad_stats"][i], 1e-7))
+        close(summary(n, r["new_params"][n]), z["new_value_stats"][i], 1e-7)
+        if "grad/" + n in z.files:
+            close(r["grads"][n], z["grad/" + n], 1e-8)
+    print("8AttentionU: %d gradients; worst gradient-summary error %.2e" % (len(meta["train_op_vars"]), worst))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # CUDA f32 path <-> reference code (runs last in the -m gpu suite)
 # --------------------------------------------------------------------------------------------------------------
 F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
