@@ -192,6 +192,11 @@ int basi_bias_relu_bwd(const basi_tensor* dy, const basi_tensor* y, int relu, fl
 int basi_add_fwd(const basi_tensor* a, const basi_tensor* b, const basi_tensor* out, void* stream);
 int basi_add_bwd(const basi_tensor* dout, const basi_tensor* da, int acc_a, const basi_tensor* db, int acc_b,
                  void* stream);
+/* F4: Net.relu on a MATERIALISED residual sum (back/8AttentionU/BAISNet.py:163-165: the hand-unrolled trunk reads both
+ * the sum `net_input = Net.add(...)` -- next 1x1_reduce / 1x1_proj -- and its ReLU -- next shortcut) and its adjoint
+ * dx (+)= dy * (y > 0).  x / y / dy / dx: same shape and dtype, channel count a multiple of the vector width. */
+int basi_relu_fwd(const basi_tensor* x, const basi_tensor* y, void* stream);
+int basi_relu_bwd(const basi_tensor* dy, const basi_tensor* y, const basi_tensor* dx, int accumulate, void* stream);
 /* F1: tf.one_hot(labels, depth=2) as float32 pairs (targets of the 2-channel weighted CE of variant B,
  * back/90AttentionSingle2/BAISRunnerTrain.py:128-131); labels float32 {0,1}, out float32 [n][2]. */
 int basi_onehot2_f32(const float* labels, float* out, int64_t n, void* stream);

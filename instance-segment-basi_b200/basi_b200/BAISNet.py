@@ -200,7 +200,7 @@ class BAISNet(PSPNet):
         self.classes.append(self.layers[scope + 'class_attention_fc'])
 
     def setup(self, is_training, num_classes, num_segment, last_pool_size, filter_number):
-        feat = self._trunk(filter_number)
+        feat = self._trunk(filter_number, wiring="8AttentionU")
         n = len(self.SCOPES)
         first_two = n - self.attention_module_num            # decoders with index >= first_two have 2 channels
         lg = self._decoder(feat, '', num_segment if first_two > 0 else 2)

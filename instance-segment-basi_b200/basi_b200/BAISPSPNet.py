@@ -262,16 +262,19 @@ class PSPNet(Network):
         Network.__init__(self, inputs, num_classes, num_segment, trainable, is_training, last_pool_size,
                          filter_number)
 
-    def _bottleneck(self, prefix, source, mid, stride, dilation, project):
+    def _bottleneck(self, prefix, source, mid, stride, dilation, project, sum_source=None):
+        """One bottleneck block reading `source` (the previous junction's ReLU).  `sum_source` (8AttentionU wiring
+        only) names the previous junction's PRE-ReLU sum: the projection of an entry block / the 1x1_reduce of any
+        other block reads that instead (see _trunk)."""
         fn_out = mid * 4
         if project:
-            (self.feed(source)
+            (self.feed(sum_source or source)
              .conv(1, 1, fn_out, stride, stride, biased=False, relu=False, name=prefix + '_1x1_proj')
              .batch_normalization(relu=False, name=prefix + '_1x1_proj_bn'))
             shortcut = prefix + '_1x1_proj_bn'
         else:
             shortcut = source
-        (self.feed(source)
+        (self.feed(source if (project or not sum_source) else sum_source)
          .conv(1, 1, mid, stride, stride, biased=False, relu=False, name=prefix + '_1x1_reduce')
          .batch_normalization(relu=True, name=prefix + '_1x1_reduce_bn')
          .zero_padding(paddings=dilation, name='padding_' + prefix))
@@ -287,8 +290,14 @@ class PSPNet(Network):
          .relu(name=prefix + '/relu'))
         return prefix + '/relu'
 
-    def _trunk(self, F):
-        """conv1_1 .. conv5_3/relu (2AddClass/BAISPSPNet.py:173-470); returns the name of the last layer."""
+    def _trunk(self, F, wiring="2AddClass"):
+        """conv1_1 .. conv5_3/relu (2AddClass/BAISPSPNet.py:173-470); returns the name of the last layer.
+
+        wiring="8AttentionU": back/8AttentionU/BAISNet.py:133-480 unrolls the same trunk by hand with one variable
+        (`net_input`) that still holds the junction SUM when the next convolution is built (:163-165), so there the
+        1x1_reduce of every non-entry block except conv2_2 and the 1x1_proj of conv3_1 / conv4_1 / conv5_1 read the
+        pre-ReLU sum of the previous junction; shortcuts, conv2_2_1x1_reduce and the entry blocks' 1x1_reduce read
+        its ReLU.  (Found by running that file: tests/golden/reference_net_8AttentionU.json "wiring".)"""
         (self.feed('data')
          .conv(3, 3, F, 2, 2, biased=False, relu=False, padding='SAME', name='conv1_1_3x3_s2_n')
          .batch_normalization(relu=False, name='conv1_1_3x3_s2_bn')
@@ -302,8 +311,11 @@ class PSPNet(Network):
         for stage, blocks, mult, stride, dilation in ((2, 3, 1, 1, 1), (3, 4, 2, 2, 1), (4, 23, 4, 1, 2),
                                                       (5, 3, 8, 1, 4)):
             for b in range(1, blocks + 1):
-                cur = self._bottleneck('conv%d_%d' % (stage, b), cur, F * mult, stride if b == 1 else 1, dilation,
-                                       project=(b == 1))
+                prefix = 'conv%d_%d' % (stage, b)
+                prev_sum = cur[:-len('/relu')] if cur.endswith('/relu') else None
+                reads_sum = wiring == "8AttentionU" and prev_sum is not None and prefix != 'conv2_2'
+                cur = self._bottleneck(prefix, cur, F * mult, stride if b == 1 else 1, dilation, project=(b == 1),
+                                       sum_source=prev_sum if reads_sum else None)
         return cur
 
     def _pyramid_decoder(self, source, F, last_pool_size, num_segment, seg_name, scope=''):

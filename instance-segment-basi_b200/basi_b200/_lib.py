@@ -74,6 +74,8 @@ SIGNATURES = {
     "basi_bn_bwd_apply": [_TP, _TP, _TP, _P, _P, _i, _TP, _TP, _i, _P],
     "basi_bias_relu_bwd": [_TP, _TP, _i, _P, _P],
     "basi_tc_conv_set_bias": [_P, _P, _i],
+    "basi_relu_fwd": [_TP, _TP, _P],
+    "basi_relu_bwd": [_TP, _TP, _TP, _i, _P],
     "basi_add_fwd": [_TP, _TP, _TP, _P],
     "basi_add_bwd": [_TP, _TP, _i, _TP, _i, _P],
     "basi_onehot2_f32": [_P, _P, _i64, _P],

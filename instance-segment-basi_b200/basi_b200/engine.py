@@ -509,24 +509,35 @@ class Engine(object):
             return
         if src.op != "add":
             raise NotImplementedError("relu after %s" % src.op)
-        ins = [self._acts[i.index] for i in src.inputs]
-        assert len(ins) == 2
-        deferred = [i for i in ins if isinstance(i, tuple) and i[0] == "bn_deferred"]
-        plain = [i for i in ins if isinstance(i, Act)]
-        if len(deferred) == 2:
-            # (proj_bn, increase_bn): main = the later one
-            res_bn, main = deferred[0][1], deferred[1][1]
-            res = res_bn.x
-        elif len(deferred) == 1 and len(plain) == 1:
-            main, res, res_bn = deferred[0][1], plain[0], None
-        else:
-            raise NotImplementedError("add of %s" % (ins,))
+        if isinstance(self._acts.get(src.index), Act):
+            # the sum itself was materialised (it has readers of its own, see _lower_add): a stand-alone ReLU
+            x = self._acts[src.index]
+            y = self._out_act(n, x.t.dtype)
+            self._acts[n.index] = y
+            self._ops.append(("relu", dict(x=x, y=y)))
+            self._call(self.fwd, "basi_relu_fwd", x.ref, y.ref, bytes=self._nbytes(x) * 2)
+            return
+        main, res, res_bn = self._junction_inputs(src)
         out = self._out_act(n)
         self._acts[n.index] = out
         self._acts[src.index] = ("pre_relu_of", out)
         op = dict(main=main, res=res, res_bn=res_bn, relu=True, out=out)
         self._ops.append(("bnact", op))
         self._emit_bnact_fwd(op)
+
+    def _junction_inputs(self, add_node):
+        """(main BN record, residual tensor, residual BN record or None) of a residual junction."""
+        ins = [self._acts[i.index] for i in add_node.inputs]
+        assert len(ins) == 2
+        deferred = [i for i in ins if isinstance(i, tuple) and i[0] == "bn_deferred"]
+        plain = [i for i in ins if isinstance(i, Act)]
+        if len(deferred) == 2:
+            # (proj_bn, increase_bn): main = the later one
+            res_bn, main = deferred[0][1], deferred[1][1]
+            return main, res_bn.x, res_bn
+        if len(deferred) == 1 and len(plain) == 1:
+            return deferred[0][1], plain[0], None
+        raise NotImplementedError("add of %s" % (ins,))
 
     def _lower_add(self, n):
         ins = [self._acts[i.index] for i in n.inputs]
@@ -537,6 +548,18 @@ class Engine(object):
             self._acts[n.index] = y
             self._ops.append(("add", dict(a=a, b=b, y=y)))
             self._call(self.fwd, "basi_add_fwd", a.ref, b.ref, y.ref)
+            return
+        if any(c.op not in ("relu", "multiply") for c in self._cons[n.index]):      # (multiply has its ReLU inside)
+            # a residual junction whose SUM is read besides its ReLU (the hand-unrolled trunk of
+            # back/8AttentionU/BAISNet.py:163-165 feeds it to the next 1x1_reduce / 1x1_proj): materialise
+            # BN(main) + residual without the ReLU; the ReLU that follows becomes its own op (_lower_relu).
+            # The adjoint runs on the generic reduce / apply pair (no stored-output mask, residual gradient).
+            main, res, res_bn = self._junction_inputs(n)
+            out = self._out_act(n)
+            self._acts[n.index] = out
+            op = dict(main=main, res=res, res_bn=res_bn, relu=False, out=out, generic_bwd=True)
+            self._ops.append(("bnact", op))
+            self._emit_bnact_fwd(op)
         # else: a residual junction, materialised by the following relu
 
     def _lower_concat(self, n):
@@ -1036,6 +1059,14 @@ class Engine(object):
         self._call(self.bwd, "basi_softmax_gate_bwd", logits.t.data_ptr(), gate.grad.t.data_ptr(), C.c_int64(n * h * w),
                    op["C"], op["sel"], C.c_float(op["thr"]), logits.grad.t.data_ptr(), acc)
 
+    def _bwd_relu(self, op):
+        x, y = op["x"], op["y"]
+        if y.grad is None or not y.gw:
+            return
+        acc = self._acc_flag(x)
+        self._call(self.bwd, "basi_relu_bwd", y.grad.ref, y.ref, x.grad.ref, acc,
+                   bytes=self._nbytes(x) * (3 + (1 if acc else 0)))
+
     def _bwd_sigmoid(self, op):
         x, y = op["x"], op["y"]
         if y.grad is None or not y.gw:
@@ -1153,7 +1184,8 @@ class Engine(object):
                 dres = op["res"].grad.ref
             nb = self._nbytes(x)
             nin = 3 if mask is not None else 2
-            if (mask is None and dres is None and self.fuse_bn_bwd and not self.dry_run
+            generic = bool(op.get("generic_bwd"))
+            if (mask is None and dres is None and self.fuse_bn_bwd and not self.dry_run and not generic
                     and _lib.load().basi_bn_bwd_fused_supported(x.ref) == 1
                     and dout.desc.ld == dout.desc.c and dx.desc.ld == dx.desc.c):
                 # reduce + apply in one cooperative launch, dout and x resident in shared memory between the phases
@@ -1163,7 +1195,7 @@ class Engine(object):
                 self.fused_bn_bwd += 1
                 continue
             bits_t = op.get("bits")
-            if (self.coop_bn_bwd and not self.dry_run
+            if (self.coop_bn_bwd and not self.dry_run and not generic
                     and _lib.load().basi_bn_bwd_coop_supported(x.ref, 1 if (mask is not None and bits_t is None) else 0,
                                                                1 if bits_t is not None else 0, dacc) == 1):
                 # reduce + dx pass in one cooperative launch (grid barrier in between)

@@ -1220,6 +1220,44 @@ __global__ void __launch_bounds__(256) bias_relu_bwd_kernel(T* __restrict__ dy, 
     for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, bsum[c]);
 }
 
+// Stand-alone ReLU of a MATERIALISED residual sum and its adjoint dX (+)= dY * (Y > 0): the hand-unrolled trunk of
+// back/8AttentionU/BAISNet.py:163-165 reads both the junction sum (next 1x1_reduce / 1x1_proj) and its ReLU (shortcut)
+template <typename T>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int C, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t r = i / cgs;
+    Vec<T> v = Vec<T>::load(x + r * ldx + cg * VN);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) v.v[j] = v.v[j] > 0.f ? v.v[j] : 0.f;
+    v.store(y + r * ldy + cg * VN);
+  }
+}
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dx,
+                                int ldx, int acc, int C, int64_t total) {
+  pdl_prologue();
+  constexpr int VN = Vec<T>::N;
+  const int cgs = C / VN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t r = i / cgs;
+    Vec<T> o = Vec<T>::load(g + r * ldg + cg * VN);
+    const Vec<T> m = Vec<T>::load(y + r * ldy + cg * VN);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o.v[j] = m.v[j] > 0.f ? o.v[j] : 0.f;
+    if (acc) {
+      const Vec<T> old = Vec<T>::load(dx + r * ldx + cg * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] += old.v[j];
+    }
+    o.store(dx + r * ldx + cg * VN);
+  }
+}
+
 // Plain tensor add (Net.add of the top-level LinkNet, BAISNet.py:244) and its adjoint (dA (+)= dOut, dB (+)= dOut)
 template <typename T>
 __global__ void add_fwd_kernel(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb, T* __restrict__ o,
@@ -1391,6 +1429,29 @@ int basi_add_bwd(const basi_tensor* dout, const basi_tensor* da, int acc_a, cons
                  acc_b, dout->c, total);
   })
   BASI_CHECK_LAUNCH("add_bwd");
+  return BASI_OK;
+}
+
+int basi_relu_fwd(const basi_tensor* x, const basi_tensor* y, void* stream) {
+  BASI_CHECK_ARG(x && y && vec_ok(x) && vec_ok(y) && same_shape(x, y) && x->dtype == y->dtype, "relu fwd: bad tensors");
+  DISPATCH_T(x->dtype, {
+    const int64_t total = pixels(x) * (x->c / Vec<T>::N);
+    basi::launch(relu_fwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x->ptr, x->ld,
+                 (T*)y->ptr, y->ld, x->c, total);
+  })
+  BASI_CHECK_LAUNCH("relu_fwd");
+  return BASI_OK;
+}
+
+int basi_relu_bwd(const basi_tensor* dy, const basi_tensor* y, const basi_tensor* dx, int accumulate, void* stream) {
+  BASI_CHECK_ARG(dy && y && dx && vec_ok(dy) && vec_ok(y) && vec_ok(dx) && same_shape(dy, y) && same_shape(dy, dx) &&
+                     dy->dtype == y->dtype && dy->dtype == dx->dtype, "relu bwd: bad tensors");
+  DISPATCH_T(dy->dtype, {
+    const int64_t total = pixels(dy) * (dy->c / Vec<T>::N);
+    basi::launch(relu_bwd_kernel<T>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)dy->ptr, dy->ld,
+                 (const T*)y->ptr, y->ld, (T*)dx->ptr, dx->ld, accumulate, dy->c, total);
+  })
+  BASI_CHECK_LAUNCH("relu_bwd");
   return BASI_OK;
 }
 

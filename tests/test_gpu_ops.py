@@ -136,9 +136,10 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
 
 # ------------------------------------------------------------------ batch norm (+relu, +residual) forward/backward
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-@pytest.mark.parametrize("mode", ["plain", "relu", "res", "res_bn"])
+@pytest.mark.parametrize("mode", ["plain", "relu", "res", "res_bn", "res_norelu"])
 @pytest.mark.parametrize("shape", [(2, 16, 16, 32), (1, 1, 1, 16), (3, 5, 7, 8), (2, 8, 8, 2048), (4, 40, 40, 128), (3, 37, 41, 512)])
 def test_batch_norm_forward_backward(dtype, mode, shape):
+    # res_norelu: BN(x) + residual WITHOUT the ReLU -- the materialised junction sum of the 8AttentionU trunk wiring
     from gpu_util import act, bf16_round, call, dev, empty_act, host, rel_err, rel_l2
     B, H, W, Cc = shape
     rng = np.random.RandomState(1)
@@ -149,13 +150,13 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     gamma, beta = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
     gamma2, beta2 = rng.uniform(0.5, 1.5, Cc).astype(np.float32), _u(rng, Cc)
     dout = rnd(_u(rng, *shape))
-    relu = mode != "plain"
+    relu = mode not in ("plain", "res_norelu")
     # oracle (float64)
     xt, x2t = nchw(x).double().requires_grad_(True), nchw(x2).double().requires_grad_(True)
     g1, b1 = torch.from_numpy(gamma).double().requires_grad_(True), torch.from_numpy(beta).double().requires_grad_(True)
     g2, b2 = torch.from_numpy(gamma2).double().requires_grad_(True), torch.from_numpy(beta2).double().requires_grad_(True)
     y = O.batch_norm(xt, g1, b1)
-    if mode == "res":
+    if mode in ("res", "res_norelu"):
         y = y + x2t
     if mode == "res_bn":
         y = y + O.batch_norm(x2t, g2, b2)
@@ -171,7 +172,7 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     call("basi_bn_stats", xa.ref, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), C.c_double(R), C.c_float(1e-5),
          bnp.data_ptr(), cnt.data_ptr())
     res_ref, res_bnp = None, None
-    if mode in ("res", "res_bn"):
+    if mode in ("res", "res_bn", "res_norelu"):
         res_ref = x2a.ref
     if mode == "res_bn":
         call("basi_bn_stats", x2a.ref, sums.data_ptr() + 8 * 2 * Cc * 8, None, None, C.c_double(R), C.c_float(1e-5), None,
@@ -201,12 +202,12 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
     call("basi_bn_bwd_reduce", da.ref, mask, xa.ref, bnp.data_ptr(), from_x, dsums.data_ptr(), C.c_double(R),
          dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), cnt.data_ptr() + 8)
     call("basi_bn_bwd_apply", da.ref, mask, xa.ref, bnp.data_ptr(), coef.data_ptr(), from_x, dxa.ref,
-         dresa.ref if mode == "res" else None, 1)
+         dresa.ref if mode in ("res", "res_norelu") else None, 1)
     btol = 2e-4 if dtype == "f32" else 3e-2
     assert rel_l2(host(dxa), nhwc(xt.grad)) < btol
     assert rel_err(host(dgamma), g1.grad.numpy()) < btol
     assert rel_err(host(dbeta), b1.grad.numpy()) < btol
-    if mode == "res":
+    if mode in ("res", "res_norelu"):
         assert rel_l2(host(dresa) - 1.0, nhwc(x2t.grad)) < btol
     if mode == "res_bn":
         dsums.zero_()
@@ -219,6 +220,37 @@ def test_batch_norm_forward_backward(dtype, mode, shape):
         call("basi_bn_bwd_apply", da.ref, mask, x2a.ref, bnp2.data_ptr(), coef.data_ptr(), 0, dx2a.ref, None, 0)
         assert rel_l2(host(dx2a), nhwc(x2t.grad)) < btol
         assert rel_err(host(dg2), g2.grad.numpy()) < btol
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 10, 10, 32), (3, 5, 7, 8), (4, 40, 40, 128)])
+def test_relu_of_materialised_sum(dtype, shape):
+    """basi_relu_fwd / basi_relu_bwd (8AttentionU trunk wiring: the junction sum and its ReLU are both read): bit-exact
+    against numpy, with and without accumulation, also on a strided (channel-slice) destination."""
+    from gpu_util import act, bf16_round, call, empty_act, host
+    from basi_b200.engine import Act
+    rng = np.random.RandomState(4)
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    rnd = (lambda a: a.astype(np.float32)) if dtype == "f32" else bf16_round
+    x = rnd(_u(rng, *shape))
+    x[0, 0, 0, :4] = [0.0, -0.0, 1.0, -1.0]
+    dy, old = rnd(_u(rng, *shape)), rnd(_u(rng, *shape))
+    xa, ya = act(x, tdt), empty_act(shape, tdt, fill=7.0)
+    call("basi_relu_fwd", xa.ref, ya.ref)
+    y = np.maximum(x, 0.0)
+    assert np.array_equal(host(ya), y)
+    for acc in (0, 1):
+        dxa = act(old, tdt)
+        call("basi_relu_bwd", act(dy, tdt).ref, ya.ref, dxa.ref, acc)
+        want = np.where(y > 0, dy, 0.0) + (old if acc else 0.0)
+        assert np.array_equal(host(dxa), rnd(want.astype(np.float32)))
+    # destination = channel slice of a wider buffer (ld > c)
+    B, H, W, Cc = shape
+    wide = torch.full((B, H, W, 2 * Cc), 3.0, dtype=tdt, device="cuda:0")
+    call("basi_relu_fwd", xa.ref, Act(wide[..., Cc:]).ref)
+    torch.cuda.synchronize()
+    got = wide.float().cpu().numpy()
+    assert np.array_equal(got[..., Cc:], y) and np.all(got[..., :Cc] == 3.0)
 
 
 # ------------------------------------------------------------------ pooling / bilinear / gate
