@@ -286,7 +286,89 @@ def run_attention_u():
                                             float(val(tr.loss_class_all))))
 
 
-OTHERS = {"8AttentionU": run_attention_u}
+def import_reference_top():
+    """The current-HEAD scripts (/root/reference/*.py) with /root/reference/slim on the path for `from nets import
+    nets_factory` -- which imports the reference's whole vendored slim model zoo, unmodified."""
+    import tensorflow.contrib.slim as slim
+    slim.shim_reset_collections()
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m.startswith("nets"):
+            del sys.modules[m]
+    sys.path.insert(0, os.path.join(REF, "slim"))
+    sys.path.insert(0, REF)
+    try:
+        mod = importlib.import_module("BAISRunnerTrain")
+    finally:
+        sys.path.remove(REF)
+        sys.path.remove(os.path.join(REF, "slim"))
+    assert os.path.realpath(mod.__file__) == os.path.join(REF, "BAISRunnerTrain.py"), mod.__file__
+    return mod
+
+
+def run_head():
+    """Current HEAD (BAISRunnerTrain.py + BAISNet.py + BAISData.py + slim/nets/vgg.py through nets_factory): the whole
+    unmodified Train.__init__ at 224^2 (the smallest size slim's vgg_16 accepts: its fc6 is a 7x7 VALID convolution on
+    pool5), batch 2 from the reference's own reader on tests/golden/voc_mini."""
+    import tempfile
+    mod = import_reference_top()
+    readers = []
+    ref_data_cls = mod.Data
+
+    class RecordingData(ref_data_cls):
+        def __init__(self, *a, **k):
+            ref_data_cls.__init__(self, *a, **k)
+            readers.append(self)
+
+    mod.Data = RecordingData
+    SH, step, batch = 224, 777, {}
+
+    def feeds(i, dtype, shape):
+        # placeholder order in Train.__init__: image, label_seg, step
+        if not batch:
+            data, ann = readers[0].next_batch_train()
+            batch.update(data=np.asarray(data, dtype=np.float32), ann=np.asarray(ann).astype(np.int64))
+        return [batch["data"], batch["ann"], np.float32(step)][i]
+
+    tf.shim_reset(param_value, feeds)
+    voc = os.path.join(HERE, "voc_mini") + "/"
+    with tempfile.TemporaryDirectory() as tmp:
+        tr = mod.Train(batch_size=B, input_size=[SH, SH], log_dir=os.path.join(tmp, "log"), data_root_path=voc,
+                       train_list="ImageSets/Segmentation/train.txt", data_path="JPEGImages/",
+                       annotation_path="SegmentationObject/", class_path="SegmentationClass/", is_test=False)
+    st = tf.shim_state()
+    u8 = np.round(batch["data"] * 255).astype(np.uint8)
+    assert np.array_equal(u8.astype(np.float32) / np.float32(255), batch["data"])     # the reader's image / 255
+    arrays = {"in/image_u8": u8, "in/label_segment": batch["ann"].astype(np.uint8), "in/step": np.float32(step)}
+    for i, sg in enumerate(tr.segments):
+        v = val(sg)
+        arrays["out/segment_stats_%d" % i] = summary("segment_%d" % i, v)
+        if v.size <= 20000:
+            arrays["out/segment_%d" % i] = v
+        arrays["out/loss_segment_%d" % i] = val(tr.loss_segments[i])
+    for k in ("loss", "loss_segment_all", "learning_rate"):
+        arrays["out/" + k] = val(getattr(tr, k))
+    grad_arrays(arrays, tr.train_op, always=("attention_0", "attention_4/segment_side_4/d_s_conv_4",
+                                             "vgg_16/conv1/conv1_1"))
+    dropouts = [t for t in st.trace if t[0] == "dropout"]
+    meta = {
+        "snapshot": "HEAD",
+        "reference_files": ["BAISRunnerTrain.py", "BAISNet.py", "BAISData.py", "slim/nets/nets_factory.py",
+                            "slim/nets/vgg.py"],
+        "config": dict(input_size=[SH, SH], batch_size=B, num_classes=tr.num_classes, learning_rate=5e-3,
+                       num_steps=tr.num_steps),
+        "step": step, "segment_shapes": [[int(s_) for s_ in sg.t.shape] for sg in tr.segments],
+        "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)] for v in st.variables.values()],
+        "train_op_vars": tr.train_op.var_names, "train_segment_side_op_vars": tr.train_segment_side_op.var_names,
+        "trace": [[op, attrs] for op, attrs in st.trace], "dropout_calls": len(dropouts),
+    }
+    save("HEAD", arrays, meta)
+    print("HEAD: %d variables (%d with a gradient, %d by the segment_side-only op), %d primitive ops; loss %.9f, "
+          "segments %s" % (len(st.variables), len(tr.train_op.var_names), len(tr.train_segment_side_op.var_names),
+                           len(st.trace), float(val(tr.loss)), meta["segment_shapes"]))
+
+
+OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

@@ -39,6 +39,34 @@ uint8 = "uint8"
 bool = "bool"  # noqa: A001  (tf.bool)
 
 
+class _Anything(object):
+    """Inert placeholder for API the reference's files only MENTION (decorators, initialisers, flags of the vendored
+    slim model zoo that `from nets import nets_factory` imports): callable, attribute-able, usable as a decorator.
+    It carries no value: if one ever reached an op of the path, that op would fail on it."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        if len(a) == 1 and not k and callable(a[0]) and not isinstance(a[0], _Anything):
+            return a[0]                                    # used as a decorator
+        return _Anything(self._name + "()")
+
+    def __getattr__(self, n):
+        if n.startswith("__"):
+            raise AttributeError(n)
+        return _Anything(self._name + "." + n)
+
+    def __iter__(self):
+        return iter(())
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # shapes / tensors
 # ----------------------------------------------------------------------------------------------------------------
@@ -579,6 +607,12 @@ class _NN(object):
         return Tensor(-(torch.log_softmax(x, dim=dim) * _val(labels).to(DT)).sum(dim=dim), name)
 
 
+    def __getattr__(self, name):          # e.g. tf.nn.relu6 in a model-zoo file that is imported but never built
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything("tf.nn." + name)
+
+
 nn = _NN()
 
 
@@ -658,8 +692,10 @@ class _Image(object):
             if align_corners and n_out > 1:
                 scale = (n_in - 1) / float(n_out - 1)
                 return [min(int(round(o * scale)), n_in - 1) for o in range(n_out)]
-            scale = n_in / float(n_out)
-            return [min(int(math.floor(o * scale)), n_in - 1) for o in range(n_out)]
+            # TF's kernel works in float32: floorf(out * (float(in) / float(out))) -- 224 -> 110 maps row 55 to
+            # 112 (float64 arithmetic would say 111)
+            scale = np.float32(n_in) / np.float32(n_out)
+            return [min(int(np.floor(np.float32(o) * scale)), n_in - 1) for o in range(n_out)]
         ih = torch.tensor(idx(hi, ho), dtype=torch.int64)
         iw = torch.tensor(idx(wi, wo), dtype=torch.int64)
         return Tensor(x.index_select(1, ih).index_select(2, iw), name)
@@ -753,3 +789,13 @@ def GPUOptions(*a, **k):
 
 def global_variables_initializer():
     return None
+
+
+def zeros_initializer(*a, **k):
+    return "zeros"
+
+
+def __getattr__(name):                    # API the vendored model zoo only mentions (see _Anything)
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Anything("tf." + name)

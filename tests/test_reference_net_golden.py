@@ -328,6 +328,77 @@ def test_cascade_oracle_train_step_reproduces_the_reference_code():
 
 
 # --------------------------------------------------------------------------------------------------------------
+# F2: the current-HEAD path -- the reference's whole Train.__init__ (BAISRunnerTrain.py + BAISNet.py + BAISData.py +
+# slim/nets/nets_factory.py -> slim/nets/vgg.py) at 224^2 on its own reader's batch of tests/golden/voc_mini
+# --------------------------------------------------------------------------------------------------------------
+def _head_inputs(z):
+    image = z["in/image_u8"].astype(np.float32) / np.float32(255)          # Data._read_image: uint8 / 255 in float32
+    return image, z["in/label_segment"].astype(np.int64)
+
+
+def test_head_inventory_is_the_reference_codes():
+    meta, z = load("HEAD")
+    trained = [(n, tuple(s)) for n, s, trainable in meta["variables"] if trainable and n in set(meta["train_op_vars"])]
+    specs = O.linknet_top_specs(1.0)
+    assert [(n, tuple(s)) for n, s in specs.items()] == trained
+    # the rest of what slim's vgg_16 builds (fc6 as a 7x7 VALID convolution, fc7) is in the reference's graph but the
+    # loss does not depend on it: minimize() has no gradient for it, no fetched value reads it
+    rest = [n for n, _, t in meta["variables"] if n not in set(meta["train_op_vars"])]
+    assert rest == ["vgg_16/fc6/weights", "vgg_16/fc6/biases", "vgg_16/fc7/weights", "vgg_16/fc7/biases"]
+    assert meta["dropout_calls"] == 1                                  # ... nor on vgg_16's dropout6
+    assert meta["train_segment_side_op_vars"] == [n for n, _ in trained if "segment_side" in n]
+    from basi_b200.BAISNet import LinkNetTop
+    from basi_b200.BAISPSPNet import Placeholder
+    S = meta["config"]["input_size"][0]
+    net = LinkNetTop(Placeholder((None, S, S, 3)))
+    assert list(net.variables.items()) == trained
+    segs, _ = net.build()
+    assert [[meta["config"]["batch_size"]] + list(nd.shape) for nd in segs] == meta["segment_shapes"]
+    # primitive ops of the path: the reference's trace minus pool5 / fc6 / dropout6 / fc7 and minus the loss code
+    ops = meta["trace"]
+    k = [t[0] for t in ops].index("dropout")
+    dead = ops[k - 4:k + 4]                                             # pool5, fc6 (+bias +relu), dropout, fc7 (+bias +relu)
+    assert [t[0] for t in dead] == ["max_pool", "conv2d", "bias_add", "relu", "dropout", "conv2d", "bias_add", "relu"]
+    live = ops[:k - 4] + ops[k + 4:]
+    n_loss = [t[0] for t in live].index("weighted_cross_entropy_with_logits") - 1
+    mine = []
+    for nd in net.nodes:
+        if nd.op == "resize_nearest":
+            mine.append(["resize_nearest_neighbor", {"align_corners": False}])
+            continue
+        sub = type("N", (), {"nodes": [nd], "variables": net.variables})()
+        mine += product_trace(sub)
+    assert mine == live[:n_loss]
+    assert [t for t in live[n_loss:] if t[0] != "resize_nearest_neighbor"][:6] == (
+        [["weighted_cross_entropy_with_logits", {"pos_weight": 1.0}]] * 5 + [["add_n", {"n": 5}]])
+
+
+def test_head_oracle_train_step_reproduces_the_reference_code():
+    meta, z = load("HEAD")
+    cfg = meta["config"]
+    params = {n: param_value(n, s, kind_of(n)) for n, s, _ in meta["variables"] if n in set(meta["train_op_vars"])}
+    image, label = _head_inputs(z)
+    # HEAD's schedule differs from the snapshots': power 0.8, 100001 steps (BAISRunnerTrain.py:33,49-50)
+    lr = float(O.poly_lr(cfg["learning_rate"], float(z["in/step"]), cfg["num_steps"], power=0.8))
+    close(lr, z["out/learning_rate"], 1e-6)
+    r = O.linknet_top_train_step(params, image, label, lr, torch.float64, pos_weight=1.0)
+    assert [list(a.shape) for a in r["segments"]] == meta["segment_shapes"]
+    for i, a in enumerate(r["segments"]):
+        close(summary("segment_%d" % i, a), z["out/segment_stats_%d" % i], 1e-9)
+        if "out/segment_%d" % i in z.files:
+            close(a, z["out/segment_%d" % i], 1e-9)
+        close(r["loss_segments"][i], z["out/loss_segment_%d" % i], 1e-11)
+    close(r["loss"], z["out/loss"], 1e-11)
+    worst = 0.0
+    for i, n in enumerate(meta["train_op_vars"]):
+        worst = max(worst, close(summary(n, r["grads"][n]), z["grad_stats"][i], 1e-7))
+        close(summary(n, r["new_params"][n]), z["new_value_stats"][i], 1e-7)
+        if "grad/" + n in z.files:
+            close(r["grads"][n], z["grad/" + n], 1e-8)
+    print("HEAD: %d gradients; worst gradient-summary error %.2e" % (len(meta["train_op_vars"]), worst))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # CUDA f32 path <-> reference code (runs last in the -m gpu suite)
 # --------------------------------------------------------------------------------------------------------------
 F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
