@@ -26,8 +26,8 @@ SNAPSHOT = {
     "5COCO": dict(num_segment=3, kind="softmax", pos_weight=1.0, class_weight=0.2, lr=5e-3, num_steps=1000001),
     # variant B (back/90AttentionSingle2/BAISRunnerTrain.py:30-52,116-156): vgg_16 trunk + attention cascade,
     # loss = mean 2-channel weighted CE of the four attention maps + class CE
-    "90AttentionSingle2": dict(num_segment=1, kind="linknet_b", pos_weight=3.0, class_weight=1.0, lr=5e-3,
-                               num_steps=500001),
+    "90AttentionSingle2": dict(num_segment=1, kind="linknet_b", pos_weight=3.0, class_weight=1.0, lr=5e-4,
+                               num_steps=500001),      # (:26 learning_rate = 5e-4 -- a tenth of the PSPNet snapshots')
     # cascaded attention re-decoding (back/8AttentionU/BAISRunnerTrain.py:28-38,161-193): 2AddClass trunk + four
     # pyramid decoders; loss on the sigmoid outputs (2 x softmax CE, 2 x doubled weighted BCE) + 0.1 * four class CEs
     "8AttentionU": dict(num_segment=4, kind="cascade", pos_weight=3.0, class_weight=0.1, lr=5e-3, num_steps=500001),

@@ -88,18 +88,25 @@ def stub_missing_data_dependencies():
                 setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
 
 
-def import_reference(snapshot):
-    """Import the snapshot's BAISRunnerTrain from /root/reference with the shim as `tensorflow`."""
+def import_reference(snapshot, slim=False):
+    """Import the snapshot's BAISRunnerTrain from /root/reference with the shim as `tensorflow` (slim=True: with
+    /root/reference/slim on the path for `from nets import nets_factory`, the reference's vendored model zoo)."""
     stub_missing_data_dependencies()
     for m in list(sys.modules):
-        if m in REF_MODULES or m.startswith("nets."):
+        if m in REF_MODULES or m.startswith("nets"):
             del sys.modules[m]
     d = os.path.join(REF, "back", snapshot) if snapshot else REF
-    sys.path.insert(0, d)
+    paths = [d] + ([os.path.join(REF, "slim")] if slim else [])
+    if slim:
+        import tensorflow.contrib.slim as slim_shim
+        slim_shim.shim_reset_collections()
+    for q in reversed(paths):
+        sys.path.insert(0, q)
     try:
         mod = importlib.import_module("BAISRunnerTrain")
     finally:
-        sys.path.remove(d)
+        for q in paths:
+            sys.path.remove(q)
     assert os.path.realpath(mod.__file__).startswith(os.path.realpath(d)), mod.__file__
     return mod
 
@@ -368,7 +375,78 @@ def run_head():
                            len(st.trace), float(val(tr.loss)), meta["segment_shapes"]))
 
 
-OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head}
+def run_variant_b():
+    """back/90AttentionSingle2 (the "point-attention x slim backbone" model): the whole unmodified Train.__init__ --
+    its Data reader on tests/golden/voc_mini (image, Gaussian click map, {0,1} attention labels, class ids),
+    LinkNet(image, mask).build() over slim's vgg_16, cal_loss, both optimizers.  The script hard-codes the class head
+    for 720^2 inputs (p_size=15, k_size=3 on the 45x45 block4), so this runs at 720^2, batch 1."""
+    import tempfile
+    mod = import_reference("90AttentionSingle2", slim=True)
+    readers = []
+    ref_data_cls = mod.Data
+
+    class RecordingData(ref_data_cls):
+        def __init__(self, *a, **k):
+            ref_data_cls.__init__(self, *a, **k)
+            readers.append(self)
+
+    mod.Data = RecordingData
+    SB, step, batch = 720, 250000, {}
+
+    def feeds(i, dtype, shape):
+        # placeholder order in Train.__init__: image, mask, label_seg, label_cls, step
+        if not batch:
+            np.random.seed(9)
+            data, mask, att, cls = readers[0].next_batch_train()
+            batch.update(data=np.asarray(data, dtype=np.float32), mask=np.asarray(mask, dtype=np.float32),
+                         att=np.asarray(att).astype(np.int64), cls=np.asarray(cls).astype(np.int64))
+        return [batch["data"], batch["mask"], batch["att"], batch["cls"], np.float32(step)][i]
+
+    tf.shim_reset(param_value, feeds)
+    voc = os.path.join(HERE, "voc_mini") + "/"
+    with tempfile.TemporaryDirectory() as tmp:
+        tr = mod.Train(batch_size=1, input_size=[SB, SB], log_dir=os.path.join(tmp, "log"), data_root_path=voc,
+                       train_list="ImageSets/Segmentation/train.txt", data_path="JPEGImages/",
+                       annotation_path="SegmentationObject/", class_path="SegmentationClass/", is_test=False)
+    st = tf.shim_state()
+    u8 = np.round(batch["data"] * 255).astype(np.uint8)
+    assert np.array_equal(u8.astype(np.float32) / np.float32(255), batch["data"])
+    arrays = {"in/image_u8": u8, "in/mask": batch["mask"], "in/label_segment": batch["att"].astype(np.uint8),
+              "in/label_classes": batch["cls"], "in/step": np.float32(step)}
+    for i, a in enumerate(tr.attentions):
+        v = val(a)
+        arrays["out/attention_stats_%d" % i] = summary("attention_%d" % i, v)
+        if v.size <= 20000:
+            arrays["out/attention_%d" % i] = v
+        arrays["out/loss_attention_%d" % i] = val(tr.loss_segments[i])
+    arrays["out/class_0"] = val(tr.classes[0])
+    for k in ("loss", "loss_segment_all", "loss_class_all", "pred_classes", "accuracy_classes", "learning_rate"):
+        arrays["out/" + k] = val(getattr(tr, k))
+    grad_arrays(arrays, tr.train_op, always=("attention_1/attention_1_attention/a_conv_3",
+                                             "attention_4/attention_4_attention/a_conv_3",
+                                             "attention_4/segment_attention_4_decoder/class_attention_fc",
+                                             "vgg_16/conv1/conv1_1"))
+    meta = {
+        "snapshot": "90AttentionSingle2",
+        "reference_files": ["back/90AttentionSingle2/BAISRunnerTrain.py", "back/90AttentionSingle2/BAISNet.py",
+                            "back/90AttentionSingle2/BAISData.py", "slim/nets/nets_factory.py", "slim/nets/vgg.py"],
+        "config": dict(input_size=[SB, SB], batch_size=1, num_classes=tr.num_classes, learning_rate=5e-4,
+                       num_steps=tr.num_steps),
+        "step": step, "attention_shapes": [[int(s_) for s_ in a.t.shape] for a in tr.attentions],
+        "segments": len(tr.segments), "classes": len(tr.classes),
+        "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)] for v in st.variables.values()],
+        "train_op_vars": tr.train_op.var_names, "train_attention_op_vars": tr.train_attention_op.var_names,
+        "trace": [[op, attrs] for op, attrs in st.trace],
+    }
+    save("90AttentionSingle2", arrays, meta)
+    print("90AttentionSingle2: %d variables (%d with a gradient, %d by the attention-only op), %d primitive ops; "
+          "loss %.9f (attention %.9f, classes %.9f), lr %.9g, attentions %s"
+          % (len(st.variables), len(tr.train_op.var_names), len(tr.train_attention_op.var_names), len(st.trace),
+             float(val(tr.loss)), float(val(tr.loss_segment_all)), float(val(tr.loss_class_all)),
+             float(val(tr.learning_rate)), meta["attention_shapes"]))
+
+
+OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

@@ -163,6 +163,10 @@ class Tensor(object):
     __rtruediv__ = _rbin(lambda a, b: a / b)
     __div__ = __truediv__
     __neg__ = lambda self: Tensor(-self.t)      # noqa: E731
+    __gt__ = _bin(lambda a, b: a > b)
+    __ge__ = _bin(lambda a, b: a >= b)
+    __lt__ = _bin(lambda a, b: a < b)
+    __le__ = _bin(lambda a, b: a <= b)
 
 
 class Variable(Tensor):

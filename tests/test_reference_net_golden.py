@@ -399,6 +399,70 @@ def test_head_oracle_train_step_reproduces_the_reference_code():
 
 
 # --------------------------------------------------------------------------------------------------------------
+# F1: variant B (back/90AttentionSingle2) -- the reference's whole Train.__init__ at the 720^2 its class head is
+# hard-coded for (p_size=15, k_size=3 on the 45x45 block4), batch 1 from its own reader on tests/golden/voc_mini
+# --------------------------------------------------------------------------------------------------------------
+def _variant_b_inputs(z):
+    image = z["in/image_u8"].astype(np.float32) / np.float32(255)
+    return image, z["in/mask"], z["in/label_segment"].astype(np.int64), z["in/label_classes"]
+
+
+def test_variant_b_inventory_is_the_reference_codes():
+    meta, z = load("90AttentionSingle2")
+    with_grad = set(meta["train_op_vars"])
+    trainable = [(n, tuple(s)) for n, s, t in meta["variables"] if t]
+    specs = O.linknet_b_specs(meta["config"]["num_classes"], 1.0)
+    on_path = [(n, s) for n, s in trainable if not n.startswith(("vgg_16/fc6", "vgg_16/fc7"))]
+    assert [(n, tuple(s)) for n, s in specs.items()] == on_path
+    # no gradient: vgg_16's fc6 / fc7 (never read) and the finest attention block's a_conv_o (its output feeds nothing)
+    assert [n for n, _ in trainable if n not in with_grad] == [
+        "vgg_16/fc6/weights", "vgg_16/fc6/biases", "vgg_16/fc7/weights", "vgg_16/fc7/biases",
+        "attention_1/attention_1_attention/a_conv_o/weights"]
+    assert meta["segments"] == 0 and meta["classes"] == 1
+    assert meta["train_attention_op_vars"] == [n for n, _ in trainable if "attention" in n and n in with_grad]
+    from basi_b200.BAISNet import LinkNet
+    from basi_b200.BAISPSPNet import Placeholder
+    S = meta["config"]["input_size"][0]
+    net = LinkNet(Placeholder((None, S, S, 3)), Placeholder((None, S, S, 1), name="mask"), True,
+                  num_classes=meta["config"]["num_classes"], p_size=15, k_size=3)
+    assert list(net.variables.items()) == on_path
+    _, atts, clss = net.build()
+    assert [[1] + list(nd.shape) for nd in atts] == meta["attention_shapes"] and len(clss) == 1
+    snap = product_snapshot_table()["90AttentionSingle2"]
+    assert snap["lr"] == meta["config"]["learning_rate"] and snap["num_steps"] == meta["config"]["num_steps"]
+
+
+def test_variant_b_oracle_train_step_reproduces_the_reference_code():
+    meta, z = load("90AttentionSingle2")
+    cfg = meta["config"]
+    params = {n: param_value(n, s, kind_of(n)) for n, s, t in meta["variables"]
+              if t and not n.startswith(("vgg_16/fc6", "vgg_16/fc7"))}
+    image, mask, label, cls = _variant_b_inputs(z)
+    lr = float(O.poly_lr(cfg["learning_rate"], float(z["in/step"]), cfg["num_steps"]))
+    close(lr, z["out/learning_rate"], 1e-6)
+    r = O.linknet_b_train_step(params, image, mask, label, cls, lr, torch.float64, p_size=15, pos_weight=3.0)
+    assert [list(a.shape) for a in r["attentions"]] == meta["attention_shapes"]
+    for i, a in enumerate(r["attentions"]):
+        close(summary("attention_%d" % i, a), z["out/attention_stats_%d" % i], 1e-9)
+        if "out/attention_%d" % i in z.files:
+            close(a, z["out/attention_%d" % i], 1e-9)
+    close(r["cls_logits"], z["out/class_0"], 1e-9)
+    close(r["loss"], z["out/loss"], 1e-11)
+    close(r["loss_attention"], z["out/loss_segment_all"], 1e-11)
+    close(r["loss_classes"], z["out/loss_class_all"], 1e-11)
+    worst = 0.0
+    for i, n in enumerate(meta["train_op_vars"]):
+        worst = max(worst, close(summary(n, r["grads"][n]), z["grad_stats"][i], 1e-7))
+        close(summary(n, r["new_params"][n]), z["new_value_stats"][i], 1e-7)
+        if "grad/" + n in z.files:
+            close(r["grads"][n], z["grad/" + n], 1e-8)
+    # the variable without a gradient stays where it was
+    n0 = "attention_1/attention_1_attention/a_conv_o/weights"
+    assert not np.any(r["grads"][n0]) and np.array_equal(r["new_params"][n0], params[n0].astype(np.float64))
+    print("90AttentionSingle2: %d gradients; worst gradient-summary error %.2e" % (len(meta["train_op_vars"]), worst))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # CUDA f32 path <-> reference code (runs last in the -m gpu suite)
 # --------------------------------------------------------------------------------------------------------------
 F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
