@@ -58,6 +58,19 @@ SNAPSHOTS = {
                               "raw_output_segment", "raw_output_classes", "pred_segment", "pred_classes",
                               "loss_segment", "loss_classes", "loss", "accuracy_segment", "accuracy_classes",
                               "step_ph", "train_op", "train_classes_op", "learning_rate")),
+    "3ThreeClass": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=21, num_segment=3, ratio=8,
+                                   last_pool_size=S // 8, filter_number=F, learning_rate=5e-3, num_steps=500001),
+                        label_values=3, label_dtype="int", seg="conv6_n_3", fc="class_attention_fc", step=31337,
+                        ret=("image_placeholder", "label_segment_placeholder", "label_classes_placeholder",
+                             "raw_output_segment", "raw_output_classes", "pred_segment", "pred_classes",
+                             "loss_segment", "loss_classes", "loss", "accuracy_segment", "accuracy_classes",
+                             "step_ph", "train_op", "train_classes_op", "learning_rate")),
+    # the segment-only snapshot (cfg2): no class head, build_net returns a different tuple; canonical names on the right
+    "1NoClass": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=1, ratio=8, last_pool_size=S // 8,
+                                filter_number=F, learning_rate=1e-2, num_steps=400001),
+                     label_values=2, label_dtype="float", seg="conv6_n", fc=None, step=200000, no_class=True,
+                     ret=("image_placeholder", "label_segment_placeholder", "loss", "accuracy_0", "accuracy_1",
+                          "step_ph", "train_op", "learning_rate", "raw_output_segment", "pred_segment")),
     "5COCO": dict(attrs=dict(input_size=(S, S), batch_size=B, num_classes=81, num_segment=3, ratio=8,
                              attention_class=2, last_pool_size=S // 8, filter_number=F, learning_rate=5e-3,
                              num_steps=1000001),
@@ -115,6 +128,21 @@ def val(x):
     return x.t.detach().numpy() if isinstance(x, tf.Tensor) else np.asarray(x)
 
 
+def save(name, arrays, meta):
+    out = os.path.join(HERE, "reference_net_%s" % name)
+    np.savez_compressed(out + ".npz", **arrays)
+    with open(out + ".json", "w") as f:
+        json.dump(meta, f, separators=(",", ":"))
+
+
+def grad_arrays(arrays, top, always=()):
+    arrays["grad_stats"] = np.stack([summary(n, top.grads[n]) for n in top.var_names])
+    arrays["new_value_stats"] = np.stack([summary(n, top.new_values[n]) for n in top.var_names])
+    for n in top.var_names:
+        if (n in FULL_GRADS or n.startswith(always)) and top.grads[n].size <= 20000:
+            arrays["grad/" + n] = top.grads[n]
+
+
 def run_pspnet_snapshot(snapshot, cfg):
     mod = import_reference(snapshot)
     captured = []
@@ -130,7 +158,8 @@ def run_pspnet_snapshot(snapshot, cfg):
     data, lab, cls = make_inputs(B, S, seed=11, n_label_values=cfg["label_values"],
                                  num_classes=cfg["attrs"]["num_classes"])
     lab_feed = lab.astype(np.float32) if cfg["label_dtype"] == "float" else lab
-    tf.shim_reset(param_value, [data, lab_feed, cls, np.float32(cfg["step"])])
+    feeds = [data, lab_feed] + ([] if cfg.get("no_class") else [cls]) + [np.float32(cfg["step"])]
+    tf.shim_reset(param_value, feeds)
 
     tr = mod.Train.__new__(mod.Train)                      # no __init__: that one opens sessions / readers / writers
     for k, v in cfg["attrs"].items():
@@ -157,14 +186,9 @@ def run_pspnet_snapshot(snapshot, cfg):
             arrays["layer/" + name] = val(t)
     arrays["layer_stats"] = np.stack(layer_stats)
 
-    top, tcls = ret["train_op"], ret["train_classes_op"]
-    arrays["grad_stats"] = np.stack([summary(n, top.grads[n]) for n in top.var_names])
-    arrays["new_value_stats"] = np.stack([summary(n, top.new_values[n]) for n in top.var_names])
-    full = [n for n in top.var_names if (n in FULL_GRADS or n.startswith(("class_attention", cfg["seg"])))
-            and top.grads[n].size <= 20000]                # (class_attention_conv/weights is 0.8 M values: summary only)
-    for n in full:
-        arrays["grad/" + n] = top.grads[n]
-    for n in tcls.var_names:                               # the class-only op must produce the same gradients
+    top, tcls = ret["train_op"], ret.get("train_classes_op")
+    grad_arrays(arrays, top, always=("class_attention", cfg["seg"]))   # (class_attention_conv/weights: summary only)
+    for n in (tcls.var_names if tcls else []):             # the class-only op must produce the same gradients
         assert np.array_equal(tcls.grads[n], top.grads[n])
 
     meta = {
@@ -174,33 +198,15 @@ def run_pspnet_snapshot(snapshot, cfg):
         "seg": cfg["seg"], "fc": cfg["fc"], "step": cfg["step"],
         "layers": [[n, s] for n, s in zip(layer_names, layer_shapes)],
         "variables": [[v.full_name, [int(s) for s in v.t.shape], bool(v.trainable)] for v in st.variables.values()],
-        "train_op_vars": top.var_names, "train_classes_op_vars": tcls.var_names,
+        "train_op_vars": top.var_names, "train_classes_op_vars": tcls.var_names if tcls else [],
         "trace": [[op, attrs] for op, attrs in st.trace[:net.ops_issued]],
         "trace_train": [[op, attrs] for op, attrs in st.trace[net.ops_issued:]],
     }
-    out = os.path.join(HERE, "reference_net_%s" % snapshot)
-    np.savez_compressed(out + ".npz", **arrays)
-    with open(out + ".json", "w") as f:
-        json.dump(meta, f, separators=(",", ":"))
+    save(snapshot, arrays, meta)
     print("%s: %d layers, %d variables (%d trained), %d primitive ops; loss %.9f (segment %.9f, classes %.9f), lr %.9g"
           % (snapshot, len(layer_names), len(st.variables), len(top.var_names), len(st.trace),
-             float(val(ret["loss"])), float(val(ret["loss_segment"])), float(val(ret["loss_classes"])),
-             float(val(ret["learning_rate"]))))
-
-
-def save(name, arrays, meta):
-    out = os.path.join(HERE, "reference_net_%s" % name)
-    np.savez_compressed(out + ".npz", **arrays)
-    with open(out + ".json", "w") as f:
-        json.dump(meta, f, separators=(",", ":"))
-
-
-def grad_arrays(arrays, top, always=()):
-    arrays["grad_stats"] = np.stack([summary(n, top.grads[n]) for n in top.var_names])
-    arrays["new_value_stats"] = np.stack([summary(n, top.new_values[n]) for n in top.var_names])
-    for n in top.var_names:
-        if (n in FULL_GRADS or n.startswith(always)) and top.grads[n].size <= 20000:
-            arrays["grad/" + n] = top.grads[n]
+             float(val(ret["loss"])), float(val(ret.get("loss_segment", ret["loss"]))),
+             float(val(ret["loss_classes"])) if "loss_classes" in ret else 0.0, float(val(ret["learning_rate"]))))
 
 
 def run_attention_u():

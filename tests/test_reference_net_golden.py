@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(HERE, "golden"))
 from oracle import basi_oracle as O                       # noqa: E402
 from ref_net_common import kind_of, param_value, summary  # noqa: E402
 
-SNAPSHOTS = ("2AddClass", "4BorderClass", "5COCO")
+SNAPSHOTS = ("1NoClass", "2AddClass", "3ThreeClass", "4BorderClass", "5COCO")
 
 
 def load(snapshot):
@@ -64,7 +64,7 @@ def product_snapshot_table():
 def test_oracle_parameter_inventory_is_the_reference_codes(snapshot):
     meta, _ = load(snapshot)
     cfg = meta["config"]
-    specs = O.param_specs(snapshot, cfg["num_classes"], cfg["num_segment"], cfg["filter_number"])
+    specs = O.param_specs(snapshot, cfg["num_classes"], cfg.get("num_segment", 1), cfg["filter_number"])
     ref = [(n, tuple(s)) for n, s, trainable in meta["variables"] if trainable]
     assert [(n, tuple(s)) for n, s in specs.items()] == ref          # names, shapes AND creation order
     # what the reference's code creates besides: the moving statistics of every tf.layers.batch_normalization
@@ -82,6 +82,7 @@ def test_oracle_train_step_reproduces_the_reference_code(snapshot):
     cfg = meta["config"]
     snap = product_snapshot_table()[snapshot]
     assert snap["lr"] == cfg["learning_rate"] and snap["num_steps"] == cfg["num_steps"]
+    cfg.setdefault("num_segment", 1)                      # (1NoClass has no such attribute: one logit channel)
     assert snap["num_segment"] == cfg["num_segment"]
     params = reference_params(meta)
     layers = [n for n, _ in meta["layers"]]
@@ -100,15 +101,17 @@ def test_oracle_train_step_reproduces_the_reference_code(snapshot):
         compared += 1
     assert compared >= 270, compared                       # every bottleneck convolution / batch norm / junction, the branches, heads
     close(r["seg_logits"], z["out/raw_output_segment"], 1e-9)
-    close(r["cls_logits"], z["out/raw_output_classes"], 1e-9)
     close(r["loss"], z["out/loss"], 1e-11)
-    close(r["loss_segment"], z["out/loss_segment"], 1e-11)
-    close(r["loss_classes"], z["out/loss_classes"], 1e-11)
-    pred, pcls = O.predict_train(r["seg_logits"], r["cls_logits"])
-    assert np.array_equal(pred, z["out/pred_segment"]) and np.array_equal(pcls, z["out/pred_classes"])
-    # the weight of the class term is whatever the reference's add_n used
-    w = (float(z["out/loss"]) - float(z["out/loss_segment"])) / float(z["out/loss_classes"])
-    assert abs(w - snap["class_weight"]) < 1e-12
+    if meta["fc"]:
+        close(r["cls_logits"], z["out/raw_output_classes"], 1e-9)
+        close(r["loss_segment"], z["out/loss_segment"], 1e-11)
+        close(r["loss_classes"], z["out/loss_classes"], 1e-11)
+        # the weight of the class term is whatever the reference's add_n used
+        w = (float(z["out/loss"]) - float(z["out/loss_segment"])) / float(z["out/loss_classes"])
+        assert abs(w - snap["class_weight"]) < 1e-12
+    pred, pcls = O.predict_train(r["seg_logits"], r.get("cls_logits"))
+    assert np.array_equal(pred, z["out/pred_segment"])
+    assert pcls is None or np.array_equal(pcls, z["out/pred_classes"])
     # every gradient and the SGD update
     names = meta["train_op_vars"]
     worst = 0.0
@@ -158,7 +161,7 @@ def build_product_net(meta):
     cfg = meta["config"]
     S = cfg["input_size"][0]
     return PSPNet({"data": Placeholder((None, S, S, 4))}, is_training=True, num_classes=cfg["num_classes"],
-                  num_segment=cfg["num_segment"], last_pool_size=cfg["last_pool_size"],
+                  num_segment=cfg.get("num_segment", 1), last_pool_size=cfg["last_pool_size"],
                   filter_number=cfg["filter_number"], attention_class=cfg.get("attention_class"),
                   variant=meta["snapshot"])
 
@@ -232,9 +235,9 @@ def test_product_builder_registers_the_reference_codes_graph(snapshot):
     cfg = meta["config"]
     seg_loss = (["weighted_cross_entropy_with_logits", {"pos_weight": snap["pos_weight"]}] if snap["kind"] == "bce"
                 else ["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_segment"]}])
-    assert meta["trace_train"] == [["resize_nearest_neighbor", {"align_corners": False}], seg_loss,
-                                   ["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_classes"]}],
-                                   ["add_n", {"n": 2}]]
+    class_part = ([["sparse_softmax_cross_entropy_with_logits", {"classes": cfg["num_classes"]}], ["add_n", {"n": 2}]]
+                  if meta["fc"] else [])
+    assert meta["trace_train"] == [["resize_nearest_neighbor", {"align_corners": False}], seg_loss] + class_part
 
 
 @pytest.mark.parametrize("snapshot", SNAPSHOTS)
@@ -244,7 +247,7 @@ def test_product_class_only_subset_is_the_reference_var_list(snapshot):
     net = build_product_net(meta)
     # Engine.set_trainable('class_attention') selects by the same substring rule over the same names
     assert [n for n in net.variables if "class_attention" in n] == meta["train_classes_op_vars"]
-    assert len(meta["train_classes_op_vars"]) == 4
+    assert len(meta["train_classes_op_vars"]) == (4 if meta["fc"] else 0)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -487,6 +490,7 @@ def test_cuda_train_step_matches_the_reference_code(snapshot):
     from basi_b200.engine import Engine
     meta, z = load(snapshot)
     cfg = meta["config"]
+    cfg.setdefault("num_segment", 1)
     snap = product_snapshot_table()[snapshot]
     B = cfg["batch_size"]
     params = reference_params(meta)
@@ -505,17 +509,19 @@ def test_cuda_train_step_matches_the_reference_code(snapshot):
                        cfg["num_segment"], cfg["last_pool_size"], snap["pos_weight"], snap["class_weight"], lr,
                        torch.float32, cfg.get("attention_class"))
     loss, lseg, lcls = eng.losses()
-    assert abs(lseg - float(z["out/loss_segment"])) < F32_TOL * max(1, abs(float(z["out/loss_segment"])))
-    assert abs(lcls - float(z["out/loss_classes"])) < F32_TOL * max(1, abs(float(z["out/loss_classes"])))
     assert abs(loss - float(z["out/loss"])) < F32_TOL * max(1, abs(float(z["out/loss"])))
     logits = eng.seg_logits.t.cpu().numpy()
     e_seg = _rel(logits.reshape(z["out/raw_output_segment"].shape), z["out/raw_output_segment"])
     assert e_seg < F32_TOL, e_seg
-    cl = eng.cls_logits.t.cpu().numpy().reshape(B, -1)
-    e_cls = _rel(cl, z["out/raw_output_classes"])
-    assert e_cls < F32_TOL + 3 * _rel(r32["cls_logits"], z["out/raw_output_classes"]), e_cls
     assert np.array_equal(eng.pred_seg.cpu().numpy().reshape(-1), z["out/pred_segment"].reshape(-1))
-    assert np.array_equal(eng.pred_cls.cpu().numpy().reshape(-1), z["out/pred_classes"].reshape(-1))
+    e_cls = 0.0
+    if meta["fc"]:
+        assert abs(lseg - float(z["out/loss_segment"])) < F32_TOL * max(1, abs(float(z["out/loss_segment"])))
+        assert abs(lcls - float(z["out/loss_classes"])) < F32_TOL * max(1, abs(float(z["out/loss_classes"])))
+        cl = eng.cls_logits.t.cpu().numpy().reshape(B, -1)
+        e_cls = _rel(cl, z["out/raw_output_classes"])
+        assert e_cls < F32_TOL + 3 * _rel(r32["cls_logits"], z["out/raw_output_classes"]), e_cls
+        assert np.array_equal(eng.pred_cls.cpu().numpy().reshape(-1), z["out/pred_classes"].reshape(-1))
     # layers stored in full
     checked = []
     for key in z.files:
