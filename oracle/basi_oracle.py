@@ -6,19 +6,33 @@ reference computes on its hot path.  It is the *checker*: only ``tests/``,
 reference`` legs may import it.  Nothing under ``instance-segment-basi_b200/``
 (the product) imports it.
 
-PARITY: the DATA functions (``mask_gaussian``, ``pack_input``, ``encode_labels_binary`` / ``_three`` / ``_border``,
-``sample_click``) are PINNED bit for bit against outputs of the reference's own BAISData.py code, which is numpy + PIL
-and runs in the build container (tests/golden/make_reference_golden.py -> tests/golden/reference_data.npz ->
-tests/test_reference_golden.py).  The CONVOLUTION PADDING / STRIDE SEMANTICS (``conv2d`` with 'SAME' at stride 1 and 2 on
-even and odd inputs, explicit padding + 'VALID', the strided 1x1 convolution = subsample; ``tf_same_pad``) are PINNED
-against the numeric golden vectors of the reference's own vendored TF-slim tests (slim/nets/resnet_v1_test.py:58-153,
-extracted by tests/golden/make_slim_golden.py -> tests/golden/slim_reference_tests.json).  The REST OF THE NETWORK
-ARITHMETIC is UNPINNED: it lives in TensorFlow 1.x, which is third-party, un-vendored and un-pinned (no requirements
-file; TF1 is implied by ``tf.contrib.slim`` / ``tf.placeholder``), it cannot be imported in this container, and the
-reference ships no other numeric test, golden vector or fixture for this path.  For
-batch norm, pooling, resize, gating, the losses and SGD the oracle therefore follows the reference's own call sites
-plus the published TF1 op semantics, and is pinned only by hand-computed known-answer cases and fp64
-finite-difference checks (tests/test_oracle.py).
+PARITY -- what is pinned against the reference itself, and how:
+
+* DATA functions (``mask_gaussian``, ``pack_input``, ``encode_labels_binary`` / ``_three`` / ``_border``,
+  ``sample_click``): bit for bit against outputs of the reference's own BAISData.py code, which is numpy + PIL and runs
+  in the build container (tests/golden/make_reference_golden.py -> reference_data.npz -> tests/test_reference_golden.py).
+* CONVOLUTION PADDING / STRIDE SEMANTICS (``conv2d`` 'SAME' at stride 1 and 2 on even and odd inputs, explicit padding +
+  'VALID', strided 1x1 = subsample, ``tf_same_pad``): against the numeric golden vectors of the reference's own
+  vendored TF-slim tests (slim/nets/resnet_v1_test.py:58-153 -> tests/golden/slim_reference_tests.json).
+* NETWORK STRUCTURE, LOSS COMPOSITION, LEARNING-RATE FORMULA, OPTIMIZER VARIABLE LISTS of every network here
+  (``pspnet_forward`` / ``losses`` / ``train_step`` for 1NoClass, 2AddClass, 3ThreeClass, 4BorderClass, 5COCO;
+  ``attention_u_*``; ``linknet_b_*``; ``linknet_top_*``): against the reference's OWN Python executed in the build
+  container.  tests/golden/make_reference_net_golden.py imports the unmodified reference modules over an eager float64
+  stand-in for the ~60 ``tf.*`` / ``slim.*`` calls they make (tests/golden/tf1_shim) and runs the reference's own
+  ``Train.build_net()`` / whole ``Train.__init__`` (for 8AttentionU, HEAD and 90AttentionSingle2 including the reference's
+  own Data reader on tests/golden/voc_mini and slim's vgg_16 through nets_factory); tests/test_reference_net_golden.py
+  holds this oracle to what that produced -- every exposed layer, logits, predictions, losses, learning rate, every
+  gradient and the SGD update, to float64 round-off (1e-9 ... 1e-15).  Two discrepancies were FOUND that way and fixed:
+  the hand-unrolled trunk of back/8AttentionU/BAISNet.py feeds the PRE-ReLU junction sum to 31 convolutions
+  (``_pspnet_trunk(wiring="8AttentionU")``), and variant B's base learning rate is 5e-4.
+* What that does NOT pin: the arithmetic of each TensorFlow primitive.  TensorFlow 1.x is third-party, un-vendored and
+  un-pinned (no requirements file; TF1 is implied by ``tf.contrib.slim`` / ``tf.placeholder``) and cannot be installed
+  here; the stand-in's primitives are a second, independently written restatement of the published TF1 op semantics
+  (NHWC tap-sum convolutions, window stacks, explicit bilinear matrices, float32 index arithmetic of
+  resize_nearest_neighbor) that agrees with this module's to round-off.  For batch norm, pooling, resize, gating and the
+  loss formulas "PARITY UNPINNED against TensorFlow's kernels" therefore still holds: they follow the reference's call
+  sites plus the published op definitions and are additionally held by hand-computed known-answer cases and fp64
+  finite-difference checks (tests/test_oracle.py).
 
 What each function restates (paths relative to /root/reference):
 

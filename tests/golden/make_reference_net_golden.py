@@ -452,7 +452,61 @@ def run_variant_b():
              float(val(tr.learning_rate)), meta["attention_shapes"]))
 
 
-OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b}
+def run_runner_one():
+    """cfg1, the reference's own CPU-runnable case: back/4BorderClass/BAISRunnerOne.py Runner(...).run(...) unmodified on
+    the reference's own fixture input/7.jpg with a click at [360, 480] -- Data.load_image (PIL decode + resize to
+    720^2, /255, Gaussian click map), PSPNet(is_training=True, filter_number=32, num_segment=4, last_pool_size=90),
+    sigmoid -> argmax, class argmax, and the PNG files the script writes."""
+    import inspect
+    import tempfile
+    from PIL import Image
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m == "BAISRunnerOne":
+            del sys.modules[m]
+    d = os.path.join(REF, "back", "4BorderClass")
+    sys.path.insert(0, d)
+    try:
+        mod = importlib.import_module("BAISRunnerOne")
+    finally:
+        sys.path.remove(d)
+    fed = {}
+
+    def feeds(i, dtype, shape):
+        # the script computes `final_batch_data` before it creates its placeholder: take it from the caller's frame
+        for fr in inspect.stack():
+            if "final_batch_data" in fr.frame.f_locals:
+                fed["data"] = np.asarray(fr.frame.f_locals["final_batch_data"], dtype=np.float32)
+                return fed["data"]
+        raise RuntimeError("final_batch_data not found")
+
+    tf.shim_reset(param_value, feeds)
+    del tf.SESSION_RUNS[:]
+    where = [360, 480]
+    with tempfile.TemporaryDirectory() as tmp:
+        mod.Runner(log_dir=os.path.join(tmp, "model"), save_dir=os.path.join(tmp, "out")).run(
+            result_filename="7_360_480_", image_filename=os.path.join(REF, "input", "7.jpg"), where=where)
+        files = {f: np.asarray(Image.open(os.path.join(tmp, "out", f))) for f in sorted(os.listdir(os.path.join(tmp, "out")))}
+    raw_output, sigmoid_output, predict_output, raw_classes, pred_classes = tf.SESSION_RUNS[-1]
+    st = tf.shim_state()
+    arrays = {"in/where": np.asarray(where), "in/click_map": fed["data"][0, :, :, 3],
+              "out/raw_output": raw_output, "out/predict_output": predict_output.astype(np.int64),
+              "out/raw_output_classes": raw_classes, "out/pred_classes": pred_classes}
+    for f, a in files.items():
+        if "pred" in f:
+            arrays["file/" + f] = a
+    meta = {"snapshot": "4BorderClass/BAISRunnerOne", "reference_files": ["back/4BorderClass/BAISRunnerOne.py",
+            "back/4BorderClass/BAISPSPNet.py", "back/4BorderClass/BAISData.py", "input/7.jpg"],
+            "config": dict(input_size=[720, 720], last_pool_size=90, filter_number=32, num_segment=4, num_classes=21),
+            "files": sorted(files), "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)]
+                                                  for v in st.variables.values()]}
+    save("RunnerOne", arrays, meta)
+    print("RunnerOne: files %s; predicted class %d; mask pixels per label %s"
+          % (sorted(files), int(pred_classes[0]), np.bincount(predict_output.reshape(-1), minlength=4).tolist()))
+
+
+OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b,
+          "RunnerOne": run_runner_one}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

@@ -448,6 +448,10 @@ def reduce_sum(input_tensor, axis=None, keepdims=False, name=None, **_):
     return Tensor(t.sum() if axis is None else t.sum(dim=axis, keepdim=keepdims), name)
 
 
+def sigmoid(x, name=None):
+    return nn.sigmoid(x, name)
+
+
 def equal(x, y, name=None):
     return Tensor(_val(x) == _val(y), name)
 
@@ -740,21 +744,44 @@ class _GradientDescentOptimizer(object):
 
 
 class _Inert(object):
-    """Saver / FileWriter / Session: control plane the scripts construct in __init__; nothing here is ever run."""
+    """Saver / FileWriter / Session: control plane the scripts construct.  Session.run(fetches, feed_dict) returns the
+    already (eagerly) computed values of the fetched tensors after checking that every fed value is the one its
+    placeholder was evaluated with -- enough for the reference's inference scripts, which build the graph and run it
+    once in the same method."""
 
     def __init__(self, *a, **k):
         self.graph = None
+        self.runs = []
 
-    def run(self, *a, **k):
-        return None
+    def run(self, fetches=None, feed_dict=None, **k):
+        if fetches is None:
+            return None
+        for ph, v in (feed_dict or {}).items():
+            assert isinstance(ph, Tensor) and np.array_equal(np.asarray(v, dtype=np.float64),
+                                                             ph.t.detach().numpy().astype(np.float64)), \
+                "Session.run: a fed value differs from the one the stand-in evaluated the graph with"
+
+        def value(f):
+            return None if f is None else f.t.detach().numpy()
+        out = [value(f) for f in fetches] if isinstance(fetches, (list, tuple)) else value(fetches)
+        self.runs.append(out)
+        SESSION_RUNS.append(out)
+        return out
 
     def __getattr__(self, name):
         raise NotImplementedError("control plane (%s): the stand-in evaluates eagerly, there is nothing to run" % name)
 
 
+SESSION_RUNS = []          # what every Session.run returned, in order (read by the golden generator)
+
+
 class _Train(object):
     GradientDescentOptimizer = _GradientDescentOptimizer
     Saver = _Inert
+
+    @staticmethod
+    def get_checkpoint_state(checkpoint_dir, latest_filename=None):
+        return None            # "No checkpoint file found.": the variables keep the values the provider gave them
 
 
 train = _Train()

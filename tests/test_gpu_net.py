@@ -572,12 +572,17 @@ def _cascade_case(S, B, F, seed=0):
 
 @pytest.mark.parametrize("precision", ["f32", "f16"])
 def test_cascade_train_step_matches_oracle(precision):
-    """Whole cascade (2AddClass trunk, 4 decoders, 4 class heads, cal_loss on the sigmoid outputs) forward / loss /
-    backward / SGD against the float64 oracle (oracle.attention_u_train_step)."""
+    """Whole cascade (the snapshot's own trunk wiring: 31 convolutions read the pre-ReLU junction sums; 4 decoders, 4
+    class heads, cal_loss on the sigmoid outputs) forward / loss / backward / SGD against the float64 oracle
+    (oracle.attention_u_train_step, itself held to the reference's own code by tests/test_reference_net_golden.py)."""
     from basi_b200.BAISNet import BAISNet, Placeholder
     from basi_b200.engine import Engine
     S, B, F = 80, 2, 8
-    params, data, lab, att, cls = _cascade_case(S, B, F)
+    # seed 5: with seed 0 one ReLU input of this net lies 1.1e-7 from zero (oracle.TRACE_RELU_MARGIN; seed 5: 1.7e-6), any
+    # float32 run flips that mask element against float64 and single gradients move by 1e-3 .. 3e-3 (measured on the
+    # B200: conv5_2_3x3/weights 3.1e-3 against a float32-oracle floor of 1.3e-4) -- a property of the input, see
+    # test_train_step_fp32_matches_oracle
+    params, data, lab, att, cls = _cascade_case(S, B, F, seed=5)
     net = BAISNet(Placeholder((None, S, S, 4)), is_training=True, num_classes=21, num_segment=4, segment_attention=1,
                   last_pool_size=S // 8, filter_number=F, attention_module_num=2)
     segs, atts, clss = net.build()
