@@ -64,18 +64,40 @@ class RunnerGUI(object):
         segment = np.asarray(np.where(predict == 1, 1, 0), dtype=np.uint8)
         return segment, cls
 
+    @staticmethod
+    def click_position(input_size, image_data, point_xy):
+        """(x, y) clicked in the displayed image -> [row, col] at the network's input size (BAISRunnerGUI.py:63-64)."""
+        return [int(input_size[0] * point_xy[1] / len(image_data)),
+                int(input_size[1] * point_xy[0] / len(image_data[0]))]
+
+    @staticmethod
+    def mask_to_image_size(segment, image_data):
+        """{0,1} uint8 mask at the input size -> the displayed image's size, BAISRunnerGUI.py:84:
+        ``Image.fromarray(segment).resize((w, h))`` with PIL's default filter -- no resample argument, like the
+        reference, so it is whatever the installed Pillow applies to an 'L' image (bicubic since Pillow 7; NEAREST,
+        which this method used before, differs from it on boundary pixels)."""
+        from PIL import Image
+        return np.asarray(Image.fromarray(segment).resize((len(image_data[0]), len(image_data))))
+
+    @staticmethod
+    def blend(image_data, segment, mask_color, opacity):
+        """The image the tool displays (BAISRunnerGUI.py:86-97): mask_color blended into the masked pixels."""
+        image_mask = np.ndarray(image_data.shape)
+        for c in range(3):
+            image_mask[:, :, c] = (1 - segment) * image_data[:, :, c] + segment * (
+                opacity * mask_color[c] + (1 - opacity) * image_data[:, :, c])
+        return image_mask.astype(np.uint8)
+
     def run_image(self, image_filename_or_data, point_xy):
         """One GUI iteration: original-resolution image + clicked (x, y) -> (mask at original size, class)."""
         from PIL import Image
         image_data = np.array(Image.open(image_filename_or_data)) if isinstance(image_filename_or_data, str) \
             else np.asarray(image_filename_or_data)
-        where = [int(self.input_size[0] * point_xy[1] / len(image_data)),
-                 int(self.input_size[1] * point_xy[0] / len(image_data[0]))]
+        where = self.click_position(self.input_size, image_data, point_xy)
         img = np.asarray(Image.fromarray(image_data.astype(np.uint8)).convert("RGB").resize(
             tuple(self.input_size), Image.BICUBIC), dtype=np.uint8)
         seg, cls = self.click(img, where)
-        seg = np.asarray(Image.fromarray(seg).resize((len(image_data[0]), len(image_data)), Image.NEAREST))
-        return seg, cls, where
+        return self.mask_to_image_size(seg, image_data), cls, where
 
 
 class Runner(object):

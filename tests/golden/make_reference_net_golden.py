@@ -505,8 +505,78 @@ def run_runner_one():
           % (sorted(files), int(pred_classes[0]), np.bincount(predict_output.reshape(-1), minlength=4).tolist()))
 
 
+def run_runner_gui():
+    """cfg1 as the reference's interactive tool runs it: back/4BorderClass/BAISRunnerGUI.py RunnerGUI(log_dir).run(
+    image, mask_color, opacity) unmodified, on input/7.jpg.  matplotlib is not installed (and there is no display): a
+    stand-in `matplotlib.pyplot` delivers ONE click through plt.ginput and ends the loop on the second call, and records
+    what the tool draws (plt.imshow of the blended image, plt.text of the class name).  `np.int` (removed from numpy
+    1.24, used at :62) is aliased to int for the run."""
+    import types
+    from PIL import Image
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m == "BAISRunnerGUI":
+            del sys.modules[m]
+    point = [130, 100]                                     # (x, y) in the 262 x 200 image
+    drawn = {"imshow": [], "text": [], "ginput": 0}
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.ion = plt.axis = plt.title = plt.clf = lambda *a, **k: None
+    plt.imshow = lambda img, *a, **k: drawn["imshow"].append(np.array(img))
+    plt.text = lambda x, y, s_, **k: drawn["text"].append(s_)
+
+    def ginput(n, timeout=0):
+        drawn["ginput"] += 1
+        if drawn["ginput"] > 1:
+            raise RuntimeError("window closed")            # the tool's own `except Exception` ends the loop
+        return [tuple(point)]
+    plt.ginput = ginput
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+    had_int = hasattr(np, "int")
+    if not had_int:
+        np.int = int
+    d = os.path.join(REF, "back", "4BorderClass")
+    sys.path.insert(0, d)
+    try:
+        mod = importlib.import_module("BAISRunnerGUI")
+    finally:
+        sys.path.remove(d)
+    image_file = os.path.join(REF, "input", "7.jpg")
+    image_data = np.array(Image.open(image_file))
+    # the stand-in evaluates the graph when it is built (load_net), so the batch the tool will feed after the click is
+    # prepared the way the tool prepares it (:63-67); Session.run then checks that the tool fed exactly this
+    where = [int(720 * point[1] / len(image_data)), int(720 * point[0] / len(image_data[0]))]
+    batch, _, _ = sys.modules["BAISData"].Data.load_image(image_data, where=where, image_size=[720, 720])
+    tf.shim_reset(param_value, [np.asarray(batch, dtype=np.float32)])
+    del tf.SESSION_RUNS[:]
+    try:
+        mod.RunnerGUI(log_dir="/nonexistent/model").run(image_file, mask_color=[255, 0, 0], opacity=0.5)
+    finally:
+        if not had_int:
+            del np.int
+        del sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"]
+    predict_output, pred_classes = tf.SESSION_RUNS[-1]
+    assert drawn["ginput"] == 2 and len(drawn["imshow"]) == 2 and len(drawn["text"]) == 1
+    blended = drawn["imshow"][1]
+    st = tf.shim_state()
+    arrays = {"in/point_xy": np.asarray(point), "in/where": np.asarray(where),
+              "out/predict_output": predict_output.astype(np.uint8), "out/pred_classes": pred_classes,
+              "out/blended": blended}
+    meta = {"snapshot": "4BorderClass/BAISRunnerGUI", "reference_files": ["back/4BorderClass/BAISRunnerGUI.py",
+            "back/4BorderClass/BAISPSPNet.py", "back/4BorderClass/BAISData.py", "input/7.jpg"],
+            "config": dict(input_size=[720, 720], last_pool_size=90, filter_number=32, num_segment=4, num_classes=21,
+                           mask_color=[255, 0, 0], opacity=0.5),
+            "class_name_drawn": drawn["text"][0],
+            "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)] for v in st.variables.values()]}
+    save("RunnerGUI", arrays, meta)
+    print("RunnerGUI: where %s, class %d (%s), mask pixels at 720^2 per label %s, blended image %s"
+          % (where, int(pred_classes[0]), drawn["text"][0], np.bincount(predict_output.reshape(-1), minlength=4).tolist(),
+             blended.shape))
+
+
 OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b,
-          "RunnerOne": run_runner_one}
+          "RunnerOne": run_runner_one, "RunnerGUI": run_runner_gui}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

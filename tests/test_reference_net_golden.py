@@ -530,6 +530,63 @@ def test_cuda_runner_one_matches_the_reference_script(tmp_path):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# cfg1 as the interactive tool runs it: back/4BorderClass/BAISRunnerGUI.py RunnerGUI.run, one click on input/7.jpg
+# --------------------------------------------------------------------------------------------------------------
+def _runner_gui_case():
+    from PIL import Image
+    meta, z = load("RunnerGUI")
+    image_data = np.array(Image.open(os.path.join(HERE, "golden", "input_7.jpg")))
+    params = {n: param_value(n, s, kind_of(n)) for n, s, t in meta["variables"] if t}
+    return meta, z, image_data, params
+
+
+def test_runner_gui_oracle_and_host_post_processing_reproduce_the_reference_tool():
+    """What the reference's GUI tool computed and DREW for one click: click position, upsampled argmax(sigmoid) map,
+    class, the mask at the displayed size and the blended image handed to plt.imshow."""
+    from basi_b200.BAISData import CategoryNames, Data
+    from basi_b200.BAISRunnerOne import RunnerGUI
+    meta, z, image_data, params = _runner_gui_case()
+    cfg = meta["config"]
+    point = [int(v) for v in z["in/point_xy"]]
+    where = RunnerGUI.click_position(cfg["input_size"], image_data, point)
+    assert where == [int(v) for v in z["in/where"]]
+    data = np.asarray(Data.load_image(image_data, where=where, image_size=cfg["input_size"])[0], dtype=np.float32)
+    with torch.no_grad():
+        out = O.pspnet_forward(O.to_torch(params, torch.float64), torch.as_tensor(data).to(torch.float64),
+                               "4BorderClass", cfg["num_segment"], cfg["last_pool_size"])
+    pred = O.predict_click(out["conv6_n_4"].numpy(), tuple(cfg["input_size"]))
+    assert np.mean(pred == z["out/predict_output"]) >= 0.99999          # (legacy bilinear in float32 vs float64: ties)
+    cls = int(np.argmax(out["class_attention_fc"].numpy(), -1)[0])
+    assert cls == int(z["out/pred_classes"][0]) and CategoryNames[cls] == meta["class_name_drawn"]
+    # host post-processing of the product on the reference's own argmax map: exactly the image the tool displayed
+    segment = np.squeeze(np.asarray(np.where(z["out/predict_output"][0] == 1, 1, 0), dtype=np.uint8))
+    small = RunnerGUI.mask_to_image_size(segment, image_data)
+    assert np.array_equal(RunnerGUI.blend(image_data, small, cfg["mask_color"], cfg["opacity"]), z["out/blended"])
+
+
+@pytest.mark.gpu
+def test_cuda_runner_gui_matches_the_reference_tool():
+    """The product's RunnerGUI.run_image (f32 mode, CUDA graph, device-side click map and legacy-bilinear argmax) on
+    tests/golden/input_7.jpg against what the reference's tool computed and drew for the same click."""
+    from basi_b200.BAISRunnerOne import RunnerGUI
+    meta, z, image_data, params = _runner_gui_case()
+    cfg = meta["config"]
+    gui = RunnerGUI(None, last_pool_size=cfg["last_pool_size"], variant="4BorderClass", num_classes=cfg["num_classes"],
+                    num_segment=cfg["num_segment"], filter_number=cfg["filter_number"], precision="f32")
+    gui.engine.set_params(params)
+    seg, cls, where = gui.run_image(os.path.join(HERE, "golden", "input_7.jpg"), [int(v) for v in z["in/point_xy"]])
+    assert where == [int(v) for v in z["in/where"]] and cls == int(z["out/pred_classes"][0])
+    full = np.asarray(np.where(gui.mask_dev.cpu().numpy()[0] == 1, 1, 0), dtype=np.uint8)
+    ref_full = np.squeeze(np.asarray(np.where(z["out/predict_output"][0] == 1, 1, 0), dtype=np.uint8))
+    agree = float(np.mean(full == ref_full))
+    assert agree >= 0.999, agree
+    blended = RunnerGUI.blend(image_data, seg, cfg["mask_color"], cfg["opacity"])
+    same = float(np.mean(np.all(blended == z["out/blended"], axis=-1)))
+    assert same >= 0.999, same
+    print("RunnerGUI: CUDA f32 vs the reference tool: mask agreement %.5f at 720^2, displayed image %.5f" % (agree, same))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # CUDA f32 path <-> reference code (runs last in the -m gpu suite)
 # --------------------------------------------------------------------------------------------------------------
 F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
