@@ -575,8 +575,71 @@ def run_runner_gui():
              blended.shape))
 
 
+def run_head_inference():
+    """Current HEAD's test script: BAISRunnerTest.py Inference(input_size, summary_dir, log_dir) -> load_model() ->
+    inference(image_path, image_index, save_path) unmodified on input/7.jpg at 224^2 (slim's vgg_16 through
+    nets_factory; pred_segment = argmax(segments[0]), the coarsest deep-supervised head; the .bmp it saves)."""
+    import inspect
+    import tempfile
+    from PIL import Image
+    import tensorflow.contrib.slim as slim_shim
+    slim_shim.shim_reset_collections()
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m.startswith("nets") or m == "BAISRunnerTest":
+            del sys.modules[m]
+    paths = [REF, os.path.join(REF, "slim")]
+    for q in reversed(paths):
+        sys.path.insert(0, q)
+    try:
+        mod = importlib.import_module("BAISRunnerTest")
+    finally:
+        for q in paths:
+            sys.path.remove(q)
+    SH = 224
+    image_file = os.path.join(REF, "input", "7.jpg")
+    # the graph is evaluated when it is built: feed what inference() will feed (Data.load_data, :137-138)
+    im = np.expand_dims(sys.modules["BAISData"].Data.load_data(image_path=image_file, input_size=[SH, SH]), axis=0)
+    # random ReLU-network parameters give a constant mask: a first pass measures the two logits of the head the script
+    # thresholds, the second pass shifts that head's bias to their median difference so the mask is a real pattern
+    head_bias = "attention_4/segment_side_4/d_s_conv_4/biases"
+    override = {}
+
+    def provider(n, s_, k):
+        return override[n] if n in override else param_value(n, s_, k)
+
+    for attempt in range(2):
+        slim_shim.shim_reset_collections()
+        tf.shim_reset(provider, [im])
+        del tf.SESSION_RUNS[:]
+        with tempfile.TemporaryDirectory() as tmp:
+            inf = mod.Inference(input_size=[SH, SH], summary_dir=os.path.join(tmp, "summary"),
+                                log_dir=os.path.join(tmp, "model"))
+            inf.load_model()
+            inf.inference(image_path=image_file, image_index=0, save_path=os.path.join(tmp, "out"))
+            bmp = np.asarray(Image.open(os.path.join(tmp, "out", "7.bmp")))
+        pred_segment = tf.SESSION_RUNS[-1][0]
+        if attempt == 0:
+            lg = val(inf.segments[0])
+            b = param_value(head_bias, (2,), "weights").astype(np.float64)
+            b[1] -= np.median(lg[..., 1] - lg[..., 0])
+            override[head_bias] = b.astype(np.float32)
+    assert 0.2 < pred_segment.mean() < 0.8, pred_segment.mean()
+    st = tf.shim_state()
+    arrays = {"out/pred_segment": pred_segment.astype(np.uint8), "file/7.bmp": bmp,
+              "out/segment_0": val(inf.segments[0]), "param_override/" + head_bias: override[head_bias]}
+    meta = {"snapshot": "HEAD/BAISRunnerTest.Inference",
+            "reference_files": ["BAISRunnerTest.py", "BAISNet.py", "BAISData.py", "slim/nets/vgg.py", "input/7.jpg"],
+            "config": dict(input_size=[SH, SH], num_classes=21),
+            "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)] for v in st.variables.values()]}
+    save("HEAD_Inference", arrays, meta)
+    print("HEAD Inference: pred_segment %s, foreground pixels %d, 7.bmp %s values %s"
+          % (pred_segment.shape, int(pred_segment.sum()), bmp.shape, np.unique(bmp).tolist()))
+
+
 OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b,
-          "RunnerOne": run_runner_one, "RunnerGUI": run_runner_gui}
+          "RunnerOne": run_runner_one, "RunnerGUI": run_runner_gui,
+          "HEAD_Inference": run_head_inference}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

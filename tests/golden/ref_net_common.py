@@ -15,10 +15,11 @@ def _rng(name, salt=0):
     return np.random.RandomState((zlib.crc32(name.encode()) + 7919 * salt) % (2 ** 31))
 
 
-def param_value(full_name, shape, kind="weights"):
+def param_value(full_name, shape, kind="weights", draw=0):
     """float32-representable 'trained-like' values: glorot-uniform weights / biases, gamma in [0.5, 1.5] (residual
-    increase branches [0.05, 0.25] so the 33-block trunk is not chaotic), beta in [-0.3, 0.3]."""
-    rng = _rng(full_name)
+    increase branches [0.05, 0.25] so the 33-block trunk is not chaotic), beta in [-0.3, 0.3].  `draw` selects another
+    independent set (a fixture whose default set gives a degenerate mask records the draw it used)."""
+    rng = _rng(full_name if not draw else "%s#%d" % (full_name, draw))
     shape = tuple(int(s) for s in shape)
     if kind == "gamma":
         lo, hi = (0.05, 0.25) if "increase_bn" in full_name else (0.5, 1.5)

@@ -587,6 +587,55 @@ def test_cuda_runner_gui_matches_the_reference_tool():
 
 
 # --------------------------------------------------------------------------------------------------------------
+# F2 inference: the reference's BAISRunnerTest.Inference(...).load_model() / .inference(...) on input/7.jpg
+# --------------------------------------------------------------------------------------------------------------
+def _head_inference_case():
+    meta, z = load("HEAD_Inference")
+    params = {n: param_value(n, s, kind_of(n)) for n, s, t in meta["variables"]
+              if t and not n.startswith(("vgg_16/fc6", "vgg_16/fc7"))}
+    for k in z.files:
+        if k.startswith("param_override/"):
+            params[k[len("param_override/"):]] = z[k]
+    return meta, z, params
+
+
+def test_head_inference_oracle_reproduces_the_reference_script():
+    from basi_b200.BAISRunnerTest import Inference
+    meta, z, params = _head_inference_case()
+    S = meta["config"]["input_size"]
+    im = Inference.load_data(os.path.join(HERE, "golden", "input_7.jpg"), S)
+    with torch.no_grad():
+        segs = O.linknet_top_forward(O.to_torch(params, torch.float64), torch.as_tensor(im[None]).to(torch.float64))
+    close(segs[0].numpy(), z["out/segment_0"], 1e-9)                   # => load_data decoded the same pixels, too
+    pred = np.argmax(segs[0].numpy(), -1).astype(np.uint8)
+    assert np.array_equal(pred, z["out/pred_segment"]) and 0.2 < pred.mean() < 0.8
+    assert np.array_equal(z["file/7.bmp"], pred[0] * 255)              # the .bmp the script saved
+
+
+@pytest.mark.gpu
+def test_cuda_head_inference_matches_the_reference_script(tmp_path):
+    """The product's BAISRunnerTest.Inference (f32 mode) with the reference run's parameters restored from a TF-named
+    checkpoint: the mask of the coarsest head and the saved 7.bmp against the reference script's."""
+    from PIL import Image
+    from basi_b200.BAISRunnerTest import Inference
+    meta, z, params = _head_inference_case()
+    log_dir = str(tmp_path / "model")
+    os.makedirs(log_dir)
+    np.savez(os.path.join(log_dir, "model.ckpt-0.npz"), **params)
+    inf = Inference(meta["config"]["input_size"], str(tmp_path / "summary"), log_dir, precision="f32")
+    assert inf.load_model() is not None
+    pred = inf.inference(os.path.join(HERE, "golden", "input_7.jpg"), 0, save_path=str(tmp_path / "out"))
+    logits = inf.engine.att_logits[0].t.float().cpu().numpy()
+    e = _rel(logits.reshape(z["out/segment_0"].shape), z["out/segment_0"])
+    assert e < F32_TOL, e
+    agree = float(np.mean(pred == z["out/pred_segment"][0]))
+    assert agree >= 0.995, agree                                       # 676 pixels: at most 3 float32 ties
+    bmp = np.asarray(Image.open(os.path.join(str(tmp_path / "out"), "7.bmp")))
+    assert float(np.mean(bmp == z["file/7.bmp"])) >= 0.995
+    print("HEAD Inference: CUDA f32 vs the reference script: logits %.2e, mask agreement %.4f" % (e, agree))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # CUDA f32 path <-> reference code (runs last in the -m gpu suite)
 # --------------------------------------------------------------------------------------------------------------
 F32_TOL = 1e-4          # BASELINE.json north_star: float32 within 1e-4 relative
