@@ -630,7 +630,7 @@ def test_cuda_head_inference_matches_the_reference_script(tmp_path):
     assert e < F32_TOL, e
     agree = float(np.mean(pred == z["out/pred_segment"][0]))
     assert agree >= 0.995, agree                                       # 676 pixels: at most 3 float32 ties
-    bmp = np.asarray(Image.open(os.path.join(str(tmp_path / "out"), "7.bmp")))
+    bmp = np.asarray(Image.open(os.path.join(str(tmp_path / "out"), "input_7.bmp")))    # (named after the image file)
     assert float(np.mean(bmp == z["file/7.bmp"])) >= 0.995
     print("HEAD Inference: CUDA f32 vs the reference script: logits %.2e, mask agreement %.4f" % (e, agree))
 
