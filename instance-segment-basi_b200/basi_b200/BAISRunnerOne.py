@@ -138,10 +138,21 @@ class Runner(object):
         nseg = raw_output.shape[-1]
         base = os.path.join(self.save_dir, result_filename)
         Image.fromarray(np.asarray(np.squeeze(data_raw), dtype=np.uint8)).save(base + "data.png")
-        Image.fromarray(np.squeeze(np.asarray(predict_output[0] * 255 // max(nseg, 1), dtype=np.uint8))).save(
-            base + "pred.png")
-        for c in range(nseg):
-            Image.fromarray(np.asarray(sigmoid_output[0, :, :, c] * 255, dtype=np.uint8)).save(
-                base + "pred_%d.png" % c)
+        if nseg == 1:
+            # the one-logit snapshots' dumps (back/2AddClass/BAISRunnerOne.py:53-62): sigmoid as grey levels, the raw
+            # logit thresholded at 0.5 (the training-time prediction rule) and the sigmoid thresholded at 0.5
+            Image.fromarray(np.asarray(np.squeeze(sigmoid_output[0] * 255), dtype=np.uint8)).save(base + "pred.png")
+            Image.fromarray(np.asarray(np.squeeze(np.greater(raw_output[0], 0.5) * 255), dtype=np.uint8)).save(
+                base + "pred_raw.png")
+            Image.fromarray(np.asarray(np.squeeze(np.greater(sigmoid_output[0], 0.5) * 255), dtype=np.uint8)).save(
+                base + "pred_sigmoid.png")
+        else:
+            Image.fromarray(np.squeeze(np.asarray(predict_output[0] * 255 // nseg, dtype=np.uint8))).save(
+                base + "pred.png")
+            for c in range(nseg):
+                Image.fromarray(np.asarray(sigmoid_output[0, :, :, c] * 255, dtype=np.uint8)).save(
+                    base + "pred_%d.png" % c)
         Image.fromarray(np.asarray(np.squeeze(gaussian_mask * 255), dtype=np.uint8)).save(base + "mask.bmp")
+        if len(loaded) > 3:
+            Image.fromarray(np.asarray(np.squeeze(loaded[4] * 255), dtype=np.uint8)).save(base + "ann.bmp")
         return result

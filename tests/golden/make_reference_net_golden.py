@@ -452,6 +452,60 @@ def run_variant_b():
              float(val(tr.learning_rate)), meta["attention_shapes"]))
 
 
+def run_runner_one_2addclass():
+    """The one-logit snapshots' inference script: back/2AddClass/BAISRunnerOne.py Runner(...).run(...) unmodified at its
+    own 400^2 on an image / instance annotation pair of tests/golden/voc_mini (the script samples the click from the
+    annotation), with every file it writes."""
+    import inspect
+    import tempfile
+    from PIL import Image
+    stub_missing_data_dependencies()
+    for m in list(sys.modules):
+        if m in REF_MODULES or m == "BAISRunnerOne":
+            del sys.modules[m]
+    d = os.path.join(REF, "back", "2AddClass")
+    sys.path.insert(0, d)
+    try:
+        mod = importlib.import_module("BAISRunnerOne")
+    finally:
+        sys.path.remove(d)
+    fed = {}
+
+    def feeds(i, dtype, shape):
+        for fr in inspect.stack():
+            if "final_batch_data" in fr.frame.f_locals:
+                fed["data"] = np.asarray(fr.frame.f_locals["final_batch_data"], dtype=np.float32)
+                return fed["data"]
+        raise RuntimeError("final_batch_data not found")
+
+    tf.shim_reset(param_value, feeds)
+    del tf.SESSION_RUNS[:]
+    voc = os.path.join(HERE, "voc_mini")
+    np.random.seed(21)
+    with tempfile.TemporaryDirectory() as tmp:
+        mod.Runner(log_dir=os.path.join(tmp, "model"), save_dir=os.path.join(tmp, "out")).run(
+            result_filename="b_", image_filename=os.path.join(voc, "JPEGImages", "b.jpg"),
+            annotation_filename=os.path.join(voc, "SegmentationObject", "b.png"), ann_index=1)
+        files = {f: np.asarray(Image.open(os.path.join(tmp, "out", f))) for f in sorted(os.listdir(os.path.join(tmp, "out")))}
+    raw_output, sigmoid_output, raw_classes, pred_classes = tf.SESSION_RUNS[-1]
+    st = tf.shim_state()
+    arrays = {"in/click_map": fed["data"][0, :, :, 3], "out/raw_output": raw_output,
+              "out/raw_output_classes": raw_classes, "out/pred_classes": pred_classes}
+    for f, a in files.items():
+        if f != "b_data.png":
+            arrays["file/" + f] = a
+    meta = {"snapshot": "2AddClass/BAISRunnerOne", "reference_files": ["back/2AddClass/BAISRunnerOne.py",
+            "back/2AddClass/BAISPSPNet.py", "back/2AddClass/BAISData.py"],
+            "config": dict(input_size=[400, 400], last_pool_size=50, filter_number=32, num_segment=1, num_classes=21,
+                           image="voc_mini/JPEGImages/b.jpg", annotation="voc_mini/SegmentationObject/b.png",
+                           ann_index=1, numpy_seed=21),
+            "files": sorted(files), "variables": [[v.full_name, [int(s_) for s_ in v.t.shape], bool(v.trainable)]
+                                                  for v in st.variables.values()]}
+    save("RunnerOne_2AddClass", arrays, meta)
+    print("RunnerOne 2AddClass: files %s; class %d; raw > 0.5 on %d pixels, sigmoid > 0.5 on %d"
+          % (sorted(files), int(pred_classes[0]), int((raw_output > 0.5).sum()), int((sigmoid_output > 0.5).sum())))
+
+
 def run_runner_one():
     """cfg1, the reference's own CPU-runnable case: back/4BorderClass/BAISRunnerOne.py Runner(...).run(...) unmodified on
     the reference's own fixture input/7.jpg with a click at [360, 480] -- Data.load_image (PIL decode + resize to
@@ -639,7 +693,8 @@ def run_head_inference():
 
 OTHERS = {"8AttentionU": run_attention_u, "HEAD": run_head, "90AttentionSingle2": run_variant_b,
           "RunnerOne": run_runner_one, "RunnerGUI": run_runner_gui,
-          "HEAD_Inference": run_head_inference}
+          "HEAD_Inference": run_head_inference,
+          "RunnerOne_2AddClass": run_runner_one_2addclass}
 
 if __name__ == "__main__":
     for snap in (sys.argv[1:] or list(SNAPSHOTS) + list(OTHERS)):

@@ -530,6 +530,69 @@ def test_cuda_runner_one_matches_the_reference_script(tmp_path):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# the one-logit snapshots' inference script: back/2AddClass/BAISRunnerOne.py at its own 400^2, click sampled from an
+# instance annotation of tests/golden/voc_mini
+# --------------------------------------------------------------------------------------------------------------
+def _runner_one_2addclass_case():
+    meta, z = load("RunnerOne_2AddClass")
+    cfg = meta["config"]
+    params = {n: param_value(n, s, kind_of(n)) for n, s, t in meta["variables"] if t}
+    image = os.path.join(HERE, "golden", cfg["image"])
+    ann = os.path.join(HERE, "golden", cfg["annotation"])
+    return meta, z, cfg, params, image, ann
+
+
+def test_runner_one_2addclass_oracle_reproduces_the_reference_script():
+    from basi_b200.BAISData import Data
+    meta, z, cfg, params, image, ann = _runner_one_2addclass_case()
+    np.random.seed(cfg["numpy_seed"])                      # the script draws the click with np.random.randint
+    loaded = Data.load_image(image, annotation_filename=ann, ann_index=cfg["ann_index"], image_size=cfg["input_size"])
+    data = np.asarray(loaded[0], dtype=np.float32)
+    assert np.array_equal(data[0, :, :, 3].view(np.uint32), z["in/click_map"].view(np.uint32))      # same click, same map
+    assert np.array_equal(np.asarray(np.squeeze(loaded[4] * 255), dtype=np.uint8), z["file/b_ann.bmp"])
+    with torch.no_grad():
+        out = O.pspnet_forward(O.to_torch(params, torch.float64), torch.as_tensor(data).to(torch.float64),
+                               "2AddClass", 1, cfg["last_pool_size"])
+    raw = out["conv6_n"].numpy()
+    close(raw, z["out/raw_output"], 1e-9)
+    close(out["class_attention_fc"].numpy(), z["out/raw_output_classes"], 1e-9)
+    # training-time rule (logit > 0.5) and the runner's rule (sigmoid > 0.5 <=> logit > 0) are different masks
+    pred, _ = O.predict_train(z["out/raw_output"])
+    assert np.array_equal((pred[0, :, :, 0] * 255).astype(np.uint8), z["file/b_pred_raw.png"])
+    assert np.array_equal(((z["out/raw_output"][0, :, :, 0] > 0) * 255).astype(np.uint8), z["file/b_pred_sigmoid.png"])
+    assert (z["file/b_pred_raw.png"] != z["file/b_pred_sigmoid.png"]).sum() > 100
+
+
+@pytest.mark.gpu
+def test_cuda_runner_one_2addclass_matches_the_reference_script(tmp_path):
+    """The product's Runner.run(variant='2AddClass', last_pool_size=50) in f32 mode against the files the reference
+    script wrote: pred.png (sigmoid grey levels), pred_raw.png (logit > 0.5), pred_sigmoid.png, mask.bmp, ann.bmp."""
+    from PIL import Image
+    from basi_b200.BAISRunnerOne import Runner
+    meta, z, cfg, params, image, ann = _runner_one_2addclass_case()
+    log_dir, save_dir = str(tmp_path / "model"), str(tmp_path / "out")
+    os.makedirs(log_dir)
+    np.savez(os.path.join(log_dir, "model.ckpt-0.npz"), **params)
+    np.random.seed(cfg["numpy_seed"])
+    res = Runner(log_dir=log_dir, save_dir=save_dir, last_pool_size=cfg["last_pool_size"], variant="2AddClass",
+                 num_segment=1, precision="f32").run(result_filename="b_", image_filename=image,
+                                                     annotation_filename=ann, ann_index=cfg["ann_index"])
+    e = _rel(res["raw_output"].reshape(z["out/raw_output"].shape), z["out/raw_output"])
+    assert e < F32_TOL, e
+    assert int(res["pred_classes"][0]) == int(z["out/pred_classes"][0])
+    worst = 1.0
+    for f in meta["files"]:
+        if f == "b_data.png":
+            continue
+        mine = np.asarray(Image.open(os.path.join(save_dir, f)))
+        same = float(np.mean(np.abs(mine.astype(int) - z["file/" + f].astype(int)) <= (1 if f == "b_pred.png" else 0)))
+        assert same >= 0.999, (f, same)
+        worst = min(worst, same)
+    print("RunnerOne 2AddClass: CUDA f32 vs the reference script: logits %.2e, files agree on >= %.5f of the pixels"
+          % (e, worst))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # cfg1 as the interactive tool runs it: back/4BorderClass/BAISRunnerGUI.py RunnerGUI.run, one click on input/7.jpg
 # --------------------------------------------------------------------------------------------------------------
 def _runner_gui_case():
