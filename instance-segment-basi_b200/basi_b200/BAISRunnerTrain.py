@@ -33,6 +33,13 @@ SNAPSHOT = {
     "8AttentionU": dict(num_segment=4, kind="cascade", pos_weight=3.0, class_weight=0.1, lr=5e-3, num_steps=500001),
 }
 
+# The current-HEAD training script (BAISRunnerTrain.py:28-50,97-115: BAISNet.LinkNet on 3-channel images, full-resolution
+# {0,1} labels, cal_loss = mean of five 2-channel weighted CEs with pos_weight 1) runs on a DIFFERENT schedule: power 0.8
+# over 100 001 steps.  Its network / loss / optimizer subset are `BAISNet.LinkNetTop` + `Engine(kind="linknet_b",
+# pos_weight=1.0)` + `Engine.set_trainable("segment_side")`; `Train` does not wrap that variant (no click input, no
+# class labels), drive the engine directly with poly_learning_rate(**HEAD_SCHEDULE-style arguments).
+HEAD_SCHEDULE = dict(base_lr=5e-3, num_steps=100001, power=0.8)
+
 
 def poly_learning_rate(base_lr, step, num_steps, power=0.9):
     """lr = base * (1 - step/num_steps)^0.9 in float32, step fed as float32 (BAISRunnerTrain.py:115-116)."""

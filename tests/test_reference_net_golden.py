@@ -384,6 +384,8 @@ def test_head_oracle_train_step_reproduces_the_reference_code():
     # HEAD's schedule differs from the snapshots': power 0.8, 100001 steps (BAISRunnerTrain.py:33,49-50)
     lr = float(O.poly_lr(cfg["learning_rate"], float(z["in/step"]), cfg["num_steps"], power=0.8))
     close(lr, z["out/learning_rate"], 1e-6)
+    from basi_b200.BAISRunnerTrain import HEAD_SCHEDULE, poly_learning_rate
+    close(poly_learning_rate(step=float(z["in/step"]), **HEAD_SCHEDULE), z["out/learning_rate"], 1e-6)
     r = O.linknet_top_train_step(params, image, label, lr, torch.float64, pos_weight=1.0)
     assert [list(a.shape) for a in r["segments"]] == meta["segment_shapes"]
     for i, a in enumerate(r["segments"]):
