@@ -181,18 +181,30 @@ class Train(object):
             lab = None
         else:
             lab = np.asarray(label_seg).reshape(pred_seg.shape)
-        if lab is None:
-            pass
-        elif self.num_segment == 1:
-            out["accuracy_0"] = float(np.mean(raw.reshape(-1) > 0.5))
-            out["accuracy_1"] = float(np.mean(lab.reshape(-1) > 0.5))
-        else:
-            out["accuracy_segment"] = float(np.mean(pred_seg == lab))
+        if lab is not None:
+            out.update(self.segment_accuracies(self.num_segment, raw, pred_seg, lab))
         if eng.cls_logits is not None:
             out["raw_output_classes"] = got["raw_output_classes"].reshape(self.batch_size, -1)
             out["pred_classes"] = got["pred_classes"]
-            out["accuracy_classes"] = float(np.mean(out["pred_classes"] == np.asarray(label_cls)))
+            out["accuracy_classes"] = self.class_accuracy(out["pred_classes"], label_cls)
         return out
+
+    @staticmethod
+    def segment_accuracies(num_segment, raw_output_segment, pred_segment, label_segment):
+        """The per-batch statistics build_net calls accuracies: one-logit snapshots report the FRACTION of positive
+        predictions / positive labels (back/2AddClass/BAISRunnerTrain.py:96-97: accuracy_0 = mean(logit > 0.5),
+        accuracy_1 = mean(label > 0.5)), the softmax snapshots tcm.accuracy(pred_segment, label)
+        (back/4BorderClass/BAISRunnerTrain.py:102)."""
+        if num_segment == 1:
+            return dict(accuracy_0=float(np.mean(np.asarray(raw_output_segment).reshape(-1) > 0.5)),
+                        accuracy_1=float(np.mean(np.asarray(label_segment).reshape(-1) > 0.5)))
+        lab = np.asarray(label_segment).reshape(np.asarray(pred_segment).shape)
+        return dict(accuracy_segment=float(np.mean(np.asarray(pred_segment) == lab)))
+
+    @staticmethod
+    def class_accuracy(pred_classes, label_classes):
+        """tcm.accuracy(pred_classes, label_classes_placeholder) (back/2AddClass/BAISRunnerTrain.py:98)."""
+        return float(np.mean(np.asarray(pred_classes) == np.asarray(label_classes)))
 
     def train(self, save_pred_freq, begin_step=0, max_steps=None):
         Tools.restore_if_y(self.engine, self.log_dir)

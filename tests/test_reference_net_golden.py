@@ -241,6 +241,22 @@ def test_product_builder_registers_the_reference_codes_graph(snapshot):
 
 
 @pytest.mark.parametrize("snapshot", SNAPSHOTS)
+def test_product_accuracy_fetches_are_the_reference_codes(snapshot):
+    """The accuracy_* values Train.run_step reports, computed by the product's host code from the reference run's own
+    logits / predictions / labels, equal what the reference's build_net computed."""
+    from basi_b200.BAISRunnerTrain import Train
+    meta, z = load(snapshot)
+    nseg = meta["config"].get("num_segment", 1)
+    got = Train.segment_accuracies(nseg, z["out/raw_output_segment"], z["out/pred_segment"], z["in/label_segment"])
+    for k, v in got.items():
+        assert abs(v - float(z["out/" + k])) < 1e-12, (k, v, float(z["out/" + k]))
+    assert set(got) == ({"accuracy_0", "accuracy_1"} if nseg == 1 else {"accuracy_segment"})
+    if meta["fc"]:
+        assert abs(Train.class_accuracy(z["out/pred_classes"], z["in/label_classes"])
+                   - float(z["out/accuracy_classes"])) < 1e-12
+
+
+@pytest.mark.parametrize("snapshot", SNAPSHOTS)
 def test_product_class_only_subset_is_the_reference_var_list(snapshot):
     """A17: `minimize(loss, var_list=[v for v in trainable_variables() if 'class_attention' in v.name])`."""
     meta, _ = load(snapshot)
