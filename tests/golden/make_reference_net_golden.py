@@ -129,7 +129,7 @@ def val(x):
 
 
 def save(name, arrays, meta):
-    out = os.path.join(HERE, "reference_net_%s" % name)
+    out = os.path.join(os.environ.get("BASI_GOLDEN_OUT", HERE), "reference_net_%s" % name)
     np.savez_compressed(out + ".npz", **arrays)
     with open(out + ".json", "w") as f:
         json.dump(meta, f, separators=(",", ":"))

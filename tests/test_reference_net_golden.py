@@ -52,6 +52,24 @@ def close(a, b, tol=1e-9):
     return err
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout exists in the build container only")
+@pytest.mark.parametrize("name", ["2AddClass", "8AttentionU"])
+def test_committed_fixture_is_what_the_reference_code_produces_today(name, tmp_path):
+    """Provenance: re-run the generator (which imports the reference's modules from /root/reference and executes them
+    over the TensorFlow stand-in) and compare with the committed fixture, array for array."""
+    import subprocess
+    env = dict(os.environ, BASI_GOLDEN_OUT=str(tmp_path))
+    subprocess.check_call([sys.executable, os.path.join(HERE, "golden", "make_reference_net_golden.py"), name],
+                          env=env, stdout=subprocess.DEVNULL)
+    meta, z = load(name)
+    with open(str(tmp_path / ("reference_net_%s.json" % name))) as f:
+        assert json.load(f) == meta
+    fresh = np.load(str(tmp_path / ("reference_net_%s.npz" % name)))
+    assert sorted(fresh.files) == sorted(z.files)
+    for k in z.files:
+        assert np.array_equal(fresh[k], z[k]), k
+
+
 def product_snapshot_table():
     from basi_b200.BAISRunnerTrain import SNAPSHOT
     return SNAPSHOT
