@@ -46,6 +46,9 @@ class Data(object):
         if is_test:
             self._data_list, self._annotation_list = self._data_list[0: 12], self._annotation_list[0: 12]
             self._class_list = self._class_list[0: 12]
+        cut = getattr(self, "_is_test_cut", None)          # (the full-resolution readers keep the first 200 entries)
+        if cut:
+            self._data_list = self._data_list[0: cut]
         self._annotations = self._read_annotation(self._annotation_list, self._class_list, self.image_size,
                                                   self.ratio)
         self._images_data = self._read_image(self._data_list, self.image_size)
@@ -148,6 +151,89 @@ class Data(object):
         gaussian_mask = Data._mask_gaussian(image_size, where)
         final_batch_data = [np.concatenate((data_data, np.expand_dims(gaussian_mask, 2)), 2)]
         return (final_batch_data, data_raw, gaussian_mask) + extra
+
+
+class DataAttention(Data):
+    """Reader of variant B (back/90AttentionSingle2/BAISData.py:17-125): instance masks at the FULL input resolution with
+    the 255 border ring counted as background, the click drawn from the mask at full resolution (no ratio), and
+    ``next_batch_train() -> (batch_data [S,S,3] f32, batch_mask [S,S,1] f32 click map, batch_attention [S,S,1] int32
+    {0,1}, batch_class)`` -- image and click map are separate feeds of ``LinkNet(input_data, input_mask, ...)``."""
+
+    def __init__(self, data_list="ImageSets/Segmentation/trainval.txt", data_path="JPEGImages/",
+                 data_root_path="./VOC2012/", annotation_path="SegmentationObject/", class_path="SegmentationClass/",
+                 batch_size=4, image_size=(720, 720), is_test=False, sigma=30, rank=0, world=1, seed=None):
+        self._is_test_cut = 200 if is_test else None       # (:32-35: the first 200 list entries)
+        Data.__init__(self, data_list, data_path, data_root_path, annotation_path, class_path, batch_size, image_size,
+                      1, False, sigma, rank, world, seed)
+
+    def _read_annotation(self, annotation_list, class_list, image_size, ratio):
+        from PIL import Image
+        if self._is_test_cut:
+            annotation_list, class_list = annotation_list[:self._is_test_cut], class_list[:self._is_test_cut]
+        out = []
+        size = (image_size[0], image_size[1])
+        for ann_index, ann_name in enumerate(annotation_list):
+            class_data = np.asarray(Image.open(class_list[ann_index]).resize(size, Image.NEAREST))
+            ann_data = np.asarray(Image.open(ann_name).resize(size, Image.NEAREST))
+            ann_data = np.where(ann_data == 255, 0, ann_data)                     # the border ring is background (:93-94)
+            for num in [i for i in range(1, 255) if np.any(ann_data == i)]:
+                ys, xs = np.where(ann_data == num)
+                cls = class_data[ys[0]][xs[0]]
+                cls = 0 if cls >= len(CategoryNames) else cls
+                out.append([ann_index, num, cls, np.where(ann_data == num, 255, ann_data) // 255])    # (:104)
+        return out
+
+    def next_batch_train(self):
+        batch_ann = self._pick(True)
+        batch_ann_attention = [np.asarray(ann[-1] == 1, dtype=np.int32) for ann in batch_ann]
+        for ann in batch_ann:
+            where = np.argwhere(ann[-1] == 1)
+            where = where[np.random.randint(0, len(where))]
+            ann[1] = [where[0], where[1]]
+        batch_data = [self._images_data[ann[0]] for ann in batch_ann]
+        batch_mask = [np.expand_dims(self._mask_gaussian(self.image_size, ann[1], self.sigma), axis=-1)
+                      for ann in batch_ann]
+        batch_attention = [np.expand_dims(a, 2) for a in batch_ann_attention]
+        batch_class = [ann[2] for ann in batch_ann]
+        self._now += 1
+        return batch_data, batch_mask, batch_attention, batch_class
+
+
+class DataTop(Data):
+    """Reader of the current-HEAD script (BAISData.py:17-128): ONE foreground map per image at the full input resolution
+    -- every labelled pixel including the 255 border ring is 1 (:86-90) -- no clicks, no classes;
+    ``next_batch_train() -> (batch_data [S,S,3] f32, batch_ann [S,S,1] {0,1})``."""
+
+    def __init__(self, data_list="ImageSets/Segmentation/trainval.txt", data_path="JPEGImages/",
+                 data_root_path="./VOC2012/", annotation_path="SegmentationObject/", class_path="SegmentationClass/",
+                 batch_size=4, image_size=(720, 720), is_test=False, rank=0, world=1, seed=None):
+        self._is_test_cut = 200 if is_test else None
+        Data.__init__(self, data_list, data_path, data_root_path, annotation_path, class_path, batch_size, image_size,
+                      1, False, 30, rank, world, seed)
+
+    def _read_annotation(self, annotation_list, class_list, image_size, ratio):
+        from PIL import Image
+        if self._is_test_cut:
+            annotation_list = annotation_list[:self._is_test_cut]
+        out = []
+        for ann_name in annotation_list:
+            ann_data = np.asarray(Image.open(ann_name).resize((image_size[0], image_size[1]), Image.NEAREST))
+            ann_data = np.where(ann_data == 255, 1, ann_data)
+            out.append(np.where(ann_data > 0, 1, 0))
+        return out
+
+    def _pick_images(self):
+        if self._now >= self.number_patch:
+            self._reshuffle()
+            self._now = 0
+        return self._random_index[self._now * self.batch_size: (self._now + 1) * self.batch_size]
+
+    def next_batch_train(self):
+        idx = self._pick_images()
+        batch_data = [self._images_data[i] for i in idx]
+        batch_ann = [np.expand_dims(self._annotations[i], axis=-1) for i in idx]
+        self._now += 1
+        return batch_data, batch_ann
 
 
 class SyntheticData(object):

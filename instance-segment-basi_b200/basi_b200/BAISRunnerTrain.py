@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-from .BAISData import Data, SyntheticData
+from .BAISData import Data, DataAttention, SyntheticData
 from .BAISPSPNet import PSPNet, Placeholder, VARIANTS
 from .BAISTools import Tools
 from .engine import Engine
@@ -76,6 +76,13 @@ class Train(object):
             self.data_reader = SyntheticData(batch_size, tuple(input_size), self.ratio, num_classes,
                                              self.num_segment, sigma=20 if variant == "5COCO" else 30,
                                              seed=seed + (dp.rank if dp else 0))
+        elif variant == "90AttentionSingle2":
+            # variant B reads full-resolution attention labels and feeds image and click map separately
+            # (back/90AttentionSingle2/BAISRunnerTrain.py:31-34,177-180)
+            self.data_reader = DataAttention(data_root_path=data_root_path, data_list=train_list, data_path=data_path,
+                                             annotation_path=annotation_path, class_path=class_path,
+                                             batch_size=batch_size, image_size=input_size, is_test=is_test,
+                                             rank=dp.rank if dp else 0, world=dp.world if dp else 1, seed=seed)
         else:
             self.data_reader = Data(data_root_path=data_root_path, data_list=train_list, data_path=data_path,
                                     annotation_path=annotation_path, class_path=class_path,
@@ -150,6 +157,11 @@ class Train(object):
             else:
                 eng.feed_clicks(images, clicks)
                 eng.feed(None, label_seg, label_cls, lr, label_att=self._attention_labels(label_seg))
+        elif self.variant == "90AttentionSingle2":
+            data, mask, ann, cls = batch if batch is not None else self.data_reader.next_batch_train()
+            label_cls, label_seg = cls, np.asarray(ann)
+            eng.feed(np.asarray(data, dtype=np.float32), label_seg, np.asarray(cls, dtype=np.int32), lr,
+                     mask=np.asarray(mask, dtype=np.float32))
         else:
             data, ann, cls, _, _ = batch if batch is not None else self.data_reader.next_batch_train()
             label_cls, label_seg = cls, np.asarray(ann)

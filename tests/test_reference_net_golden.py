@@ -502,6 +502,42 @@ def test_variant_b_oracle_train_step_reproduces_the_reference_code():
 
 
 # --------------------------------------------------------------------------------------------------------------
+# the readers of variant B and of the current-HEAD script: the batches the reference's own readers fed to the runs above
+# --------------------------------------------------------------------------------------------------------------
+VOC_MINI = os.path.join(HERE, "golden", "voc_mini") + "/"
+
+
+def test_variant_b_reader_reproduces_the_reference_readers_batch():
+    """back/90AttentionSingle2/BAISData.py on tests/golden/voc_mini at 720^2: image, full-resolution click map (bit for
+    bit), {0,1} attention labels with the border ring as background, class id -- the batch of the variant-B fixture."""
+    from basi_b200.BAISData import DataAttention
+    meta, z = load("90AttentionSingle2")
+    S = meta["config"]["input_size"]
+    reader = DataAttention(data_root_path=VOC_MINI, data_list="ImageSets/Segmentation/train.txt", batch_size=1,
+                           image_size=S)
+    np.random.seed(9)                                      # the seed the generator set before next_batch_train()
+    data, mask, att, cls = reader.next_batch_train()
+    assert np.array_equal(np.asarray(data, np.float32), z["in/image_u8"].astype(np.float32) / np.float32(255))
+    assert np.array_equal(np.asarray(mask, np.float32).view(np.uint32), z["in/mask"].view(np.uint32))
+    assert np.asarray(att).dtype == np.int32 and np.array_equal(np.asarray(att), z["in/label_segment"])
+    assert [int(c) for c in cls] == [int(c) for c in z["in/label_classes"]]
+    assert reader.number_patch == len(reader._annotations) and len(reader._annotations) == 8      # instances, not images
+
+
+def test_head_reader_reproduces_the_reference_readers_batch():
+    """BAISData.py (HEAD) on tests/golden/voc_mini at 224^2: one foreground map per image, the 255 border ring counted
+    as foreground -- the batch of the HEAD fixture."""
+    from basi_b200.BAISData import DataTop
+    meta, z = load("HEAD")
+    reader = DataTop(data_root_path=VOC_MINI, data_list="ImageSets/Segmentation/train.txt",
+                     batch_size=meta["config"]["batch_size"], image_size=meta["config"]["input_size"])
+    data, ann = reader.next_batch_train()
+    assert np.array_equal(np.asarray(data, np.float32), z["in/image_u8"].astype(np.float32) / np.float32(255))
+    assert np.array_equal(np.asarray(ann), z["in/label_segment"]) and set(np.unique(np.asarray(ann))) == {0, 1}
+    assert reader.number_patch == 1                        # 3 images, batch 2
+
+
+# --------------------------------------------------------------------------------------------------------------
 # cfg1, the reference's own CPU-runnable case: back/4BorderClass/BAISRunnerOne.py Runner.run on input/7.jpg
 # --------------------------------------------------------------------------------------------------------------
 def _runner_one_case():
