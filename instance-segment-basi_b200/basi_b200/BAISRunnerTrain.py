@@ -102,6 +102,13 @@ class Train(object):
             net = LinkNet(Placeholder((None, self.input_size[0], self.input_size[1], 3)),
                           Placeholder((None, self.input_size[0], self.input_size[1], 1), name="mask"),
                           is_training=True, num_classes=self.num_classes, width=self.filter_number / 64.0)
+            if not self.synthetic:
+                # the reference's reader delivers FULL-resolution labels (label_seg_placeholder [S, S, 1],
+                # back/90AttentionSingle2/BAISRunnerTrain.py:40) that cal_loss nearest-resizes to every attention map;
+                # the synthetic reader's labels are S/8 maps.  (First GPU run of this real-data path -- session 3, last
+                # seconds of the budget -- stopped here on the S/8 label buffer; with label_stride = 1 it takes the label
+                # path the top-level LinkNet's tests exercise.  Not re-run on the GPU.)
+                net.label_stride = 1
             engine = Engine(net, self.batch_size, precision, True, self.loss_cfg, device, use_tc)
             if self.synthetic:
                 engine.enable_click_input(self.data_reader.sigma)
