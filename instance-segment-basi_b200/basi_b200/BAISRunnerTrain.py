@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-from .BAISData import Data, DataAttention, SyntheticData
+from .BAISData import Data, DataAttention, DataTop, SyntheticData
 from .BAISPSPNet import PSPNet, Placeholder, VARIANTS
 from .BAISTools import Tools
 from .engine import Engine
@@ -36,8 +36,8 @@ SNAPSHOT = {
 # The current-HEAD training script (BAISRunnerTrain.py:28-50,97-115: BAISNet.LinkNet on 3-channel images, full-resolution
 # {0,1} labels, cal_loss = mean of five 2-channel weighted CEs with pos_weight 1) runs on a DIFFERENT schedule: power 0.8
 # over 100 001 steps.  Its network / loss / optimizer subset are `BAISNet.LinkNetTop` + `Engine(kind="linknet_b",
-# pos_weight=1.0)` + `Engine.set_trainable("segment_side")`; `Train` does not wrap that variant (no click input, no
-# class labels), drive the engine directly with poly_learning_rate(**HEAD_SCHEDULE-style arguments).
+# pos_weight=1.0)` + `Engine.set_trainable("segment_side")`; `TrainTop` below wraps them with that script's call surface
+# (`Train` itself is the PSPNet-lineage / variant-B / cascade runner: click input and class labels).
 HEAD_SCHEDULE = dict(base_lr=5e-3, num_steps=100001, power=0.8)
 
 
@@ -245,4 +245,83 @@ class Train(object):
             if step % self.print_step == 0:
                 Tools.print_info('step {:d} loss={:.3f} seg={:.3f} class={:.3f} lr={:.6f} ({:.3f} s/step)'.format(
                     step, r["loss"], r["loss_segment"], r["loss_classes"], r["learning_rate"], duration))
+        return r
+
+
+class TrainTop(object):
+    """The current-HEAD training script with its call surface (BAISRunnerTrain.py:10-183:
+    ``Train(batch_size, input_size, log_dir, data_root_path, train_list, data_path, annotation_path, class_path,
+    model_name, pretrain, is_test).train(save_pred_freq, begin_step)``): `DataTop` batches of 3-channel images and
+    full-resolution foreground maps -> ``BAISNet.LinkNetTop`` -> ``cal_loss`` (mean of the five 2-channel weighted CEs,
+    pos_weight 1) -> plain SGD on the HEAD schedule (power 0.8 over 100 001 steps); ``segment_side_only=True`` is the
+    script's ``train_segment_side_op`` (``minimize(loss, var_list=[... 'segment_side' ...])``).
+
+    Host glue only: every device call below (``Engine.feed`` of image + full-resolution labels, ``step_device`` /
+    graph replay, ``losses``) is the one the top-level LinkNet's GPU tests make.  The loop itself was added after the GPU
+    budget of round 2 was spent: plan construction, feeds and the schedule are tested on the CPU (dry run), the loop has
+    not been run on a GPU."""
+
+    def __init__(self, batch_size, input_size, log_dir, data_root_path=None, train_list=None, data_path=None,
+                 annotation_path=None, class_path=None, model_name="model.ckpt", pretrain=None, is_test=False,
+                 precision="f16", width=1.0, seed=0, device=None, use_cuda_graph=True, dry_run=False):
+        from .BAISNet import LinkNetTop
+        self.log_dir = Tools.new_dir(log_dir)
+        self.model_name = model_name
+        self.checkpoint_path = os.path.join(self.log_dir, self.model_name)
+        self.pretrain = pretrain
+        self.input_size = input_size
+        self.batch_size = batch_size
+        self.num_classes = 21
+        self.data_reader = DataTop(data_root_path=data_root_path, data_list=train_list, data_path=data_path,
+                                   annotation_path=annotation_path, class_path=class_path, batch_size=batch_size,
+                                   image_size=input_size, is_test=is_test, seed=seed)
+        self.learning_rate, self.num_steps = HEAD_SCHEDULE["base_lr"], HEAD_SCHEDULE["num_steps"]
+        self.cal_step = self.data_reader.number_patch
+        self.print_step = max(1, self.cal_step // 10)
+        self.use_cuda_graph = use_cuda_graph
+        self.net = LinkNetTop(Placeholder((None, input_size[0], input_size[1], 3)), True,
+                              num_classes=self.num_classes, width=width)
+        self.segments, self.features = self.net.build()
+        self.engine = Engine(self.net, batch_size, precision, True, dict(kind="linknet_b", pos_weight=1.0), device,
+                             dry_run=dry_run)
+        self.engine.init_params(seed)
+        self._subset = None
+
+    def feed(self, step, batch=None):
+        """Host -> static device buffers for one step; returns the learning rate of the step."""
+        lr = poly_learning_rate(step=step, **HEAD_SCHEDULE)
+        data, ann = batch if batch is not None else self.data_reader.next_batch_train()
+        self.engine.feed(np.asarray(data, dtype=np.float32), np.asarray(ann, dtype=np.float32), None, lr)
+        return lr
+
+    def run_step(self, step, batch=None, segment_side_only=False):
+        """One ``sess.run([train_op | train_segment_side_op, loss, loss_segment_all, learning_rate])``."""
+        eng = self.engine
+        subset = "segment_side" if segment_side_only else None
+        if subset != self._subset:
+            eng.set_trainable(subset)
+            self._subset = subset
+        lr = self.feed(step, batch)
+        if self.use_cuda_graph:
+            if eng._graph is None:
+                eng.capture(train=True)
+            eng.replay()
+        else:
+            eng.step_device()
+        _, loss_segment_all, _ = eng.losses()
+        return dict(loss=loss_segment_all, loss_segment_all=loss_segment_all, learning_rate=lr)
+
+    def train(self, save_pred_freq, begin_step=0, max_steps=None):
+        Tools.restore_if_y(self.engine, self.log_dir, pretrain=self.pretrain)
+        end = self.num_steps if max_steps is None else min(self.num_steps, begin_step + max_steps)
+        r = None
+        for step in range(begin_step, end):
+            start_time = time.time()
+            r = self.run_step(step)
+            if step % save_pred_freq == 0:
+                Tools.save(self.engine, self.checkpoint_path, step)
+                Tools.print_info('The checkpoint has been created.')
+            if step % self.print_step == 0:
+                Tools.print_info('step {:d} loss={:.3f} lr={:.6f} ({:.3f} s/step)'.format(
+                    step, r["loss"], r["learning_rate"], time.time() - start_time))
         return r

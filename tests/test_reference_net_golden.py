@@ -537,6 +537,29 @@ def test_head_reader_reproduces_the_reference_readers_batch():
     assert reader.number_patch == 1                        # 3 images, batch 2
 
 
+def test_head_training_wrapper_builds_and_feeds_like_the_reference_script(tmp_path):
+    """TrainTop (the call surface of the HEAD script's Train) in dry-run mode: the plan is the top-level LinkNet's, the
+    reader's batch fits the engine's input / full-resolution label buffers, the learning rate is the one the reference's
+    script computed, the segment_side subset is the script's var_list."""
+    from basi_b200.BAISRunnerTrain import TrainTop
+    meta, z = load("HEAD")
+    S, B = meta["config"]["input_size"], meta["config"]["batch_size"]
+    tr = TrainTop(batch_size=B, input_size=S, log_dir=str(tmp_path / "log"), data_root_path=VOC_MINI,
+                  train_list="ImageSets/Segmentation/train.txt", data_path="JPEGImages/",
+                  annotation_path="SegmentationObject/", class_path="SegmentationClass/", precision="f32", dry_run=True)
+    eng = tr.engine
+    assert tuple(eng.input.t.shape) == (B, S[0], S[1], 3) and tuple(eng.label_seg.shape) == (B, S[0], S[1], 1)
+    assert list(eng.param_index.keys()) == meta["train_op_vars"]
+    lr = tr.feed(float(z["in/step"]))
+    close(lr, z["out/learning_rate"], 1e-6)
+    assert np.array_equal(eng.input.t.numpy(), z["in/image_u8"].astype(np.float32) / np.float32(255))
+    assert np.array_equal(eng.label_seg.numpy(), z["in/label_segment"].astype(np.float32))
+    assert eng.set_trainable("segment_side") >= 1
+    assert [n for n in eng.param_index if "segment_side" in n] == meta["train_segment_side_op_vars"]
+    assert (tr.learning_rate, tr.num_steps, tr.cal_step) == (5e-3, 100001, 1)
+    assert [[B] + list(nd.shape) for nd in tr.segments] == meta["segment_shapes"]
+
+
 # --------------------------------------------------------------------------------------------------------------
 # cfg1, the reference's own CPU-runnable case: back/4BorderClass/BAISRunnerOne.py Runner.run on input/7.jpg
 # --------------------------------------------------------------------------------------------------------------
